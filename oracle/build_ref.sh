@@ -1,0 +1,65 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- build oracle/_ref/libalva_ref.so from the reference's own sources.
+# TEST INFRASTRUCTURE: the .so is git-ignored, travels to the GPU box, and is only ever loaded by
+# tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference arms.
+#
+# Nothing from /root/reference is copied into the repo: the vendored OpenCV 4.5.5 / Ceres 2.0 are
+# configured out-of-tree (SURVEY.md Appendix A recipe) into $ALVA_REF_PREFIX (default /tmp/probe; the
+# survey's build is reused when present) and AlvaAR's ceres_parametrization.cpp is compiled in place.
+# NOTE (DESIGN.md "Oracle"): OpenCV and Ceres cannot be compiled without their generated headers, so
+# this step runs their cmake configure offline; it is optional -- every parity test also runs
+# against the committed golden vectors with the plain-C restatement when the .so is absent.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF=${ALVA_REFERENCE:-/root/reference}
+P=${ALVA_REF_PREFIX:-/tmp/probe}
+OUT="$HERE/_ref"
+[ -d "$REF/src/slam/src" ] || { echo "reference tree not found at $REF" >&2; exit 3; }
+mkdir -p "$OUT" "$P"
+J=${JOBS:-$(nproc)}
+if [ ! -f "$P/ocv_install/lib/libopencv_core.a" ]; then
+  mkdir -p "$P/ocv" && cd "$P/ocv"
+  cmake -G Ninja "$REF/src/libs/opencv" -DCMAKE_BUILD_TYPE=Release -DCMAKE_POLICY_VERSION_MINIMUM=3.5 \
+    -DCMAKE_INSTALL_PREFIX="$P/ocv_install" -DBUILD_LIST=core,imgproc,features2d,flann,video,calib3d \
+    -DBUILD_SHARED_LIBS=OFF -DBUILD_TESTS=OFF -DBUILD_PERF_TESTS=OFF -DBUILD_EXAMPLES=OFF -DBUILD_opencv_apps=OFF \
+    -DBUILD_JAVA=OFF -DBUILD_opencv_python3=OFF -DWITH_IPP=OFF -DWITH_ITT=OFF -DWITH_OPENCL=OFF -DWITH_CUDA=OFF \
+    -DWITH_PROTOBUF=OFF -DWITH_QUIRC=OFF -DWITH_ADE=OFF -DWITH_JPEG=OFF -DWITH_PNG=OFF -DWITH_TIFF=OFF -DWITH_WEBP=OFF \
+    -DWITH_OPENJPEG=OFF -DWITH_JASPER=OFF -DWITH_OPENEXR=OFF -DWITH_FFMPEG=OFF -DWITH_GSTREAMER=OFF -DWITH_V4L=OFF \
+    -DWITH_GTK=OFF -DWITH_EIGEN=OFF -DWITH_LAPACK=OFF -DWITH_1394=OFF -DWITH_VTK=OFF -DBUILD_ZLIB=ON \
+    -DCMAKE_POSITION_INDEPENDENT_CODE=ON > cfg.log 2>&1
+  ninja -j"$J" install > build.log 2>&1
+fi
+if [ ! -f "$P/ceres_install/lib/libceres.a" ]; then
+  mkdir -p "$P/eigen_stub" "$P/ceres"
+  cat > "$P/eigen_stub/Eigen3Config.cmake" <<EOS
+if(NOT TARGET Eigen3::Eigen)
+  add_library(Eigen3::Eigen INTERFACE IMPORTED)
+  set_target_properties(Eigen3::Eigen PROPERTIES INTERFACE_INCLUDE_DIRECTORIES "$REF/src/libs/eigen")
+endif()
+set(EIGEN3_INCLUDE_DIR "$REF/src/libs/eigen")
+set(EIGEN3_INCLUDE_DIRS "$REF/src/libs/eigen")
+set(EIGEN3_VERSION_STRING "3.4.0")
+set(Eigen3_VERSION "3.4.0")
+set(EIGEN3_FOUND TRUE)
+EOS
+  printf 'set(PACKAGE_VERSION "3.4.0")\nset(PACKAGE_VERSION_COMPATIBLE TRUE)\n' > "$P/eigen_stub/Eigen3ConfigVersion.cmake"
+  cd "$P/ceres"
+  cmake -G Ninja "$REF/src/libs/ceres-solver" -DCMAKE_BUILD_TYPE=Release -DCMAKE_POLICY_VERSION_MINIMUM=3.5 \
+    -DCMAKE_INSTALL_PREFIX="$P/ceres_install" -DEigen3_DIR="$P/eigen_stub" -DBUILD_SHARED_LIBS=OFF -DBUILD_EXAMPLES=OFF \
+    -DBUILD_TESTING=OFF -DBUILD_BENCHMARKS=OFF -DEIGENSPARSE=ON -DSUITESPARSE=OFF -DCXSPARSE=OFF -DLAPACK=OFF \
+    -DMINIGLOG=ON -DGFLAGS=OFF -DCERES_THREADING_MODEL=NO_THREADS -DCMAKE_POSITION_INDEPENDENT_CODE=ON > cfg.log 2>&1
+  ninja -j"$J" install > build.log 2>&1
+fi
+INC="-I$REF/src/slam/src -I$P/ocv_install/include/opencv4 -I$REF/src/libs/eigen -I$REF/src/libs/Sophus \
+ -I$P/ceres_install/include -I$P/ceres_install/include/ceres/internal/miniglog"
+cd "$OUT"
+g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/ceres_parametrization.cpp" -o ceres_parametrization.o $INC
+g++ -std=c++17 -O2 -w -fPIC -c "$HERE/ref_harness.cpp" -o ref_harness.o $INC
+g++ -shared -o libalva_ref.so ref_harness.o ceres_parametrization.o \
+  -Wl,--start-group "$P"/ocv_install/lib/libopencv_video.a "$P"/ocv_install/lib/libopencv_calib3d.a \
+  "$P"/ocv_install/lib/libopencv_features2d.a "$P"/ocv_install/lib/libopencv_flann.a \
+  "$P"/ocv_install/lib/libopencv_imgproc.a "$P"/ocv_install/lib/libopencv_core.a \
+  "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a -Wl,--end-group \
+  -lpthread -ldl -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL
+rm -f ref_harness.o ceres_parametrization.o
+echo "built $OUT/libalva_ref.so"
