@@ -1,0 +1,706 @@
+// frontend.cu -- RGBA->gray, Gaussian pyramid and FAST-9 (+score, +3x3 NMS) for sm_100a.
+//
+// What is computed (bit-exact with the reference; the CPU restatement is oracle/alva_oracle.c):
+//   gray   : cv::cvtColor(RGBA2GRAY)           reference call site src/slam/src/system.cpp:111-112
+//   pyramid: cv::pyrDown per level             src/slam/src/visual_frontend.cpp:696 -> opencv
+//                                              video/src/lkpyramid.cpp:726-822, imgproc/src/pyramids.cpp:783-900
+//   FAST   : cv::FAST(thr, nms, TYPE_9_16)     opencv features2d/src/fast.cpp:57-292, fast_score.cpp:119-210
+//
+// How (B200-first, HBM-bound integer/byte work -- no tensor cores here):
+//   * one CTA per 120x62 pixel tile; the RGBA box (128x70 px, 35 KB) arrives by ONE TMA bulk-tensor
+//     copy (cp.async.bulk.tensor.3d, zero-filled out of bounds) signalled on an mbarrier;
+//   * gray is produced once into shared memory (4 px / thread, 128-bit LDS, 32-bit STS) and streamed
+//     to HBM with coalesced 32-bit stores; L1 of the pyramid is produced from the same shared tile with
+//     16x2-lane SWAR arithmetic, so the input is read from HBM exactly once;
+//   * FAST runs bit-sliced on 4 pixels per register (SWAR): per-byte threshold compares via the
+//     borrow trick, the 9-of-16 contiguity test as 3-input LOP3 networks -- branch-free, no divergence;
+//   * corners are compacted with warp ballots into per-warp shared-memory queues and scored 32 at a time
+//     with packed 16x2 min/max (VIMNMX.U16x2); NMS is again SWAR over the shared score tile;
+//   * keypoints leave as packed keys (y<<20 | x<<8 | score); a row-bucket pass restores cv::FAST's
+//     row-major order when the caller asks for it.
+#include "alva_common.cuh"
+#include "../../include/alva_b200.h"
+
+namespace {
+
+constexpr int TW = 120, TH = 62;          // tile interior
+constexpr int BW = TW + 8, BH = TH + 8;   // loaded box (halo 4)
+constexpr int GP = 144;                   // gray smem pitch (bytes); image x0 sits at byte 8
+constexpr int GPW = GP / 4;
+constexpr int SP = 128;                   // score smem pitch; image x0-4 sits at byte 0
+constexpr int SPW = SP / 4;
+constexpr int SR = TH + 2;                // score rows: image y0-1 .. y0+TH
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int QCAP = 160;                 // per-warp pending-corner queue
+constexpr int KPCAP = 1888;               // >= TW*TH/4 (NMS leaves at most one keypoint per 2x2)
+
+struct FrontendParams {
+    const uint8_t* src;   // rgba (RGBA mode) or gray (gray mode), tightly packed frames
+    uint8_t* l0;          // gray out (RGBA mode), may be null
+    uint8_t* l1;          // first pyramid level out, may be null
+    uint32_t* keys;       // may be null (no FAST)
+    int32_t* counts;
+    int w, h, nframes, tiles_x, tiles_y;
+    int thr, cap, use_tma;
+};
+
+struct __align__(128) SmemLayout {
+    uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode)
+    uint8_t gray[GP * BH];         // TMA destination (gray mode)
+    uint8_t score[SP * SR];
+    uint32_t kplist[KPCAP];
+    uint16_t queue[NWARPS][QCAP];
+    uint64_t bar;
+    int kpcount;
+    int kpbase;
+};
+
+// ---- gray conversion of 4 RGBA pixels (uint4 = 4 x RGBA8) ------------------------------------------
+__device__ __forceinline__ uint32_t gray1(uint32_t px) {
+    uint32_t r = px & 0xff, g = (px >> 8) & 0xff, b = (px >> 16) & 0xff;
+    return (r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
+}
+__device__ __forceinline__ uint32_t gray4(uint4 p) {
+    return gray1(p.x) | (gray1(p.y) << 8) | (gray1(p.z) << 16) | (gray1(p.w) << 24);
+}
+
+// ---- FAST-9 detection on 4 horizontally adjacent pixels --------------------------------------------
+// ring[k] holds ring pixel k of the four centres (byte j = centre j).  Returns per-byte bit-7 masks.
+__device__ __forceinline__ void fast_detect4(const uint32_t (&ring)[16], uint32_t c, uint32_t thr4, uint32_t& bright,
+                                             uint32_t& dark) {
+    const uint32_t hi = __vaddus4(c, thr4);   // min(c + t, 255)
+    const uint32_t lo = __vsubus4(c, thr4);   // max(c - t, 0)
+    const uint32_t Cb = (hi | ALVA_H) + ALVA_H;   // (hi|H) - (r & L) == Cb - (r|H)
+    const uint32_t Cd = lo & ALVA_L;
+    uint32_t B[16], D[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t r = ring[k], rH = r | ALVA_H;
+        const uint32_t tb = Cb - rH;   // bit7: (hi & 127) >= (r & 127)
+        const uint32_t td = rH - Cd;   // bit7: (r & 127) >= (lo & 127)
+        // bright: r > hi  <=> !(hi >= r)
+        B[k] = ~((hi & ~r) | (~(hi ^ r) & tb));
+        // dark: r < lo <=> !(r >= lo)
+        D[k] = ~((r & ~lo) | (~(r ^ lo) & td));
+    }
+    uint32_t Tb[16], Td[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        Tb[s] = B[s] & B[(s + 1) & 15] & B[(s + 2) & 15];
+        Td[s] = D[s] & D[(s + 1) & 15] & D[(s + 2) & 15];
+    }
+    uint32_t ab = 0, ad = 0;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        ab |= Tb[s] & Tb[(s + 3) & 15] & Tb[(s + 6) & 15];
+        ad |= Td[s] & Td[(s + 3) & 15] & Td[(s + 6) & 15];
+    }
+    bright = ab & ALVA_H;
+    dark = ad & ALVA_H;
+}
+
+// ---- corner score (cornerScore<16>) for one pixel, packed 16x2 min/max -----------------------------
+// p: centre pixel in the gray smem tile.  dark != 0: the arc is darker than the centre.
+// returns max over the 16 arcs of min over the arc of |centre - ring| in the corner's polarity (= score + 1).
+__device__ __forceinline__ int fast_strength(const uint8_t* p, int dark) {
+    constexpr int o[16] = {3 * GP,      3 * GP + 1,  2 * GP + 2,  GP + 3,      3,           -GP + 3,
+                           -2 * GP + 2, -3 * GP + 1, -3 * GP,     -3 * GP - 1, -2 * GP - 2, -GP - 3,
+                           -3,          GP - 3,      2 * GP - 2,  3 * GP - 1};
+    const uint32_t c = p[0];
+    const uint32_t cc = c | (c << 16);
+    const int sgn = dark ? -1 : 1;
+    // e[k] = (±(ring_k - c) + 256, ±(ring_{k+8} - c) + 256) as two unsigned 16-bit lanes
+    uint32_t e[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t pk = (uint32_t)p[o[k]] | ((uint32_t)p[o[k + 8]] << 16);
+        e[k] = (uint32_t)((int)(pk - cc) * sgn) + 0x01000100u;
+    }
+    // circular sliding minimum of width 9 over 16 elements; register k holds elements (k, k+8)
+    uint32_t sw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sw[k] = __byte_perm(e[k], 0, 0x1032);   // halves swapped: (k+8, k)
+    uint32_t m2[8], m4[8], m8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) m2[k] = __vminu2(e[k], k + 1 < 8 ? e[k + 1] : sw[0]);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        m4[k] = __vminu2(m2[k], k + 2 < 8 ? m2[k + 2] : __byte_perm(m2[k + 2 - 8], 0, 0x1032));
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        m8[k] = __vminu2(m4[k], k + 4 < 8 ? m4[k + 4] : __byte_perm(m4[k + 4 - 8], 0, 0x1032));
+    uint32_t best = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) best = __vmaxu2(best, __vminu2(m8[k], sw[k]));   // 9th element: k+8 / k
+    const int b = max((int)(best & 0xffff), (int)(best >> 16));
+    return b - 256;
+}
+
+template <bool RGBA>
+__global__ void __launch_bounds__(NTHREADS, 3)
+frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes are allocated)
+    SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int t = blockIdx.x;
+    const int tiles_per_frame = P.tiles_x * P.tiles_y;
+    const int f = t / tiles_per_frame;
+    t -= f * tiles_per_frame;
+    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int w = P.w, h = P.h;
+
+    // ------------------------------------------------------------------ A. load the tile
+    if (P.use_tma) {
+        if (tid == 0) {
+            mbar_init(&S.bar, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (RGBA) {
+                mbar_arrive_expect_tx(&S.bar, BW * BH * 4);
+                tma_load_3d(S.rgba, &tmap, &S.bar, x0 - 4, y0 - 4, f);
+            } else {
+                mbar_arrive_expect_tx(&S.bar, GP * BH);
+                tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8, y0 - 4, f);
+            }
+        }
+    } else {
+        if (RGBA) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src) + (size_t)f * w * h;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(S.rgba);
+            for (int i = tid; i < BW * BH; i += NTHREADS) {
+                const int by = i / BW, bx = i - by * BW;
+                const int x = x0 - 4 + bx, y = y0 - 4 + by;
+                dst[i] = (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0u;
+            }
+        } else {
+            const uint8_t* src = P.src + (size_t)f * w * h;
+            for (int i = tid; i < GP * BH; i += NTHREADS) {
+                const int by = i / GP, bx = i - by * GP;
+                const int x = x0 - 8 + bx, y = y0 - 4 + by;
+                S.gray[i] = (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0;
+            }
+        }
+    }
+    // zero the score tile and counters while the copy is in flight
+    {
+        uint32_t* sc = reinterpret_cast<uint32_t*>(S.score);
+        for (int i = tid; i < SP * SR / 4; i += NTHREADS) sc[i] = 0;
+        if (tid == 0) S.kpcount = 0;
+    }
+    if (P.use_tma) mbar_wait(&S.bar, 0);
+    else __syncthreads();
+
+    // ------------------------------------------------------------------ B. gray
+    if (RGBA) {
+        const uint4* src4 = reinterpret_cast<const uint4*>(S.rgba);
+        uint32_t* gw = reinterpret_cast<uint32_t*>(S.gray);
+        uint8_t* l0 = P.l0 ? P.l0 + (size_t)f * w * h : nullptr;
+        const bool w4 = (w & 3) == 0;
+        for (int i = tid; i < (BW / 4) * BH; i += NTHREADS) {
+            const int by = i >> 5, g = i & 31;   // BW/4 == 32 groups per row
+            const uint32_t v = gray4(src4[i]);
+            gw[by * GPW + 1 + g] = v;            // image x0-4+4g at gray byte 4+4g
+            if (l0 && g >= 1 && g <= 30 && by >= 4 && by < 4 + TH) {
+                const int x = x0 + 4 * (g - 1), y = y0 + by - 4;
+                if (y < h && x < w) {
+                    uint8_t* d = l0 + (size_t)y * w + x;
+                    if (w4) *reinterpret_cast<uint32_t*>(d) = v;   // x % 4 == 0 and w % 4 == 0 -> aligned, in range
+                    else
+                        for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(v >> (8 * j));
+                }
+            }
+        }
+        // columns x0-8..x0-5 and x0+TW+4..x0+TW+7 are never written: only garbage lanes read them
+    }
+    __syncthreads();
+
+    // reflect-101 fix-up of the 2-px halo outside the image (pyrDown borders).  FAST never reads it:
+    // its candidates lie >= 3 px inside the image.
+    const bool edge_l = (x0 == 0), edge_r = (x0 + TW >= w), edge_t = (y0 == 0), edge_b = (y0 + TH >= h);
+    if (P.l1 && (edge_l || edge_r || edge_t || edge_b)) {
+        if (edge_l || edge_r) {
+            for (int r = tid; r < BH; r += NTHREADS) {
+                uint8_t* row = S.gray + r * GP;
+                if (edge_l) { row[7] = row[9]; row[6] = row[10]; }
+                if (edge_r) {
+                    const int cw = w - x0 + 8;   // gray byte of image column w
+                    row[cw] = row[cw - 2];
+                    row[cw + 1] = row[cw - 3];
+                }
+            }
+            __syncthreads();
+        }
+        if (edge_t || edge_b) {
+            for (int c = tid; c < GP; c += NTHREADS) {
+                if (edge_t) { S.gray[3 * GP + c] = S.gray[5 * GP + c]; S.gray[2 * GP + c] = S.gray[6 * GP + c]; }
+                if (edge_b) {
+                    const int rh = h - y0 + 4;   // gray row of image row h
+                    S.gray[rh * GP + c] = S.gray[(rh - 2) * GP + c];
+                    S.gray[(rh + 1) * GP + c] = S.gray[(rh - 3) * GP + c];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    const uint32_t* G = reinterpret_cast<const uint32_t*>(S.gray);
+
+    // ------------------------------------------------------------------ C. pyramid level 1 (16x2 SWAR)
+    if (P.l1) {
+        const int w1 = (w + 1) >> 1, h1 = (h + 1) >> 1;
+        uint8_t* l1 = P.l1 + (size_t)f * w1 * h1;
+        const int pc = tid % 30, sg = tid / 30;   // 30 pair-columns x 8 row segments (threads 240..255 idle)
+        if (sg < 8) {
+            const int lx = (x0 >> 1) + 2 * pc;
+            const int ly0 = (y0 >> 1) + 4 * sg;
+            if (lx < w1 && ly0 < h1) {
+                const uint32_t* base = G + (8 * sg + 2) * GPW + 1 + pc;   // gray row 2j+2 for j = 4*sg
+                uint32_t hrow[11];
+#pragma unroll
+                for (int r = 0; r < 11; r++) {
+                    const uint32_t L = base[r * GPW], M = base[r * GPW + 1], R = base[r * GPW + 2];
+                    const uint32_t c0 = M & 0x00ff00ffu;
+                    const uint32_t r1 = (M >> 8) & 0x00ff00ffu;
+                    const uint32_t l1v = __byte_perm(L, M, 0x6543) & 0x00ff00ffu;
+                    const uint32_t l2v = __byte_perm(L, M, 0x5432) & 0x00ff00ffu;
+                    const uint32_t r2 = __byte_perm(M, R, 0x5432) & 0x00ff00ffu;
+                    hrow[r] = c0 * 6u + (l1v + r1) * 4u + l2v + r2;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int ly = ly0 + j;
+                    if (ly < h1 && 4 * sg + j < TH / 2) {
+                        const uint32_t v = hrow[2 * j] + hrow[2 * j + 4] + (hrow[2 * j + 1] + hrow[2 * j + 3]) * 4u +
+                                           hrow[2 * j + 2] * 6u;
+                        const uint32_t o = ((v + 0x00800080u) >> 8) & 0x00ff00ffu;
+                        uint8_t* d = l1 + (size_t)ly * w1 + lx;
+                        d[0] = (uint8_t)o;
+                        if (lx + 1 < w1) d[1] = (uint8_t)(o >> 16);
+                    }
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ D. FAST detect + score
+    if (P.keys) {
+        const uint32_t thr4 = (uint32_t)P.thr * 0x01010101u;
+        // lane = group column gc (image x = x0-4+4*gc .. +3); per-byte validity of this lane's pixels
+        uint32_t vmask = 0;
+        {
+            const int xlo = max(3, x0 - 1), xhi = min(w - 4, x0 + TW);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 - 4 + 4 * lane + j;
+                if (x >= xlo && x <= xhi) vmask |= 0x80u << (8 * j);
+            }
+        }
+        const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
+        uint16_t* Q = S.queue[warp];
+        int qn = 0;
+        const uint32_t lt = (1u << lane) - 1;
+        for (int rr = warp; rr < SR; rr += NWARPS) {
+            const int y = y0 - 1 + rr;
+            if (y >= ylo && y <= yhi) {   // warp-uniform
+                const int r = rr + 3;     // gray smem row of the centre
+                const uint32_t* g0 = G + r * GPW + 1 + lane;
+                uint32_t ring[16];
+                uint32_t c;
+                {
+                    const uint32_t Lp3 = g0[3 * GPW - 1], Mp3 = g0[3 * GPW], Rp3 = g0[3 * GPW + 1];
+                    ring[0] = Mp3;
+                    ring[1] = __byte_perm(Mp3, Rp3, 0x4321);
+                    ring[15] = __byte_perm(Lp3, Mp3, 0x6543);
+                    const uint32_t Lp2 = g0[2 * GPW - 1], Mp2 = g0[2 * GPW], Rp2 = g0[2 * GPW + 1];
+                    ring[2] = __byte_perm(Mp2, Rp2, 0x5432);
+                    ring[14] = __byte_perm(Lp2, Mp2, 0x5432);
+                    const uint32_t Lp1 = g0[GPW - 1], Mp1 = g0[GPW], Rp1 = g0[GPW + 1];
+                    ring[3] = __byte_perm(Mp1, Rp1, 0x6543);
+                    ring[13] = __byte_perm(Lp1, Mp1, 0x4321);
+                    const uint32_t L0 = g0[-1], M0 = g0[0], R0 = g0[1];
+                    c = M0;
+                    ring[4] = __byte_perm(M0, R0, 0x6543);
+                    ring[12] = __byte_perm(L0, M0, 0x4321);
+                    const uint32_t Lm1 = g0[-GPW - 1], Mm1 = g0[-GPW], Rm1 = g0[-GPW + 1];
+                    ring[5] = __byte_perm(Mm1, Rm1, 0x6543);
+                    ring[11] = __byte_perm(Lm1, Mm1, 0x4321);
+                    const uint32_t Lm2 = g0[-2 * GPW - 1], Mm2 = g0[-2 * GPW], Rm2 = g0[-2 * GPW + 1];
+                    ring[6] = __byte_perm(Mm2, Rm2, 0x5432);
+                    ring[10] = __byte_perm(Lm2, Mm2, 0x5432);
+                    const uint32_t Lm3 = g0[-3 * GPW - 1], Mm3 = g0[-3 * GPW], Rm3 = g0[-3 * GPW + 1];
+                    ring[7] = __byte_perm(Mm3, Rm3, 0x4321);
+                    ring[8] = Mm3;
+                    ring[9] = __byte_perm(Lm3, Mm3, 0x6543);
+                }
+                uint32_t bright, dark;
+                fast_detect4(ring, c, thr4, bright, dark);
+                bright &= vmask;
+                dark &= vmask;
+                const uint32_t any = bright | dark;
+                // warp-ballot compaction of corner pixels into the warp queue
+                const int pix0 = r * GP + 4 + 4 * lane;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool has = (any >> (8 * j + 7)) & 1;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, has);
+                    if (has) {
+                        const int pos = qn + __popc(bal & lt);
+                        Q[pos] = (uint16_t)((pix0 + j) | (((dark >> (8 * j + 7)) & 1) << 15));
+                    }
+                    qn += __popc(bal);
+                }
+                __syncwarp();
+            }
+            // drain full batches (and everything after the last row)
+            const bool last = rr + NWARPS >= SR;
+            while (qn >= 32 || (last && qn > 0)) {
+                const int take = min(qn, 32);
+                if (lane < take) {
+                    const uint32_t e = Q[qn - take + lane];
+                    const int pix = e & 0x7fff;
+                    const int s = fast_strength(S.gray + pix, e >> 15);
+                    const int pr = pix / GP, pcg = pix - pr * GP;
+                    S.score[(pr - 3) * SP + (pcg - 4)] = (uint8_t)(s - 1);
+                }
+                qn -= take;
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ E. 3x3 NMS (strict >) + emit
+    if (P.keys) {
+        const uint32_t* Sw = reinterpret_cast<const uint32_t*>(S.score);
+        for (int item = tid; item < 30 * TH; item += NTHREADS) {
+            const int rr = 1 + item / 30, gc = 1 + item % 30;
+            const uint32_t* s0 = Sw + rr * SPW + gc;
+            const uint32_t Sv = s0[0];
+            if (Sv == 0) continue;
+            uint32_t ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const uint32_t L = s0[dy * SPW - 1], M = s0[dy * SPW], R = s0[dy * SPW + 1];
+                const uint32_t nl = __byte_perm(L, M, 0x6543), nr = __byte_perm(M, R, 0x4321);
+                ok &= ~swar_ge_raw(nl, Sv);   // Sv > nl  <=> !(nl >= Sv)
+                ok &= ~swar_ge_raw(nr, Sv);
+                if (dy != 0) ok &= ~swar_ge_raw(M, Sv);
+            }
+            ok &= ALVA_H;
+            const int y = y0 + rr - 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((ok >> (8 * j + 7)) & 1) {
+                    const int x = x0 + 4 * (gc - 1) + j;
+                    const uint32_t sc = (Sv >> (8 * j)) & 0xff;
+                    const int pos = atomicAdd(&S.kpcount, 1);
+                    if (pos < KPCAP) S.kplist[pos] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
+                }
+        }
+        __syncthreads();
+        const int n = min(S.kpcount, KPCAP);
+        if (tid == 0) S.kpbase = n ? atomicAdd(P.counts + f, n) : 0;
+        __syncthreads();
+        const int base = S.kpbase;
+        uint32_t* out = P.keys + (size_t)f * P.cap;
+        for (int i = tid; i < n; i += NTHREADS)
+            if (base + i < P.cap) out[base + i] = S.kplist[i];
+    }
+}
+
+// ---- standalone RGBA -> gray (alva_k_gray) ---------------------------------------------------------
+__global__ void gray_kernel(const uint8_t* __restrict__ rgba, uint8_t* __restrict__ gray, size_t npix) {
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < npix) {
+        const uint4 p = __ldg(reinterpret_cast<const uint4*>(rgba) + i4 / 4);
+        *reinterpret_cast<uint32_t*>(gray + i4) = gray4(p);
+    } else {
+        for (size_t i = i4; i < npix; i++) gray[i] = (uint8_t)gray1(reinterpret_cast<const uint32_t*>(rgba)[i]);
+    }
+}
+
+// ---- generic pyrDown (any size; used for levels >= 2 and alva_k_pyrdown) ----------------------------
+__global__ void pyrdown_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h, int nframes) {
+    const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)f * w * h;
+    int xs[5], acc = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) xs[i] = reflect101(2 * x + i - 2, w);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t* row = s + (size_t)reflect101(2 * y + j - 2, h) * w;
+        const int hsum = __ldg(row + xs[0]) + __ldg(row + xs[4]) + 4 * (__ldg(row + xs[1]) + __ldg(row + xs[3])) +
+                         6 * __ldg(row + xs[2]);
+        const int kj = (j == 0 || j == 4) ? 1 : (j == 2 ? 6 : 4);
+        acc += kj * hsum;
+    }
+    dst[(size_t)f * dw * dh + (size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+// ---- restore cv::FAST's row-major order: bucket by row, then sort each row's few keys by x ---------
+__global__ void __launch_bounds__(1024) order_keys_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                          const int32_t* __restrict__ counts, int cap, int h) {
+    extern __shared__ int osm[];   // rowstart[h+1], rowfill[h]
+    int* rowstart = osm;
+    int* rowfill = osm + h + 1;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int n = min(counts[f], cap);
+    const uint32_t* kin = in + (size_t)f * cap;
+    uint32_t* kout = out + (size_t)f * cap;
+    for (int i = tid; i <= h; i += nt) rowstart[i] = 0;
+    for (int i = tid; i < h; i += nt) rowfill[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicAdd(&rowstart[(kin[i] >> 20) + 1], 1);
+    __syncthreads();
+    // inclusive scan of rowstart[1..h] (h <= 4096): chunked serial + cross-chunk
+    {
+        __shared__ int part[1024];
+        const int chunk = (h + nt) / nt;
+        const int b = tid * chunk + 1, e = min(b + chunk, h + 1);
+        int s = 0;
+        for (int i = b; i < e; i++) s += rowstart[i];
+        part[tid] = s;
+        __syncthreads();
+        for (int off = 1; off < nt; off <<= 1) {
+            int v = tid >= off ? part[tid - off] : 0;
+            __syncthreads();
+            part[tid] += v;
+            __syncthreads();
+        }
+        int run = tid ? part[tid - 1] : 0;
+        for (int i = b; i < e; i++) { run += rowstart[i]; rowstart[i] = run; }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t k = kin[i];
+        const int y = k >> 20;
+        kout[rowstart[y] + atomicAdd(&rowfill[y], 1)] = k;
+    }
+    __syncthreads();
+    for (int y = tid; y < h; y += nt) {   // insertion sort within the row (keys of one row differ in x)
+        const int b = rowstart[y], e = rowstart[y + 1];
+        for (int i = b + 1; i < e; i++) {
+            const uint32_t k = kout[i];
+            int j = i - 1;
+            while (j >= b && kout[j] > k) { kout[j + 1] = kout[j]; j--; }
+            kout[j + 1] = k;
+        }
+    }
+}
+
+// ---- KeyPointsFilter::retainBest on packed keys (one CTA per frame) --------------------------------
+__global__ void __launch_bounds__(1024) retain_best_kernel(const uint32_t* __restrict__ in, const int32_t* __restrict__ counts,
+                                                           int cap, int w, int h, int n_keep, int edge,
+                                                           uint32_t* __restrict__ out, int32_t* __restrict__ out_counts,
+                                                           int out_cap) {
+    __shared__ int hist[256];
+    __shared__ int thr_s, cnt_s;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int n = min(counts[f], cap);
+    const uint32_t* kin = in + (size_t)f * cap;
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;
+    if (tid == 0) cnt_s = 0;
+    __syncthreads();
+    auto inside = [&](uint32_t k) {
+        if (edge <= 0) return true;
+        const int x = ALVA_KEY_X(k), y = ALVA_KEY_Y(k);
+        return x >= edge && x < w - edge && y >= edge && y < h - edge;
+    };
+    int local = 0;
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t k = kin[i];
+        if (inside(k)) { atomicAdd(&hist[k & 255], 1); local++; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int s = 0; s < 256; s++) total += hist[s];
+        int thr = 0;
+        if (n_keep >= 0 && total > n_keep) {
+            if (n_keep == 0) thr = 256;
+            else {
+                int acc = 0;
+                for (int s = 255; s >= 0; s--) { acc += hist[s]; if (acc >= n_keep) { thr = s; break; } }
+            }
+        }
+        thr_s = thr;
+    }
+    __syncthreads();
+    const int thr = thr_s;
+    uint32_t* kout = out + (size_t)f * out_cap;
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t k = kin[i];
+        if (inside(k) && (int)(k & 255) >= thr) {
+            const int pos = atomicAdd(&cnt_s, 1);
+            if (pos < out_cap) kout[pos] = k;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) out_counts[f] = cnt_s;
+}
+
+}  // namespace
+
+// =================================================================================== host launchers
+static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
+                           uint8_t* l1, int thr, uint32_t* keys, int32_t* counts, int cap) {
+    FrontendParams P{};
+    P.src = src; P.l0 = l0; P.l1 = l1; P.keys = keys; P.counts = counts;
+    P.w = w; P.h = h; P.nframes = nframes;
+    P.tiles_x = (w + TW - 1) / TW; P.tiles_y = (h + TH - 1) / TH;
+    P.thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr); P.cap = cap;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    bool tma_ok;
+    if (rgba_mode) {
+        uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)nframes};
+        uint64_t strides[2] = {(uint64_t)w * 4, (uint64_t)w * h * 4};
+        uint32_t box[3] = {BW, BH, 1};
+        tma_ok = (w % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
+                 alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src, dims, strides, box);
+    } else {
+        uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)nframes};
+        uint64_t strides[2] = {(uint64_t)w, (uint64_t)w * h};
+        uint32_t box[3] = {GP, BH, 1};
+        tma_ok = (w % 16 == 0) && (((size_t)w * h) % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                 alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, src, dims, strides, box);
+    }
+    P.use_tma = tma_ok ? 1 : 0;
+    const int grid = P.tiles_x * P.tiles_y * nframes;
+    const size_t smem = sizeof(SmemLayout) + 128;
+    if (rgba_mode) {
+        ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_tile_kernel<true><<<grid, NTHREADS, smem, ctx->stream>>>(tmap, P);
+    } else {
+        ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_tile_kernel<false><<<grid, NTHREADS, smem, ctx->stream>>>(tmap, P);
+    }
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int launch_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) {
+    const int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, nframes);
+    pyrdown_kernel<<<grid, block, 0, ctx->stream>>>(src, dst, w, h, nframes);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int launch_order(alva_ctx* ctx, const uint32_t* in, uint32_t* out, const int32_t* counts, int cap, int h,
+                        int nframes) {
+    const size_t smem = (size_t)(2 * h + 1) * sizeof(int);
+    order_keys_kernel<<<nframes, 1024, smem, ctx->stream>>>(in, out, counts, cap, h);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int check_dims(int w, int h, int nframes) {
+    if (w < 16 || h < 16 || w > ALVA_MAX_DIM || h > ALVA_MAX_DIM || nframes < 1) {
+        alva_set_error("invalid frame geometry %dx%d x%d (need 16..%d)", w, h, nframes, ALVA_MAX_DIM);
+        return ALVA_E_INVALID;
+    }
+    return 0;
+}
+
+extern "C" int alva_k_gray(alva_ctx* ctx, const uint8_t* rgba, uint8_t* gray, int w, int h, int nframes) {
+    if (!ctx || !rgba || !gray || w < 1 || h < 1 || nframes < 1) { alva_set_error("alva_k_gray: bad argument"); return ALVA_E_INVALID; }
+    const size_t npix = (size_t)w * h * nframes;
+    const size_t nthr = (npix + 3) / 4;
+    gray_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(rgba, gray, npix);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int alva_k_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) {
+    if (!ctx || !src || !dst || w < 1 || h < 1 || nframes < 1) { alva_set_error("alva_k_pyrdown: bad argument"); return ALVA_E_INVALID; }
+    return launch_pyrdown(ctx, src, dst, w, h, nframes);
+}
+
+static int fast_common(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
+                       uint8_t* l1, uint8_t* l2, uint8_t* l3, int thr, uint32_t* keys, int32_t* counts, int cap,
+                       int sorted) {
+    if (int e = check_dims(w, h, nframes)) return e;
+    if (keys && (!counts || cap < 1)) { alva_set_error("keys given without counts/cap"); return ALVA_E_INVALID; }
+    uint32_t* raw = keys;
+    if (keys && sorted) {
+        raw = (uint32_t*)alva_scratch(ctx, (size_t)nframes * cap * sizeof(uint32_t));
+        if (!raw) return ALVA_E_CUDA;
+    }
+    if (keys) ALVA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * nframes, ctx->stream));
+    if (int e = launch_frontend(ctx, rgba_mode, src, w, h, nframes, l0, l1, thr, raw, counts, cap)) return e;
+    if (l1 && l2) {
+        const int w1 = (w + 1) / 2, h1 = (h + 1) / 2;
+        if (int e = launch_pyrdown(ctx, l1, l2, w1, h1, nframes)) return e;
+        if (l3) {
+            const int w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
+            if (int e = launch_pyrdown(ctx, l2, l3, w2, h2, nframes)) return e;
+        }
+    }
+    if (keys && sorted)
+        if (int e = launch_order(ctx, raw, keys, counts, cap, h, nframes)) return e;
+    return 0;
+}
+
+extern "C" int alva_k_fast9(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, int thr, uint32_t* keys,
+                            int32_t* counts, int cap, int sorted) {
+    if (!ctx || !gray || !keys) { alva_set_error("alva_k_fast9: bad argument"); return ALVA_E_INVALID; }
+    return fast_common(ctx, false, gray, w, h, nframes, nullptr, nullptr, nullptr, nullptr, thr, keys, counts, cap, sorted);
+}
+
+extern "C" int alva_k_frontend(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1,
+                               uint8_t* l2, uint8_t* l3, int thr, uint32_t* keys, int32_t* counts, int cap, int sorted) {
+    if (!ctx || !rgba) { alva_set_error("alva_k_frontend: bad argument"); return ALVA_E_INVALID; }
+    return fast_common(ctx, true, rgba, w, h, nframes, l0, l1, l2, l3, thr, keys, counts, cap, sorted);
+}
+
+extern "C" int alva_k_retain_best(alva_ctx* ctx, const uint32_t* keys, const int32_t* counts, int cap, int nframes, int w,
+                                  int h, int n, int edge, uint32_t* out_keys, int32_t* out_counts, int out_cap) {
+    if (!ctx || !keys || !counts || !out_keys || !out_counts || nframes < 1 || cap < 1 || out_cap < 1) {
+        alva_set_error("alva_k_retain_best: bad argument");
+        return ALVA_E_INVALID;
+    }
+    uint32_t* tmp = (uint32_t*)alva_scratch(ctx, (size_t)nframes * out_cap * sizeof(uint32_t));
+    if (!tmp) return ALVA_E_CUDA;
+    retain_best_kernel<<<nframes, 1024, 0, ctx->stream>>>(keys, counts, cap, w, h, n, edge, tmp, out_counts, out_cap);
+    ALVA_LAUNCH_CHECK(ctx);
+    return launch_order(ctx, tmp, out_keys, out_counts, out_cap, h, nframes);
+}
+
+// Host-buffer front end: pinned/pageable host RGBA in, packed keys + counts out.  The copies are part of the call
+// (bench.py's e2e leg; also what a host without device pointers binds).
+extern "C" int alva_h_frontend(alva_ctx* ctx, const uint8_t* rgba_host, int w, int h, int nframes, int thr,
+                               uint32_t* keys_host, int32_t* counts_host, int cap) {
+    if (!ctx || !rgba_host || !keys_host || !counts_host) { alva_set_error("alva_h_frontend: bad argument"); return ALVA_E_INVALID; }
+    if (int e = check_dims(w, h, nframes)) return e;
+    const size_t in_bytes = (size_t)w * h * 4 * nframes;
+    const size_t key_bytes = (size_t)cap * nframes * sizeof(uint32_t);
+    const size_t cnt_bytes = ((size_t)nframes * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t need = in_bytes + key_bytes + cnt_bytes + 512;
+    if (need > ctx->dev_stage_bytes) {
+        if (ctx->dev_stage) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->dev_stage)); ctx->dev_stage = nullptr; }
+        ALVA_CUDA(cudaMalloc(&ctx->dev_stage, need));
+        ctx->dev_stage_bytes = need;
+    }
+    uint8_t* d_in = (uint8_t*)ctx->dev_stage;
+    uint32_t* d_keys = (uint32_t*)(d_in + ((in_bytes + 255) & ~(size_t)255));
+    int32_t* d_cnt = (int32_t*)((uint8_t*)d_keys + ((key_bytes + 255) & ~(size_t)255));
+    ALVA_CUDA(cudaMemcpyAsync(d_in, rgba_host, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int e = fast_common(ctx, true, d_in, w, h, nframes, nullptr, nullptr, nullptr, nullptr, thr, d_keys, d_cnt, cap, 0)) return e;
+    ALVA_CUDA(cudaMemcpyAsync(counts_host, d_cnt, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, ctx->stream));
+    ALVA_CUDA(cudaMemcpyAsync(keys_host, d_keys, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ALVA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < nframes; f++)
+        if (counts_host[f] > cap) { alva_set_error("frame %d: %d corners exceed cap %d", f, counts_host[f], cap); return ALVA_E_CAPACITY; }
+    return 0;
+}

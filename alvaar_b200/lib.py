@@ -1,0 +1,148 @@
+"""ctypes binding of libalva_b200.so (include/alva_b200.h).  Device buffers are torch CUDA tensors;
+only their data pointers cross the boundary."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORB_FMA = 1
+ORB_IC_ANGLE = 2
+
+
+class AlvaError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libalva_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libalva_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise AlvaError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(p)
+        vp, i32, i64 = C.c_void_p, C.c_int, C.c_longlong
+        L.alva_version.restype = i32
+        L.alva_last_error.restype = C.c_char_p
+        L.alva_ctx_create.restype = vp
+        L.alva_ctx_create.argtypes = [i32, vp]
+        L.alva_ctx_destroy.argtypes = [vp]
+        L.alva_ctx_sync.argtypes = [vp]
+        L.alva_ctx_launches.restype = i64
+        L.alva_ctx_launches.argtypes = [vp]
+        L.alva_k_gray.argtypes = [vp, vp, vp, i32, i32, i32]
+        L.alva_k_pyrdown.argtypes = [vp, vp, vp, i32, i32, i32]
+        L.alva_k_fast9.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]
+        L.alva_k_frontend.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32]
+        L.alva_k_retain_best.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32]
+        for name, args in _OPTIONAL.items():
+            if hasattr(L, name):
+                getattr(L, name).argtypes = args
+        _lib = L
+    return _lib
+
+
+_vp, _i32 = C.c_void_p, C.c_int
+_OPTIONAL = {
+    "alva_k_orb_blur": [_vp, _vp, _vp, _i32, _i32, _i32, _i32],
+    "alva_k_orb_describe": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
+    "alva_k_hamming_knn2": [_vp, _vp, _i32, _vp, _i32, _vp],
+    "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
+}
+
+
+def key_x(k):
+    return (k >> 8) & 0xFFF
+
+
+def key_y(k):
+    return (k >> 20) & 0xFFF
+
+
+def key_score(k):
+    return k & 0xFF
+
+
+def unpack_keys(keys):
+    """packed uint32/int64 numpy array -> (n, 3) int32 array of (x, y, score)."""
+    import numpy as np
+    k = np.asarray(keys).astype(np.int64) & 0xFFFFFFFF
+    return np.stack([(k >> 8) & 0xFFF, (k >> 20) & 0xFFF, k & 0xFF], -1).astype(np.int32)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One CUDA device + stream (alva_ctx).  Methods mirror the alva_k_* entry points on torch tensors."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = self.L.alva_ctx_create(int(device), C.c_void_p(stream) if stream else None)
+        if not h:
+            raise AlvaError(self.L.alva_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.alva_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, allow_capacity=False):
+        if rc != 0 and not (allow_capacity and rc == -3):
+            raise AlvaError(f"rc={rc}: {self.L.alva_last_error().decode()}")
+        return rc
+
+    def sync(self):
+        self._chk(self.L.alva_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.alva_ctx_launches(self.h))
+
+    # ---- stages -------------------------------------------------------------------------------
+    def gray(self, rgba, gray, w, h, n):
+        self._chk(self.L.alva_k_gray(self.h, _ptr(rgba), _ptr(gray), w, h, n))
+
+    def pyrdown(self, src, dst, w, h, n):
+        self._chk(self.L.alva_k_pyrdown(self.h, _ptr(src), _ptr(dst), w, h, n))
+
+    def fast9(self, gray, w, h, n, thr, keys, counts, cap, sorted_=True):
+        self._chk(self.L.alva_k_fast9(self.h, _ptr(gray), w, h, n, thr, _ptr(keys), _ptr(counts), cap,
+                                      1 if sorted_ else 0))
+
+    def frontend(self, rgba, w, h, n, l0, l1, l2, l3, thr, keys, counts, cap, sorted_=False):
+        self._chk(self.L.alva_k_frontend(self.h, _ptr(rgba), w, h, n, _ptr(l0), _ptr(l1), _ptr(l2), _ptr(l3),
+                                         thr, _ptr(keys), _ptr(counts), cap, 1 if sorted_ else 0))
+
+    def retain_best(self, keys, counts, cap, n, w, h, nkeep, edge, out_keys, out_counts, out_cap):
+        self._chk(self.L.alva_k_retain_best(self.h, _ptr(keys), _ptr(counts), cap, n, w, h, nkeep, edge,
+                                            _ptr(out_keys), _ptr(out_counts), out_cap))
+
+    def orb_blur(self, gray, blurred, w, h, n, flags=0):
+        self._chk(self.L.alva_k_orb_blur(self.h, _ptr(gray), _ptr(blurred), w, h, n, flags))
+
+    def orb_describe(self, gray, blurred, w, h, n, pts, npts_per_frame, npts, flags, desc, kept, angles=None):
+        self._chk(self.L.alva_k_orb_describe(self.h, _ptr(gray), _ptr(blurred), w, h, n, _ptr(pts),
+                                             _ptr(npts_per_frame), npts, flags, _ptr(desc), _ptr(kept),
+                                             _ptr(angles)))
+
+    def hamming_knn2(self, q, nq, t, nt, out):
+        self._chk(self.L.alva_k_hamming_knn2(self.h, _ptr(q), nq, _ptr(t), nt, _ptr(out)))

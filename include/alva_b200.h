@@ -1,0 +1,113 @@
+/* include/alva_b200.h -- C ABI of libalva_b200.so: the B200-native per-frame visual-SLAM hot path
+ * behind AlvaAR's `System` API.
+ *
+ * Drop-in boundary.  The reference exposes its C++ `System` class to JavaScript
+ * through embind (reference: src/slam/src/embind.cpp:9-18, src/slam/src/system.hpp:19-56); pointers
+ * cross as 32-bit ints because the host there is wasm32.  This header is what a native host binds
+ * instead: opaque handles, real pointers, explicit sizes, no C++/torch types.
+ *
+ *   alva_system_*   : one-to-one with System::{configure,reset,findCameraPose,findCameraPoseWithIMU,
+ *                     findPlane,getFramePoints}  (system.hpp:28-38)
+ *   alva_k_*        : kernel-level entry points for each stage of the hot path (device pointers),
+ *                     the units the parity tests and the ncu captures address
+ *   alva_h_*        : the same stages on HOST buffers (H2D + kernel + D2H inside the call) -- the
+ *                     "e2e" leg of bench.py and what a non-CUDA host would call
+ *
+ * All functions return 0 on success or a negative ALVA_E_* code; alva_last_error() gives the text.
+ * A context is bound to one CUDA device and one stream; it is not thread-safe (the reference System
+ * is single-threaded and non-re-entrant too, SURVEY 8b "Threading").
+ */
+#ifndef ALVA_B200_H
+#define ALVA_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALVA_OK            0
+#define ALVA_E_INVALID    -1   /* bad argument */
+#define ALVA_E_CUDA       -2   /* CUDA runtime/driver error (see alva_last_error) */
+#define ALVA_E_CAPACITY   -3   /* an output list overflowed its capacity */
+#define ALVA_E_STATE      -4   /* call out of order (e.g. not configured) */
+
+/* Packed corner key: (y << 20) | (x << 8) | score.  Sorting keys ascending == cv::FAST's row-major
+ * output order (reference: opencv/modules/features2d/src/fast.cpp:283-288). */
+#define ALVA_KEY_X(k)     (((k) >> 8) & 0xFFFu)
+#define ALVA_KEY_Y(k)     (((k) >> 20) & 0xFFFu)
+#define ALVA_KEY_SCORE(k) ((k) & 0xFFu)
+#define ALVA_MAX_DIM      4095
+
+#define ALVA_ORB_FMA        1   /* blur with fused multiply-add (native AVX2 OpenCV dispatch); default = unfused
+                                   (SSE baseline == the shipped WASM simd128 arithmetic) */
+#define ALVA_ORB_IC_ANGLE   2   /* steer rBRIEF by the intensity-centroid angle (ORB::detect mode) instead of
+                                   AlvaAR's constant -1 degree (feature_extractor.cpp:179-182) */
+
+typedef struct alva_ctx alva_ctx;
+typedef struct alva_system alva_system;
+
+int         alva_version(void);
+const char* alva_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (NULL = the context creates its own). */
+alva_ctx* alva_ctx_create(int device, void* stream);
+void      alva_ctx_destroy(alva_ctx* ctx);
+int       alva_ctx_sync(alva_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long alva_ctx_launches(const alva_ctx* ctx);
+
+/* ---- kernel-level stages (DEVICE pointers; batches of nframes tightly packed frames) --------- */
+
+/* cv::cvtColor(RGBA2GRAY)  -- reference call site src/slam/src/system.cpp:111-112 */
+int alva_k_gray(alva_ctx*, const uint8_t* rgba, uint8_t* gray, int w, int h, int nframes);
+
+/* cv::pyrDown, one level   -- level step of cv::buildOpticalFlowPyramid,
+ * reference call site src/slam/src/visual_frontend.cpp:696 (opencv video/src/lkpyramid.cpp:726-822) */
+int alva_k_pyrdown(alva_ctx*, const uint8_t* src, uint8_t* dst, int w, int h, int nframes);
+
+/* cv::FAST(gray, thr, nms=true, TYPE_9_16) on each frame (opencv features2d/src/fast.cpp:496).
+ * keys[f*cap + i]: packed corner keys; counts[f] = true number found (may exceed cap: then only cap
+ * are stored and the call returns ALVA_E_CAPACITY after completing).  sorted != 0: row-major order. */
+int alva_k_fast9(alva_ctx*, const uint8_t* gray, int w, int h, int nframes, int thr,
+                 uint32_t* keys, int32_t* counts, int cap, int sorted);
+
+/* Fused front end: RGBA -> gray L0 (+ L1..L3 Gaussian pyramid) + FAST-9 corners of L0 in one pass over
+ * the input (system.cpp:112 + visual_frontend.cpp:672-698 + orb.cpp:849-850).  L1/L2/L3 may be NULL
+ * (then the pyramid stops at the first NULL level).  Level k is ((w_{k-1}+1)/2) x ((h_{k-1}+1)/2). */
+int alva_k_frontend(alva_ctx*, const uint8_t* rgba, int w, int h, int nframes,
+                    uint8_t* l0, uint8_t* l1, uint8_t* l2, uint8_t* l3,
+                    int thr, uint32_t* keys, int32_t* counts, int cap, int sorted);
+
+/* KeyPointsFilter::retainBest(n) on FAST keys (features2d/src/keypoint.cpp:69-90): keeps every corner
+ * whose score >= the n-th best score (ties can make it more than n), border-filtered like ORB
+ * (edge = 31: orb.cpp:1130) when edge > 0; result sorted row-major.  out_counts[f] <= out_cap. */
+int alva_k_retain_best(alva_ctx*, const uint32_t* keys, const int32_t* counts, int cap, int nframes,
+                       int w, int h, int n, int edge, uint32_t* out_keys, int32_t* out_counts, int out_cap);
+
+/* ORB pre-blur: GaussianBlur(7x7, sigma 2, REFLECT_101) as ORB applies it (orb.cpp:1188). */
+int alva_k_orb_blur(alva_ctx*, const uint8_t* gray, uint8_t* blurred, int w, int h, int nframes, int flags);
+
+/* rBRIEF-256 at given points (FeatureExtractor::describeFeaturePoints, feature_extractor.cpp:160-214 ->
+ * ORB::compute, orb.cpp:219-350).  pts: [nframes][npts][2] float (x, y); npts_per_frame may be NULL
+ * (= npts for every frame).  desc: [nframes][npts][32]; kept: [nframes][npts] (0 = dropped by the 31-px
+ * border rule).  angles_out (optional, [nframes][npts]): the angle used, in degrees.
+ * `gray` is needed only with ALVA_ORB_IC_ANGLE (moments are taken on the un-blurred image). */
+int alva_k_orb_describe(alva_ctx*, const uint8_t* gray, const uint8_t* blurred, int w, int h, int nframes,
+                        const float* pts, const int32_t* npts_per_frame, int npts, int flags,
+                        uint8_t* desc, uint8_t* kept, float* angles_out);
+
+/* Brute-force Hamming 2-NN (BFMatcher(NORM_HAMMING).knnMatch(k=2), features2d/src/matchers.cpp:757;
+ * tie rule core/src/batch_distance.cpp:235-248).  q: [nq][32], t: [nt][32] bytes;
+ * out[4*i] = {idx0, dist0, idx1, dist1} (int32; -1 when nt < 2). */
+int alva_k_hamming_knn2(alva_ctx*, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out);
+
+/* ---- host-buffer variants (copies inside; used for e2e timing and by non-CUDA hosts) ---------- */
+int alva_h_frontend(alva_ctx*, const uint8_t* rgba_host, int w, int h, int nframes, int thr,
+                    uint32_t* keys_host, int32_t* counts_host, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALVA_B200_H */

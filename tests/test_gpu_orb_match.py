@@ -1,0 +1,148 @@
+"""GPU parity tests (B200): ORB blur / rBRIEF descriptors / IC angle / Hamming 2-NN vs the oracle and goldens.
+Descriptors and match indices are bit-exact; the blur is float arithmetic rounded to u8 and is checked bit-exact
+too (the kernel pins evaluation order and fusion exactly like the reference build it mirrors)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import P, golden
+from alvaar_b200 import synth, ORB_FMA, ORB_IC_ANGLE
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("w,h", [(1280, 720), (641, 479), (64, 64), (130, 35)])
+@pytest.mark.parametrize("fma", [0, 1])
+def test_orb_blur(gpu_ctx, oracle, w, h, fma):
+    img = synth.crop(w, h, 11, 13)
+    want = np.empty_like(img)
+    oracle.orc_orb_blur(P(img), w, h, fma, P(want))
+    out = torch.zeros((h, w), dtype=torch.uint8, device=DEV)
+    gpu_ctx.orb_blur(dev(img), out, w, h, 1, ORB_FMA if fma else 0)
+    assert (out.cpu().numpy() == want).all()
+
+
+def test_orb_blur_golden(gpu_ctx):
+    g = golden("orb")
+    h, w = g["img"].shape
+    for flags, key in ((0, "blur"), (ORB_FMA, "blur_fma")):
+        out = torch.zeros((h, w), dtype=torch.uint8, device=DEV)
+        gpu_ctx.orb_blur(dev(g["img"]), out, w, h, 1, flags)
+        assert (out.cpu().numpy() == g[key]).all()
+
+
+def gpu_describe(gpu_ctx, img, blur, pts, flags, nframes=1, npf=None):
+    h, w = img.shape[-2:]
+    n = pts.shape[-2]
+    desc = torch.zeros((nframes, n, 32), dtype=torch.uint8, device=DEV)
+    kept = torch.zeros((nframes, n), dtype=torch.uint8, device=DEV)
+    ang = torch.zeros((nframes, n), dtype=torch.float32, device=DEV)
+    gpu_ctx.orb_describe(dev(img), dev(blur), w, h, nframes, dev(pts), None if npf is None else dev(npf), n, flags,
+                         desc, kept, ang)
+    torch.cuda.synchronize()
+    return desc.cpu().numpy(), kept.cpu().numpy(), ang.cpu().numpy()
+
+
+def test_orb_describe_constant_angle(gpu_ctx, oracle):
+    """AlvaAR mode: every keypoint steered by -1 degree (feature_extractor.cpp:179-182)."""
+    w, h = 1280, 720
+    img = synth.crop(w, h, 40, 60)
+    blur = np.empty_like(img)
+    oracle.orc_orb_blur(P(img), w, h, 0, P(blur))
+    rng = np.random.default_rng(1)
+    n = 100000                                   # >= 1e5 keypoints (SURVEY 7 "hard parts")
+    pts = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], 1).astype(np.float32)
+    pts[:5000] = np.floor(pts[:5000]) + 0.5      # round-half-even cases
+    want_d, want_k = np.zeros((n, 32), np.uint8), np.zeros(n, np.uint8)
+    oracle.orc_orb_describe(P(blur), w, h, P(pts), None, n, P(want_d), P(want_k))
+    d, k, a = gpu_describe(gpu_ctx, img, blur, pts, 0)
+    assert (k[0] == want_k).all() and (d[0] == want_d).all()
+    assert (a[0][want_k == 1] == -1).all()
+
+
+def test_orb_describe_ic_angle(gpu_ctx, oracle):
+    """ORB detect mode: intensity-centroid angle (exact integer moments + fastAtan2) then steered BRIEF."""
+    w, h = 1280, 720
+    img = synth.crop(w, h, 400, 300)
+    blur = np.empty_like(img)
+    oracle.orc_orb_blur(P(img), w, h, 0, P(blur))
+    rng = np.random.default_rng(2)
+    n = 50000
+    pts = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], 1).astype(np.float32)
+    ang = np.zeros(n, np.float32)
+    oracle.orc_ic_angles(P(img), w, h, P(pts), n, P(ang))
+    want_d, want_k = np.zeros((n, 32), np.uint8), np.zeros(n, np.uint8)
+    oracle.orc_orb_describe(P(blur), w, h, P(pts), P(ang), n, P(want_d), P(want_k))
+    d, k, a = gpu_describe(gpu_ctx, img, blur, pts, ORB_IC_ANGLE)
+    m = want_k == 1
+    assert (k[0] == want_k).all()
+    assert (a[0][m].view(np.uint32) == ang[m].view(np.uint32)).all()      # angles bit-identical
+    assert (d[0][m] == want_d[m]).all()
+
+
+
+def test_orb_golden(gpu_ctx):
+    g = golden("orb")
+    img, blur = g["img"], g["blur"]
+    d, k, _ = gpu_describe(gpu_ctx, img, blur, g["pts"], 0)
+    m = g["kept"] == 1
+    assert (k[0] == g["kept"]).all() and (d[0][m] == g["desc"][m]).all()
+    # reference ORB::detectAndCompute keypoints: angle + descriptor straight from the reference
+    kp = g["det_kp"]
+    d, k, a = gpu_describe(gpu_ctx, img, blur, np.ascontiguousarray(kp[:, :2]), ORB_IC_ANGLE)
+    assert k[0].all()
+    assert (a[0].view(np.uint32) == kp[:, 3].copy().view(np.uint32)).all()
+    assert (d[0] == g["det_desc"]).all()
+
+
+def test_orb_describe_ragged_batch(gpu_ctx, oracle):
+    """Several frames with different point counts in one call; slots past the count come back empty."""
+    w, h, nf, n = 320, 240, 3, 64
+    imgs = np.stack([synth.crop(w, h, 50 * f, 80 * f) for f in range(nf)])
+    blurs = np.stack([np.empty_like(imgs[0]) for _ in range(nf)])
+    for f in range(nf):
+        oracle.orc_orb_blur(P(imgs[f]), w, h, 0, P(blurs[f]))
+    rng = np.random.default_rng(4)
+    pts = np.stack([rng.uniform(0, w, (nf, n)), rng.uniform(0, h, (nf, n))], -1).astype(np.float32)
+    npf = np.array([64, 0, 17], np.int32)
+    d, k, _ = gpu_describe(gpu_ctx, imgs, blurs, pts, 0, nf, npf)
+    for f in range(nf):
+        want_d, want_k = np.zeros((n, 32), np.uint8), np.zeros(n, np.uint8)
+        c = int(npf[f])
+        if c:
+            oracle.orc_orb_describe(P(blurs[f]), w, h, P(np.ascontiguousarray(pts[f, :c])), None, c, P(want_d), P(want_k))
+        assert (k[f] == want_k).all() and (d[f] == want_d).all()
+
+
+@pytest.mark.parametrize("nq,nt", [(1000, 10000), (1000, 1000), (7, 1), (1, 2), (33, 1025), (1000, 20000)])
+def test_knn2_vs_oracle(gpu_ctx, oracle, nq, nt):
+    q, t = synth.make_descriptors(nq, nt, seed=nq + nt, planted=0.3 if nt >= nq else 0.0)
+    if nt > 100:
+        t[nt // 2:nt // 2 + 20] = t[:20]          # exact duplicates -> tie rule (lowest index first)
+    want = np.zeros((nq, 4), np.int32)
+    oracle.orc_knn2(P(q), nq, P(t), nt, P(want))
+    out = torch.zeros((nq, 4), dtype=torch.int32, device=DEV)
+    gpu_ctx.hamming_knn2(dev(q), nq, dev(t), nt, out)
+    assert (out.cpu().numpy() == want).all()
+
+
+def test_knn2_golden(gpu_ctx):
+    g = golden("knn")
+    out = torch.zeros((len(g["q"]), 4), dtype=torch.int32, device=DEV)
+    gpu_ctx.hamming_knn2(dev(g["q"]), len(g["q"]), dev(g["t"]), len(g["t"]), out)
+    assert (out.cpu().numpy() == g["out"]).all()
+
+
+def test_knn2_self_match_property(gpu_ctx):
+    """Size-independent property at the largest size: matching a set against itself gives (i, 0) first."""
+    _, t = synth.make_descriptors(8, 20000, seed=5, planted=0.0)
+    d_t = dev(t)
+    out = torch.zeros((20000, 4), dtype=torch.int32, device=DEV)
+    gpu_ctx.hamming_knn2(d_t, 20000, d_t, 20000, out)
+    o = out.cpu().numpy()
+    assert (o[:, 0] == np.arange(20000)).all() and (o[:, 1] == 0).all() and (o[:, 3] > 0).all()
