@@ -124,3 +124,92 @@ def make_descriptors(nq=1000, nt=10000, seed=7, planted=0.3, flip=0.08):
     noise = np.packbits(rng.random((npl, 256)) < flip, axis=1)
     q[:npl] = t[idx] ^ noise
     return q, t
+
+
+def _quat_from_R(R):
+    """(x, y, z, w) unit quaternion of a rotation matrix."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = [(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s]
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = [0, 0, 0, 0]
+        q[i] = 0.25 * s
+        q[j] = (R[j, i] + R[i, j]) / s
+        q[k] = (R[k, i] + R[i, k]) / s
+        q[3] = (R[k, j] - R[j, k]) / s
+    q = np.array(q)
+    return q / np.linalg.norm(q)
+
+
+def make_ba_problem(nkf=20, nlm=3000, obs_per_lm=4, seed=42, w=1280, h=720, noise_px=0.5, outlier_frac=0.05,
+                    outlier_px=20.0, pose_noise_t=0.01, pose_noise_r_deg=0.2, nconst=2):
+    """Local-BA problem in the reference's parametrisation: nkf cameras on a circle arc looking
+    at a point cloud (depth 2-8 m), every landmark observed by `obs_per_lm` of its 6 nearest cameras; the first
+    observer is the ANCHOR (inverse depth, no residual) -> nlm*(obs_per_lm-1) residuals; pixel noise, 5 % gross
+    outliers, perturbed initial poses, the `nconst` oldest keyframes fixed.
+    Returns a dict of flat arrays in the layout of include/alva_b200.h (poses = [t, q(x,y,z,w)] camera-to-world)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = intrinsics(w, h)
+    # cameras on an arc, looking along +z with a slight toe-in
+    poses_gt = []
+    for k in range(nkf):
+        a = (k - (nkf - 1) / 2) * 0.03
+        t = np.array([3.0 * np.sin(a) + 0.08 * k, 0.02 * np.sin(0.7 * k), 0.3 * (1 - np.cos(a))])
+        R = _rot(0.01 * np.sin(k), -a * 0.8, 0.005 * k)
+        poses_gt.append((R, t))
+    # landmarks: sample a pixel + depth in a random camera, keep if visible in >= obs_per_lm cameras
+    pts, obs_list = [], []
+    while len(pts) < nlm:
+        k0 = rng.integers(0, nkf)
+        u, v, z = rng.uniform(40, w - 40), rng.uniform(40, h - 40), rng.uniform(2.0, 8.0)
+        R, t = poses_gt[k0]
+        X = R @ np.array([(u - cx) / fx * z, (v - cy) / fy * z, z]) + t
+        vis = []
+        for k, (Rk, tk) in enumerate(poses_gt):
+            pc = Rk.T @ (X - tk)
+            if pc[2] > 0.5:
+                uu, vv = fx * pc[0] / pc[2] + cx, fy * pc[1] / pc[2] + cy
+                if 20 <= uu < w - 20 and 20 <= vv < h - 20:
+                    vis.append((abs(k - k0), k, uu, vv))
+        if len(vis) < obs_per_lm:
+            continue
+        vis.sort()
+        near = vis[:6]
+        sel = sorted(rng.choice(len(near), obs_per_lm, replace=False))
+        chosen = sorted([near[i] for i in sel], key=lambda e: e[1])
+        pts.append(X)
+        obs_list.append([(k, uu, vv) for _, k, uu, vv in chosen])
+    # perturbed initial poses
+    poses = np.zeros((nkf, 7))
+    for k, (R, t) in enumerate(poses_gt):
+        if k >= nconst:
+            dr = np.deg2rad(rng.normal(0, pose_noise_r_deg, 3))
+            R = _rot(*dr) @ R
+            t = t + rng.normal(0, pose_noise_t, 3)
+        poses[k, :3] = t
+        poses[k, 3:] = _quat_from_R(R)
+    pose_const = np.zeros(nkf, np.uint8)
+    pose_const[:nconst] = 1
+    anch_kf = np.zeros(nlm, np.int32)
+    anch_uv = np.zeros((nlm, 2))
+    invd = np.zeros(nlm)
+    okf, olm, ouv = [], [], []
+    for l, (X, ob) in enumerate(zip(pts, obs_list)):
+        ka, ua, va = ob[0]
+        anch_kf[l] = ka
+        anch_uv[l] = (ua + rng.normal(0, noise_px), va + rng.normal(0, noise_px))
+        Ra, ta = poses_gt[ka]
+        za = (Ra.T @ (X - ta))[2]
+        invd[l] = 1.0 / (za * (1 + rng.normal(0, 0.02)))
+        for k, uu, vv in ob[1:]:
+            sig = outlier_px if rng.random() < outlier_frac else noise_px
+            okf.append(k)
+            olm.append(l)
+            ouv.append((uu + rng.normal(0, sig), vv + rng.normal(0, sig)))
+    return dict(calib=np.array([fx, fy, cx, cy]), poses=poses, pose_const=pose_const, invd=invd, anch_kf=anch_kf,
+                anch_uv=np.ascontiguousarray(anch_uv), obs_kf=np.array(okf, np.int32), obs_lm=np.array(olm, np.int32),
+                obs_uv=np.ascontiguousarray(np.array(ouv)), huber=float(np.sqrt(5.9915)))

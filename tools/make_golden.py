@@ -94,6 +94,14 @@ def main():
     out = np.zeros((200, 4), np.int32)
     R.ref_knn2(P(q), 200, P(t), 500, P(out))
     np.savez_compressed(os.path.join(OUT, "knn.npz"), q=q, t=t, out=out)
+    # ---- local BA: ceres::Solve (SPARSE_SCHUR, LM, <= 5 it, Huber) on AlvaAR's anchored-inverse-depth functor
+    pb = synth.make_ba_problem(8, 300, 3, seed=7)
+    poses, invd = pb["poses"].copy(), pb["invd"].copy()
+    summary, costs = np.zeros(8), np.zeros(64)
+    R.ref_ba_solve(P(pb["calib"]), P(poses), P(pb["pose_const"]), len(poses), P(invd), P(pb["anch_kf"]), P(pb["anch_uv"]),
+                   len(invd), P(pb["obs_kf"]), P(pb["obs_lm"]), P(pb["obs_uv"]), len(pb["obs_kf"]),
+                   C.c_double(pb["huber"]), 5, P(summary), P(costs))
+    np.savez_compressed(os.path.join(OUT, "ba.npz"), poses_out=poses, invd_out=invd, summary=summary, costs=costs, **pb)
     print("golden vectors written to", OUT)
 
 
