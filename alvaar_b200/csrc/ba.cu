@@ -1,0 +1,786 @@
+// ba.cu -- local bundle adjustment (anchored inverse depth, SE(3) poses) on sm_100a: residual/Jacobian build,
+// Huber re-weighting, Schur-complement reduction to the reduced camera system, dense Cholesky, back-substitution and
+// Ceres' Levenberg-Marquardt trust-region control flow -- all on the device, batched over independent problems.
+//
+// Reference behaviour (CPU restatement: oracle/ba_oracle.c; pinned against ceres::Solve itself):
+//   cost functor      DirectSE3::ReprojectionErrorKSE3AnchInvDepth::Evaluate   src/slam/src/ceres_parametrization.cpp:157-269
+//   plus-op           SE3Parameterization::Plus                                src/slam/src/ceres_parametrization.hpp:224-240
+//   problem / options Optimizer::localBA                                       src/slam/src/optimizer.cpp:20-262
+//   robust loss       HuberLoss + Corrector                                    ceres-solver/internal/ceres/loss_function.cc:48-62, corrector.cc:36-134
+//   Schur reduction   SchurEliminator::Eliminate / BackSubstitute              ceres-solver/internal/ceres/schur_eliminator_impl.h:176-375
+//   LM shell          LevenbergMarquardtStrategy, TrustRegionMinimizer         levenberg_marquardt_strategy.cc:66-160, trust_region_minimizer.cc
+//
+// FP64 throughout (the north-star tolerance is 1e-4 relative; we land at ~1e-9).  The e-blocks are 1-dimensional
+// (inverse depth), so (E'E)^-1 is a scalar reciprocal per landmark; the reduced system is <= 20 poses x 6 = 120 wide
+// and lives in ONE CTA's shared memory for the Cholesky / triangular solves.  The trust-region decisions
+// (accept / reject, radius update, function / parameter / gradient tolerance) run in single-CTA "control" kernels
+// that read and write a device-resident state block, so an entire solve is a fixed launch sequence with no host
+// synchronisation (graph-capturable).
+#include "alva_common.cuh"
+#include "../../include/alva_b200.h"
+#include <math.h>
+#include <float.h>
+
+namespace {
+
+constexpr int NMAX = 128;   // max reduced-system width (>= 6 * free poses), padded
+constexpr int LIN_THREADS = 128;
+
+struct BaState {
+    double radius, decrease_factor, x_cost, cand_cost, xnorm, gmax, model_change;
+    double se_min, se_cur, se_ref, se_cand, se_acc_ref, se_acc_cand;
+    double initial_cost, push_cost;
+    int reuse_diagonal, invalid_steps, iteration, last_success, n_success, n_iter, term, done;
+    int relin, step_ok, ncols, pad;
+};
+
+// per-problem views into the workspace
+struct BaProblem {
+    // inputs
+    const double* calib;       // [4]
+    double* poses;             // [nkf*7] in/out
+    const uint8_t* pose_const; // [nkf]
+    double* invd;              // [nlm]   in/out
+    const int32_t* anch_kf;    // [nlm]
+    const double* anch_uv;     // [nlm*2]
+    const int32_t* obs_kf;     // [nobs]
+    const int32_t* obs_lm;     // [nobs]  (-1 = unused slot)
+    const double* obs_uv;      // [nobs*2]
+    // workspace
+    double *res, *Ja, *Jp, *Jd;             // per obs: 2, 12, 12, 2
+    double *wp;                             // per obs: 6  (F_p^T e)
+    double *nf, *gf, *scf, *diagf, *Df;     // [NMAX]
+    double *ne, *ge, *sce, *diage, *De;     // [nlm]
+    double *ete, *etb, *wa, *ye;            // [nlm], [nlm], [nlm*6], [nlm]
+    double *S, *rhs, *yf;                   // [NMAX*NMAX], [NMAX], [NMAX]
+    double *cand_poses, *cand_invd;         // [nkf*7], [nlm]
+    double *cost_part;                      // [nblk]
+    int32_t *pose_col;                      // [nkf]
+    int32_t *lm_start, *lm_obs;             // CSR landmark -> observations: [nlm+1], [nobs]
+    BaState* st;
+};
+
+struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; };
+
+// ------------------------------------------------------------------------------------------ SE(3) helpers
+__device__ __forceinline__ void quat_to_R(const double* q, double* R) {   // q = (x,y,z,w), normalised here
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// SE3Parameterization::Plus: out = exp([ups, om]) * (t, q)   (Sophus se3.hpp:763-784, so3.hpp:585-621)
+__device__ void se3_plus(const double* x, const double* delta, double* out) {
+    const double* ups = delta;
+    const double* om = delta + 3;
+    const double theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    const double eps = 1e-10;
+    double theta, imag, real;
+    if (theta_sq < eps * eps) {
+        theta = 0;
+        const double t4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * t4;
+        real = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * t4;
+    } else {
+        theta = sqrt(theta_sq);
+        const double half = 0.5 * theta;
+        imag = sin(half) / theta;
+        real = cos(half);
+    }
+    const double dq[4] = {imag * om[0], imag * om[1], imag * om[2], real};
+    double Rd[9];
+    quat_to_R(dq, Rd);
+    const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+    double V[9];
+    if (theta < eps) {
+        for (int i = 0; i < 9; i++) V[i] = Rd[i];
+    } else {
+        const double a = (1 - cos(theta)) / theta_sq, b = (theta - sin(theta)) / (theta_sq * theta);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double o2 = 0;
+                for (int k = 0; k < 3; k++) o2 += O[3 * i + k] * O[3 * k + j];
+                V[3 * i + j] = (i == j ? 1.0 : 0.0) + a * O[3 * i + j] + b * o2;
+            }
+    }
+    for (int i = 0; i < 3; i++)
+        out[i] = V[3 * i] * ups[0] + V[3 * i + 1] * ups[1] + V[3 * i + 2] * ups[2] + Rd[3 * i] * x[0] + Rd[3 * i + 1] * x[1] +
+                 Rd[3 * i + 2] * x[2];
+    const double qn = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+    const double bx = x[3] / qn, by = x[4] / qn, bz = x[5] / qn, bw = x[6] / qn;
+    const double ax = dq[0], ay = dq[1], az = dq[2], aw = dq[3];
+    double q[4] = {aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                   aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz};
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) out[3 + i] = q[i] / n;
+}
+
+// ReprojectionErrorKSE3AnchInvDepth::Evaluate; Ja/Jp are the LOCAL 2x6 Jacobians (J_global * [I6; 0])
+__device__ __forceinline__ bool ba_evaluate(const double* calib, const double* anch, const double* pose, double invd, double u,
+                                            double v, double ua, double va, double* res, double* Ja, double* Jp, double* Jd) {
+    const double fx = calib[0], fy = calib[1], cx = calib[2], cy = calib[3];
+    double Rwa[9], Rwc[9];
+    quat_to_R(anch + 3, Rwa);
+    quat_to_R(pose + 3, Rwc);
+    const double zanch = 1.0 / invd;
+    const double ap[3] = {zanch * (ua - cx) / fx, zanch * (va - cy) / fy, zanch};
+    double Ra[3], wpt[3];
+    for (int i = 0; i < 3; i++) {
+        Ra[i] = Rwa[3 * i] * ap[0] + Rwa[3 * i + 1] * ap[1] + Rwa[3 * i + 2] * ap[2];
+        wpt[i] = Ra[i] + anch[i];
+    }
+    const double d[3] = {wpt[0] - pose[0], wpt[1] - pose[1], wpt[2] - pose[2]};
+    double cp[3];
+    for (int i = 0; i < 3; i++) cp[i] = Rwc[i] * d[0] + Rwc[3 + i] * d[1] + Rwc[6 + i] * d[2];
+    const double iz = 1.0 / cp[2];
+    res[0] = fx * cp[0] * iz + cx - u;
+    res[1] = fy * cp[1] * iz + cy - v;
+    if (Ja) {
+        const double iz2 = iz * iz;
+        const double Jc[6] = {iz * fx, 0, -cp[0] * iz2 * fx, 0, iz * fy, -cp[1] * iz2 * fy};
+        double JR[6];
+        for (int r = 0; r < 2; r++)
+            for (int c = 0; c < 3; c++)
+                JR[3 * r + c] = Jc[3 * r] * Rwc[3 * c] + Jc[3 * r + 1] * Rwc[3 * c + 1] + Jc[3 * r + 2] * Rwc[3 * c + 2];
+        const double Sk[9] = {0, -wpt[2], wpt[1], wpt[2], 0, -wpt[0], -wpt[1], wpt[0], 0};
+        for (int r = 0; r < 2; r++)
+            for (int c = 0; c < 3; c++) {
+                const double js = JR[3 * r] * Sk[c] + JR[3 * r + 1] * Sk[3 + c] + JR[3 * r + 2] * Sk[6 + c];
+                Ja[6 * r + c] = JR[3 * r + c];
+                Ja[6 * r + 3 + c] = -js;
+                Jp[6 * r + c] = -JR[3 * r + c];
+                Jp[6 * r + 3 + c] = js;
+            }
+        for (int r = 0; r < 2; r++) Jd[r] = -zanch * (JR[3 * r] * Ra[0] + JR[3 * r + 1] * Ra[1] + JR[3 * r + 2] * Ra[2]);
+    }
+    return cp[2] > 0;
+}
+
+__device__ __forceinline__ void huber(double s, double delta, double& rho0, double& rho1) {
+    if (delta > 0 && s > delta * delta) {
+        const double r = sqrt(s);
+        rho0 = 2 * delta * r - delta * delta;
+        rho1 = fmax(DBL_MIN, delta / r);
+    } else { rho0 = s; rho1 = 1.0; }
+}
+
+// deterministic block reduction (fixed tree), result valid in thread 0
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = NT / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    return sm[0];
+}
+
+// ------------------------------------------------------------------------------------------ setup (1 CTA / problem)
+__global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    __shared__ int ref[256];
+    __shared__ int scan_s[257];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 256; k += 256) ref[k] = 0;
+    for (int l = tid; l <= D.nlm; l += 256) P.lm_start[l] = 0;
+    __syncthreads();
+    // counts per landmark (exact integer atomics) and referenced poses
+    for (int o = tid; o < D.nobs; o += 256) {
+        const int l = P.obs_lm[o];
+        if (l < 0) continue;
+        atomicAdd(&P.lm_start[l + 1], 1);
+        ref[P.anch_kf[l]] = 1;
+        ref[P.obs_kf[o]] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0;
+        for (int k = 0; k < D.nkf; k++) {
+            if (!P.pose_const[k] && ref[k]) { P.pose_col[k] = c; c += 6; }
+            else P.pose_col[k] = -1;
+        }
+        BaState& s = *P.st;
+        s.ncols = c;
+        s.radius = 1e4; s.decrease_factor = 2.0; s.reuse_diagonal = 0; s.invalid_steps = 0; s.iteration = 0;
+        s.last_success = 1; s.n_success = 0; s.n_iter = 0; s.term = 1; s.done = 0; s.relin = 1; s.step_ok = 0;
+        s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
+    }
+    // exclusive scan of counts -> lm_start (chunked: 256 threads)
+    {
+        const int chunk = (D.nlm + 256) / 256;
+        const int b = tid * chunk + 1, e = min(b + chunk, D.nlm + 1);
+        int sum = 0;
+        for (int i = b; i < e; i++) sum += P.lm_start[i];
+        scan_s[tid + 1] = sum;
+        if (tid == 0) scan_s[0] = 0;
+        __syncthreads();
+        if (tid == 0) for (int i = 1; i <= 256; i++) scan_s[i] += scan_s[i - 1];
+        __syncthreads();
+        int run = scan_s[tid];
+        for (int i = b; i < e; i++) { run += P.lm_start[i]; P.lm_start[i] = run; }
+        __syncthreads();
+    }
+    // fill: thread per landmark scans?  cheaper: every observation finds its slot by counting earlier obs of the
+    // same landmark -- obs lists are short and the reference emits them grouped, so do a deterministic per-landmark
+    // pass: thread l walks the whole obs array only if ungrouped.  Common case (grouped, ascending): slot = o - first.
+    for (int l = tid; l < D.nlm; l += 256) {
+        const int b = P.lm_start[l], e = P.lm_start[l + 1];
+        if (e == b) continue;
+        // fast path: find the first obs of l by binary search assuming obs_lm is non-decreasing
+        int lo = 0, hi = D.nobs;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; const int v = P.obs_lm[mid]; if (v >= 0 && v < l) lo = mid + 1; else hi = mid; }
+        bool grouped = (lo + (e - b) <= D.nobs);
+        for (int i = 0; grouped && i < e - b; i++) grouped = (P.obs_lm[lo + i] == l);
+        if (grouped) { for (int i = 0; i < e - b; i++) P.lm_obs[b + i] = lo + i; }
+        else { int c = b; for (int o = 0; o < D.nobs && c < e; o++) if (P.obs_lm[o] == l) P.lm_obs[c++] = o; }
+    }
+    for (int i = tid; i < NMAX; i += 256) { P.nf[i] = 0; P.gf[i] = 0; }
+    for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------ linearise (thread / obs)
+// FULL: residuals + Jacobians at the current point, squared column norms and gradient (atomics on the pose columns);
+// otherwise cost only at the candidate point.  Per-block cost partials (deterministic order in the control kernels).
+template <bool FULL>
+__global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    __shared__ double red[LIN_THREADS];
+    const BaState& st = *P.st;
+    const bool active = FULL ? (st.relin && !st.done) : (st.step_ok && !st.done);
+    if (!active) return;   // uniform per CTA
+    const int o = blockIdx.x * LIN_THREADS + threadIdx.x;
+    double cost = 0;
+    const int l = o < D.nobs ? P.obs_lm[o] : -1;
+    if (l >= 0) {
+        const double* poses = FULL ? P.poses : P.cand_poses;
+        const double* invd = FULL ? P.invd : P.cand_invd;
+        const int ka = P.anch_kf[l], kp = P.obs_kf[o];
+        double r[2], Ja[12], Jp[12], Jd[2];
+        ba_evaluate(P.calib, poses + 7 * ka, poses + 7 * kp, invd[l], P.obs_uv[2 * o], P.obs_uv[2 * o + 1], P.anch_uv[2 * l],
+                    P.anch_uv[2 * l + 1], r, FULL ? Ja : nullptr, Jp, Jd);
+        double rho0, rho1;
+        huber(r[0] * r[0] + r[1] * r[1], D.huber, rho0, rho1);
+        cost = 0.5 * rho0;
+        if (FULL) {
+            const double sc = sqrt(rho1);
+            r[0] *= sc; r[1] *= sc;
+            P.res[2 * o] = r[0]; P.res[2 * o + 1] = r[1];
+            Jd[0] *= sc; Jd[1] *= sc;
+            P.Jd[2 * o] = Jd[0]; P.Jd[2 * o + 1] = Jd[1];
+            atomicAdd(&P.ne[l], Jd[0] * Jd[0] + Jd[1] * Jd[1]);
+            atomicAdd(&P.ge[l], Jd[0] * r[0] + Jd[1] * r[1]);
+            const int ca = P.pose_col[ka], cp = P.pose_col[kp];
+#pragma unroll
+            for (int i = 0; i < 12; i++) { Ja[i] *= sc; Jp[i] *= sc; P.Ja[12 * o + i] = Ja[i]; P.Jp[12 * o + i] = Jp[i]; }
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if (ca >= 0) {
+                    atomicAdd(&P.nf[ca + c], Ja[c] * Ja[c] + Ja[6 + c] * Ja[6 + c]);
+                    atomicAdd(&P.gf[ca + c], Ja[c] * r[0] + Ja[6 + c] * r[1]);
+                }
+                if (cp >= 0) {
+                    atomicAdd(&P.nf[cp + c], Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c]);
+                    atomicAdd(&P.gf[cp + c], Jp[c] * r[0] + Jp[6 + c] * r[1]);
+                }
+            }
+        }
+    }
+    const double tot = block_sum<LIN_THREADS>(cost, red);
+    if (threadIdx.x == 0) P.cost_part[blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------ control: before the step
+// TrustRegionMinimizer::{IterationZero, FinalizeIterationAndCheckIfMinimizerCanContinue} + LM ComputeStep's diagonal.
+__global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    BaState& st = *P.st;
+    __shared__ double red[256];
+    __shared__ int go;
+    const int tid = threadIdx.x;
+    const int n = st.ncols;
+    if (st.done) return;
+    if (st.relin) {
+        // cost at the (new) current point, in a fixed summation order
+        double c = 0;
+        for (int i = tid; i < D.nblk; i += 256) c += P.cost_part[i];
+        const double x_cost = block_sum<256>(c, red);
+        // |x|
+        double xn = 0;
+        for (int k = tid; k < D.nkf; k += 256)
+            if (P.pose_col[k] >= 0) for (int i = 0; i < 7; i++) xn += P.poses[7 * k + i] * P.poses[7 * k + i];
+        for (int l = tid; l < D.nlm; l += 256)
+            if (P.lm_start[l + 1] > P.lm_start[l]) xn += P.invd[l] * P.invd[l];
+        __syncthreads();
+        xn = block_sum<256>(xn, red);
+        // gradient max-norm |x - Plus(x, -g)|_inf
+        double gm = 0;
+        for (int k = tid; k < D.nkf; k += 256) {
+            const int c0 = P.pose_col[k];
+            if (c0 < 0) continue;
+            double dlt[6], out[7];
+            for (int i = 0; i < 6; i++) dlt[i] = -P.gf[c0 + i];
+            se3_plus(P.poses + 7 * k, dlt, out);
+            for (int i = 0; i < 7; i++) gm = fmax(gm, fabs(P.poses[7 * k + i] - out[i]));
+        }
+        for (int l = tid; l < D.nlm; l += 256)
+            if (P.lm_start[l + 1] > P.lm_start[l]) gm = fmax(gm, fabs(P.ge[l]));
+        __syncthreads();
+        red[tid] = gm;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); __syncthreads(); }
+        gm = red[0];
+        if (st.iteration == 0) {   // Jacobi scaling is fixed at iteration 0 (trust_region_minimizer.cc:266-275)
+            for (int i = tid; i < n; i += 256) P.scf[i] = 1.0 / (1.0 + sqrt(P.nf[i]));
+            for (int l = tid; l < D.nlm; l += 256) P.sce[l] = 1.0 / (1.0 + sqrt(P.ne[l]));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            st.x_cost = x_cost; st.xnorm = sqrt(xn); st.gmax = gm; st.push_cost = x_cost;
+            if (st.iteration == 0) {
+                st.initial_cost = x_cost;
+                st.se_min = st.se_cur = st.se_ref = st.se_cand = x_cost;
+            }
+            st.relin = 0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (st.last_success) st.n_success++;
+        st.n_iter++;
+        int cont = 1;
+        if (st.iteration >= D.max_iter) { st.term = 1; cont = 0; }
+        else if (st.last_success && st.gmax <= 1e-10) { st.term = 0; cont = 0; }
+        else if (st.radius <= 1e-32) { st.term = 0; cont = 0; }
+        if (!cont) st.done = 1;
+        else { st.iteration++; st.last_success = 0; }
+        go = cont;
+    }
+    __syncthreads();
+    if (!go) return;
+    // LM diagonal (levenberg_marquardt_strategy.cc:76-88)
+    const bool reuse = st.reuse_diagonal;
+    const double radius = st.radius;
+    __syncthreads();   // everyone has read the state before thread 0 updates it below
+    for (int i = tid; i < n; i += 256) {
+        if (!reuse) P.diagf[i] = fmin(fmax(P.nf[i] * P.scf[i] * P.scf[i], 1e-6), 1e32);
+        P.Df[i] = sqrt(P.diagf[i] / radius);
+    }
+    for (int l = tid; l < D.nlm; l += 256) {
+        if (!reuse) P.diage[l] = fmin(fmax(P.ne[l] * P.sce[l] * P.sce[l], 1e-6), 1e32);
+        P.De[l] = sqrt(P.diage[l] / radius);
+    }
+    for (int i = tid; i < NMAX * NMAX; i += 256) P.S[i] = 0;
+    for (int i = tid; i < NMAX; i += 256) P.rhs[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) P.S[i * NMAX + i] = P.Df[i] * P.Df[i];
+    if (tid == 0) st.reuse_diagonal = 1;
+}
+
+// ------------------------------------------------------------------------------------------ Schur (thread / landmark)
+// S += F'F - (E'F)'(E'E + D^2)^-1 (E'F),  rhs += F'b - (E'F)'(E'E + D^2)^-1 E'b  for this landmark's rows
+__global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    if (P.st->done) return;
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= D.nlm) return;
+    const int b = P.lm_start[l], e = P.lm_start[l + 1];
+    if (e == b) return;
+    const int ca = P.pose_col[P.anch_kf[l]];
+    const double sce = P.sce[l];
+    double ete = P.De[l] * P.De[l], etb = 0, wa[6] = {0, 0, 0, 0, 0, 0};
+    double sca[6];
+    for (int c = 0; c < 6; c++) sca[c] = ca >= 0 ? P.scf[ca + c] : 0.0;
+    double Saa[36];
+    for (int i = 0; i < 36; i++) Saa[i] = 0;
+    double rha[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = b; i < e; i++) {
+        const int o = P.lm_obs[i];
+        const int cp = P.pose_col[P.obs_kf[o]];
+        const double e0 = P.Jd[2 * o] * sce, e1 = P.Jd[2 * o + 1] * sce;
+        const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
+        ete += e0 * e0 + e1 * e1;
+        etb += e0 * r0 + e1 * r1;
+        double Fa[12], Fp[12];
+        for (int c = 0; c < 6; c++) {
+            Fa[c] = P.Ja[12 * o + c] * sca[c]; Fa[6 + c] = P.Ja[12 * o + 6 + c] * sca[c];
+            const double s = cp >= 0 ? P.scf[cp + c] : 0.0;
+            Fp[c] = P.Jp[12 * o + c] * s; Fp[6 + c] = P.Jp[12 * o + 6 + c] * s;
+        }
+        for (int c = 0; c < 6; c++) {
+            wa[c] += e0 * Fa[c] + e1 * Fa[6 + c];
+            P.wp[6 * o + c] = e0 * Fp[c] + e1 * Fp[6 + c];
+            rha[c] += Fa[c] * r0 + Fa[6 + c] * r1;
+        }
+        if (ca >= 0)
+            for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 6; c++) Saa[6 * a + c] += Fa[a] * Fa[c] + Fa[6 + a] * Fa[6 + c];
+        if (cp >= 0) {
+            for (int a = 0; a < 6; a++) {
+                atomicAdd(&P.rhs[cp + a], Fp[a] * r0 + Fp[6 + a] * r1);
+                for (int c = 0; c < 6; c++) {
+                    atomicAdd(&P.S[(cp + a) * NMAX + cp + c], Fp[a] * Fp[c] + Fp[6 + a] * Fp[6 + c]);
+                    if (ca >= 0) {
+                        const double x = Fa[a] * Fp[c] + Fa[6 + a] * Fp[6 + c];   // (anchor row a, observer col c)
+                        atomicAdd(&P.S[(ca + a) * NMAX + cp + c], x);
+                        atomicAdd(&P.S[(cp + c) * NMAX + ca + a], x);
+                    }
+                }
+            }
+        }
+    }
+    const double inv = 1.0 / ete;
+    P.ete[l] = ete;
+    P.etb[l] = etb;
+    for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
+    if (ca >= 0)
+        for (int a = 0; a < 6; a++) {
+            atomicAdd(&P.rhs[ca + a], rha[a] - wa[a] * inv * etb);
+            for (int c = 0; c < 6; c++) atomicAdd(&P.S[(ca + a) * NMAX + ca + c], Saa[6 * a + c] - wa[a] * inv * wa[c]);
+        }
+    // - w w' / ete over (observer, observer) and (anchor, observer) pairs
+    for (int i = b; i < e; i++) {
+        const int oi = P.lm_obs[i];
+        const int ci = P.pose_col[P.obs_kf[oi]];
+        if (ci < 0) continue;
+        double wi[6];
+        for (int c = 0; c < 6; c++) wi[c] = P.wp[6 * oi + c];
+        for (int a = 0; a < 6; a++) atomicAdd(&P.rhs[ci + a], -wi[a] * inv * etb);
+        if (ca >= 0)
+            for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 6; c++) {
+                    const double x = -wa[a] * inv * wi[c];
+                    atomicAdd(&P.S[(ca + a) * NMAX + ci + c], x);
+                    atomicAdd(&P.S[(ci + c) * NMAX + ca + a], x);
+                }
+        for (int j = b; j < e; j++) {
+            const int oj = P.lm_obs[j];
+            const int cj = P.pose_col[P.obs_kf[oj]];
+            if (cj < 0) continue;
+            for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 6; c++) atomicAdd(&P.S[(ci + a) * NMAX + cj + c], -wi[a] * inv * P.wp[6 * oj + c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ solve (1 CTA / problem)
+// dense Cholesky of the reduced camera system in shared memory, triangular solves, back-substitution of the inverse
+// depths, model cost change -(J s)'(r + J s / 2), candidate point Plus(x, delta).
+__global__ void __launch_bounds__(256) ba_solve_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    extern __shared__ double sm[];
+    const BaProblem P = probs[blockIdx.x];
+    BaState& st = *P.st;
+    if (st.done) return;
+    const int n = st.ncols, tid = threadIdx.x;
+    const int ld = n + 1;   // padded leading dimension (bank conflicts)
+    double* L = sm;                 // n x ld
+    double* y = sm + (size_t)NMAX * (NMAX + 1);   // n
+    double* red = y + NMAX;         // 256
+    __shared__ int ok_s;
+    for (int i = tid; i < n * n; i += 256) { const int r = i / n, c = i - r * n; L[r * ld + c] = P.S[r * NMAX + c]; }
+    if (tid == 0) ok_s = 1;
+    __syncthreads();
+    for (int j = 0; j < n; j++) {
+        // column j: L[j][j] = sqrt(A[j][j]) (the trailing updates below have already been applied)
+        if (tid == 0) {
+            const double d = L[j * ld + j];
+            if (!(d > 0)) ok_s = 0;
+            L[j * ld + j] = sqrt(d > 0 ? d : 1.0);
+        }
+        __syncthreads();
+        const double djj = L[j * ld + j];
+        for (int i = j + 1 + tid; i < n; i += 256) L[i * ld + j] /= djj;
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][k] -= L[i][j] * L[k][j], j < k <= i
+        const int m = n - j - 1;
+        for (int t = tid; t < m * m; t += 256) {
+            const int i = j + 1 + t / m, k = j + 1 + t % m;
+            if (k <= i) L[i * ld + k] -= L[i * ld + j] * L[k * ld + j];
+        }
+        __syncthreads();
+    }
+    // forward / backward substitution by warp 0 (lane-strided dot products)
+    if (tid < 32) {
+        for (int i = 0; i < n; i++) {
+            double s = 0;
+            for (int k = tid; k < i; k += 32) s += L[i * ld + k] * y[k];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (tid == 0) y[i] = (P.rhs[i] - s) / L[i * ld + i];
+            __syncwarp();
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double s = 0;
+            for (int k = i + 1 + tid; k < n; k += 32) s += L[k * ld + i] * y[k];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (tid == 0) y[i] = (y[i] - s) / L[i * ld + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const bool ok = ok_s != 0;
+    for (int i = tid; i < n; i += 256) P.yf[i] = y[i];
+    // back-substitute the inverse depths: ye = (E'b - E'F yf) / (E'E + D^2)
+    for (int l = tid; l < D.nlm; l += 256) {
+        const int b = P.lm_start[l], e = P.lm_start[l + 1];
+        if (e == b) { P.ye[l] = 0; continue; }
+        double s = P.etb[l];
+        const int ca = P.pose_col[P.anch_kf[l]];
+        if (ca >= 0) for (int c = 0; c < 6; c++) s -= P.wa[6 * l + c] * y[ca + c];
+        for (int i = b; i < e; i++) {
+            const int o = P.lm_obs[i];
+            const int cp = P.pose_col[P.obs_kf[o]];
+            if (cp >= 0) for (int c = 0; c < 6; c++) s -= P.wp[6 * o + c] * y[cp + c];
+        }
+        P.ye[l] = s / P.ete[l];
+    }
+    __syncthreads();
+    // model cost change with step = -y (scaled coordinates)
+    double acc = 0;
+    for (int o = tid; o < D.nobs; o += 256) {
+        const int l = P.obs_lm[o];
+        if (l < 0) continue;
+        const int ca = P.pose_col[P.anch_kf[l]], cp = P.pose_col[P.obs_kf[o]];
+        const double se = -P.ye[l] * P.sce[l];
+        double m0 = P.Jd[2 * o] * se, m1 = P.Jd[2 * o + 1] * se;
+        for (int c = 0; c < 6; c++) {
+            if (ca >= 0) { const double s = -y[ca + c] * P.scf[ca + c]; m0 += P.Ja[12 * o + c] * s; m1 += P.Ja[12 * o + 6 + c] * s; }
+            if (cp >= 0) { const double s = -y[cp + c] * P.scf[cp + c]; m0 += P.Jp[12 * o + c] * s; m1 += P.Jp[12 * o + 6 + c] * s; }
+        }
+        acc += m0 * (P.res[2 * o] + m0 / 2.0) + m1 * (P.res[2 * o + 1] + m1 / 2.0);
+    }
+    const double tot = block_sum<256>(acc, red);
+    const double model_change = -tot;
+    const bool valid = ok && (model_change > 0.0);
+    // candidate point
+    if (valid) {
+        for (int k = tid; k < D.nkf; k += 256) {
+            const int c0 = P.pose_col[k];
+            if (c0 >= 0) {
+                double dlt[6];
+                for (int i = 0; i < 6; i++) dlt[i] = -y[c0 + i] * P.scf[c0 + i];
+                se3_plus(P.poses + 7 * k, dlt, P.cand_poses + 7 * k);
+            } else
+                for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = P.poses[7 * k + i];
+        }
+        for (int l = tid; l < D.nlm; l += 256)
+            P.cand_invd[l] = P.invd[l] + ((P.lm_start[l + 1] > P.lm_start[l]) ? -P.ye[l] * P.sce[l] : 0.0);
+    }
+    if (tid == 0) { st.model_change = model_change; st.step_ok = valid ? 1 : 0; }
+}
+
+// ------------------------------------------------------------------------------------------ control: after the step
+__global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    BaState& st = *P.st;
+    __shared__ double red[256];
+    __shared__ int accept_s;
+    const int tid = threadIdx.x;
+    if (st.done) return;
+    if (!st.step_ok) {   // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
+        if (tid == 0) {
+            if (++st.invalid_steps >= 5) { st.term = 2; st.done = 1; }
+            st.radius *= 0.5;
+            st.reuse_diagonal = 1;
+            st.push_cost = st.x_cost;
+        }
+        return;
+    }
+    double c = 0;
+    for (int i = tid; i < D.nblk; i += 256) c += P.cost_part[i];
+    const double cand_cost = block_sum<256>(c, red);
+    double sn = 0;
+    for (int k = tid; k < D.nkf; k += 256)
+        if (P.pose_col[k] >= 0)
+            for (int i = 0; i < 7; i++) { const double d = P.poses[7 * k + i] - P.cand_poses[7 * k + i]; sn += d * d; }
+    for (int l = tid; l < D.nlm; l += 256)
+        if (P.lm_start[l + 1] > P.lm_start[l]) { const double d = P.invd[l] - P.cand_invd[l]; sn += d * d; }
+    __syncthreads();
+    sn = block_sum<256>(sn, red);
+    if (tid == 0) {
+        int accept = 0;
+        st.invalid_steps = 0;
+        st.cand_cost = cand_cost;
+        const double step_norm = sqrt(sn);
+        if (step_norm <= 1e-8 * (st.xnorm + 1e-8)) { st.term = 0; st.done = 1; }                 // ParameterToleranceReached
+        else if (fabs(st.x_cost - cand_cost) <= 1e-3 * st.x_cost) { st.term = 0; st.done = 1; }  // FunctionToleranceReached
+        else {
+            const double mc = st.model_change;
+            const double rel = (st.se_cur - cand_cost) / mc;
+            const double hist = (st.se_ref - cand_cost) / (st.se_acc_ref + mc);
+            const double quality = fmax(rel, hist);
+            if (quality > 1e-3) {
+                accept = 1;
+                st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * quality - 1.0, 3)));
+                st.decrease_factor = 2.0;
+                st.reuse_diagonal = 0;
+                st.se_cur = cand_cost; st.se_acc_cand += mc; st.se_acc_ref += mc;
+                bool nonmono = false;
+                if (st.se_cur < st.se_min) { st.se_min = st.se_cur; st.se_cand = st.se_cur; st.se_acc_cand = 0; }
+                else { nonmono = true; if (st.se_cur > st.se_cand) { st.se_cand = st.se_cur; st.se_acc_cand = 0; } }
+                if (!nonmono) { st.se_ref = st.se_cand; st.se_acc_ref = st.se_acc_cand; }
+                st.last_success = 1;
+                st.relin = 1;
+            } else {
+                st.radius = st.radius / st.decrease_factor;
+                st.decrease_factor *= 2.0;
+                st.reuse_diagonal = 1;
+                st.push_cost = cand_cost;
+            }
+        }
+        accept_s = accept;
+    }
+    __syncthreads();
+    if (accept_s) {
+        for (int i = tid; i < 7 * D.nkf; i += 256) P.poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += 256) P.invd[l] = P.cand_invd[l];
+        for (int i = tid; i < NMAX; i += 256) { P.nf[i] = 0; P.gf[i] = 0; }
+        for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; }
+    }
+}
+
+// kernel-level dump of the linearisation (corrected residuals and local Jacobians) for parity tests
+__global__ void ba_linearize_dump_kernel(const double* calib, const double* poses, const double* invd, const int32_t* anch_kf,
+                                         const double* anch_uv, const int32_t* obs_kf, const int32_t* obs_lm,
+                                         const double* obs_uv, int nobs, double hub, double* res, double* Ja, double* Jp,
+                                         double* Jd, double* cost) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nobs) return;
+    const int l = obs_lm[o];
+    double r[2] = {0, 0}, A[12], Pp[12], Dd[2];
+    for (int i = 0; i < 12; i++) A[i] = Pp[i] = 0;
+    Dd[0] = Dd[1] = 0;
+    double c = 0;
+    if (l >= 0) {
+        ba_evaluate(calib, poses + 7 * anch_kf[l], poses + 7 * obs_kf[o], invd[l], obs_uv[2 * o], obs_uv[2 * o + 1],
+                    anch_uv[2 * l], anch_uv[2 * l + 1], r, A, Pp, Dd);
+        double rho0, rho1;
+        huber(r[0] * r[0] + r[1] * r[1], hub, rho0, rho1);
+        c = 0.5 * rho0;
+        const double sc = sqrt(rho1);
+        r[0] *= sc; r[1] *= sc; Dd[0] *= sc; Dd[1] *= sc;
+        for (int i = 0; i < 12; i++) { A[i] *= sc; Pp[i] *= sc; }
+    }
+    res[2 * o] = r[0]; res[2 * o + 1] = r[1]; Jd[2 * o] = Dd[0]; Jd[2 * o + 1] = Dd[1];
+    for (int i = 0; i < 12; i++) { Ja[12 * o + i] = A[i]; Jp[12 * o + i] = Pp[i]; }
+    cost[o] = c;
+}
+
+__global__ void ba_summary_kernel(const BaProblem* __restrict__ probs, double* __restrict__ summary) {
+    const BaState& st = *probs[blockIdx.x].st;
+    if (threadIdx.x == 0) {
+        double* s = summary + 8 * blockIdx.x;
+        s[0] = st.initial_cost; s[1] = st.x_cost; s[2] = st.n_success; s[3] = st.n_iter; s[4] = st.term;
+        s[5] = st.ncols; s[6] = st.radius; s[7] = st.iteration;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// Workspace carving: one contiguous block per problem.
+static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
+    size_t d = 0;
+    d += (size_t)nobs * (2 + 12 + 12 + 2 + 6);      // res, Ja, Jp, Jd, wp
+    d += 5 * (size_t)NMAX;                           // nf gf scf diagf Df
+    d += 5 * (size_t)nlm;                            // ne ge sce diage De
+    d += (size_t)nlm * (1 + 1 + 6 + 1);              // ete etb wa ye
+    d += (size_t)NMAX * NMAX + 2 * NMAX;             // S rhs yf
+    d += (size_t)nkf * 7 + nlm;                      // cand
+    d += (size_t)nblk;                               // cost partials
+    size_t bytes = d * sizeof(double);
+    bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
+    bytes += align_up(sizeof(BaState), 8);
+    return align_up(bytes, 256);
+}
+
+extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                               const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                               const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
+                               int max_iter, double* summary) {
+    if (!ctx || nprob < 1 || nkf < 1 || nkf > 256 || nlm < 1 || nobs < 1 || !calib || !poses || !pose_const || !invd ||
+        !anch_kf || !anch_uv || !obs_kf || !obs_lm || !obs_uv || max_iter < 0) {
+        alva_set_error("alva_k_ba_solve: bad argument (need 1 <= nkf <= 256)");
+        return ALVA_E_INVALID;
+    }
+    const int nblk = (nobs + LIN_THREADS - 1) / LIN_THREADS;
+    const size_t per = ba_ws_bytes(nkf, nlm, nobs, nblk);
+    const size_t tab = align_up(sizeof(BaProblem) * nprob, 256);
+    uint8_t* ws = (uint8_t*)alva_scratch(ctx, tab + per * nprob);
+    if (!ws) return ALVA_E_CUDA;
+    // the (small) table of per-problem pointers is built on the host and copied once per call
+    std::string hostbuf(sizeof(BaProblem) * nprob, '\0');
+    BaProblem* hp = reinterpret_cast<BaProblem*>(&hostbuf[0]);
+    for (int p = 0; p < nprob; p++) {
+        BaProblem& P = hp[p];
+        P.calib = calib + 4 * (size_t)p; P.poses = poses + 7 * (size_t)nkf * p; P.pose_const = pose_const + (size_t)nkf * p;
+        P.invd = invd + (size_t)nlm * p; P.anch_kf = anch_kf + (size_t)nlm * p; P.anch_uv = anch_uv + 2 * (size_t)nlm * p;
+        P.obs_kf = obs_kf + (size_t)nobs * p; P.obs_lm = obs_lm + (size_t)nobs * p; P.obs_uv = obs_uv + 2 * (size_t)nobs * p;
+        double* d = reinterpret_cast<double*>(ws + tab + per * p);
+        auto take = [&](size_t n) { double* r = d; d += n; return r; };
+        P.res = take(2 * (size_t)nobs); P.Ja = take(12 * (size_t)nobs); P.Jp = take(12 * (size_t)nobs); P.Jd = take(2 * (size_t)nobs);
+        P.wp = take(6 * (size_t)nobs);
+        P.nf = take(NMAX); P.gf = take(NMAX); P.scf = take(NMAX); P.diagf = take(NMAX); P.Df = take(NMAX);
+        P.ne = take(nlm); P.ge = take(nlm); P.sce = take(nlm); P.diage = take(nlm); P.De = take(nlm);
+        P.ete = take(nlm); P.etb = take(nlm); P.wa = take(6 * (size_t)nlm); P.ye = take(nlm);
+        P.S = take((size_t)NMAX * NMAX); P.rhs = take(NMAX); P.yf = take(NMAX);
+        P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
+        uint8_t* b = reinterpret_cast<uint8_t*>(d);
+        P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
+        P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
+        P.lm_obs = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
+        P.st = reinterpret_cast<BaState*>(b);
+    }
+    ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
+    ALVA_CUDA(cudaStreamSynchronize(ctx->stream));   // hostbuf is pageable: make the copy complete before it dies
+    const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
+    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter};
+    const size_t solve_smem = ((size_t)NMAX * (NMAX + 1) + NMAX + 256) * sizeof(double);
+    ALVA_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    ba_setup_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+    ALVA_LAUNCH_CHECK(ctx);
+    const dim3 lin_grid(nblk, nprob), schur_grid((nlm + 127) / 128, nprob);
+    for (int it = 0; it <= max_iter; it++) {
+        ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_pre_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        if (it == max_iter) break;   // the last pass only finalises (iteration count reached)
+        ba_schur_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_solve_kernel<<<nprob, 256, solve_smem, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_linearize_kernel<false><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_post_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+    }
+    if (summary) {
+        ba_summary_kernel<<<nprob, 32, 0, ctx->stream>>>(dp, summary);
+        ALVA_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, const double* calib, const double* poses,
+                                   const double* invd, const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf,
+                                   const int32_t* obs_lm, const double* obs_uv, double huber_delta, double* res, double* Ja,
+                                   double* Jp, double* Jd, double* cost_per_obs) {
+    if (!ctx || nobs < 1 || !calib || !poses || !invd || !res || !Ja || !Jp || !Jd || !cost_per_obs) {
+        alva_set_error("alva_k_ba_linearize: bad argument");
+        return ALVA_E_INVALID;
+    }
+    (void)nkf; (void)nlm;
+    ba_linearize_dump_kernel<<<(nobs + 127) / 128, 128, 0, ctx->stream>>>(calib, poses, invd, anch_kf, anch_uv, obs_kf, obs_lm,
+                                                                         obs_uv, nobs, huber_delta, res, Ja, Jp, Jd, cost_per_obs);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}

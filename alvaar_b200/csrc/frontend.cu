@@ -589,6 +589,12 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     return 0;
 }
 
+// the fused launch alone (pipeline.cu brackets it with CUDA events for the roofline measurement)
+int alva_frontend_main_launch(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1, int thr,
+                              uint32_t* keys, int32_t* counts, int cap) {
+    return launch_frontend(ctx, true, rgba, w, h, nframes, l0, l1, thr, keys, counts, cap);
+}
+
 static int launch_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) {
     const int dw = (w + 1) / 2, dh = (h + 1) / 2;
     dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, nframes);

@@ -26,11 +26,15 @@ __device__ __forceinline__ void top2_insert(uint32_t& k0, uint32_t& k1, uint32_t
     }
 }
 
+// counts != nullptr: the queries are [nbatch][qcap] slots of which only the first counts[b] are live; warps that hold
+// no live query leave immediately (their partials are never read).
 __global__ void __launch_bounds__(WPC * 32) knn2_partial_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
-                                                                int nt, uint2* __restrict__ partial, int nchunks) {
+                                                                int nt, uint2* __restrict__ partial, int nchunks,
+                                                                const int32_t* __restrict__ counts, int qcap) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = (blockIdx.x * WPC + warp) * QPW;
     if (q0 >= nq) return;
+    if (counts) { const int b = q0 / qcap; if (q0 - b * qcap >= counts[b]) return; }
     const int chunk = blockIdx.y;
     const int tb = chunk * CHUNK, te = min(nt, tb + CHUNK);
     uint4 qa[QPW], qb[QPW];
@@ -67,11 +71,14 @@ __global__ void __launch_bounds__(WPC * 32) knn2_partial_kernel(const uint4* __r
     }
 }
 
-__global__ void knn2_merge_kernel(const uint2* __restrict__ partial, int nq, int nchunks, int32_t* __restrict__ out) {
+__global__ void knn2_merge_kernel(const uint2* __restrict__ partial, int nq, int nchunks, int32_t* __restrict__ out,
+                                  const int32_t* __restrict__ counts, int qcap) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     uint32_t k0 = NONE, k1 = NONE;
-    for (int c = 0; c < nchunks; c++) {
+    bool live = true;
+    if (counts) { const int b = qi / qcap; live = (qi - b * qcap) < counts[b]; }
+    for (int c = 0; live && c < nchunks; c++) {
         const uint2 p = partial[(size_t)qi * nchunks + c];
         top2_insert(k0, k1, p.x);
         top2_insert(k0, k1, p.y);
@@ -96,9 +103,28 @@ extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, cons
     uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
     if (!partial) return ALVA_E_CUDA;
     dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
-    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks);
+    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, nullptr, 0);
     ALVA_LAUNCH_CHECK(ctx);
-    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out);
+    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, nullptr, 0);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int alva_k_hamming_knn2_batch(alva_ctx* ctx, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
+                                         const uint8_t* t, int nt, int32_t* out) {
+    if (!ctx || !q || !counts || !t || !out || nbatch < 1 || qcap < 1 || (qcap % QPW) != 0 || nt < 1 || nt >= (1 << 22) ||
+        ((uintptr_t)q & 15) || ((uintptr_t)t & 15) || ((uintptr_t)out & 15)) {
+        alva_set_error("alva_k_hamming_knn2_batch: bad argument (qcap must be a multiple of %d)", QPW);
+        return ALVA_E_INVALID;
+    }
+    const int nq = nbatch * qcap;
+    const int nchunks = (nt + CHUNK - 1) / CHUNK;
+    uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
+    if (!partial) return ALVA_E_CUDA;
+    dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
+    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, counts, qcap);
+    ALVA_LAUNCH_CHECK(ctx);
+    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
 }

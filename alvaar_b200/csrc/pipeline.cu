@@ -1,0 +1,255 @@
+// pipeline.cu -- the per-frame hot path as ONE object: a batch of RGBA frames goes through
+//   gray + Gaussian pyramid + FAST-9/NMS  ->  retainBest(nfeatures)  ->  ORB (blur + IC angle + rBRIEF-256)
+//   ->  brute-force Hamming 2-NN against the local map's descriptors  ->  (every kf_interval-th frame) local BA
+// with every intermediate resident in HBM and no host synchronisation inside a step.  This is what the reference does
+// per frame / per keyframe on the CPU (System::findCameraPose -> VisualFrontend::track ->
+// MapManager::createKeyframe -> Mapper::matchingToLocalMap -> Optimizer::localBA), restated for the north-star
+// feature front end; `System` (system.cu) drives it one frame at a time, bench.py drives it in batches.
+#include "alva_common.cuh"
+#include "../../include/alva_b200.h"
+#include <vector>
+
+// stage entry points implemented in the other translation units
+extern "C" int alva_k_hamming_knn2_batch(alva_ctx*, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
+                                         const uint8_t* t, int nt, int32_t* out);
+
+namespace {
+
+__global__ void keys_to_points_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ counts, int cap,
+                                      float* __restrict__ pts) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const int n = min(counts[f], cap);
+    float2 p = make_float2(0.f, 0.f);
+    if (i < n) {
+        const uint32_t k = keys[(size_t)f * cap + i];
+        p = make_float2((float)ALVA_KEY_X(k), (float)ALVA_KEY_Y(k));
+    }
+    reinterpret_cast<float2*>(pts)[(size_t)f * cap + i] = p;
+}
+
+__global__ void clamp_counts_kernel(int32_t* counts, int n, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = min(counts[i], cap);
+}
+
+}  // namespace
+
+struct alva_pipeline {
+    alva_ctx* ctx = nullptr;
+    alva_pipeline_config cfg{};
+    int w1, h1, w2, h2, w3, h3;
+    int kcap = 32768;   // raw FAST corners per frame
+    int fcap = 0;       // selected features per frame (slots)
+    int nprob = 0;      // BA problems per step
+    // device buffers
+    uint8_t *l0 = nullptr, *l1 = nullptr, *l2 = nullptr, *l3 = nullptr, *blur = nullptr;
+    uint32_t *keys = nullptr, *sel = nullptr;
+    int32_t *counts = nullptr, *selcounts = nullptr;
+    float *pts = nullptr, *angles = nullptr;
+    uint8_t *desc = nullptr, *kept = nullptr, *map = nullptr;
+    int32_t* matches = nullptr;
+    // BA batch: pristine copies + working copies
+    double *ba_calib = nullptr, *ba_poses0 = nullptr, *ba_poses = nullptr, *ba_invd0 = nullptr, *ba_invd = nullptr,
+           *ba_anch_uv = nullptr, *ba_obs_uv = nullptr, *ba_summary = nullptr;
+    uint8_t* ba_const = nullptr;
+    int32_t *ba_anch_kf = nullptr, *ba_obs_kf = nullptr, *ba_obs_lm = nullptr;
+    bool have_map = false, have_ba = false;
+    // host-step staging
+    uint8_t* in_dev = nullptr;
+    static constexpr int NEV = 64;      // ring of event pairs around the fused front-end launch
+    cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
+    bool profile = false;
+    long long step_index = 0;
+    std::vector<void*> allocs;
+};
+
+static int palloc(alva_pipeline* p, void** ptr, size_t bytes) {
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { alva_set_error("pipeline cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return ALVA_E_CUDA; }
+    p->allocs.push_back(*ptr);
+    return 0;
+}
+#define PALLOC(field, bytes) do { if (int e_ = palloc(p, (void**)&p->field, (bytes))) { alva_pipeline_destroy(p); return nullptr; } } while (0)
+
+extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
+    if (!p) return;
+    cudaStreamSynchronize(p->ctx->stream);
+    for (void* a : p->allocs) cudaFree(a);
+    for (int i = 0; i < alva_pipeline::NEV; i++) {
+        if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
+        if (p->ev1[i]) cudaEventDestroy(p->ev1[i]);
+    }
+    delete p;
+}
+
+extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipeline_config* cfg) {
+    if (!ctx || !cfg || cfg->batch < 1 || cfg->w < 64 || cfg->h < 64 || cfg->w > ALVA_MAX_DIM || cfg->h > ALVA_MAX_DIM ||
+        cfg->nfeatures < 1 || cfg->map_size < 0 || cfg->kf_interval < 0) {
+        alva_set_error("alva_pipeline_create: bad configuration");
+        return nullptr;
+    }
+    alva_pipeline* p = new alva_pipeline();
+    p->ctx = ctx;
+    p->cfg = *cfg;
+    const int w = cfg->w, h = cfg->h, B = cfg->batch;
+    p->w1 = (w + 1) / 2; p->h1 = (h + 1) / 2; p->w2 = (p->w1 + 1) / 2; p->h2 = (p->h1 + 1) / 2;
+    p->w3 = (p->w2 + 1) / 2; p->h3 = (p->h2 + 1) / 2;
+    p->fcap = ((cfg->nfeatures + cfg->nfeatures / 2 + 63) / 64) * 64;   // retainBest keeps ties: 1.5x head-room
+    p->kcap = (w * h) / 16 > 32768 ? (w * h) / 16 : 32768;
+    p->nprob = cfg->kf_interval > 0 ? (B + cfg->kf_interval - 1) / cfg->kf_interval : 0;
+    PALLOC(l0, (size_t)B * w * h); PALLOC(l1, (size_t)B * p->w1 * p->h1); PALLOC(l2, (size_t)B * p->w2 * p->h2);
+    PALLOC(l3, (size_t)B * p->w3 * p->h3); PALLOC(blur, (size_t)B * w * h);
+    PALLOC(keys, (size_t)B * p->kcap * 4); PALLOC(counts, (size_t)B * 4);
+    PALLOC(sel, (size_t)B * p->fcap * 4); PALLOC(selcounts, (size_t)B * 4);
+    PALLOC(pts, (size_t)B * p->fcap * 8); PALLOC(angles, (size_t)B * p->fcap * 4);
+    PALLOC(desc, (size_t)B * p->fcap * 32); PALLOC(kept, (size_t)B * p->fcap);
+    PALLOC(matches, (size_t)B * p->fcap * 16);
+    PALLOC(map, (size_t)(cfg->map_size > 0 ? cfg->map_size : 1) * 32);
+    if (p->nprob > 0) {
+        const size_t np = p->nprob, nkf = cfg->ba_nkf, nlm = cfg->ba_nlm, nobs = cfg->ba_nobs;
+        if (nkf < 1 || nlm < 1 || nobs < 1) { alva_set_error("alva_pipeline_create: BA dimensions missing"); alva_pipeline_destroy(p); return nullptr; }
+        PALLOC(ba_calib, np * 4 * 8); PALLOC(ba_poses0, np * nkf * 7 * 8); PALLOC(ba_poses, np * nkf * 7 * 8);
+        PALLOC(ba_invd0, np * nlm * 8); PALLOC(ba_invd, np * nlm * 8); PALLOC(ba_anch_uv, np * nlm * 16);
+        PALLOC(ba_obs_uv, np * nobs * 16); PALLOC(ba_summary, np * 8 * 8); PALLOC(ba_const, np * nkf);
+        PALLOC(ba_anch_kf, np * nlm * 4); PALLOC(ba_obs_kf, np * nobs * 4); PALLOC(ba_obs_lm, np * nobs * 4);
+    }
+    for (int i = 0; i < alva_pipeline::NEV; i++)
+        if (cudaEventCreate(&p->ev0[i]) != cudaSuccess || cudaEventCreate(&p->ev1[i]) != cudaSuccess) {
+            alva_set_error("cudaEventCreate failed");
+            alva_pipeline_destroy(p);
+            return nullptr;
+        }
+    return p;
+}
+
+extern "C" int alva_pipeline_set_map(alva_pipeline* p, const uint8_t* desc_host, int n) {
+    if (!p || !desc_host || n != p->cfg.map_size) { alva_set_error("alva_pipeline_set_map: need exactly map_size descriptors"); return ALVA_E_INVALID; }
+    ALVA_CUDA(cudaMemcpyAsync(p->map, desc_host, (size_t)n * 32, cudaMemcpyHostToDevice, p->ctx->stream));
+    ALVA_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    p->have_map = true;
+    return 0;
+}
+
+// One BA problem (host arrays, layout of alva_k_ba_solve) replicated into slot `slot` of the per-step BA batch.
+extern "C" int alva_pipeline_set_ba(alva_pipeline* p, int slot, const double* calib, const double* poses, const uint8_t* pose_const,
+                                    const double* invd, const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf,
+                                    const int32_t* obs_lm, const double* obs_uv) {
+    if (!p || slot < 0 || slot >= p->nprob) { alva_set_error("alva_pipeline_set_ba: bad slot"); return ALVA_E_INVALID; }
+    const size_t nkf = p->cfg.ba_nkf, nlm = p->cfg.ba_nlm, nobs = p->cfg.ba_nobs, s = slot;
+    cudaStream_t st = p->ctx->stream;
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_calib + 4 * s, calib, 32, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_poses0 + nkf * 7 * s, poses, nkf * 56, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_const + nkf * s, pose_const, nkf, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_invd0 + nlm * s, invd, nlm * 8, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_anch_kf + nlm * s, anch_kf, nlm * 4, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_anch_uv + 2 * nlm * s, anch_uv, nlm * 16, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_obs_kf + nobs * s, obs_kf, nobs * 4, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_obs_lm + nobs * s, obs_lm, nobs * 4, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_obs_uv + 2 * nobs * s, obs_uv, nobs * 16, cudaMemcpyHostToDevice, st));
+    ALVA_CUDA(cudaStreamSynchronize(st));
+    if (slot == p->nprob - 1) p->have_ba = true;
+    return 0;
+}
+
+extern "C" int alva_pipeline_profile(alva_pipeline* p, int enable) {
+    if (!p) return ALVA_E_INVALID;
+    p->profile = enable != 0;
+    p->step_index = 0;
+    return 0;
+}
+
+// Durations (ms) of the fused front-end launch (gray + pyramid L1 + FAST) of the last min(n, steps, 64) steps since
+// profiling was enabled, measured with CUDA events on the launch stream.  Returns how many were written.
+extern "C" int alva_pipeline_frontend_ms(alva_pipeline* p, float* ms, int n) {
+    if (!p || !ms || !p->profile) { alva_set_error("profiling not enabled"); return ALVA_E_STATE; }
+    ALVA_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    const long long have = p->step_index < alva_pipeline::NEV ? p->step_index : alva_pipeline::NEV;
+    const int m = n < have ? n : (int)have;
+    for (int i = 0; i < m; i++) {
+        const int slot = (int)((p->step_index - 1 - i) % alva_pipeline::NEV);
+        ALVA_CUDA(cudaEventElapsedTime(&ms[i], p->ev0[slot], p->ev1[slot]));
+    }
+    return m;
+}
+
+// defined in frontend.cu: the fused launch alone (so the events bracket exactly the dominant kernel)
+int alva_frontend_main_launch(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1, int thr,
+                              uint32_t* keys, int32_t* counts, int cap);
+
+extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) {
+    if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
+    if (p->cfg.map_size > 0 && !p->have_map) { alva_set_error("pipeline: local map not set"); return ALVA_E_STATE; }
+    if (p->nprob > 0 && !p->have_ba) { alva_set_error("pipeline: BA problems not set"); return ALVA_E_STATE; }
+    alva_ctx* ctx = p->ctx;
+    const alva_pipeline_config& c = p->cfg;
+    const int B = c.batch, w = c.w, h = c.h;
+    cudaStream_t st = ctx->stream;
+    // 1. fused front end (+ pyramid levels 2, 3)
+    ALVA_CUDA(cudaMemsetAsync(p->counts, 0, sizeof(int32_t) * B, st));
+    const int slot = (int)(p->step_index % alva_pipeline::NEV);
+    if (p->profile) ALVA_CUDA(cudaEventRecord(p->ev0[slot], st));
+    if (int e = alva_frontend_main_launch(ctx, rgba_dev, w, h, B, p->l0, p->l1, c.fast_thr, p->keys, p->counts, p->kcap)) return e;
+    if (p->profile) { ALVA_CUDA(cudaEventRecord(p->ev1[slot], st)); p->step_index++; }
+    if (int e = alva_k_pyrdown(ctx, p->l1, p->l2, p->w1, p->h1, B)) return e;
+    if (int e = alva_k_pyrdown(ctx, p->l2, p->l3, p->w2, p->h2, B)) return e;
+    // 2. retainBest(nfeatures) inside ORB's 31-px border, row-major
+    if (int e = alva_k_retain_best(ctx, p->keys, p->counts, p->kcap, B, w, h, c.nfeatures, 31, p->sel, p->selcounts, p->fcap)) return e;
+    clamp_counts_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->selcounts, B, p->fcap);
+    ALVA_LAUNCH_CHECK(ctx);
+    keys_to_points_kernel<<<dim3((p->fcap + 127) / 128, B), 128, 0, st>>>(p->sel, p->selcounts, p->fcap, p->pts);
+    ALVA_LAUNCH_CHECK(ctx);
+    // 3. ORB
+    if (int e = alva_k_orb_blur(ctx, p->l0, p->blur, w, h, B, c.orb_flags & ALVA_ORB_FMA)) return e;
+    if (int e = alva_k_orb_describe(ctx, p->l0, p->blur, w, h, B, p->pts, p->selcounts, p->fcap, c.orb_flags, p->desc, p->kept, p->angles)) return e;
+    // 4. match against the local map
+    if (c.map_size > 0)
+        if (int e = alva_k_hamming_knn2_batch(ctx, p->desc, p->selcounts, B, p->fcap, p->map, c.map_size, p->matches)) return e;
+    // 5. local BA for this step's keyframes
+    if (p->nprob > 0) {
+        const size_t np = p->nprob;
+        ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
+        ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
+        if (int e = alva_k_ba_solve(ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
+                                    p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber,
+                                    c.ba_max_iter, p->ba_summary))
+            return e;
+    }
+    return 0;
+}
+
+// Host-buffer step (the e2e leg): H2D of the batch, the step, D2H of the per-frame results.
+extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
+                                       double* ba_poses_host, double* ba_summary_host) {
+    if (!p || !rgba_host) { alva_set_error("alva_pipeline_step_host: bad argument"); return ALVA_E_INVALID; }
+    const alva_pipeline_config& c = p->cfg;
+    const size_t in_bytes = (size_t)c.batch * c.w * c.h * 4;
+    if (!p->in_dev) { if (int e = palloc(p, (void**)&p->in_dev, in_bytes)) return e; }
+    cudaStream_t st = p->ctx->stream;
+    ALVA_CUDA(cudaMemcpyAsync(p->in_dev, rgba_host, in_bytes, cudaMemcpyHostToDevice, st));
+    if (int e = alva_pipeline_step_dev(p, p->in_dev)) return e;
+    if (nfeat_host) ALVA_CUDA(cudaMemcpyAsync(nfeat_host, p->selcounts, sizeof(int32_t) * c.batch, cudaMemcpyDeviceToHost, st));
+    if (matches_host && c.map_size > 0)
+        ALVA_CUDA(cudaMemcpyAsync(matches_host, p->matches, (size_t)c.batch * p->fcap * 16, cudaMemcpyDeviceToHost, st));
+    if (p->nprob > 0) {
+        if (ba_poses_host) ALVA_CUDA(cudaMemcpyAsync(ba_poses_host, p->ba_poses, (size_t)p->nprob * c.ba_nkf * 56, cudaMemcpyDeviceToHost, st));
+        if (ba_summary_host) ALVA_CUDA(cudaMemcpyAsync(ba_summary_host, p->ba_summary, (size_t)p->nprob * 64, cudaMemcpyDeviceToHost, st));
+    }
+    ALVA_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: fcap, kcap, nprob, map_size */) {
+    if (!p || !out) return ALVA_E_INVALID;
+    out[0] = p->fcap; out[1] = p->kcap; out[2] = p->nprob; out[3] = p->cfg.map_size;
+    return 0;
+}
+
+// device pointer of an intermediate (tests): 0 l0, 1 l1, 2 l2, 3 l3, 4 blur, 5 keys, 6 counts, 7 sel, 8 selcounts, 9 pts,
+// 10 angles, 11 desc, 12 kept, 13 matches, 14 ba_poses, 15 ba_invd, 16 ba_summary
+extern "C" void* alva_pipeline_buffer(alva_pipeline* p, int which) {
+    if (!p) return nullptr;
+    void* t[] = {p->l0, p->l1, p->l2, p->l3, p->blur, p->keys, p->counts, p->sel, p->selcounts, p->pts, p->angles, p->desc,
+                 p->kept, p->matches, p->ba_poses, p->ba_invd, p->ba_summary};
+    return (which >= 0 && which < 17) ? t[which] : nullptr;
+}

@@ -55,6 +55,8 @@ _OPTIONAL = {
     "alva_k_orb_describe": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "alva_k_hamming_knn2": [_vp, _vp, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
+    "alva_k_ba_solve": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i32, _vp],
+    "alva_k_ba_linearize": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp],
 }
 
 
@@ -146,3 +148,15 @@ class Context:
 
     def hamming_knn2(self, q, nq, t, nt, out):
         self._chk(self.L.alva_k_hamming_knn2(self.h, _ptr(q), nq, _ptr(t), nt, _ptr(out)))
+
+    def ba_solve(self, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv,
+                 huber, max_iter, summary=None):
+        self._chk(self.L.alva_k_ba_solve(self.h, nprob, nkf, nlm, nobs, _ptr(calib), _ptr(poses), _ptr(pose_const), _ptr(invd),
+                                         _ptr(anch_kf), _ptr(anch_uv), _ptr(obs_kf), _ptr(obs_lm), _ptr(obs_uv), huber,
+                                         max_iter, _ptr(summary)))
+
+    def ba_linearize(self, nkf, nlm, nobs, calib, poses, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, huber, res, Ja, Jp,
+                     Jd, cost):
+        self._chk(self.L.alva_k_ba_linearize(self.h, nkf, nlm, nobs, _ptr(calib), _ptr(poses), _ptr(invd), _ptr(anch_kf),
+                                             _ptr(anch_uv), _ptr(obs_kf), _ptr(obs_lm), _ptr(obs_uv), huber, _ptr(res),
+                                             _ptr(Ja), _ptr(Jp), _ptr(Jd), _ptr(cost)))

@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native per-frame visual-SLAM hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code on the host cores
+
+Metric (BASELINE.json): frames/sec @1280x720, 1000 ORB features/frame, 20-keyframe local BA; plus the achieved HBM
+bandwidth of the fused pyramid+FAST kernel against the measured copy peak (MEASURED_PEAKS.json).
+
+One "step" = one pass of the whole hot path over a batch of BATCH synthetic frames:
+  RGBA -> gray + 4-level Gaussian pyramid + FAST-9/NMS (level 0) -> retainBest(1000) -> ORB (7x7 blur, IC angle,
+  rBRIEF-256) -> brute-force Hamming 2-NN against a 10 000-descriptor local map -> one local BA
+  (20 KF x 3000 landmarks x 12 000 observations, LM <= 5 it, Huber, Schur) per KF_INTERVAL frames.
+`value`  : inputs already resident in HBM when the timed region starts (CUDA events, max over ranks).
+`e2e`    : the same step through the host-buffer C-ABI call (alva_pipeline_step_host): pinned host RGBA in,
+           per-frame feature counts + matches + BA poses back out, copies inside the timed region.
+Multi-GPU: independent camera streams shard one-per-GPU (weak scaling, no data-path collective).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1280, 720
+BATCH = 64            # frames per step: 64 x 3.69 MB RGBA = 236 MB per step, larger than the 126 MB L2
+NFEAT = 1000
+MAP_SIZE = 10000
+KF_INTERVAL = 5
+BA_NKF, BA_NLM, BA_OBS_PER_LM, BA_ITERS = 20, 3000, 4, 5
+FAST_THR = 20
+# algorithmic bytes of the fused front-end kernel per frame: RGBA read once + gray + L1 written once
+ALGO_BYTES_FRONTEND = 4 * W * H + W * H + ((W + 1) // 2) * ((H + 1) // 2)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.maxclk = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.maxclk = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.maxclk,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def load_cpu_impl():
+    """oracle/_ref (the reference's own vendored OpenCV 4.5.5 + Ceres 2.0 build) if it travelled here, else the
+    plain-C port.  Returns (lib, kind)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libalva_ref.so")
+    if os.path.exists(ref):
+        try:
+            return C.CDLL(ref), "reference"
+        except OSError:
+            pass
+    so = os.path.join(ROOT, "oracle", "_build", "libalva_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return C.CDLL(so), "port"
+
+
+def cpu_pipeline_frames(L, kind, frames_rgba, map_desc, ba, nthreads):
+    """The reference's CPU path for the same step on `frames_rgba` ([n, H, W, 4]); returns seconds.
+    reference kind: cv::cvtColor + buildOpticalFlowPyramid(win 9, 3 levels) + ORB::detectAndCompute(1000, 1 level:
+    FAST + Harris + retainBest + IC angle + blur + rBRIEF) + BFMatcher.knnMatch(k=2) with cv::setNumThreads(nthreads),
+    and ceres::Solve once per KF_INTERVAL frames (single-threaded, as the product is)."""
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    n = len(frames_rgba)
+    gray = np.empty((H, W), np.uint8)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        L.ref_config(1, nthreads)
+        lv = [np.empty((H, W), np.uint8), np.empty(((H + 1) // 2, (W + 1) // 2), np.uint8)]
+        lv.append(np.empty(((lv[1].shape[0] + 1) // 2, (lv[1].shape[1] + 1) // 2), np.uint8))
+        lv.append(np.empty(((lv[2].shape[0] + 1) // 2, (lv[2].shape[1] + 1) // 2), np.uint8))
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in lv])
+        kp = np.empty((4096, 5), np.float32)
+        desc = np.empty((4096, 32), np.uint8)
+        out = np.empty((4096, 4), np.int32)
+        for f in range(n):
+            L.ref_gray(P(frames_rgba[f]), W, H, P(gray))
+            L.ref_build_pyramid(P(gray), W, H, 9, 3, ptrs, None)
+            nd = L.ref_orb_detect(P(gray), W, H, NFEAT, FAST_THR, P(kp), P(desc), 4096)
+            L.ref_knn2(P(desc), min(nd, 4096), P(map_desc), len(map_desc), P(out))
+            if f % KF_INTERVAL == 0:
+                run_cpu_ba(L, "ref", ba)
+    else:
+        xs = np.empty((W * H // 4, 3), np.int32)
+        blur = np.empty((H, W), np.uint8)
+        for f in range(n):
+            L.orc_gray(P(frames_rgba[f]), W, H, P(gray))
+            cur, cw, ch = gray, W, H
+            for _ in range(3):
+                nxt = np.empty(((ch + 1) // 2, (cw + 1) // 2), np.uint8)
+                L.orc_pyrdown(P(cur), cw, ch, P(nxt))
+                cur, cw, ch = nxt, nxt.shape[1], nxt.shape[0]
+            nk = L.orc_fast9(P(gray), W, H, FAST_THR, 1, P(xs), len(xs))
+            k = xs[:nk]
+            k = k[(k[:, 0] >= 31) & (k[:, 0] < W - 31) & (k[:, 1] >= 31) & (k[:, 1] < H - 31)]
+            thr = L.orc_retain_best_threshold(P(np.ascontiguousarray(k)), len(k), NFEAT)
+            k = k[k[:, 2] >= thr]
+            pts = np.ascontiguousarray(k[:, :2].astype(np.float32))
+            ang = np.empty(len(pts), np.float32)
+            L.orc_ic_angles(P(gray), W, H, P(pts), len(pts), P(ang))
+            L.orc_orb_blur(P(gray), W, H, 0, P(blur))
+            desc = np.empty((len(pts), 32), np.uint8)
+            kept = np.empty(len(pts), np.uint8)
+            L.orc_orb_describe(P(blur), W, H, P(pts), P(ang), len(pts), P(desc), P(kept))
+            out = np.empty((len(pts), 4), np.int32)
+            L.orc_knn2(P(desc), len(pts), P(map_desc), len(map_desc), P(out))
+            if f % KF_INTERVAL == 0:
+                run_cpu_ba(L, "orc", ba)
+    return time.perf_counter() - t0
+
+
+def run_cpu_ba(L, prefix, pb):
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    poses, invd = pb["poses"].copy(), pb["invd"].copy()
+    summary = np.zeros(8)
+    getattr(L, prefix + "_ba_solve")(P(pb["calib"]), P(poses), P(pb["pose_const"]), len(poses), P(invd), P(pb["anch_kf"]),
+                                    P(pb["anch_uv"]), len(invd), P(pb["obs_kf"]), P(pb["obs_lm"]), P(pb["obs_uv"]),
+                                    len(pb["obs_kf"]), C.c_double(pb["huber"]), BA_ITERS, P(summary), None)
+
+
+def bench_reference(args, rank, world):
+    if rank != 0:
+        return
+    from alvaar_b200 import synth
+    L, kind = load_cpu_impl()
+    cores = os.cpu_count() or 1
+    nthreads = cores
+    sample = 8 if kind == "reference" else 2          # frames per CPU step: a bounded sample of the 64-frame step
+    frames, _ = synth.make_frames(sample, W, H)
+    _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
+    ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_pipeline_frames(L, kind, frames[:2], map_desc, ba, nthreads)
+    steps = max(1, min(args.steps, 3))
+    t = sum(cpu_pipeline_frames(L, kind, frames, map_desc, ba, nthreads) for _ in range(steps))
+    fps = sample * steps / t
+    line = {"impl": "reference", "metric": "frames_per_sec_720p_1000orb_20kf_ba", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": workload_config(sample),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads if kind == "reference" else 1, "kind": kind,
+                             "sample": f"{sample} frames/step x {steps} steps of the 720p workload "
+                                       "(cv::setNumThreads(all cores) for the OpenCV stages, Ceres single-threaded as shipped)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(batch):
+    return {"workload": "c2_720p_stream+c4_local_ba", "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
+            "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "7x7 blur + IC angle + rBRIEF-256, 1 level",
+            "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
+            "ba_every_n_frames": KF_INTERVAL, "l2_policy": "inputs (236 MB/step) larger than L2 (126 MB)",
+            "parallelism": "1 stream batch per GPU"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def bench_b200(args, rank, world, local_rank):
+    import torch
+    import alvaar_b200
+    from alvaar_b200 import synth
+    from alvaar_b200.pipeline import Pipeline
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    frames, _ = synth.make_frames(BATCH, W, H, seed=99 + rank)
+    _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
+    ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
+    stream = torch.cuda.Stream()
+    ctx = alvaar_b200.Context(local_rank, stream.cuda_stream)
+    pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE,
+                    map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
+                    ba_max_iter=BA_ITERS, ba_huber=ba["huber"])
+    pipe.set_map(map_desc)
+    for s in range(pipe.nprob):
+        pipe.set_ba(s, ba)
+    host_in = torch.from_numpy(frames).pin_memory()
+    d_in = host_in.to(f"cuda:{local_rank}")
+    nfeat_host = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
+    matches_host = torch.zeros((BATCH, pipe.fcap, 4), dtype=torch.int32).pin_memory()
+    poses_host = torch.zeros((max(pipe.nprob, 1), BA_NKF, 7), dtype=torch.float64).pin_memory()
+    summ_host = torch.zeros((max(pipe.nprob, 1), 8), dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    pipe.profile(True)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            pipe.step_dev(d_in)
+        barrier()
+        l0 = ctx.launches
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pipe.profile(True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            pipe.step_dev(d_in)
+        ev1.record(stream)
+        barrier()
+        launches = ctx.launches - l0
+        ms = ev0.elapsed_time(ev1)
+        fe = pipe.frontend_ms(args.steps)
+        pipe.profile(False)
+        # e2e: host buffers through the C-ABI call, copies inside the timed region
+        for _ in range(min(args.warmup, 2)):
+            pipe.step_host(host_in, nfeat_host, matches_host, poses_host, summ_host)
+        barrier()
+        e2e_steps = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(e2e_steps):
+            pipe.step_host(host_in, nfeat_host, matches_host, poses_host, summ_host)
+        ev1.record(stream)
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1)
+        _ = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    fps = world * BATCH * args.steps / (ms * 1e-3)
+    e2e_fps = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
+    peak, peak_src = read_peaks()
+    fe_avg_ms = float(np.mean(fe))
+    achieved = ALGO_BYTES_FRONTEND * BATCH / (fe_avg_ms * 1e-3) / 1e9
+    nf = nfeat_host.numpy()
+    summ = summ_host.numpy()
+    h2d = int(host_in.numel())
+    d2h = int(nfeat_host.numel() * 4 + matches_host.numel() * 4 + poses_host.numel() * 8 + summ_host.numel() * 8)
+
+    # CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        L, kind = load_cpu_impl()
+        cores = os.cpu_count() or 1
+        sample = 8 if kind == "reference" else 2
+        cpu_pipeline_frames(L, kind, frames[:2], map_desc, ba, cores)
+        tcpu = cpu_pipeline_frames(L, kind, frames[:sample], map_desc, ba, cores)
+        cpu = {"value": sample / tcpu, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+               "sample": f"{sample} frames of the same 720p step (incl. {(sample + KF_INTERVAL - 1) // KF_INTERVAL} local BA solves), "
+                         "OpenCV stages on all host cores, Ceres single-threaded as shipped"}
+
+    line = {"metric": "frames_per_sec_720p_1000orb_20kf_ba", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": workload_config(BATCH),
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "alva_pipeline_step_host (pinned host RGBA in, counts+matches+BA poses out)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"kernel": "frontend_tile_kernel<RGBA> (gray + pyramid L1 + FAST-9/NMS, fused)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_FRONTEND * BATCH,
+                         "launch_ms": fe_avg_ms},
+            "cpu_baseline": cpu,
+            "stats": {"features_per_frame_mean": float(nf.mean()), "features_per_frame_min": int(nf.min()),
+                      "ba_final_over_initial_cost": float((summ[:, 1] / np.maximum(summ[:, 0], 1e-300)).mean()),
+                      "ba_iterations_mean": float(summ[:, 3].mean())}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        bench_reference(args, rank, world)
+    else:
+        bench_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

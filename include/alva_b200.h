@@ -103,6 +103,83 @@ int alva_k_orb_describe(alva_ctx*, const uint8_t* gray, const uint8_t* blurred, 
  * out[4*i] = {idx0, dist0, idx1, dist1} (int32; -1 when nt < 2). */
 int alva_k_hamming_knn2(alva_ctx*, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out);
 
+/* Batched variant: q is [nbatch][qcap][32] of which only the first counts[b] slots of batch b are live (qcap a
+ * multiple of 8); dead slots come back as -1. */
+int alva_k_hamming_knn2_batch(alva_ctx*, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
+                              const uint8_t* t, int nt, int32_t* out);
+
+/* Local bundle adjustment, batched over nprob independent problems of identical dimensions
+ * (Optimizer::localBA, src/slam/src/optimizer.cpp:4-531, solved the way ceres::Solve does with the reference's
+ * options: SPARSE_SCHUR elimination of the inverse depths, Levenberg-Marquardt, Huber(huber_delta), Jacobi scaling,
+ * function_tolerance 1e-3, at most max_iter iterations, no wall-clock cap).  All pointers are DEVICE pointers, FP64.
+ *   calib [nprob][4] (fx fy cx cy)                poses [nprob][nkf][7] = [t, q(x,y,z,w)] camera-to-world, IN/OUT
+ *   pose_const [nprob][nkf] (1 = fixed)           invd [nprob][nlm] inverse depth in the anchor keyframe, IN/OUT
+ *   anch_kf [nprob][nlm], anch_uv [nprob][nlm][2]  anchor keyframe index and (undistorted) pixel of each landmark
+ *   obs_kf/obs_lm [nprob][nobs], obs_uv [nprob][nobs][2]   the non-anchor observations; obs_lm = -1 marks an unused slot
+ *   summary [nprob][8] (optional): initial cost, final cost, #successful steps, #iterations, termination
+ *   (0 convergence, 1 iteration limit, 2 failure), reduced-system width, final radius, last iteration index. */
+int alva_k_ba_solve(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                    const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                    const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta, int max_iter,
+                    double* summary);
+
+/* Residual / Jacobian build alone (DirectSE3::ReprojectionErrorKSE3AnchInvDepth::Evaluate,
+ * src/slam/src/ceres_parametrization.cpp:157-269, + Huber corrector): res [nobs][2], Ja/Jp [nobs][2][6] (local
+ * Jacobians wrt anchor / observing pose), Jd [nobs][2] (wrt inverse depth), cost_per_obs [nobs]. */
+int alva_k_ba_linearize(alva_ctx*, int nkf, int nlm, int nobs, const double* calib, const double* poses, const double* invd,
+                        const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf, const int32_t* obs_lm,
+                        const double* obs_uv, double huber_delta, double* res, double* Ja, double* Jp, double* Jd,
+                        double* cost_per_obs);
+
+/* ---- the whole per-frame hot path as one object ------------------------------------------------
+ * A batch of frames goes gray + pyramid + FAST -> retainBest -> ORB -> Hamming 2-NN vs the local map -> local BA on
+ * the step's keyframes, every intermediate resident in HBM, no host synchronisation inside a step
+ * (reference per-frame / per-keyframe sequence: System::findCameraPose system.cpp:106-121 -> VisualFrontend::track
+ * visual_frontend.cpp:21-35 -> MapManager::createKeyframe map_manager.cpp:24,193 -> Mapper::matchingToLocalMap
+ * mapper.cpp:293 -> Optimizer::localBA optimizer.cpp:4). */
+typedef struct alva_pipeline alva_pipeline;
+typedef struct alva_pipeline_config {
+    int w, h, batch;        /* frame geometry and frames per step */
+    int fast_thr;           /* FAST threshold (ORB default 20) */
+    int nfeatures;          /* retainBest target per frame */
+    int orb_flags;          /* ALVA_ORB_* */
+    int map_size;           /* descriptors in the local map (0 = no matching) */
+    int kf_interval;        /* one local BA per kf_interval frames (0 = no BA) */
+    int ba_nkf, ba_nlm, ba_nobs, ba_max_iter;
+    double ba_huber;
+} alva_pipeline_config;
+
+alva_pipeline* alva_pipeline_create(alva_ctx*, const alva_pipeline_config*);
+void alva_pipeline_destroy(alva_pipeline*);
+int  alva_pipeline_set_map(alva_pipeline*, const uint8_t* desc_host, int n);
+int  alva_pipeline_set_ba(alva_pipeline*, int slot, const double* calib, const double* poses, const uint8_t* pose_const,
+                          const double* invd, const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf,
+                          const int32_t* obs_lm, const double* obs_uv);
+int  alva_pipeline_step_dev(alva_pipeline*, const uint8_t* rgba_dev);
+int  alva_pipeline_step_host(alva_pipeline*, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
+                             double* ba_poses_host, double* ba_summary_host);
+int  alva_pipeline_profile(alva_pipeline*, int enable);
+int  alva_pipeline_frontend_ms(alva_pipeline*, float* ms, int n);   /* CUDA-event durations of the fused front-end launch */
+int  alva_pipeline_info(const alva_pipeline*, int32_t* out4);
+void* alva_pipeline_buffer(alva_pipeline*, int which);
+
+/* ---- System: the reference's public class, one handle per camera stream ------------------------
+ * One-to-one with System::{configure, reset, findCameraPose, findCameraPoseWithIMU, findPlane, getFramePoints}
+ * (reference src/slam/src/system.hpp:28-38; JS caller src/system.js:58-237).  Host pointers, caller-owned buffers:
+ * rgba = W*H*4 bytes (read only), pose16 = 16 floats (R rows in [0..2],[4..6],[8..10], t in [12..14], [15] = 1;
+ * src/slam/src/utils.cpp:3-27).  findCameraPose returns 1 tracking / 2 tracker was reset / 3 not initialised
+ * (system.cpp:163-174) or a negative ALVA_E_* code. */
+alva_system* alva_system_create(int device);
+void alva_system_destroy(alva_system*);
+int  alva_system_configure(alva_system*, int w, int h, double fx, double fy, double cx, double cy,
+                           double k1, double k2, double p1, double p2);
+int  alva_system_reset(alva_system*);
+int  alva_system_find_camera_pose(alva_system*, const uint8_t* rgba, float* pose16);
+int  alva_system_find_camera_pose_imu(alva_system*, const uint8_t* rgba, const double* imu, float* pose16);
+int  alva_system_find_plane(alva_system*, float* out16, int iterations);
+int  alva_system_get_frame_points(alva_system*, int32_t* xy, int cap_pairs);   /* returns the true count */
+int  alva_system_num_matched(alva_system*);   /* features of the last frame matched to the local map */
+
 /* ---- host-buffer variants (copies inside; used for e2e timing and by non-CUDA hosts) ---------- */
 int alva_h_frontend(alva_ctx*, const uint8_t* rgba_host, int w, int h, int nframes, int thr,
                     uint32_t* keys_host, int32_t* counts_host, int cap);

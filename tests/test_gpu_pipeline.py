@@ -1,0 +1,86 @@
+"""GPU parity test (B200): the whole per-frame hot path as one object (alva_pipeline_*) against the stage-by-stage
+oracle: gray -> pyramid -> FAST -> retainBest -> ORB (IC angle) -> Hamming 2-NN -> local BA."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import P
+from alvaar_b200 import synth, unpack_keys, ORB_IC_ANGLE
+from alvaar_b200.pipeline import Pipeline
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000)])
+def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
+    frames, _ = synth.make_frames(batch, w, h, seed=5)
+    q, mapd = synth.make_descriptors(8, 2000, seed=3)
+    ba = synth.make_ba_problem(8, 300, 3, seed=7)
+    pipe = Pipeline(gpu_ctx, w, h, batch, fast_thr=20, nfeatures=nfeat, orb_flags=ORB_IC_ANGLE, map_size=2000, kf_interval=2,
+                    ba_nkf=8, ba_nlm=300, ba_nobs=len(ba["obs_kf"]), ba_max_iter=5, ba_huber=ba["huber"])
+    pipe.set_map(mapd)
+    for s in range(pipe.nprob):
+        pipe.set_ba(s, ba)
+    host_in = torch.from_numpy(frames).pin_memory()
+    nfeat_h = torch.zeros(batch, dtype=torch.int32).pin_memory()
+    match_h = torch.zeros((batch, pipe.fcap, 4), dtype=torch.int32).pin_memory()
+    poses_h = torch.zeros((pipe.nprob, 8, 7), dtype=torch.float64).pin_memory()
+    summ_h = torch.zeros((pipe.nprob, 8), dtype=torch.float64).pin_memory()
+    pipe.step_host(host_in, nfeat_h, match_h, poses_h, summ_h)
+    # and the device-resident entry point gives the same answer
+    pipe.step_dev(host_in.to(DEV))
+    torch.cuda.synchronize()
+    fcap = pipe.fcap
+    sel = pipe.buffer("sel", (batch, fcap), torch.int32).cpu().numpy().view(np.uint32)
+    selc = pipe.buffer("selcounts", (batch,), torch.int32).cpu().numpy()
+    desc = pipe.buffer("desc", (batch, fcap, 32), torch.uint8).cpu().numpy()
+    kept = pipe.buffer("kept", (batch, fcap), torch.uint8).cpu().numpy()
+    matches = pipe.buffer("matches", (batch, fcap, 4), torch.int32).cpu().numpy()
+    assert (selc == nfeat_h.numpy()).all() and (matches == match_h.numpy()).all()
+    sizes = [(w, h)]
+    for _ in range(3):
+        sizes.append(((sizes[-1][0] + 1) // 2, (sizes[-1][1] + 1) // 2))
+    lv = [pipe.buffer(f"l{k}", (batch, sizes[k][1], sizes[k][0]), torch.uint8).cpu().numpy() for k in range(4)]
+    for f in range(batch):
+        gray = np.empty((h, w), np.uint8)
+        oracle.orc_gray(P(frames[f]), w, h, P(gray))
+        assert (lv[0][f] == gray).all()
+        cur = gray
+        for k in (1, 2, 3):
+            nxt = np.empty((sizes[k][1], sizes[k][0]), np.uint8)
+            oracle.orc_pyrdown(P(cur), cur.shape[1], cur.shape[0], P(nxt))
+            assert (lv[k][f] == nxt).all()
+            cur = nxt
+        xs = np.zeros((w * h // 4, 3), np.int32)
+        n = oracle.orc_fast9(P(gray), w, h, 20, 1, P(xs), len(xs))
+        k = xs[:n]
+        k = np.ascontiguousarray(k[(k[:, 0] >= 31) & (k[:, 0] < w - 31) & (k[:, 1] >= 31) & (k[:, 1] < h - 31)])
+        thr = oracle.orc_retain_best_threshold(P(k), len(k), nfeat)
+        want = k[k[:, 2] >= thr]
+        c = int(selc[f])
+        assert c == len(want) and nfeat <= c <= fcap
+        assert (unpack_keys(sel[f, :c]) == want).all()
+        pts = np.ascontiguousarray(want[:, :2].astype(np.float32))
+        ang = np.zeros(c, np.float32)
+        oracle.orc_ic_angles(P(gray), w, h, P(pts), c, P(ang))
+        blur = np.empty_like(gray)
+        oracle.orc_orb_blur(P(gray), w, h, 0, P(blur))
+        wd, wk = np.zeros((c, 32), np.uint8), np.zeros(c, np.uint8)
+        oracle.orc_orb_describe(P(blur), w, h, P(pts), P(ang), c, P(wd), P(wk))
+        assert wk.all() and (kept[f, :c] == 1).all() and (kept[f, c:] == 0).all()
+        assert (desc[f, :c] == wd).all()
+        wm = np.zeros((c, 4), np.int32)
+        oracle.orc_knn2(P(wd), c, P(mapd), len(mapd), P(wm))
+        assert (matches[f, :c] == wm).all() and (matches[f, c:] == -1).all()
+    wp, wdpt = ba["poses"].copy(), ba["invd"].copy()
+    ws = np.zeros(8)
+    oracle.orc_ba_solve(P(ba["calib"]), P(wp), P(ba["pose_const"]), 8, P(wdpt), P(ba["anch_kf"]), P(ba["anch_uv"]), 300,
+                        P(ba["obs_kf"]), P(ba["obs_lm"]), P(ba["obs_uv"]), len(ba["obs_kf"]), C.c_double(ba["huber"]), 5, P(ws),
+                        None)
+    for s in range(pipe.nprob):
+        assert np.allclose(poses_h[s].numpy(), wp, rtol=1e-4, atol=1e-9)
+        assert (summ_h[s].numpy()[2:5] == ws[2:5]).all()
+    pipe.close()
