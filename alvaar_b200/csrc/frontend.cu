@@ -20,6 +20,7 @@
 //     row-major order when the caller asks for it.
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -152,6 +153,11 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
     const int x0 = tx * TW, y0 = ty * TH;
     const int w = P.w, h = P.h;
+    // TMA needs the box start 16-byte aligned along the innermost dimension.  RGBA: (x0-4)*4 B is always a multiple of 16.
+    // Gray (u8): x0-8 is 0 or 8 mod 16, so the box starts `sh` bytes earlier and the tile sits `sh` bytes further right
+    // in the shared rows (pitch 144 still covers x0-8 .. x0+TW+7).
+    const int sh = RGBA ? 0 : ((x0 - 8) & 15);
+    const int cbw = 1 + (sh >> 2);   // word index (within a gray smem row) of image column x0-4
 
     // ------------------------------------------------------------------ A. load the tile
     if (P.use_tma) {
@@ -166,7 +172,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
                 tma_load_3d(S.rgba, &tmap, &S.bar, x0 - 4, y0 - 4, f);
             } else {
                 mbar_arrive_expect_tx(&S.bar, GP * BH);
-                tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8, y0 - 4, f);
+                tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8 - sh, y0 - 4, f);
             }
         }
     } else {
@@ -182,7 +188,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             const uint8_t* src = P.src + (size_t)f * w * h;
             for (int i = tid; i < GP * BH; i += NTHREADS) {
                 const int by = i / GP, bx = i - by * GP;
-                const int x = x0 - 8 + bx, y = y0 - 4 + by;
+                const int x = x0 - 8 - sh + bx, y = y0 - 4 + by;
                 S.gray[i] = (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(src + (size_t)y * w + x) : 0;
             }
         }
@@ -227,9 +233,9 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         if (edge_l || edge_r) {
             for (int r = tid; r < BH; r += NTHREADS) {
                 uint8_t* row = S.gray + r * GP;
-                if (edge_l) { row[7] = row[9]; row[6] = row[10]; }
+                if (edge_l) { row[7 + sh] = row[9 + sh]; row[6 + sh] = row[10 + sh]; }
                 if (edge_r) {
-                    const int cw = w - x0 + 8;   // gray byte of image column w
+                    const int cw = w - x0 + 8 + sh;   // gray byte of image column w
                     row[cw] = row[cw - 2];
                     row[cw + 1] = row[cw - 3];
                 }
@@ -260,7 +266,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             const int lx = (x0 >> 1) + 2 * pc;
             const int ly0 = (y0 >> 1) + 4 * sg;
             if (lx < w1 && ly0 < h1) {
-                const uint32_t* base = G + (8 * sg + 2) * GPW + 1 + pc;   // gray row 2j+2 for j = 4*sg
+                const uint32_t* base = G + (8 * sg + 2) * GPW + cbw + pc;   // gray row 2j+2 for j = 4*sg
                 uint32_t hrow[11];
 #pragma unroll
                 for (int r = 0; r < 11; r++) {
@@ -309,7 +315,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             const int y = y0 - 1 + rr;
             if (y >= ylo && y <= yhi) {   // warp-uniform
                 const int r = rr + 3;     // gray smem row of the centre
-                const uint32_t* g0 = G + r * GPW + 1 + lane;
+                const uint32_t* g0 = G + r * GPW + cbw + lane;
                 uint32_t ring[16];
                 uint32_t c;
                 {
@@ -344,7 +350,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
                 dark &= vmask;
                 const uint32_t any = bright | dark;
                 // warp-ballot compaction of corner pixels into the warp queue
-                const int pix0 = r * GP + 4 + 4 * lane;
+                const int pix0 = r * GP + 4 * (cbw + lane);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const bool has = (any >> (8 * j + 7)) & 1;
@@ -366,7 +372,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
                     const int pix = e & 0x7fff;
                     const int s = fast_strength(S.gray + pix, e >> 15);
                     const int pr = pix / GP, pcg = pix - pr * GP;
-                    S.score[(pr - 3) * SP + (pcg - 4)] = (uint8_t)(s - 1);
+                    S.score[(pr - 3) * SP + (pcg - 4 * cbw)] = (uint8_t)(s - 1);
                 }
                 qn -= take;
                 __syncwarp();
@@ -575,7 +581,8 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
         tma_ok = (w % 16 == 0) && (((size_t)w * h) % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
                  alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, src, dims, strides, box);
     }
-    P.use_tma = tma_ok ? 1 : 0;
+    static const bool no_tma = getenv("ALVA_DISABLE_TMA") != nullptr;   // debugging aid: force the plain-load path
+    P.use_tma = (tma_ok && !no_tma) ? 1 : 0;
     const int grid = P.tiles_x * P.tiles_y * nframes;
     const size_t smem = sizeof(SmemLayout) + 128;
     if (rgba_mode) {

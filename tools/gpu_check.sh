@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# One GPU-box visit: parity tests file by file (a crashed CUDA context only poisons its own process), a short bench,
+# the ncu launch list of the bench command and one full capture of the dominant kernel.  Everything lands in gpurun_out/.
+set +e
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
+FILES=${FILES:-"test_gpu_frontend test_gpu_orb_match test_gpu_ba test_gpu_pipeline test_gpu_system"}
+for f in $FILES; do
+  timeout 420 python -m pytest tests/$f.py -m gpu -x -q --durations=4 -p no:cacheprovider > gpurun_out/$f.log 2>&1
+  echo "== $f rc=$?"; tail -14 gpurun_out/$f.log
+done
+if ! grep -q " passed" gpurun_out/test_gpu_frontend.log || grep -q "failed" gpurun_out/test_gpu_frontend.log; then
+  echo "== frontend failed: retry without TMA and under compute-sanitizer"
+  ALVA_DISABLE_TMA=1 timeout 300 python -m pytest tests/test_gpu_frontend.py -m gpu -x -q -p no:cacheprovider 2>&1 | tail -6
+  timeout 240 compute-sanitizer --tool memcheck --print-limit 5 python tools/gpu_repro.py > gpurun_out/sanitizer.log 2>&1; tail -30 gpurun_out/sanitizer.log
+fi
+if [ "${SKIP_BENCH:-0}" != "1" ]; then
+  timeout 400 python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  echo "== bench rc=$?"; tail -c 2500 gpurun_out/bench.json; tail -4 gpurun_out/bench.err
+  timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; tail -c 600 gpurun_out/bench_ref.json
+fi
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  echo "== ncu list rc=$?"; wc -l gpurun_out/launches.csv
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:frontend_tile -s 1 -c 2 -f -o gpurun_out/prof_frontend \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+  echo "== ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep
+fi
