@@ -20,6 +20,7 @@
 #include "../../include/alva_b200.h"
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 namespace {
 
@@ -57,10 +58,11 @@ struct BaProblem {
     double *cost_part;                      // [nblk]
     int32_t *pose_col;                      // [nkf]
     int32_t *lm_start, *lm_obs;             // CSR landmark -> observations: [nlm+1], [nobs]
+    double* Wt;                             // dense Schur path: [nlm_pad][NMAX]
     BaState* st;
 };
 
-struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; };
+struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; int nlm_pad; };
 
 // ------------------------------------------------------------------------------------------ SE(3) helpers
 __device__ __forceinline__ void quat_to_R(const double* q, double* R) {   // q = (x,y,z,w), normalised here
@@ -385,10 +387,19 @@ __global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict
 
 // ------------------------------------------------------------------------------------------ Schur (thread / landmark)
 // S += F'F - (E'F)'(E'E + D^2)^-1 (E'F),  rhs += F'b - (E'F)'(E'E + D^2)^-1 E'b  for this landmark's rows
+// DENSE = true: the -(E'F)'(E'E)^-1(E'F) term is NOT accumulated here; instead the landmark's row of
+// Wt = diag(E'E + D^2)^-1/2 (E'F)  (nlm x 128, zero outside the landmark's pose blocks) is written for the FP64
+// tensor-core SYRK below (S -= Wt' Wt), which is where that term is a genuine dense contraction.
+template <bool DENSE>
 __global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     if (P.st->done) return;
     const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= D.nlm_pad) return;
+    if (DENSE) {   // rows are rewritten every iteration; padding rows and unused landmarks stay zero
+        double* row = P.Wt + (size_t)l * NMAX;
+        for (int i = 0; i < NMAX; i++) row[i] = 0.0;
+    }
     if (l >= D.nlm) return;
     const int b = P.lm_start[l], e = P.lm_start[l + 1];
     if (e == b) return;
@@ -442,8 +453,24 @@ __global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restri
     if (ca >= 0)
         for (int a = 0; a < 6; a++) {
             atomicAdd(&P.rhs[ca + a], rha[a] - wa[a] * inv * etb);
-            for (int c = 0; c < 6; c++) atomicAdd(&P.S[(ca + a) * NMAX + ca + c], Saa[6 * a + c] - wa[a] * inv * wa[c]);
+            for (int c = 0; c < 6; c++)
+                atomicAdd(&P.S[(ca + a) * NMAX + ca + c], DENSE ? Saa[6 * a + c] : Saa[6 * a + c] - wa[a] * inv * wa[c]);
         }
+    if (DENSE) {
+        const double rs = sqrt(inv);
+        double* row = P.Wt + (size_t)l * NMAX;
+        if (ca >= 0) for (int c = 0; c < 6; c++) row[ca + c] += wa[c] * rs;
+        for (int i = b; i < e; i++) {
+            const int oi = P.lm_obs[i];
+            const int ci = P.pose_col[P.obs_kf[oi]];
+            if (ci < 0) continue;
+            for (int c = 0; c < 6; c++) {
+                row[ci + c] += P.wp[6 * oi + c] * rs;
+                atomicAdd(&P.rhs[ci + c], -P.wp[6 * oi + c] * inv * etb);
+            }
+        }
+        return;
+    }
     // - w w' / ete over (observer, observer) and (anchor, observer) pairs
     for (int i = b; i < e; i++) {
         const int oi = P.lm_obs[i];
@@ -466,6 +493,62 @@ __global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restri
             for (int a = 0; a < 6; a++)
                 for (int c = 0; c < 6; c++) atomicAdd(&P.S[(ci + a) * NMAX + cj + c], -wi[a] * inv * P.wp[6 * oj + c]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dense Schur term on tensor cores
+// S -= Wt' * Wt  with Wt [K = nlm_pad][128] row-major, FP64 tensor-core MMA (mma.sync.m8n8k4.f64 -> SASS DMMA; tcgen05 has
+// no FP64 kind).  Grid: (16 output blocks of 32x32) x (K splits) x problems; 4 warps per CTA interleave the K steps, the
+// four partial 32x32 blocks are summed in shared memory and added to S with one FP64 atomic per element.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int SYRK_KSPLIT = 8;
+
+__global__ void __launch_bounds__(128) ba_syrk_dmma_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.z];
+    if (P.st->done) return;
+    __shared__ double part[4][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.x >> 2, bj = blockIdx.x & 3;          // 4 x 4 blocks of 32 x 32
+    const int i0 = bi * 32, j0 = bj * 32;
+    const int n = P.st->ncols;
+    if (i0 >= n || j0 >= n) return;                                // block entirely in the padding
+    const int ksteps = D.nlm_pad / 4;
+    const int per = (ksteps + SYRK_KSPLIT - 1) / SYRK_KSPLIT;
+    const int kb = blockIdx.y * per, ke = min(ksteps, kb + per);
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int kr = lane & 3, cc = lane >> 2;
+    for (int ks = kb + warp; ks < ke; ks += 4) {
+        const double* row = P.Wt + (size_t)(4 * ks + kr) * NMAX;
+        double av[4], bv[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { av[t] = __ldg(row + i0 + 8 * t + cc); bv[t] = __ldg(row + j0 + 8 * t + cc); }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+    }
+    // C fragment: row = lane / 4, cols = 2 * (lane % 4) + {0, 1}
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            part[warp][8 * a + cc][8 * b + 2 * kr] = acc[a][b][0];
+            part[warp][8 * a + cc][8 * b + 2 * kr + 1] = acc[a][b][1];
+        }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * 32; t += 128) {
+        const int r = t >> 5, c = t & 31;
+        const double v = part[0][r][c] + part[1][r][c] + part[2][r][c] + part[3][r][c];
+        if (v != 0.0) atomicAdd(&P.S[(i0 + r) * NMAX + j0 + c], -v);
     }
 }
 
@@ -687,8 +770,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 // Workspace carving: one contiguous block per problem.
+static int g_ba_dense_schur = 0;   // alva_set_option("ba_dense_schur", 1): tensor-core SYRK for the Schur term
+
 static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     size_t d = 0;
+    if (g_ba_dense_schur) d += (size_t)((nlm + 3) / 4 * 4) * NMAX;
     d += (size_t)nobs * (2 + 12 + 12 + 2 + 6);      // res, Ja, Jp, Jd, wp
     d += 5 * (size_t)NMAX;                           // nf gf scf diagf Df
     d += 5 * (size_t)nlm;                            // ne ge sce diage De
@@ -733,6 +819,7 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         P.ete = take(nlm); P.etb = take(nlm); P.wa = take(6 * (size_t)nlm); P.ye = take(nlm);
         P.S = take((size_t)NMAX * NMAX); P.rhs = take(NMAX); P.yf = take(NMAX);
         P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
+        P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
         uint8_t* b = reinterpret_cast<uint8_t*>(d);
         P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
         P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
@@ -742,20 +829,28 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
     ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
     ALVA_CUDA(cudaStreamSynchronize(ctx->stream));   // hostbuf is pageable: make the copy complete before it dies
     const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
-    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter};
+    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4};
+    const bool dense = g_ba_dense_schur != 0;
     const size_t solve_smem = ((size_t)NMAX * (NMAX + 1) + NMAX + 256) * sizeof(double);
     ALVA_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     ba_setup_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
-    const dim3 lin_grid(nblk, nprob), schur_grid((nlm + 127) / 128, nprob);
+    const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     for (int it = 0; it <= max_iter; it++) {
         ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_pre_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         if (it == max_iter) break;   // the last pass only finalises (iteration count reached)
-        ba_schur_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
-        ALVA_LAUNCH_CHECK(ctx);
+        if (dense) {
+            ba_schur_kernel<true><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
+            ALVA_LAUNCH_CHECK(ctx);
+            ba_syrk_dmma_kernel<<<syrk_grid, 128, 0, ctx->stream>>>(dp, D);
+            ALVA_LAUNCH_CHECK(ctx);
+        } else {
+            ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
+            ALVA_LAUNCH_CHECK(ctx);
+        }
         ba_solve_kernel<<<nprob, 256, solve_smem, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_linearize_kernel<false><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
@@ -783,4 +878,12 @@ extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, co
                                                                          obs_uv, nobs, huber_delta, res, Ja, Jp, Jd, cost_per_obs);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// Library-wide options: "ba_dense_schur" = 1 routes the -(E'F)'(E'E)^-1(E'F) term of the Schur complement through the
+// FP64 tensor-core SYRK (S -= Wt'Wt) instead of per-landmark atomics.  Returns 0, or ALVA_E_INVALID for an unknown name.
+extern "C" int alva_set_option(const char* name, int value) {
+    if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
+    alva_set_error("alva_set_option: unknown option");
+    return ALVA_E_INVALID;
 }

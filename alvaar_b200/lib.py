@@ -41,6 +41,7 @@ def lib():
         L.alva_k_pyrdown.argtypes = [vp, vp, vp, i32, i32, i32]
         L.alva_k_fast9.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]
         L.alva_k_frontend.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32]
+        L.alva_set_option.argtypes = [C.c_char_p, i32]
         L.alva_k_retain_best.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32]
         for name, args in _OPTIONAL.items():
             if hasattr(L, name):

@@ -123,6 +123,10 @@ int alva_k_ba_solve(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
                     const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta, int max_iter,
                     double* summary);
 
+/* Library-wide switches.  "ba_dense_schur" = 1: compute the -(E'F)'(E'E)^-1(E'F) part of the Schur complement as a dense
+ * FP64 tensor-core SYRK (S -= Wt'Wt, DMMA) instead of per-landmark atomics (default 0). */
+int alva_set_option(const char* name, int value);
+
 /* Residual / Jacobian build alone (DirectSE3::ReprojectionErrorKSE3AnchInvDepth::Evaluate,
  * src/slam/src/ceres_parametrization.cpp:157-269, + Huber corrector): res [nobs][2], Ja/Jp [nobs][2][6] (local
  * Jacobians wrt anchor / observing pose), Jd [nobs][2] (wrt inverse depth), cost_per_obs [nobs]. */

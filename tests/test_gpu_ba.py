@@ -113,3 +113,21 @@ def test_solve_improves_ground_truth_error(gpu_ctx):
     gp, gd, gs = gpu_solve(gpu_ctx, [pb])
     assert np.isfinite(gp).all() and np.isfinite(gd).all()
     assert gs[0, 1] < 0.5 * gs[0, 0] and gs[0, 4] in (0.0, 1.0)
+
+
+def test_solve_dense_schur_tensor_cores(gpu_ctx, oracle):
+    """Same solve with the Schur term computed by the FP64 tensor-core SYRK (S -= Wt'Wt, DMMA) instead of atomics."""
+    from alvaar_b200 import lib
+    L = lib()
+    pb = synth.make_ba_problem(20, 3000, 4, seed=42)
+    wp, wd, ws = oracle_solve(oracle, pb)
+    assert L.alva_set_option(b"ba_dense_schur", 1) == 0
+    try:
+        gp, gd, gs = gpu_solve(gpu_ctx, [pb, pb])
+    finally:
+        L.alva_set_option(b"ba_dense_schur", 0)
+    for i in range(2):
+        assert (gs[i, 2:5] == ws[2:5]).all(), (gs[i], ws)
+        assert np.allclose(gp[i], wp, rtol=1e-4, atol=1e-9) and np.allclose(gd[i], wd, rtol=1e-4, atol=1e-9)
+        assert np.abs(gp[i] - wp).max() < 1e-7
+    assert L.alva_set_option(b"no_such_option", 1) == -1
