@@ -20,6 +20,10 @@ struct alva_ctx {
     // staging for the host-buffer (alva_h_*) entry points
     void* dev_stage = nullptr;
     size_t dev_stage_bytes = 0;
+    // BA: fingerprint of the per-problem pointer table currently resident at the head of `scratch`
+    uint64_t ba_table_key = 0;
+    void* ba_ws = nullptr;          // BA workspace (own allocation: the table must survive other stages' scratch use)
+    size_t ba_ws_bytes = 0;
 };
 
 void alva_set_error(const char* fmt, ...);

@@ -12,7 +12,8 @@
 //
 // FP64 throughout (the north-star tolerance is 1e-4 relative; we land at ~1e-9).  The e-blocks are 1-dimensional
 // (inverse depth), so (E'E)^-1 is a scalar reciprocal per landmark; the reduced system is <= 20 poses x 6 = 120 wide
-// and lives in ONE CTA's shared memory for the Cholesky / triangular solves.  The trust-region decisions
+// and lives in ONE CTA's shared memory for the (blocked) Cholesky / triangular solves; the Schur complement itself is
+// assembled block-wise by a gather kernel (one warp per 6x6 pose-pair block, no atomics, bit-reproducible).  The trust-region decisions
 // (accept / reject, radius update, function / parameter / gradient tolerance) run in single-CTA "control" kernels
 // that read and write a device-resident state block, so an entire solve is a fixed launch sequence with no host
 // synchronisation (graph-capturable).
@@ -26,13 +27,17 @@ namespace {
 
 constexpr int NMAX = 128;   // max reduced-system width (>= 6 * free poses), padded
 constexpr int LIN_THREADS = 128;
+constexpr int NBMAX = NMAX / 6;                 // 21 free poses at most
+constexpr int MAXKEYS = NBMAX * (NBMAX + 1) / 2;   // upper-triangular 6x6 blocks of the reduced system
+constexpr int BS_THREADS = 128;                // back-substitution CTA
 
 struct BaState {
     double radius, decrease_factor, x_cost, cand_cost, xnorm, gmax, model_change;
     double se_min, se_cur, se_ref, se_cand, se_acc_ref, se_acc_cand;
     double initial_cost, push_cost;
     int reuse_diagonal, invalid_steps, iteration, last_success, n_success, n_iter, term, done;
-    int relin, step_ok, ncols, pad;
+    int relin, step_ok, ncols, chol_ok;
+    int nkeys, nentries, use_gather, nb;
 };
 
 // per-problem views into the workspace
@@ -59,10 +64,13 @@ struct BaProblem {
     int32_t *pose_col;                      // [nkf]
     int32_t *lm_start, *lm_obs;             // CSR landmark -> observations: [nlm+1], [nobs]
     double* Wt;                             // dense Schur path: [nlm_pad][NMAX]
+    double* mc_part;                        // model-cost partials, one per back-substitution CTA
+    int32_t *key_start;                     // gather Schur: [MAXKEYS + 1] entry ranges per upper-triangular pose-pair block
+    uint32_t *entries;                      // gather Schur: (landmark << 16) | (slot_u << 8) | slot_v, ordered by landmark
     BaState* st;
 };
 
-struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; int nlm_pad; };
+struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; int nlm_pad; int ecap; int nbs; };
 
 // ------------------------------------------------------------------------------------------ SE(3) helpers
 __device__ __forceinline__ void quat_to_R(const double* q, double* R) {   // q = (x,y,z,w), normalised here
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restri
         s.radius = 1e4; s.decrease_factor = 2.0; s.reuse_diagonal = 0; s.invalid_steps = 0; s.iteration = 0;
         s.last_success = 1; s.n_success = 0; s.n_iter = 0; s.term = 1; s.done = 0; s.relin = 1; s.step_ok = 0;
         s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
+        s.chol_ok = 1; s.use_gather = 0; s.nkeys = 0; s.nentries = 0; s.nb = c / 6;
     }
     // exclusive scan of counts -> lm_start (chunked: 256 threads)
     {
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProbl
     const BaProblem P = probs[blockIdx.y];
     __shared__ double red[LIN_THREADS];
     const BaState& st = *P.st;
-    const bool active = FULL ? (st.relin && !st.done) : (st.step_ok && !st.done);
+    const bool active = FULL ? (st.relin && !st.done) : !st.done;
     if (!active) return;   // uniform per CTA
     const int o = blockIdx.x * LIN_THREADS + threadIdx.x;
     double cost = 0;
@@ -394,6 +403,7 @@ template <bool DENSE>
 __global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     if (P.st->done) return;
+    if (!DENSE && P.st->use_gather) return;   // the gather path already assembled S
     const int l = blockIdx.x * 128 + threadIdx.x;
     if (l >= D.nlm_pad) return;
     if (DENSE) {   // rows are rewritten every iteration; padding rows and unused landmarks stay zero
@@ -552,111 +562,367 @@ __global__ void __launch_bounds__(128) ba_syrk_dmma_kernel(const BaProblem* __re
     }
 }
 
-// ------------------------------------------------------------------------------------------ solve (1 CTA / problem)
-// dense Cholesky of the reduced camera system in shared memory, triangular solves, back-substitution of the inverse
-// depths, model cost change -(J s)'(r + J s / 2), candidate point Plus(x, delta).
-__global__ void __launch_bounds__(256) ba_solve_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+
+// ------------------------------------------------------------------------------------------ gather-form Schur (no atomics)
+// The reduced camera system is assembled block by block: S[bi][bj] = sum over the landmarks that see both poses of
+//   F_u'F_v - w_u w_v' / (E'E + D^2)        (u, v = the landmark's slots holding poses bi, bj; w = F'e)
+// A slot is 0 for the anchor keyframe and 1 + k for the landmark's k-th observation.  The (block -> landmark pairs)
+// lists depend only on the problem's structure, so they are built once per solve (deterministically, in landmark
+// order) by ba_keys_*; every LM iteration then runs ba_lm_kernel (per-landmark E'E, E'b, F'e) and ba_gather_kernel
+// (one warp per block, fixed summation order -> bit-reproducible results, zero atomics).
+__device__ __forceinline__ int slot_col(const BaProblem& P, int l, int s) {
+    return s == 0 ? P.pose_col[P.anch_kf[l]] : P.pose_col[P.obs_kf[P.lm_obs[P.lm_start[l] + s - 1]]];
+}
+__device__ __forceinline__ int key_of(int bi, int bj) {   // bi <= bj, row-major upper triangle over NBMAX
+    return bi * NBMAX - bi * (bi - 1) / 2 + (bj - bi);
+}
+
+// count the entries of one block (MODE 0) or fill them (MODE 1); one warp per block, landmarks scanned in order, so
+// the entry order (and with it every floating-point summation order downstream) is deterministic.
+template <int MODE>
+__global__ void __launch_bounds__(32) ba_keys_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    const int nb = P.st->ncols / 6;
+    const int key = blockIdx.x;
+    int bi = 0, rem = key;
+    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
+    const int bj = bi + rem;
+    const int lane = threadIdx.x;
+    if (bi >= nb || bj >= nb) { if (MODE == 0 && lane == 0) P.key_start[key + 1] = 0; return; }
+    if (MODE == 1 && !P.st->use_gather) return;
+    int total = 0;
+    const int base = MODE == 1 ? P.key_start[key] : 0;
+    for (int l0 = 0; l0 < D.nlm; l0 += 32) {
+        const int l = l0 + lane;
+        const int ns = l < D.nlm ? (P.lm_start[l + 1] - P.lm_start[l]) : 0;   // observations; slots 0..ns when ns > 0
+        int cnt = 0;
+        if (ns > 0)
+            for (int u = 0; u <= ns; u++) {
+                const int cu = slot_col(P, l, u);
+                if (cu < 0) continue;
+                for (int v = u; v <= ns; v++) {
+                    const int cv = slot_col(P, l, v);
+                    if (cv >= 0 && min(cu, cv) / 6 == bi && max(cu, cv) / 6 == bj) cnt++;
+                }
+            }
+        int maxc = cnt;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, off));
+        for (int r = 0; r < maxc; r++) {      // round r: every lane contributes its r-th pair (usually maxc == 1)
+            const bool has = r < cnt;
+            const uint32_t bal = __ballot_sync(0xffffffffu, has);
+            if (MODE == 1 && has) {
+                uint32_t ent = 0;
+                int seen = 0;
+                for (int u = 0; u <= ns && seen <= r; u++) {
+                    const int cu = slot_col(P, l, u);
+                    if (cu < 0) continue;
+                    for (int v = u; v <= ns && seen <= r; v++) {
+                        const int cv = slot_col(P, l, v);
+                        if (cv >= 0 && min(cu, cv) / 6 == bi && max(cu, cv) / 6 == bj) {
+                            if (seen == r) {   // (slot holding pose bi, slot holding pose bj)
+                                const int s_i = (cu <= cv) ? u : v, s_j = (cu <= cv) ? v : u;
+                                ent = ((uint32_t)l << 16) | ((uint32_t)s_i << 8) | (uint32_t)s_j;
+                            }
+                            seen++;
+                        }
+                    }
+                }
+                const int pos = base + total + __popc(bal & ((1u << lane) - 1));
+                if (pos < D.ecap) P.entries[pos] = ent;
+            }
+            total += __popc(bal);
+        }
+    }
+    if (MODE == 0 && lane == 0) P.key_start[key + 1] = total;
+}
+
+// exclusive scan of the key counts + decision whether the gather path can be used (entry capacity, slot ids < 256)
+__global__ void __launch_bounds__(256) ba_keys_scan_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    __shared__ int maxobs_s;
+    if (threadIdx.x == 0) maxobs_s = 0;
+    __syncthreads();
+    int mo = 0;
+    for (int l = threadIdx.x; l < D.nlm; l += 256) mo = max(mo, P.lm_start[l + 1] - P.lm_start[l]);
+    atomicMax(&maxobs_s, mo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        P.key_start[0] = 0;
+        for (int k = 0; k < MAXKEYS; k++) { const int c = P.key_start[k + 1]; run += c; P.key_start[k + 1] = run; }
+        BaState& st = *P.st;
+        st.nentries = run;
+        st.nkeys = MAXKEYS;
+        st.nb = st.ncols / 6;
+        st.use_gather = (run <= D.ecap && maxobs_s < 255 && D.nlm < 65536) ? 1 : 0;
+    }
+}
+
+// per-landmark Schur ingredients: E'E + D^2, E'b, F'e for the anchor slot (wa) and every observation slot (wp)
+__global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    if (P.st->done || !P.st->use_gather) return;
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= D.nlm) return;
+    const int b = P.lm_start[l], e = P.lm_start[l + 1];
+    if (e == b) return;
+    const int ca = P.pose_col[P.anch_kf[l]];
+    const double sce = P.sce[l];
+    double ete = P.De[l] * P.De[l], etb = 0, wa[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = b; i < e; i++) {
+        const int o = P.lm_obs[i];
+        const int cp = P.pose_col[P.obs_kf[o]];
+        const double e0 = P.Jd[2 * o] * sce, e1 = P.Jd[2 * o + 1] * sce;
+        ete += e0 * e0 + e1 * e1;
+        etb += e0 * P.res[2 * o] + e1 * P.res[2 * o + 1];
+        for (int c = 0; c < 6; c++) {
+            if (ca >= 0) wa[c] += (e0 * P.Ja[12 * o + c] + e1 * P.Ja[12 * o + 6 + c]) * P.scf[ca + c];
+            P.wp[6 * o + c] = cp >= 0 ? (e0 * P.Jp[12 * o + c] + e1 * P.Jp[12 * o + 6 + c]) * P.scf[cp + c] : 0.0;
+        }
+    }
+    P.ete[l] = ete;
+    P.etb[l] = etb;
+    for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
+}
+
+// one warp per upper-triangular 6x6 block (bi <= bj): lanes stride over the block's entries, each keeps a private
+// 6x6 (+ rhs) accumulator, then a fixed-order shuffle reduction; the block and its mirror are stored, no atomics.
+__global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    const BaState& st = *P.st;
+    if (st.done || !st.use_gather) return;
+    const int key = blockIdx.x;
+    int bi = 0, rem = key;
+    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
+    const int bj = bi + rem;
+    if (bi >= st.nb || bj >= st.nb) return;
+    const int lane = threadIdx.x;
+    const int ci = 6 * bi, cj = 6 * bj;
+    double acc[36], rh[6];
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) rh[i] = 0.0;
+    double sci[6], scj[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
+    const int eb = P.key_start[key], ee = P.key_start[key + 1];
+    for (int idx = eb + lane; idx < ee; idx += 32) {
+        const uint32_t en = P.entries[idx];
+        const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
+        const int ob = P.lm_start[l];
+        const double inv = 1.0 / P.ete[l], etb = P.etb[l];
+        const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+        double wu[6], wv[6], C[36];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            wu[c] = su ? P.wp[6 * ou + c] : P.wa[6 * l + c];
+            wv[c] = sv ? P.wp[6 * ov + c] : P.wa[6 * l + c];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) C[6 * a + c] = -wu[a] * inv * wv[c];
+        // F_u' F_v: non-zero only when both slots share a residual row pair
+        if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
+            const int oe = P.lm_start[l + 1];
+            for (int i = ob; i < oe; i++) {
+                const int o = P.lm_obs[i];
+                double F0[6], F1[6];
+#pragma unroll
+                for (int c = 0; c < 6; c++) { F0[c] = P.Ja[12 * o + c] * sci[c]; F1[c] = P.Ja[12 * o + 6 + c] * sci[c]; }
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    rh[a] += F0[a] * P.res[2 * o] + F1[a] * P.res[2 * o + 1];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) C[6 * a + c] += F0[a] * F0[c] + F1[a] * F1[c];
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) rh[a] -= wu[a] * inv * etb;
+        } else if (su == sv) {                           // observation x itself
+            double F0[6], F1[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) { F0[c] = P.Jp[12 * ou + c] * sci[c]; F1[c] = P.Jp[12 * ou + 6 + c] * sci[c]; }
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                rh[a] += F0[a] * P.res[2 * ou] + F1[a] * P.res[2 * ou + 1] - wu[a] * inv * etb;
+#pragma unroll
+                for (int c = 0; c < 6; c++) C[6 * a + c] += F0[a] * F0[c] + F1[a] * F1[c];
+            }
+        } else if (su == 0 || sv == 0) {                 // anchor x observation (either order): rows of that observation
+            const int o = su ? ou : ov;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const double a0 = (su ? P.Jp[12 * o + a] : P.Ja[12 * o + a]) * sci[a];
+                const double a1 = (su ? P.Jp[12 * o + 6 + a] : P.Ja[12 * o + 6 + a]) * sci[a];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const double b0 = (sv ? P.Jp[12 * o + c] : P.Ja[12 * o + c]) * scj[c];
+                    const double b1 = (sv ? P.Jp[12 * o + 6 + c] : P.Ja[12 * o + 6 + c]) * scj[c];
+                    C[6 * a + c] += a0 * b0 + a1 * b1;
+                }
+            }
+        }
+        // two different slots on the same pose (never produced by localBA): the ordered pair (v, u) lands in the same
+        // diagonal block, add its transpose as well
+        const bool dup = (bi == bj) && (su != sv);
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[6 * a + c] += C[6 * a + c] + (dup ? C[6 * c + a] : 0.0);
+    }
+    // fixed-order butterfly reduction
+#pragma unroll
+    for (int i = 0; i < 36; i++)
+#pragma unroll
+        for (int off = 16; off; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    if (bi == bj) {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int off = 16; off; off >>= 1) rh[i] += __shfl_xor_sync(0xffffffffu, rh[i], off);
+    }
+    if (lane == 0) {
+        if (bi == bj) {
+            for (int a = 0; a < 6; a++) {
+                P.rhs[ci + a] = rh[a];
+                for (int c = 0; c < 6; c++) {
+                    const double v = acc[6 * a + c] + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
+                    P.S[(ci + a) * NMAX + ci + c] = v;
+                }
+            }
+        } else {
+            for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 6; c++) {
+                    P.S[(ci + a) * NMAX + cj + c] = acc[6 * a + c];
+                    P.S[(cj + c) * NMAX + ci + a] = acc[6 * a + c];
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ Cholesky (1 CTA / problem)
+// Blocked right-looking Cholesky of the <= 126 x 126 reduced system in shared memory: per 8-column panel, warp 0 factors
+// the panel with warp-synchronous steps, then all 1024 threads apply the rank-8 update to the trailing lower triangle.
+// Followed by the two triangular solves (warp 0).  yf = S^-1 rhs.
+constexpr int CH_THREADS = 1024, CH_NB = 8;
+__global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     extern __shared__ double sm[];
     const BaProblem P = probs[blockIdx.x];
     BaState& st = *P.st;
     if (st.done) return;
-    const int n = st.ncols, tid = threadIdx.x;
-    const int ld = n + 1;   // padded leading dimension (bank conflicts)
-    double* L = sm;                 // n x ld
-    double* y = sm + (size_t)NMAX * (NMAX + 1);   // n
-    double* red = y + NMAX;         // 256
+    const int n = st.ncols, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = NMAX + 1;
+    double* L = sm;               // NMAX x ld
+    double* y = sm + NMAX * ld;   // NMAX
     __shared__ int ok_s;
-    for (int i = tid; i < n * n; i += 256) { const int r = i / n, c = i - r * n; L[r * ld + c] = P.S[r * NMAX + c]; }
+    for (int i = tid; i < n * n; i += CH_THREADS) { const int r = i / n, c = i - r * n; L[r * ld + c] = P.S[r * NMAX + c]; }
     if (tid == 0) ok_s = 1;
     __syncthreads();
-    for (int j = 0; j < n; j++) {
-        // column j: L[j][j] = sqrt(A[j][j]) (the trailing updates below have already been applied)
-        if (tid == 0) {
-            const double d = L[j * ld + j];
-            if (!(d > 0)) ok_s = 0;
-            L[j * ld + j] = sqrt(d > 0 ? d : 1.0);
+    for (int j0 = 0; j0 < n; j0 += CH_NB) {
+        const int jb = min(CH_NB, n - j0);
+        if (warp == 0) {
+            for (int j = j0; j < j0 + jb; j++) {
+                double d = L[j * ld + j];
+                if (!(d > 0)) { if (lane == 0) ok_s = 0; d = 1.0; }
+                const double dj = sqrt(d);
+                __syncwarp();
+                if (lane == 0) L[j * ld + j] = dj;
+                for (int i = j + 1 + lane; i < n; i += 32) L[i * ld + j] /= dj;
+                __syncwarp();
+                // update the remaining columns of the panel
+                for (int k = j + 1; k < j0 + jb; k++) {
+                    const double lkj = L[k * ld + j];
+                    for (int i = k + lane; i < n; i += 32) L[i * ld + k] -= L[i * ld + j] * lkj;
+                }
+                __syncwarp();
+            }
         }
         __syncthreads();
-        const double djj = L[j * ld + j];
-        for (int i = j + 1 + tid; i < n; i += 256) L[i * ld + j] /= djj;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][k] -= L[i][j] * L[k][j], j < k <= i
-        const int m = n - j - 1;
-        for (int t = tid; t < m * m; t += 256) {
-            const int i = j + 1 + t / m, k = j + 1 + t % m;
-            if (k <= i) L[i * ld + k] -= L[i * ld + j] * L[k * ld + j];
+        // trailing update: A[i][k] -= sum_{c in panel} L[i][c] L[k][c],  j0 + jb <= k <= i < n
+        const int t0 = j0 + jb, m = n - t0;
+        for (int t = tid; t < m * m; t += CH_THREADS) {
+            const int i = t0 + t / m, k = t0 + t % m;
+            if (k > i) continue;
+            double s = 0;
+            for (int c = j0; c < j0 + jb; c++) s += L[i * ld + c] * L[k * ld + c];
+            L[i * ld + k] -= s;
         }
         __syncthreads();
     }
-    // forward / backward substitution by warp 0 (lane-strided dot products)
-    if (tid < 32) {
+    if (warp == 0) {
         for (int i = 0; i < n; i++) {
             double s = 0;
-            for (int k = tid; k < i; k += 32) s += L[i * ld + k] * y[k];
+            for (int k = lane; k < i; k += 32) s += L[i * ld + k] * y[k];
 #pragma unroll
             for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (tid == 0) y[i] = (P.rhs[i] - s) / L[i * ld + i];
+            if (lane == 0) y[i] = (P.rhs[i] - s) / L[i * ld + i];
             __syncwarp();
         }
         for (int i = n - 1; i >= 0; i--) {
             double s = 0;
-            for (int k = i + 1 + tid; k < n; k += 32) s += L[k * ld + i] * y[k];
+            for (int k = i + 1 + lane; k < n; k += 32) s += L[k * ld + i] * y[k];
 #pragma unroll
             for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (tid == 0) y[i] = (y[i] - s) / L[i * ld + i];
+            if (lane == 0) y[i] = (y[i] - s) / L[i * ld + i];
             __syncwarp();
         }
+        for (int i = lane; i < n; i += 32) P.yf[i] = y[i];
+        if (lane == 0) st.chol_ok = ok_s;
     }
-    __syncthreads();
-    const bool ok = ok_s != 0;
-    for (int i = tid; i < n; i += 256) P.yf[i] = y[i];
-    // back-substitute the inverse depths: ye = (E'b - E'F yf) / (E'E + D^2)
-    for (int l = tid; l < D.nlm; l += 256) {
-        const int b = P.lm_start[l], e = P.lm_start[l + 1];
-        if (e == b) { P.ye[l] = 0; continue; }
-        double s = P.etb[l];
-        const int ca = P.pose_col[P.anch_kf[l]];
-        if (ca >= 0) for (int c = 0; c < 6; c++) s -= P.wa[6 * l + c] * y[ca + c];
-        for (int i = b; i < e; i++) {
-            const int o = P.lm_obs[i];
-            const int cp = P.pose_col[P.obs_kf[o]];
-            if (cp >= 0) for (int c = 0; c < 6; c++) s -= P.wp[6 * o + c] * y[cp + c];
-        }
-        P.ye[l] = s / P.ete[l];
-    }
-    __syncthreads();
-    // model cost change with step = -y (scaled coordinates)
+}
+
+// ------------------------------------------------------------------------------------------ back-substitution (thread / landmark)
+// ye = (E'b - E'F yf) / (E'E + D^2), candidate inverse depths, this landmark's share of the model cost change
+// -(J s)'(r + J s / 2); CTA (0, p) also builds the candidate poses Plus(x, delta).
+__global__ void __launch_bounds__(BS_THREADS) ba_backsub_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    __shared__ double red[BS_THREADS];
+    if (P.st->done) return;
+    const int l = blockIdx.x * BS_THREADS + threadIdx.x;
     double acc = 0;
-    for (int o = tid; o < D.nobs; o += 256) {
-        const int l = P.obs_lm[o];
-        if (l < 0) continue;
-        const int ca = P.pose_col[P.anch_kf[l]], cp = P.pose_col[P.obs_kf[o]];
-        const double se = -P.ye[l] * P.sce[l];
-        double m0 = P.Jd[2 * o] * se, m1 = P.Jd[2 * o + 1] * se;
-        for (int c = 0; c < 6; c++) {
-            if (ca >= 0) { const double s = -y[ca + c] * P.scf[ca + c]; m0 += P.Ja[12 * o + c] * s; m1 += P.Ja[12 * o + 6 + c] * s; }
-            if (cp >= 0) { const double s = -y[cp + c] * P.scf[cp + c]; m0 += P.Jp[12 * o + c] * s; m1 += P.Jp[12 * o + 6 + c] * s; }
-        }
-        acc += m0 * (P.res[2 * o] + m0 / 2.0) + m1 * (P.res[2 * o + 1] + m1 / 2.0);
+    if (blockIdx.x == 0 && (int)threadIdx.x < D.nkf) {
+        const int k = threadIdx.x, c0 = P.pose_col[k];
+        if (c0 >= 0) {
+            double dlt[6];
+            for (int i = 0; i < 6; i++) dlt[i] = -P.yf[c0 + i] * P.scf[c0 + i];
+            se3_plus(P.poses + 7 * k, dlt, P.cand_poses + 7 * k);
+        } else
+            for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = P.poses[7 * k + i];
     }
-    const double tot = block_sum<256>(acc, red);
-    const double model_change = -tot;
-    const bool valid = ok && (model_change > 0.0);
-    // candidate point
-    if (valid) {
-        for (int k = tid; k < D.nkf; k += 256) {
-            const int c0 = P.pose_col[k];
-            if (c0 >= 0) {
-                double dlt[6];
-                for (int i = 0; i < 6; i++) dlt[i] = -y[c0 + i] * P.scf[c0 + i];
-                se3_plus(P.poses + 7 * k, dlt, P.cand_poses + 7 * k);
-            } else
-                for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = P.poses[7 * k + i];
-        }
-        for (int l = tid; l < D.nlm; l += 256)
-            P.cand_invd[l] = P.invd[l] + ((P.lm_start[l + 1] > P.lm_start[l]) ? -P.ye[l] * P.sce[l] : 0.0);
+    if (l < D.nlm) {
+        const int b = P.lm_start[l], e = P.lm_start[l + 1];
+        double ye = 0;
+        if (e > b) {
+            double s = P.etb[l];
+            const int ca = P.pose_col[P.anch_kf[l]];
+            if (ca >= 0) for (int c = 0; c < 6; c++) s -= P.wa[6 * l + c] * P.yf[ca + c];
+            for (int i = b; i < e; i++) {
+                const int o = P.lm_obs[i];
+                const int cp = P.pose_col[P.obs_kf[o]];
+                if (cp >= 0) for (int c = 0; c < 6; c++) s -= P.wp[6 * o + c] * P.yf[cp + c];
+            }
+            ye = s / P.ete[l];
+            const double se = -ye * P.sce[l];
+            for (int i = b; i < e; i++) {
+                const int o = P.lm_obs[i];
+                const int cp = P.pose_col[P.obs_kf[o]];
+                double m0 = P.Jd[2 * o] * se, m1 = P.Jd[2 * o + 1] * se;
+                for (int c = 0; c < 6; c++) {
+                    if (ca >= 0) { const double q = -P.yf[ca + c] * P.scf[ca + c]; m0 += P.Ja[12 * o + c] * q; m1 += P.Ja[12 * o + 6 + c] * q; }
+                    if (cp >= 0) { const double q = -P.yf[cp + c] * P.scf[cp + c]; m0 += P.Jp[12 * o + c] * q; m1 += P.Jp[12 * o + 6 + c] * q; }
+                }
+                acc += m0 * (P.res[2 * o] + m0 / 2.0) + m1 * (P.res[2 * o + 1] + m1 / 2.0);
+            }
+            P.cand_invd[l] = P.invd[l] + se;
+        } else
+            P.cand_invd[l] = P.invd[l];
+        P.ye[l] = ye;
     }
-    if (tid == 0) { st.model_change = model_change; st.step_ok = valid ? 1 : 0; }
+    const double tot = block_sum<BS_THREADS>(acc, red);
+    if (threadIdx.x == 0) P.mc_part[blockIdx.x] = tot;
 }
 
 // ------------------------------------------------------------------------------------------ control: after the step
@@ -667,12 +933,20 @@ __global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restric
     __shared__ int accept_s;
     const int tid = threadIdx.x;
     if (st.done) return;
-    if (!st.step_ok) {   // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
+    // model cost change -(J s)'(r + J s / 2) from the back-substitution partials (fixed order)
+    double mcs = 0;
+    for (int i = tid; i < D.nbs; i += 256) mcs += P.mc_part[i];
+    const double model_change = -block_sum<256>(mcs, red);
+    const bool valid = st.chol_ok && (model_change > 0.0);
+    __syncthreads();
+    if (!valid) {   // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
         if (tid == 0) {
+            st.model_change = model_change;
             if (++st.invalid_steps >= 5) { st.term = 2; st.done = 1; }
             st.radius *= 0.5;
             st.reuse_diagonal = 1;
             st.push_cost = st.x_cost;
+            st.chol_ok = 1;
         }
         return;
     }
@@ -695,7 +969,8 @@ __global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restric
         if (step_norm <= 1e-8 * (st.xnorm + 1e-8)) { st.term = 0; st.done = 1; }                 // ParameterToleranceReached
         else if (fabs(st.x_cost - cand_cost) <= 1e-3 * st.x_cost) { st.term = 0; st.done = 1; }  // FunctionToleranceReached
         else {
-            const double mc = st.model_change;
+            const double mc = model_change;
+            st.model_change = model_change;
             const double rel = (st.se_cur - cand_cost) / mc;
             const double hist = (st.se_ref - cand_cost) / (st.se_acc_ref + mc);
             const double quality = fmax(rel, hist);
@@ -782,8 +1057,10 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     d += (size_t)NMAX * NMAX + 2 * NMAX;             // S rhs yf
     d += (size_t)nkf * 7 + nlm;                      // cand
     d += (size_t)nblk;                               // cost partials
+    d += (size_t)((nlm + BS_THREADS - 1) / BS_THREADS);   // model-cost partials
     size_t bytes = d * sizeof(double);
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
+    bytes += align_up((size_t)(MAXKEYS + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
     bytes += align_up(sizeof(BaState), 8);
     return align_up(bytes, 256);
 }
@@ -800,42 +1077,70 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
     const int nblk = (nobs + LIN_THREADS - 1) / LIN_THREADS;
     const size_t per = ba_ws_bytes(nkf, nlm, nobs, nblk);
     const size_t tab = align_up(sizeof(BaProblem) * nprob, 256);
-    uint8_t* ws = (uint8_t*)alva_scratch(ctx, tab + per * nprob);
-    if (!ws) return ALVA_E_CUDA;
-    // the (small) table of per-problem pointers is built on the host and copied once per call
-    std::string hostbuf(sizeof(BaProblem) * nprob, '\0');
-    BaProblem* hp = reinterpret_cast<BaProblem*>(&hostbuf[0]);
-    for (int p = 0; p < nprob; p++) {
-        BaProblem& P = hp[p];
-        P.calib = calib + 4 * (size_t)p; P.poses = poses + 7 * (size_t)nkf * p; P.pose_const = pose_const + (size_t)nkf * p;
-        P.invd = invd + (size_t)nlm * p; P.anch_kf = anch_kf + (size_t)nlm * p; P.anch_uv = anch_uv + 2 * (size_t)nlm * p;
-        P.obs_kf = obs_kf + (size_t)nobs * p; P.obs_lm = obs_lm + (size_t)nobs * p; P.obs_uv = obs_uv + 2 * (size_t)nobs * p;
-        double* d = reinterpret_cast<double*>(ws + tab + per * p);
-        auto take = [&](size_t n) { double* r = d; d += n; return r; };
-        P.res = take(2 * (size_t)nobs); P.Ja = take(12 * (size_t)nobs); P.Jp = take(12 * (size_t)nobs); P.Jd = take(2 * (size_t)nobs);
-        P.wp = take(6 * (size_t)nobs);
-        P.nf = take(NMAX); P.gf = take(NMAX); P.scf = take(NMAX); P.diagf = take(NMAX); P.Df = take(NMAX);
-        P.ne = take(nlm); P.ge = take(nlm); P.sce = take(nlm); P.diage = take(nlm); P.De = take(nlm);
-        P.ete = take(nlm); P.etb = take(nlm); P.wa = take(6 * (size_t)nlm); P.ye = take(nlm);
-        P.S = take((size_t)NMAX * NMAX); P.rhs = take(NMAX); P.yf = take(NMAX);
-        P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
-        P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
-        uint8_t* b = reinterpret_cast<uint8_t*>(d);
-        P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
-        P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
-        P.lm_obs = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
-        P.st = reinterpret_cast<BaState*>(b);
+    if (tab + per * nprob > ctx->ba_ws_bytes) {
+        if (ctx->ba_ws) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->ba_ws)); ctx->ba_ws = nullptr; ctx->ba_ws_bytes = 0; }
+        ALVA_CUDA(cudaMalloc(&ctx->ba_ws, tab + per * nprob));
+        ctx->ba_ws_bytes = tab + per * nprob;
+        ctx->ba_table_key = 0;
     }
-    ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
-    ALVA_CUDA(cudaStreamSynchronize(ctx->stream));   // hostbuf is pageable: make the copy complete before it dies
+    uint8_t* ws = (uint8_t*)ctx->ba_ws;
+    // The (small) table of per-problem pointers lives at the head of the scratch block.  It only depends on the argument
+    // pointers and dimensions, so it is rebuilt (one synchronous copy) only when those change -- a steady-state solve
+    // enqueues kernels and nothing else.
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    mix((uint64_t)(uintptr_t)ws); mix(nprob); mix(nkf); mix(nlm); mix(nobs); mix((uint64_t)g_ba_dense_schur);
+    mix((uint64_t)(uintptr_t)calib); mix((uint64_t)(uintptr_t)poses); mix((uint64_t)(uintptr_t)pose_const); mix((uint64_t)(uintptr_t)invd);
+    mix((uint64_t)(uintptr_t)anch_kf); mix((uint64_t)(uintptr_t)anch_uv); mix((uint64_t)(uintptr_t)obs_kf);
+    mix((uint64_t)(uintptr_t)obs_lm); mix((uint64_t)(uintptr_t)obs_uv);
+    if (key != ctx->ba_table_key) {
+        std::string hostbuf(sizeof(BaProblem) * nprob, '\0');
+        BaProblem* hp = reinterpret_cast<BaProblem*>(&hostbuf[0]);
+        for (int p = 0; p < nprob; p++) {
+            BaProblem& P = hp[p];
+            P.calib = calib + 4 * (size_t)p; P.poses = poses + 7 * (size_t)nkf * p; P.pose_const = pose_const + (size_t)nkf * p;
+            P.invd = invd + (size_t)nlm * p; P.anch_kf = anch_kf + (size_t)nlm * p; P.anch_uv = anch_uv + 2 * (size_t)nlm * p;
+            P.obs_kf = obs_kf + (size_t)nobs * p; P.obs_lm = obs_lm + (size_t)nobs * p; P.obs_uv = obs_uv + 2 * (size_t)nobs * p;
+            double* d = reinterpret_cast<double*>(ws + tab + per * p);
+            auto take = [&](size_t n) { double* r = d; d += n; return r; };
+            P.res = take(2 * (size_t)nobs); P.Ja = take(12 * (size_t)nobs); P.Jp = take(12 * (size_t)nobs); P.Jd = take(2 * (size_t)nobs);
+            P.wp = take(6 * (size_t)nobs);
+            P.nf = take(NMAX); P.gf = take(NMAX); P.scf = take(NMAX); P.diagf = take(NMAX); P.Df = take(NMAX);
+            P.ne = take(nlm); P.ge = take(nlm); P.sce = take(nlm); P.diage = take(nlm); P.De = take(nlm);
+            P.ete = take(nlm); P.etb = take(nlm); P.wa = take(6 * (size_t)nlm); P.ye = take(nlm);
+            P.S = take((size_t)NMAX * NMAX); P.rhs = take(NMAX); P.yf = take(NMAX);
+            P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
+            P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
+            P.mc_part = take((size_t)((nlm + BS_THREADS - 1) / BS_THREADS));
+            uint8_t* b = reinterpret_cast<uint8_t*>(d);
+            P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
+            P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
+            P.lm_obs = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
+            P.key_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(MAXKEYS + 1) * 4, 8);
+            P.entries = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+            P.st = reinterpret_cast<BaState*>(b);
+        }
+        ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
+        ALVA_CUDA(cudaStreamSynchronize(ctx->stream));   // hostbuf is pageable: the copy must finish before it dies
+        ctx->ba_table_key = key;
+    }
     const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
-    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4};
+    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4, 8 * nobs + 2 * nlm, (nlm + BS_THREADS - 1) / BS_THREADS};
     const bool dense = g_ba_dense_schur != 0;
-    const size_t solve_smem = ((size_t)NMAX * (NMAX + 1) + NMAX + 256) * sizeof(double);
-    ALVA_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + NMAX) * sizeof(double);
+    ALVA_CUDA(cudaFuncSetAttribute(ba_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     ba_setup_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
+    const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob);
+    if (!dense) {   // structure of the gather-form Schur complement, once per solve
+        ba_keys_kernel<0><<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_keys_scan_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_keys_kernel<1><<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+    }
     for (int it = 0; it <= max_iter; it++) {
         ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
@@ -848,10 +1153,16 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
             ba_syrk_dmma_kernel<<<syrk_grid, 128, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
         } else {
-            ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
+            ba_lm_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);           // gather path (no-op if structure too large)
+            ALVA_LAUNCH_CHECK(ctx);
+            ba_gather_kernel<<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+            ALVA_LAUNCH_CHECK(ctx);
+            ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);  // atomic fallback (no-op when gather ran)
             ALVA_LAUNCH_CHECK(ctx);
         }
-        ba_solve_kernel<<<nprob, 256, solve_smem, ctx->stream>>>(dp, D);
+        ba_chol_kernel<<<nprob, CH_THREADS, chol_smem, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_backsub_kernel<<<bs_grid, BS_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_linearize_kernel<false><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);

@@ -57,6 +57,9 @@ struct alva_pipeline {
     bool have_map = false, have_ba = false;
     // host-step staging
     uint8_t* in_dev = nullptr;
+    static constexpr int NCHUNK = 4;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[NCHUNK] = {}, start_ev = nullptr;
     static constexpr int NEV = 64;      // ring of event pairs around the fused front-end launch
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
     bool profile = false;
@@ -76,6 +79,12 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
     for (void* a : p->allocs) cudaFree(a);
+    if (p->copy_stream) {
+        cudaStreamSynchronize(p->copy_stream);
+        cudaStreamDestroy(p->copy_stream);
+        for (int i = 0; i < alva_pipeline::NCHUNK; i++) if (p->chunk_ev[i]) cudaEventDestroy(p->chunk_ev[i]);
+        if (p->start_ev) cudaEventDestroy(p->start_ev);
+    }
     for (int i = 0; i < alva_pipeline::NEV; i++) {
         if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
         if (p->ev1[i]) cudaEventDestroy(p->ev1[i]);
@@ -177,57 +186,104 @@ extern "C" int alva_pipeline_frontend_ms(alva_pipeline* p, float* ms, int n) {
 int alva_frontend_main_launch(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1, int thr,
                               uint32_t* keys, int32_t* counts, int cap);
 
-extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) {
-    if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
-    if (p->cfg.map_size > 0 && !p->have_map) { alva_set_error("pipeline: local map not set"); return ALVA_E_STATE; }
-    if (p->nprob > 0 && !p->have_ba) { alva_set_error("pipeline: BA problems not set"); return ALVA_E_STATE; }
+// Stages 1-4 on frames [f0, f0 + nf) of the batch (every buffer is frame-major, so a range is a pointer offset).
+static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, int nf, bool timed) {
     alva_ctx* ctx = p->ctx;
     const alva_pipeline_config& c = p->cfg;
-    const int B = c.batch, w = c.w, h = c.h;
+    const int w = c.w, h = c.h;
     cudaStream_t st = ctx->stream;
+    const size_t F = (size_t)f0;
+    uint8_t *l0 = p->l0 + F * w * h, *l1 = p->l1 + F * p->w1 * p->h1, *l2 = p->l2 + F * p->w2 * p->h2, *l3 = p->l3 + F * p->w3 * p->h3;
+    uint8_t* blur = p->blur + F * w * h;
+    uint32_t *keys = p->keys + F * p->kcap, *sel = p->sel + F * p->fcap;
+    int32_t *counts = p->counts + F, *selcounts = p->selcounts + F;
     // 1. fused front end (+ pyramid levels 2, 3)
-    ALVA_CUDA(cudaMemsetAsync(p->counts, 0, sizeof(int32_t) * B, st));
+    ALVA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * nf, st));
     const int slot = (int)(p->step_index % alva_pipeline::NEV);
-    if (p->profile) ALVA_CUDA(cudaEventRecord(p->ev0[slot], st));
-    if (int e = alva_frontend_main_launch(ctx, rgba_dev, w, h, B, p->l0, p->l1, c.fast_thr, p->keys, p->counts, p->kcap)) return e;
-    if (p->profile) { ALVA_CUDA(cudaEventRecord(p->ev1[slot], st)); p->step_index++; }
-    if (int e = alva_k_pyrdown(ctx, p->l1, p->l2, p->w1, p->h1, B)) return e;
-    if (int e = alva_k_pyrdown(ctx, p->l2, p->l3, p->w2, p->h2, B)) return e;
+    if (timed && p->profile) ALVA_CUDA(cudaEventRecord(p->ev0[slot], st));
+    if (int e = alva_frontend_main_launch(ctx, rgba_dev + F * w * h * 4, w, h, nf, l0, l1, c.fast_thr, keys, counts, p->kcap)) return e;
+    if (timed && p->profile) { ALVA_CUDA(cudaEventRecord(p->ev1[slot], st)); p->step_index++; }
+    if (int e = alva_k_pyrdown(ctx, l1, l2, p->w1, p->h1, nf)) return e;
+    if (int e = alva_k_pyrdown(ctx, l2, l3, p->w2, p->h2, nf)) return e;
     // 2. retainBest(nfeatures) inside ORB's 31-px border, row-major
-    if (int e = alva_k_retain_best(ctx, p->keys, p->counts, p->kcap, B, w, h, c.nfeatures, 31, p->sel, p->selcounts, p->fcap)) return e;
-    clamp_counts_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->selcounts, B, p->fcap);
+    if (int e = alva_k_retain_best(ctx, keys, counts, p->kcap, nf, w, h, c.nfeatures, 31, sel, selcounts, p->fcap)) return e;
+    clamp_counts_kernel<<<(nf + 127) / 128, 128, 0, st>>>(selcounts, nf, p->fcap);
     ALVA_LAUNCH_CHECK(ctx);
-    keys_to_points_kernel<<<dim3((p->fcap + 127) / 128, B), 128, 0, st>>>(p->sel, p->selcounts, p->fcap, p->pts);
+    keys_to_points_kernel<<<dim3((p->fcap + 127) / 128, nf), 128, 0, st>>>(sel, selcounts, p->fcap, p->pts + F * p->fcap * 2);
     ALVA_LAUNCH_CHECK(ctx);
     // 3. ORB
-    if (int e = alva_k_orb_blur(ctx, p->l0, p->blur, w, h, B, c.orb_flags & ALVA_ORB_FMA)) return e;
-    if (int e = alva_k_orb_describe(ctx, p->l0, p->blur, w, h, B, p->pts, p->selcounts, p->fcap, c.orb_flags, p->desc, p->kept, p->angles)) return e;
+    if (int e = alva_k_orb_blur(ctx, l0, blur, w, h, nf, c.orb_flags & ALVA_ORB_FMA)) return e;
+    if (int e = alva_k_orb_describe(ctx, l0, blur, w, h, nf, p->pts + F * p->fcap * 2, selcounts, p->fcap, c.orb_flags,
+                                    p->desc + F * p->fcap * 32, p->kept + F * p->fcap, p->angles + F * p->fcap))
+        return e;
     // 4. match against the local map
     if (c.map_size > 0)
-        if (int e = alva_k_hamming_knn2_batch(ctx, p->desc, p->selcounts, B, p->fcap, p->map, c.map_size, p->matches)) return e;
-    // 5. local BA for this step's keyframes
-    if (p->nprob > 0) {
-        const size_t np = p->nprob;
-        ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
-        ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
-        if (int e = alva_k_ba_solve(ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
-                                    p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber,
-                                    c.ba_max_iter, p->ba_summary))
+        if (int e = alva_k_hamming_knn2_batch(ctx, p->desc + F * p->fcap * 32, selcounts, nf, p->fcap, p->map, c.map_size,
+                                              p->matches + F * p->fcap * 4))
             return e;
-    }
     return 0;
 }
 
-// Host-buffer step (the e2e leg): H2D of the batch, the step, D2H of the per-frame results.
+// 5. local BA for this step's keyframes
+static int pipeline_ba(alva_pipeline* p) {
+    if (p->nprob <= 0) return 0;
+    const alva_pipeline_config& c = p->cfg;
+    cudaStream_t st = p->ctx->stream;
+    const size_t np = p->nprob;
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
+    return alva_k_ba_solve(p->ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
+                           p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber, c.ba_max_iter,
+                           p->ba_summary);
+}
+
+static int pipeline_ready(alva_pipeline* p) {
+    if (p->cfg.map_size > 0 && !p->have_map) { alva_set_error("pipeline: local map not set"); return ALVA_E_STATE; }
+    if (p->nprob > 0 && !p->have_ba) { alva_set_error("pipeline: BA problems not set"); return ALVA_E_STATE; }
+    return 0;
+}
+
+extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) {
+    if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
+    if (int e = pipeline_ready(p)) return e;
+    if (int e = pipeline_frames(p, rgba_dev, 0, p->cfg.batch, true)) return e;
+    return pipeline_ba(p);
+}
+
+// Host-buffer step (the e2e leg): the batch is uploaded in chunks on a dedicated copy stream while the compute stream
+// works on the chunks that have already landed (event-ordered), then the per-frame results come back.  One call, one
+// synchronisation at the end.
 extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
                                        double* ba_poses_host, double* ba_summary_host) {
     if (!p || !rgba_host) { alva_set_error("alva_pipeline_step_host: bad argument"); return ALVA_E_INVALID; }
+    if (int e = pipeline_ready(p)) return e;
     const alva_pipeline_config& c = p->cfg;
-    const size_t in_bytes = (size_t)c.batch * c.w * c.h * 4;
-    if (!p->in_dev) { if (int e = palloc(p, (void**)&p->in_dev, in_bytes)) return e; }
+    const size_t frame_bytes = (size_t)c.w * c.h * 4;
+    if (!p->in_dev) { if (int e = palloc(p, (void**)&p->in_dev, frame_bytes * c.batch)) return e; }
+    if (!p->copy_stream) {
+        ALVA_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < alva_pipeline::NCHUNK; i++) ALVA_CUDA(cudaEventCreateWithFlags(&p->chunk_ev[i], cudaEventDisableTiming));
+        ALVA_CUDA(cudaEventCreateWithFlags(&p->start_ev, cudaEventDisableTiming));
+    }
     cudaStream_t st = p->ctx->stream;
-    ALVA_CUDA(cudaMemcpyAsync(p->in_dev, rgba_host, in_bytes, cudaMemcpyHostToDevice, st));
-    if (int e = alva_pipeline_step_dev(p, p->in_dev)) return e;
+    const int nchunk = c.batch >= 4 * alva_pipeline::NCHUNK ? alva_pipeline::NCHUNK : 1;
+    const int per = (c.batch + nchunk - 1) / nchunk;
+    // the upload may not overwrite frames an earlier step on the compute stream is still reading
+    ALVA_CUDA(cudaEventRecord(p->start_ev, st));
+    ALVA_CUDA(cudaStreamWaitEvent(p->copy_stream, p->start_ev, 0));
+    for (int i = 0; i < nchunk; i++) {
+        const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
+        if (nf <= 0) break;
+        ALVA_CUDA(cudaMemcpyAsync(p->in_dev + frame_bytes * f0, rgba_host + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice, p->copy_stream));
+        ALVA_CUDA(cudaEventRecord(p->chunk_ev[i], p->copy_stream));
+    }
+    for (int i = 0; i < nchunk; i++) {
+        const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
+        if (nf <= 0) break;
+        ALVA_CUDA(cudaStreamWaitEvent(st, p->chunk_ev[i], 0));
+        if (int e = pipeline_frames(p, p->in_dev, f0, nf, false)) return e;
+    }
+    if (int e = pipeline_ba(p)) return e;
     if (nfeat_host) ALVA_CUDA(cudaMemcpyAsync(nfeat_host, p->selcounts, sizeof(int32_t) * c.batch, cudaMemcpyDeviceToHost, st));
     if (matches_host && c.map_size > 0)
         ALVA_CUDA(cudaMemcpyAsync(matches_host, p->matches, (size_t)c.batch * p->fcap * 16, cudaMemcpyDeviceToHost, st));
