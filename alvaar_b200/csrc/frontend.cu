@@ -33,7 +33,7 @@ constexpr int SPW = SP / 4;
 constexpr int SR = TH + 2;                // score rows: image y0-1 .. y0+TH
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int QCAP = 160;                 // per-warp pending-corner queue
+constexpr int QCAP = 1024;                // per-warp candidate queue (32 lanes x 8 rows x 4 px): lives in the idle RGBA staging buffer
 constexpr int KPCAP = 1888;               // >= TW*TH/4 (NMS leaves at most one keypoint per 2x2)
 
 struct FrontendParams {
@@ -47,99 +47,82 @@ struct FrontendParams {
 };
 
 struct __align__(128) SmemLayout {
-    uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode)
+    uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode); after the gray pass it is reused for the per-warp queues
     uint8_t gray[GP * BH];         // TMA destination (gray mode)
     uint8_t score[SP * SR];
     uint32_t kplist[KPCAP];
-    uint16_t queue[NWARPS][QCAP];
     uint64_t bar;
     int kpcount;
     int kpbase;
 };
 
 // ---- gray conversion of 4 RGBA pixels (uint4 = 4 x RGBA8) ------------------------------------------
-__device__ __forceinline__ uint32_t gray1(uint32_t px) {
-    uint32_t r = px & 0xff, g = (px >> 8) & 0xff, b = (px >> 16) & 0xff;
-    return (r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15;
+// Y = (9798 R + 19235 G + 3735 B + 2^14) >> 15.  With every term doubled the result is byte 2 of the accumulator, so
+// two 16x8-bit dot-product instructions (IDP.2A, FMA pipe) per pixel and three PRMT per four pixels do the whole job.
+__device__ __forceinline__ uint32_t gray_acc(uint32_t px) {
+    return __dp2a_hi(7470u, px, __dp2a_lo(19596u | (38470u << 16), px, 32768u));
 }
+__device__ __forceinline__ uint32_t gray1(uint32_t px) { return gray_acc(px) >> 16; }
 __device__ __forceinline__ uint32_t gray4(uint4 p) {
-    return gray1(p.x) | (gray1(p.y) << 8) | (gray1(p.z) << 16) | (gray1(p.w) << 24);
+    const uint32_t lo = __byte_perm(gray_acc(p.x), gray_acc(p.y), 0x0062);
+    const uint32_t hi = __byte_perm(gray_acc(p.z), gray_acc(p.w), 0x0062);
+    return __byte_perm(lo, hi, 0x5410);
 }
 
-// ---- FAST-9 detection on 4 horizontally adjacent pixels --------------------------------------------
-// ring[k] holds ring pixel k of the four centres (byte j = centre j).  Returns per-byte bit-7 masks.
-__device__ __forceinline__ void fast_detect4(const uint32_t (&ring)[16], uint32_t c, uint32_t thr4, uint32_t& bright,
-                                             uint32_t& dark) {
-    const uint32_t hi = __vaddus4(c, thr4);   // min(c + t, 255)
-    const uint32_t lo = __vsubus4(c, thr4);   // max(c - t, 0)
-    const uint32_t Cb = (hi | ALVA_H) + ALVA_H;   // (hi|H) - (r & L) == Cb - (r|H)
-    const uint32_t Cd = lo & ALVA_L;
-    uint32_t B[16], D[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t r = ring[k], rH = r | ALVA_H;
-        const uint32_t tb = Cb - rH;   // bit7: (hi & 127) >= (r & 127)
-        const uint32_t td = rH - Cd;   // bit7: (r & 127) >= (lo & 127)
-        // bright: r > hi  <=> !(hi >= r)
-        B[k] = ~((hi & ~r) | (~(hi ^ r) & tb));
-        // dark: r < lo <=> !(r >= lo)
-        D[k] = ~((r & ~lo) | (~(r ^ lo) & td));
-    }
-    uint32_t Tb[16], Td[16];
-#pragma unroll
-    for (int s = 0; s < 16; s++) {
-        Tb[s] = B[s] & B[(s + 1) & 15] & B[(s + 2) & 15];
-        Td[s] = D[s] & D[(s + 1) & 15] & D[(s + 2) & 15];
-    }
-    uint32_t ab = 0, ad = 0;
-#pragma unroll
-    for (int s = 0; s < 16; s++) {
-        ab |= Tb[s] & Tb[(s + 3) & 15] & Tb[(s + 6) & 15];
-        ad |= Td[s] & Td[(s + 3) & 15] & Td[(s + 6) & 15];
-    }
-    bright = ab & ALVA_H;
-    dark = ad & ALVA_H;
+// ---- FAST-9 candidate test, bit-sliced over 4 pixels x 8 rows --------------------------------------
+// A pixel can only be a FAST-9 corner if 9 contiguous ring pixels differ from the centre by more than t (either sign).
+// |ring - c| comes from one VABSDIFF4 per ring element and four pixels, "> t" from the add-and-carry trick, and the
+// resulting bit-7 flags of EIGHT rows are packed into one 32-bit word per ring element (a 64-bit multiply-add on the
+// FMA pipe does the shift-and-accumulate), so the 9-of-16 contiguity network (40 LOP3) runs once per 32 pixels.
+// Candidates then get their exact score (both polarities) in fast_strength2(); score > t decides cornerness exactly
+// as cornerScore / the ring test do in the reference.
+template <bool HI_THR>
+__device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t c, uint32_t K) {
+    const uint32_t a = __vabsdiffu4(ring, c);
+    const uint32_t sum = (a & ALVA_L) + K;
+    return HI_THR ? (sum & a & ALVA_H) : ((sum | a) & ALVA_H);
 }
 
-// ---- corner score (cornerScore<16>) for one pixel, packed 16x2 min/max -----------------------------
-// p: centre pixel in the gray smem tile.  dark != 0: the arc is darker than the centre.
-// returns max over the 16 arcs of min over the arc of |centre - ring| in the corner's polarity (= score + 1).
-__device__ __forceinline__ int fast_strength(const uint8_t* p, int dark) {
+// exact corner strength of one pixel: max over the 16 arcs of min over the arc of (ring - c) [bright] or (c - ring) [dark]
+__device__ __forceinline__ int fast_strength2(const uint8_t* p) {
     constexpr int o[16] = {3 * GP,      3 * GP + 1,  2 * GP + 2,  GP + 3,      3,           -GP + 3,
                            -2 * GP + 2, -3 * GP + 1, -3 * GP,     -3 * GP - 1, -2 * GP - 2, -GP - 3,
                            -3,          GP - 3,      2 * GP - 2,  3 * GP - 1};
     const uint32_t c = p[0];
-    const uint32_t cc = c | (c << 16);
-    const int sgn = dark ? -1 : 1;
-    // e[k] = (±(ring_k - c) + 256, ±(ring_{k+8} - c) + 256) as two unsigned 16-bit lanes
-    uint32_t e[8];
+    const uint32_t bias = 0x01000100u - (c | (c << 16));
+    // e[k] = (ring_k - c + 256, ring_{k+8} - c + 256) as two unsigned 16-bit lanes; es = halves swapped
+    uint32_t e[8], es[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const uint32_t pk = (uint32_t)p[o[k]] | ((uint32_t)p[o[k + 8]] << 16);
-        e[k] = (uint32_t)((int)(pk - cc) * sgn) + 0x01000100u;
+        e[k] = ((uint32_t)p[o[k]] | ((uint32_t)p[o[k + 8]] << 16)) + bias;
+        es[k] = __byte_perm(e[k], 0, 0x1032);
     }
-    // circular sliding minimum of width 9 over 16 elements; register k holds elements (k, k+8)
-    uint32_t sw[8];
+    // register k of a 16-long circular sequence holds elements (k, k + 8); index m >= 8 is the swapped register m - 8
+#define CIRC(arr, sw, m) ((m) < 8 ? arr[(m)] : sw[(m) - 8])
+    uint32_t tn[8], tx[8], tns[8], txs[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) sw[k] = __byte_perm(e[k], 0, 0x1032);   // halves swapped: (k+8, k)
-    uint32_t m2[8], m4[8], m8[8];
+    for (int k = 0; k < 8; k++) {
+        tn[k] = __vimin3_u16x2(e[k], CIRC(e, es, k + 1), CIRC(e, es, k + 2));
+        tx[k] = __vimax3_u16x2(e[k], CIRC(e, es, k + 1), CIRC(e, es, k + 2));
+    }
 #pragma unroll
-    for (int k = 0; k < 8; k++) m2[k] = __vminu2(e[k], k + 1 < 8 ? e[k + 1] : sw[0]);
+    for (int k = 0; k < 6; k++) { tns[k] = __byte_perm(tn[k], 0, 0x1032); txs[k] = __byte_perm(tx[k], 0, 0x1032); }
+    uint32_t bmax = 0, dmin = 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-        m4[k] = __vminu2(m2[k], k + 2 < 8 ? m2[k + 2] : __byte_perm(m2[k + 2 - 8], 0, 0x1032));
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        m8[k] = __vminu2(m4[k], k + 4 < 8 ? m4[k + 4] : __byte_perm(m4[k + 4 - 8], 0, 0x1032));
-    uint32_t best = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) best = __vmaxu2(best, __vminu2(m8[k], sw[k]));   // 9th element: k+8 / k
-    const int b = max((int)(best & 0xffff), (int)(best >> 16));
-    return b - 256;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t a9n = __vimin3_u16x2(tn[k], CIRC(tn, tns, k + 3), CIRC(tn, tns, k + 6));
+        const uint32_t a9x = __vimax3_u16x2(tx[k], CIRC(tx, txs, k + 3), CIRC(tx, txs, k + 6));
+        bmax = __vmaxu2(bmax, a9n);
+        dmin = __vminu2(dmin, a9x);
+    }
+#undef CIRC
+    const int sb = (int)max(bmax & 0xffffu, bmax >> 16) - 256;     // bright: max_arc min(ring - c)
+    const int sd = 256 - (int)min(dmin & 0xffffu, dmin >> 16);     // dark:   max_arc min(c - ring)
+    return max(sb, sd);
 }
 
 template <bool RGBA>
-__global__ void __launch_bounds__(NTHREADS, 3)
+__global__ void __launch_bounds__(NTHREADS, 2)
 frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
     extern __shared__ uint8_t smem_raw[];
     // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes are allocated)
@@ -208,18 +191,18 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         uint32_t* gw = reinterpret_cast<uint32_t*>(S.gray);
         uint8_t* l0 = P.l0 ? P.l0 + (size_t)f * w * h : nullptr;
         const bool w4 = (w & 3) == 0;
-        for (int i = tid; i < (BW / 4) * BH; i += NTHREADS) {
-            const int by = i >> 5, g = i & 31;   // BW/4 == 32 groups per row
-            const uint32_t v = gray4(src4[i]);
-            gw[by * GPW + 1 + g] = v;            // image x0-4+4g at gray byte 4+4g
-            if (l0 && g >= 1 && g <= 30 && by >= 4 && by < 4 + TH) {
-                const int x = x0 + 4 * (g - 1), y = y0 + by - 4;
-                if (y < h && x < w) {
-                    uint8_t* d = l0 + (size_t)y * w + x;
-                    if (w4) *reinterpret_cast<uint32_t*>(d) = v;   // x % 4 == 0 and w % 4 == 0 -> aligned, in range
-                    else
-                        for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(v >> (8 * j));
-                }
+        const int g = lane;                                   // BW/4 == 32 groups per row: lane = group
+        const int x = x0 + 4 * (g - 1);
+        const bool colstore = l0 && g >= 1 && g <= 30 && x < w;
+        for (int by = warp; by < BH; by += NWARPS) {
+            const uint32_t v = gray4(src4[by * 32 + g]);
+            gw[by * GPW + 1 + g] = v;                         // image x0-4+4g at gray byte 4+4g
+            const int y = y0 + by - 4;
+            if (colstore && by >= 4 && by < 4 + TH && y < h) {
+                uint8_t* d = l0 + (size_t)y * w + x;
+                if (w4) *reinterpret_cast<uint32_t*>(d) = v;  // x % 4 == 0 and w % 4 == 0 -> aligned, in range
+                else
+                    for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(v >> (8 * j));
             }
         }
         // columns x0-8..x0-5 and x0+TW+4..x0+TW+7 are never written: only garbage lanes read them
@@ -257,7 +240,9 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
 
     const uint32_t* G = reinterpret_cast<const uint32_t*>(S.gray);
 
-    // ------------------------------------------------------------------ C. pyramid level 1 (16x2 SWAR)
+    // ------------------------------------------------------------------ C. pyramid level 1
+    // [1 4 6 4 1] x [1 4 6 4 1] / 256 on even pixels.  Horizontal taps are 8-bit dot products (IDP.4A, FMA pipe) on the
+    // packed gray words; a thread owns two adjacent outputs and four output rows (11 input rows, rolling).
     if (P.l1) {
         const int w1 = (w + 1) >> 1, h1 = (h + 1) >> 1;
         uint8_t* l1 = P.l1 + (size_t)f * w1 * h1;
@@ -267,115 +252,130 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             const int ly0 = (y0 >> 1) + 4 * sg;
             if (lx < w1 && ly0 < h1) {
                 const uint32_t* base = G + (8 * sg + 2) * GPW + cbw + pc;   // gray row 2j+2 for j = 4*sg
-                uint32_t hrow[11];
+                uint32_t hA[11], hB[11];
 #pragma unroll
                 for (int r = 0; r < 11; r++) {
                     const uint32_t L = base[r * GPW], M = base[r * GPW + 1], R = base[r * GPW + 2];
-                    const uint32_t c0 = M & 0x00ff00ffu;
-                    const uint32_t r1 = (M >> 8) & 0x00ff00ffu;
-                    const uint32_t l1v = __byte_perm(L, M, 0x6543) & 0x00ff00ffu;
-                    const uint32_t l2v = __byte_perm(L, M, 0x5432) & 0x00ff00ffu;
-                    const uint32_t r2 = __byte_perm(M, R, 0x5432) & 0x00ff00ffu;
-                    hrow[r] = c0 * 6u + (l1v + r1) * 4u + l2v + r2;
+                    // output A centred on M0: L2 L3 M0 M1 M2 ; output B centred on M2: M0 M1 M2 M3 R0
+                    hA[r] = __dp4a(__byte_perm(L, M, 0x5432), 0x04060401u, __dp4a(M, 0x00010000u, 0u));
+                    hB[r] = __dp4a(M, 0x04060401u, __dp4a(R, 0x00000001u, 0u));
                 }
+                const bool pair_ok = (lx + 1 < w1), al16 = ((w1 & 1) == 0);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int ly = ly0 + j;
                     if (ly < h1 && 4 * sg + j < TH / 2) {
-                        const uint32_t v = hrow[2 * j] + hrow[2 * j + 4] + (hrow[2 * j + 1] + hrow[2 * j + 3]) * 4u +
-                                           hrow[2 * j + 2] * 6u;
-                        const uint32_t o = ((v + 0x00800080u) >> 8) & 0x00ff00ffu;
+                        const uint32_t vA = hA[2 * j] + hA[2 * j + 4] + (hA[2 * j + 1] + hA[2 * j + 3]) * 4u + hA[2 * j + 2] * 6u + 128u;
+                        const uint32_t vB = hB[2 * j] + hB[2 * j + 4] + (hB[2 * j + 1] + hB[2 * j + 3]) * 4u + hB[2 * j + 2] * 6u + 128u;
+                        const uint32_t o = __byte_perm(vA, vB, 0x0051);   // (vA >> 8) & 255 | ((vB >> 8) & 255) << 8
                         uint8_t* d = l1 + (size_t)ly * w1 + lx;
-                        d[0] = (uint8_t)o;
-                        if (lx + 1 < w1) d[1] = (uint8_t)(o >> 16);
+                        if (pair_ok && al16) *reinterpret_cast<uint16_t*>(d) = (uint16_t)o;
+                        else { d[0] = (uint8_t)o; if (pair_ok) d[1] = (uint8_t)(o >> 8); }
                     }
                 }
             }
         }
     }
 
-    // ------------------------------------------------------------------ D. FAST detect + score
+    // ------------------------------------------------------------------ D. FAST candidates + exact score
+    // warp w owns score rows 8w .. 8w+7 (image rows y0-1+8w ..); lane = 4-pixel group column (image x0-4+4*lane ..)
+    uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;   // the RGBA staging buffer is idle from here on
     if (P.keys) {
-        const uint32_t thr4 = (uint32_t)P.thr * 0x01010101u;
-        // lane = group column gc (image x = x0-4+4*gc .. +3); per-byte validity of this lane's pixels
-        uint32_t vmask = 0;
+        const int thr = P.thr;
+        const bool hi_thr = thr >= 128;
+        const uint32_t K = (uint32_t)(hi_thr ? 255 - thr : 127 - thr) * 0x01010101u;
+        // validity of this lane's 4 pixels (columns) and of the warp's 8 rows, as a (8j + i) bit mask
+        uint32_t vm = 0;
         {
             const int xlo = max(3, x0 - 1), xhi = min(w - 4, x0 + TW);
+            const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
+            uint32_t rowbits = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = x0 - 4 + 4 * lane + j;
-                if (x >= xlo && x <= xhi) vmask |= 0x80u << (8 * j);
-            }
+            for (int i = 0; i < 8; i++) { const int y = y0 - 1 + 8 * warp + i; if (y >= ylo && y <= yhi) rowbits |= 1u << i; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int x = x0 - 4 + 4 * lane + j; if (x >= xlo && x <= xhi) vm |= rowbits << (8 * j); }
         }
-        const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
-        uint16_t* Q = S.queue[warp];
         int qn = 0;
-        const uint32_t lt = (1u << lane) - 1;
-        for (int rr = warp; rr < SR; rr += NWARPS) {
-            const int y = y0 - 1 + rr;
-            if (y >= ylo && y <= yhi) {   // warp-uniform
-                const int r = rr + 3;     // gray smem row of the centre
-                const uint32_t* g0 = G + r * GPW + cbw + lane;
-                uint32_t ring[16];
-                uint32_t c;
-                {
-                    const uint32_t Lp3 = g0[3 * GPW - 1], Mp3 = g0[3 * GPW], Rp3 = g0[3 * GPW + 1];
-                    ring[0] = Mp3;
-                    ring[1] = __byte_perm(Mp3, Rp3, 0x4321);
-                    ring[15] = __byte_perm(Lp3, Mp3, 0x6543);
-                    const uint32_t Lp2 = g0[2 * GPW - 1], Mp2 = g0[2 * GPW], Rp2 = g0[2 * GPW + 1];
-                    ring[2] = __byte_perm(Mp2, Rp2, 0x5432);
-                    ring[14] = __byte_perm(Lp2, Mp2, 0x5432);
-                    const uint32_t Lp1 = g0[GPW - 1], Mp1 = g0[GPW], Rp1 = g0[GPW + 1];
-                    ring[3] = __byte_perm(Mp1, Rp1, 0x6543);
-                    ring[13] = __byte_perm(Lp1, Mp1, 0x4321);
-                    const uint32_t L0 = g0[-1], M0 = g0[0], R0 = g0[1];
-                    c = M0;
-                    ring[4] = __byte_perm(M0, R0, 0x6543);
-                    ring[12] = __byte_perm(L0, M0, 0x4321);
-                    const uint32_t Lm1 = g0[-GPW - 1], Mm1 = g0[-GPW], Rm1 = g0[-GPW + 1];
-                    ring[5] = __byte_perm(Mm1, Rm1, 0x6543);
-                    ring[11] = __byte_perm(Lm1, Mm1, 0x4321);
-                    const uint32_t Lm2 = g0[-2 * GPW - 1], Mm2 = g0[-2 * GPW], Rm2 = g0[-2 * GPW + 1];
-                    ring[6] = __byte_perm(Mm2, Rm2, 0x5432);
-                    ring[10] = __byte_perm(Lm2, Mm2, 0x5432);
-                    const uint32_t Lm3 = g0[-3 * GPW - 1], Mm3 = g0[-3 * GPW], Rm3 = g0[-3 * GPW + 1];
-                    ring[7] = __byte_perm(Mm3, Rm3, 0x4321);
-                    ring[8] = Mm3;
-                    ring[9] = __byte_perm(Lm3, Mm3, 0x6543);
-                }
-                uint32_t bright, dark;
-                fast_detect4(ring, c, thr4, bright, dark);
-                bright &= vmask;
-                dark &= vmask;
-                const uint32_t any = bright | dark;
-                // warp-ballot compaction of corner pixels into the warp queue
-                const int pix0 = r * GP + 4 * (cbw + lane);
+        if (__any_sync(0xffffffffu, vm != 0)) {
+            // gray rows needed: centre rows r0 .. r0+7 with r0 = 8*warp + 3, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
+            const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
+            uint32_t Lw[7], Mw[7], Rw[7];   // rolling 7-row window: slot (row % 7)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool has = (any >> (8 * j + 7)) & 1;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, has);
-                    if (has) {
-                        const int pos = qn + __popc(bal & lt);
-                        Q[pos] = (uint16_t)((pix0 + j) | (((dark >> (8 * j + 7)) & 1) << 15));
-                    }
-                    qn += __popc(bal);
+            for (int r = 0; r < 6; r++) { Lw[r] = g0[r * GPW - 1]; Mw[r] = g0[r * GPW]; Rw[r] = g0[r * GPW + 1]; }
+            unsigned long long acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] = 0ull;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                {   // bring in window row i + 6
+                    const int r = i + 6;
+                    Lw[r % 7] = g0[r * GPW - 1]; Mw[r % 7] = g0[r * GPW]; Rw[r % 7] = g0[r * GPW + 1];
                 }
-                __syncwarp();
+                // window rows i .. i+6 <-> dy = -3 .. +3
+#define WL(dy) Lw[(i + 3 + (dy)) % 7]
+#define WM(dy) Mw[(i + 3 + (dy)) % 7]
+#define WR(dy) Rw[(i + 3 + (dy)) % 7]
+                uint32_t ring[16];
+                ring[0] = WM(3);
+                ring[1] = __byte_perm(WM(3), WR(3), 0x4321);
+                ring[15] = __byte_perm(WL(3), WM(3), 0x6543);
+                ring[2] = __byte_perm(WM(2), WR(2), 0x5432);
+                ring[14] = __byte_perm(WL(2), WM(2), 0x5432);
+                ring[3] = __byte_perm(WM(1), WR(1), 0x6543);
+                ring[13] = __byte_perm(WL(1), WM(1), 0x4321);
+                ring[4] = __byte_perm(WM(0), WR(0), 0x6543);
+                ring[12] = __byte_perm(WL(0), WM(0), 0x4321);
+                ring[5] = __byte_perm(WM(-1), WR(-1), 0x6543);
+                ring[11] = __byte_perm(WL(-1), WM(-1), 0x4321);
+                ring[6] = __byte_perm(WM(-2), WR(-2), 0x5432);
+                ring[10] = __byte_perm(WL(-2), WM(-2), 0x5432);
+                ring[7] = __byte_perm(WM(-3), WR(-3), 0x4321);
+                ring[8] = WM(-3);
+                ring[9] = __byte_perm(WL(-3), WM(-3), 0x6543);
+                const uint32_t c = WM(0);
+#undef WL
+#undef WM
+#undef WR
+                // flag(bit 7 of byte j) -> bit 8j + i of the packed word: (U * 2^(25+i)) >> 32 == U >> (7 - i)
+                const unsigned long long mul = 1ull << (25 + i);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t U = hi_thr ? absdiff_gt<true>(ring[k], c, K) : absdiff_gt<false>(ring[k], c, K);
+                    acc[k] += (unsigned long long)U * mul;
+                }
             }
-            // drain full batches (and everything after the last row)
-            const bool last = rr + NWARPS >= SR;
-            while (qn >= 32 || (last && qn > 0)) {
-                const int take = min(qn, 32);
-                if (lane < take) {
-                    const uint32_t e = Q[qn - take + lane];
-                    const int pix = e & 0x7fff;
-                    const int s = fast_strength(S.gray + pix, e >> 15);
-                    const int pr = pix / GP, pcg = pix - pr * GP;
-                    S.score[(pr - 3) * SP + (pcg - 4 * cbw)] = (uint8_t)(s - 1);
+            uint32_t A[16], T[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) A[k] = (uint32_t)(acc[k] >> 32);
+#pragma unroll
+            for (int k = 0; k < 16; k++) T[k] = A[k] & A[(k + 1) & 15] & A[(k + 2) & 15];
+            uint32_t cand = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) cand |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+            cand &= vm;
+            // ordered compaction of the candidate pixels into the warp queue (one prefix sum per 8 rows)
+            const int mine = __popc(cand);
+            int incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+            int pos = incl - mine;
+            qn = __shfl_sync(0xffffffffu, incl, 31);
+            const int pixbase = (8 * warp + 3) * GP + 4 * (cbw + lane);
+            while (cand) {
+                const int b = __ffs(cand) - 1;
+                cand &= cand - 1;
+                Q[pos++] = (uint16_t)(pixbase + (b & 7) * GP + (b >> 3));
+            }
+            __syncwarp();
+            for (int q0 = 0; q0 < qn; q0 += 32) {
+                if (q0 + lane < qn) {
+                    const int pix = Q[q0 + lane];
+                    const int sc = fast_strength2(S.gray + pix);
+                    if (sc > thr) {
+                        const int pr = pix / GP, pcg = pix - pr * GP;
+                        S.score[(pr - 3) * SP + (pcg - 4 * cbw)] = (uint8_t)(sc - 1);
+                    }
                 }
-                qn -= take;
-                __syncwarp();
             }
         }
     }
@@ -384,30 +384,55 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     // ------------------------------------------------------------------ E. 3x3 NMS (strict >) + emit
     if (P.keys) {
         const uint32_t* Sw = reinterpret_cast<const uint32_t*>(S.score);
-        for (int item = tid; item < 30 * TH; item += NTHREADS) {
-            const int rr = 1 + item / 30, gc = 1 + item % 30;
-            const uint32_t* s0 = Sw + rr * SPW + gc;
-            const uint32_t Sv = s0[0];
-            if (Sv == 0) continue;
-            uint32_t ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
+        // pass 1: every lane lists the rows (of its warp's 8) where its score word is non-zero; the (row, lane) items are
+        // compacted per warp so that pass 2 runs with full lanes on the ~25 % of words that hold a corner
+        uint32_t nz = 0;
+        if (lane >= 1 && lane <= 30) {
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const uint32_t L = s0[dy * SPW - 1], M = s0[dy * SPW], R = s0[dy * SPW + 1];
-                const uint32_t nl = __byte_perm(L, M, 0x6543), nr = __byte_perm(M, R, 0x4321);
-                ok &= ~swar_ge_raw(nl, Sv);   // Sv > nl  <=> !(nl >= Sv)
-                ok &= ~swar_ge_raw(nr, Sv);
-                if (dy != 0) ok &= ~swar_ge_raw(M, Sv);
+            for (int i = 0; i < 8; i++) {
+                const int rr = 8 * warp + i;
+                if (rr >= 1 && rr <= TH && Sw[rr * SPW + lane] != 0) nz |= 1u << i;
             }
-            ok &= ALVA_H;
-            const int y = y0 + rr - 1;
+        }
+        const int mine = __popc(nz);
+        int incl = mine;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((ok >> (8 * j + 7)) & 1) {
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        int pos = incl - mine;
+        const int nitems = __shfl_sync(0xffffffffu, incl, 31);
+        while (nz) {
+            const int i = __ffs(nz) - 1;
+            nz &= nz - 1;
+            Q[pos++] = (uint16_t)((8 * warp + i) * SPW + lane);
+        }
+        __syncwarp();
+        for (int q0 = 0; q0 < nitems; q0 += 32) {
+            if (q0 + lane < nitems) {
+                const int widx = Q[q0 + lane];
+                const int rr = widx / SPW, gc = widx - rr * SPW;
+                const uint32_t* s0 = Sw + widx;
+                const uint32_t Sv = s0[0];
+                uint32_t ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++) {
+                    const uint32_t L = s0[dy * SPW - 1], M = s0[dy * SPW], R = s0[dy * SPW + 1];
+                    const uint32_t nl = __byte_perm(L, M, 0x6543), nr = __byte_perm(M, R, 0x4321);
+                    ok &= ~swar_ge_raw(nl, Sv);   // Sv > nl  <=> !(nl >= Sv)
+                    ok &= ~swar_ge_raw(nr, Sv);
+                    if (dy != 0) ok &= ~swar_ge_raw(M, Sv);
+                }
+                ok &= ALVA_H;
+                const int y = y0 + rr - 1;
+                while (ok) {
+                    const int b = __ffs(ok) - 1;   // bit 8j + 7
+                    ok &= ok - 1;
+                    const int j = b >> 3;
                     const int x = x0 + 4 * (gc - 1) + j;
                     const uint32_t sc = (Sv >> (8 * j)) & 0xff;
-                    const int pos = atomicAdd(&S.kpcount, 1);
-                    if (pos < KPCAP) S.kplist[pos] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
+                    const int kp = atomicAdd(&S.kpcount, 1);
+                    if (kp < KPCAP) S.kplist[kp] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
                 }
+            }
         }
         __syncthreads();
         const int n = min(S.kpcount, KPCAP);

@@ -90,8 +90,13 @@ class Context:
     """One CUDA device + stream (alva_ctx).  Methods mirror the alva_k_* entry points on torch tensors."""
 
     def __init__(self, device=0, stream=None):
+        """stream: None -> the context creates its own non-blocking stream; an integer cudaStream_t handle otherwise.
+        Handle 0 (torch's default stream) is passed as cudaStreamLegacy (0x1): in the C ABI a NULL stream means
+        "create one", so the legacy default stream has to be named explicitly."""
         self.L = lib()
-        h = self.L.alva_ctx_create(int(device), C.c_void_p(stream) if stream else None)
+        if stream is not None and int(stream) == 0:
+            stream = 1   # cudaStreamLegacy
+        h = self.L.alva_ctx_create(int(device), C.c_void_p(int(stream)) if stream is not None else None)
         if not h:
             raise AlvaError(self.L.alva_last_error().decode())
         self.h = C.c_void_p(h)

@@ -51,7 +51,8 @@ int         alva_version(void);
 const char* alva_last_error(void);
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* device: CUDA ordinal.  stream: a cudaStream_t to run on (NULL = the context creates its own). */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on; NULL = the context creates its own non-blocking stream
+ * (to run on the legacy default stream pass cudaStreamLegacy, i.e. (void*)0x1). */
 alva_ctx* alva_ctx_create(int device, void* stream);
 void      alva_ctx_destroy(alva_ctx* ctx);
 int       alva_ctx_sync(alva_ctx* ctx);

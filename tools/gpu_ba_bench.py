@@ -7,7 +7,7 @@ import alvaar_b200
 from alvaar_b200 import synth, lib
 NP = 13
 pb = synth.make_ba_problem(20, 3000, 4, seed=42)
-ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)
+ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)  # handle 0 -> legacy default stream
 st = lambda k: torch.from_numpy(np.stack([pb[k]] * NP)).cuda()
 calib, poses0, const, invd0 = st("calib"), st("poses"), st("pose_const"), st("invd")
 akf, auv, okf, olm, ouv = st("anch_kf"), st("anch_uv"), st("obs_kf"), st("obs_lm"), st("obs_uv")
