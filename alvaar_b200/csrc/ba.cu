@@ -28,7 +28,7 @@ namespace {
 constexpr int NMAX = 128;   // max reduced-system width (>= 6 * free poses), padded
 constexpr int LIN_THREADS = 128;
 constexpr int NBMAX = NMAX / 6;                 // 21 free poses at most
-constexpr int MAXKEYS = NBMAX * (NBMAX + 1) / 2;   // upper-triangular 6x6 blocks of the reduced system
+constexpr int MAXKEYS = NBMAX * (NBMAX + 1) / 2;   // upper-triangular 6x6 blocks of the reduced system (grid of the gather kernel)
 constexpr int BS_THREADS = 128;                // back-substitution CTA
 
 struct BaState {
@@ -37,7 +37,7 @@ struct BaState {
     double initial_cost, push_cost;
     int reuse_diagonal, invalid_steps, iteration, last_success, n_success, n_iter, term, done;
     int relin, step_ok, ncols, chol_ok;
-    int nkeys, nentries, use_gather, nb;
+    int use_gather, nb, pad0, pad1;
 };
 
 // per-problem views into the workspace
@@ -65,8 +65,9 @@ struct BaProblem {
     int32_t *lm_start, *lm_obs;             // CSR landmark -> observations: [nlm+1], [nobs]
     double* Wt;                             // dense Schur path: [nlm_pad][NMAX]
     double* mc_part;                        // model-cost partials, one per back-substitution CTA
-    int32_t *key_start;                     // gather Schur: [MAXKEYS + 1] entry ranges per upper-triangular pose-pair block
-    uint32_t *entries;                      // gather Schur: (landmark << 16) | (slot_u << 8) | slot_v, ordered by landmark
+    int32_t *obs_col, *anch_col;            // reduced-system column of each observation's / landmark anchor's pose (-1: fixed)
+    int32_t *pstart;                        // gather Schur: [NBMAX + 1] ranges of plist per free pose
+    uint32_t *plist;                        // gather Schur: (landmark << 8) | slot, every (landmark, slot) seeing that pose, by landmark
     BaState* st;
 };
 
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restri
         s.radius = 1e4; s.decrease_factor = 2.0; s.reuse_diagonal = 0; s.invalid_steps = 0; s.iteration = 0;
         s.last_success = 1; s.n_success = 0; s.n_iter = 0; s.term = 1; s.done = 0; s.relin = 1; s.step_ok = 0;
         s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
-        s.chol_ok = 1; s.use_gather = 0; s.nkeys = 0; s.nentries = 0; s.nb = c / 6;
+        s.chol_ok = 1; s.use_gather = 0; s.nb = c / 6;
     }
     // exclusive scan of counts -> lm_start (chunked: 256 threads)
     {
@@ -252,7 +253,8 @@ __global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restri
         else { int c = b; for (int o = 0; o < D.nobs && c < e; o++) if (P.obs_lm[o] == l) P.lm_obs[c++] = o; }
     }
     for (int i = tid; i < NMAX; i += 256) { P.nf[i] = 0; P.gf[i] = 0; }
-    for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; }
+    for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; P.anch_col[l] = P.pose_col[P.anch_kf[l]]; }
+    for (int o = tid; o < D.nobs; o += 256) P.obs_col[o] = P.obs_lm[o] >= 0 ? P.pose_col[P.obs_kf[o]] : -1;
 }
 
 // ------------------------------------------------------------------------------------------ linearise (thread / obs)
@@ -568,94 +570,43 @@ __global__ void __launch_bounds__(128) ba_syrk_dmma_kernel(const BaProblem* __re
 //   F_u'F_v - w_u w_v' / (E'E + D^2)        (u, v = the landmark's slots holding poses bi, bj; w = F'e)
 // A slot is 0 for the anchor keyframe and 1 + k for the landmark's k-th observation.  The (block -> landmark pairs)
 // lists depend only on the problem's structure, so they are built once per solve (deterministically, in landmark
-// order) by ba_keys_*; every LM iteration then runs ba_lm_kernel (per-landmark E'E, E'b, F'e) and ba_gather_kernel
+// order) by ba_plist_kernel; every LM iteration then runs ba_lm_kernel (per-landmark E'E, E'b, F'e) and ba_gather_kernel
 // (one warp per block, fixed summation order -> bit-reproducible results, zero atomics).
-__device__ __forceinline__ int slot_col(const BaProblem& P, int l, int s) {
-    return s == 0 ? P.pose_col[P.anch_kf[l]] : P.pose_col[P.obs_kf[P.lm_obs[P.lm_start[l] + s - 1]]];
-}
-__device__ __forceinline__ int key_of(int bi, int bj) {   // bi <= bj, row-major upper triangle over NBMAX
-    return bi * NBMAX - bi * (bi - 1) / 2 + (bj - bi);
-}
-
-// count the entries of one block (MODE 0) or fill them (MODE 1); one warp per block, landmarks scanned in order, so
-// the entry order (and with it every floating-point summation order downstream) is deterministic.
+// Per free pose: the (landmark, slot) pairs that see it, in landmark order (deterministic).  MODE 0 counts, MODE 1 fills;
+// one warp per pose block, ballot-ordered appends.  Also decides whether the gather path applies (slot ids < 255).
 template <int MODE>
-__global__ void __launch_bounds__(32) ba_keys_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+__global__ void __launch_bounds__(32) ba_plist_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const int nb = P.st->ncols / 6;
-    const int key = blockIdx.x;
-    int bi = 0, rem = key;
-    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
-    const int bj = bi + rem;
-    const int lane = threadIdx.x;
-    if (bi >= nb || bj >= nb) { if (MODE == 0 && lane == 0) P.key_start[key + 1] = 0; return; }
-    if (MODE == 1 && !P.st->use_gather) return;
-    int total = 0;
-    const int base = MODE == 1 ? P.key_start[key] : 0;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= nb) { if (MODE == 0 && lane == 0) P.pstart[b + 1] = 0; return; }
+    const int col = 6 * b;
+    int base = 0;
+    if (MODE == 1) { for (int i = 0; i < b; i++) base += P.pstart[i + 1]; }   // counts of the preceding poses (pass 0 output)
+    int total = 0, maxobs = 0;
     for (int l0 = 0; l0 < D.nlm; l0 += 32) {
         const int l = l0 + lane;
-        const int ns = l < D.nlm ? (P.lm_start[l + 1] - P.lm_start[l]) : 0;   // observations; slots 0..ns when ns > 0
-        int cnt = 0;
-        if (ns > 0)
-            for (int u = 0; u <= ns; u++) {
-                const int cu = slot_col(P, l, u);
-                if (cu < 0) continue;
-                for (int v = u; v <= ns; v++) {
-                    const int cv = slot_col(P, l, v);
-                    if (cv >= 0 && min(cu, cv) / 6 == bi && max(cu, cv) / 6 == bj) cnt++;
-                }
-            }
-        int maxc = cnt;
+        const int ob = l < D.nlm ? P.lm_start[l] : 0;
+        const int ns = l < D.nlm ? (P.lm_start[l + 1] - ob) : 0;
+        maxobs = max(maxobs, ns);
+        int maxs = ns > 0 ? ns + 1 : 0;
 #pragma unroll
-        for (int off = 16; off; off >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, off));
-        for (int r = 0; r < maxc; r++) {      // round r: every lane contributes its r-th pair (usually maxc == 1)
-            const bool has = r < cnt;
-            const uint32_t bal = __ballot_sync(0xffffffffu, has);
-            if (MODE == 1 && has) {
-                uint32_t ent = 0;
-                int seen = 0;
-                for (int u = 0; u <= ns && seen <= r; u++) {
-                    const int cu = slot_col(P, l, u);
-                    if (cu < 0) continue;
-                    for (int v = u; v <= ns && seen <= r; v++) {
-                        const int cv = slot_col(P, l, v);
-                        if (cv >= 0 && min(cu, cv) / 6 == bi && max(cu, cv) / 6 == bj) {
-                            if (seen == r) {   // (slot holding pose bi, slot holding pose bj)
-                                const int s_i = (cu <= cv) ? u : v, s_j = (cu <= cv) ? v : u;
-                                ent = ((uint32_t)l << 16) | ((uint32_t)s_i << 8) | (uint32_t)s_j;
-                            }
-                            seen++;
-                        }
-                    }
-                }
-                const int pos = base + total + __popc(bal & ((1u << lane) - 1));
-                if (pos < D.ecap) P.entries[pos] = ent;
-            }
+        for (int off = 16; off; off >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, off));
+        for (int sl = 0; sl < maxs; sl++) {      // slot-major rounds keep (landmark, slot) order within a 32-landmark chunk
+            bool hit = false;
+            if (ns > 0 && sl <= ns) hit = (sl == 0 ? P.anch_col[l] : P.obs_col[P.lm_obs[ob + sl - 1]]) == col;
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            if (MODE == 1 && hit) P.plist[base + total + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)l << 8) | (uint32_t)sl;
             total += __popc(bal);
         }
     }
-    if (MODE == 0 && lane == 0) P.key_start[key + 1] = total;
-}
-
-// exclusive scan of the key counts + decision whether the gather path can be used (entry capacity, slot ids < 256)
-__global__ void __launch_bounds__(256) ba_keys_scan_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.x];
-    __shared__ int maxobs_s;
-    if (threadIdx.x == 0) maxobs_s = 0;
-    __syncthreads();
-    int mo = 0;
-    for (int l = threadIdx.x; l < D.nlm; l += 256) mo = max(mo, P.lm_start[l + 1] - P.lm_start[l]);
-    atomicMax(&maxobs_s, mo);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        P.key_start[0] = 0;
-        for (int k = 0; k < MAXKEYS; k++) { const int c = P.key_start[k + 1]; run += c; P.key_start[k + 1] = run; }
-        BaState& st = *P.st;
-        st.nentries = run;
-        st.nkeys = MAXKEYS;
-        st.nb = st.ncols / 6;
-        st.use_gather = (run <= D.ecap && maxobs_s < 255 && D.nlm < 65536) ? 1 : 0;
+    if (MODE == 0) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, off));
+        if (lane == 0) {
+            P.pstart[b + 1] = total;
+            if (b == 0) { P.st->use_gather = (maxobs < 255 && D.nlm < (1 << 24)) ? 1 : 0; P.st->nb = nb; }
+        }
     }
 }
 
@@ -707,13 +658,19 @@ __global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restri
     double sci[6], scj[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
-    const int eb = P.key_start[key], ee = P.key_start[key + 1];
+    int eb = 0;
+    for (int i = 0; i < bi; i++) eb += P.pstart[i + 1];
+    const int ee = eb + P.pstart[bi + 1];
     for (int idx = eb + lane; idx < ee; idx += 32) {
-        const uint32_t en = P.entries[idx];
-        const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
-        const int ob = P.lm_start[l];
+        const uint32_t en = P.plist[idx];
+        const int l = en >> 8, su = en & 0xff;
+        const int ob = P.lm_start[l], ns = P.lm_start[l + 1] - ob;
         const double inv = 1.0 / P.ete[l], etb = P.etb[l];
-        const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+        const int ou = su ? P.lm_obs[ob + su - 1] : -1;
+        // partner slots holding pose bj (for the diagonal block: sv >= su, each unordered pair once)
+        for (int sv = (bi == bj ? su : 0); sv <= ns; sv++) {
+        const int ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+        if ((sv ? P.obs_col[ov] : P.anch_col[l]) != cj) continue;
         double wu[6], wv[6], C[36];
 #pragma unroll
         for (int c = 0; c < 6; c++) {
@@ -772,6 +729,7 @@ __global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restri
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int c = 0; c < 6; c++) acc[6 * a + c] += C[6 * a + c] + (dup ? C[6 * c + a] : 0.0);
+        }   // sv
     }
     // fixed-order butterfly reduction
 #pragma unroll
@@ -830,7 +788,8 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
                 const double dj = sqrt(d);
                 __syncwarp();
                 if (lane == 0) L[j * ld + j] = dj;
-                for (int i = j + 1 + lane; i < n; i += 32) L[i * ld + j] /= dj;
+                const double rdj = 1.0 / dj;
+                for (int i = j + 1 + lane; i < n; i += 32) L[i * ld + j] *= rdj;
                 __syncwarp();
                 // update the remaining columns of the panel
                 for (int k = j + 1; k < j0 + jb; k++) {
@@ -1060,7 +1019,8 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     d += (size_t)((nlm + BS_THREADS - 1) / BS_THREADS);   // model-cost partials
     size_t bytes = d * sizeof(double);
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
-    bytes += align_up((size_t)(MAXKEYS + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+    bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
+    bytes += align_up((size_t)(NBMAX + 1) * 4, 8) + align_up(((size_t)nobs + (size_t)nlm) * 4, 8);   // pstart, plist
     bytes += align_up(sizeof(BaState), 8);
     return align_up(bytes, 256);
 }
@@ -1116,8 +1076,10 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
             P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
             P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
             P.lm_obs = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
-            P.key_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(MAXKEYS + 1) * 4, 8);
-            P.entries = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+            P.obs_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
+            P.anch_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nlm * 4, 8);
+            P.pstart = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX + 1) * 4, 8);
+            P.plist = reinterpret_cast<uint32_t*>(b); b += align_up(((size_t)nobs + (size_t)nlm) * 4, 8);
             P.st = reinterpret_cast<BaState*>(b);
         }
         ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
@@ -1134,11 +1096,10 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
     const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob);
     if (!dense) {   // structure of the gather-form Schur complement, once per solve
-        ba_keys_kernel<0><<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+        const dim3 pl_grid(NBMAX, nprob);
+        ba_plist_kernel<0><<<pl_grid, 32, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_keys_scan_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
-        ALVA_LAUNCH_CHECK(ctx);
-        ba_keys_kernel<1><<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+        ba_plist_kernel<1><<<pl_grid, 32, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
     for (int it = 0; it <= max_iter; it++) {
