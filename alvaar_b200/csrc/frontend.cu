@@ -44,6 +44,7 @@ struct FrontendParams {
     int32_t* counts;
     int w, h, nframes, tiles_x, tiles_y;
     int thr, cap, use_tma;
+    uint32_t mul[7];      // 2^(25+i): kept as run-time data so the row-packing multiply-high stays an FMA-pipe IMAD.HI
 };
 
 struct __align__(128) SmemLayout {
@@ -122,7 +123,7 @@ __device__ __forceinline__ int fast_strength2(const uint8_t* p) {
 }
 
 template <bool RGBA>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, 3)
 frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
     extern __shared__ uint8_t smem_raw[];
     // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes are allocated)
@@ -285,26 +286,31 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         const bool hi_thr = thr >= 128;
         const uint32_t K = (uint32_t)(hi_thr ? 255 - thr : 127 - thr) * 0x01010101u;
         // validity of this lane's 4 pixels (columns) and of the warp's 8 rows, as a (8j + i) bit mask
-        uint32_t vm = 0;
+        uint32_t vm;
         {
             const int xlo = max(3, x0 - 1), xhi = min(w - 4, x0 + TW);
             const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
-            uint32_t rowbits = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) { const int y = y0 - 1 + 8 * warp + i; if (y >= ylo && y <= yhi) rowbits |= 1u << i; }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { const int x = x0 - 4 + 4 * lane + j; if (x >= xlo && x <= xhi) vm |= rowbits << (8 * j); }
+            const int yb = y0 - 1 + 8 * warp;                 // image row of bit 0
+            const int r0v = max(ylo - yb, 0), r1v = min(yhi - yb, 7);   // valid row bits [r0v, r1v]
+            const uint32_t rowbits = r1v >= r0v ? ((0xffu >> (7 - r1v)) & (0xffu << r0v)) & 0xffu : 0u;
+            const int xb = x0 - 4 + 4 * lane;                 // image column of byte 0
+            const int c0v = max(xlo - xb, 0), c1v = min(xhi - xb, 3);   // valid bytes [c0v, c1v]
+            const uint32_t colbytes = c1v >= c0v ? ((0x01010101u >> (8 * (3 - c1v))) & (0x01010101u << (8 * c0v))) : 0u;
+            vm = colbytes * rowbits;                          // rowbits replicated into every valid byte
         }
         int qn = 0;
         if (__any_sync(0xffffffffu, vm != 0)) {
             // gray rows needed: centre rows r0 .. r0+7 with r0 = 8*warp + 3, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
             const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
             uint32_t Lw[7], Mw[7], Rw[7];   // rolling 7-row window: slot (row % 7)
+            uint32_t mulreg[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) mulreg[i] = P.mul[i];
 #pragma unroll
             for (int r = 0; r < 6; r++) { Lw[r] = g0[r * GPW - 1]; Mw[r] = g0[r * GPW]; Rw[r] = g0[r * GPW + 1]; }
-            unsigned long long acc[16];
+            uint32_t acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) acc[k] = 0ull;
+            for (int k = 0; k < 16; k++) acc[k] = 0u;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 {   // bring in window row i + 6
@@ -336,19 +342,19 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
 #undef WL
 #undef WM
 #undef WR
-                // flag(bit 7 of byte j) -> bit 8j + i of the packed word: (U * 2^(25+i)) >> 32 == U >> (7 - i)
-                const unsigned long long mul = 1ull << (25 + i);
+                // flag (bit 7 of byte j) -> bit 8j + i of the packed word: hi32(U * 2^(25+i)) == U >> (7 - i).  mad.hi keeps the
+                // shift-and-accumulate on the FMA pipe (a plain shift would be strength-reduced onto the saturated ALU pipe);
+                // row 7 needs no shift at all.
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
                     const uint32_t U = hi_thr ? absdiff_gt<true>(ring[k], c, K) : absdiff_gt<false>(ring[k], c, K);
-                    acc[k] += (unsigned long long)U * mul;
+                    if (i < 7) asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(U), "r"(mulreg[i]));
+                    else acc[k] += U;
                 }
             }
-            uint32_t A[16], T[16];
+            uint32_t T[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) A[k] = (uint32_t)(acc[k] >> 32);
-#pragma unroll
-            for (int k = 0; k < 16; k++) T[k] = A[k] & A[(k + 1) & 15] & A[(k + 2) & 15];
+            for (int k = 0; k < 16; k++) T[k] = acc[k] & acc[(k + 1) & 15] & acc[(k + 2) & 15];
             uint32_t cand = 0;
 #pragma unroll
             for (int k = 0; k < 16; k++) cand |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
@@ -590,6 +596,7 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     P.w = w; P.h = h; P.nframes = nframes;
     P.tiles_x = (w + TW - 1) / TW; P.tiles_y = (h + TH - 1) / TH;
     P.thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr); P.cap = cap;
+    for (int i = 0; i < 7; i++) P.mul[i] = 1u << (25 + i);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     bool tma_ok;
