@@ -68,6 +68,8 @@ struct BaProblem {
     int32_t *obs_col, *anch_col;            // reduced-system column of each observation's / landmark anchor's pose (-1: fixed)
     int32_t *pstart;                        // gather Schur: [NBMAX + 1] ranges of plist per free pose
     uint32_t *plist;                        // gather Schur: (landmark << 8) | slot, every (landmark, slot) seeing that pose, by landmark
+    int32_t *blk_start;                     // gather Schur: [NBMAX*NBMAX + 1] entry ranges per 6x6 block (bi <= bj), row-major
+    uint32_t *pairs;                        // gather Schur: (landmark << 16) | (slot_u << 8) | slot_v per block, in plist order
     BaState* st;
 };
 
@@ -193,16 +195,24 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 }
 
 // ------------------------------------------------------------------------------------------ setup (1 CTA / problem)
-__global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+// Structure of the problem, computed once per solve: free-pose columns, landmark -> observation CSR, and per free pose
+// the list of (landmark, slot) pairs that see it (slot 0 = anchor keyframe, 1 + k = the landmark's k-th observation).
+// The pose lists are an order-preserving multisplit (warp match + prefix), so every list -- and every floating-point
+// sum taken over one later -- has a fixed order: the whole solve is bit-reproducible.
+constexpr int SETUP_THREADS = 1024;
+__global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.x];
     __shared__ int ref[256];
-    __shared__ int scan_s[257];
-    const int tid = threadIdx.x;
-    for (int k = tid; k < 256; k += 256) ref[k] = 0;
-    for (int l = tid; l <= D.nlm; l += 256) P.lm_start[l] = 0;
+    __shared__ int scan_s[SETUP_THREADS + 1];
+    __shared__ int wcount[32][NBMAX + 1];
+    __shared__ int run[NBMAX + 1], pl_base[NBMAX + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = SETUP_THREADS;
+    for (int k = tid; k < 256; k += NT) ref[k] = 0;
+    for (int l = tid; l <= D.nlm; l += NT) P.lm_start[l] = 0;
     __syncthreads();
     // counts per landmark (exact integer atomics) and referenced poses
-    for (int o = tid; o < D.nobs; o += 256) {
+    for (int o = tid; o < D.nobs; o += NT) {
         const int l = P.obs_lm[o];
         if (l < 0) continue;
         atomicAdd(&P.lm_start[l + 1], 1);
@@ -223,28 +233,33 @@ __global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restri
         s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
         s.chol_ok = 1; s.use_gather = 0; s.nb = c / 6;
     }
-    // exclusive scan of counts -> lm_start (chunked: 256 threads)
+    // exclusive scan of counts -> lm_start
     {
-        const int chunk = (D.nlm + 256) / 256;
+        const int chunk = (D.nlm + NT) / NT;
         const int b = tid * chunk + 1, e = min(b + chunk, D.nlm + 1);
         int sum = 0;
         for (int i = b; i < e; i++) sum += P.lm_start[i];
         scan_s[tid + 1] = sum;
         if (tid == 0) scan_s[0] = 0;
         __syncthreads();
-        if (tid == 0) for (int i = 1; i <= 256; i++) scan_s[i] += scan_s[i - 1];
+        if (warp == 0) {   // inclusive scan of the NT partials, 32 per lane
+            int v[NT / 32], t = 0;
+            for (int i = 0; i < NT / 32; i++) { t += scan_s[1 + lane * (NT / 32) + i]; v[i] = t; }
+            int incl = t;
+            for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
+            const int excl = incl - t;
+            for (int i = 0; i < NT / 32; i++) scan_s[1 + lane * (NT / 32) + i] = excl + v[i];
+        }
         __syncthreads();
-        int run = scan_s[tid];
-        for (int i = b; i < e; i++) { run += P.lm_start[i]; P.lm_start[i] = run; }
+        int r = scan_s[tid];
+        for (int i = b; i < e; i++) { r += P.lm_start[i]; P.lm_start[i] = r; }
         __syncthreads();
     }
-    // fill: thread per landmark scans?  cheaper: every observation finds its slot by counting earlier obs of the
-    // same landmark -- obs lists are short and the reference emits them grouped, so do a deterministic per-landmark
-    // pass: thread l walks the whole obs array only if ungrouped.  Common case (grouped, ascending): slot = o - first.
-    for (int l = tid; l < D.nlm; l += 256) {
+    // landmark -> observation lists.  Common case: obs_lm is non-decreasing (the reference emits observations grouped by
+    // landmark), then the list is a contiguous index range found by binary search; otherwise a linear scan.
+    for (int l = tid; l < D.nlm; l += NT) {
         const int b = P.lm_start[l], e = P.lm_start[l + 1];
         if (e == b) continue;
-        // fast path: find the first obs of l by binary search assuming obs_lm is non-decreasing
         int lo = 0, hi = D.nobs;
         while (lo < hi) { const int mid = (lo + hi) >> 1; const int v = P.obs_lm[mid]; if (v >= 0 && v < l) lo = mid + 1; else hi = mid; }
         bool grouped = (lo + (e - b) <= D.nobs);
@@ -252,13 +267,70 @@ __global__ void __launch_bounds__(256) ba_setup_kernel(const BaProblem* __restri
         if (grouped) { for (int i = 0; i < e - b; i++) P.lm_obs[b + i] = lo + i; }
         else { int c = b; for (int o = 0; o < D.nobs && c < e; o++) if (P.obs_lm[o] == l) P.lm_obs[c++] = o; }
     }
-    for (int i = tid; i < NMAX; i += 256) { P.nf[i] = 0; P.gf[i] = 0; }
-    for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; P.anch_col[l] = P.pose_col[P.anch_kf[l]]; }
-    for (int o = tid; o < D.nobs; o += 256) P.obs_col[o] = P.obs_lm[o] >= 0 ? P.pose_col[P.obs_kf[o]] : -1;
+    for (int l = tid; l < D.nlm; l += NT) P.anch_col[l] = P.pose_col[P.anch_kf[l]];
+    for (int o = tid; o < D.nobs; o += NT) P.obs_col[o] = P.obs_lm[o] >= 0 ? P.pose_col[P.obs_kf[o]] : -1;
+    for (int i = tid; i <= NBMAX; i += NT) { run[i] = 0; pl_base[i] = 0; }
+    __syncthreads();
+    // ---- per-pose (landmark, slot) lists: items = [anchor of every used landmark] ++ [CSR positions in order]
+    const int nobs_used = P.lm_start[D.nlm];
+    const int nitems = D.nlm + nobs_used;
+    auto item = [&](int t, int& key, uint32_t& val) {
+        key = -1; val = 0;
+        if (t < D.nlm) {
+            if (P.lm_start[t + 1] > P.lm_start[t] && P.anch_col[t] >= 0) { key = P.anch_col[t] / 6; val = (uint32_t)t << 8; }
+        } else if (t < nitems) {
+            const int i = t - D.nlm, o = P.lm_obs[i], l = P.obs_lm[o];
+            if (P.obs_col[o] >= 0) { key = P.obs_col[o] / 6; val = ((uint32_t)l << 8) | (uint32_t)(i - P.lm_start[l] + 1); }
+        }
+    };
+    int maxobs = 0;
+    for (int l = tid; l < D.nlm; l += NT) maxobs = max(maxobs, P.lm_start[l + 1] - P.lm_start[l]);
+    for (int t = tid; t < nitems; t += NT) {   // pass 0: totals per pose
+        int key; uint32_t val;
+        item(t, key, val);
+        if (key >= 0) atomicAdd(&pl_base[key + 1], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        P.pstart[0] = 0;
+        for (int k = 0; k < NBMAX; k++) { P.pstart[k + 1] = pl_base[k + 1]; pl_base[k + 1] += pl_base[k]; }   // pstart[k+1] = count
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < nitems; t0 += NT) {   // pass 1: ordered fill
+        for (int i = tid; i < 32 * (NBMAX + 1); i += NT) (&wcount[0][0])[i] = 0;
+        __syncthreads();
+        int key; uint32_t val;
+        item(t0 + tid, key, val);
+        const uint32_t m = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(m & ((1u << lane) - 1));
+        if (key >= 0 && rank == 0) wcount[warp][key] = __popc(m);
+        __syncthreads();
+        if (tid < NBMAX) {   // exclusive prefix over the warps, per key
+            int acc = 0;
+            for (int wv = 0; wv < 32; wv++) { const int c = wcount[wv][tid]; wcount[wv][tid] = acc; acc += c; }
+            scan_s[tid] = acc;   // chunk total of this key
+        }
+        __syncthreads();
+        if (key >= 0) P.plist[pl_base[key] + run[key] + wcount[warp][key] + rank] = val;
+        __syncthreads();
+        if (tid < NBMAX) run[tid] += scan_s[tid];
+        __syncthreads();
+    }
+    // the gather path packs (landmark, slot_u, slot_v) into 32 bits
+    maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, 16)); maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, 8));
+    maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, 4)); maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, 2));
+    maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, 1));
+    if (lane == 0) scan_s[warp] = maxobs;
+    __syncthreads();
+    if (tid == 0) {
+        int mo = 0;
+        for (int i = 0; i < NT / 32; i++) mo = max(mo, scan_s[i]);
+        P.st->use_gather = (mo < 255 && D.nlm < 65536) ? 1 : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ linearise (thread / obs)
-// FULL: residuals + Jacobians at the current point, squared column norms and gradient (atomics on the pose columns);
+// FULL: residuals + Jacobians at the current point (column norms and gradient follow in ba_stats_kernel, without atomics);
 // otherwise cost only at the candidate point.  Per-block cost partials (deterministic order in the control kernels).
 template <bool FULL>
 __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProblem* __restrict__ probs, BaDims D) {
@@ -286,26 +358,155 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProbl
             P.res[2 * o] = r[0]; P.res[2 * o + 1] = r[1];
             Jd[0] *= sc; Jd[1] *= sc;
             P.Jd[2 * o] = Jd[0]; P.Jd[2 * o + 1] = Jd[1];
-            atomicAdd(&P.ne[l], Jd[0] * Jd[0] + Jd[1] * Jd[1]);
-            atomicAdd(&P.ge[l], Jd[0] * r[0] + Jd[1] * r[1]);
-            const int ca = P.pose_col[ka], cp = P.pose_col[kp];
 #pragma unroll
             for (int i = 0; i < 12; i++) { Ja[i] *= sc; Jp[i] *= sc; P.Ja[12 * o + i] = Ja[i]; P.Jp[12 * o + i] = Jp[i]; }
-#pragma unroll
-            for (int c = 0; c < 6; c++) {
-                if (ca >= 0) {
-                    atomicAdd(&P.nf[ca + c], Ja[c] * Ja[c] + Ja[6 + c] * Ja[6 + c]);
-                    atomicAdd(&P.gf[ca + c], Ja[c] * r[0] + Ja[6 + c] * r[1]);
-                }
-                if (cp >= 0) {
-                    atomicAdd(&P.nf[cp + c], Jp[c] * Jp[c] + Jp[6 + c] * Jp[6 + c]);
-                    atomicAdd(&P.gf[cp + c], Jp[c] * r[0] + Jp[6 + c] * r[1]);
-                }
-            }
         }
     }
     const double tot = block_sum<LIN_THREADS>(cost, red);
     if (threadIdx.x == 0) P.cost_part[blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------ column norms and gradient
+// Squared column norms of the (unscaled) Jacobian and the gradient J'r, in fixed summation order:
+//   blocks [0, nbs)          : thread per landmark -> inverse-depth column (ne, ge)
+//   blocks [nbs, nbs+NBMAX)  : 4 warps per free pose over its (landmark, slot) list -> 6 pose columns (nf, gf)
+__global__ void __launch_bounds__(BS_THREADS) ba_stats_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    const BaState& st = *P.st;
+    if (st.done || !st.relin) return;
+    __shared__ double part[4][12];
+    if ((int)blockIdx.x < D.nbs) {
+        const int l = blockIdx.x * BS_THREADS + threadIdx.x;
+        if (l >= D.nlm) return;
+        double ne = 0, ge = 0;
+        for (int i = P.lm_start[l]; i < P.lm_start[l + 1]; i++) {
+            const int o = P.lm_obs[i];
+            const double d0 = P.Jd[2 * o], d1 = P.Jd[2 * o + 1];
+            ne += d0 * d0 + d1 * d1;
+            ge += d0 * P.res[2 * o] + d1 * P.res[2 * o + 1];
+        }
+        P.ne[l] = ne;
+        P.ge[l] = ge;
+        return;
+    }
+    const int b = blockIdx.x - D.nbs;
+    if (b >= st.ncols / 6) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int eb = 0;
+    for (int i = 0; i < b; i++) eb += P.pstart[i + 1];
+    const int ee = eb + P.pstart[b + 1];
+    double v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = 0;
+    for (int idx = eb + threadIdx.x; idx < ee; idx += BS_THREADS) {
+        const uint32_t en = P.plist[idx];
+        const int l = en >> 8, su = en & 0xff;
+        const int ob = P.lm_start[l];
+        if (su) {
+            const int o = P.lm_obs[ob + su - 1];
+            const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const double j0 = P.Jp[12 * o + c], j1 = P.Jp[12 * o + 6 + c];
+                v[c] += j0 * j0 + j1 * j1;
+                v[6 + c] += j0 * r0 + j1 * r1;
+            }
+        } else {
+            for (int i = ob; i < P.lm_start[l + 1]; i++) {
+                const int o = P.lm_obs[i];
+                const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const double j0 = P.Ja[12 * o + c], j1 = P.Ja[12 * o + 6 + c];
+                    v[c] += j0 * j0 + j1 * j1;
+                    v[6 + c] += j0 * r0 + j1 * r1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+        if (lane == 0) part[warp][i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const double t = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+        if (threadIdx.x < 6) P.nf[6 * b + threadIdx.x] = t;
+        else P.gf[6 * b + threadIdx.x - 6] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ gather-form Schur: block lists
+// For block row bi: every (landmark, slot_u) of pose bi's list is paired with the landmark's slots holding pose bj >= bi
+// (bj == bi: slot_v >= slot_u, each unordered pair once).  MODE 0 counts the entries of each block, MODE 1 fills them in
+// list order (ballot-ordered appends).  One warp per block row.
+template <int MODE>
+__global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    BaState& st = *P.st;
+    const int nb = st.ncols / 6, bi = blockIdx.x, lane = threadIdx.x;
+    if (!st.use_gather) return;
+    if (bi >= nb) {
+        if (MODE == 0) for (int bj = lane; bj < NBMAX; bj += 32) P.blk_start[bi * NBMAX + bj + 1] = 0;
+        return;
+    }
+    int base_row = 0;   // MODE 1: entries of all preceding block rows
+    if (MODE == 1) {
+        int sum = 0;
+        for (int i = lane; i < bi * NBMAX; i += 32) sum += P.blk_start[i + 1];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        base_row = sum;
+    }
+    int eb = 0;
+    for (int i = 0; i < bi; i++) eb += P.pstart[i + 1];
+    const int ee = eb + P.pstart[bi + 1];
+    int cnt[NBMAX];      // running entry count of block (bi, bj), identical in every lane
+    int boff[NBMAX];     // MODE 1: start of block (bi, bj)
+#pragma unroll
+    for (int bj = 0; bj < NBMAX; bj++) { cnt[bj] = 0; boff[bj] = 0; }
+    if (MODE == 1) {
+        int run = base_row;
+#pragma unroll
+        for (int bj = 0; bj < NBMAX; bj++) { boff[bj] = run; run += P.blk_start[bi * NBMAX + bj + 1]; }
+    }
+    for (int c0 = eb; c0 < ee; c0 += 32) {
+        const int idx = c0 + lane;
+        const bool live = idx < ee;
+        const uint32_t en = live ? P.plist[idx] : 0u;
+        const int l = en >> 8, su = en & 0xff;
+        const int ob = live ? P.lm_start[l] : 0, ns = live ? P.lm_start[l + 1] - ob : -1;
+        for (int sv = 0; sv <= 255; sv++) {                 // slot-major rounds (ns is small: 3 in the reference's problems)
+            if (!__any_sync(0xffffffffu, live && sv <= ns)) break;
+            int bjv = -1;
+            if (live && sv <= ns) {
+                const int cv = sv ? P.obs_col[P.lm_obs[ob + sv - 1]] : P.anch_col[l];
+                if (cv >= 0) { const int bj = cv / 6; if (bj > bi || (bj == bi && sv >= su)) bjv = bj; }
+            }
+#pragma unroll
+            for (int bj = 0; bj < NBMAX; bj++) {
+                if (bj < bi) continue;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bjv == bj);
+                if (bal == 0) continue;
+                if (MODE == 1 && bjv == bj) {
+                    const int pos = boff[bj] + cnt[bj] + __popc(bal & ((1u << lane) - 1));
+                    if (pos < D.ecap) P.pairs[pos] = ((uint32_t)l << 16) | ((uint32_t)su << 8) | (uint32_t)sv;
+                }
+                cnt[bj] += __popc(bal);
+            }
+        }
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int bj = 0; bj < NBMAX; bj++) if (lane == 0) P.blk_start[bi * NBMAX + bj + 1] = cnt[bj];
+    } else if (bi == nb - 1 && lane == 0) {
+        int total = base_row;
+#pragma unroll
+        for (int bj = 0; bj < NBMAX; bj++) total += cnt[bj];
+        if (total > D.ecap) st.use_gather = 0;   // structure too large for the entry buffer: the atomic path takes over
+    }
 }
 
 // ------------------------------------------------------------------------------------------ control: before the step
@@ -572,44 +773,6 @@ __global__ void __launch_bounds__(128) ba_syrk_dmma_kernel(const BaProblem* __re
 // lists depend only on the problem's structure, so they are built once per solve (deterministically, in landmark
 // order) by ba_plist_kernel; every LM iteration then runs ba_lm_kernel (per-landmark E'E, E'b, F'e) and ba_gather_kernel
 // (one warp per block, fixed summation order -> bit-reproducible results, zero atomics).
-// Per free pose: the (landmark, slot) pairs that see it, in landmark order (deterministic).  MODE 0 counts, MODE 1 fills;
-// one warp per pose block, ballot-ordered appends.  Also decides whether the gather path applies (slot ids < 255).
-template <int MODE>
-__global__ void __launch_bounds__(32) ba_plist_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.y];
-    const int nb = P.st->ncols / 6;
-    const int b = blockIdx.x, lane = threadIdx.x;
-    if (b >= nb) { if (MODE == 0 && lane == 0) P.pstart[b + 1] = 0; return; }
-    const int col = 6 * b;
-    int base = 0;
-    if (MODE == 1) { for (int i = 0; i < b; i++) base += P.pstart[i + 1]; }   // counts of the preceding poses (pass 0 output)
-    int total = 0, maxobs = 0;
-    for (int l0 = 0; l0 < D.nlm; l0 += 32) {
-        const int l = l0 + lane;
-        const int ob = l < D.nlm ? P.lm_start[l] : 0;
-        const int ns = l < D.nlm ? (P.lm_start[l + 1] - ob) : 0;
-        maxobs = max(maxobs, ns);
-        int maxs = ns > 0 ? ns + 1 : 0;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) maxs = max(maxs, __shfl_xor_sync(0xffffffffu, maxs, off));
-        for (int sl = 0; sl < maxs; sl++) {      // slot-major rounds keep (landmark, slot) order within a 32-landmark chunk
-            bool hit = false;
-            if (ns > 0 && sl <= ns) hit = (sl == 0 ? P.anch_col[l] : P.obs_col[P.lm_obs[ob + sl - 1]]) == col;
-            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-            if (MODE == 1 && hit) P.plist[base + total + __popc(bal & ((1u << lane) - 1))] = ((uint32_t)l << 8) | (uint32_t)sl;
-            total += __popc(bal);
-        }
-    }
-    if (MODE == 0) {
-#pragma unroll
-        for (int off = 16; off; off >>= 1) maxobs = max(maxobs, __shfl_xor_sync(0xffffffffu, maxobs, off));
-        if (lane == 0) {
-            P.pstart[b + 1] = total;
-            if (b == 0) { P.st->use_gather = (maxobs < 255 && D.nlm < (1 << 24)) ? 1 : 0; P.st->nb = nb; }
-        }
-    }
-}
-
 // per-landmark Schur ingredients: E'E + D^2, E'b, F'e for the anchor slot (wa) and every observation slot (wp)
 __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
@@ -637,19 +800,28 @@ __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict_
     for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
 }
 
-// one warp per upper-triangular 6x6 block (bi <= bj): lanes stride over the block's entries, each keeps a private
-// 6x6 (+ rhs) accumulator, then a fixed-order shuffle reduction; the block and its mirror are stored, no atomics.
-__global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+// One CTA (4 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
+// private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction; the block and its mirror are
+// stored -- no atomics, bit-reproducible.
+__global__ void __launch_bounds__(128) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
     if (st.done || !st.use_gather) return;
-    const int key = blockIdx.x;
-    int bi = 0, rem = key;
-    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
-    const int bj = bi + rem;
-    if (bi >= st.nb || bj >= st.nb) return;
-    const int lane = threadIdx.x;
+    const int bi = blockIdx.x / NBMAX, bj = blockIdx.x % NBMAX;
+    if (bj < bi || bi >= st.nb || bj >= st.nb) return;
+    __shared__ double red[4][42];
+    __shared__ int eb_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci = 6 * bi, cj = 6 * bj;
+    if (warp == 0) {   // start of this block's entries = sum of the counts of all preceding blocks
+        int sum = 0;
+        for (int i = lane; i < (int)blockIdx.x; i += 32) sum += P.blk_start[i + 1];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0) eb_s = sum;
+    }
+    __syncthreads();
+    const int eb = eb_s, ee = eb + P.blk_start[blockIdx.x + 1];
     double acc[36], rh[6];
 #pragma unroll
     for (int i = 0; i < 36; i++) acc[i] = 0.0;
@@ -658,19 +830,12 @@ __global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restri
     double sci[6], scj[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
-    int eb = 0;
-    for (int i = 0; i < bi; i++) eb += P.pstart[i + 1];
-    const int ee = eb + P.pstart[bi + 1];
-    for (int idx = eb + lane; idx < ee; idx += 32) {
-        const uint32_t en = P.plist[idx];
-        const int l = en >> 8, su = en & 0xff;
-        const int ob = P.lm_start[l], ns = P.lm_start[l + 1] - ob;
+    for (int idx = eb + tid; idx < ee; idx += 128) {
+        const uint32_t en = P.pairs[idx];
+        const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
+        const int ob = P.lm_start[l];
         const double inv = 1.0 / P.ete[l], etb = P.etb[l];
-        const int ou = su ? P.lm_obs[ob + su - 1] : -1;
-        // partner slots holding pose bj (for the diagonal block: sv >= su, each unordered pair once)
-        for (int sv = (bi == bj ? su : 0); sv <= ns; sv++) {
-        const int ov = sv ? P.lm_obs[ob + sv - 1] : -1;
-        if ((sv ? P.obs_col[ov] : P.anch_col[l]) != cj) continue;
+        const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
         double wu[6], wv[6], C[36];
 #pragma unroll
         for (int c = 0; c < 6; c++) {
@@ -729,103 +894,91 @@ __global__ void __launch_bounds__(32) ba_gather_kernel(const BaProblem* __restri
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int c = 0; c < 6; c++) acc[6 * a + c] += C[6 * a + c] + (dup ? C[6 * c + a] : 0.0);
-        }   // sv
     }
-    // fixed-order butterfly reduction
+    // fixed-order reduction: butterfly inside each warp, then the four warps in order
 #pragma unroll
-    for (int i = 0; i < 36; i++)
+    for (int i = 0; i < 36; i++) {
 #pragma unroll
         for (int off = 16; off; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-    if (bi == bj) {
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int off = 16; off; off >>= 1) rh[i] += __shfl_xor_sync(0xffffffffu, rh[i], off);
+        if (lane == 0) red[warp][i] = acc[i];
     }
-    if (lane == 0) {
-        if (bi == bj) {
-            for (int a = 0; a < 6; a++) {
-                P.rhs[ci + a] = rh[a];
-                for (int c = 0; c < 6; c++) {
-                    const double v = acc[6 * a + c] + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
-                    P.S[(ci + a) * NMAX + ci + c] = v;
-                }
-            }
-        } else {
-            for (int a = 0; a < 6; a++)
-                for (int c = 0; c < 6; c++) {
-                    P.S[(ci + a) * NMAX + cj + c] = acc[6 * a + c];
-                    P.S[(cj + c) * NMAX + ci + a] = acc[6 * a + c];
-                }
-        }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) rh[i] += __shfl_xor_sync(0xffffffffu, rh[i], off);
+        if (lane == 0) red[warp][36 + i] = rh[i];
+    }
+    __syncthreads();
+    if (tid < 36) {
+        const int a = tid / 6, c = tid % 6;
+        const double v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        if (bi == bj) P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
+        else { P.S[(ci + a) * NMAX + cj + c] = v; P.S[(cj + c) * NMAX + ci + a] = v; }
+    } else if (tid < 42 && bi == bj) {
+        const int a = tid - 36;
+        P.rhs[ci + a] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
     }
 }
 
-// ------------------------------------------------------------------------------------------ Cholesky (1 CTA / problem)
-// Blocked right-looking Cholesky of the <= 126 x 126 reduced system in shared memory: per 8-column panel, warp 0 factors
-// the panel with warp-synchronous steps, then all 1024 threads apply the rank-8 update to the trailing lower triangle.
-// Followed by the two triangular solves (warp 0).  yf = S^-1 rhs.
-constexpr int CH_THREADS = 1024, CH_NB = 8;
+// ------------------------------------------------------------------------------------------ reduced solve (1 CTA / problem)
+// Left-looking LDL' of the <= 126 x 126 reduced camera system in shared memory: column j of V = L D is one parallel
+// matrix-vector product over the already finished columns (8 threads per row, shuffle-reduced) and ONE barrier -- no
+// square roots, no trailing updates, no serial panel.  S = L D L' with L[i][k] = V[i][k] / d_k.  Then the two triangular
+// solves (warp 0, lane-strided dot products).  yf = S^-1 rhs.
+constexpr int CH_THREADS = 1024;
 __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     extern __shared__ double sm[];
     const BaProblem P = probs[blockIdx.x];
     BaState& st = *P.st;
     if (st.done) return;
-    const int n = st.ncols, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = st.ncols, tid = threadIdx.x, lane = tid & 31;
     const int ld = NMAX + 1;
-    double* L = sm;               // NMAX x ld
-    double* y = sm + NMAX * ld;   // NMAX
+    double* V = sm;                 // NMAX x ld, lower triangle
+    double* invd = sm + NMAX * ld;  // NMAX
+    double* y = invd + NMAX;        // NMAX
     __shared__ int ok_s;
-    for (int i = tid; i < n * n; i += CH_THREADS) { const int r = i / n, c = i - r * n; L[r * ld + c] = P.S[r * NMAX + c]; }
+    for (int i = tid; i < n * n; i += CH_THREADS) { const int r = i / n, c = i - r * n; V[r * ld + c] = P.S[r * NMAX + c]; }
     if (tid == 0) ok_s = 1;
     __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += CH_NB) {
-        const int jb = min(CH_NB, n - j0);
-        if (warp == 0) {
-            for (int j = j0; j < j0 + jb; j++) {
-                double d = L[j * ld + j];
-                if (!(d > 0)) { if (lane == 0) ok_s = 0; d = 1.0; }
-                const double dj = sqrt(d);
-                __syncwarp();
-                if (lane == 0) L[j * ld + j] = dj;
-                const double rdj = 1.0 / dj;
-                for (int i = j + 1 + lane; i < n; i += 32) L[i * ld + j] *= rdj;
-                __syncwarp();
-                // update the remaining columns of the panel
-                for (int k = j + 1; k < j0 + jb; k++) {
-                    const double lkj = L[k * ld + j];
-                    for (int i = k + lane; i < n; i += 32) L[i * ld + k] -= L[i * ld + j] * lkj;
+    const int row = tid >> 3, part = tid & 7;
+    for (int j = 0; j < n; j++) {
+        const bool act = row >= j && row < n;
+        double s = 0;
+        if (act)
+            for (int k = part; k < j; k += 8) s += V[row * ld + k] * (V[j * ld + k] * invd[k]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans four rows)
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (act) {
+            if (part == 0) {
+                const double v = V[row * ld + j] - s;
+                V[row * ld + j] = v;
+                if (row == j) {
+                    if (!(v > 0)) ok_s = 0;
+                    invd[j] = 1.0 / (v > 0 ? v : 1.0);
                 }
-                __syncwarp();
             }
         }
         __syncthreads();
-        // trailing update: A[i][k] -= sum_{c in panel} L[i][c] L[k][c],  j0 + jb <= k <= i < n
-        const int t0 = j0 + jb, m = n - t0;
-        for (int t = tid; t < m * m; t += CH_THREADS) {
-            const int i = t0 + t / m, k = t0 + t % m;
-            if (k > i) continue;
-            double s = 0;
-            for (int c = j0; c < j0 + jb; c++) s += L[i * ld + c] * L[k * ld + c];
-            L[i * ld + k] -= s;
-        }
-        __syncthreads();
     }
-    if (warp == 0) {
+    if (tid < 32) {
+        // forward: z_i = b_i - sum_{k<i} L[i][k] z_k ; then w = z / d ; backward: x_i = w_i - sum_{k>i} L[k][i] x_k
         for (int i = 0; i < n; i++) {
             double s = 0;
-            for (int k = lane; k < i; k += 32) s += L[i * ld + k] * y[k];
+            for (int k = lane; k < i; k += 32) s += V[i * ld + k] * invd[k] * y[k];
 #pragma unroll
             for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) y[i] = (P.rhs[i] - s) / L[i * ld + i];
+            if (lane == 0) y[i] = P.rhs[i] - s;
             __syncwarp();
         }
+        for (int i = lane; i < n; i += 32) y[i] *= invd[i];
+        __syncwarp();
         for (int i = n - 1; i >= 0; i--) {
             double s = 0;
-            for (int k = i + 1 + lane; k < n; k += 32) s += L[k * ld + i] * y[k];
+            for (int k = i + 1 + lane; k < n; k += 32) s += V[k * ld + i] * y[k];
 #pragma unroll
             for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) y[i] = (y[i] - s) / L[i * ld + i];
+            if (lane == 0) y[i] -= s * invd[i];
             __syncwarp();
         }
         for (int i = lane; i < n; i += 32) P.yf[i] = y[i];
@@ -1021,6 +1174,7 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
     bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
     bytes += align_up((size_t)(NBMAX + 1) * 4, 8) + align_up(((size_t)nobs + (size_t)nlm) * 4, 8);   // pstart, plist
+    bytes += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);   // blk_start, pairs
     bytes += align_up(sizeof(BaState), 8);
     return align_up(bytes, 256);
 }
@@ -1080,6 +1234,8 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
             P.anch_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nlm * 4, 8);
             P.pstart = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX + 1) * 4, 8);
             P.plist = reinterpret_cast<uint32_t*>(b); b += align_up(((size_t)nobs + (size_t)nlm) * 4, 8);
+            P.blk_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8);
+            P.pairs = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
             P.st = reinterpret_cast<BaState*>(b);
         }
         ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
@@ -1089,21 +1245,23 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
     const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
     BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4, 8 * nobs + 2 * nlm, (nlm + BS_THREADS - 1) / BS_THREADS};
     const bool dense = g_ba_dense_schur != 0;
-    const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + NMAX) * sizeof(double);
+    const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + 2 * NMAX) * sizeof(double);
     ALVA_CUDA(cudaFuncSetAttribute(ba_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-    ba_setup_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+    ba_setup_kernel<<<nprob, SETUP_THREADS, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
-    const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob);
+    const dim3 key_grid(NBMAX * NBMAX, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
     if (!dense) {   // structure of the gather-form Schur complement, once per solve
-        const dim3 pl_grid(NBMAX, nprob);
-        ba_plist_kernel<0><<<pl_grid, 32, 0, ctx->stream>>>(dp, D);
+        const dim3 pr_grid(NBMAX, nprob);
+        ba_pairs_kernel<0><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_plist_kernel<1><<<pl_grid, 32, 0, ctx->stream>>>(dp, D);
+        ba_pairs_kernel<1><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
     for (int it = 0; it <= max_iter; it++) {
         ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_stats_kernel<<<stats_grid, BS_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_pre_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
@@ -1116,7 +1274,7 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         } else {
             ba_lm_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);           // gather path (no-op if structure too large)
             ALVA_LAUNCH_CHECK(ctx);
-            ba_gather_kernel<<<key_grid, 32, 0, ctx->stream>>>(dp, D);
+            ba_gather_kernel<<<key_grid, 128, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
             ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);  // atomic fallback (no-op when gather ran)
             ALVA_LAUNCH_CHECK(ctx);
