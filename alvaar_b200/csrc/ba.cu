@@ -448,6 +448,8 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
     BaState& st = *P.st;
     const int nb = st.ncols / 6, bi = blockIdx.x, lane = threadIdx.x;
     if (!st.use_gather) return;
+    __shared__ int cnt[NBMAX];    // running entry count of block (bi, bj)
+    __shared__ int boff[NBMAX];   // MODE 1: start of block (bi, bj)
     if (bi >= nb) {
         if (MODE == 0) for (int bj = lane; bj < NBMAX; bj += 32) P.blk_start[bi * NBMAX + bj + 1] = 0;
         return;
@@ -460,18 +462,15 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
         for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         base_row = sum;
     }
+    if (lane < NBMAX) cnt[lane] = 0;
+    if (lane == 0) {
+        int run = base_row;
+        for (int bj = 0; bj < NBMAX; bj++) { boff[bj] = run; if (MODE == 1) run += P.blk_start[bi * NBMAX + bj + 1]; }
+    }
+    __syncwarp();
     int eb = 0;
     for (int i = 0; i < bi; i++) eb += P.pstart[i + 1];
     const int ee = eb + P.pstart[bi + 1];
-    int cnt[NBMAX];      // running entry count of block (bi, bj), identical in every lane
-    int boff[NBMAX];     // MODE 1: start of block (bi, bj)
-#pragma unroll
-    for (int bj = 0; bj < NBMAX; bj++) { cnt[bj] = 0; boff[bj] = 0; }
-    if (MODE == 1) {
-        int run = base_row;
-#pragma unroll
-        for (int bj = 0; bj < NBMAX; bj++) { boff[bj] = run; run += P.blk_start[bi * NBMAX + bj + 1]; }
-    }
     for (int c0 = eb; c0 < ee; c0 += 32) {
         const int idx = c0 + lane;
         const bool live = idx < ee;
@@ -484,26 +483,29 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
             if (live && sv <= ns) {
                 const int cv = sv ? P.obs_col[P.lm_obs[ob + sv - 1]] : P.anch_col[l];
                 if (cv >= 0) { const int bj = cv / 6; if (bj > bi || (bj == bi && sv >= su)) bjv = bj; }
+                // a landmark seen twice from one keyframe (two slots on the same pose) needs the transposed contribution
+                // as well; localBA never builds that, so such problems simply take the atomic Schur path instead
+                if (MODE == 0 && cv >= 0 && cv / 6 == bi && sv > su) st.use_gather = 0;
             }
-#pragma unroll
-            for (int bj = 0; bj < NBMAX; bj++) {
-                if (bj < bi) continue;
-                const uint32_t bal = __ballot_sync(0xffffffffu, bjv == bj);
-                if (bal == 0) continue;
-                if (MODE == 1 && bjv == bj) {
-                    const int pos = boff[bj] + cnt[bj] + __popc(bal & ((1u << lane) - 1));
+            // lanes that hit the same block append in lane order: one match instead of one ballot per block
+            const uint32_t m = __match_any_sync(0xffffffffu, bjv);
+            if (bjv >= 0) {
+                const int rank = __popc(m & ((1u << lane) - 1));
+                const int old = cnt[bjv];
+                if (MODE == 1) {
+                    const int pos = boff[bjv] + old + rank;
                     if (pos < D.ecap) P.pairs[pos] = ((uint32_t)l << 16) | ((uint32_t)su << 8) | (uint32_t)sv;
                 }
-                cnt[bj] += __popc(bal);
+                __syncwarp(m);
+                if (rank == 0) cnt[bjv] = old + __popc(m);
             }
+            __syncwarp();
         }
     }
     if (MODE == 0) {
-#pragma unroll
-        for (int bj = 0; bj < NBMAX; bj++) if (lane == 0) P.blk_start[bi * NBMAX + bj + 1] = cnt[bj];
+        if (lane < NBMAX) P.blk_start[bi * NBMAX + lane + 1] = cnt[lane];
     } else if (bi == nb - 1 && lane == 0) {
         int total = base_row;
-#pragma unroll
         for (int bj = 0; bj < NBMAX; bj++) total += cnt[bj];
         if (total > D.ecap) st.use_gather = 0;   // structure too large for the entry buffer: the atomic path takes over
     }
@@ -800,28 +802,101 @@ __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict_
     for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
 }
 
-// One CTA (4 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
+// Contribution of one (landmark, slot_u, slot_v) entry to block (bi, bj):  C = F_u'F_v - w_u w_v' / (E'E + D^2)  and, for
+// u == v, the right-hand side F_u'b - w_u E'b / (E'E + D^2).  TRANSPOSE adds C' instead (second half of a duplicate-pose pair).
+template <bool TRANSPOSE>   // TRANSPOSE is kept for completeness; the kernel only instantiates <false>
+__device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, const double* sci, const double* scj, double* acc,
+                                             double* rh) {
+    const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
+    const int ob = P.lm_start[l];
+    const double inv = 1.0 / P.ete[l], etb = P.etb[l];
+    const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+    double wu[6], wv[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        wu[c] = (su ? P.wp[6 * ou + c] : P.wa[6 * l + c]) * inv;
+        wv[c] = sv ? P.wp[6 * ov + c] : P.wa[6 * l + c];
+    }
+#define ACC(a, c) acc[TRANSPOSE ? 6 * (c) + (a) : 6 * (a) + (c)]
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) ACC(a, c) -= wu[a] * wv[c];
+    // F_u' F_v: non-zero only when both slots share a residual row pair
+    if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
+        const int oe = P.lm_start[l + 1];
+        for (int i = ob; i < oe; i++) {
+            const int o = P.lm_obs[i];
+            double F0[6], F1[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) { F0[c] = P.Ja[12 * o + c] * sci[c]; F1[c] = P.Ja[12 * o + 6 + c] * sci[c]; }
+            const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                if (!TRANSPOSE) rh[a] += F0[a] * r0 + F1[a] * r1;
+#pragma unroll
+                for (int c = 0; c < 6; c++) ACC(a, c) += F0[a] * F0[c] + F1[a] * F1[c];
+            }
+        }
+        if (!TRANSPOSE)
+#pragma unroll
+            for (int a = 0; a < 6; a++) rh[a] -= wu[a] * etb;
+    } else if (su == sv) {                           // observation x itself
+        double F0[6], F1[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { F0[c] = P.Jp[12 * ou + c] * sci[c]; F1[c] = P.Jp[12 * ou + 6 + c] * sci[c]; }
+        const double r0 = P.res[2 * ou], r1 = P.res[2 * ou + 1];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            if (!TRANSPOSE) rh[a] += F0[a] * r0 + F1[a] * r1 - wu[a] * etb;
+#pragma unroll
+            for (int c = 0; c < 6; c++) ACC(a, c) += F0[a] * F0[c] + F1[a] * F1[c];
+        }
+    } else if (su == 0 || sv == 0) {                 // anchor x observation (either order): rows of that observation
+        const int o = su ? ou : ov;
+        double A0[6], A1[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            A0[a] = (su ? P.Jp[12 * o + a] : P.Ja[12 * o + a]) * sci[a];
+            A1[a] = (su ? P.Jp[12 * o + 6 + a] : P.Ja[12 * o + 6 + a]) * sci[a];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const double b0 = (sv ? P.Jp[12 * o + c] : P.Ja[12 * o + c]) * scj[c];
+            const double b1 = (sv ? P.Jp[12 * o + 6 + c] : P.Ja[12 * o + 6 + c]) * scj[c];
+#pragma unroll
+            for (int a = 0; a < 6; a++) ACC(a, c) += A0[a] * b0 + A1[a] * b1;
+        }
+    }
+#undef ACC
+}
+
+// One CTA (2 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
 // private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction; the block and its mirror are
 // stored -- no atomics, bit-reproducible.
-__global__ void __launch_bounds__(128) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+constexpr int GA_THREADS = 64;
+__global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
     if (st.done || !st.use_gather) return;
-    const int bi = blockIdx.x / NBMAX, bj = blockIdx.x % NBMAX;
-    if (bj < bi || bi >= st.nb || bj >= st.nb) return;
-    __shared__ double red[4][42];
+    int bi = 0, rem = blockIdx.x;                        // grid.x enumerates the upper triangle over NBMAX
+    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
+    const int bj = bi + rem;
+    if (bi >= st.nb || bj >= st.nb) return;
+    const int blk = bi * NBMAX + bj;
+    __shared__ double red[GA_THREADS / 32][42];
     __shared__ int eb_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci = 6 * bi, cj = 6 * bj;
     if (warp == 0) {   // start of this block's entries = sum of the counts of all preceding blocks
         int sum = 0;
-        for (int i = lane; i < (int)blockIdx.x; i += 32) sum += P.blk_start[i + 1];
+        for (int i = lane; i < blk; i += 32) sum += P.blk_start[i + 1];
 #pragma unroll
         for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         if (lane == 0) eb_s = sum;
     }
     __syncthreads();
-    const int eb = eb_s, ee = eb + P.blk_start[blockIdx.x + 1];
+    const int eb = eb_s, ee = eb + P.blk_start[blk + 1];
     double acc[36], rh[6];
 #pragma unroll
     for (int i = 0; i < 36; i++) acc[i] = 0.0;
@@ -830,72 +905,11 @@ __global__ void __launch_bounds__(128) ba_gather_kernel(const BaProblem* __restr
     double sci[6], scj[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
-    for (int idx = eb + tid; idx < ee; idx += 128) {
+    for (int idx = eb + tid; idx < ee; idx += GA_THREADS) {
         const uint32_t en = P.pairs[idx];
-        const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
-        const int ob = P.lm_start[l];
-        const double inv = 1.0 / P.ete[l], etb = P.etb[l];
-        const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
-        double wu[6], wv[6], C[36];
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            wu[c] = su ? P.wp[6 * ou + c] : P.wa[6 * l + c];
-            wv[c] = sv ? P.wp[6 * ov + c] : P.wa[6 * l + c];
-        }
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int c = 0; c < 6; c++) C[6 * a + c] = -wu[a] * inv * wv[c];
-        // F_u' F_v: non-zero only when both slots share a residual row pair
-        if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
-            const int oe = P.lm_start[l + 1];
-            for (int i = ob; i < oe; i++) {
-                const int o = P.lm_obs[i];
-                double F0[6], F1[6];
-#pragma unroll
-                for (int c = 0; c < 6; c++) { F0[c] = P.Ja[12 * o + c] * sci[c]; F1[c] = P.Ja[12 * o + 6 + c] * sci[c]; }
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    rh[a] += F0[a] * P.res[2 * o] + F1[a] * P.res[2 * o + 1];
-#pragma unroll
-                    for (int c = 0; c < 6; c++) C[6 * a + c] += F0[a] * F0[c] + F1[a] * F1[c];
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 6; a++) rh[a] -= wu[a] * inv * etb;
-        } else if (su == sv) {                           // observation x itself
-            double F0[6], F1[6];
-#pragma unroll
-            for (int c = 0; c < 6; c++) { F0[c] = P.Jp[12 * ou + c] * sci[c]; F1[c] = P.Jp[12 * ou + 6 + c] * sci[c]; }
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-                rh[a] += F0[a] * P.res[2 * ou] + F1[a] * P.res[2 * ou + 1] - wu[a] * inv * etb;
-#pragma unroll
-                for (int c = 0; c < 6; c++) C[6 * a + c] += F0[a] * F0[c] + F1[a] * F1[c];
-            }
-        } else if (su == 0 || sv == 0) {                 // anchor x observation (either order): rows of that observation
-            const int o = su ? ou : ov;
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-                const double a0 = (su ? P.Jp[12 * o + a] : P.Ja[12 * o + a]) * sci[a];
-                const double a1 = (su ? P.Jp[12 * o + 6 + a] : P.Ja[12 * o + 6 + a]) * sci[a];
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    const double b0 = (sv ? P.Jp[12 * o + c] : P.Ja[12 * o + c]) * scj[c];
-                    const double b1 = (sv ? P.Jp[12 * o + 6 + c] : P.Ja[12 * o + 6 + c]) * scj[c];
-                    C[6 * a + c] += a0 * b0 + a1 * b1;
-                }
-            }
-        }
-        // two different slots on the same pose (never produced by localBA): the ordered pair (v, u) lands in the same
-        // diagonal block, add its transpose as well
-        const bool dup = (bi == bj) && (su != sv);
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc[6 * a + c] += C[6 * a + c] + (dup ? C[6 * c + a] : 0.0);
+        gather_entry<false>(P, en, sci, scj, acc, rh);   // (duplicate-pose pairs never reach this kernel: see ba_pairs_kernel)
     }
-    // fixed-order reduction: butterfly inside each warp, then the four warps in order
+    // fixed-order reduction: butterfly inside each warp, then the warps in order
 #pragma unroll
     for (int i = 0; i < 36; i++) {
 #pragma unroll
@@ -909,14 +923,15 @@ __global__ void __launch_bounds__(128) ba_gather_kernel(const BaProblem* __restr
         if (lane == 0) red[warp][36 + i] = rh[i];
     }
     __syncthreads();
-    if (tid < 36) {
-        const int a = tid / 6, c = tid % 6;
-        const double v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-        if (bi == bj) P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
-        else { P.S[(ci + a) * NMAX + cj + c] = v; P.S[(cj + c) * NMAX + ci + a] = v; }
-    } else if (tid < 42 && bi == bj) {
-        const int a = tid - 36;
-        P.rhs[ci + a] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    if (tid < 42) {
+        double v = 0;
+#pragma unroll
+        for (int wv = 0; wv < GA_THREADS / 32; wv++) v += red[wv][tid];
+        if (tid < 36) {
+            const int a = tid / 6, c = tid % 6;
+            if (bi == bj) P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
+            else { P.S[(ci + a) * NMAX + cj + c] = v; P.S[(cj + c) * NMAX + ci + a] = v; }
+        } else if (bi == bj) P.rhs[ci + tid - 36] = v;
     }
 }
 
@@ -925,7 +940,7 @@ __global__ void __launch_bounds__(128) ba_gather_kernel(const BaProblem* __restr
 // matrix-vector product over the already finished columns (8 threads per row, shuffle-reduced) and ONE barrier -- no
 // square roots, no trailing updates, no serial panel.  S = L D L' with L[i][k] = V[i][k] / d_k.  Then the two triangular
 // solves (warp 0, lane-strided dot products).  yf = S^-1 rhs.
-constexpr int CH_THREADS = 1024;
+constexpr int CH_THREADS = 512, CH_PARTS = 4;   // 128 rows x 4 threads per row
 __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     extern __shared__ double sm[];
     const BaProblem P = probs[blockIdx.x];
@@ -933,55 +948,58 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
     if (st.done) return;
     const int n = st.ncols, tid = threadIdx.x, lane = tid & 31;
     const int ld = NMAX + 1;
-    double* V = sm;                 // NMAX x ld, lower triangle
+    double* V = sm;                 // (n + 1) x ld: row n is the right-hand side (augmented system)
     double* invd = sm + NMAX * ld;  // NMAX
-    double* y = invd + NMAX;        // NMAX
     __shared__ int ok_s;
     for (int i = tid; i < n * n; i += CH_THREADS) { const int r = i / n, c = i - r * n; V[r * ld + c] = P.S[r * NMAX + c]; }
+    for (int i = tid; i < n; i += CH_THREADS) V[n * ld + i] = P.rhs[i];
     if (tid == 0) ok_s = 1;
     __syncthreads();
-    const int row = tid >> 3, part = tid & 7;
+    // column j of V = L D:  V[i][j] = A[i][j] - sum_{k<j} V[i][k] V[j][k] / d_k  for all rows i >= j -- including the
+    // augmented row n, whose entries are the forward-substituted right-hand side z = L^-1 b.
+    const int row = tid / CH_PARTS, part = tid % CH_PARTS;
     for (int j = 0; j < n; j++) {
-        const bool act = row >= j && row < n;
-        double s = 0;
-        if (act)
-            for (int k = part; k < j; k += 8) s += V[row * ld + k] * (V[j * ld + k] * invd[k]);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans four rows)
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const bool act = row >= j && row <= n;
+        double s0 = 0, s1 = 0;
         if (act) {
-            if (part == 0) {
-                const double v = V[row * ld + j] - s;
-                V[row * ld + j] = v;
-                if (row == j) {
-                    if (!(v > 0)) ok_s = 0;
-                    invd[j] = 1.0 / (v > 0 ? v : 1.0);
-                }
+            int k = part;
+            for (; k + CH_PARTS < j; k += 2 * CH_PARTS) {
+                s0 += V[row * ld + k] * (V[j * ld + k] * invd[k]);
+                s1 += V[row * ld + k + CH_PARTS] * (V[j * ld + k + CH_PARTS] * invd[k + CH_PARTS]);
+            }
+            if (k < j) s0 += V[row * ld + k] * (V[j * ld + k] * invd[k]);
+        }
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans eight rows)
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (act && part == 0) {
+            const double v = V[row * ld + j] - s;
+            V[row * ld + j] = v;
+            if (row == j) {
+                if (!(v > 0)) ok_s = 0;
+                invd[j] = 1.0 / (v > 0 ? v : 1.0);
             }
         }
         __syncthreads();
     }
+    // backward: x = L^-T D^-1 z, column-oriented inside one warp: lane owns entries lane, lane+32, lane+64, lane+96 in
+    // registers; after x_i is final it is broadcast and eliminated from the entries above it.
     if (tid < 32) {
-        // forward: z_i = b_i - sum_{k<i} L[i][k] z_k ; then w = z / d ; backward: x_i = w_i - sum_{k>i} L[k][i] x_k
-        for (int i = 0; i < n; i++) {
-            double s = 0;
-            for (int k = lane; k < i; k += 32) s += V[i * ld + k] * invd[k] * y[k];
+        double xr[4];
 #pragma unroll
-            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) y[i] = P.rhs[i] - s;
-            __syncwarp();
-        }
-        for (int i = lane; i < n; i += 32) y[i] *= invd[i];
-        __syncwarp();
+        for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; xr[q] = i < n ? V[n * ld + i] * invd[i] : 0.0; }
         for (int i = n - 1; i >= 0; i--) {
-            double s = 0;
-            for (int k = i + 1 + lane; k < n; k += 32) s += V[k * ld + i] * y[k];
+            const int qi = i >> 5;                                             // warp-uniform
+            const double own = qi == 0 ? xr[0] : qi == 1 ? xr[1] : qi == 2 ? xr[2] : xr[3];
+            const double xi = __shfl_sync(0xffffffffu, own, i & 31);
 #pragma unroll
-            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) y[i] -= s * invd[i];
-            __syncwarp();
+            for (int q = 0; q < 4; q++) {
+                const int k = lane + 32 * q;
+                if (k < i) xr[q] -= V[i * ld + k] * invd[k] * xi;
+            }
         }
-        for (int i = lane; i < n; i += 32) P.yf[i] = y[i];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < n) P.yf[i] = xr[q]; }
         if (lane == 0) st.chol_ok = ok_s;
     }
 }
@@ -1245,12 +1263,12 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
     const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
     BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4, 8 * nobs + 2 * nlm, (nlm + BS_THREADS - 1) / BS_THREADS};
     const bool dense = g_ba_dense_schur != 0;
-    const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + 2 * NMAX) * sizeof(double);
+    const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + NMAX) * sizeof(double);
     ALVA_CUDA(cudaFuncSetAttribute(ba_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     ba_setup_kernel<<<nprob, SETUP_THREADS, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
-    const dim3 key_grid(NBMAX * NBMAX, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
+    const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
     if (!dense) {   // structure of the gather-form Schur complement, once per solve
         const dim3 pr_grid(NBMAX, nprob);
         ba_pairs_kernel<0><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
@@ -1274,7 +1292,7 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         } else {
             ba_lm_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);           // gather path (no-op if structure too large)
             ALVA_LAUNCH_CHECK(ctx);
-            ba_gather_kernel<<<key_grid, 128, 0, ctx->stream>>>(dp, D);
+            ba_gather_kernel<<<key_grid, GA_THREADS, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
             ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);  // atomic fallback (no-op when gather ran)
             ALVA_LAUNCH_CHECK(ctx);

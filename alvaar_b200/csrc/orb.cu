@@ -22,15 +22,23 @@ __constant__ int8_t c_pattern[1024] = {
 // getGaussianKernel(7, 2, CV_32F) (imgproc/src/smooth.dispatch.cpp:76-190): k[3], k[2]=k[4], k[1]=k[5], k[0]=k[6]
 __constant__ uint32_t c_gauss_bits[4] = {0x3e5d4ae0u, 0x3e434a39u, 0x3e06387eu, 0x3d8fafb1u};
 
-constexpr int BTW = 128, BTH = 32;          // blur tile
-constexpr int BIP = BTW + 8;                // input smem pitch (halo 3, padded to 4)
-constexpr int BIR = BTH + 6;
+constexpr int BTW = 128, BTH = 64;          // blur tile (outputs)
+constexpr int BIP = BTW + 16;               // input smem pitch in bytes: image x0-8 at byte 0 (only x0-3 .. x0+BTW+2 are used)
+constexpr int BIR = BTH + 6;                // input rows y0-3 .. y0+BTH+2
 
+// u8 -> f32 without the conversion pipe: 0x4B000000 | b is the float 2^23 + b; one PRMT + one FADD (exact)
+__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t sel) {
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), 8388608.f);
+}
+
+// Separable 7x7 Gaussian exactly as OpenCV's float path evaluates it (see file header): row pass then column pass.
+// Thread = 4 adjacent pixels: the row pass reads three packed words and produces a float4; the column pass walks an
+// 8-row strip with a rolling 7-row window of float4, packs 4 results and stores one 32-bit word.
 template <bool FMA>
 __global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w,
                                                        int h) {
-    __shared__ uint8_t in_s[BIR][BIP];
-    __shared__ float row_s[BIR][BTW];
+    __shared__ __align__(16) uint8_t in_s[BIR][BIP];
+    __shared__ __align__(16) float row_s[BIR][BTW];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH;
     const size_t fo = (size_t)blockIdx.z * w * h;
@@ -39,53 +47,82 @@ __global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict
 #pragma unroll
     for (int i = 0; i < 4; i++) k[i] = __uint_as_float(c_gauss_bits[i]);   // k[j] = weight at distance j
 
-    for (int i = tid; i < BIR * BIP; i += 256) {
-        const int r = i / BIP, c = i - r * BIP;
-        const int x = reflect101(min(x0 + c - 4, w + 3), w), y = reflect101(min(y0 + r - 3, h + 3), h);
-        in_s[r][c] = __ldg(s + (size_t)y * w + x);
+    const bool interior = (x0 >= 8) && (x0 + BTW + 8 <= w) && ((w & 3) == 0) && ((((uintptr_t)src) & 3) == 0);
+    if (interior) {   // word loads, rows reflected
+        for (int i = tid; i < BIR * (BIP / 4); i += 256) {
+            const int r = i / (BIP / 4), c4 = i - r * (BIP / 4);
+            const int y = reflect101(min(y0 + r - 3, h + 3), h);
+            reinterpret_cast<uint32_t*>(&in_s[r][0])[c4] = __ldg(reinterpret_cast<const uint32_t*>(s + (size_t)y * w + x0 - 8) + c4);
+        }
+    } else {
+        for (int i = tid; i < BIR * BIP; i += 256) {
+            const int r = i / BIP, c = i - r * BIP;
+            const int x = reflect101(max(min(x0 + c - 8, w + 7), -8), w), y = reflect101(min(y0 + r - 3, h + 3), h);
+            in_s[r][c] = __ldg(s + (size_t)y * w + x);
+        }
     }
     __syncthreads();
     // row filter: s = k0*S[0]; s += k[i]*S[i], left to right (RowFilter<uchar,float>, filter.simd.hpp:2477-2487)
-    for (int i = tid; i < BIR * BTW; i += 256) {
-        const int r = i / BTW, c = i - r * BTW;
-        const uint8_t* S = &in_s[r][c + 1];   // S[0] = pixel x-3
-        float acc;
-        if (FMA) {
-            acc = 0.f;
+    for (int i = tid; i < BIR * (BTW / 4); i += 256) {
+        const int r = i >> 5, g = i & 31;                      // BTW / 4 == 32 groups per row
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&in_s[r][0]) + 1 + g;   // W0 = x-4..x-1, W1 = x..x+3, W2 = x+4..x+7
+        const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2];
+        float f[10];                                            // pixels x-3 .. x+6
+        f[0] = byte_to_float(W0, 0x7651); f[1] = byte_to_float(W0, 0x7652); f[2] = byte_to_float(W0, 0x7653);
+        f[3] = byte_to_float(W1, 0x7650); f[4] = byte_to_float(W1, 0x7651); f[5] = byte_to_float(W1, 0x7652);
+        f[6] = byte_to_float(W1, 0x7653); f[7] = byte_to_float(W2, 0x7650); f[8] = byte_to_float(W2, 0x7651);
+        f[9] = byte_to_float(W2, 0x7652);
+        float o[4];
 #pragma unroll
-            for (int t = 0; t < 7; t++) acc = __fmaf_rn((float)S[t], k[t < 3 ? 3 - t : t - 3], acc);
-        } else {
-            acc = __fmul_rn(k[3], (float)S[0]);
+        for (int j = 0; j < 4; j++) {
+            float acc;
+            if (FMA) {
+                acc = 0.f;
 #pragma unroll
-            for (int t = 1; t < 7; t++) acc = __fadd_rn(acc, __fmul_rn(k[t < 3 ? 3 - t : t - 3], (float)S[t]));
+                for (int t = 0; t < 7; t++) acc = __fmaf_rn(f[j + t], k[t < 3 ? 3 - t : t - 3], acc);
+            } else {
+                acc = __fmul_rn(k[3], f[j]);
+#pragma unroll
+                for (int t = 1; t < 7; t++) acc = __fadd_rn(acc, __fmul_rn(k[t < 3 ? 3 - t : t - 3], f[j + t]));
+            }
+            o[j] = acc;
         }
-        row_s[r][c] = acc;
+        *reinterpret_cast<float4*>(&row_s[r][4 * g]) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
     // column filter: s = k3*R[0]; s += k[3+j]*(R[+j] + R[-j]) (SymmColumnFilter, filter.simd.hpp:2697-2790), cvRound
-    for (int i = tid; i < BTH * (BTW / 4); i += 256) {
-        const int r = i / (BTW / 4), c4 = (i - r * (BTW / 4)) * 4;
-        const int y = y0 + r;
-        if (y >= h) continue;
-        uint32_t packed = 0;
+    {
+        const int g = tid & 31, strip = tid >> 5;              // 32 column groups x 8 strips of 8 rows
+        const int x = x0 + 4 * g;
+        float4 win[7];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = c4 + j;
-            float acc = FMA ? __fmaf_rn(k[0], row_s[r + 3][c], 0.f) : __fmul_rn(k[0], row_s[r + 3][c]);
+        for (int r = 0; r < 6; r++) win[r] = *reinterpret_cast<const float4*>(&row_s[8 * strip + r][4 * g]);
 #pragma unroll
-            for (int d = 1; d <= 3; d++) {
-                const float ab = __fadd_rn(row_s[r + 3 + d][c], row_s[r + 3 - d][c]);
-                acc = FMA ? __fmaf_rn(k[d], ab, acc) : __fadd_rn(acc, __fmul_rn(k[d], ab));
+        for (int i = 0; i < 8; i++) {
+            win[(i + 6) % 7] = *reinterpret_cast<const float4*>(&row_s[8 * strip + i + 6][4 * g]);
+            const int y = y0 + 8 * strip + i;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#define WV(d) (reinterpret_cast<const float*>(&win[(i + 3 + (d)) % 7])[j])
+                float acc = FMA ? __fmaf_rn(k[0], WV(0), 0.f) : __fmul_rn(k[0], WV(0));
+#pragma unroll
+                for (int d = 1; d <= 3; d++) {
+                    const float ab = __fadd_rn(WV(d), WV(-d));
+                    acc = FMA ? __fmaf_rn(k[d], ab, acc) : __fadd_rn(acc, __fmul_rn(k[d], ab));
+                }
+#undef WV
+                int v = __float2int_rn(acc);
+                v = max(0, min(255, v));
+                packed |= (uint32_t)v << (8 * j);
             }
-            int v = __float2int_rn(acc);
-            v = max(0, min(255, v));
-            packed |= (uint32_t)v << (8 * j);
+            if (y < h && x < w) {
+                uint8_t* d = dst + fo + (size_t)y * w + x;
+                if (x + 3 < w && ((w & 3) == 0)) *reinterpret_cast<uint32_t*>(d) = packed;
+                else
+                    for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(packed >> (8 * j));
+            }
         }
-        const int x = x0 + c4;
-        uint8_t* d = dst + fo + (size_t)y * w + x;
-        if (x + 3 < w && ((w & 3) == 0)) *reinterpret_cast<uint32_t*>(d) = packed;
-        else
-            for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(packed >> (8 * j));
     }
 }
 

@@ -131,3 +131,26 @@ def test_solve_dense_schur_tensor_cores(gpu_ctx, oracle):
         assert np.allclose(gp[i], wp, rtol=1e-4, atol=1e-9) and np.allclose(gd[i], wd, rtol=1e-4, atol=1e-9)
         assert np.abs(gp[i] - wp).max() < 1e-7
     assert L.alva_set_option(b"no_such_option", 1) == -1
+
+
+def test_solve_duplicate_pose_falls_back(gpu_ctx, oracle):
+    """A landmark observed twice from the same keyframe (two slots on one pose) is outside what the gather-form Schur
+    assembles; the solver must detect it and take the atomic path -- same answer as the oracle."""
+    pb = synth.make_ba_problem(8, 200, 3, seed=11)
+    # duplicate the first residual observation of 20 landmarks (keeping observations grouped by landmark)
+    order = []
+    for o in range(len(pb["obs_lm"])):
+        order.append(o)
+        l = pb["obs_lm"][o]
+        if l < 20 and (o == 0 or pb["obs_lm"][o - 1] != l):
+            order.append(o)
+    order = np.array(order)
+    pb["obs_lm"], pb["obs_kf"] = pb["obs_lm"][order], pb["obs_kf"][order]
+    uv = pb["obs_uv"][order].copy()
+    dup = np.r_[False, order[1:] == order[:-1]]
+    uv[dup] += 0.3
+    pb["obs_uv"] = np.ascontiguousarray(uv)
+    wp, wd, ws = oracle_solve(oracle, pb)
+    gp, gd, gs = gpu_solve(gpu_ctx, [pb])
+    assert (gs[0, 2:5] == ws[2:5]).all(), (gs[0], ws)
+    assert np.allclose(gp[0], wp, rtol=1e-4, atol=1e-9) and np.allclose(gd[0], wd, rtol=1e-4, atol=1e-9)
