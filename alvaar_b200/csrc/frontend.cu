@@ -122,6 +122,70 @@ __device__ __forceinline__ int fast_strength2(const uint8_t* p) {
     return max(sb, sd);
 }
 
+// Candidate mask of one lane's 4-pixel column over 8 rows (bit 8j + i = pixel j, row i): 9 contiguous ring pixels differ
+// from the centre by more than t.  g0 points at the word of the lane's pixels in the first of the 14 gray rows involved.
+template <bool HI_THR>
+__device__ __forceinline__ uint32_t fast_candidates8(const uint32_t* g0, uint32_t K, const uint32_t* mul) {
+    // gray rows needed: centre rows r0 .. r0+7 with r0 = 8*warp + 3, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
+    uint32_t Lw[7], Mw[7], Rw[7];   // rolling 7-row window: slot (row % 7)
+    uint32_t mulreg[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) mulreg[i] = mul[i];
+#pragma unroll
+    for (int r = 0; r < 6; r++) { Lw[r] = g0[r * GPW - 1]; Mw[r] = g0[r * GPW]; Rw[r] = g0[r * GPW + 1]; }
+    uint32_t acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        {   // bring in window row i + 6
+            const int r = i + 6;
+            Lw[r % 7] = g0[r * GPW - 1]; Mw[r % 7] = g0[r * GPW]; Rw[r % 7] = g0[r * GPW + 1];
+        }
+        // window rows i .. i+6 <-> dy = -3 .. +3
+#define WL(dy) Lw[(i + 3 + (dy)) % 7]
+#define WM(dy) Mw[(i + 3 + (dy)) % 7]
+#define WR(dy) Rw[(i + 3 + (dy)) % 7]
+        uint32_t ring[16];
+        ring[0] = WM(3);
+        ring[1] = __byte_perm(WM(3), WR(3), 0x4321);
+        ring[15] = __byte_perm(WL(3), WM(3), 0x6543);
+        ring[2] = __byte_perm(WM(2), WR(2), 0x5432);
+        ring[14] = __byte_perm(WL(2), WM(2), 0x5432);
+        ring[3] = __byte_perm(WM(1), WR(1), 0x6543);
+        ring[13] = __byte_perm(WL(1), WM(1), 0x4321);
+        ring[4] = __byte_perm(WM(0), WR(0), 0x6543);
+        ring[12] = __byte_perm(WL(0), WM(0), 0x4321);
+        ring[5] = __byte_perm(WM(-1), WR(-1), 0x6543);
+        ring[11] = __byte_perm(WL(-1), WM(-1), 0x4321);
+        ring[6] = __byte_perm(WM(-2), WR(-2), 0x5432);
+        ring[10] = __byte_perm(WL(-2), WM(-2), 0x5432);
+        ring[7] = __byte_perm(WM(-3), WR(-3), 0x4321);
+        ring[8] = WM(-3);
+        ring[9] = __byte_perm(WL(-3), WM(-3), 0x6543);
+        const uint32_t c = WM(0);
+#undef WL
+#undef WM
+#undef WR
+        // flag (bit 7 of byte j) -> bit 8j + i of the packed word: hi32(U * 2^(25+i)) == U >> (7 - i).  mad.hi keeps the
+        // shift-and-accumulate on the FMA pipe (a plain shift would be strength-reduced onto the saturated ALU pipe);
+        // row 7 needs no shift at all.
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t U = absdiff_gt<HI_THR>(ring[k], c, K);
+            if (i < 7) asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(U), "r"(mulreg[i]));
+            else acc[k] += U;
+        }
+    }
+    uint32_t T[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = acc[k] & acc[(k + 1) & 15] & acc[(k + 2) & 15];
+    uint32_t cand = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) cand |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+    return cand;
+}
+
 template <bool RGBA>
 __global__ void __launch_bounds__(NTHREADS, 3)
 frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
@@ -300,64 +364,9 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         }
         int qn = 0;
         if (__any_sync(0xffffffffu, vm != 0)) {
-            // gray rows needed: centre rows r0 .. r0+7 with r0 = 8*warp + 3, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
+            // gray rows needed: centre rows 8*warp+3 .. 8*warp+10, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
             const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
-            uint32_t Lw[7], Mw[7], Rw[7];   // rolling 7-row window: slot (row % 7)
-            uint32_t mulreg[7];
-#pragma unroll
-            for (int i = 0; i < 7; i++) mulreg[i] = P.mul[i];
-#pragma unroll
-            for (int r = 0; r < 6; r++) { Lw[r] = g0[r * GPW - 1]; Mw[r] = g0[r * GPW]; Rw[r] = g0[r * GPW + 1]; }
-            uint32_t acc[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) acc[k] = 0u;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                {   // bring in window row i + 6
-                    const int r = i + 6;
-                    Lw[r % 7] = g0[r * GPW - 1]; Mw[r % 7] = g0[r * GPW]; Rw[r % 7] = g0[r * GPW + 1];
-                }
-                // window rows i .. i+6 <-> dy = -3 .. +3
-#define WL(dy) Lw[(i + 3 + (dy)) % 7]
-#define WM(dy) Mw[(i + 3 + (dy)) % 7]
-#define WR(dy) Rw[(i + 3 + (dy)) % 7]
-                uint32_t ring[16];
-                ring[0] = WM(3);
-                ring[1] = __byte_perm(WM(3), WR(3), 0x4321);
-                ring[15] = __byte_perm(WL(3), WM(3), 0x6543);
-                ring[2] = __byte_perm(WM(2), WR(2), 0x5432);
-                ring[14] = __byte_perm(WL(2), WM(2), 0x5432);
-                ring[3] = __byte_perm(WM(1), WR(1), 0x6543);
-                ring[13] = __byte_perm(WL(1), WM(1), 0x4321);
-                ring[4] = __byte_perm(WM(0), WR(0), 0x6543);
-                ring[12] = __byte_perm(WL(0), WM(0), 0x4321);
-                ring[5] = __byte_perm(WM(-1), WR(-1), 0x6543);
-                ring[11] = __byte_perm(WL(-1), WM(-1), 0x4321);
-                ring[6] = __byte_perm(WM(-2), WR(-2), 0x5432);
-                ring[10] = __byte_perm(WL(-2), WM(-2), 0x5432);
-                ring[7] = __byte_perm(WM(-3), WR(-3), 0x4321);
-                ring[8] = WM(-3);
-                ring[9] = __byte_perm(WL(-3), WM(-3), 0x6543);
-                const uint32_t c = WM(0);
-#undef WL
-#undef WM
-#undef WR
-                // flag (bit 7 of byte j) -> bit 8j + i of the packed word: hi32(U * 2^(25+i)) == U >> (7 - i).  mad.hi keeps the
-                // shift-and-accumulate on the FMA pipe (a plain shift would be strength-reduced onto the saturated ALU pipe);
-                // row 7 needs no shift at all.
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const uint32_t U = hi_thr ? absdiff_gt<true>(ring[k], c, K) : absdiff_gt<false>(ring[k], c, K);
-                    if (i < 7) asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(U), "r"(mulreg[i]));
-                    else acc[k] += U;
-                }
-            }
-            uint32_t T[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) T[k] = acc[k] & acc[(k + 1) & 15] & acc[(k + 2) & 15];
-            uint32_t cand = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) cand |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+            uint32_t cand = hi_thr ? fast_candidates8<true>(g0, K, P.mul) : fast_candidates8<false>(g0, K, P.mul);
             cand &= vm;
             // ordered compaction of the candidate pixels into the warp queue (one prefix sum per 8 rows)
             const int mine = __popc(cand);

@@ -184,7 +184,14 @@ def bench_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(batch):
+def workload_config(batch, world=1, loop_closure=False):
+    cfg = _workload_config(batch)
+    cfg["parallelism"] = f"{world} independent camera-stream batch(es), one per GPU" + (
+        "; NCCL all-gather of keyframe descriptor blocks + cross-stream Hamming match per step" if loop_closure else "")
+    return cfg
+
+
+def _workload_config(batch):
     return {"workload": "c2_720p_stream+c4_local_ba", "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
             "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "7x7 blur + IC angle + rBRIEF-256, 1 level",
             "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
@@ -229,11 +236,33 @@ def bench_b200(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # Optional cross-stream loop-closure exchange: every rank contributes the descriptor blocks of
+    # this step's keyframes (fixed shape [nprob, fcap, 32] + counts), NCCL all-gathers them over NVLink, and the newest
+    # local keyframe is matched (brute-force Hamming 2-NN) against every gathered block.  No reference behaviour to
+    # match (the reference is single-stream); validated as "gather == concatenation of the per-rank inputs".
+    lc = None
+    if dist is not None and not args.no_loop_closure:
+        from alvaar_b200 import dist as adist
+        kf_idx = torch.arange(0, BATCH, KF_INTERVAL, device=f"cuda:{local_rank}")[:pipe.nprob]
+        desc_all = pipe.buffer("desc", (BATCH, pipe.fcap, 32), torch.uint8)
+        cnt_all = pipe.buffer("selcounts", (BATCH,), torch.int32)
+        lc_out = torch.zeros((pipe.fcap, 4), dtype=torch.int32, device=f"cuda:{local_rank}")
+
+        def lc():
+            kd = desc_all.index_select(0, kf_idx).contiguous()
+            kc = cnt_all.index_select(0, kf_idx).contiguous()
+            gd, gc = adist.gather_keyframe_descriptors(kd, kc)
+            q = kd[-1]
+            ctx.hamming_knn2(q, pipe.fcap, gd.reshape(-1, 32), gd.numel() // 32, lc_out)
+            return gd, gc
+
     sampler = ClockSampler(local_rank)
     pipe.profile(True)
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             pipe.step_dev(d_in)
+            if lc:
+                lc()
         barrier()
         l0 = ctx.launches
         sampler.start()
@@ -242,6 +271,8 @@ def bench_b200(args, rank, world, local_rank):
         ev0.record(stream)
         for _ in range(args.steps):
             pipe.step_dev(d_in)
+            if lc:
+                gathered = lc()
         ev1.record(stream)
         barrier()
         launches = ctx.launches - l0
@@ -297,7 +328,7 @@ def bench_b200(args, rank, world, local_rank):
     line = {"metric": "frames_per_sec_720p_1000orb_20kf_ba", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": workload_config(BATCH),
+            "config": workload_config(BATCH, world, lc is not None),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "alva_pipeline_step_host (pinned host RGBA in, counts+matches+BA poses out)"},
             "gpu_launches": int(launches),
@@ -322,6 +353,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -233,6 +233,66 @@ int ref_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
     return s.IsSolutionUsable() ? 1 : 0;
 }
 
+// Optimizer::localBA numerics, steps 2-4 (src/slam/src/optimizer.cpp:251-359): solve (Huber), drop the residuals whose
+// functor reports chi2err_ > chi2_thr or a non-positive depth AT ITS LAST EVALUATION, and -- only if something was
+// dropped -- solve again (<= 5 it) and flag once more.  flags[o]: 0 kept, 1 removed after the first solve, 2 flagged
+// after the second.  Wall-clock caps lifted.  summary[0..4] first solve, summary[5..9] second solve (zeros if skipped).
+int ref_ba_local(const double* calib, double* poses, const uint8_t* pose_const, int nkf,
+                 double* invd, const int32_t* anch_kf, const double* anch_uv, int nlm,
+                 const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, int nobs,
+                 double huber_delta, double chi2_thr, int max_iter, int32_t* flags, double* summary) {
+    ceres::Problem problem;
+    ceres::LossFunction* loss = huber_delta > 0 ? new ceres::HuberLoss(huber_delta) : nullptr;
+    auto* ordering = new ceres::ParameterBlockOrdering;
+    double K[4] = {calib[0], calib[1], calib[2], calib[3]};
+    problem.AddParameterBlock(K, 4);
+    ordering->AddElementToGroup(K, 1);
+    problem.SetParameterBlockConstant(K);
+    for (int i = 0; i < nkf; i++) {
+        problem.AddParameterBlock(poses + 7 * i, 7, new SE3Parameterization());
+        ordering->AddElementToGroup(poses + 7 * i, 1);
+        if (pose_const[i]) problem.SetParameterBlockConstant(poses + 7 * i);
+    }
+    for (int l = 0; l < nlm; l++) { problem.AddParameterBlock(invd + l, 1); ordering->AddElementToGroup(invd + l, 0); }
+    std::vector<DirectSE3::ReprojectionErrorKSE3AnchInvDepth*> fs(nobs, nullptr);
+    std::vector<ceres::ResidualBlockId> rids(nobs);
+    for (int o = 0; o < nobs; o++) {
+        flags[o] = 0;
+        int l = obs_lm[o];
+        if (l < 0) continue;
+        fs[o] = new DirectSE3::ReprojectionErrorKSE3AnchInvDepth(obs_uv[2 * o], obs_uv[2 * o + 1], anch_uv[2 * l], anch_uv[2 * l + 1], 1.);
+        rids[o] = problem.AddResidualBlock(fs[o], loss, K, poses + 7 * anch_kf[l], poses + 7 * obs_kf[o], invd + l);
+    }
+    ceres::Solver::Options options;
+    options.linear_solver_ordering.reset(ordering);
+    options.linear_solver_type = ceres::SPARSE_SCHUR;
+    options.trust_region_strategy_type = ceres::LEVENBERG_MARQUARDT;
+    options.num_threads = 1;
+    options.max_num_iterations = max_iter;
+    options.function_tolerance = 0.001;
+    options.max_solver_time_in_seconds = 1e9;
+    ceres::Solver::Summary s;
+    ceres::Solve(options, &problem, &s);
+    for (int i = 0; i < 10; i++) summary[i] = 0;
+    summary[0] = s.initial_cost; summary[1] = s.final_cost; summary[2] = s.num_successful_steps;
+    summary[3] = (double)s.iterations.size(); summary[4] = (double)s.termination_type;
+    int nbad = 0;
+    for (int o = 0; o < nobs; o++) {
+        if (!fs[o]) continue;
+        if (fs[o]->chi2err_ > chi2_thr || !fs[o]->isDepthPositive_) { problem.RemoveResidualBlock(rids[o]); fs[o] = nullptr; flags[o] = 1; nbad++; }
+    }
+    if (huber_delta > 0 && nbad > 0) {
+        options.max_num_iterations = 5;
+        ceres::Solver::Summary s2;
+        ceres::Solve(options, &problem, &s2);
+        summary[5] = s2.initial_cost; summary[6] = s2.final_cost; summary[7] = s2.num_successful_steps;
+        summary[8] = (double)s2.iterations.size(); summary[9] = (double)s2.termination_type;
+        for (int o = 0; o < nobs; o++)
+            if (fs[o] && (fs[o]->chi2err_ > chi2_thr || !fs[o]->isDepthPositive_)) flags[o] = 2;
+    }
+    return nbad;
+}
+
 // SE3Parameterization::Plus (src/slam/src/ceres_parametrization.hpp:224-240)
 void ref_se3_plus(const double* x, const double* delta, double* out) {
     SE3Parameterization p; p.Plus(x, delta, out);
