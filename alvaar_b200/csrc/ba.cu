@@ -37,7 +37,8 @@ struct BaState {
     double initial_cost, push_cost;
     int reuse_diagonal, invalid_steps, iteration, last_success, n_success, n_iter, term, done;
     int relin, step_ok, ncols, chol_ok;
-    int use_gather, nb, pad0, pad1;
+    int use_gather, nb, nbad, has_last;   // nbad / has_last: alva_k_ba_local (outliers removed, last evaluated point is cand)
+    int skipped, pad0;
 };
 
 // per-problem views into the workspace
@@ -70,10 +71,15 @@ struct BaProblem {
     uint32_t *plist;                        // gather Schur: (landmark << 8) | slot, every (landmark, slot) seeing that pose, by landmark
     int32_t *blk_start;                     // gather Schur: [NBMAX*NBMAX + 1] entry ranges per 6x6 block (bi <= bj), row-major
     uint32_t *pairs;                        // gather Schur: (landmark << 16) | (slot_u << 8) | slot_v per block, in plist order
+    // alva_k_ba_local only (null otherwise): obs_lm above then points at obs_lm_w, the working copy removals are made in
+    const int32_t* obs_lm_in;               // caller's obs_lm
+    int32_t* obs_lm_w;                      // [nobs]
+    int32_t* flags;                         // [nobs] out: 0 kept, 1 removed after solve 1, 2 flagged after solve 2
+    double *last_poses, *last_invd;         // point of the cost functors' last evaluation (see ba_post_kernel)
     BaState* st;
 };
 
-struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; int nlm_pad; int ecap; int nbs; };
+struct BaDims { int nkf, nlm, nobs, nblk; double huber; int max_iter; int nlm_pad; int ecap; int nbs; int pass; };
 
 // ------------------------------------------------------------------------------------------ SE(3) helpers
 __device__ __forceinline__ void quat_to_R(const double* q, double* R) {   // q = (x,y,z,w), normalised here
@@ -208,6 +214,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem
     __shared__ int run[NBMAX + 1], pl_base[NBMAX + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = SETUP_THREADS;
+    if (D.pass == 1 && (P.st->nbad == 0 || !(D.huber > 0))) {
+        // second solve of localBA runs only if the first one lost residuals (optimizer.cpp:305): otherwise every kernel
+        // of this pass is a no-op for this problem
+        if (tid == 0) { P.st->done = 1; P.st->skipped = 1; P.st->use_gather = 0; P.st->has_last = 0; }
+        return;
+    }
     for (int k = tid; k < 256; k += NT) ref[k] = 0;
     for (int l = tid; l <= D.nlm; l += NT) P.lm_start[l] = 0;
     __syncthreads();
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem
         s.radius = 1e4; s.decrease_factor = 2.0; s.reuse_diagonal = 0; s.invalid_steps = 0; s.iteration = 0;
         s.last_success = 1; s.n_success = 0; s.n_iter = 0; s.term = 1; s.done = 0; s.relin = 1; s.step_ok = 0;
         s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
-        s.chol_ok = 1; s.use_gather = 0; s.nb = c / 6;
+        s.chol_ok = 1; s.use_gather = 0; s.nb = c / 6; s.has_last = 0; s.skipped = 0;
     }
     // exclusive scan of counts -> lm_start
     {
@@ -1080,6 +1092,13 @@ __global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restric
         }
         return;
     }
+    if (P.last_poses) {
+        // the candidate has been evaluated (cost-only pass): from here until the next valid step it is the point the
+        // reference's functors were evaluated at last, whether or not the step is accepted or a tolerance ends the solve
+        for (int i = tid; i < 7 * D.nkf; i += 256) P.last_poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += 256) P.last_invd[l] = P.cand_invd[l];
+        if (tid == 0) st.has_last = 1;
+    }
     double c = 0;
     for (int i = tid; i < D.nblk; i += 256) c += P.cost_part[i];
     const double cand_cost = block_sum<256>(c, red);
@@ -1161,6 +1180,44 @@ __global__ void ba_linearize_dump_kernel(const double* calib, const double* pose
     cost[o] = c;
 }
 
+// ------------------------------------------------------------------------------------------ localBA outlier handling
+// Optimizer::localBA (optimizer.cpp:273-299, 330-356): after a solve, a residual is an outlier if the functor's LAST
+// evaluation saw chi2 = |r|^2 (sigma = 1) above the threshold or a non-positive depth.
+__global__ void ba_local_init_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < D.nobs) { P.obs_lm_w[o] = P.obs_lm_in[o]; P.flags[o] = 0; }
+    if (o == 0) { P.st->nbad = 0; P.st->has_last = 0; P.st->skipped = 0; }
+}
+
+template <int MARK>
+__global__ void __launch_bounds__(LIN_THREADS) ba_flag_kernel(const BaProblem* __restrict__ probs, BaDims D, double chi2_thr) {
+    const BaProblem P = probs[blockIdx.y];
+    BaState& st = *P.st;
+    if (MARK == 2 && st.skipped) return;
+    const int o = blockIdx.x * LIN_THREADS + threadIdx.x;
+    const int l = o < D.nobs ? P.obs_lm_w[o] : -1;
+    if (l < 0) return;
+    const double* poses = st.has_last ? P.last_poses : P.poses;
+    const double* invd = st.has_last ? P.last_invd : P.invd;
+    double r[2];
+    const bool front = ba_evaluate(P.calib, poses + 7 * P.anch_kf[l], poses + 7 * P.obs_kf[o], invd[l], P.obs_uv[2 * o],
+                                   P.obs_uv[2 * o + 1], P.anch_uv[2 * l], P.anch_uv[2 * l + 1], r, nullptr, nullptr, nullptr);
+    if (r[0] * r[0] + r[1] * r[1] > chi2_thr || !front) {
+        P.flags[o] = MARK;
+        if (MARK == 1) { P.obs_lm_w[o] = -1; atomicAdd(&st.nbad, 1); }   // RemoveResidualBlock; integer count: order-independent
+    }
+}
+
+__global__ void ba_summary_local_kernel(const BaProblem* __restrict__ probs, double* __restrict__ summary, int second) {
+    const BaState& st = *probs[blockIdx.x].st;
+    if (threadIdx.x == 0) {
+        double* s = summary + 10 * blockIdx.x + 5 * second;
+        if (second && st.skipped) { s[0] = s[1] = s[2] = s[3] = s[4] = 0; return; }
+        s[0] = st.initial_cost; s[1] = st.x_cost; s[2] = st.n_success; s[3] = st.n_iter; s[4] = st.term;
+    }
+}
+
 __global__ void ba_summary_kernel(const BaProblem* __restrict__ probs, double* __restrict__ summary) {
     const BaState& st = *probs[blockIdx.x].st;
     if (threadIdx.x == 0) {
@@ -1197,17 +1254,17 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     return align_up(bytes, 256);
 }
 
-extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
-                               const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
-                               const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
-                               int max_iter, double* summary) {
-    if (!ctx || nprob < 1 || nkf < 1 || nkf > 256 || nlm < 1 || nobs < 1 || !calib || !poses || !pose_const || !invd ||
-        !anch_kf || !anch_uv || !obs_kf || !obs_lm || !obs_uv || max_iter < 0) {
-        alva_set_error("alva_k_ba_solve: bad argument (need 1 <= nkf <= 256)");
-        return ALVA_E_INVALID;
-    }
+// Table of per-problem pointers at the head of ctx->ba_ws.  It depends only on the argument pointers and dimensions, so
+// it is rebuilt (one synchronous copy) only when those change -- a steady-state solve enqueues kernels and nothing else.
+// local: alva_k_ba_local's extra buffers (working obs_lm, last evaluated point) and its flags output.
+static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                      const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                      const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, int32_t* flags,
+                      const BaProblem** dp_out, BaDims* D_out) {
+    const bool local = flags != nullptr;
     const int nblk = (nobs + LIN_THREADS - 1) / LIN_THREADS;
-    const size_t per = ba_ws_bytes(nkf, nlm, nobs, nblk);
+    const size_t per_local = align_up((size_t)nobs * 4, 8) + (7 * (size_t)nkf + (size_t)nlm) * sizeof(double);
+    const size_t per = align_up(ba_ws_bytes(nkf, nlm, nobs, nblk) + (local ? per_local : 0), 256);
     const size_t tab = align_up(sizeof(BaProblem) * nprob, 256);
     if (tab + per * nprob > ctx->ba_ws_bytes) {
         if (ctx->ba_ws) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->ba_ws)); ctx->ba_ws = nullptr; ctx->ba_ws_bytes = 0; }
@@ -1216,15 +1273,12 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         ctx->ba_table_key = 0;
     }
     uint8_t* ws = (uint8_t*)ctx->ba_ws;
-    // The (small) table of per-problem pointers lives at the head of the scratch block.  It only depends on the argument
-    // pointers and dimensions, so it is rebuilt (one synchronous copy) only when those change -- a steady-state solve
-    // enqueues kernels and nothing else.
     uint64_t key = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
     mix((uint64_t)(uintptr_t)ws); mix(nprob); mix(nkf); mix(nlm); mix(nobs); mix((uint64_t)g_ba_dense_schur);
     mix((uint64_t)(uintptr_t)calib); mix((uint64_t)(uintptr_t)poses); mix((uint64_t)(uintptr_t)pose_const); mix((uint64_t)(uintptr_t)invd);
     mix((uint64_t)(uintptr_t)anch_kf); mix((uint64_t)(uintptr_t)anch_uv); mix((uint64_t)(uintptr_t)obs_kf);
-    mix((uint64_t)(uintptr_t)obs_lm); mix((uint64_t)(uintptr_t)obs_uv);
+    mix((uint64_t)(uintptr_t)obs_lm); mix((uint64_t)(uintptr_t)obs_uv); mix((uint64_t)(uintptr_t)flags);
     if (key != ctx->ba_table_key) {
         std::string hostbuf(sizeof(BaProblem) * nprob, '\0');
         BaProblem* hp = reinterpret_cast<BaProblem*>(&hostbuf[0]);
@@ -1244,6 +1298,8 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
             P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
             P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
             P.mc_part = take((size_t)((nlm + BS_THREADS - 1) / BS_THREADS));
+            P.last_poses = local ? take(7 * (size_t)nkf) : nullptr;
+            P.last_invd = local ? take(nlm) : nullptr;
             uint8_t* b = reinterpret_cast<uint8_t*>(d);
             P.pose_col = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nkf * 4, 8);
             P.lm_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(nlm + 1) * 4, 8);
@@ -1254,20 +1310,33 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
             P.plist = reinterpret_cast<uint32_t*>(b); b += align_up(((size_t)nobs + (size_t)nlm) * 4, 8);
             P.blk_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8);
             P.pairs = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+            P.obs_lm_in = nullptr; P.obs_lm_w = nullptr; P.flags = nullptr;
+            if (local) {
+                P.obs_lm_in = P.obs_lm;
+                P.obs_lm_w = reinterpret_cast<int32_t*>(b); b += align_up((size_t)nobs * 4, 8);
+                P.obs_lm = P.obs_lm_w;
+                P.flags = flags + (size_t)nobs * p;
+            }
             P.st = reinterpret_cast<BaState*>(b);
         }
         ALVA_CUDA(cudaMemcpyAsync(ws, hp, sizeof(BaProblem) * nprob, cudaMemcpyHostToDevice, ctx->stream));
         ALVA_CUDA(cudaStreamSynchronize(ctx->stream));   // hostbuf is pageable: the copy must finish before it dies
         ctx->ba_table_key = key;
     }
-    const BaProblem* dp = reinterpret_cast<const BaProblem*>(ws);
-    BaDims D{nkf, nlm, nobs, nblk, huber_delta, max_iter, (nlm + 3) / 4 * 4, 8 * nobs + 2 * nlm, (nlm + BS_THREADS - 1) / BS_THREADS};
+    *dp_out = reinterpret_cast<const BaProblem*>(ws);
+    *D_out = BaDims{nkf, nlm, nobs, nblk, 0.0, 0, (nlm + 3) / 4 * 4, 8 * nobs + 2 * nlm, (nlm + BS_THREADS - 1) / BS_THREADS, 0};
+    return 0;
+}
+
+// One trust-region solve: structure, then max_iter x (linearise, reduce, factor, back-substitute, evaluate, decide).
+// Every decision is taken on the device (BaState), so the host only enqueues; kernels of a finished problem return at once.
+static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int nprob) {
     const bool dense = g_ba_dense_schur != 0;
     const size_t chol_smem = ((size_t)NMAX * (NMAX + 1) + NMAX) * sizeof(double);
     ALVA_CUDA(cudaFuncSetAttribute(ba_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     ba_setup_kernel<<<nprob, SETUP_THREADS, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
-    const dim3 lin_grid(nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
+    const dim3 lin_grid(D.nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
     if (!dense) {   // structure of the gather-form Schur complement, once per solve
         const dim3 pr_grid(NBMAX, nprob);
@@ -1276,14 +1345,14 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         ba_pairs_kernel<1><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
-    for (int it = 0; it <= max_iter; it++) {
+    for (int it = 0; it <= D.max_iter; it++) {
         ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_stats_kernel<<<stats_grid, BS_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_pre_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        if (it == max_iter) break;   // the last pass only finalises (iteration count reached)
+        if (it == D.max_iter) break;   // the last pass only finalises (iteration count reached)
         if (dense) {
             ba_schur_kernel<true><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
@@ -1306,10 +1375,68 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
         ba_post_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
+    return 0;
+}
+
+static bool ba_args_ok(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const void* calib, const void* poses,
+                       const void* pose_const, const void* invd, const void* anch_kf, const void* anch_uv, const void* obs_kf,
+                       const void* obs_lm, const void* obs_uv, int max_iter) {
+    return ctx && nprob >= 1 && nkf >= 1 && nkf <= 256 && nlm >= 1 && nobs >= 1 && calib && poses && pose_const && invd &&
+           anch_kf && anch_uv && obs_kf && obs_lm && obs_uv && max_iter >= 0;
+}
+
+extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                               const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                               const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
+                               int max_iter, double* summary) {
+    if (!ba_args_ok(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, max_iter)) {
+        alva_set_error("alva_k_ba_solve: bad argument (need 1 <= nkf <= 256)");
+        return ALVA_E_INVALID;
+    }
+    const BaProblem* dp;
+    BaDims D;
+    if (int e = ba_prepare(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv,
+                           nullptr, &dp, &D))
+        return e;
+    D.huber = huber_delta; D.max_iter = max_iter;
+    if (int e = ba_run_solve(ctx, dp, D, nprob)) return e;
     if (summary) {
         ba_summary_kernel<<<nprob, 32, 0, ctx->stream>>>(dp, summary);
         ALVA_LAUNCH_CHECK(ctx);
     }
+    return 0;
+}
+
+// Optimizer::localBA steps 2-4 (src/slam/src/optimizer.cpp:251-359) for nprob independent problems, all on the device:
+// solve (Huber, <= max_iter), remove the residuals whose last evaluation was an outlier, and -- per problem, only if it
+// lost residuals and the robust loss is on -- solve again (<= 5 iterations) and flag once more.
+extern "C" int alva_k_ba_local(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                               const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                               const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
+                               double chi2_thr, int max_iter, int32_t* flags, double* summary) {
+    if (!ba_args_ok(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, max_iter) ||
+        !flags) {
+        alva_set_error("alva_k_ba_local: bad argument (need 1 <= nkf <= 256, flags != NULL)");
+        return ALVA_E_INVALID;
+    }
+    const BaProblem* dp;
+    BaDims D;
+    if (int e = ba_prepare(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv,
+                           flags, &dp, &D))
+        return e;
+    D.huber = huber_delta; D.max_iter = max_iter;
+    const dim3 obs_grid(D.nblk, nprob);
+    ba_local_init_kernel<<<obs_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
+    ALVA_LAUNCH_CHECK(ctx);
+    if (int e = ba_run_solve(ctx, dp, D, nprob)) return e;
+    if (summary) { ba_summary_local_kernel<<<nprob, 32, 0, ctx->stream>>>(dp, summary, 0); ALVA_LAUNCH_CHECK(ctx); }
+    ba_flag_kernel<1><<<obs_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D, chi2_thr);
+    ALVA_LAUNCH_CHECK(ctx);
+    D.pass = 1; D.max_iter = 5;   // optimizer.cpp:309: the refinement is capped at 5 iterations
+    if (int e = ba_run_solve(ctx, dp, D, nprob)) return e;
+    ba_flag_kernel<2><<<obs_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D, chi2_thr);
+    ALVA_LAUNCH_CHECK(ctx);
+    if (summary) { ba_summary_local_kernel<<<nprob, 32, 0, ctx->stream>>>(dp, summary, 1); ALVA_LAUNCH_CHECK(ctx); }
     return 0;
 }
 

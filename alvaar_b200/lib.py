@@ -57,6 +57,8 @@ _OPTIONAL = {
     "alva_k_hamming_knn2": [_vp, _vp, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_ba_solve": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i32, _vp],
+    "alva_k_ba_local": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double,
+                        _i32, _vp, _vp],
     "alva_k_ba_linearize": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp],
 }
 
@@ -160,6 +162,13 @@ class Context:
         self._chk(self.L.alva_k_ba_solve(self.h, nprob, nkf, nlm, nobs, _ptr(calib), _ptr(poses), _ptr(pose_const), _ptr(invd),
                                          _ptr(anch_kf), _ptr(anch_uv), _ptr(obs_kf), _ptr(obs_lm), _ptr(obs_uv), huber,
                                          max_iter, _ptr(summary)))
+
+    def ba_local(self, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv,
+                 huber, chi2_thr, max_iter, flags, summary=None):
+        """Optimizer::localBA steps 2-4 (solve, remove outliers, conditional re-solve, flag) -- see alva_k_ba_local."""
+        self._chk(self.L.alva_k_ba_local(self.h, nprob, nkf, nlm, nobs, _ptr(calib), _ptr(poses), _ptr(pose_const), _ptr(invd),
+                                         _ptr(anch_kf), _ptr(anch_uv), _ptr(obs_kf), _ptr(obs_lm), _ptr(obs_uv), huber,
+                                         chi2_thr, max_iter, _ptr(flags), _ptr(summary)))
 
     def ba_linearize(self, nkf, nlm, nobs, calib, poses, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, huber, res, Ja, Jp,
                      Jd, cost):

@@ -124,6 +124,23 @@ int alva_k_ba_solve(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
                     const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta, int max_iter,
                     double* summary);
 
+/* The numerical body of Optimizer::localBA after problem assembly (src/slam/src/optimizer.cpp:251-359), batched like
+ * alva_k_ba_solve and entirely on the device (no host decision between the steps):
+ *   1. solve (as alva_k_ba_solve, <= max_iter iterations)                                 optimizer.cpp:251-271
+ *   2. an observation is an outlier if, at the point its cost functor was evaluated LAST (the last candidate the
+ *      minimiser evaluated, accepted or not), chi2 = |r|^2 > chi2_thr or the depth is not positive; outliers are removed
+ *      (flags = 1)                                                                        optimizer.cpp:273-299
+ *   3. per problem, only if it lost observations and huber_delta > 0: solve again, <= 5 iterations, same loss
+ *                                                                                         optimizer.cpp:305-327
+ *   4. flag (flags = 2, not removed) the observations that are outliers after that solve   optimizer.cpp:330-356
+ * obs_lm is not modified; flags [nprob][nobs] int32 (0 = inlier / unused slot); summary (optional) [nprob][10]:
+ * {initial cost, final cost, #successful, #iterations, termination} of solve 1, then of solve 2 (zeros if skipped).
+ * The reference's 1 ms wall-clock cap on step 3 (and 5 ms on step 1) is lifted, as everywhere in this library. */
+int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
+                    const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
+                    const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta, double chi2_thr,
+                    int max_iter, int32_t* flags, double* summary);
+
 /* Library-wide switches.  "ba_dense_schur" = 1: compute the -(E'F)'(E'E)^-1(E'F) part of the Schur complement as a dense
  * FP64 tensor-core SYRK (S -= Wt'Wt, DMMA) instead of per-landmark atomics (default 0). */
 int alva_set_option(const char* name, int value);

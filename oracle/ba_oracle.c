@@ -183,6 +183,7 @@ static double ba_cost_only(const ba_view* v, const double* poses, const double* 
     double cost = 0;
     for (int o = 0; o < v->nobs; o++) {
         int l = v->obs_lm[o];
+        if (l < 0) continue; /* removed residual block */
         double obs[4] = {v->obs_uv[2 * o], v->obs_uv[2 * o + 1], v->anch_uv[2 * l], v->anch_uv[2 * l + 1]}, r[2], s;
         orc_ba_evaluate(v->calib, poses + 7 * v->anch_kf[l], poses + 7 * v->obs_kf[o], invd[l], obs, r, 0, 0, 0, &s);
         double r0, r1;
@@ -199,6 +200,11 @@ static double ba_linearize(const ba_view* v, const double* poses, const double* 
     double cost = 0;
     for (int o = 0; o < v->nobs; o++) {
         int l = v->obs_lm[o];
+        if (l < 0) {
+            res[2 * o] = res[2 * o + 1] = Jd[2 * o] = Jd[2 * o + 1] = 0;
+            for (int i = 0; i < 12; i++) Ja[12 * o + i] = Jp[12 * o + i] = 0;
+            continue;
+        }
         double obs[4] = {v->obs_uv[2 * o], v->obs_uv[2 * o + 1], v->anch_uv[2 * l], v->anch_uv[2 * l + 1]}, s;
         orc_ba_evaluate(v->calib, poses + 7 * v->anch_kf[l], poses + 7 * v->obs_kf[o], invd[l], obs, res + 2 * o,
                         Ja + 12 * o, Jp + 12 * o, Jd + 2 * o, &s);
@@ -229,6 +235,7 @@ static void ba_colnorms(const ba_view* v, const double* Ja, const double* Jp, co
     memset(nf, 0, sizeof(double) * v->ncols_f);
     memset(ne, 0, sizeof(double) * v->nlm);
     for (int o = 0; o < v->nobs; o++) {
+        if (v->obs_lm[o] < 0) continue;
         int l = v->obs_lm[o], ca = v->pose_col[v->anch_kf[l]], cp = v->pose_col[v->obs_kf[o]];
         ne[l] += Jd[2 * o] * Jd[2 * o] + Jd[2 * o + 1] * Jd[2 * o + 1];
         for (int c = 0; c < 6; c++) {
@@ -253,6 +260,7 @@ static void ba_schur(const ba_view* v, const double* res, const double* Ja, cons
     for (int l = 0; l < v->nlm; l++) { ete[l] = D_e[l] * D_e[l]; etb[l] = 0; }
     for (int i = 0; i < n; i++) S[i * n + i] = D_f[i] * D_f[i];
     for (int o = 0; o < v->nobs; o++) {
+        if (v->obs_lm[o] < 0) continue;
         int l = v->obs_lm[o], ca = v->pose_col[v->anch_kf[l]], cp = v->pose_col[v->obs_kf[o]];
         double e[2] = {Jd[2 * o] * sc_e[l], Jd[2 * o + 1] * sc_e[l]};
         double F[2][12];
@@ -366,6 +374,7 @@ static void setup_view(ba_view* v, int* pose_col, int* lm_used)
     memset(lm_used, 0, sizeof(int) * v->nlm);
     for (int o = 0; o < v->nobs; o++) {
         int l = v->obs_lm[o];
+        if (l < 0) continue;
         lm_used[l] = 1;
         ref[v->anch_kf[l]] = 1;
         ref[v->obs_kf[o]] = 1;
@@ -410,9 +419,13 @@ int orc_ba_first_schur(const double* calib, const double* poses, const uint8_t* 
 
 /* Same contract as ref_ba_solve in oracle/ref_harness.cpp.  summary[0..4] = initial cost, final cost,
  * #successful steps, #iterations (including iteration 0), termination (0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE). */
-int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, int nkf, double* invd,
-                 const int32_t* anch_kf, const double* anch_uv, int nlm, const int32_t* obs_kf, const int32_t* obs_lm,
-                 const double* obs_uv, int nobs, double huber_delta, int max_iter, double* summary, double* iter_costs)
+/* last_p / last_d (optional): the point at which the cost functors were evaluated LAST -- the candidate of the last
+ * iteration that got as far as evaluating one (accepted or not), else the start point.  The reference reads chi2err_ /
+ * isDepthPositive_ out of the functors after Solve (optimizer.cpp:273-299), i.e. at exactly this point. */
+static int ba_solve_impl(const double* calib, double* poses, const uint8_t* pose_const, int nkf, double* invd,
+                         const int32_t* anch_kf, const double* anch_uv, int nlm, const int32_t* obs_kf,
+                         const int32_t* obs_lm, const double* obs_uv, int nobs, double huber_delta, int max_iter,
+                         double* summary, double* iter_costs, double* last_p, double* last_d)
 {
     ba_view v = {calib, nkf, nlm, nobs, pose_const, anch_kf, obs_kf, obs_lm, anch_uv, obs_uv, huber_delta, 0, 0, 0, 0};
     int* pose_col = (int*)malloc(sizeof(int) * nkf);
@@ -433,6 +446,7 @@ int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
     double radius = 1e4, decrease_factor = 2.0;
     int reuse_diagonal = 0, invalid_steps = 0;
     double x_cost = ba_linearize(&v, poses, invd, res, Ja, Jp, Jd);
+    if (last_p) { memcpy(last_p, poses, sizeof(double) * 7 * nkf); memcpy(last_d, invd, sizeof(double) * nlm); }
     ba_colnorms(&v, Ja, Jp, Jd, nf, ne);
     for (int i = 0; i < n; i++) scf[i] = 1.0 / (1.0 + sqrt(nf[i]));
     for (int l = 0; l < nlm; l++) sce[l] = 1.0 / (1.0 + sqrt(ne[l]));
@@ -448,6 +462,7 @@ int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
         memset(gf, 0, sizeof(double) * n);                                                                            \
         memset(ge, 0, sizeof(double) * nlm);                                                                          \
         for (int o = 0; o < nobs; o++) {                                                                              \
+            if (obs_lm[o] < 0) continue;                                                                              \
             int l = obs_lm[o], ca = pose_col[anch_kf[l]], cp = pose_col[obs_kf[o]];                                   \
             ge[l] += Jd[2 * o] * res[2 * o] + Jd[2 * o + 1] * res[2 * o + 1];                                         \
             for (int c = 0; c < 6; c++) {                                                                             \
@@ -497,6 +512,7 @@ int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
             /* step = -y ; model residuals = J_scaled * step */
             double acc = 0;
             for (int o = 0; o < nobs; o++) {
+                if (obs_lm[o] < 0) continue;
                 int l = obs_lm[o], ca = pose_col[anch_kf[l]], cp = pose_col[obs_kf[o]];
                 double m[2] = {Jd[2 * o] * sce[l] * -ye[l], Jd[2 * o + 1] * sce[l] * -ye[l]};
                 for (int c = 0; c < 6; c++) {
@@ -520,6 +536,7 @@ int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
         for (int l = 0; l < nlm; l++) de[l] = -ye[l] * sce[l];
         apply_step(&v, poses, invd, df, de, cand_p, cand_d);
         double cand_cost = ba_cost_only(&v, cand_p, cand_d);
+        if (last_p) { memcpy(last_p, cand_p, sizeof(double) * 7 * nkf); memcpy(last_d, cand_d, sizeof(double) * nlm); }
         /* ParameterToleranceReached / FunctionToleranceReached: return WITHOUT taking the step or pushing a summary */
         double step_norm = x_diff(&v, poses, invd, cand_p, cand_d, 0);
         if (step_norm <= 1e-8 * (xn + 1e-8)) { term = 0; break; }
@@ -560,4 +577,58 @@ int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, 
     free(diag_e); free(ete); free(etb); free(W); free(S); free(rhs); free(yf); free(ye); free(df); free(de); free(cand_p);
     free(cand_d); free(gf); free(ge); free(pose_col); free(lm_used);
     return term != 2;
+}
+
+int orc_ba_solve(const double* calib, double* poses, const uint8_t* pose_const, int nkf, double* invd,
+                 const int32_t* anch_kf, const double* anch_uv, int nlm, const int32_t* obs_kf, const int32_t* obs_lm,
+                 const double* obs_uv, int nobs, double huber_delta, int max_iter, double* summary, double* iter_costs)
+{
+    return ba_solve_impl(calib, poses, pose_const, nkf, invd, anch_kf, anch_uv, nlm, obs_kf, obs_lm, obs_uv, nobs,
+                         huber_delta, max_iter, summary, iter_costs, 0, 0);
+}
+
+/* chi2 = |r|^2 of the RAW residual (sigma = 1) and the depth sign, per observation, at (poses, invd):
+ * ReprojectionErrorKSE3AnchInvDepth::Evaluate's side outputs (ceres_parametrization.hpp:136-139). */
+static int ba_flag_outliers(const double* calib, const double* poses, const double* invd, const int32_t* anch_kf,
+                            const double* anch_uv, const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv,
+                            int nobs, double chi2_thr, int32_t* flags, int mark)
+{
+    int n = 0;
+    for (int o = 0; o < nobs; o++) {
+        int l = obs_lm[o];
+        if (l < 0) continue;
+        double obs[4] = {obs_uv[2 * o], obs_uv[2 * o + 1], anch_uv[2 * l], anch_uv[2 * l + 1]}, r[2], s;
+        int depth_pos = orc_ba_evaluate(calib, poses + 7 * anch_kf[l], poses + 7 * obs_kf[o], invd[l], obs, r, 0, 0, 0, &s);
+        if (s > chi2_thr || !depth_pos) { flags[o] = mark; n++; }
+    }
+    return n;
+}
+
+/* Optimizer::localBA steps 2-4 (optimizer.cpp:251-359): solve, drop the residuals flagged at the last evaluated point,
+ * and -- only if something was dropped (and the robust loss is on) -- solve again with <= 5 iterations and flag once
+ * more.  flags[o]: 0 kept, 1 removed after the first solve, 2 flagged after the second.  Returns #removed (pass 1).
+ * summary[0..4] / [5..9] as orc_ba_solve for the two solves (zeros when the second is skipped). */
+int orc_ba_local(const double* calib, double* poses, const uint8_t* pose_const, int nkf, double* invd,
+                 const int32_t* anch_kf, const double* anch_uv, int nlm, const int32_t* obs_kf, const int32_t* obs_lm,
+                 const double* obs_uv, int nobs, double huber_delta, double chi2_thr, int max_iter, int32_t* flags,
+                 double* summary)
+{
+    double* last_p = malloc(sizeof(double) * 7 * nkf);
+    double* last_d = malloc(sizeof(double) * nlm);
+    int32_t* lm = malloc(sizeof(int32_t) * nobs);
+    memcpy(lm, obs_lm, sizeof(int32_t) * nobs);
+    memset(flags, 0, sizeof(int32_t) * nobs);
+    for (int i = 0; i < 10; i++) summary[i] = 0;
+    ba_solve_impl(calib, poses, pose_const, nkf, invd, anch_kf, anch_uv, nlm, obs_kf, lm, obs_uv, nobs, huber_delta,
+                  max_iter, summary, 0, last_p, last_d);
+    int nbad = ba_flag_outliers(calib, last_p, last_d, anch_kf, anch_uv, obs_kf, lm, obs_uv, nobs, chi2_thr, flags, 1);
+    if (huber_delta > 0 && nbad > 0) {
+        for (int o = 0; o < nobs; o++)
+            if (flags[o]) lm[o] = -1;
+        ba_solve_impl(calib, poses, pose_const, nkf, invd, anch_kf, anch_uv, nlm, obs_kf, lm, obs_uv, nobs, huber_delta, 5,
+                      summary + 5, 0, last_p, last_d);
+        ba_flag_outliers(calib, last_p, last_d, anch_kf, anch_uv, obs_kf, lm, obs_uv, nobs, chi2_thr, flags, 2);
+    }
+    free(last_p); free(last_d); free(lm);
+    return nbad;
 }

@@ -83,3 +83,52 @@ def test_solve_golden(oracle):
     assert np.allclose(summary[:2], g["summary"][:2], rtol=1e-9)
     assert np.allclose(poses, g["poses_out"], rtol=1e-4, atol=1e-9)
     assert np.allclose(invd, g["invd_out"], rtol=1e-4, atol=1e-9)
+
+
+def local_with(L, prefix, pb, max_iter=5, thr=5.9915):
+    poses, invd = pb["poses"].copy(), pb["invd"].copy()
+    summary, flags = np.zeros(10), np.zeros(len(pb["obs_kf"]), np.int32)
+    fn = getattr(L, prefix + "_ba_local")
+    fn.restype = C.c_int
+    nbad = fn(P(pb["calib"]), P(poses), P(pb["pose_const"]), len(poses), P(invd), P(pb["anch_kf"]), P(pb["anch_uv"]), len(invd),
+              P(pb["obs_kf"]), P(pb["obs_lm"]), P(pb["obs_uv"]), len(pb["obs_kf"]), C.c_double(pb["huber"]), C.c_double(thr),
+              max_iter, P(flags), P(summary))
+    return nbad, poses, invd, flags, summary
+
+
+@pytest.mark.parametrize("nkf,nlm,k,seed", [(20, 3000, 4, 42), (8, 300, 3, 7), (12, 800, 5, 3), (10, 400, 3, 11)])
+def test_local_ba_vs_ceres(oracle, ref, nkf, nlm, k, seed):
+    """Optimizer::localBA steps 2-4 (solve, drop chi2 / negative-depth outliers at the functors' last evaluation,
+    conditional second solve, second flagging): identical outlier sets and iteration counts, solution to 1e-12."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libalva_ref.so not built here")
+    pb = synth.make_ba_problem(nkf, nlm, k, seed=seed)
+    ra, pa, da, fa, sa = local_with(ref, "ref", pb)
+    rb, pb_, db, fb, sb = local_with(oracle, "orc", pb)
+    assert ra == rb and ra > 0 and (fa == fb).all()
+    assert (sa[[2, 3, 4, 7, 8, 9]] == sb[[2, 3, 4, 7, 8, 9]]).all()
+    assert np.allclose(sa, sb, rtol=1e-9)
+    assert np.abs(pa - pb_).max() < 1e-11 and np.abs(da - db).max() < 1e-11
+
+
+def test_local_ba_no_outliers_skips_second_solve(oracle, ref):
+    """Without outliers the refinement must not run (optimizer.cpp:305): result == plain first solve."""
+    pb = synth.make_ba_problem(8, 300, 3, seed=7, outlier_frac=0.0, noise_px=0.2)
+    nb, p1, d1, f1, s1 = local_with(oracle, "orc", pb, thr=1e9)
+    ok, p0, d0, s0, _ = solve_with(oracle, "orc", pb)
+    assert nb == 0 and (f1 == 0).all() and (s1[5:] == 0).all()
+    assert (p1 == p0).all() and (d1 == d0).all()
+    if ref is not None:
+        nr, pr, dr, fr, sr = local_with(ref, "ref", pb, thr=1e9)
+        assert nr == 0 and np.abs(pr - p1).max() < 1e-11
+
+
+def test_local_ba_golden_ceres(oracle):
+    g = golden("ba_local")
+    pb = {k: np.ascontiguousarray(g[k]) for k in ("calib", "poses", "pose_const", "invd", "anch_kf", "anch_uv", "obs_kf",
+                                                   "obs_lm", "obs_uv")}
+    pb["huber"] = float(g["huber"])
+    nb, p, d, f, s = local_with(oracle, "orc", pb)
+    assert (f == g["flags"]).all() and nb == (g["flags"] == 1).sum() and (g["flags"] == 2).sum() >= 1
+    assert (s[[2, 3, 4, 7, 8, 9]] == g["summary"][[2, 3, 4, 7, 8, 9]]).all()
+    assert np.abs(p - g["poses_out"]).max() < 1e-11 and np.abs(d - g["invd_out"]).max() < 1e-11

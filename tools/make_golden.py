@@ -102,8 +102,25 @@ def main():
                    len(invd), P(pb["obs_kf"]), P(pb["obs_lm"]), P(pb["obs_uv"]), len(pb["obs_kf"]),
                    C.c_double(pb["huber"]), 5, P(summary), P(costs))
     np.savez_compressed(os.path.join(OUT, "ba.npz"), poses_out=poses, invd_out=invd, summary=summary, costs=costs, **pb)
+    golden_ba_local()
     print("golden vectors written to", OUT)
 
 
+def golden_ba_local():
+    """Optimizer::localBA steps 2-4 with Ceres itself (ref_ba_local): solve, remove outliers, re-solve, flag."""
+    pb = synth.make_ba_problem(12, 800, 5, seed=3)
+    poses, invd = pb["poses"].copy(), pb["invd"].copy()
+    summary, flags = np.zeros(10), np.zeros(len(pb["obs_kf"]), np.int32)
+    R.ref_ba_local.restype = C.c_int
+    nbad = R.ref_ba_local(P(pb["calib"]), P(poses), P(pb["pose_const"]), len(poses), P(invd), P(pb["anch_kf"]), P(pb["anch_uv"]),
+                          len(invd), P(pb["obs_kf"]), P(pb["obs_lm"]), P(pb["obs_uv"]), len(pb["obs_kf"]),
+                          C.c_double(pb["huber"]), C.c_double(5.9915), 5, P(flags), P(summary))
+    assert nbad == (flags == 1).sum() and nbad > 0
+    np.savez_compressed(os.path.join(OUT, "ba_local.npz"), poses_out=poses, invd_out=invd, summary=summary, flags=flags, **pb)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ba_local":
+        golden_ba_local()
+    else:
+        main()
