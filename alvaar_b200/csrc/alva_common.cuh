@@ -24,6 +24,8 @@ struct alva_ctx {
     uint64_t ba_table_key = 0;
     void* ba_ws = nullptr;          // BA workspace (own allocation: the table must survive other stages' scratch use)
     size_t ba_ws_bytes = 0;
+    void* det_ws = nullptr;         // alva_k_orb_detect's intermediate lists (own allocation, same reason)
+    size_t det_ws_bytes = 0;
 };
 
 void alva_set_error(const char* fmt, ...);

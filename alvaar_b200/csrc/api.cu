@@ -108,6 +108,7 @@ extern "C" void alva_ctx_destroy(alva_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->dev_stage) cudaFree(ctx->dev_stage);
     if (ctx->ba_ws) cudaFree(ctx->ba_ws);
+    if (ctx->det_ws) cudaFree(ctx->det_ws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

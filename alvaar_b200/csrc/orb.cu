@@ -11,6 +11,7 @@
 // The blur is order- and fusion-sensitive float arithmetic: every product and sum below is an explicit
 // __fmul_rn/__fadd_rn (or one __fmaf_rn in ALVA_ORB_FMA mode) so nvcc cannot re-associate or contract it.
 #include "alva_common.cuh"
+#include <algorithm>
 #include "../../include/alva_b200.h"
 #include <math.h>
 
@@ -230,6 +231,132 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
     }
 }
 
+// ---- HarrisResponses (features2d/src/orb.cpp:130-177): blockSize 7, k = 0.04; one warp per keypoint ----------------
+// Integer Sobel sums over the 7x7 block (exact), then the float formula in the reference's operation order.
+__global__ void __launch_bounds__(256) harris_kernel(const uint8_t* __restrict__ gray, int w, int h, const float* __restrict__ pts,
+                                                     const int32_t* __restrict__ npts_per_frame, int npts,
+                                                     float* __restrict__ resp) {
+    const int lane = threadIdx.x & 31, f = blockIdx.y;
+    const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kp >= npts) return;
+    const int n = npts_per_frame ? min(npts_per_frame[f], npts) : npts;
+    const size_t o = (size_t)f * npts + kp;
+    if (kp >= n) { if (lane == 0) resp[o] = 0.f; return; }
+    const int x0 = __float2int_rn(pts[2 * o]), y0 = __float2int_rn(pts[2 * o + 1]);
+    if (x0 < 4 || y0 < 4 || x0 >= w - 4 || y0 >= h - 4) { if (lane == 0) resp[o] = 0.f; return; }
+    const uint8_t* c = gray + (size_t)f * w * h + (size_t)y0 * w + x0;
+    int a = 0, b = 0, cc = 0;
+    for (int i = lane; i < 49; i += 32) {
+        const int dy = i / 7 - 3, dx = i % 7 - 3;
+        const uint8_t* p = c + dy * w + dx;
+        const int tl = p[-w - 1], tc = p[-w], tr = p[-w + 1], ml = p[-1], mr = p[1], bl = p[w - 1], bc = p[w], br = p[w + 1];
+        const int Ix = (mr - ml) * 2 + (tr - tl) + (br - bl);
+        const int Iy = (bc - tc) * 2 + (bl - tl) + (br - tr);
+        a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+        cc += __shfl_xor_sync(0xffffffffu, cc, off);
+    }
+    if (lane == 0) {
+        // scale = 1.f/((1 << 2) * blockSize * 255.f); scale_sq_sq = scale*scale*scale*scale (orb.cpp:145-146)
+        const float scale = __fdiv_rn(1.f, 7140.f);
+        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+        const float fa = (float)a, fb = (float)b, fc = (float)cc;
+        const float sum = __fadd_rn(fa, fb);
+        // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq   (orb.cpp:173-174)
+        const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
+        resp[o] = __fmul_rn(v, s4);
+    }
+}
+
+// ---- KeyPointsFilter::retainBest(n) on float responses (keypoint.cpp:69-90), one CTA per frame ----------------------
+// Radix-select the n-th largest response, keep every keypoint with response >= it, in input (row-major) order.
+// Writes (x, y, response, 0) rows + the (x, y) list the describe kernel reads.
+__device__ __forceinline__ uint32_t float_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(1024) retain_best_f32_kernel(const float* __restrict__ pts, const float* __restrict__ resp,
+                                                               const int32_t* __restrict__ counts, int cap, int n_keep,
+                                                               float* __restrict__ kp_out, float* __restrict__ pts_out,
+                                                               int32_t* __restrict__ out_counts, int out_cap) {
+    __shared__ int hist[256];
+    __shared__ uint32_t prefix_s, mask_s;
+    __shared__ int krem_s, wsum[32], base_s;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(counts[f], cap);
+    const float* r = resp + (size_t)f * cap;
+    float thr = -INFINITY;
+    if (n_keep >= 0 && n > n_keep) {
+        if (n_keep == 0) thr = INFINITY;
+        else {
+            if (tid == 0) { prefix_s = 0; mask_s = 0; krem_s = n_keep; }
+            for (int pass = 3; pass >= 0; pass--) {
+                for (int i = tid; i < 256; i += 1024) hist[i] = 0;
+                __syncthreads();
+                const uint32_t prefix = prefix_s, mask = mask_s;
+                for (int i = tid; i < n; i += 1024) {
+                    const uint32_t k = float_key(r[i]);
+                    if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0, k = krem_s, bsel = 0;
+                    for (int bkt = 255; bkt >= 0; bkt--) {
+                        if (acc + hist[bkt] >= k) { bsel = bkt; break; }
+                        acc += hist[bkt];
+                    }
+                    krem_s = k - acc;
+                    prefix_s = prefix | ((uint32_t)bsel << (8 * pass));
+                    mask_s = mask | (0xffu << (8 * pass));
+                }
+                __syncthreads();
+            }
+            const uint32_t k = prefix_s;
+            thr = __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+        }
+    }
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {   // ordered compaction
+        const int i = i0 + tid;
+        const bool keep = i < n && r[i] >= thr;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int wv = 0; wv < warp; wv++) off += wsum[wv];
+        const int pos = off + __popc(m & ((1u << lane) - 1));
+        if (keep && pos < out_cap) {
+            const size_t src = (size_t)f * cap + i, dst = (size_t)f * out_cap + pos;
+            const float x = pts[2 * src], y = pts[2 * src + 1];
+            kp_out[4 * dst] = x; kp_out[4 * dst + 1] = y; kp_out[4 * dst + 2] = r[i]; kp_out[4 * dst + 3] = 0.f;
+            pts_out[2 * dst] = x; pts_out[2 * dst + 1] = y;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int wv = 0; wv < 32; wv++) t += wsum[wv]; base_s += t; }
+        __syncthreads();
+    }
+    if (tid == 0) out_counts[f] = base_s;
+}
+
+__global__ void detect_finish_kernel(const float* __restrict__ angles, const int32_t* __restrict__ counts, int out_cap,
+                                     float* __restrict__ kp_out) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < min(counts[f], out_cap)) kp_out[4 * ((size_t)f * out_cap + i) + 3] = angles[(size_t)f * out_cap + i];
+}
+
+__global__ void keys_to_pts_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ counts, int cap,
+                                   float* __restrict__ pts) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(counts[f], cap)) return;
+    const uint32_t k = keys[(size_t)f * cap + i];
+    reinterpret_cast<float2*>(pts)[(size_t)f * cap + i] = make_float2((float)ALVA_KEY_X(k), (float)ALVA_KEY_Y(k));
+}
+
 }  // namespace
 
 extern "C" int alva_k_orb_blur(alva_ctx* ctx, const uint8_t* gray, uint8_t* blurred, int w, int h, int nframes, int flags) {
@@ -255,6 +382,66 @@ extern "C" int alva_k_orb_describe(alva_ctx* ctx, const uint8_t* gray, const uin
     dim3 grid((npts + 7) / 8, nframes);
     orb_describe_kernel<<<grid, 256, 0, ctx->stream>>>(gray, blurred, w, h, pts, npts_per_frame, npts, flags, desc, kept,
                                                        angles_out);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int alva_k_harris(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, const float* pts,
+                             const int32_t* npts_per_frame, int npts, float* resp) {
+    if (!ctx || !gray || !pts || !resp || w < 9 || h < 9 || nframes < 1 || npts < 1) {
+        alva_set_error("alva_k_harris: bad argument");
+        return ALVA_E_INVALID;
+    }
+    dim3 grid((npts + 7) / 8, nframes);
+    harris_kernel<<<grid, 256, 0, ctx->stream>>>(gray, w, h, pts, npts_per_frame, npts, resp);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ORB::detectAndCompute, nlevels = 1 (orb.cpp:970-1218 with computeKeyPoints :785-958): FAST(thr, nms) -> border 31 ->
+// retainBest(2n) by FAST score -> Harris -> retainBest(n) by Harris -> IC angle -> blur -> steered rBRIEF.
+// Composition of this library's own stage kernels; intermediate lists live in a context-owned workspace.
+extern "C" int alva_k_orb_detect(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, int nfeatures, int fast_thr,
+                                 int flags, float* kp_out, uint8_t* desc, int32_t* counts, int out_cap) {
+    if (!ctx || !gray || !kp_out || !desc || !counts || w < 64 || h < 64 || nframes < 1 || nfeatures < 1 || out_cap < 1) {
+        alva_set_error("alva_k_orb_detect: bad argument (need w, h >= 64)");
+        return ALVA_E_INVALID;
+    }
+    const int kcap = (int)std::min<size_t>(std::max<size_t>(8192, (size_t)w * h / 24), 1u << 20);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_keys = al((size_t)nframes * kcap * 4), b_pts = al((size_t)nframes * kcap * 8), b_resp = al((size_t)nframes * kcap * 4);
+    const size_t b_cnt = al((size_t)nframes * 4), b_img = al((size_t)nframes * w * h);
+    const size_t b_pts2 = al((size_t)nframes * out_cap * 8), b_ang = al((size_t)nframes * out_cap * 4), b_kept = al((size_t)nframes * out_cap);
+    const size_t need = 2 * b_keys + b_pts + b_resp + 2 * b_cnt + b_img + b_pts2 + b_ang + b_kept;
+    if (need > ctx->det_ws_bytes) {
+        if (ctx->det_ws) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->det_ws)); ctx->det_ws = nullptr; ctx->det_ws_bytes = 0; }
+        ALVA_CUDA(cudaMalloc(&ctx->det_ws, need));
+        ctx->det_ws_bytes = need;
+    }
+    uint8_t* b = (uint8_t*)ctx->det_ws;
+    uint32_t* keys0 = (uint32_t*)b; b += b_keys;
+    uint32_t* keys1 = (uint32_t*)b; b += b_keys;
+    float* pts1 = (float*)b; b += b_pts;
+    float* resp = (float*)b; b += b_resp;
+    int32_t* cnt0 = (int32_t*)b; b += b_cnt;
+    int32_t* cnt1 = (int32_t*)b; b += b_cnt;
+    uint8_t* blurred = b; b += b_img;
+    float* pts2 = (float*)b; b += b_pts2;
+    float* ang = (float*)b; b += b_ang;
+    uint8_t* kept = b;
+    if (int e = alva_k_fast9(ctx, gray, w, h, nframes, fast_thr, keys0, cnt0, kcap, 1)) return e;
+    if (int e = alva_k_retain_best(ctx, keys0, cnt0, kcap, nframes, w, h, 2 * nfeatures, 31, keys1, cnt1, kcap)) return e;
+    dim3 kgrid((kcap + 255) / 256, nframes);
+    keys_to_pts_kernel<<<kgrid, 256, 0, ctx->stream>>>(keys1, cnt1, kcap, pts1);
+    ALVA_LAUNCH_CHECK(ctx);
+    if (int e = alva_k_harris(ctx, gray, w, h, nframes, pts1, cnt1, kcap, resp)) return e;
+    retain_best_f32_kernel<<<nframes, 1024, 0, ctx->stream>>>(pts1, resp, cnt1, kcap, nfeatures, kp_out, pts2, counts, out_cap);
+    ALVA_LAUNCH_CHECK(ctx);
+    if (int e = alva_k_orb_blur(ctx, gray, blurred, w, h, nframes, flags)) return e;
+    if (int e = alva_k_orb_describe(ctx, gray, blurred, w, h, nframes, pts2, counts, out_cap, flags | ALVA_ORB_IC_ANGLE, desc, kept, ang))
+        return e;
+    dim3 fgrid((out_cap + 255) / 256, nframes);
+    detect_finish_kernel<<<fgrid, 256, 0, ctx->stream>>>(ang, counts, out_cap, kp_out);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
 }

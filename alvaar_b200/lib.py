@@ -56,6 +56,8 @@ _OPTIONAL = {
     "alva_k_orb_describe": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "alva_k_hamming_knn2": [_vp, _vp, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
+    "alva_k_harris": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "alva_k_orb_detect": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32],
     "alva_k_ba_solve": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i32, _vp],
     "alva_k_ba_local": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double,
                         _i32, _vp, _vp],
@@ -156,6 +158,14 @@ class Context:
 
     def hamming_knn2(self, q, nq, t, nt, out):
         self._chk(self.L.alva_k_hamming_knn2(self.h, _ptr(q), nq, _ptr(t), nt, _ptr(out)))
+
+    def harris(self, gray, w, h, nframes, pts, npts_per_frame, npts, resp):
+        self._chk(self.L.alva_k_harris(self.h, _ptr(gray), w, h, nframes, _ptr(pts), _ptr(npts_per_frame), npts, _ptr(resp)))
+
+    def orb_detect(self, gray, w, h, nframes, nfeatures, fast_thr, flags, kp_out, desc, counts, out_cap):
+        """ORB::detectAndCompute (nlevels 1, HARRIS_SCORE) -- see alva_k_orb_detect."""
+        self._chk(self.L.alva_k_orb_detect(self.h, _ptr(gray), w, h, nframes, nfeatures, fast_thr, flags, _ptr(kp_out),
+                                           _ptr(desc), _ptr(counts), out_cap))
 
     def ba_solve(self, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv,
                  huber, max_iter, summary=None):

@@ -99,6 +99,20 @@ int alva_k_orb_describe(alva_ctx*, const uint8_t* gray, const uint8_t* blurred, 
                         const float* pts, const int32_t* npts_per_frame, int npts, int flags,
                         uint8_t* desc, uint8_t* kept, float* angles_out);
 
+/* HarrisResponses (features2d/src/orb.cpp:130-177; blockSize 7, k 0.04) at the given points: resp [nframes][npts] float
+ * (0 for unused slots and for points closer than 4 px to the border).  pts / npts_per_frame as alva_k_orb_describe. */
+int alva_k_harris(alva_ctx*, const uint8_t* gray, int w, int h, int nframes, const float* pts,
+                  const int32_t* npts_per_frame, int npts, float* resp);
+
+/* ORB::detectAndCompute with nlevels = 1, HARRIS_SCORE, edgeThreshold = patchSize = 31 (orb.cpp:970-1218, computeKeyPoints
+ * :785-958): FAST(fast_thr, nms) -> border 31 -> retainBest(2*nfeatures) on the FAST score -> Harris -> retainBest(nfeatures)
+ * on the Harris response (ties kept, so counts can exceed nfeatures) -> IC angle -> blur -> steered rBRIEF.
+ * kp_out [nframes][out_cap][4] float = {x, y, Harris response, angle in degrees}; desc [nframes][out_cap][32];
+ * counts[f] = keypoints found (only the first out_cap are stored).  Order: row-major (y, x) -- the reference's order is
+ * whatever std::nth_element leaves, so compare as sets.  flags: ALVA_ORB_FMA selects the blur arithmetic. */
+int alva_k_orb_detect(alva_ctx*, const uint8_t* gray, int w, int h, int nframes, int nfeatures, int fast_thr, int flags,
+                      float* kp_out, uint8_t* desc, int32_t* counts, int out_cap);
+
 /* Brute-force Hamming 2-NN (BFMatcher(NORM_HAMMING).knnMatch(k=2), features2d/src/matchers.cpp:757;
  * tie rule core/src/batch_distance.cpp:235-248).  q: [nq][32], t: [nt][32] bytes;
  * out[4*i] = {idx0, dist0, idx1, dist1} (int32; -1 when nt < 2). */

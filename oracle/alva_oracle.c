@@ -442,3 +442,60 @@ int orc_retain_best_threshold(const int32_t* xys, int count, int n)
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB::detectAndCompute with nlevels = 1, HARRIS_SCORE, edgeThreshold = patchSize = 31
+ * (features2d/src/orb.cpp:970-1218; computeKeyPoints :785-958):
+ *   FAST(thr, nms) -> runByImageBorder(31) -> retainBest(2n) on the FAST score -> HarrisResponses ->
+ *   retainBest(n) on the Harris response -> ICAngles -> GaussianBlur -> steered rBRIEF.
+ * The reference's output order is whatever nth_element/partition leave; here: row-major (y, x).
+ * kp[4*i] = {x, y, response, angle}; returns the count (only the first cap are written).
+ * ---------------------------------------------------------------------------------------------- */
+static int cmp_float_desc(const void* a, const void* b)
+{
+    float x = *(const float*)a, y = *(const float*)b;
+    return (x < y) - (x > y);
+}
+
+int orc_orb_detect(const uint8_t* img, int w, int h, int nfeatures, int fast_thr, int fused, float* kp, uint8_t* desc,
+                   int cap)
+{
+    int cap0 = w * h / 8 + 16;
+    int32_t* xys = (int32_t*)malloc(sizeof(int32_t) * 3 * (size_t)cap0);
+    int n0 = orc_fast9(img, w, h, fast_thr, 1, xys, cap0);
+    /* border 31: Rect(31, 31, w-31, h-31).contains(pt) */
+    int n1 = 0;
+    if (!(h <= 62 || w <= 62))
+        for (int i = 0; i < n0; i++) {
+            int x = xys[3 * i], y = xys[3 * i + 1];
+            if (x >= 31 && x < w - 31 && y >= 31 && y < h - 31) { memmove(xys + 3 * n1, xys + 3 * i, 12); n1++; }
+        }
+    int thr = orc_retain_best_threshold(xys, n1, 2 * nfeatures);
+    int n2 = 0;
+    for (int i = 0; i < n1; i++)
+        if (xys[3 * i + 2] >= thr) { memmove(xys + 3 * n2, xys + 3 * i, 12); n2++; }
+    float* pts = (float*)malloc(sizeof(float) * 2 * (size_t)(n2 + 1));
+    float* hr = (float*)malloc(sizeof(float) * (size_t)(n2 + 1));
+    float* tmp = (float*)malloc(sizeof(float) * (size_t)(n2 + 1));
+    for (int i = 0; i < n2; i++) { pts[2 * i] = (float)xys[3 * i]; pts[2 * i + 1] = (float)xys[3 * i + 1]; }
+    orc_harris(img, w, h, pts, n2, hr);
+    float fthr = -INFINITY;
+    if (n2 > nfeatures) {
+        memcpy(tmp, hr, sizeof(float) * n2);
+        qsort(tmp, n2, sizeof(float), cmp_float_desc);
+        fthr = tmp[nfeatures - 1];
+    }
+    int n3 = 0;
+    for (int i = 0; i < n2; i++)
+        if (hr[i] >= fthr) { pts[2 * n3] = pts[2 * i]; pts[2 * n3 + 1] = pts[2 * i + 1]; hr[n3] = hr[i]; n3++; }
+    int nw = n3 < cap ? n3 : cap;
+    float* ang = (float*)malloc(sizeof(float) * (size_t)(n3 + 1));
+    uint8_t* blur = (uint8_t*)malloc((size_t)w * h);
+    uint8_t* keptv = (uint8_t*)malloc((size_t)n3 + 1);
+    orc_ic_angles(img, w, h, pts, n3, ang);
+    orc_orb_blur(img, w, h, fused, blur);
+    orc_orb_describe(blur, w, h, pts, ang, nw, desc, keptv);
+    for (int i = 0; i < nw; i++) { kp[4 * i] = pts[2 * i]; kp[4 * i + 1] = pts[2 * i + 1]; kp[4 * i + 2] = hr[i]; kp[4 * i + 3] = ang[i]; }
+    free(xys); free(pts); free(hr); free(tmp); free(ang); free(blur); free(keptv);
+    return n3;
+}

@@ -146,3 +146,52 @@ def test_knn2_self_match_property(gpu_ctx):
     gpu_ctx.hamming_knn2(d_t, 20000, d_t, 20000, out)
     o = out.cpu().numpy()
     assert (o[:, 0] == np.arange(20000)).all() and (o[:, 1] == 0).all() and (o[:, 3] > 0).all()
+
+
+@pytest.mark.parametrize("w,h,n", [(640, 480, 700), (130, 100, 40)])
+def test_harris_vs_oracle(gpu_ctx, oracle, w, h, n):
+    """HarrisResponses: integer block sums + float formula in the reference's order -> bit-identical floats."""
+    img = synth.crop(w, h, 31, 77)
+    rng = np.random.default_rng(w)
+    pts = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], -1).astype(np.float32)
+    want = np.zeros(n, np.float32)
+    oracle.orc_harris(P(img), w, h, P(pts), n, P(want))
+    out = torch.full((n,), -1.0, dtype=torch.float32, device=DEV)
+    gpu_ctx.harris(dev(img), w, h, 1, dev(pts), None, n, out)
+    assert (out.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all()
+    assert (want != 0).sum() > n // 2
+
+
+def gpu_detect(gpu_ctx, imgs, nfeat, thr, flags=0, cap=4096):
+    nf, h, w = imgs.shape
+    kp = torch.zeros((nf, cap, 4), dtype=torch.float32, device=DEV)
+    desc = torch.zeros((nf, cap, 32), dtype=torch.uint8, device=DEV)
+    cnt = torch.zeros(nf, dtype=torch.int32, device=DEV)
+    gpu_ctx.orb_detect(dev(imgs), w, h, nf, nfeat, thr, flags, kp, desc, cnt, cap)
+    torch.cuda.synchronize()
+    return kp.cpu().numpy(), desc.cpu().numpy(), cnt.cpu().numpy()
+
+
+def test_orb_detect_golden(gpu_ctx):
+    """alva_k_orb_detect == the reference's ORB::detectAndCompute keypoint set (x, y, Harris response, IC angle, rBRIEF)."""
+    g = golden("orb")
+    kp, d, c = gpu_detect(gpu_ctx, g["img"][None], 300, 20)
+    gk, gd = g["det_kp"], g["det_desc"]
+    o = np.lexsort((gk[:, 0], gk[:, 1]))
+    n = int(c[0])
+    assert n == len(gk)
+    assert (kp[0, :n].view(np.uint32) == np.ascontiguousarray(gk[o][:, :4]).view(np.uint32)).all()
+    assert (d[0, :n] == gd[o]).all()
+
+
+@pytest.mark.parametrize("w,h,nfeat,thr,fma", [(1280, 720, 1000, 20, 0), (640, 480, 500, 20, 1), (200, 150, 1000, 10, 0),
+                                               (320, 240, 0 + 1, 30, 0)])
+def test_orb_detect_vs_oracle(gpu_ctx, oracle, w, h, nfeat, thr, fma):
+    imgs = np.stack([synth.crop(w, h, 40 + 97 * f, 10 + 53 * f) for f in range(3)])
+    kp, d, c = gpu_detect(gpu_ctx, imgs, nfeat, thr, ORB_FMA if fma else 0)
+    for f in range(3):
+        wk, wd = np.zeros((4096, 4), np.float32), np.zeros((4096, 32), np.uint8)
+        n = oracle.orc_orb_detect(P(imgs[f]), w, h, nfeat, thr, fma, P(wk), P(wd), 4096)
+        assert n == c[f] and n >= min(nfeat, 1)
+        assert (kp[f, :n].view(np.uint32) == wk[:n].view(np.uint32)).all()
+        assert (d[f, :n] == wd[:n]).all()

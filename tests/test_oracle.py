@@ -154,3 +154,38 @@ def test_live_reference_orb(oracle, ref):
         ref.ref_orb_compute(P(img), w, h, P(pts), P(angles) if angles is not None else None, n, P(da), P(ka))
         oracle.orc_orb_describe(P(blur), w, h, P(pts), P(angles) if angles is not None else None, n, P(db), P(kb))
         assert (ka == kb).all() and (da[ka == 1] == db[ka == 1]).all()
+
+
+def _sorted_kp(kp, desc):
+    o = np.lexsort((kp[:, 0], kp[:, 1]))
+    return kp[o], desc[o]
+
+
+def test_orb_detect_composition_golden(oracle):
+    """orc_orb_detect (FAST -> border -> retainBest(2n) -> Harris -> retainBest(n) -> IC angle -> blur -> rBRIEF) equals the
+    reference's ORB::detectAndCompute keypoint SET bit for bit (x, y, response, angle, descriptor)."""
+    g = golden("orb")
+    img = np.ascontiguousarray(g["img"])
+    h, w = img.shape
+    kp, d = np.zeros((2000, 4), np.float32), np.zeros((2000, 32), np.uint8)
+    n = oracle.orc_orb_detect(P(img), w, h, 300, 20, 0, P(kp), P(d), 2000)
+    gk, gd = _sorted_kp(g["det_kp"], g["det_desc"])
+    assert n == len(gk)
+    assert (kp[:n].view(np.uint32) == np.ascontiguousarray(gk[:, :4]).view(np.uint32)).all()
+    assert (d[:n] == gd).all()
+
+
+@pytest.mark.parametrize("w,h,nfeat,thr", [(640, 480, 500, 20), (320, 240, 100, 30), (200, 150, 1000, 10)])
+def test_orb_detect_composition_vs_reference(oracle, ref, w, h, nfeat, thr):
+    if ref is None:
+        pytest.skip("oracle/_ref/libalva_ref.so not built here")
+    img = synth.crop(w, h, 100 + w, 50 + h // 2)
+    assert img.shape == (h, w)
+    kp, d = np.zeros((8000, 4), np.float32), np.zeros((8000, 32), np.uint8)
+    n = oracle.orc_orb_detect(P(img), w, h, nfeat, thr, 0, P(kp), P(d), 8000)
+    rk, rd = np.zeros((8000, 5), np.float32), np.zeros((8000, 32), np.uint8)
+    nr = ref.ref_orb_detect(P(img), w, h, nfeat, thr, P(rk), P(rd), 8000)
+    assert n == nr and n > 20
+    gk, gd = _sorted_kp(rk[:nr], rd[:nr])
+    assert (kp[:n].view(np.uint32) == np.ascontiguousarray(gk[:, :4]).view(np.uint32)).all()
+    assert (d[:n] == gd).all()
