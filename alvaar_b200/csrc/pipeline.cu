@@ -62,6 +62,12 @@ struct alva_pipeline {
     cudaEvent_t chunk_ev[NCHUNK] = {}, start_ev = nullptr;
     static constexpr int NEV = 64;      // ring of event pairs around the fused front-end launch
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
+    // local BA runs beside the per-frame stages on its own (high-priority) stream, as the reference architecture's mapper
+    // does beside the tracker: forked from / joined back into ctx->stream with events, so callers still see one stream
+    alva_ctx* ba_ctx = nullptr;
+    cudaStream_t ba_stream = nullptr;
+    cudaEvent_t ba_fork = nullptr, ba_join = nullptr;
+    bool ba_forked = false;
     bool profile = false;
     long long step_index = 0;
     std::vector<void*> allocs;
@@ -79,6 +85,10 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
     for (void* a : p->allocs) cudaFree(a);
+    if (p->ba_ctx) { alva_ctx_destroy(p->ba_ctx); p->ba_ctx = nullptr; }
+    if (p->ba_stream) { cudaStreamSynchronize(p->ba_stream); cudaStreamDestroy(p->ba_stream); }
+    if (p->ba_fork) cudaEventDestroy(p->ba_fork);
+    if (p->ba_join) cudaEventDestroy(p->ba_join);
     if (p->copy_stream) {
         cudaStreamSynchronize(p->copy_stream);
         cudaStreamDestroy(p->copy_stream);
@@ -122,6 +132,16 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
         PALLOC(ba_invd0, np * nlm * 8); PALLOC(ba_invd, np * nlm * 8); PALLOC(ba_anch_uv, np * nlm * 16);
         PALLOC(ba_obs_uv, np * nobs * 16); PALLOC(ba_summary, np * 8 * 8); PALLOC(ba_const, np * nkf);
         PALLOC(ba_anch_kf, np * nlm * 4); PALLOC(ba_obs_kf, np * nobs * 4); PALLOC(ba_obs_lm, np * nobs * 4);
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&p->ba_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ba_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ba_join, cudaEventDisableTiming) != cudaSuccess ||
+            !(p->ba_ctx = alva_ctx_create(ctx->device, (void*)p->ba_stream))) {
+            alva_set_error("alva_pipeline_create: BA stream setup failed");
+            alva_pipeline_destroy(p);
+            return nullptr;
+        }
     }
     for (int i = 0; i < alva_pipeline::NEV; i++)
         if (cudaEventCreate(&p->ev0[i]) != cudaSuccess || cudaEventCreate(&p->ev1[i]) != cudaSuccess) {
@@ -187,7 +207,9 @@ int alva_frontend_main_launch(alva_ctx* ctx, const uint8_t* rgba, int w, int h, 
                               uint32_t* keys, int32_t* counts, int cap);
 
 // Stages 1-4 on frames [f0, f0 + nf) of the batch (every buffer is frame-major, so a range is a pointer offset).
-static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, int nf, bool timed) {
+static int pipeline_ba_fork(alva_pipeline* p);
+
+static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, int nf, bool timed, bool fork_ba) {
     alva_ctx* ctx = p->ctx;
     const alva_pipeline_config& c = p->cfg;
     const int w = c.w, h = c.h;
@@ -203,6 +225,9 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
     if (timed && p->profile) ALVA_CUDA(cudaEventRecord(p->ev0[slot], st));
     if (int e = alva_frontend_main_launch(ctx, rgba_dev + F * w * h * 4, w, h, nf, l0, l1, c.fast_thr, keys, counts, p->kcap)) return e;
     if (timed && p->profile) { ALVA_CUDA(cudaEventRecord(p->ev1[slot], st)); p->step_index++; }
+    // the step's local BA starts here, beside everything below (after the front end so that the event pair above times
+    // that kernel alone)
+    if (fork_ba) if (int e = pipeline_ba_fork(p)) return e;
     if (int e = alva_k_pyrdown(ctx, l1, l2, p->w1, p->h1, nf)) return e;
     if (int e = alva_k_pyrdown(ctx, l2, l3, p->w2, p->h2, nf)) return e;
     // 2. retainBest(nfeatures) inside ORB's 31-px border, row-major
@@ -224,17 +249,41 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
     return 0;
 }
 
-// 5. local BA for this step's keyframes
-static int pipeline_ba(alva_pipeline* p) {
-    if (p->nprob <= 0) return 0;
+// 5. local BA for this step's keyframes.  Forked at the start of the step onto the BA stream (its inputs do not depend on
+// this step's frames), joined at the end: small dependent launches (1 CTA per problem in the factorisation) that would
+// otherwise leave most SMs idle overlap the wide per-frame kernels.
+extern int alva_g_ba_overlap;   // alva_set_option("pipeline_ba_overlap", 0): run BA after the frame stages instead (A/B measurement)
+
+static int pipeline_ba_launch(alva_pipeline* p) {
     const alva_pipeline_config& c = p->cfg;
-    cudaStream_t st = p->ctx->stream;
+    cudaStream_t st = p->ba_stream;
     const size_t np = p->nprob;
+    ALVA_CUDA(cudaEventRecord(p->ba_fork, p->ctx->stream));
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_fork, 0));
     ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
     ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
-    return alva_k_ba_solve(p->ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
-                           p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber, c.ba_max_iter,
-                           p->ba_summary);
+    const long long before = p->ba_ctx->launches;
+    const int e = alva_k_ba_solve(p->ba_ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
+                                  p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber, c.ba_max_iter,
+                                  p->ba_summary);
+    p->ctx->launches += p->ba_ctx->launches - before;   // one launch counter per pipeline (alva_ctx_launches)
+    p->ba_forked = true;
+    return e;
+}
+
+static int pipeline_ba_fork(alva_pipeline* p) {
+    if (p->nprob <= 0 || !alva_g_ba_overlap) return 0;
+    return pipeline_ba_launch(p);
+}
+
+static int pipeline_ba_join(alva_pipeline* p) {
+    if (p->nprob > 0 && !alva_g_ba_overlap && !p->ba_forked)
+        if (int e = pipeline_ba_launch(p)) return e;
+    if (!p->ba_forked) return 0;
+    p->ba_forked = false;
+    ALVA_CUDA(cudaEventRecord(p->ba_join, p->ba_stream));
+    ALVA_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ba_join, 0));
+    return 0;
 }
 
 static int pipeline_ready(alva_pipeline* p) {
@@ -246,8 +295,8 @@ static int pipeline_ready(alva_pipeline* p) {
 extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) {
     if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
     if (int e = pipeline_ready(p)) return e;
-    if (int e = pipeline_frames(p, rgba_dev, 0, p->cfg.batch, true)) return e;
-    return pipeline_ba(p);
+    if (int e = pipeline_frames(p, rgba_dev, 0, p->cfg.batch, true, true)) { pipeline_ba_join(p); return e; }
+    return pipeline_ba_join(p);
 }
 
 // Host-buffer step (the e2e leg): the batch is uploaded in chunks on a dedicated copy stream while the compute stream
@@ -281,9 +330,9 @@ extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_hos
         const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
         if (nf <= 0) break;
         ALVA_CUDA(cudaStreamWaitEvent(st, p->chunk_ev[i], 0));
-        if (int e = pipeline_frames(p, p->in_dev, f0, nf, false)) return e;
+        if (int e = pipeline_frames(p, p->in_dev, f0, nf, false, i == 0)) { pipeline_ba_join(p); return e; }
     }
-    if (int e = pipeline_ba(p)) return e;
+    if (int e = pipeline_ba_join(p)) return e;
     if (nfeat_host) ALVA_CUDA(cudaMemcpyAsync(nfeat_host, p->selcounts, sizeof(int32_t) * c.batch, cudaMemcpyDeviceToHost, st));
     if (matches_host && c.map_size > 0)
         ALVA_CUDA(cudaMemcpyAsync(matches_host, p->matches, (size_t)c.batch * p->fcap * 16, cudaMemcpyDeviceToHost, st));

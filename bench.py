@@ -195,7 +195,9 @@ def _workload_config(batch):
     return {"workload": "c2_720p_stream+c4_local_ba", "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
             "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "7x7 blur + IC angle + rBRIEF-256, 1 level",
             "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
-            "ba_every_n_frames": KF_INTERVAL, "l2_policy": "inputs (236 MB/step) larger than L2 (126 MB)",
+            "ba_every_n_frames": KF_INTERVAL,
+            "ba_schedule": "own high-priority stream, forked after the front end and joined at the end of the step",
+            "l2_policy": "inputs (236 MB/step) larger than L2 (126 MB)",
             "parallelism": "1 stream batch per GPU"}
 
 
@@ -217,6 +219,7 @@ def bench_b200(args, rank, world, local_rank):
     ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
     stream = torch.cuda.Stream()
     ctx = alvaar_b200.Context(local_rank, stream.cuda_stream)
+    ctx.L.alva_set_option(b"pipeline_ba_overlap", 0 if args.no_ba_overlap else 1)
     pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE,
                     map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
                     ba_max_iter=BA_ITERS, ba_huber=ba["huber"])
@@ -353,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba-overlap", action="store_true", help="run the local BA after the frame stages instead of beside them")
     ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
