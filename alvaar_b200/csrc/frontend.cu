@@ -49,9 +49,9 @@ struct FrontendParams {
 
 struct __align__(128) SmemLayout {
     uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode); after the gray pass it is reused for the per-warp queues
+                                   // (first NWARPS*QCAP*2 bytes) and the tile's keypoint list (KPCAP words after them)
     uint8_t gray[GP * BH];         // TMA destination (gray mode)
     uint8_t score[SP * SR];
-    uint32_t kplist[KPCAP];
     uint64_t bar;
     int kpcount;
     int kpbase;
@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t fast_candidates8(const uint32_t* g0, uint32_
 }
 
 template <bool RGBA>
-__global__ void __launch_bounds__(NTHREADS, 3)
+__global__ void __launch_bounds__(NTHREADS, 4)
 frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
     extern __shared__ uint8_t smem_raw[];
     // TMA destinations must be 128-byte aligned: align the dynamic window by hand (128 spare bytes are allocated)
@@ -345,6 +345,8 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     // ------------------------------------------------------------------ D. FAST candidates + exact score
     // warp w owns score rows 8w .. 8w+7 (image rows y0-1+8w ..); lane = 4-pixel group column (image x0-4+4*lane ..)
     uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;   // the RGBA staging buffer is idle from here on
+    uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + NWARPS * QCAP * 2);
+    static_assert(NWARPS * QCAP * 2 + KPCAP * 4 <= BW * BH * 4, "queues + keypoint list must fit the staging buffer");
     if (P.keys) {
         const int thr = P.thr;
         const bool hi_thr = thr >= 128;
@@ -445,7 +447,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
                     const int x = x0 + 4 * (gc - 1) + j;
                     const uint32_t sc = (Sv >> (8 * j)) & 0xff;
                     const int kp = atomicAdd(&S.kpcount, 1);
-                    if (kp < KPCAP) S.kplist[kp] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
+                    if (kp < KPCAP) kplist[kp] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
                 }
             }
         }
@@ -456,7 +458,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         const int base = S.kpbase;
         uint32_t* out = P.keys + (size_t)f * P.cap;
         for (int i = tid; i < n; i += NTHREADS)
-            if (base + i < P.cap) out[base + i] = S.kplist[i];
+            if (base + i < P.cap) out[base + i] = kplist[i];
     }
 }
 
