@@ -597,6 +597,62 @@ __global__ void __launch_bounds__(1024) retain_best_kernel(const uint32_t* __res
     if (tid == 0) out_counts[f] = cnt_s;
 }
 
+// ---- Scharr derivative image of a pyramid level (cv::buildOpticalFlowPyramid withDerivatives, lkpyramid.cpp:57-150) ----
+// HBM-bound streaming: W*H bytes in, 4*W*H out (int16 dx, dy interleaved).  A thread owns a 4-pixel column strip of
+// SCH_ROWS rows with a rolling 3-row window, so every input row is read once per strip (+2 halo rows) and every output
+// is one 128-bit store.  Reflect-101 in both directions, exactly as the reference picks its neighbour rows / columns.
+constexpr int SCH_ROWS = 8;
+__device__ __forceinline__ void scharr_load6(const uint8_t* __restrict__ row, int x, int w, bool fast, int v[6]) {
+    if (fast && x >= 4 && x + 8 <= w) {
+        const uint32_t L = __ldg(reinterpret_cast<const uint32_t*>(row + x - 4));
+        const uint32_t M = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        const uint32_t R = __ldg(reinterpret_cast<const uint32_t*>(row + x + 4));
+        v[0] = L >> 24; v[1] = M & 255; v[2] = (M >> 8) & 255; v[3] = (M >> 16) & 255; v[4] = M >> 24; v[5] = R & 255;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            int xx = x - 1 + c;
+            if (xx < 0) xx = w > 1 ? 1 : 0;                       // trow[-1] = trow[1]
+            else if (xx >= w) xx = (xx == w) ? (w > 1 ? w - 2 : 0) : w - 1;   // trow[w] = trow[w-2]; beyond: unused lanes
+            v[c] = __ldg(row + xx);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) scharr_kernel(const uint8_t* __restrict__ src, int16_t* __restrict__ dst, int w, int h) {
+    const int gx = blockIdx.x * 32 + threadIdx.x, x = 4 * gx;
+    const int ys = (blockIdx.y * 8 + threadIdx.y) * SCH_ROWS;
+    if (x >= w || ys >= h) return;
+    const uint8_t* img = src + (size_t)blockIdx.z * w * h;
+    int16_t* out = dst + (size_t)blockIdx.z * w * h * 2;
+    const bool fast = (w & 3) == 0 && ((uintptr_t)src & 3) == 0;
+    auto rrow = [&](int y) { return y < 0 ? (h > 1 ? 1 : 0) : (y >= h ? (h > 1 ? h - 2 : 0) : y); };
+    int a[6], b[6], c[6];
+    scharr_load6(img + (size_t)rrow(ys - 1) * w, x, w, fast, a);
+    scharr_load6(img + (size_t)rrow(ys) * w, x, w, fast, b);
+#pragma unroll
+    for (int i = 0; i < SCH_ROWS; i++) {
+        const int y = ys + i;
+        if (y >= h) break;
+        scharr_load6(img + (size_t)rrow(y + 1) * w, x, w, fast, c);
+        int t0[6], t1[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { t0[k] = (a[k] + c[k]) * 3 + b[k] * 10; t1[k] = c[k] - a[k]; }
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int dx = t0[k + 2] - t0[k];
+            const int dy = (t1[k] + t1[k + 2]) * 3 + t1[k + 1] * 10;
+            o[k] = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+        }
+        uint32_t* d = reinterpret_cast<uint32_t*>(out) + (size_t)y * w + x;
+        if (fast && ((uintptr_t)dst & 15) == 0) *reinterpret_cast<uint4*>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) d[k] = o[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { a[k] = b[k]; b[k] = c[k]; }
+    }
+}
+
 }  // namespace
 
 // =================================================================================== host launchers
@@ -674,6 +730,17 @@ extern "C" int alva_k_gray(alva_ctx* ctx, const uint8_t* rgba, uint8_t* gray, in
     const size_t npix = (size_t)w * h * nframes;
     const size_t nthr = (npix + 3) / 4;
     gray_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(rgba, gray, npix);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int alva_k_scharr(alva_ctx* ctx, const uint8_t* gray, int16_t* deriv, int w, int h, int nframes) {
+    if (!ctx || !gray || !deriv || w < 1 || h < 1 || nframes < 1 || ((uintptr_t)deriv & 3)) {
+        alva_set_error("alva_k_scharr: bad argument");
+        return ALVA_E_INVALID;
+    }
+    dim3 block(32, 8), grid(((w + 3) / 4 + 31) / 32, (h + 8 * SCH_ROWS - 1) / (8 * SCH_ROWS), nframes);
+    scharr_kernel<<<grid, block, 0, ctx->stream>>>(gray, deriv, w, h);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int QPW = 8;          // queries per warp
 constexpr int WPC = 8;          // warps per CTA
-constexpr int CHUNK = 1024;     // train descriptors per partial
+constexpr int MIN_CHUNK = 512;  // never split the train set finer than this
 constexpr uint32_t NONE = 0xffffffffu;
 
 __device__ __forceinline__ void top2_insert(uint32_t& k0, uint32_t& k1, uint32_t key) {
@@ -26,17 +26,89 @@ __device__ __forceinline__ void top2_insert(uint32_t& k0, uint32_t& k1, uint32_t
     }
 }
 
+__device__ __forceinline__ uint32_t xor2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("xor.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t csa_sum(uint32_t a, uint32_t b, uint32_t c) {     // a ^ b ^ c
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t csa_carry(uint32_t a, uint32_t b, uint32_t c) {   // majority(a, b, c)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// exact warp-wide top-2 of the 32 per-lane (best, second) key pairs with three REDUX (keys are unique: the index is in them)
+__device__ __forceinline__ void warp_top2(uint32_t k0, uint32_t k1, uint32_t& m0, uint32_t& m1) {
+    m0 = __reduce_min_sync(0xffffffffu, k0);
+    const uint32_t s = __reduce_min_sync(0xffffffffu, k0 == m0 ? NONE : k0);
+    m1 = min(s, __reduce_min_sync(0xffffffffu, k1));
+}
+
+// one train descriptor per lane against the warp's QPW queries
+template <bool TAIL>
+__device__ __forceinline__ void knn_step(const uint4 (&qa)[QPW], const uint4 (&qb)[QPW], uint32_t (&k0)[QPW], uint32_t (&k1)[QPW],
+                                         uint32_t (&tk)[QPW], const uint4* __restrict__ t, int j, int te, uint32_t mul22,
+                                         uint32_t mul23, uint32_t mul24) {
+    const bool valid = !TAIL || j < te;
+    const int jl = valid ? j : te - 1;
+    const uint4 a = __ldg(t + 2 * jl), b = __ldg(t + 2 * jl + 1);
+    uint32_t key[QPW];
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < QPW; i++) {
+        // 256-bit popcount with 4 POPC instead of 8: three carry-save adders (sum = a^b^c, carry = maj(a,b,c): one LOP3
+        // each) compress the eight xor words into ones / twos / fours planes:
+        //   d = popc(ones) + popc(w7) + 2 popc(twos) + 4 popc(fours).
+        // (opaque asm: left to itself the compiler re-associates the xors into the adders and ends up with ~21 LOP3
+        //  per distance instead of the 16 written here)
+        const uint32_t x0 = xor2(qa[i].x, a.x), x1 = xor2(qa[i].y, a.y), x2 = xor2(qa[i].z, a.z), x3 = xor2(qa[i].w, a.w);
+        const uint32_t x4 = xor2(qb[i].x, b.x), x5 = xor2(qb[i].y, b.y), x6 = xor2(qb[i].z, b.z), x7 = xor2(qb[i].w, b.w);
+        const uint32_t s1 = csa_sum(x0, x1, x2), c1 = csa_carry(x0, x1, x2);
+        const uint32_t s2 = csa_sum(x3, x4, x5), c2 = csa_carry(x3, x4, x5);
+        const uint32_t s3 = csa_sum(s1, s2, x6), c3 = csa_carry(s1, s2, x6);
+        const uint32_t s4 = csa_sum(c1, c2, c3), c4 = csa_carry(c1, c2, c3);
+        // key = (d << 22) + j, as a chain of multiply-adds
+        uint32_t k = (uint32_t)(__popc(s3) + __popc(x7)) * mul22 + (uint32_t)j;
+        k = (uint32_t)__popc(s4) * mul23 + k;
+        k = (uint32_t)__popc(c4) * mul24 + k;
+        key[i] = (TAIL && !valid) ? NONE : k;
+        hit |= key[i] < tk[i];
+    }
+    if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+        for (int i = 0; i < QPW; i++) {
+            if (__any_sync(0xffffffffu, key[i] < tk[i])) {
+                top2_insert(k0[i], k1[i], key[i]);
+                uint32_t m0;
+                warp_top2(k0[i], k1[i], m0, tk[i]);
+            }
+        }
+    }
+}
+
 // counts != nullptr: the queries are [nbatch][qcap] slots of which only the first counts[b] are live; warps that hold
 // no live query leave immediately (their partials are never read).
+//
+// Selection costs almost nothing: every warp keeps, per query, the key of the warp-wide SECOND best seen so far (tk).  A
+// candidate can only change the final answer if its key is below tk, so the common path per distance is one compare; the
+// rare path (about 2 ln N times per query) inserts into the lane's private pair and refreshes tk with three REDUX.
+// mul = {2^22, 2^23, 2^24} as run-time data: weights and key packing become IMADs on the FMA pipe instead of shifts /
+// LEAs on the ALU pipe, which the 16 LOP3 per distance already saturate.
 __global__ void __launch_bounds__(WPC * 32) knn2_partial_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
-                                                                int nt, uint2* __restrict__ partial, int nchunks,
-                                                                const int32_t* __restrict__ counts, int qcap) {
+                                                                int nt, uint2* __restrict__ partial, int nchunks, int chunk_len,
+                                                                const int32_t* __restrict__ counts, int qcap, uint32_t mul22,
+                                                                uint32_t mul23, uint32_t mul24) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = (blockIdx.x * WPC + warp) * QPW;
     if (q0 >= nq) return;
     if (counts) { const int b = q0 / qcap; if (q0 - b * qcap >= counts[b]) return; }
     const int chunk = blockIdx.y;
-    const int tb = chunk * CHUNK, te = min(nt, tb + CHUNK);
+    const int tb = chunk * chunk_len, te = min(nt, tb + chunk_len);
     uint4 qa[QPW], qb[QPW];
 #pragma unroll
     for (int i = 0; i < QPW; i++) {
@@ -44,38 +116,19 @@ __global__ void __launch_bounds__(WPC * 32) knn2_partial_kernel(const uint4* __r
         qa[i] = __ldg(q + 2 * qi);
         qb[i] = __ldg(q + 2 * qi + 1);
     }
-    uint32_t k0[QPW], k1[QPW];
+    uint32_t k0[QPW], k1[QPW], tk[QPW];
 #pragma unroll
-    for (int i = 0; i < QPW; i++) k0[i] = k1[i] = NONE;
-    for (int j = tb + lane; j < te; j += 32) {
-        const uint4 a = __ldg(t + 2 * j), b = __ldg(t + 2 * j + 1);
-#pragma unroll
-        for (int i = 0; i < QPW; i++) {
-            // 256-bit popcount with 4 POPC instead of 8: the POPC pipe (16 lanes/clk/SM) is the bound, the LOP3 pipe has
-            // slack, so three carry-save adders (sum = a^b^c, carry = maj(a,b,c): 2 LOP3 each) first compress the eight
-            // xor words into ones / twos / fours planes:  d = popc(ones) + popc(w7) + 2 popc(twos) + 4 popc(fours).
-            const uint32_t x0 = qa[i].x ^ a.x, x1 = qa[i].y ^ a.y, x2 = qa[i].z ^ a.z, x3 = qa[i].w ^ a.w;
-            const uint32_t x4 = qb[i].x ^ b.x, x5 = qb[i].y ^ b.y, x6 = qb[i].z ^ b.z, x7 = qb[i].w ^ b.w;
-            const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 | x1));
-            const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 | x4));
-            const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
-            const uint32_t s4 = c1 ^ c2 ^ c3, c4 = (c1 & c2) | (c3 & (c1 | c2));
-            const int d = __popc(s3) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
-            top2_insert(k0[i], k1[i], ((uint32_t)d << 22) | (uint32_t)j);
-        }
-    }
-    // warp-shuffle merge of the 32 per-lane (best, second) pairs
+    for (int i = 0; i < QPW; i++) k0[i] = k1[i] = tk[i] = NONE;
+    const int full_steps = (te - tb) >> 5;   // warp-uniform trip count (the rare path votes)
+    for (int sidx = 0; sidx < full_steps; sidx++)
+        knn_step<false>(qa, qb, k0, k1, tk, t, tb + 32 * sidx + lane, te, mul22, mul23, mul24);
+    if (tb + 32 * full_steps < te)   // ragged tail: lanes past the end contribute nothing
+        knn_step<true>(qa, qb, k0, k1, tk, t, tb + 32 * full_steps + lane, te, mul22, mul23, mul24);
 #pragma unroll
     for (int i = 0; i < QPW; i++) {
-        uint32_t a0 = k0[i], a1 = k1[i];
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            const uint32_t b0 = __shfl_xor_sync(0xffffffffu, a0, off), b1 = __shfl_xor_sync(0xffffffffu, a1, off);
-            const uint32_t lo = min(a0, b0), hi = max(a0, b0);
-            a1 = min(hi, min(a1, b1));
-            a0 = lo;
-        }
-        if (lane == 0 && q0 + i < nq) partial[(size_t)(q0 + i) * nchunks + chunk] = make_uint2(a0, a1);
+        uint32_t m0, m1;
+        warp_top2(k0[i], k1[i], m0, m1);
+        if (lane == 0 && q0 + i < nq) partial[(size_t)(q0 + i) * nchunks + chunk] = make_uint2(m0, m1);
     }
 }
 
@@ -101,17 +154,33 @@ __global__ void knn2_merge_kernel(const uint2* __restrict__ partial, int nq, int
 
 }  // namespace
 
+// Chunking of the train set: one chunk per CTA row.  Long chunks make the selection filter effective (its rare path runs
+// ~2 ln(chunk) times per query), so split only as far as needed to give the GPU a few waves of CTAs.
+static void knn_chunks(const alva_ctx* ctx, int nq, int nt, int* nchunks, int* chunk_len) {
+    const int ctas_q = (nq + QPW * WPC - 1) / (QPW * WPC);
+    const int target = 8 * ctx->num_sms;   // 2 resident CTAs per SM x 4 waves
+    int n = (target + ctas_q - 1) / ctas_q;
+    const int nmax = (nt + MIN_CHUNK - 1) / MIN_CHUNK;
+    if (n > nmax) n = nmax;
+    if (n < 1) n = 1;
+    int len = ((nt + n - 1) / n + 31) & ~31;
+    *nchunks = (nt + len - 1) / len;
+    *chunk_len = len;
+}
+
 extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) {
     if (!ctx || !q || !t || !out || nq < 1 || nt < 1 || nt >= (1 << 22) || ((uintptr_t)q & 15) || ((uintptr_t)t & 15) ||
         ((uintptr_t)out & 15)) {
         alva_set_error("alva_k_hamming_knn2: bad argument (need 16-byte aligned buffers, 1 <= nt < 2^22)");
         return ALVA_E_INVALID;
     }
-    const int nchunks = (nt + CHUNK - 1) / CHUNK;
+    int nchunks, chunk_len;
+    knn_chunks(ctx, nq, nt, &nchunks, &chunk_len);
     uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
     if (!partial) return ALVA_E_CUDA;
     dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
-    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, nullptr, 0);
+    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
+                                                            nullptr, 0, 1u << 22, 1u << 23, 1u << 24);
     ALVA_LAUNCH_CHECK(ctx);
     knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, nullptr, 0);
     ALVA_LAUNCH_CHECK(ctx);
@@ -126,11 +195,13 @@ extern "C" int alva_k_hamming_knn2_batch(alva_ctx* ctx, const uint8_t* q, const 
         return ALVA_E_INVALID;
     }
     const int nq = nbatch * qcap;
-    const int nchunks = (nt + CHUNK - 1) / CHUNK;
+    int nchunks, chunk_len;
+    knn_chunks(ctx, nq, nt, &nchunks, &chunk_len);
     uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
     if (!partial) return ALVA_E_CUDA;
     dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
-    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, counts, qcap);
+    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
+                                                            counts, qcap, 1u << 22, 1u << 23, 1u << 24);
     ALVA_LAUNCH_CHECK(ctx);
     knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
     ALVA_LAUNCH_CHECK(ctx);

@@ -68,6 +68,12 @@ int alva_k_gray(alva_ctx*, const uint8_t* rgba, uint8_t* gray, int w, int h, int
  * reference call site src/slam/src/visual_frontend.cpp:696 (opencv video/src/lkpyramid.cpp:726-822) */
 int alva_k_pyrdown(alva_ctx*, const uint8_t* src, uint8_t* dst, int w, int h, int nframes);
 
+/* Scharr derivative image of one pyramid level, as cv::buildOpticalFlowPyramid(withDerivatives = true) builds it for the KLT
+ * tracker (visual_frontend.cpp:696 -> video/src/lkpyramid.cpp:57-150, 800-808): deriv [nframes][h][w][2] int16 = (dx, dy),
+ * dx = [3 10 3]^T x [-1 0 1], dy = [-1 0 1]^T x [3 10 3], reflect-101 neighbours.  (The reference then pads the derivative
+ * image with a CONSTANT 0 border of the window size; that padding is a view concern of its Mat, not stored here.) */
+int alva_k_scharr(alva_ctx*, const uint8_t* gray, int16_t* deriv, int w, int h, int nframes);
+
 /* cv::FAST(gray, thr, nms=true, TYPE_9_16) on each frame (opencv features2d/src/fast.cpp:496).
  * keys[f*cap + i]: packed corner keys; counts[f] = true number found (may exceed cap: then only cap
  * are stored and the call returns ALVA_E_CAPACITY after completing).  sorted != 0: row-major order. */

@@ -499,3 +499,34 @@ int orc_orb_detect(const uint8_t* img, int w, int h, int nfeatures, int fast_thr
     free(xys); free(pts); free(hr); free(tmp); free(ang); free(blur); free(keptv);
     return n3;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Scharr derivative image of one pyramid level, as cv::buildOpticalFlowPyramid(withDerivatives = true)
+ * stores it (video/src/lkpyramid.cpp:57-150, ScharrDerivInvoker): with reflect-101 neighbours in both
+ * directions (row -1 -> row 1, column -1 -> column 1; a single row/column reflects onto itself),
+ *   t0 = 3 (s[y-1] + s[y+1]) + 10 s[y]      t1 = s[y+1] - s[y-1]                (vertical, per column)
+ *   dx = t0[x+1] - t0[x-1]                  dy = 3 (t1[x-1] + t1[x+1]) + 10 t1[x]
+ * out: int16 [h][w][2] = (dx, dy) interleaved.  |dx|, |dy| <= 16 * 255: no int16 wrap.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_scharr(const uint8_t* img, int w, int h, int16_t* out)
+{
+    int* t0 = (int*)malloc(sizeof(int) * (size_t)(w + 2));
+    int* t1 = (int*)malloc(sizeof(int) * (size_t)(w + 2));
+    for (int y = 0; y < h; y++) {
+        const uint8_t* r0 = img + (size_t)(y > 0 ? y - 1 : (h > 1 ? 1 : 0)) * w;
+        const uint8_t* r1 = img + (size_t)y * w;
+        const uint8_t* r2 = img + (size_t)(y < h - 1 ? y + 1 : (h > 1 ? h - 2 : 0)) * w;
+        for (int x = 0; x < w; x++) {
+            t0[x + 1] = (r0[x] + r2[x]) * 3 + r1[x] * 10;
+            t1[x + 1] = r2[x] - r0[x];
+        }
+        int x0 = w > 1 ? 1 : 0, x1 = w > 1 ? w - 2 : 0;
+        t0[0] = t0[x0 + 1]; t0[w + 1] = t0[x1 + 1];
+        t1[0] = t1[x0 + 1]; t1[w + 1] = t1[x1 + 1];
+        for (int x = 0; x < w; x++) {
+            out[((size_t)y * w + x) * 2] = (int16_t)(t0[x + 2] - t0[x]);
+            out[((size_t)y * w + x) * 2 + 1] = (int16_t)((t1[x + 2] + t1[x]) * 3 + t1[x + 1] * 10);
+        }
+    }
+    free(t0); free(t1);
+}

@@ -204,3 +204,28 @@ def test_retain_best(gpu_ctx, oracle):
         c = ocounts[f].item()
         got = unpack_keys(okeys[f, :c].cpu().numpy().view(np.uint32))
         assert c == len(want) >= 500 and (got == want).all()
+
+
+@pytest.mark.parametrize("w,h,n", [(1280, 720, 2), (640, 360, 1), (161, 91, 2), (45, 37, 3), (6, 5, 1), (1, 9, 1), (9, 1, 1),
+                                   (2, 2, 1)])
+def test_scharr_vs_oracle(gpu_ctx, oracle, w, h, n):
+    """Derivative image of buildOpticalFlowPyramid(withDerivatives): int16 (dx, dy), bit-exact, incl. odd widths
+    (byte path) and degenerate 1-pixel-wide / -high levels."""
+    imgs = np.stack([np.ascontiguousarray(synth.crop(max(w, 16), max(h, 16), 10 + 37 * f, 20 + 11 * f)[:h, :w]) for f in range(n)])
+    out = torch.full((n, h, w, 2), -7, dtype=torch.int16, device=DEV)
+    gpu_ctx.scharr(dev(imgs), out, w, h, n)
+    got = out.cpu().numpy()
+    for f in range(n):
+        want = np.zeros((h, w, 2), np.int16)
+        oracle.orc_scharr(P(np.ascontiguousarray(imgs[f])), w, h, P(want))
+        assert (got[f] == want).all()
+
+
+def test_scharr_golden(gpu_ctx):
+    g = golden("scharr")
+    for k in range(4):
+        lv = g[f"l{k}"]
+        h, w = lv.shape
+        out = torch.zeros((h, w, 2), dtype=torch.int16, device=DEV)
+        gpu_ctx.scharr(dev(lv), out, w, h, 1)
+        assert (out.cpu().numpy() == g[f"d{k}"]).all()

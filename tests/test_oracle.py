@@ -189,3 +189,27 @@ def test_orb_detect_composition_vs_reference(oracle, ref, w, h, nfeat, thr):
     gk, gd = _sorted_kp(rk[:nr], rd[:nr])
     assert (kp[:n].view(np.uint32) == np.ascontiguousarray(gk[:, :4]).view(np.uint32)).all()
     assert (d[:n] == gd).all()
+
+
+def test_scharr_golden(oracle):
+    """Derivative pyramid of buildOpticalFlowPyramid(withDerivatives): int16 (dx, dy) per level, bit-exact."""
+    g = golden("scharr")
+    for k in range(4):
+        lv = np.ascontiguousarray(g[f"l{k}"])
+        h, w = lv.shape
+        out = np.zeros((h, w, 2), np.int16)
+        oracle.orc_scharr(P(lv), w, h, P(out))
+        assert (out == g[f"d{k}"]).all()
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (33, 17), (7, 5), (1, 9), (9, 1), (2, 2)])
+def test_scharr_vs_reference(oracle, ref, w, h):
+    if ref is None:
+        pytest.skip("oracle/_ref/libalva_ref.so not built here")
+    img = np.ascontiguousarray(synth.crop(max(w, 16), max(h, 16), 40, 60)[:h, :w])
+    lv, dv = np.zeros((h, w), np.uint8), np.zeros((h, w, 2), np.int16)
+    LP, DP = (C.c_void_p * 4)(lv.ctypes.data, None, None, None), (C.c_void_p * 4)(dv.ctypes.data, None, None, None)
+    ref.ref_build_pyramid(P(img), w, h, 3, 0, LP, DP)
+    out = np.zeros((h, w, 2), np.int16)
+    oracle.orc_scharr(P(img), w, h, P(out))
+    assert (lv == img).all() and (out == dv).all()

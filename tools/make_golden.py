@@ -103,6 +103,7 @@ def main():
                    C.c_double(pb["huber"]), 5, P(summary), P(costs))
     np.savez_compressed(os.path.join(OUT, "ba.npz"), poses_out=poses, invd_out=invd, summary=summary, costs=costs, **pb)
     golden_ba_local()
+    golden_scharr()
     print("golden vectors written to", OUT)
 
 
@@ -119,8 +120,28 @@ def golden_ba_local():
     np.savez_compressed(os.path.join(OUT, "ba_local.npz"), poses_out=poses, invd_out=invd, summary=summary, flags=flags, **pb)
 
 
+def golden_scharr():
+    """Derivative pyramid of cv::buildOpticalFlowPyramid(win 9, maxLevel 3, withDerivatives = true)."""
+    w, h = 161, 91
+    img = synth.crop(w, h, 300, 200)
+    ws, hs = [w], [h]
+    for _ in range(3):
+        ws.append((ws[-1] + 1) // 2)
+        hs.append((hs[-1] + 1) // 2)
+    lv = [np.zeros((hs[k], ws[k]), np.uint8) for k in range(4)]
+    dv = [np.zeros((hs[k], ws[k], 2), np.int16) for k in range(4)]
+    LP = (C.c_void_p * 4)(*[a.ctypes.data for a in lv])
+    DP = (C.c_void_p * 4)(*[a.ctypes.data for a in dv])
+    got = R.ref_build_pyramid(P(img), w, h, 9, 3, LP, DP)
+    assert got == 3
+    np.savez_compressed(os.path.join(OUT, "scharr.npz"), img=img, **{f"l{k}": lv[k] for k in range(4)},
+                        **{f"d{k}": dv[k] for k in range(4)})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ba_local":
         golden_ba_local()
+    elif len(sys.argv) > 1 and sys.argv[1] == "scharr":
+        golden_scharr()
     else:
         main()
