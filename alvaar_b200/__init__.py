@@ -5,7 +5,7 @@ package is the thin ctypes binding the tests and ``bench.py`` use.  There is NO 
 works anywhere (so the symbol table can be checked), but creating a context without a B200 raises.
 """
 from .lib import (AlvaError, Context, lib, lib_path, key_x, key_y, key_score, unpack_keys,
-                  ORB_FMA, ORB_IC_ANGLE)
+                  ORB_FMA, ORB_IC_ANGLE, ORB_HARRIS)
 
 __all__ = ["AlvaError", "Context", "lib", "lib_path", "key_x", "key_y", "key_score", "unpack_keys",
-           "ORB_FMA", "ORB_IC_ANGLE"]
+           "ORB_FMA", "ORB_IC_ANGLE", "ORB_HARRIS"]

@@ -21,6 +21,7 @@
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace {
 
@@ -259,15 +260,30 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         const int g = lane;                                   // BW/4 == 32 groups per row: lane = group
         const int x = x0 + 4 * (g - 1);
         const bool colstore = l0 && g >= 1 && g <= 30 && x < w;
-        for (int by = warp; by < BH; by += NWARPS) {
-            const uint32_t v = gray4(src4[by * 32 + g]);
-            gw[by * GPW + 1 + g] = v;                         // image x0-4+4g at gray byte 4+4g
-            const int y = y0 + by - 4;
-            if (colstore && by >= 4 && by < 4 + TH && y < h) {
-                uint8_t* d = l0 + (size_t)y * w + x;
-                if (w4) *reinterpret_cast<uint32_t*>(d) = v;  // x % 4 == 0 and w % 4 == 0 -> aligned, in range
-                else
-                    for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(v >> (8 * j));
+        // warp `warp` converts box rows warp, warp + 8, ... (9 rounds, the last one only for rows < BH).  Fully unrolled with
+        // pointer increments: all loads of a warp are in flight together and the per-row index arithmetic disappears.
+        constexpr int ROUNDS = (BH + NWARPS - 1) / NWARPS;
+        const uint4* sp = src4 + warp * 32 + g;
+        uint32_t* gp = gw + warp * GPW + 1 + g;             // image x0-4+4g at gray byte 4+4g
+        uint4 px[ROUNDS];
+#pragma unroll
+        for (int it = 0; it < ROUNDS; it++)
+            if (it < ROUNDS - 1 || warp + NWARPS * it < BH) px[it] = sp[it * NWARPS * 32];
+        uint8_t* d = l0 ? l0 + (size_t)(y0 + warp - 4) * w + x : nullptr;
+        const size_t dstep = (size_t)NWARPS * w;
+#pragma unroll
+        for (int it = 0; it < ROUNDS; it++) {
+            const int by = warp + NWARPS * it;
+            if (it < ROUNDS - 1 || by < BH) {
+                const uint32_t v = gray4(px[it]);
+                gp[it * NWARPS * GPW] = v;
+                const int y = y0 + by - 4;
+                if (colstore && by >= 4 && by < 4 + TH && y < h) {
+                    uint8_t* dd = d + it * dstep;
+                    if (w4) *reinterpret_cast<uint32_t*>(dd) = v;  // x % 4 == 0 and w % 4 == 0 -> aligned, in range
+                    else
+                        for (int j = 0; j < 4 && x + j < w; j++) dd[j] = (uint8_t)(v >> (8 * j));
+                }
             }
         }
         // columns x0-8..x0-5 and x0+TW+4..x0+TW+7 are never written: only garbage lanes read them
@@ -424,12 +440,14 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         }
         __syncwarp();
         for (int q0 = 0; q0 < nitems; q0 += 32) {
+            uint32_t ok = 0, Sv = 0;
+            int rr = 0, gc = 0;
             if (q0 + lane < nitems) {
                 const int widx = Q[q0 + lane];
-                const int rr = widx / SPW, gc = widx - rr * SPW;
+                rr = widx / SPW; gc = widx - rr * SPW;
                 const uint32_t* s0 = Sw + widx;
-                const uint32_t Sv = s0[0];
-                uint32_t ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
+                Sv = s0[0];
+                ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
 #pragma unroll
                 for (int dy = -1; dy <= 1; dy++) {
                     const uint32_t L = s0[dy * SPW - 1], M = s0[dy * SPW], R = s0[dy * SPW + 1];
@@ -439,15 +457,28 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
                     if (dy != 0) ok &= ~swar_ge_raw(M, Sv);
                 }
                 ok &= ALVA_H;
-                const int y = y0 + rr - 1;
-                while (ok) {
-                    const int b = __ffs(ok) - 1;   // bit 8j + 7
-                    ok &= ok - 1;
-                    const int j = b >> 3;
-                    const int x = x0 + 4 * (gc - 1) + j;
-                    const uint32_t sc = (Sv >> (8 * j)) & 0xff;
-                    const int kp = atomicAdd(&S.kpcount, 1);
-                    if (kp < KPCAP) kplist[kp] = ((uint32_t)y << 20) | ((uint32_t)x << 8) | sc;
+            }
+            // Two horizontally adjacent pixels cannot both be strict maxima, so a 4-pixel word holds at most 2 keypoints:
+            // two ballots rank them and ONE shared atomic per warp round reserves the slots (per-keypoint atomics on the
+            // CTA counter serialised the whole CTA here).
+            const int c = __popc(ok);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, c >= 1), m2 = __ballot_sync(0xffffffffu, c >= 2);
+            const int n1 = __popc(m1), tot = n1 + __popc(m2);
+            if (tot) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.kpcount, tot);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t lt = (1u << lane) - 1u;
+                const uint32_t yx = ((uint32_t)(y0 + rr - 1) << 20) | ((uint32_t)(x0 + 4 * (gc - 1)) << 8);
+                if (c >= 1) {
+                    const int j = (__ffs(ok) - 1) >> 3;
+                    const int kp = base + __popc(m1 & lt);
+                    if (kp < KPCAP) kplist[kp] = yx + ((uint32_t)j << 8) + ((Sv >> (8 * j)) & 0xff);
+                }
+                if (c >= 2) {
+                    const int j = (31 - __clz(ok)) >> 3;
+                    const int kp = base + n1 + __popc(m2 & lt);
+                    if (kp < KPCAP) kplist[kp] = yx + ((uint32_t)j << 8) + ((Sv >> (8 * j)) & 0xff);
                 }
             }
         }
@@ -618,9 +649,21 @@ __device__ __forceinline__ void scharr_load6(const uint8_t* __restrict__ row, in
         }
     }
 }
-__global__ void __launch_bounds__(256) scharr_kernel(const uint8_t* __restrict__ src, int16_t* __restrict__ dst, int w, int h) {
+struct ScharrLevels {   // up to 4 pyramid levels in one launch: blockIdx.y runs through the levels' row blocks
+    const uint8_t* src[4];
+    int16_t* dst[4];
+    int w[4], h[4], yb0[5];   // yb0[k] = first blockIdx.y of level k, yb0[nlev] = gridDim.y
+    int nlev;
+};
+__global__ void __launch_bounds__(256) scharr_kernel(const ScharrLevels L) {
+    int lev = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < L.nlev && (int)blockIdx.y >= L.yb0[k]) lev = k;
+    const int w = L.w[lev], h = L.h[lev];
+    const uint8_t* src = L.src[lev];
+    int16_t* dst = L.dst[lev];
     const int gx = blockIdx.x * 32 + threadIdx.x, x = 4 * gx;
-    const int ys = (blockIdx.y * 8 + threadIdx.y) * SCH_ROWS;
+    const int ys = ((blockIdx.y - L.yb0[lev]) * 8 + threadIdx.y) * SCH_ROWS;
     if (x >= w || ys >= h) return;
     const uint8_t* img = src + (size_t)blockIdx.z * w * h;
     int16_t* out = dst + (size_t)blockIdx.z * w * h * 2;
@@ -734,15 +777,29 @@ extern "C" int alva_k_gray(alva_ctx* ctx, const uint8_t* rgba, uint8_t* gray, in
     return 0;
 }
 
+// internal (pipeline.cu): the derivative images of up to 4 levels in ONE launch (the small levels are launch-bound alone)
+int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src, int16_t* const* dst, const int* w, const int* h,
+                              int nframes) {
+    ScharrLevels L{};
+    L.nlev = nlev;
+    int yb = 0, gx = 1;
+    for (int k = 0; k < nlev; k++) {
+        L.src[k] = src[k]; L.dst[k] = dst[k]; L.w[k] = w[k]; L.h[k] = h[k]; L.yb0[k] = yb;
+        yb += (h[k] + 8 * SCH_ROWS - 1) / (8 * SCH_ROWS);
+        gx = std::max(gx, ((w[k] + 3) / 4 + 31) / 32);
+    }
+    for (int k = nlev; k < 5; k++) L.yb0[k] = yb;
+    scharr_kernel<<<dim3(gx, yb, nframes), dim3(32, 8), 0, ctx->stream>>>(L);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int alva_k_scharr(alva_ctx* ctx, const uint8_t* gray, int16_t* deriv, int w, int h, int nframes) {
     if (!ctx || !gray || !deriv || w < 1 || h < 1 || nframes < 1 || ((uintptr_t)deriv & 3)) {
         alva_set_error("alva_k_scharr: bad argument");
         return ALVA_E_INVALID;
     }
-    dim3 block(32, 8), grid(((w + 3) / 4 + 31) / 32, (h + 8 * SCH_ROWS - 1) / (8 * SCH_ROWS), nframes);
-    scharr_kernel<<<grid, block, 0, ctx->stream>>>(gray, deriv, w, h);
-    ALVA_LAUNCH_CHECK(ctx);
-    return 0;
+    return alva_scharr_levels_launch(ctx, 1, &gray, &deriv, &w, &h, nframes);
 }
 
 extern "C" int alva_k_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) {

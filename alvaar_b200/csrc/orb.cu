@@ -235,40 +235,46 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
 // Integer Sobel sums over the 7x7 block (exact), then the float formula in the reference's operation order.
 __global__ void __launch_bounds__(256) harris_kernel(const uint8_t* __restrict__ gray, int w, int h, const float* __restrict__ pts,
                                                      const int32_t* __restrict__ npts_per_frame, int npts,
-                                                     float* __restrict__ resp) {
+                                                     float* __restrict__ resp, int zero_dead) {
     const int lane = threadIdx.x & 31, f = blockIdx.y;
-    const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (kp >= npts) return;
     const int n = npts_per_frame ? min(npts_per_frame[f], npts) : npts;
-    const size_t o = (size_t)f * npts + kp;
-    if (kp >= n) { if (lane == 0) resp[o] = 0.f; return; }
-    const int x0 = __float2int_rn(pts[2 * o]), y0 = __float2int_rn(pts[2 * o + 1]);
-    if (x0 < 4 || y0 < 4 || x0 >= w - 4 || y0 >= h - 4) { if (lane == 0) resp[o] = 0.f; return; }
-    const uint8_t* c = gray + (size_t)f * w * h + (size_t)y0 * w + x0;
-    int a = 0, b = 0, cc = 0;
-    for (int i = lane; i < 49; i += 32) {
-        const int dy = i / 7 - 3, dx = i % 7 - 3;
-        const uint8_t* p = c + dy * w + dx;
-        const int tl = p[-w - 1], tc = p[-w], tr = p[-w + 1], ml = p[-1], mr = p[1], bl = p[w - 1], bc = p[w], br = p[w + 1];
-        const int Ix = (mr - ml) * 2 + (tr - tl) + (br - bl);
-        const int Iy = (bc - tc) * 2 + (bl - tl) + (br - tr);
-        a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
-    }
+    // grid-stride over the slots: the slot capacity can be far larger than the live count (pre-selection lists), and a
+    // grid sized by capacity would be launch-bound
+    for (int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); kp < npts; kp += gridDim.x * (blockDim.x >> 5)) {
+        const size_t o = (size_t)f * npts + kp;
+        if (kp >= n) {
+            if (zero_dead && lane == 0) resp[o] = 0.f;
+            if (!zero_dead) break;
+            continue;
+        }
+        const int x0 = __float2int_rn(pts[2 * o]), y0 = __float2int_rn(pts[2 * o + 1]);
+        if (x0 < 4 || y0 < 4 || x0 >= w - 4 || y0 >= h - 4) { if (lane == 0) resp[o] = 0.f; continue; }
+        const uint8_t* c = gray + (size_t)f * w * h + (size_t)y0 * w + x0;
+        int a = 0, b = 0, cc = 0;
+        for (int i = lane; i < 49; i += 32) {
+            const int dy = i / 7 - 3, dx = i % 7 - 3;
+            const uint8_t* p = c + dy * w + dx;
+            const int tl = p[-w - 1], tc = p[-w], tr = p[-w + 1], ml = p[-1], mr = p[1], bl = p[w - 1], bc = p[w], br = p[w + 1];
+            const int Ix = (mr - ml) * 2 + (tr - tl) + (br - bl);
+            const int Iy = (bc - tc) * 2 + (bl - tl) + (br - tr);
+            a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+        }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, off);
-        b += __shfl_xor_sync(0xffffffffu, b, off);
-        cc += __shfl_xor_sync(0xffffffffu, cc, off);
-    }
-    if (lane == 0) {
-        // scale = 1.f/((1 << 2) * blockSize * 255.f); scale_sq_sq = scale*scale*scale*scale (orb.cpp:145-146)
-        const float scale = __fdiv_rn(1.f, 7140.f);
-        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
-        const float fa = (float)a, fb = (float)b, fc = (float)cc;
-        const float sum = __fadd_rn(fa, fb);
-        // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq   (orb.cpp:173-174)
-        const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
-        resp[o] = __fmul_rn(v, s4);
+        for (int off = 16; off; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+            cc += __shfl_xor_sync(0xffffffffu, cc, off);
+        }
+        if (lane == 0) {
+            // scale = 1.f/((1 << 2) * blockSize * 255.f); scale_sq_sq = scale*scale*scale*scale (orb.cpp:145-146)
+            const float scale = __fdiv_rn(1.f, 7140.f);
+            const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+            const float fa = (float)a, fb = (float)b, fc = (float)cc;
+            const float sum = __fadd_rn(fa, fb);
+            // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq   (orb.cpp:173-174)
+            const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
+            resp[o] = __fmul_rn(v, s4);
+        }
     }
 }
 
@@ -282,6 +288,7 @@ __device__ __forceinline__ uint32_t float_key(float v) {
 __global__ void __launch_bounds__(1024) retain_best_f32_kernel(const float* __restrict__ pts, const float* __restrict__ resp,
                                                                const int32_t* __restrict__ counts, int cap, int n_keep,
                                                                float* __restrict__ kp_out, float* __restrict__ pts_out,
+                                                               const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                                                                int32_t* __restrict__ out_counts, int out_cap) {
     __shared__ int hist[256];
     __shared__ uint32_t prefix_s, mask_s;
@@ -333,8 +340,9 @@ __global__ void __launch_bounds__(1024) retain_best_f32_kernel(const float* __re
         if (keep && pos < out_cap) {
             const size_t src = (size_t)f * cap + i, dst = (size_t)f * out_cap + pos;
             const float x = pts[2 * src], y = pts[2 * src + 1];
-            kp_out[4 * dst] = x; kp_out[4 * dst + 1] = y; kp_out[4 * dst + 2] = r[i]; kp_out[4 * dst + 3] = 0.f;
+            if (kp_out) { kp_out[4 * dst] = x; kp_out[4 * dst + 1] = y; kp_out[4 * dst + 2] = r[i]; kp_out[4 * dst + 3] = 0.f; }
             pts_out[2 * dst] = x; pts_out[2 * dst + 1] = y;
+            if (keys_out) keys_out[dst] = keys_in[src];
         }
         __syncthreads();
         if (tid == 0) { int t = 0; for (int wv = 0; wv < 32; wv++) t += wsum[wv]; base_s += t; }
@@ -386,16 +394,32 @@ extern "C" int alva_k_orb_describe(alva_ctx* ctx, const uint8_t* gray, const uin
     return 0;
 }
 
+// internal (pipeline.cu): KeyPointsFilter::retainBest(n) on float responses, order-preserving; optional packed keys
+int alva_retain_best_f32_launch(alva_ctx* ctx, const float* pts, const float* resp, const int32_t* counts, int cap, int nframes,
+                                int n_keep, float* pts_out, const uint32_t* keys_in, uint32_t* keys_out, int32_t* out_counts,
+                                int out_cap) {
+    retain_best_f32_kernel<<<nframes, 1024, 0, ctx->stream>>>(pts, resp, counts, cap, n_keep, nullptr, pts_out, keys_in, keys_out,
+                                                              out_counts, out_cap);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// zero_dead = 0 (internal callers with huge slot capacities): slots past the live count are left untouched
+int alva_harris_launch(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, const float* pts, const int32_t* npts_per_frame,
+                       int npts, float* resp, int zero_dead) {
+    dim3 grid(std::min((npts + 7) / 8, 256), nframes);
+    harris_kernel<<<grid, 256, 0, ctx->stream>>>(gray, w, h, pts, npts_per_frame, npts, resp, zero_dead);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int alva_k_harris(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, const float* pts,
                              const int32_t* npts_per_frame, int npts, float* resp) {
     if (!ctx || !gray || !pts || !resp || w < 9 || h < 9 || nframes < 1 || npts < 1) {
         alva_set_error("alva_k_harris: bad argument");
         return ALVA_E_INVALID;
     }
-    dim3 grid((npts + 7) / 8, nframes);
-    harris_kernel<<<grid, 256, 0, ctx->stream>>>(gray, w, h, pts, npts_per_frame, npts, resp);
-    ALVA_LAUNCH_CHECK(ctx);
-    return 0;
+    return alva_harris_launch(ctx, gray, w, h, nframes, pts, npts_per_frame, npts, resp, 1);
 }
 
 // ORB::detectAndCompute, nlevels = 1 (orb.cpp:970-1218 with computeKeyPoints :785-958): FAST(thr, nms) -> border 31 ->
@@ -434,8 +458,8 @@ extern "C" int alva_k_orb_detect(alva_ctx* ctx, const uint8_t* gray, int w, int 
     dim3 kgrid((kcap + 255) / 256, nframes);
     keys_to_pts_kernel<<<kgrid, 256, 0, ctx->stream>>>(keys1, cnt1, kcap, pts1);
     ALVA_LAUNCH_CHECK(ctx);
-    if (int e = alva_k_harris(ctx, gray, w, h, nframes, pts1, cnt1, kcap, resp)) return e;
-    retain_best_f32_kernel<<<nframes, 1024, 0, ctx->stream>>>(pts1, resp, cnt1, kcap, nfeatures, kp_out, pts2, counts, out_cap);
+    if (int e = alva_harris_launch(ctx, gray, w, h, nframes, pts1, cnt1, kcap, resp, 0)) return e;
+    retain_best_f32_kernel<<<nframes, 1024, 0, ctx->stream>>>(pts1, resp, cnt1, kcap, nfeatures, kp_out, pts2, nullptr, nullptr, counts, out_cap);
     ALVA_LAUNCH_CHECK(ctx);
     if (int e = alva_k_orb_blur(ctx, gray, blurred, w, h, nframes, flags)) return e;
     if (int e = alva_k_orb_describe(ctx, gray, blurred, w, h, nframes, pts2, counts, out_cap, flags | ALVA_ORB_IC_ANGLE, desc, kept, ang))

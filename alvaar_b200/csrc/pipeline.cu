@@ -16,10 +16,11 @@ extern "C" int alva_k_hamming_knn2_batch(alva_ctx*, const uint8_t* q, const int3
 namespace {
 
 __global__ void keys_to_points_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ counts, int cap,
-                                      float* __restrict__ pts) {
+                                      float* __restrict__ pts, int live_only) {
     const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap) return;
     const int n = min(counts[f], cap);
+    if (live_only && i >= n) return;   // large pre-selection lists: dead slots are never read
     float2 p = make_float2(0.f, 0.f);
     if (i < n) {
         const uint32_t k = keys[(size_t)f * cap + i];
@@ -44,7 +45,10 @@ struct alva_pipeline {
     int nprob = 0;      // BA problems per step
     // device buffers
     uint8_t *l0 = nullptr, *l1 = nullptr, *l2 = nullptr, *l3 = nullptr, *blur = nullptr;
-    uint32_t *keys = nullptr, *sel = nullptr;
+    int16_t *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;   // Scharr derivative levels (cfg.derivatives)
+    uint32_t *keys = nullptr, *sel = nullptr, *keys2 = nullptr;   // keys2 / counts2 / pts2 / resp2: ALVA_ORB_HARRIS pre-selection
+    int32_t* counts2 = nullptr;
+    float *pts2 = nullptr, *resp2 = nullptr;
     int32_t *counts = nullptr, *selcounts = nullptr;
     float *pts = nullptr, *angles = nullptr;
     uint8_t *desc = nullptr, *kept = nullptr, *map = nullptr;
@@ -64,6 +68,11 @@ struct alva_pipeline {
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
     // local BA runs beside the per-frame stages on its own (high-priority) stream, as the reference architecture's mapper
     // does beside the tracker: forked from / joined back into ctx->stream with events, so callers still see one stream
+    // feature selection (retainBest / Harris / retainBest: small, latency-bound kernels) runs on a second stream beside the
+    // pyramid, derivative and blur kernels, which do not depend on it; joined before the descriptors
+    alva_ctx* sel_ctx = nullptr;
+    cudaStream_t sel_stream = nullptr;
+    cudaEvent_t sel_fork = nullptr, sel_join = nullptr;
     alva_ctx* ba_ctx = nullptr;
     cudaStream_t ba_stream = nullptr;
     cudaEvent_t ba_fork = nullptr, ba_join = nullptr;
@@ -85,6 +94,10 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
     for (void* a : p->allocs) cudaFree(a);
+    if (p->sel_ctx) { alva_ctx_destroy(p->sel_ctx); p->sel_ctx = nullptr; }
+    if (p->sel_stream) { cudaStreamSynchronize(p->sel_stream); cudaStreamDestroy(p->sel_stream); }
+    if (p->sel_fork) cudaEventDestroy(p->sel_fork);
+    if (p->sel_join) cudaEventDestroy(p->sel_join);
     if (p->ba_ctx) { alva_ctx_destroy(p->ba_ctx); p->ba_ctx = nullptr; }
     if (p->ba_stream) { cudaStreamSynchronize(p->ba_stream); cudaStreamDestroy(p->ba_stream); }
     if (p->ba_fork) cudaEventDestroy(p->ba_fork);
@@ -119,8 +132,16 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
     p->nprob = cfg->kf_interval > 0 ? (B + cfg->kf_interval - 1) / cfg->kf_interval : 0;
     PALLOC(l0, (size_t)B * w * h); PALLOC(l1, (size_t)B * p->w1 * p->h1); PALLOC(l2, (size_t)B * p->w2 * p->h2);
     PALLOC(l3, (size_t)B * p->w3 * p->h3); PALLOC(blur, (size_t)B * w * h);
+    if (cfg->derivatives) {
+        PALLOC(d0, (size_t)B * w * h * 4); PALLOC(d1, (size_t)B * p->w1 * p->h1 * 4);
+        PALLOC(d2, (size_t)B * p->w2 * p->h2 * 4); PALLOC(d3, (size_t)B * p->w3 * p->h3 * 4);
+    }
     PALLOC(keys, (size_t)B * p->kcap * 4); PALLOC(counts, (size_t)B * 4);
     PALLOC(sel, (size_t)B * p->fcap * 4); PALLOC(selcounts, (size_t)B * 4);
+    if (cfg->orb_flags & ALVA_ORB_HARRIS) {
+        PALLOC(keys2, (size_t)B * p->kcap * 4); PALLOC(counts2, (size_t)B * 4);
+        PALLOC(pts2, (size_t)B * p->kcap * 8); PALLOC(resp2, (size_t)B * p->kcap * 4);
+    }
     PALLOC(pts, (size_t)B * p->fcap * 8); PALLOC(angles, (size_t)B * p->fcap * 4);
     PALLOC(desc, (size_t)B * p->fcap * 32); PALLOC(kept, (size_t)B * p->fcap);
     PALLOC(matches, (size_t)B * p->fcap * 16);
@@ -142,6 +163,14 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
             alva_pipeline_destroy(p);
             return nullptr;
         }
+    }
+    if (cudaStreamCreateWithFlags(&p->sel_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->sel_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->sel_join, cudaEventDisableTiming) != cudaSuccess ||
+        !(p->sel_ctx = alva_ctx_create(ctx->device, (void*)p->sel_stream))) {
+        alva_set_error("alva_pipeline_create: selection stream setup failed");
+        alva_pipeline_destroy(p);
+        return nullptr;
     }
     for (int i = 0; i < alva_pipeline::NEV; i++)
         if (cudaEventCreate(&p->ev0[i]) != cudaSuccess || cudaEventCreate(&p->ev1[i]) != cudaSuccess) {
@@ -203,6 +232,13 @@ extern "C" int alva_pipeline_frontend_ms(alva_pipeline* p, float* ms, int n) {
 }
 
 // defined in frontend.cu: the fused launch alone (so the events bracket exactly the dominant kernel)
+int alva_harris_launch(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, const float* pts, const int32_t* npts_per_frame,
+                       int npts, float* resp, int zero_dead);
+int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src, int16_t* const* dst, const int* w, const int* h,
+                              int nframes);
+int alva_retain_best_f32_launch(alva_ctx* ctx, const float* pts, const float* resp, const int32_t* counts, int cap, int nframes,
+                                int n_keep, float* pts_out, const uint32_t* keys_in, uint32_t* keys_out, int32_t* out_counts,
+                                int out_cap);
 int alva_frontend_main_launch(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1, int thr,
                               uint32_t* keys, int32_t* counts, int cap);
 
@@ -228,16 +264,51 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
     // the step's local BA starts here, beside everything below (after the front end so that the event pair above times
     // that kernel alone)
     if (fork_ba) if (int e = pipeline_ba_fork(p)) return e;
+    // 2. feature selection inside ORB's 31-px border, row-major -- on the selection stream
+    alva_ctx* sc = p->sel_ctx;
+    cudaStream_t ss = p->sel_stream;
+    const long long sel_before = sc->launches;
+    ALVA_CUDA(cudaEventRecord(p->sel_fork, st));
+    ALVA_CUDA(cudaStreamWaitEvent(ss, p->sel_fork, 0));
+    if (c.orb_flags & ALVA_ORB_HARRIS) {
+        // ORB::detectAndCompute's own rule (orb.cpp:855-925): retainBest(2n) on the FAST score, Harris response of the
+        // survivors, retainBest(n) on that
+        uint32_t* keys2 = p->keys2 + F * p->kcap;
+        int32_t* counts2 = p->counts2 + F;
+        float *pts2 = p->pts2 + F * p->kcap * 2, *resp2 = p->resp2 + F * p->kcap;
+        if (int e = alva_k_retain_best(sc, keys, counts, p->kcap, nf, w, h, 2 * c.nfeatures, 31, keys2, counts2, p->kcap)) return e;
+        clamp_counts_kernel<<<(nf + 127) / 128, 128, 0, ss>>>(counts2, nf, p->kcap);
+        ALVA_LAUNCH_CHECK(sc);
+        keys_to_points_kernel<<<dim3((p->kcap + 127) / 128, nf), 128, 0, ss>>>(keys2, counts2, p->kcap, pts2, 1);
+        ALVA_LAUNCH_CHECK(sc);
+        if (int e = alva_harris_launch(sc, l0, w, h, nf, pts2, counts2, p->kcap, resp2, 0)) return e;
+        if (int e = alva_retain_best_f32_launch(sc, pts2, resp2, counts2, p->kcap, nf, c.nfeatures, p->pts + F * p->fcap * 2, keys2, sel,
+                                                selcounts, p->fcap))
+            return e;
+        clamp_counts_kernel<<<(nf + 127) / 128, 128, 0, ss>>>(selcounts, nf, p->fcap);
+        ALVA_LAUNCH_CHECK(sc);
+    } else {
+        if (int e = alva_k_retain_best(sc, keys, counts, p->kcap, nf, w, h, c.nfeatures, 31, sel, selcounts, p->fcap)) return e;
+        clamp_counts_kernel<<<(nf + 127) / 128, 128, 0, ss>>>(selcounts, nf, p->fcap);
+        ALVA_LAUNCH_CHECK(sc);
+        keys_to_points_kernel<<<dim3((p->fcap + 127) / 128, nf), 128, 0, ss>>>(sel, selcounts, p->fcap, p->pts + F * p->fcap * 2, 0);
+        ALVA_LAUNCH_CHECK(sc);
+    }
+    ALVA_CUDA(cudaEventRecord(p->sel_join, ss));
+    ctx->launches += sc->launches - sel_before;
+    // 1b. rest of the pyramid + derivative levels (main stream, concurrent with the selection)
     if (int e = alva_k_pyrdown(ctx, l1, l2, p->w1, p->h1, nf)) return e;
     if (int e = alva_k_pyrdown(ctx, l2, l3, p->w2, p->h2, nf)) return e;
-    // 2. retainBest(nfeatures) inside ORB's 31-px border, row-major
-    if (int e = alva_k_retain_best(ctx, keys, counts, p->kcap, nf, w, h, c.nfeatures, 31, sel, selcounts, p->fcap)) return e;
-    clamp_counts_kernel<<<(nf + 127) / 128, 128, 0, st>>>(selcounts, nf, p->fcap);
-    ALVA_LAUNCH_CHECK(ctx);
-    keys_to_points_kernel<<<dim3((p->fcap + 127) / 128, nf), 128, 0, st>>>(sel, selcounts, p->fcap, p->pts + F * p->fcap * 2);
-    ALVA_LAUNCH_CHECK(ctx);
+    if (c.derivatives) {   // the derivative pyramid the KLT tracker reads (buildOpticalFlowPyramid withDerivatives)
+        const uint8_t* srcs[4] = {l0, l1, l2, l3};
+        int16_t* dsts[4] = {p->d0 + F * w * h * 2, p->d1 + F * p->w1 * p->h1 * 2, p->d2 + F * p->w2 * p->h2 * 2,
+                            p->d3 + F * p->w3 * p->h3 * 2};
+        const int ws[4] = {w, p->w1, p->w2, p->w3}, hs[4] = {h, p->h1, p->h2, p->h3};
+        if (int e = alva_scharr_levels_launch(ctx, 4, srcs, dsts, ws, hs, nf)) return e;
+    }
     // 3. ORB
     if (int e = alva_k_orb_blur(ctx, l0, blur, w, h, nf, c.orb_flags & ALVA_ORB_FMA)) return e;
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->sel_join, 0));
     if (int e = alva_k_orb_describe(ctx, l0, blur, w, h, nf, p->pts + F * p->fcap * 2, selcounts, p->fcap, c.orb_flags,
                                     p->desc + F * p->fcap * 32, p->kept + F * p->fcap, p->angles + F * p->fcap))
         return e;
@@ -355,6 +426,6 @@ extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: f
 extern "C" void* alva_pipeline_buffer(alva_pipeline* p, int which) {
     if (!p) return nullptr;
     void* t[] = {p->l0, p->l1, p->l2, p->l3, p->blur, p->keys, p->counts, p->sel, p->selcounts, p->pts, p->angles, p->desc,
-                 p->kept, p->matches, p->ba_poses, p->ba_invd, p->ba_summary};
-    return (which >= 0 && which < 17) ? t[which] : nullptr;
+                 p->kept, p->matches, p->ba_poses, p->ba_invd, p->ba_summary, p->d0, p->d1, p->d2, p->d3};
+    return (which >= 0 && which < 21) ? t[which] : nullptr;
 }

@@ -6,6 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORB_FMA = 1
 ORB_IC_ANGLE = 2
+ORB_HARRIS = 4
 
 
 class AlvaError(RuntimeError):

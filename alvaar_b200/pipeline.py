@@ -9,16 +9,17 @@ from .lib import AlvaError, lib
 class _Config(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("batch", C.c_int), ("fast_thr", C.c_int), ("nfeatures", C.c_int),
                 ("orb_flags", C.c_int), ("map_size", C.c_int), ("kf_interval", C.c_int), ("ba_nkf", C.c_int),
-                ("ba_nlm", C.c_int), ("ba_nobs", C.c_int), ("ba_max_iter", C.c_int), ("ba_huber", C.c_double)]
+                ("ba_nlm", C.c_int), ("ba_nobs", C.c_int), ("ba_max_iter", C.c_int), ("ba_huber", C.c_double),
+                ("derivatives", C.c_int), ("reserved", C.c_int)]
 
 
 BUF = dict(l0=0, l1=1, l2=2, l3=3, blur=4, keys=5, counts=6, sel=7, selcounts=8, pts=9, angles=10, desc=11, kept=12,
-           matches=13, ba_poses=14, ba_invd=15, ba_summary=16)
+           matches=13, ba_poses=14, ba_invd=15, ba_summary=16, d0=17, d1=18, d2=19, d3=20)
 
 
 class Pipeline:
     def __init__(self, ctx, w, h, batch, fast_thr=20, nfeatures=1000, orb_flags=2, map_size=0, kf_interval=0, ba_nkf=0,
-                 ba_nlm=0, ba_nobs=0, ba_max_iter=5, ba_huber=0.0):
+                 ba_nlm=0, ba_nobs=0, ba_max_iter=5, ba_huber=0.0, derivatives=False):
         self.ctx, self.L = ctx, lib()
         L = self.L
         L.alva_pipeline_create.restype = C.c_void_p
@@ -34,7 +35,7 @@ class Pipeline:
         L.alva_pipeline_buffer.restype = C.c_void_p
         L.alva_pipeline_buffer.argtypes = [C.c_void_p, C.c_int]
         self.cfg = _Config(w, h, batch, fast_thr, nfeatures, orb_flags, map_size, kf_interval, ba_nkf, ba_nlm, ba_nobs,
-                           ba_max_iter, ba_huber)
+                           ba_max_iter, ba_huber, 1 if derivatives else 0, 0)
         h_ = L.alva_pipeline_create(ctx.h, C.byref(self.cfg))
         if not h_:
             raise AlvaError(L.alva_last_error().decode())

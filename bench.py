@@ -217,7 +217,8 @@ def workload_config(batch, world=1, loop_closure=False):
 
 def _workload_config(batch):
     return {"workload": "c2_720p_stream+c4_local_ba", "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
-            "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "7x7 blur + IC angle + rBRIEF-256, 1 level",
+            "pyramid": "4 levels + Scharr derivative levels (buildOpticalFlowPyramid withDerivatives, as the reference)",
+            "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "ORB::detectAndCompute semantics, 1 level: FAST-9 -> retainBest(2n) -> Harris -> retainBest(n) -> IC angle -> 7x7 blur -> rBRIEF-256",
             "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
             "ba_every_n_frames": KF_INTERVAL,
             "ba_schedule": "own high-priority stream, forked after the front end and joined at the end of the step",
@@ -244,9 +245,9 @@ def bench_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     ctx = alvaar_b200.Context(local_rank, stream.cuda_stream)
     ctx.L.alva_set_option(b"pipeline_ba_overlap", 0 if args.no_ba_overlap else 1)
-    pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE,
+    pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE | alvaar_b200.ORB_HARRIS,
                     map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
-                    ba_max_iter=BA_ITERS, ba_huber=ba["huber"])
+                    ba_max_iter=BA_ITERS, ba_huber=ba["huber"], derivatives=True)
     pipe.set_map(map_desc)
     for s in range(pipe.nprob):
         pipe.set_ba(s, ba)

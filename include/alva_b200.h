@@ -41,6 +41,9 @@ extern "C" {
 
 #define ALVA_ORB_FMA        1   /* blur with fused multiply-add (native AVX2 OpenCV dispatch); default = unfused
                                    (SSE baseline == the shipped WASM simd128 arithmetic) */
+#define ALVA_ORB_HARRIS     4   /* alva_pipeline only: select the features as ORB::detectAndCompute does (HARRIS_SCORE,
+                                   orb.cpp:849-925): retainBest(2n) on the FAST score, then retainBest(n) on the Harris
+                                   response -- instead of retainBest(n) on the FAST score alone */
 #define ALVA_ORB_IC_ANGLE   2   /* steer rBRIEF by the intensity-centroid angle (ORB::detect mode) instead of
                                    AlvaAR's constant -1 degree (feature_extractor.cpp:179-182) */
 
@@ -191,6 +194,9 @@ typedef struct alva_pipeline_config {
     int kf_interval;        /* one local BA per kf_interval frames (0 = no BA) */
     int ba_nkf, ba_nlm, ba_nobs, ba_max_iter;
     double ba_huber;
+    int derivatives;        /* != 0: also build the Scharr derivative image of every pyramid level, as the reference's
+                               buildOpticalFlowPyramid(..., withDerivatives = true) does each frame (visual_frontend.cpp:696) */
+    int reserved;
 } alva_pipeline_config;
 
 alva_pipeline* alva_pipeline_create(alva_ctx*, const alva_pipeline_config*);

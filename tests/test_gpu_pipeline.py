@@ -20,7 +20,7 @@ def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
     q, mapd = synth.make_descriptors(8, 2000, seed=3)
     ba = synth.make_ba_problem(8, 300, 3, seed=7)
     pipe = Pipeline(gpu_ctx, w, h, batch, fast_thr=20, nfeatures=nfeat, orb_flags=ORB_IC_ANGLE, map_size=2000, kf_interval=2,
-                    ba_nkf=8, ba_nlm=300, ba_nobs=len(ba["obs_kf"]), ba_max_iter=5, ba_huber=ba["huber"])
+                    ba_nkf=8, ba_nlm=300, ba_nobs=len(ba["obs_kf"]), ba_max_iter=5, ba_huber=ba["huber"], derivatives=True)
     pipe.set_map(mapd)
     for s in range(pipe.nprob):
         pipe.set_ba(s, ba)
@@ -44,6 +44,7 @@ def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
     for _ in range(3):
         sizes.append(((sizes[-1][0] + 1) // 2, (sizes[-1][1] + 1) // 2))
     lv = [pipe.buffer(f"l{k}", (batch, sizes[k][1], sizes[k][0]), torch.uint8).cpu().numpy() for k in range(4)]
+    dv = [pipe.buffer(f"d{k}", (batch, sizes[k][1], sizes[k][0], 2), torch.int16).cpu().numpy() for k in range(4)]
     for f in range(batch):
         gray = np.empty((h, w), np.uint8)
         oracle.orc_gray(P(frames[f]), w, h, P(gray))
@@ -54,6 +55,10 @@ def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
             oracle.orc_pyrdown(P(cur), cur.shape[1], cur.shape[0], P(nxt))
             assert (lv[k][f] == nxt).all()
             cur = nxt
+        for k in range(4):   # derivative pyramid (buildOpticalFlowPyramid withDerivatives)
+            want = np.zeros((sizes[k][1], sizes[k][0], 2), np.int16)
+            oracle.orc_scharr(P(np.ascontiguousarray(lv[k][f])), sizes[k][0], sizes[k][1], P(want))
+            assert (dv[k][f] == want).all()
         xs = np.zeros((w * h // 4, 3), np.int32)
         n = oracle.orc_fast9(P(gray), w, h, 20, 1, P(xs), len(xs))
         k = xs[:n]
@@ -83,4 +88,37 @@ def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
     for s in range(pipe.nprob):
         assert np.allclose(poses_h[s].numpy(), wp, rtol=1e-4, atol=1e-9)
         assert (summ_h[s].numpy()[2:5] == ws[2:5]).all()
+    pipe.close()
+
+
+@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000)])
+def test_pipeline_detect_and_compute_mode(gpu_ctx, oracle, w, h, batch, nfeat):
+    """orb_flags = IC_ANGLE | HARRIS: the pipeline's feature set per frame is exactly ORB::detectAndCompute(nfeat, 1 level)'s
+    (oracle composition pinned bit-for-bit to the reference in tests/test_oracle.py), and the matches follow from it."""
+    from alvaar_b200 import ORB_HARRIS
+    frames, _ = synth.make_frames(batch, w, h, seed=8)
+    _, mapd = synth.make_descriptors(8, 1500, seed=4)
+    pipe = Pipeline(gpu_ctx, w, h, batch, fast_thr=20, nfeatures=nfeat, orb_flags=ORB_IC_ANGLE | ORB_HARRIS, map_size=1500)
+    pipe.set_map(mapd)
+    pipe.step_dev(torch.from_numpy(frames).to(DEV))
+    torch.cuda.synchronize()
+    fcap = pipe.fcap
+    sel = pipe.buffer("sel", (batch, fcap), torch.int32).cpu().numpy().view(np.uint32)
+    selc = pipe.buffer("selcounts", (batch,), torch.int32).cpu().numpy()
+    desc = pipe.buffer("desc", (batch, fcap, 32), torch.uint8).cpu().numpy()
+    ang = pipe.buffer("angles", (batch, fcap), torch.float32).cpu().numpy()
+    matches = pipe.buffer("matches", (batch, fcap, 4), torch.int32).cpu().numpy()
+    for f in range(batch):
+        gray = np.empty((h, w), np.uint8)
+        oracle.orc_gray(P(frames[f]), w, h, P(gray))
+        wk, wd = np.zeros((4096, 4), np.float32), np.zeros((4096, 32), np.uint8)
+        n = oracle.orc_orb_detect(P(gray), w, h, nfeat, 20, 0, P(wk), P(wd), 4096)
+        assert n == selc[f] and nfeat <= n <= fcap
+        k = unpack_keys(sel[f, :n])
+        assert (k[:, 0] == wk[:n, 0]).all() and (k[:, 1] == wk[:n, 1]).all()
+        assert (ang[f, :n].view(np.uint32) == wk[:n, 3].copy().view(np.uint32)).all()
+        assert (desc[f, :n] == wd[:n]).all()
+        wm = np.zeros((n, 4), np.int32)
+        oracle.orc_knn2(P(np.ascontiguousarray(wd[:n])), n, P(mapd), len(mapd), P(wm))
+        assert (matches[f, :n] == wm).all() and (matches[f, n:] == -1).all()
     pipe.close()
