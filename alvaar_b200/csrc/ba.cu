@@ -1457,11 +1457,13 @@ extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, co
 
 // Library-wide options: "ba_dense_schur" = 1 routes the -(E'F)'(E'E)^-1(E'F) term of the Schur complement through the
 // FP64 tensor-core SYRK (S -= Wt'Wt) instead of per-landmark atomics.  Returns 0, or ALVA_E_INVALID for an unknown name.
+extern int alva_g_knn_qpw;   // hamming.cu
 int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside the frame stages
 
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_ba_overlap")) { alva_g_ba_overlap = value ? 1 : 0; return 0; }
+    if (name && !strcmp(name, "knn_qpw") && (value == 4 || value == 8)) { alva_g_knn_qpw = value; return 0; }
     alva_set_error("alva_set_option: unknown option");
     return ALVA_E_INVALID;
 }

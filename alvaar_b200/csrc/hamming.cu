@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int QPW = 8;          // queries per warp
+constexpr int QPW_MAX = 8;      // queries per warp: 8 (128 registers, 16 warps/SM) or 4 (<= 80 registers, 24 warps/SM); the batch
+                                // entry point requires qcap % 8 == 0 so that either grouping never straddles two frames
 constexpr int WPC = 8;          // warps per CTA
 constexpr int MIN_CHUNK = 512;  // never split the train set finer than this
 constexpr uint32_t NONE = 0xffffffffu;
@@ -50,7 +51,7 @@ __device__ __forceinline__ void warp_top2(uint32_t k0, uint32_t k1, uint32_t& m0
 }
 
 // one train descriptor per lane against the warp's QPW queries
-template <bool TAIL>
+template <int QPW, bool TAIL>
 __device__ __forceinline__ void knn_step(const uint4 (&qa)[QPW], const uint4 (&qb)[QPW], uint32_t (&k0)[QPW], uint32_t (&k1)[QPW],
                                          uint32_t (&tk)[QPW], const uint4* __restrict__ t, int j, int te, uint32_t mul22,
                                          uint32_t mul23, uint32_t mul24) {
@@ -99,36 +100,42 @@ __device__ __forceinline__ void knn_step(const uint4 (&qa)[QPW], const uint4 (&q
 // rare path (about 2 ln N times per query) inserts into the lane's private pair and refreshes tk with three REDUX.
 // mul = {2^22, 2^23, 2^24} as run-time data: weights and key packing become IMADs on the FMA pipe instead of shifts /
 // LEAs on the ALU pipe, which the 16 LOP3 per distance already saturate.
-__global__ void __launch_bounds__(WPC * 32) knn2_partial_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
+template <int QPW>
+__global__ void __launch_bounds__(WPC * 32, QPW == 8 ? 2 : 3) knn2_partial_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
                                                                 int nt, uint2* __restrict__ partial, int nchunks, int chunk_len,
                                                                 const int32_t* __restrict__ counts, int qcap, uint32_t mul22,
                                                                 uint32_t mul23, uint32_t mul24) {
+    // One CTA = 8 warps x 8 queries against one chunk of the train set.  CTAs are deliberately short-lived (tens of
+    // microseconds): the step's local BA and pyramid kernels run beside this one on other streams and can only get SM
+    // resources when a CTA retires -- a persistent variant of this kernel starved them and cost 25 % of the step.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q0 = (blockIdx.x * WPC + warp) * QPW;
-    if (q0 >= nq) return;
-    if (counts) { const int b = q0 / qcap; if (q0 - b * qcap >= counts[b]) return; }
-    const int chunk = blockIdx.y;
-    const int tb = chunk * chunk_len, te = min(nt, tb + chunk_len);
-    uint4 qa[QPW], qb[QPW];
+    {
+        const int q0 = (blockIdx.x * WPC + warp) * QPW;
+        if (q0 >= nq) return;
+        if (counts) { const int b = q0 / qcap; if (q0 - b * qcap >= counts[b]) return; }
+        const int chunk = blockIdx.y;
+        const int tb = chunk * chunk_len, te = min(nt, tb + chunk_len);
+        uint4 qa[QPW], qb[QPW];
 #pragma unroll
-    for (int i = 0; i < QPW; i++) {
-        const int qi = min(q0 + i, nq - 1);
-        qa[i] = __ldg(q + 2 * qi);
-        qb[i] = __ldg(q + 2 * qi + 1);
-    }
-    uint32_t k0[QPW], k1[QPW], tk[QPW];
+        for (int i = 0; i < QPW; i++) {
+            const int qi = min(q0 + i, nq - 1);
+            qa[i] = __ldg(q + 2 * qi);
+            qb[i] = __ldg(q + 2 * qi + 1);
+        }
+        uint32_t k0[QPW], k1[QPW], tk[QPW];
 #pragma unroll
-    for (int i = 0; i < QPW; i++) k0[i] = k1[i] = tk[i] = NONE;
-    const int full_steps = (te - tb) >> 5;   // warp-uniform trip count (the rare path votes)
-    for (int sidx = 0; sidx < full_steps; sidx++)
-        knn_step<false>(qa, qb, k0, k1, tk, t, tb + 32 * sidx + lane, te, mul22, mul23, mul24);
-    if (tb + 32 * full_steps < te)   // ragged tail: lanes past the end contribute nothing
-        knn_step<true>(qa, qb, k0, k1, tk, t, tb + 32 * full_steps + lane, te, mul22, mul23, mul24);
+        for (int i = 0; i < QPW; i++) k0[i] = k1[i] = tk[i] = NONE;
+        const int full_steps = (te - tb) >> 5;   // warp-uniform trip count (the rare path votes)
+        for (int sidx = 0; sidx < full_steps; sidx++)
+            knn_step<QPW, false>(qa, qb, k0, k1, tk, t, tb + 32 * sidx + lane, te, mul22, mul23, mul24);
+        if (tb + 32 * full_steps < te)   // ragged tail: lanes past the end contribute nothing
+            knn_step<QPW, true>(qa, qb, k0, k1, tk, t, tb + 32 * full_steps + lane, te, mul22, mul23, mul24);
 #pragma unroll
-    for (int i = 0; i < QPW; i++) {
-        uint32_t m0, m1;
-        warp_top2(k0[i], k1[i], m0, m1);
-        if (lane == 0 && q0 + i < nq) partial[(size_t)(q0 + i) * nchunks + chunk] = make_uint2(m0, m1);
+        for (int i = 0; i < QPW; i++) {
+            uint32_t m0, m1;
+            warp_top2(k0[i], k1[i], m0, m1);
+            if (lane == 0 && q0 + i < nq) partial[(size_t)(q0 + i) * nchunks + chunk] = make_uint2(m0, m1);
+        }
     }
 }
 
@@ -154,11 +161,11 @@ __global__ void knn2_merge_kernel(const uint2* __restrict__ partial, int nq, int
 
 }  // namespace
 
-// Chunking of the train set: one chunk per CTA row.  Long chunks make the selection filter effective (its rare path runs
-// ~2 ln(chunk) times per query), so split only as far as needed to give the GPU a few waves of CTAs.
-static void knn_chunks(const alva_ctx* ctx, int nq, int nt, int* nchunks, int* chunk_len) {
+// Chunking of the train set.  Long chunks make the selection filter effective (its rare path runs ~2 ln(chunk) times per
+// query); short CTAs keep the launch tail small and let concurrent streams in.  Aim at ~16 waves.
+static void knn_chunks(const alva_ctx* ctx, int nq, int nt, int QPW, int* nchunks, int* chunk_len) {
     const int ctas_q = (nq + QPW * WPC - 1) / (QPW * WPC);
-    const int target = 8 * ctx->num_sms;   // 2 resident CTAs per SM x 4 waves
+    const int target = (QPW == 8 ? 2 : 3) * ctx->num_sms * 16;   // ~16 waves of the 2 resident CTAs per SM: short CTAs, negligible tail
     int n = (target + ctas_q - 1) / ctas_q;
     const int nmax = (nt + MIN_CHUNK - 1) / MIN_CHUNK;
     if (n > nmax) n = nmax;
@@ -168,42 +175,43 @@ static void knn_chunks(const alva_ctx* ctx, int nq, int nt, int* nchunks, int* c
     *chunk_len = len;
 }
 
+int alva_g_knn_qpw = 4;   // alva_set_option("knn_qpw", 4 | 8)
+
+static int knn_launch(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out, const int32_t* counts, int qcap) {
+    int nchunks, chunk_len;
+    const int QPW = alva_g_knn_qpw == 4 ? 4 : 8;
+    knn_chunks(ctx, nq, nt, QPW, &nchunks, &chunk_len);
+    uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
+    if (!partial) return ALVA_E_CUDA;
+    dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
+    if (QPW == 8)
+        knn2_partial_kernel<8><<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
+                                                                   counts, qcap, 1u << 22, 1u << 23, 1u << 24);
+    else
+        knn2_partial_kernel<4><<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
+                                                                   counts, qcap, 1u << 22, 1u << 23, 1u << 24);
+    ALVA_LAUNCH_CHECK(ctx);
+    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) {
     if (!ctx || !q || !t || !out || nq < 1 || nt < 1 || nt >= (1 << 22) || ((uintptr_t)q & 15) || ((uintptr_t)t & 15) ||
         ((uintptr_t)out & 15)) {
         alva_set_error("alva_k_hamming_knn2: bad argument (need 16-byte aligned buffers, 1 <= nt < 2^22)");
         return ALVA_E_INVALID;
     }
-    int nchunks, chunk_len;
-    knn_chunks(ctx, nq, nt, &nchunks, &chunk_len);
-    uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
-    if (!partial) return ALVA_E_CUDA;
-    dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
-    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
-                                                            nullptr, 0, 1u << 22, 1u << 23, 1u << 24);
-    ALVA_LAUNCH_CHECK(ctx);
-    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, nullptr, 0);
-    ALVA_LAUNCH_CHECK(ctx);
-    return 0;
+    return knn_launch(ctx, q, nq, t, nt, out, nullptr, 0);
 }
 
 extern "C" int alva_k_hamming_knn2_batch(alva_ctx* ctx, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
                                          const uint8_t* t, int nt, int32_t* out) {
-    if (!ctx || !q || !counts || !t || !out || nbatch < 1 || qcap < 1 || (qcap % QPW) != 0 || nt < 1 || nt >= (1 << 22) ||
+    if (!ctx || !q || !counts || !t || !out || nbatch < 1 || qcap < 1 || (qcap % QPW_MAX) != 0 || nt < 1 || nt >= (1 << 22) ||
         ((uintptr_t)q & 15) || ((uintptr_t)t & 15) || ((uintptr_t)out & 15)) {
-        alva_set_error("alva_k_hamming_knn2_batch: bad argument (qcap must be a multiple of %d)", QPW);
+        alva_set_error("alva_k_hamming_knn2_batch: bad argument (qcap must be a multiple of %d)", QPW_MAX);
         return ALVA_E_INVALID;
     }
     const int nq = nbatch * qcap;
-    int nchunks, chunk_len;
-    knn_chunks(ctx, nq, nt, &nchunks, &chunk_len);
-    uint2* partial = (uint2*)alva_scratch(ctx, (size_t)nq * nchunks * sizeof(uint2));
-    if (!partial) return ALVA_E_CUDA;
-    dim3 grid((nq + QPW * WPC - 1) / (QPW * WPC), nchunks);
-    knn2_partial_kernel<<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
-                                                            counts, qcap, 1u << 22, 1u << 23, 1u << 24);
-    ALVA_LAUNCH_CHECK(ctx);
-    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
-    ALVA_LAUNCH_CHECK(ctx);
-    return 0;
+    return knn_launch(ctx, q, nbatch * qcap, t, nt, out, counts, qcap);
 }

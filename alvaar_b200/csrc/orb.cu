@@ -14,6 +14,8 @@
 #include <algorithm>
 #include "../../include/alva_b200.h"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -24,7 +26,9 @@ __constant__ int8_t c_pattern[1024] = {
 __constant__ uint32_t c_gauss_bits[4] = {0x3e5d4ae0u, 0x3e434a39u, 0x3e06387eu, 0x3d8fafb1u};
 
 constexpr int BTW = 128, BTH = 64;          // blur tile (outputs)
-constexpr int BIP = BTW + 16;               // input smem pitch in bytes: image x0-8 at byte 0 (only x0-3 .. x0+BTW+2 are used)
+constexpr int BIP = BTW + 32;               // input smem pitch in bytes: image x0-16 at byte 0 (x0-3 .. x0+BTW+2 are used);
+                                            // 16 halo bytes so that a TMA box starts 16-byte aligned
+constexpr int BIX = 16;                     // byte of image column x0
 constexpr int BIR = BTH + 6;                // input rows y0-3 .. y0+BTH+2
 
 // u8 -> f32 without the conversion pipe: 0x4B000000 | b is the float 2^23 + b; one PRMT + one FADD (exact)
@@ -33,13 +37,16 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t sel) {
 }
 
 // Separable 7x7 Gaussian exactly as OpenCV's float path evaluates it (see file header): row pass then column pass.
+// The (BTW+32) x (BTH+6) input tile arrives by ONE TMA bulk-tensor copy (out-of-image bytes come back as zeros and the
+// reflect-101 border is patched in shared memory); geometries TMA cannot address take a plain-load path.
 // Thread = 4 adjacent pixels: the row pass reads three packed words and produces a float4; the column pass walks an
 // 8-row strip with a rolling 7-row window of float4, packs 4 results and stores one 32-bit word.
 template <bool FMA>
-__global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w,
-                                                       int h) {
-    __shared__ __align__(16) uint8_t in_s[BIR][BIP];
+__global__ void __launch_bounds__(256) orb_blur_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                       const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int w, int h) {
+    __shared__ __align__(128) uint8_t in_s[BIR][BIP];
     __shared__ __align__(16) float row_s[BIR][BTW];
+    __shared__ uint64_t bar;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH;
     const size_t fo = (size_t)blockIdx.z * w * h;
@@ -48,17 +55,44 @@ __global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict
 #pragma unroll
     for (int i = 0; i < 4; i++) k[i] = __uint_as_float(c_gauss_bits[i]);   // k[j] = weight at distance j
 
-    const bool interior = (x0 >= 8) && (x0 + BTW + 8 <= w) && ((w & 3) == 0) && ((((uintptr_t)src) & 3) == 0);
-    if (interior) {   // word loads, rows reflected
-        for (int i = tid; i < BIR * (BIP / 4); i += 256) {
-            const int r = i / (BIP / 4), c4 = i - r * (BIP / 4);
-            const int y = reflect101(min(y0 + r - 3, h + 3), h);
-            reinterpret_cast<uint32_t*>(&in_s[r][0])[c4] = __ldg(reinterpret_cast<const uint32_t*>(s + (size_t)y * w + x0 - 8) + c4);
+    if (use_tma) {
+        if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar, BIP * BIR);
+            tma_load_3d(&in_s[0][0], &tmap, &bar, x0 - BIX, y0 - 3, blockIdx.z);
+        }
+        mbar_wait(&bar, 0);
+        // reflect-101 patch of what lies outside the image: columns first (rows inside the image), then whole rows
+        const bool el = (x0 == 0), er = (x0 + BTW + 3 > w);
+        if (el || er) {
+            for (int r = tid; r < BIR; r += 256) {
+                const int y = y0 - 3 + r;
+                if (y < 0 || y >= h) continue;
+                uint8_t* row = &in_s[r][0];
+                if (el) { row[BIX - 1] = row[BIX + 1]; row[BIX - 2] = row[BIX + 2]; row[BIX - 3] = row[BIX + 3]; }
+                if (er) {
+                    const int cw = w - x0 + BIX;   // byte of image column w
+                    if (cw + 2 < BIP) { row[cw] = row[cw - 2]; row[cw + 1] = row[cw - 3]; row[cw + 2] = row[cw - 4]; }
+                }
+            }
+            __syncthreads();
+        }
+        if (y0 == 0 || y0 + BTH + 3 > h) {
+            for (int i = tid; i < 6 * (BIP / 4); i += 256) {
+                const int j = i / (BIP / 4), c4 = i - j * (BIP / 4);
+                // j = 0..2: image rows -1, -2, -3 (top);  j = 3..5: rows h, h+1, h+2 (bottom)
+                const int y = j < 3 ? -1 - j : h + (j - 3);
+                const int ys = j < 3 ? 1 + j : h - 2 - (j - 3);
+                const int r = y - y0 + 3, rs = ys - y0 + 3;
+                if (r >= 0 && r < BIR && rs >= 0 && rs < BIR && ys >= 0 && ys < h)
+                    reinterpret_cast<uint32_t*>(&in_s[r][0])[c4] = reinterpret_cast<const uint32_t*>(&in_s[rs][0])[c4];
+            }
         }
     } else {
         for (int i = tid; i < BIR * BIP; i += 256) {
             const int r = i / BIP, c = i - r * BIP;
-            const int x = reflect101(max(min(x0 + c - 8, w + 7), -8), w), y = reflect101(min(y0 + r - 3, h + 3), h);
+            const int x = reflect101(max(min(x0 + c - BIX, w + 7), -8), w), y = reflect101(min(y0 + r - 3, h + 3), h);
             in_s[r][c] = __ldg(s + (size_t)y * w + x);
         }
     }
@@ -66,7 +100,7 @@ __global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict
     // row filter: s = k0*S[0]; s += k[i]*S[i], left to right (RowFilter<uchar,float>, filter.simd.hpp:2477-2487)
     for (int i = tid; i < BIR * (BTW / 4); i += 256) {
         const int r = i >> 5, g = i & 31;                      // BTW / 4 == 32 groups per row
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&in_s[r][0]) + 1 + g;   // W0 = x-4..x-1, W1 = x..x+3, W2 = x+4..x+7
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&in_s[r][0]) + BIX / 4 - 1 + g;   // W0 = x-4..x-1, W1 = x..x+3, W2 = x+4..x+7
         const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2];
         float f[10];                                            // pixels x-3 .. x+6
         f[0] = byte_to_float(W0, 0x7651); f[1] = byte_to_float(W0, 0x7652); f[2] = byte_to_float(W0, 0x7653);
@@ -373,8 +407,17 @@ extern "C" int alva_k_orb_blur(alva_ctx* ctx, const uint8_t* gray, uint8_t* blur
         return ALVA_E_INVALID;
     }
     dim3 grid((w + BTW - 1) / BTW, (h + BTH - 1) / BTH, nframes);
-    if (flags & ALVA_ORB_FMA) orb_blur_kernel<true><<<grid, 256, 0, ctx->stream>>>(gray, blurred, w, h);
-    else orb_blur_kernel<false><<<grid, 256, 0, ctx->stream>>>(gray, blurred, w, h);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)nframes};
+    const uint64_t strides[2] = {(uint64_t)w, (uint64_t)w * h};
+    const uint32_t box[3] = {BIP, BIR, 1};
+    static const bool no_tma = getenv("ALVA_DISABLE_TMA") != nullptr;   // debugging aid: force the plain-load path
+    const int use_tma = (!no_tma && (w % 16) == 0 && w >= BIP && h >= 8 && ((uintptr_t)gray % 16) == 0 &&
+                         alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, gray, dims, strides, box))
+                            ? 1 : 0;
+    if (flags & ALVA_ORB_FMA) orb_blur_kernel<true><<<grid, 256, 0, ctx->stream>>>(tmap, use_tma, gray, blurred, w, h);
+    else orb_blur_kernel<false><<<grid, 256, 0, ctx->stream>>>(tmap, use_tma, gray, blurred, w, h);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
 }

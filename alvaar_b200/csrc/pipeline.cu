@@ -72,7 +72,7 @@ struct alva_pipeline {
     // pyramid, derivative and blur kernels, which do not depend on it; joined before the descriptors
     alva_ctx* sel_ctx = nullptr;
     cudaStream_t sel_stream = nullptr;
-    cudaEvent_t sel_fork = nullptr, sel_join = nullptr;
+    cudaEvent_t sel_fork = nullptr, sel_join = nullptr, pyr_join = nullptr;
     alva_ctx* ba_ctx = nullptr;
     cudaStream_t ba_stream = nullptr;
     cudaEvent_t ba_fork = nullptr, ba_join = nullptr;
@@ -98,6 +98,7 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (p->sel_stream) { cudaStreamSynchronize(p->sel_stream); cudaStreamDestroy(p->sel_stream); }
     if (p->sel_fork) cudaEventDestroy(p->sel_fork);
     if (p->sel_join) cudaEventDestroy(p->sel_join);
+    if (p->pyr_join) cudaEventDestroy(p->pyr_join);
     if (p->ba_ctx) { alva_ctx_destroy(p->ba_ctx); p->ba_ctx = nullptr; }
     if (p->ba_stream) { cudaStreamSynchronize(p->ba_stream); cudaStreamDestroy(p->ba_stream); }
     if (p->ba_fork) cudaEventDestroy(p->ba_fork);
@@ -167,6 +168,7 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
     if (cudaStreamCreateWithFlags(&p->sel_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->sel_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->sel_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->pyr_join, cudaEventDisableTiming) != cudaSuccess ||
         !(p->sel_ctx = alva_ctx_create(ctx->device, (void*)p->sel_stream))) {
         alva_set_error("alva_pipeline_create: selection stream setup failed");
         alva_pipeline_destroy(p);
@@ -295,17 +297,19 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
         ALVA_LAUNCH_CHECK(sc);
     }
     ALVA_CUDA(cudaEventRecord(p->sel_join, ss));
-    ctx->launches += sc->launches - sel_before;
-    // 1b. rest of the pyramid + derivative levels (main stream, concurrent with the selection)
-    if (int e = alva_k_pyrdown(ctx, l1, l2, p->w1, p->h1, nf)) return e;
-    if (int e = alva_k_pyrdown(ctx, l2, l3, p->w2, p->h2, nf)) return e;
+    // 1b. rest of the pyramid + derivative levels: bandwidth-bound, nothing in this step reads them, so they follow the
+    // selection on the side stream and overlap the ALU-bound descriptor / matching kernels on the main stream
+    if (int e = alva_k_pyrdown(sc, l1, l2, p->w1, p->h1, nf)) return e;
+    if (int e = alva_k_pyrdown(sc, l2, l3, p->w2, p->h2, nf)) return e;
     if (c.derivatives) {   // the derivative pyramid the KLT tracker reads (buildOpticalFlowPyramid withDerivatives)
         const uint8_t* srcs[4] = {l0, l1, l2, l3};
         int16_t* dsts[4] = {p->d0 + F * w * h * 2, p->d1 + F * p->w1 * p->h1 * 2, p->d2 + F * p->w2 * p->h2 * 2,
                             p->d3 + F * p->w3 * p->h3 * 2};
         const int ws[4] = {w, p->w1, p->w2, p->w3}, hs[4] = {h, p->h1, p->h2, p->h3};
-        if (int e = alva_scharr_levels_launch(ctx, 4, srcs, dsts, ws, hs, nf)) return e;
+        if (int e = alva_scharr_levels_launch(sc, 4, srcs, dsts, ws, hs, nf)) return e;
     }
+    ALVA_CUDA(cudaEventRecord(p->pyr_join, ss));
+    ctx->launches += sc->launches - sel_before;
     // 3. ORB
     if (int e = alva_k_orb_blur(ctx, l0, blur, w, h, nf, c.orb_flags & ALVA_ORB_FMA)) return e;
     ALVA_CUDA(cudaStreamWaitEvent(st, p->sel_join, 0));
@@ -317,6 +321,7 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
         if (int e = alva_k_hamming_knn2_batch(ctx, p->desc + F * p->fcap * 32, selcounts, nf, p->fcap, p->map, c.map_size,
                                               p->matches + F * p->fcap * 4))
             return e;
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->pyr_join, 0));   // the step is complete only with its pyramid
     return 0;
 }
 

@@ -56,6 +56,7 @@ _OPTIONAL = {
     "alva_k_orb_blur": [_vp, _vp, _vp, _i32, _i32, _i32, _i32],
     "alva_k_orb_describe": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "alva_k_hamming_knn2": [_vp, _vp, _i32, _vp, _i32, _vp],
+    "alva_k_hamming_knn2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_scharr": [_vp, _vp, _vp, _i32, _i32, _i32],
     "alva_k_harris": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
@@ -163,6 +164,9 @@ class Context:
 
     def scharr(self, gray, deriv, w, h, nframes=1):
         self._chk(self.L.alva_k_scharr(self.h, _ptr(gray), _ptr(deriv), w, h, nframes))
+
+    def hamming_knn2_batch(self, q, counts, nbatch, qcap, t, nt, out):
+        self._chk(self.L.alva_k_hamming_knn2_batch(self.h, _ptr(q), _ptr(counts), nbatch, qcap, _ptr(t), nt, _ptr(out)))
 
     def harris(self, gray, w, h, nframes, pts, npts_per_frame, npts, resp):
         self._chk(self.L.alva_k_harris(self.h, _ptr(gray), w, h, nframes, _ptr(pts), _ptr(npts_per_frame), npts, _ptr(resp)))

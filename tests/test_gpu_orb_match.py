@@ -16,7 +16,7 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
 
-@pytest.mark.parametrize("w,h", [(1280, 720), (641, 479), (64, 64), (130, 35)])
+@pytest.mark.parametrize("w,h", [(1280, 720), (641, 479), (64, 64), (130, 35), (256, 100), (176, 64), (1296, 130), (160, 8)])
 @pytest.mark.parametrize("fma", [0, 1])
 def test_orb_blur(gpu_ctx, oracle, w, h, fma):
     img = synth.crop(w, h, 11, 13)
