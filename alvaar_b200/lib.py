@@ -59,6 +59,8 @@ _OPTIONAL = {
     "alva_k_hamming_knn2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_scharr": [_vp, _vp, _vp, _i32, _i32, _i32],
+    "alva_k_klt_lk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.c_double, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
+    "alva_k_klt_fb": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp, _i32, _vp],
     "alva_k_harris": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "alva_k_orb_detect": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32],
     "alva_k_ba_solve": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i32, _vp],
@@ -164,6 +166,26 @@ class Context:
 
     def scharr(self, gray, deriv, w, h, nframes=1):
         self._chk(self.L.alva_k_scharr(self.h, _ptr(gray), _ptr(deriv), w, h, nframes))
+
+    @staticmethod
+    def _ptr_table(levels):
+        """host array of device pointers (one per pyramid level)"""
+        return (C.c_void_p * len(levels))(*[t.data_ptr() for t in levels])
+
+    def klt_lk(self, prev_img, prev_der, cur_img, w, h, nframes, levels, pts, nxt, npts, status, err=None, win=9,
+               max_count=30, epsilon=0.01, use_initial=True, npts_per_frame=None):
+        """cv::calcOpticalFlowPyrLK on prebuilt pyramids (lists of per-level tensors) -- see alva_k_klt_lk."""
+        self._chk(self.L.alva_k_klt_lk(self.h, self._ptr_table(prev_img), self._ptr_table(prev_der), self._ptr_table(cur_img),
+                                       w, h, nframes, len(prev_img) - 1, levels, win, max_count, epsilon,
+                                       1 if use_initial else 0, _ptr(pts), _ptr(nxt), _ptr(npts_per_frame), npts,
+                                       _ptr(status), _ptr(err)))
+
+    def klt_fb(self, prev_img, prev_der, cur_img, cur_der, w, h, nframes, levels, pts, priors, npts, good, win=9,
+               error_value=30.0, max_fb_dist=0.5, npts_per_frame=None):
+        """FeatureTracker::fbKltTracking, fused -- see alva_k_klt_fb."""
+        self._chk(self.L.alva_k_klt_fb(self.h, self._ptr_table(prev_img), self._ptr_table(prev_der), self._ptr_table(cur_img),
+                                       self._ptr_table(cur_der), w, h, nframes, len(prev_img) - 1, levels, win, error_value,
+                                       max_fb_dist, _ptr(pts), _ptr(priors), _ptr(npts_per_frame), npts, _ptr(good)))
 
     def hamming_knn2_batch(self, q, counts, nbatch, qcap, t, nt, out):
         self._chk(self.L.alva_k_hamming_knn2_batch(self.h, _ptr(q), _ptr(counts), nbatch, qcap, _ptr(t), nt, _ptr(out)))

@@ -132,6 +132,30 @@ int alva_k_hamming_knn2(alva_ctx*, const uint8_t* q, int nq, const uint8_t* t, i
 int alva_k_hamming_knn2_batch(alva_ctx*, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
                               const uint8_t* t, int nt, int32_t* out);
 
+/* Pyramidal Lucas-Kanade on prebuilt pyramids: cv::calcOpticalFlowPyrLK(prevPyr, nextPyr, prevPts, nextPts, status, err,
+ * Size(win, win), levels, TermCriteria(COUNT+EPS, max_count, epsilon), [USE_INITIAL_FLOW] | LK_GET_MIN_EIGENVALS, 1e-4)
+ * (opencv video/src/lkpyramid.cpp:1238-1398, LKTrackerInvoker :183-722) -- the call FeatureTracker::fbKltTracking makes
+ * (src/slam/src/feature_tracker.cpp:35-38).  prev_img / prev_der / cur_img: HOST arrays of pyr_levels + 1 DEVICE pointers,
+ * level k = [nframes][h_k][w_k] u8 (alva_k_frontend / alva_k_pyrdown) resp. [nframes][h_k][w_k][2] int16 (alva_k_scharr),
+ * w_k = (w_{k-1} + 1) / 2; the reference's padded borders (REFLECT_101 image, constant-0 derivative) are implied.
+ * pts / next: [nframes][npts][2] float (next: initial flow in, tracked position out); npts_per_frame may be NULL;
+ * status [nframes][npts] u8, err (optional) [nframes][npts] float = min eigenvalue at level 0.  win must be 9
+ * (State::kltWinSizeWH_, src/slam/src/state.hpp:52).  Results are bit-identical to the reference's SSE float path. */
+int alva_k_klt_lk(alva_ctx*, const uint8_t* const* prev_img, const int16_t* const* prev_der, const uint8_t* const* cur_img,
+                  int w, int h, int nframes, int pyr_levels, int levels, int win, int max_count, double epsilon,
+                  int use_initial, const float* pts, float* next, const int32_t* npts_per_frame, int npts,
+                  uint8_t* status, float* err);
+
+/* FeatureTracker::fbKltTracking (src/slam/src/feature_tracker.cpp:5-111; caller VisualFrontend::kltTrackingFromMotionPrior,
+ * visual_frontend.cpp:103-243) in ONE launch: forward LK from the priors on `levels` levels (criteria 30 it / 0.01 px,
+ * system.cpp:31), the reference's gates (status, min-eig err > error_value, 1-px inBorder), backward LK on level 0 from
+ * the tracked position towards the original one, and the |p - back| > max_fb_dist gate.  priors [nframes][npts][2] in/out
+ * (written for every live point, like the reference's priorKeypoints); good [nframes][npts] u8 = keypointStatus. */
+int alva_k_klt_fb(alva_ctx*, const uint8_t* const* prev_img, const int16_t* const* prev_der, const uint8_t* const* cur_img,
+                  const int16_t* const* cur_der, int w, int h, int nframes, int pyr_levels, int levels, int win,
+                  float error_value, float max_fb_dist, const float* pts, float* priors, const int32_t* npts_per_frame,
+                  int npts, uint8_t* good);
+
 /* Local bundle adjustment, batched over nprob independent problems of identical dimensions
  * (Optimizer::localBA, src/slam/src/optimizer.cpp:4-531, solved the way ceres::Solve does with the reference's
  * options: SPARSE_SCHUR elimination of the inverse depths, Levenberg-Marquardt, Huber(huber_delta), Jacobi scaling,

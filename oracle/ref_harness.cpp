@@ -17,6 +17,7 @@
 #include <sophus/se3.hpp>
 #include <ceres/ceres.h>
 #include "ceres_parametrization.hpp"   // /root/reference/src/slam/src (AlvaAR's own cost functors)
+#include "feature_tracker.hpp"         // /root/reference/src/slam/src (AlvaAR's own forward-backward KLT wrapper)
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -296,6 +297,47 @@ int ref_ba_local(const double* calib, double* poses, const uint8_t* pose_const, 
 // SE3Parameterization::Plus (src/slam/src/ceres_parametrization.hpp:224-240)
 void ref_se3_plus(const double* x, const double* delta, double* out) {
     SE3Parameterization p; p.Plus(x, delta, out);
+}
+
+// VisualFrontend::preprocessImage + kltTrackingFromMotionPrior's tracker call, unmodified reference code:
+//   cv::buildOpticalFlowPyramid(prev / cur, win, pyr_levels)                 src/slam/src/visual_frontend.cpp:696
+//   FeatureTracker(30, 0.01).fbKltTracking(prevPyr, curPyr, win, levels, error_value, max_fb_dist, pts, priors, status)
+//                                                                            src/slam/src/feature_tracker.cpp:5-111
+// pts [n][2] previous positions; priors [n][2] in/out; good [n] out.  Returns the pyramid's max level.
+int ref_fb_klt(const uint8_t* prev, const uint8_t* cur, int w, int h, int win, int pyr_levels, int levels,
+               float error_value, float max_fb_dist, const float* pts, float* priors, uint8_t* good, int n) {
+    cv::Mat gp(h, w, CV_8UC1, (void*)prev), gc(h, w, CV_8UC1, (void*)cur);
+    std::vector<cv::Mat> pp, pc;
+    int got = cv::buildOpticalFlowPyramid(gp, pp, cv::Size(win, win), pyr_levels);
+    cv::buildOpticalFlowPyramid(gc, pc, cv::Size(win, win), pyr_levels);
+    std::vector<cv::Point2f> p(n), q(n);
+    for (int i = 0; i < n; i++) { p[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]); q[i] = cv::Point2f(priors[2 * i], priors[2 * i + 1]); }
+    std::vector<bool> st;
+    FeatureTracker tracker(30, 0.01f);
+    tracker.fbKltTracking(pp, pc, win, levels, error_value, max_fb_dist, p, q, st);
+    for (int i = 0; i < n; i++) {
+        priors[2 * i] = q[i].x; priors[2 * i + 1] = q[i].y;
+        good[i] = (i < (int)st.size() && st[i]) ? 1 : 0;
+    }
+    return got;
+}
+
+// cv::calcOpticalFlowPyrLK on prebuilt pyramids with the flags AlvaAR uses (feature_tracker.cpp:35-38):
+// USE_INITIAL_FLOW (optional) + LK_GET_MIN_EIGENVALS, TermCriteria(COUNT+EPS, max_count, epsilon).
+int ref_klt_lk(const uint8_t* prev, const uint8_t* cur, int w, int h, int win, int pyr_levels, int levels, int max_count,
+               double epsilon, int use_initial, const float* pts, float* next, uint8_t* status, float* err, int n) {
+    cv::Mat gp(h, w, CV_8UC1, (void*)prev), gc(h, w, CV_8UC1, (void*)cur);
+    std::vector<cv::Mat> pp, pc;
+    int got = cv::buildOpticalFlowPyramid(gp, pp, cv::Size(win, win), pyr_levels);
+    cv::buildOpticalFlowPyramid(gc, pc, cv::Size(win, win), pyr_levels);
+    std::vector<cv::Point2f> p(n), q(n);
+    for (int i = 0; i < n; i++) { p[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]); q[i] = cv::Point2f(next[2 * i], next[2 * i + 1]); }
+    std::vector<uchar> st; std::vector<float> er;
+    cv::calcOpticalFlowPyrLK(pp, pc, p, q, st, er, cv::Size(win, win), levels,
+                             cv::TermCriteria(cv::TermCriteria::COUNT + cv::TermCriteria::EPS, max_count, epsilon),
+                             (use_initial ? cv::OPTFLOW_USE_INITIAL_FLOW : 0) + cv::OPTFLOW_LK_GET_MIN_EIGENVALS);
+    for (int i = 0; i < n; i++) { next[2 * i] = q[i].x; next[2 * i + 1] = q[i].y; status[i] = st[i]; err[i] = er[i]; }
+    return got;
 }
 
 }  // extern "C"
