@@ -59,6 +59,8 @@ _OPTIONAL = {
     "alva_k_hamming_knn2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_scharr": [_vp, _vp, _vp, _i32, _i32, _i32],
+    "alva_k_p3p_lmeds": [_vp, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_uint32, _vp, _vp, _vp],
+    "alva_k_pnp": [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _i32, _i32, _i32, _vp, _vp],
     "alva_k_klt_lk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.c_double, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "alva_k_klt_fb": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp, _i32, _vp],
     "alva_k_harris": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
@@ -186,6 +188,19 @@ class Context:
         self._chk(self.L.alva_k_klt_fb(self.h, self._ptr_table(prev_img), self._ptr_table(prev_der), self._ptr_table(cur_img),
                                        self._ptr_table(cur_der), w, h, nframes, len(prev_img) - 1, levels, win, error_value,
                                        max_fb_dist, _ptr(pts), _ptr(priors), _ptr(npts_per_frame), npts, _ptr(good)))
+
+    def p3p_lmeds(self, nprob, cap, bvs, wpts, counts, Twc_out, outlier, info=None, max_iter=100, err_px=3.0, fx=1.0, fy=1.0,
+                  seed=12345):
+        """MultiViewGeometry::p3pRansac (Kneip P3P + LMedS), batched -- see alva_k_p3p_lmeds."""
+        self._chk(self.L.alva_k_p3p_lmeds(self.h, nprob, cap, _ptr(bvs), _ptr(wpts), _ptr(counts), max_iter, err_px, fx, fy,
+                                          seed, _ptr(Twc_out), _ptr(outlier), _ptr(info)))
+
+    def pnp(self, nprob, cap, K, uv, X, counts, poses, outlier, summary, huber_delta, chi2_thr, max_iter=5, use_robust=True,
+            apply_l2=True):
+        """MultiViewGeometry::ceresPnP, batched -- see alva_k_pnp."""
+        self._chk(self.L.alva_k_pnp(self.h, nprob, cap, _ptr(K), _ptr(uv), _ptr(X), _ptr(counts), _ptr(poses), huber_delta,
+                                    chi2_thr, max_iter, 1 if use_robust else 0, 1 if apply_l2 else 0, _ptr(outlier),
+                                    _ptr(summary)))
 
     def hamming_knn2_batch(self, q, counts, nbatch, qcap, t, nt, out):
         self._chk(self.L.alva_k_hamming_knn2_batch(self.h, _ptr(q), _ptr(counts), nbatch, qcap, _ptr(t), nt, _ptr(out)))

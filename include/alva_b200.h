@@ -156,6 +156,33 @@ int alva_k_klt_fb(alva_ctx*, const uint8_t* const* prev_img, const int16_t* cons
                   float error_value, float max_fb_dist, const float* pts, float* priors, const int32_t* npts_per_frame,
                   int npts, uint8_t* good);
 
+/* Per-frame pose, step 1: MultiViewGeometry::p3pRansac(observations, wPoints, max_iter, err_px, optimize = false, doRandom,
+ * fx, fy, Twc, outliers) (src/slam/src/multi_view_geometry.cpp:24-127; caller VisualFrontend::computePose,
+ * visual_frontend.cpp:299-312) = Kneip P3P inside OpenGV's Least-Median-of-Squares loop (always max_iter successful draws,
+ * sample size 4, score = median of squared bearing distances, inliers: distance <= 1 - cos(atan(err_px / focal))), batched
+ * over nprob independent problems.  DEVICE pointers, FP64: bvs / wpts [nprob][cap][3] (unit bearing vectors / world points;
+ * only the first counts[p] are live, counts may be NULL, cap <= 4096).  seed: the sampler's std::mt19937 seed -- the
+ * reference uses 12345 when State::multiViewRandomEnabled_ is false and the clock otherwise (state.hpp:67).
+ * Twc_out [nprob][12]: camera-to-world [R | t], 3x4 row-major (unspecified when the problem fails); outlier [nprob][cap]
+ * (1 = outlier / dead slot); info (optional) [nprob][4] = {success (>= 5 inliers and R orthogonal: what p3pRansac returns),
+ * #inliers, best median, #draws}. */
+int alva_k_p3p_lmeds(alva_ctx*, int nprob, int cap, const double* bvs, const double* wpts, const int32_t* counts,
+                     int max_iter, float err_px, float fx, float fy, uint32_t seed, double* Twc_out, uint8_t* outlier,
+                     double* info);
+
+/* Per-frame pose, step 2: MultiViewGeometry::ceresPnP (src/slam/src/multi_view_geometry.cpp:129-223; functor
+ * DirectSE3::ReprojectionErrorSE3, ceres_parametrization.cpp:96-155): Levenberg-Marquardt on the 6-dof pose with
+ * Huber(huber_delta) (use_robust), residuals with chi2 > chi2_thr or non-positive depth at their last evaluation flagged as
+ * outliers, and (apply_l2) a second, non-robust solve without them.  Solved the way ceres::Solve does with the reference's
+ * options (<= max_iter iterations, function_tolerance 1e-3, Jacobi scaling; the 5 ms wall-clock cap is lifted), batched
+ * over nprob problems, every decision on the device.  K [nprob][4] = fx fy cx cy; uv [nprob][cap][2] undistorted pixels;
+ * X [nprob][cap][3]; poses [nprob][7] = [t, q(x,y,z,w)] camera-to-world IN/OUT (left untouched when every point is an
+ * outlier, as in the reference); outlier [nprob][cap]; summary [nprob][12] = {initial cost, final cost, #successful,
+ * #iterations, termination} of solve 1, the same of solve 2 (zeros if skipped), return value of ceresPnP (0/1), #outliers. */
+int alva_k_pnp(alva_ctx*, int nprob, int cap, const double* K, const double* uv, const double* X, const int32_t* counts,
+               double* poses, double huber_delta, double chi2_thr, int max_iter, int use_robust, int apply_l2,
+               uint8_t* outlier, double* summary);
+
 /* Local bundle adjustment, batched over nprob independent problems of identical dimensions
  * (Optimizer::localBA, src/slam/src/optimizer.cpp:4-531, solved the way ceres::Solve does with the reference's
  * options: SPARSE_SCHUR elimination of the inverse depths, Levenberg-Marquardt, Huber(huber_delta), Jacobi scaling,

@@ -50,17 +50,29 @@ EOS
     -DMINIGLOG=ON -DGFLAGS=OFF -DCERES_THREADING_MODEL=NO_THREADS -DCMAKE_POSITION_INDEPENDENT_CODE=ON > cfg.log 2>&1
   ninja -j"$J" install > build.log 2>&1
 fi
-INC="-I$REF/src/slam/src -I$P/ocv_install/include/opencv4 -I$REF/src/libs/eigen -I$REF/src/libs/Sophus \
+# OpenGV 1.0 (P3P-Kneip / LMedS for the per-frame pose): its own CMake flags (-march=native -O3) produce a library that
+# crashes under gcc 13, so the sources are compiled directly, in place, with plain -O2.
+if [ ! -f "$P/opengv/libopengv.a" ]; then
+  mkdir -p "$P/opengv/obj"
+  GV="$REF/src/libs/opengv"
+  find "$GV/src" -name '*.cpp' | grep -v -i -e python -e matlab | while read -r f; do
+    o="$P/opengv/obj/$(echo "${f#$GV/src/}" | tr '/' '_' | sed 's/\.cpp$/.o/')"
+    echo "g++ -std=c++17 -O2 -w -fPIC -fno-strict-aliasing -I$GV/include -I$REF/src/libs/eigen -I$REF/src/libs/eigen/unsupported -c $f -o $o"
+  done | xargs -P "$J" -I{} sh -c '{}'
+  ar rcs "$P/opengv/libopengv.a" "$P"/opengv/obj/*.o
+fi
+INC="-I$REF/src/slam/src -I$REF/src/libs/opengv/include -I$P/ocv_install/include/opencv4 -I$REF/src/libs/eigen -I$REF/src/libs/Sophus \
  -I$P/ceres_install/include -I$P/ceres_install/include/ceres/internal/miniglog"
 cd "$OUT"
 g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/ceres_parametrization.cpp" -o ceres_parametrization.o $INC
 g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/feature_tracker.cpp" -o feature_tracker.o $INC
+g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/multi_view_geometry.cpp" -o multi_view_geometry.o $INC
 g++ -std=c++17 -O2 -w -fPIC -c "$HERE/ref_harness.cpp" -o ref_harness.o $INC
-g++ -shared -o libalva_ref.so ref_harness.o ceres_parametrization.o feature_tracker.o \
+g++ -shared -o libalva_ref.so ref_harness.o ceres_parametrization.o feature_tracker.o multi_view_geometry.o \
   -Wl,--start-group "$P"/ocv_install/lib/libopencv_video.a "$P"/ocv_install/lib/libopencv_calib3d.a \
   "$P"/ocv_install/lib/libopencv_features2d.a "$P"/ocv_install/lib/libopencv_flann.a \
   "$P"/ocv_install/lib/libopencv_imgproc.a "$P"/ocv_install/lib/libopencv_core.a \
-  "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a -Wl,--end-group \
+  "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a "$P"/opengv/libopengv.a -Wl,--end-group \
   -lpthread -ldl -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL
-rm -f ref_harness.o ceres_parametrization.o feature_tracker.o
+rm -f ref_harness.o ceres_parametrization.o feature_tracker.o multi_view_geometry.o
 echo "built $OUT/libalva_ref.so"

@@ -18,6 +18,7 @@
 #include <ceres/ceres.h>
 #include "ceres_parametrization.hpp"   // /root/reference/src/slam/src (AlvaAR's own cost functors)
 #include "feature_tracker.hpp"         // /root/reference/src/slam/src (AlvaAR's own forward-backward KLT wrapper)
+#include "multi_view_geometry.hpp"     // /root/reference/src/slam/src (P3P-LMedS via OpenGV, Ceres PnP)
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -338,6 +339,41 @@ int ref_klt_lk(const uint8_t* prev, const uint8_t* cur, int w, int h, int win, i
                              (use_initial ? cv::OPTFLOW_USE_INITIAL_FLOW : 0) + cv::OPTFLOW_LK_GET_MIN_EIGENVALS);
     for (int i = 0; i < n; i++) { next[2 * i] = q[i].x; next[2 * i + 1] = q[i].y; status[i] = st[i]; err[i] = er[i]; }
     return got;
+}
+
+// MultiViewGeometry::p3pRansac (src/slam/src/multi_view_geometry.cpp:24-127), unmodified, called as
+// VisualFrontend::computePose does (visual_frontend.cpp:299-312): optimize = false; doRandom = false pins the sampler's
+// seed to 12345 (SampleConsensusProblem.hpp:43-46).  bvs/wpts [n][3]; Twc_out 3x4 row-major [R | t]; outlier [n].
+int ref_p3p_lmeds(const double* bvs, const double* wpts, int n, int max_iter, float err_px, float fx, float fy,
+                  double* Twc_out, uint8_t* outlier) {
+    std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>> b(n), w(n);
+    for (int i = 0; i < n; i++) { b[i] = Eigen::Vector3d(bvs[3 * i], bvs[3 * i + 1], bvs[3 * i + 2]); w[i] = Eigen::Vector3d(wpts[3 * i], wpts[3 * i + 1], wpts[3 * i + 2]); }
+    Sophus::SE3d Twc;
+    std::vector<int> out;
+    bool ok = MultiViewGeometry::p3pRansac(b, w, max_iter, err_px, false, false, fx, fy, Twc, out);
+    memset(outlier, 0, n);
+    for (int i : out) outlier[i] = 1;
+    Eigen::Matrix3d R = Twc.rotationMatrix();
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Twc_out[4 * i + j] = R(i, j); Twc_out[4 * i + 3] = Twc.translation()[i]; }
+    return ok ? 1 : 0;
+}
+
+// MultiViewGeometry::ceresPnP (src/slam/src/multi_view_geometry.cpp:129-223), unmodified (its 5 ms wall-clock cap stays:
+// the test problems solve in well under a millisecond).  pose [t, q(x,y,z,w)] in/out; uv [n][2]; X [n][3]; outlier [n].
+int ref_pnp(const double* uv, const double* X, int n, double* pose, int max_iter, float chi2th, int use_robust, int apply_l2,
+            float fx, float fy, float cx, float cy, uint8_t* outlier) {
+    std::vector<Eigen::Vector2d, Eigen::aligned_allocator<Eigen::Vector2d>> k(n);
+    std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>> w(n);
+    for (int i = 0; i < n; i++) { k[i] = Eigen::Vector2d(uv[2 * i], uv[2 * i + 1]); w[i] = Eigen::Vector3d(X[3 * i], X[3 * i + 1], X[3 * i + 2]); }
+    Sophus::SE3d Twc(Eigen::Quaterniond(pose[6], pose[3], pose[4], pose[5]), Eigen::Vector3d(pose[0], pose[1], pose[2]));
+    std::vector<int> out;
+    bool ok = MultiViewGeometry::ceresPnP(k, w, Twc, max_iter, chi2th, use_robust != 0, apply_l2 != 0, fx, fy, cx, cy, out);
+    memset(outlier, 0, n);
+    for (int i : out) outlier[i] = 1;
+    for (int i = 0; i < 3; i++) pose[i] = Twc.translation()[i];
+    const Eigen::Quaterniond& q = Twc.unit_quaternion();
+    pose[3] = q.x(); pose[4] = q.y(); pose[5] = q.z(); pose[6] = q.w();
+    return ok ? 1 : 0;
 }
 
 }  // extern "C"
