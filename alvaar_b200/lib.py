@@ -59,6 +59,8 @@ _OPTIONAL = {
     "alva_k_hamming_knn2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp],
     "alva_h_frontend": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_scharr": [_vp, _vp, _vp, _i32, _i32, _i32],
+    "alva_k_detect_grid": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32],
+    "alva_k_corner_subpix": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32],
     "alva_k_p3p_lmeds": [_vp, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_uint32, _vp, _vp, _vp],
     "alva_k_pnp": [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _i32, _i32, _i32, _vp, _vp],
     "alva_k_klt_lk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.c_double, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -188,6 +190,15 @@ class Context:
         self._chk(self.L.alva_k_klt_fb(self.h, self._ptr_table(prev_img), self._ptr_table(prev_der), self._ptr_table(cur_img),
                                        self._ptr_table(cur_der), w, h, nframes, len(prev_img) - 1, levels, win, error_value,
                                        max_fb_dist, _ptr(pts), _ptr(priors), _ptr(npts_per_frame), npts, _ptr(good)))
+
+    def detect_grid(self, gray, w, h, nframes, cell, cur, ncur, cur_cap, roi, quality, out, out_int, counts, out_cap):
+        """FeatureExtractor::detectFeaturePoints, batched -- see alva_k_detect_grid.  roi: 4 python ints (host)."""
+        r = (C.c_int32 * 4)(*[int(v) for v in roi])
+        self._chk(self.L.alva_k_detect_grid(self.h, _ptr(gray), w, h, nframes, cell, _ptr(cur), _ptr(ncur), cur_cap, r,
+                                            _ptr(quality), _ptr(out), _ptr(out_int), _ptr(counts), out_cap))
+
+    def corner_subpix(self, gray, w, h, nframes, pts, counts, cap):
+        self._chk(self.L.alva_k_corner_subpix(self.h, _ptr(gray), w, h, nframes, _ptr(pts), _ptr(counts), cap))
 
     def p3p_lmeds(self, nprob, cap, bvs, wpts, counts, Twc_out, outlier, info=None, max_iter=100, err_px=3.0, fx=1.0, fy=1.0,
                   seed=12345):

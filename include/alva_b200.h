@@ -132,6 +132,25 @@ int alva_k_hamming_knn2(alva_ctx*, const uint8_t* q, int nq, const uint8_t* t, i
 int alva_k_hamming_knn2_batch(alva_ctx*, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
                               const uint8_t* t, int nt, int32_t* out);
 
+/* The reference's keyframe corner detector, FeatureExtractor::detectFeaturePoints(image, cell, currKeypoints, roi)
+ * (src/slam/src/feature_extractor.cpp:11-158; caller MapManager::extractKeypoints, map_manager.cpp:193-222), batched over frames:
+ * per empty grid cell, GaussianBlur 3x3 -> cornerMinEigenVal(block 3, Sobel 3) -> best and second-best maximum under a shared
+ * suppression mask (discs of radius cell/4 around the frame's current keypoints and around accepted maxima, in the
+ * reference's serial cell order), ROI and quality gates, primaries in cell order followed by secondaries, the quality
+ * adaptation x0.5 / x1.5, and cv::cornerSubPix(3x3 half-window, 30 it, 0.01).  DEVICE pointers.
+ *   gray [nframes][h][w]; cur [nframes][cur_cap][2] float pixel positions of the current keypoints, ncur [nframes] (both may
+ *   be NULL); roi (HOST) = {x, y, width, height} (CameraCalibration's border rect, 20 px); quality [nframes] double IN/OUT =
+ *   maxQuality_ (0.001 at start, system.cpp:29); out [nframes][out_cap][2] float sub-pixel corners; out_int (optional)
+ *   [nframes][out_cap][2] int32 the integer maxima before refinement; counts [nframes] (true count; only out_cap are stored).
+ * 8 <= cell <= 64 (the reference uses 40).  Bit-identical to the reference run with cv::setNumThreads(1). */
+int alva_k_detect_grid(alva_ctx*, const uint8_t* gray, int w, int h, int nframes, int cell, const float* cur,
+                       const int32_t* ncur, int cur_cap, const int32_t* roi, double* quality, float* out, int32_t* out_int,
+                       int32_t* counts, int out_cap);
+
+/* cv::cornerSubPix(image, pts, Size(3, 3), Size(-1, -1), TermCriteria(EPS + MAX_ITER, 30, 0.01)) alone
+ * (imgproc/src/cornersubpix.cpp:44-160; feature_extractor.cpp:148-155): pts [nframes][cap][2] IN/OUT, counts [nframes]. */
+int alva_k_corner_subpix(alva_ctx*, const uint8_t* gray, int w, int h, int nframes, float* pts, const int32_t* counts, int cap);
+
 /* Pyramidal Lucas-Kanade on prebuilt pyramids: cv::calcOpticalFlowPyrLK(prevPyr, nextPyr, prevPts, nextPts, status, err,
  * Size(win, win), levels, TermCriteria(COUNT+EPS, max_count, epsilon), [USE_INITIAL_FLOW] | LK_GET_MIN_EIGENVALS, 1e-4)
  * (opencv video/src/lkpyramid.cpp:1238-1398, LKTrackerInvoker :183-722) -- the call FeatureTracker::fbKltTracking makes

@@ -18,6 +18,7 @@
 #include <ceres/ceres.h>
 #include "ceres_parametrization.hpp"   // /root/reference/src/slam/src (AlvaAR's own cost functors)
 #include "feature_tracker.hpp"         // /root/reference/src/slam/src (AlvaAR's own forward-backward KLT wrapper)
+#include "feature_extractor.hpp"       // /root/reference/src/slam/src (grid Shi-Tomasi detector)
 #include "multi_view_geometry.hpp"     // /root/reference/src/slam/src (P3P-LMedS via OpenGV, Ceres PnP)
 #include <cstdint>
 #include <cstring>
@@ -374,6 +375,39 @@ int ref_pnp(const double* uv, const double* X, int n, double* pose, int max_iter
     const Eigen::Quaterniond& q = Twc.unit_quaternion();
     pose[3] = q.x(); pose[4] = q.y(); pose[5] = q.z(); pose[6] = q.w();
     return ok ? 1 : 0;
+}
+
+// FeatureExtractor(max_quality).detectFeaturePoints(image, cell, currKeypoints, roi)  -- unmodified reference code
+// (src/slam/src/feature_extractor.cpp:11-158), cv::setNumThreads(1) through ref_config.  The adapted maxQuality_ is private;
+// it is recovered by replaying the reference's own rule (:138-145) on the returned count -- n_occ is returned for that.
+// cur [ncur][2]; roi {x, y, w, h}; out [cap][2] (sub-pixel positions).  Returns the number of points.
+int ref_detect_points(const uint8_t* gray, int w, int h, int cell, const float* cur, int ncur, const int* roi,
+                      double max_quality, float* out, int cap) {
+    cv::Mat g(h, w, CV_8UC1, (void*)gray);
+    std::vector<cv::Point2f> c(ncur);
+    for (int i = 0; i < ncur; i++) c[i] = cv::Point2f(cur[2 * i], cur[2 * i + 1]);
+    FeatureExtractor fe(max_quality);
+    std::vector<cv::Point2f> pts = fe.detectFeaturePoints(g, cell, c, cv::Rect(roi[0], roi[1], roi[2], roi[3]));
+    for (int i = 0; i < (int)pts.size() && i < cap; i++) { out[2 * i] = pts[i].x; out[2 * i + 1] = pts[i].y; }
+    return (int)pts.size();
+}
+
+// the cell pipeline's intermediate, for pinning the float stages: GaussianBlur(3x3) on the ROI of the full image followed by
+// cornerMinEigenVal(block 3, Sobel 3), exactly as feature_extractor.cpp:64-70 calls them.  hmap [cell][cell].
+void ref_min_eig_cell(const uint8_t* gray, int w, int h, int x0, int y0, int cell, float* hmap, uint8_t* blurred) {
+    cv::Mat g(h, w, CV_8UC1, (void*)gray), f, m;
+    cv::GaussianBlur(g(cv::Rect(x0, y0, cell, cell)), f, cv::Size(3, 3), 0.);
+    cv::cornerMinEigenVal(f, m, 3, 3);
+    for (int y = 0; y < cell; y++) { memcpy(hmap + (size_t)y * cell, m.ptr<float>(y), sizeof(float) * cell); if (blurred) memcpy(blurred + (size_t)y * cell, f.ptr(y), cell); }
+}
+
+// cv::cornerSubPix(image, pts, Size(win, win), Size(-1, -1), TermCriteria(EPS + MAX_ITER, max_iter, eps))
+void ref_corner_subpix(const uint8_t* gray, int w, int h, float* pts, int n, int win, int max_iter, double eps) {
+    cv::Mat g(h, w, CV_8UC1, (void*)gray);
+    std::vector<cv::Point2f> p(n);
+    for (int i = 0; i < n; i++) p[i] = cv::Point2f(pts[2 * i], pts[2 * i + 1]);
+    cv::cornerSubPix(g, p, cv::Size(win, win), cv::Size(-1, -1), cv::TermCriteria(cv::TermCriteria::EPS + cv::TermCriteria::MAX_ITER, max_iter, eps));
+    for (int i = 0; i < n; i++) { pts[2 * i] = p[i].x; pts[2 * i + 1] = p[i].y; }
 }
 
 }  // extern "C"
