@@ -21,6 +21,7 @@
 #include <float.h>
 #include <math.h>
 #include <vector>
+#include <stdlib.h>
 
 namespace {
 
@@ -37,6 +38,7 @@ struct DetectParams {
     int hw[MAX_RADIUS + 1];  // cv::circle disk half-widths per |row offset|
     uint8_t* occ;            // [nframes][(nch+1)*(ncw+1)]
     float* hmap;             // [nframes][ncells][cs*cs]
+    float4* cand;            // [nframes][ncells]: {best, index, second best (outside the best's disc), index} under the static mask
     uint32_t* mask;          // [nframes][h][mw] bit = 1: allowed
     int mw;
     double* quality;         // [nframes] in/out
@@ -45,6 +47,7 @@ struct DetectParams {
     int32_t* counts;         // [nframes]
     int out_cap;
     float sp_mask[49];       // cornerSubPix Gaussian window (host expf)
+    int32_t* dbg;            // optional [8] counters (ALVA_DETECT_DEBUG): why the select kernel re-scanned a cell
 };
 
 __device__ __forceinline__ int refl(int p, int n) {
@@ -141,6 +144,9 @@ __global__ void __launch_bounds__(256) detect_mineig_kernel(const DetectParams P
     }
     __syncthreads();
     float* hmap = P.hmap + ((size_t)f * P.nch * P.ncw + cell) * cs * cs;
+    float* hs = rd;   // the row-filter buffer is free again: keep the masked values for the two arg-max passes
+    const uint32_t* mask = P.mask + (size_t)f * P.h * P.mw;
+    __syncthreads();
     for (int i = tid; i < cs * cs; i += blockDim.x) {
         const int y = i / cs, x = i - y * cs;
         double A = 0, B = 0, C = 0;
@@ -154,65 +160,171 @@ __global__ void __launch_bounds__(256) detect_mineig_kernel(const DetectParams P
             }
         const float a = (float)A * 0.5f, b = (float)B, cc = (float)C * 0.5f;
         const float t = a - cc;
-        hmap[i] = (a + cc) - __fsqrt_rn(b * b + t * t);
+        const float v = (a + cc) - __fsqrt_rn(b * b + t * t);
+        const int X = x0 + x, Y = y0 + y;
+        const bool allowed = (mask[(size_t)Y * P.mw + (X >> 5)] >> (X & 31)) & 1u;   // static mask: discs of the current keypoints
+        hs[i] = allowed ? v : 0.0f;
+        hmap[i] = hs[i];   // stored already multiplied by the static mask (hMap.mul(mask), feature_extractor.cpp:77)
+    }
+    __syncthreads();
+    // best and second-best (outside the best's disc) under the static mask, first index on ties -- what the reference's two
+    // minMaxLoc calls return whenever no neighbouring cell's detection reaches into this cell (checked in the select kernel)
+    __shared__ float red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int s_p1;
+    float4 res;
+    for (int pass = 0; pass < 2; pass++) {
+        const int p1 = pass ? s_p1 : -1;
+        const int p1y = p1 >= 0 ? p1 / cs : 0, p1x = p1 >= 0 ? p1 - p1y * cs : 0;
+        float best = -FLT_MAX;
+        int bidx = 0x7fffffff;
+        for (int i = tid; i < cs * cs; i += blockDim.x) {
+            float v = hs[i];
+            if (pass) {
+                const int y = i / cs, x = i - y * cs;
+                const int ady = abs(y - p1y), adx = abs(x - p1x);
+                if (ady <= P.rad && adx <= P.hw[ady]) v = 0.0f;
+            }
+            if (v > best) { best = v; bidx = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = bidx; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < 8; k++)
+                if (red_v[k] > best || (red_v[k] == best && red_i[k] < bidx)) { best = red_v[k]; bidx = red_i[k]; }
+            if (pass == 0) { s_p1 = bidx; res.x = best; res.y = __int_as_float(bidx); }
+            else { res.z = best; res.w = __int_as_float(bidx); P.cand[(size_t)f * P.nch * P.ncw + cell] = res; }
+        }
+        __syncthreads();
     }
 }
 
-// ---- D2: serial-order selection by wavefront (one CTA per frame, one warp per cell of the current step)
+// ---- D2: serial-order selection by wavefront (one CTA per frame, one warp per cell of the current step).
+// Everything a cell needs in the common case is in shared memory: its two pre-computed maxima and the detections of the
+// four neighbours processed before it.  Only when a neighbour's disc covers a pre-computed maximum is the cell re-scanned
+// (static bit mask AND the neighbouring / own discs); nothing is written to HBM until the final list.
 __global__ void __launch_bounds__(512) detect_select_kernel(const DetectParams P) {
-    extern __shared__ int32_t sel[];      // prim[ncells], sec[ncells]  (x | y << 16, -1 = none)
+    extern __shared__ int32_t sel[];      // prim[ncells], sec[ncells]  (x | y << 16, -1 = none), then float4 cand[ncells], occ bytes
     __shared__ int s_nocc;
+    __shared__ int shw[MAX_RADIUS + 1];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     const int cs = P.cs, ncells = P.nch * P.ncw;
+    if (tid <= MAX_RADIUS) shw[tid] = P.hw[tid];
     int32_t* prim = sel;
     int32_t* sec = sel + ncells;
+    float4* cand = reinterpret_cast<float4*>(sel + 2 * ncells + ((2 * ncells) & 3 ? 4 - ((2 * ncells) & 3) : 0));
+    uint8_t* socc = reinterpret_cast<uint8_t*>(cand + ncells);
     const uint8_t* occ = P.occ + (size_t)f * (P.nch + 1) * (P.ncw + 1);
-    uint32_t* mask = P.mask + (size_t)f * P.h * P.mw;
     const double q = P.quality[f];
-    for (int i = tid; i < 2 * ncells; i += blockDim.x) sel[i] = -1;
-    if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < ncells; i++) n += occ[(i / P.ncw) * (P.ncw + 1) + (i % P.ncw)] ? 1 : 0;
-        s_nocc = n;
+    if (tid == 0) s_nocc = 0;
+    __syncthreads();
+    int myocc = 0;
+    for (int i = tid; i < ncells; i += blockDim.x) {
+        const int r = i / P.ncw, c = i - r * P.ncw;
+        const uint8_t o = occ[r * (P.ncw + 1) + c];
+        const int x0 = c * cs, y0 = r * cs;
+        const bool searched = !o && (x0 + cs < P.w - 1 && y0 + cs < P.h - 1);
+        socc[i] = o ? 1 : (searched ? 0 : 2);
+        myocc += o ? 1 : 0;
+        prim[i] = -1; sec[i] = -1;
+        if (searched) cand[i] = P.cand[(size_t)f * ncells + i];
     }
+    if (myocc) atomicAdd(&s_nocc, myocc);
     __syncthreads();
     const int nsteps = (P.ncw - 1) + 2 * (P.nch - 1) + 1;
     for (int t = 0; t < nsteps; t++) {
-        // rows r with 0 <= t - 2r < ncw
         const int rlo = max(0, (t - (P.ncw - 1) + 1) / 2), rhi = min(P.nch - 1, t / 2);
         for (int r = rlo + wid; r <= rhi; r += nw) {
             const int c = t - 2 * r;
             if (c < 0 || c >= P.ncw) continue;
             const int cell = r * P.ncw + c;
-            if (occ[r * (P.ncw + 1) + c]) continue;
+            if (socc[cell]) continue;
             const int x0 = c * cs, y0 = r * cs;
-            if (!(x0 + cs < P.w - 1 && y0 + cs < P.h - 1)) continue;
-            const float* hmap = P.hmap + ((size_t)f * ncells + cell) * cs * cs;
-            for (int pass = 0; pass < 2; pass++) {
-                float best = -FLT_MAX;
-                int bidx = 0x7fffffff;
-                for (int e = lane; e < cs * cs; e += 32) {
-                    const int y = e / cs, x = e - y * cs;
-                    const int X = x0 + x, Y = y0 + y;
-                    const bool allowed = (mask[(size_t)Y * P.mw + (X >> 5)] >> (X & 31)) & 1u;
-                    const float v = allowed ? hmap[e] : 0.0f;
-                    if (v > best) { best = v; bidx = e; }
-                }
+            // discs that can reach into this cell: detections of W, NW, N, NE (processed in earlier steps), later the own primary.
+            // Fixed register slots (an absent detection sits far away), half-widths from shared memory: the test is on the
+            // wavefront's critical path.
+            int dcx[9], dcy[9];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-                    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+            for (int k = 0; k < 4; k++) {
+                const int rr = r + (k == 0 ? 0 : -1), c2 = c + (k == 0 ? -1 : k - 2);
+                const bool in = !(rr < 0 || c2 < 0 || c2 >= P.ncw);
+#pragma unroll
+                for (int which = 0; which < 2; which++) {
+                    const int32_t v = in ? (which ? sec : prim)[rr * P.ncw + c2] : -1;
+                    dcx[2 * k + which] = v >= 0 ? (v & 0xffff) : -30000;
+                    dcy[2 * k + which] = v >= 0 ? (v >> 16) : -30000;
+                }
+            }
+            dcx[8] = dcy[8] = -30000;
+            auto covered = [&](int X, int Y) {
+                bool cov = false;
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const int ady = abs(Y - dcy[k]), adx = abs(X - dcx[k]);
+                    if (ady <= P.rad && adx <= shw[ady]) cov = true;
+                }
+                return cov;
+            };
+            const float4 cd = cand[cell];
+            int P1idx = -1;
+            for (int pass = 0; pass < 2; pass++) {
+                float best;
+                int bidx;
+                // fast path: the pre-computed static-mask maximum stands unless a neighbour's disc covers it (the second one
+                // also needs the primary to be exactly the pre-computed one: it was taken outside THAT disc)
+                const float fm = pass ? cd.z : cd.x;
+                const int fi = __float_as_int(pass ? cd.w : cd.y);
+                bool fast = fm > 0.0f && (pass == 0 || P1idx == __float_as_int(cd.y));
+                if (fast) {
+                    const int fy = fi / cs, fx = fi - fy * cs;
+                    fast = !covered(x0 + fx, y0 + fy);
+                }
+                if (P.dbg && lane == 0) {
+                    atomicAdd(P.dbg + 0, 1);
+                    if (!fast) atomicAdd(P.dbg + 1 + (fm > 0.0f ? (pass == 0 || P1idx == __float_as_int(cd.y) ? 2 : 1) : 0), 1);
+                }
+                if (fast) { best = fm; bidx = fi; }
+                else {
+                    // re-scan: the statically masked map (from the cell kernel) with the neighbouring / own discs applied.  Loads
+                    // are issued eight deep: the scan sits on the wavefront's critical path, so its latency is what counts
+                    const float* hmap = P.hmap + ((size_t)f * ncells + cell) * cs * cs;
+                    best = -FLT_MAX;
+                    bidx = 0x7fffffff;
+                    for (int e0 = lane; e0 < cs * cs; e0 += 32 * 8) {
+                        float hv[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { const int e = e0 + 32 * k; hv[k] = e < cs * cs ? __ldg(hmap + e) : -FLT_MAX; }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int e = e0 + 32 * k;
+                            // a disc can only lower a value to 0, so only values that could still win (or any value while the
+                            // running best is negative) need the disc test
+                            if (e < cs * cs && (hv[k] > best || best < 0.0f)) {
+                                const int y = e / cs, x = e - y * cs;
+                                const float v = covered(x0 + x, y0 + y) ? 0.0f : hv[k];
+                                if (v > best) { best = v; bidx = e; }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+                        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+                    }
                 }
                 const int by = bidx / cs, bx = bidx - by * cs;
                 const int X = bx + x0, Y = by + y0;
                 if (X < P.roi[0] || Y < P.roi[1] || X >= P.roi[0] + P.roi[2] || Y >= P.roi[1] + P.roi[3]) break;
-                if ((double)best >= q) {
-                    if (lane == 0) (pass == 0 ? prim : sec)[cell] = X | (Y << 16);
-                    clear_disk(mask, P.mw, P.w, P.h, X, Y, P.rad, P.hw, lane, 32);
-                    __syncwarp();
-                    __threadfence_block();
-                }
+                if (!((double)best >= q)) break;   // nothing is drawn, so the second search would repeat this one and fail alike
+                if (pass == 0) { P1idx = bidx; dcx[8] = X; dcy[8] = Y; }
+                if (lane == 0) (pass == 0 ? prim : sec)[cell] = X | (Y << 16);
             }
         }
         __syncthreads();
@@ -221,12 +333,11 @@ __global__ void __launch_bounds__(512) detect_select_kernel(const DetectParams P
     if (tid == 0) {
         float* out = P.out + (size_t)f * P.out_cap * 2;
         int32_t* oi = P.out_int ? P.out_int + (size_t)f * P.out_cap * 2 : nullptr;
-        int n = 0, stored = 0;
+        int n = 0;
         auto put = [&](int32_t v) {
             if (n < P.out_cap) {
                 out[2 * n] = (float)(v & 0xffff); out[2 * n + 1] = (float)(v >> 16);
                 if (oi) { oi[2 * n] = v & 0xffff; oi[2 * n + 1] = v >> 16; }
-                stored++;
             }
             n++;
         };
@@ -389,7 +500,8 @@ extern "C" int alva_k_detect_grid(alva_ctx* ctx, const uint8_t* gray, int w, int
     const size_t occ_b = (((size_t)nframes * (P.nch + 1) * (P.ncw + 1)) + 255) & ~(size_t)255;
     const size_t hmap_b = (size_t)nframes * ncells * cell * cell * sizeof(float);
     const size_t mask_b = (size_t)nframes * h * P.mw * sizeof(uint32_t);
-    const size_t need = occ_b + hmap_b + mask_b + 512;
+    const size_t cand_b = (size_t)nframes * ncells * sizeof(float4);
+    const size_t need = occ_b + hmap_b + mask_b + cand_b + 1024;
     if (need > ctx->det_ws_bytes) {
         if (ctx->det_ws) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->det_ws)); ctx->det_ws = nullptr; ctx->det_ws_bytes = 0; }
         ALVA_CUDA(cudaMalloc(&ctx->det_ws, need));
@@ -397,19 +509,33 @@ extern "C" int alva_k_detect_grid(alva_ctx* ctx, const uint8_t* gray, int w, int
     }
     uint8_t* ws = (uint8_t*)ctx->det_ws;
     P.occ = ws; P.hmap = (float*)(ws + occ_b); P.mask = (uint32_t*)(ws + occ_b + hmap_b);
+    P.cand = (float4*)(ws + ((occ_b + hmap_b + mask_b + 255) & ~(size_t)255));
     P.quality = quality; P.out = out; P.out_int = out_int; P.counts = counts; P.out_cap = out_cap;
+    static int32_t* dbg_dev = nullptr;
+    static const bool dbg_on = getenv("ALVA_DETECT_DEBUG") != nullptr;
+    if (dbg_on) {
+        if (!dbg_dev) { ALVA_CUDA(cudaMalloc(&dbg_dev, 32)); }
+        ALVA_CUDA(cudaMemsetAsync(dbg_dev, 0, 32, ctx->stream));
+        P.dbg = dbg_dev;
+    }
     detect_prepare_kernel<<<nframes, 512, 0, ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
     const size_t sm1 = (size_t)(2 * cell * (cell + 2) + 2 * cell * cell) * sizeof(float) + (size_t)cell * cell;
     ALVA_CUDA(cudaFuncSetAttribute(detect_mineig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
     detect_mineig_kernel<<<dim3(ncells, nframes), 256, sm1, ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
-    const size_t sm2 = (size_t)2 * ncells * sizeof(int32_t);
+    const size_t sm2 = (size_t)2 * ncells * sizeof(int32_t) + 16 + (size_t)ncells * (sizeof(float4) + 1);
     if (sm2 > 200 * 1024) { alva_set_error("alva_k_detect_grid: too many cells (%d)", ncells); return ALVA_E_INVALID; }
     ALVA_CUDA(cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     detect_select_kernel<<<nframes, 512, sm2, ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
     corner_subpix_kernel<<<dim3((out_cap + 63) / 64, nframes), 64, 0, ctx->stream>>>(P, out, counts, out_cap, 30, 0.01 * 0.01);
     ALVA_LAUNCH_CHECK(ctx);
+    if (dbg_on) {
+        int32_t hdbg[8];
+        ALVA_CUDA(cudaMemcpyAsync(hdbg, dbg_dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ALVA_CUDA(cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[detect] searches %d, re-scans: max<=0 %d, primary differs %d, covered %d\n", hdbg[0], hdbg[1], hdbg[2], hdbg[3]);
+    }
     return 0;
 }

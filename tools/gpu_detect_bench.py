@@ -9,7 +9,7 @@ from alvaar_b200 import synth
 w, h, cs = 1280, 720, 40
 fr, _ = synth.make_frames(4, w, h, seed=3, rgba=False)
 ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)
-for B in (13, 64, 1):
+for B in [int(x) for x in os.environ.get("DET_B", "13,64,1").split(",")]:
     imgs = torch.from_numpy(np.ascontiguousarray(fr)).cuda().repeat((B + 3) // 4, 1, 1)[:B].contiguous()
     rng = np.random.default_rng(0)
     ncur = 250
