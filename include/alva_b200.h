@@ -300,7 +300,13 @@ int  alva_system_find_camera_pose(alva_system*, const uint8_t* rgba, float* pose
 int  alva_system_find_camera_pose_imu(alva_system*, const uint8_t* rgba, const double* imu, float* pose16);
 int  alva_system_find_plane(alva_system*, float* out16, int iterations);
 int  alva_system_get_frame_points(alva_system*, int32_t* xy, int cap_pairs);   /* returns the true count */
-int  alva_system_num_matched(alva_system*);   /* features of the last frame matched to the local map */
+int  alva_system_num_matched(alva_system*);   /* keypoints of the current frame that are tracked from the last keyframe */
+/* the frame's keypoints with their track ids (keypoint id == map point id, src/slam/src/map_manager.cpp:166-191) and
+ * pixel positions px [cap][2]; returns the true count */
+int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, int cap);
+/* 1 once the reference's initialisation test has fired (median parallax > 40 px, visual_frontend.cpp:419-430); the
+ * 5-point initialisation itself is not built yet, so the status stays 3 */
+int  alva_system_init_due(alva_system*);
 
 /* ---- host-buffer variants (copies inside; used for e2e timing and by non-CUDA hosts) ---------- */
 int alva_h_frontend(alva_ctx*, const uint8_t* rgba_host, int w, int h, int nframes, int thr,

@@ -64,16 +64,23 @@ fi
 INC="-I$REF/src/slam/src -I$REF/src/libs/opencv/modules/highgui/include -I$REF/src/libs/opencv/modules/imgcodecs/include -I$REF/src/libs/opencv/modules/videoio/include -I$REF/src/libs/opengv/include -I$P/ocv_install/include/opencv4 -I$REF/src/libs/eigen -I$REF/src/libs/Sophus \
  -I$P/ceres_install/include -I$P/ceres_install/include/ceres/internal/miniglog"
 cd "$OUT"
-g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/ceres_parametrization.cpp" -o ceres_parametrization.o $INC
-g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/feature_tracker.cpp" -o feature_tracker.o $INC
-g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/multi_view_geometry.cpp" -o multi_view_geometry.o $INC
-g++ -std=c++17 -O2 -w -fPIC -c "$REF/src/slam/src/feature_extractor.cpp" -o feature_extractor.o $INC
+# every AlvaAR source except the Emscripten binding, compiled where it lies, unmodified (system.cpp needs C++20 for its
+# unqualified duration_cast)
+OBJS=""
+for f in camera_calibration ceres_parametrization feature_extractor feature_tracker frame map_manager map_point mapper \
+         multi_view_geometry optimizer state system utils visual_frontend; do
+  echo "g++ -std=c++20 -O2 -w -fPIC -c $REF/src/slam/src/$f.cpp -o $OUT/$f.o $INC"
+  OBJS="$OBJS $f.o"
+done | xargs -P "$J" -I{} sh -c '{}'
+for f in camera_calibration ceres_parametrization feature_extractor feature_tracker frame map_manager map_point mapper \
+         multi_view_geometry optimizer state system utils visual_frontend; do OBJS="$OBJS $f.o"; done
 g++ -std=c++17 -O2 -w -fPIC -c "$HERE/ref_harness.cpp" -o ref_harness.o $INC
-g++ -shared -o libalva_ref.so ref_harness.o ceres_parametrization.o feature_tracker.o multi_view_geometry.o feature_extractor.o \
+g++ -std=c++20 -O2 -w -fPIC -c "$HERE/ref_system.cpp" -o ref_system.o $INC
+g++ -shared -o libalva_ref.so ref_harness.o ref_system.o $OBJS \
   -Wl,--start-group "$P"/ocv_install/lib/libopencv_video.a "$P"/ocv_install/lib/libopencv_calib3d.a \
   "$P"/ocv_install/lib/libopencv_features2d.a "$P"/ocv_install/lib/libopencv_flann.a \
   "$P"/ocv_install/lib/libopencv_imgproc.a "$P"/ocv_install/lib/libopencv_core.a \
   "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a "$P"/opengv/libopengv.a -Wl,--end-group \
   -lpthread -ldl -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL
-rm -f ref_harness.o ceres_parametrization.o feature_tracker.o multi_view_geometry.o feature_extractor.o
+rm -f ref_harness.o ref_system.o $OBJS
 echo "built $OUT/libalva_ref.so"
