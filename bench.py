@@ -322,6 +322,7 @@ def bench_b200(args, rank, world, local_rank):
         _ = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    tracking = tracking_stage_times(ctx, pipe, stream, local_rank) if rank == 0 else None
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
@@ -370,10 +371,78 @@ def bench_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "stats": {"features_per_frame_mean": float(nf.mean()), "features_per_frame_min": int(nf.min()),
                       "ba_final_over_initial_cost": float((summ[:, 1] / np.maximum(summ[:, 0], 1e-300)).mean()),
-                      "ba_iterations_mean": float(summ[:, 3].mean())}}
+                      "ba_iterations_mean": float(summ[:, 3].mean()),
+                      "tracking_stages_us": tracking}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def tracking_stage_times(ctx, pipe, stream, local_rank):
+    """The reference's own per-frame association / pose stages on the same batch, timed one by
+    one with CUDA events AFTER the headline measurement (they are reported, not part of `value`): forward-backward KLT of
+    every frame's 1000 selected features into the next frame (63 frame pairs out of the step's pyramids), P3P-LMedS and
+    PnP on 64 synthetic 1000-point problems, the grid Shi-Tomasi detector + cornerSubPix on the step's 13 keyframes."""
+    import torch
+    from alvaar_b200 import synth
+    dev = f"cuda:{local_rank}"
+    ws, hs = [W], [H]
+    for _ in range(3):
+        ws.append((ws[-1] + 1) // 2); hs.append((hs[-1] + 1) // 2)
+    lv = [pipe.buffer(f"l{k}", (BATCH, hs[k], ws[k]), torch.uint8) for k in range(4)]
+    dv = [pipe.buffer(f"d{k}", (BATCH, hs[k], ws[k], 2), torch.int16) for k in range(4)]
+    pts = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
+    cnt = pipe.buffer("selcounts", (BATCH,), torch.int32)
+    nf = BATCH - 1
+    good = torch.zeros((nf, pipe.fcap), dtype=torch.uint8, device=dev)
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return float(np.median(ts[1:]))
+
+    out = {}
+    with torch.cuda.stream(stream):
+        pri = torch.empty((nf, pipe.fcap, 2), dtype=torch.float32, device=dev)
+
+        def klt():
+            pri.copy_(pts[:nf])
+            ctx.klt_fb([t[:nf] for t in lv], [t[:nf] for t in dv], [t[1:] for t in lv], [t[1:] for t in dv], W, H, nf, 3,
+                       pts[:nf], pri, pipe.fcap, good, npts_per_frame=cnt[:nf])
+        out[f"klt_fb_{nf}x{NFEAT}"] = timed(klt)
+        out["klt_tracked_fraction"] = float(good.sum().item()) / float(cnt[:nf].sum().item())
+        prs = [synth.make_pose_problem(NFEAT, i, w=W, h=H, outlier_frac=0.1) for i in range(8)]
+        t = lambda key: torch.from_numpy(np.stack([prs[i % 8][key] for i in range(BATCH)])).to(dev)  # noqa: E731
+        bv, X, uv, pose0 = t("bv"), t("X"), t("uv"), t("pose0")
+        K = torch.from_numpy(np.tile(prs[0]["K"], (BATCH, 1))).to(dev)
+        T = torch.zeros((BATCH, 12), dtype=torch.float64, device=dev)
+        outl = torch.zeros((BATCH, NFEAT), dtype=torch.uint8, device=dev)
+        info = torch.zeros((BATCH, 4), dtype=torch.float64, device=dev)
+        summ = torch.zeros((BATCH, 12), dtype=torch.float64, device=dev)
+        out[f"p3p_lmeds_{BATCH}x{NFEAT}"] = timed(lambda: ctx.p3p_lmeds(BATCH, NFEAT, bv, X, None, T, outl, info, fx=float(prs[0]["K"][0]),
+                                                                       fy=float(prs[0]["K"][1])))
+
+        def pnp():
+            p = pose0.clone()
+            ctx.pnp(BATCH, NFEAT, K, uv, X, None, p, outl, summ, float(np.sqrt(np.float32(5.9915))), float(np.float32(5.9915)))
+        out[f"pnp_{BATCH}x{NFEAT}"] = timed(pnp)
+        assert int(info[:, 0].sum().item()) == BATCH and int(summ[:, 10].sum().item()) == BATCH
+        kf = torch.arange(0, BATCH, KF_INTERVAL, device=dev)
+        kimg = lv[0].index_select(0, kf).contiguous()
+        kcur = pts.index_select(0, kf)[:, ::2].contiguous()      # half of the tracked points: about half the cells stay free
+        kn = torch.clamp(cnt.index_select(0, kf) // 2, max=kcur.shape[1]).to(torch.int32).contiguous()
+        dout = torch.zeros((len(kf), 2048, 2), dtype=torch.float32, device=dev)
+        dcnt = torch.zeros(len(kf), dtype=torch.int32, device=dev)
+
+        def det():
+            q = torch.full((len(kf),), 0.001, dtype=torch.float64, device=dev)
+            ctx.detect_grid(kimg, W, H, len(kf), 40, kcur, kn, kcur.shape[1], [20, 20, W - 40, H - 40], q, dout, None, dcnt, 2048)
+        out[f"detect_grid_{len(kf)}kf"] = timed(det)
+        out["detect_corners_per_kf"] = float(dcnt.float().mean().item())
+    return out
 
 
 def main():

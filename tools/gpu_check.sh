@@ -5,12 +5,13 @@ set +e
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-FILES=${FILES:-"test_gpu_frontend test_gpu_orb_match test_gpu_ba test_gpu_pipeline test_gpu_system"}
+FILES=${FILES:-"test_gpu_frontend test_gpu_orb_match test_gpu_ba test_gpu_pipeline test_gpu_klt test_gpu_pose test_gpu_detect test_gpu_system"}
+rm -f gpurun_out/test_gpu_*.log
 for f in $FILES; do
   timeout 420 python -m pytest tests/$f.py -m gpu -x -q --durations=4 -p no:cacheprovider > gpurun_out/$f.log 2>&1
   echo "== $f rc=$?"; tail -14 gpurun_out/$f.log
 done
-if ! grep -q " passed" gpurun_out/test_gpu_frontend.log || grep -q "failed" gpurun_out/test_gpu_frontend.log; then
+if [ -f gpurun_out/test_gpu_frontend.log ] && { ! grep -q " passed" gpurun_out/test_gpu_frontend.log || grep -q "failed" gpurun_out/test_gpu_frontend.log; }; then
   echo "== frontend failed: retry without TMA and under compute-sanitizer"
   ALVA_DISABLE_TMA=1 timeout 300 python -m pytest tests/test_gpu_frontend.py -m gpu -x -q -p no:cacheprovider 2>&1 | tail -6
   timeout 240 compute-sanitizer --tool memcheck --print-limit 5 python tools/gpu_repro.py > gpurun_out/sanitizer.log 2>&1; tail -30 gpurun_out/sanitizer.log
