@@ -251,3 +251,82 @@ def make_pose_problem(n=300, seed=0, w=1280, h=720, noise_px=0.5, outlier_frac=0
     pose0 = np.concatenate([t + rng.normal(0, pose_noise[0], 3), q0 / np.linalg.norm(q0)])
     return dict(K=K, pose_true=np.concatenate([t, q]), pose0=pose0, X=np.ascontiguousarray(X), uv=np.ascontiguousarray(obs),
                 bv=np.ascontiguousarray(bv), outlier_true=out)
+
+
+def make_match_problem(seed=0, w=640, h=480, n_kf=6, n_frame_kp=150, n_local=400, dup_frac=0.4, cell=40):
+    """A consistent little map for Mapper::matchToMap (mapper.cpp:354-587), in flat arrays:
+    keyframes with poses; a current frame observing n_frame_kp map points (its keypoints); n_local further map points of the
+    local map that the frame does not observe -- a fraction dup_frac of them are re-detections of frame keypoints (same
+    world point up to noise, seen from DISJOINT keyframes, descriptors a few bits apart), the rest are unrelated.
+    Poses are T_wc = [t, q(x,y,z,w)]; pixels are projections + noise; descriptors 256-bit."""
+    rng = np.random.default_rng(seed)
+    K = np.array(intrinsics(w, h))
+
+    def rand_pose(scale):
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        ang = rng.uniform(0, 0.08)
+        return np.concatenate([rng.normal(0, scale, 3), np.sin(ang / 2) * ax, [np.cos(ang / 2)]])
+
+    def project(pose, X):
+        R = quat_to_R(pose[3:])
+        c = (X - pose[:3]) @ R
+        return np.stack([K[0] * c[:, 0] / c[:, 2] + K[2], K[1] * c[:, 1] / c[:, 2] + K[3]], 1), c[:, 2]
+
+    kf_T = np.stack([rand_pose(0.15) for _ in range(n_kf)])
+    cur_T = rand_pose(0.15)
+    # world points seen by the current frame
+    uv = np.stack([rng.uniform(10, w - 10, n_frame_kp), rng.uniform(10, h - 10, n_frame_kp)], 1)
+    z = rng.uniform(2, 8, n_frame_kp)
+    Rc = quat_to_R(cur_T[3:])
+    Xc = np.stack([(uv[:, 0] - K[2]) / K[0] * z, (uv[:, 1] - K[3]) / K[1] * z, z], 1)
+    Xa = Xc @ Rc.T + cur_T[:3]
+    base_desc = rng.integers(0, 256, (n_frame_kp, 32), dtype=np.uint8)
+
+    def flip(d, nbits):
+        d = d.copy()
+        for b in rng.integers(0, 256, nbits):
+            d[b >> 3] ^= np.uint8(1 << (b & 7))
+        return d
+
+    mp_id, mp_wpt, mp_is3d, obs_start, obs_kf, obs_px, desc_start, desc_kf, desc = [], [], [], [0], [], [], [0], [], []
+
+    def add_mp(pid, X, kfs, dbase, is3d=True, flips=6):
+        mp_id.append(pid); mp_wpt.append(X); mp_is3d.append(1 if is3d else 0)
+        for k in kfs:
+            p, _ = project(kf_T[k], X[None])
+            q = p[0] + rng.normal(0, 0.4, 2)   # keyframe keypoints live on the keyframe's grid: keep them inside the image
+            obs_kf.append(k); obs_px.append(np.array([min(max(q[0], 1.0), w - 2.0), min(max(q[1], 1.0), h - 2.0)]))
+            desc_kf.append(k); desc.append(flip(dbase, int(rng.integers(0, flips + 1))))
+        obs_start.append(len(obs_kf)); desc_start.append(len(desc_kf))
+
+    half = n_kf // 2
+    kp_id, kp_px = [], []
+    for i in range(n_frame_kp):       # the frame's keypoints: observed in keyframes of the FIRST half
+        pid = 1000 + i
+        kfs = sorted(rng.choice(half, size=int(rng.integers(1, half + 1)), replace=False).tolist())
+        add_mp(pid, Xa[i], kfs, base_desc[i], is3d=bool(rng.random() < 0.8))
+        kp_id.append(pid); kp_px.append(uv[i] + rng.normal(0, 0.3, 2))
+    local_ids = []
+    for j in range(n_local):          # local map points not observed by the frame
+        pid = 5000 + j
+        if rng.random() < dup_frac:   # a re-detection of frame keypoint i, seen from the SECOND half (disjoint keyframe sets)
+            i = int(rng.integers(0, n_frame_kp))
+            X = Xa[i] + rng.normal(0, 0.002, 3)
+            kfs = sorted((half + rng.choice(n_kf - half, size=int(rng.integers(1, n_kf - half + 1)), replace=False)).tolist())
+            if rng.random() < 0.15:   # some share a keyframe with the keypoint's map point: not a candidate
+                kfs = sorted(set(kfs) | {0})
+            add_mp(pid, X, kfs, base_desc[i], is3d=bool(rng.random() < 0.9), flips=10)
+        else:
+            u = np.array([rng.uniform(-50, w + 50), rng.uniform(-50, h + 50)]); zz = rng.uniform(-1, 8)
+            X = np.array([(u[0] - K[2]) / K[0] * zz, (u[1] - K[3]) / K[1] * zz, zz]) @ Rc.T + cur_T[:3]
+            kfs = sorted(rng.choice(n_kf, size=int(rng.integers(1, 4)), replace=False).tolist())
+            add_mp(pid, X, kfs, rng.integers(0, 256, 32, dtype=np.uint8), is3d=bool(rng.random() < 0.9))
+        local_ids.append(pid)
+    local_ids += kp_id[:10]           # a few ids the frame already observes: skipped (mapper.cpp:404-407)
+    f32, i32 = np.float32, np.int32
+    return dict(w=w, h=h, K=K, cell=cell, cur_T=cur_T, kp_id=np.array(kp_id, i32), kp_px=np.array(kp_px, f32),
+                kf_id=np.arange(n_kf, dtype=i32) + 3, kf_T=np.ascontiguousarray(kf_T), mp_id=np.array(mp_id, i32),
+                mp_wpt=np.ascontiguousarray(np.array(mp_wpt)), mp_is3d=np.array(mp_is3d, np.uint8),
+                obs_start=np.array(obs_start, i32), obs_kf=np.array(obs_kf, i32), obs_px=np.array(obs_px, f32),
+                desc_start=np.array(desc_start, i32), desc_kf=np.array(desc_kf, i32), desc=np.ascontiguousarray(np.array(desc, np.uint8)),
+                local_ids=np.array(local_ids, i32))

@@ -202,6 +202,26 @@ int alva_k_pnp(alva_ctx*, int nprob, int cap, const double* K, const double* uv,
                double* poses, double huber_delta, double chi2_thr, int max_iter, int use_robust, int apply_l2,
                uint8_t* outlier, double* summary);
 
+/* Mapper::matchToMap (src/slam/src/mapper.cpp:354-587; caller matchingToLocalMap :293-352): every local-map point the
+ * keyframe does not observe yet is projected into it (depth >= 0.1, view angle, in image), compared with the keypoints of
+ * the 2x2 grid cells around the projection (pixel gate max_proj_err, doubled below 30 3-D keypoints; the two map points never
+ * observed in one keyframe; mean co-projection error of the keypoint's own observations; minimum Hamming distance over all
+ * per-keyframe descriptor pairs, MapPoint::computeMinDescDist), best / second best with the 0.9 ratio test, and per keypoint
+ * the map point with the smallest distance (the last one in processing order on ties).  The map is flat SoA, DEVICE pointers:
+ *   Twc_cur [7] = [t, q(x,y,z,w)]; keypoints in grid insertion order: kp_mp [n_kp] = index of the keypoint's own map point in
+ *   the table (-1: none), kp_px [n_kp][2]; nkp3d (HOST int) = Frame::numKeypoints3d_; kf_Twc [n_kf][7], n_kf <= 64;
+ *   map point table: mp_wpt [n_mp][3], mp_is3d [n_mp], observations CSR obs_start [n_mp + 1] -> obs_kf (keyframe INDEX,
+ *   ascending keyframe id) / obs_px [..][2], descriptors CSR desc_start [n_mp + 1] -> desc [..][32] (16-byte aligned);
+ *   local_mp [n_local] = table indices of the local map in the host's iteration order (that order decides ties, as the
+ *   reference's unordered_set order does).  Zero lens distortion (what the JS shim passes).
+ * Out: kp_match [n_kp] = table index of the matched local map point or -1, kp_dist (optional) its Hamming distance,
+ * n_match [1] the number of matched keypoints. */
+int alva_k_match_to_map(alva_ctx*, int w, int h, int cell, double fx, double fy, double cx, double cy, const double* Twc_cur,
+                        int n_kp, const int32_t* kp_mp, const float* kp_px, int nkp3d, int n_kf, const double* kf_Twc, int n_mp,
+                        const double* mp_wpt, const uint8_t* mp_is3d, const int32_t* obs_start, const int32_t* obs_kf,
+                        const float* obs_px, const int32_t* desc_start, const uint8_t* desc, int n_local, const int32_t* local_mp,
+                        float max_proj_err, float dist_ratio, int32_t* kp_match, float* kp_dist, int32_t* n_match);
+
 /* Local bundle adjustment, batched over nprob independent problems of identical dimensions
  * (Optimizer::localBA, src/slam/src/optimizer.cpp:4-531, solved the way ceres::Solve does with the reference's
  * options: SPARSE_SCHUR elimination of the inverse depths, Levenberg-Marquardt, Huber(huber_delta), Jacobi scaling,

@@ -81,4 +81,70 @@ int ref_system_info(void* h, int32_t* out6) {
     return 0;
 }
 
+// Mapper::matchToMap (src/slam/src/mapper.cpp:354-587) -- private; reached through the same `private public` switch -- on a map
+// rebuilt from flat arrays with the reference's own classes (Frame, MapPoint, MapManager, Mapper), nothing re-implemented:
+//   current frame: pose Twc [t, q(x,y,z,w)], keypoints (id, px) added in the given order (that order is the grid-cell order
+//                  getSurroundingKeypoints walks), nkp3d = Frame::numKeypoints3d_ (doubles the pixel gate below 30)
+//   keyframes    : id + pose; their keypoints come from the observations below
+//   map points   : id, world point, is3d; observations (keyframe index, pixel in that keyframe) = observedKeyframeIds_ and
+//                  the keyframe's keypoint; descriptors per keyframe = mapKeyframeDescriptors_ (desc_ = the last one)
+//   local map    : the ids matchToMap iterates -- an std::unordered_set<int>; its iteration order decides ties, so the
+//                  order the reference used is returned in order_out (the oracle and the GPU take it as input)
+// Returns the number of (keypoint id -> map point id) pairs written to match_kp / match_mp (ascending keypoint id).
+int ref_match_to_map(int w, int h, double fx, double fy, double cx, double cy, const double* Twc_cur, int n_kp, const int32_t* kp_id,
+                     const float* kp_px, int nkp3d, int n_kf, const int32_t* kf_id, const double* kf_Twc, int n_mp,
+                     const int32_t* mp_id, const double* mp_wpt, const uint8_t* mp_is3d, const int32_t* obs_start,
+                     const int32_t* obs_kf, const float* obs_px, const int32_t* desc_start, const int32_t* desc_kf,
+                     const uint8_t* desc, int n_local, const int32_t* local_ids, float max_proj_err, float dist_ratio,
+                     int32_t* order_out, int32_t* match_kp, int32_t* match_mp) {
+    std::cout.setstate(std::ios_base::failbit);
+    auto state = std::make_shared<State>(w, h, 40);
+    auto calib = std::make_shared<CameraCalibration>(fx, fy, cx, cy, 0., 0., 0., 0., w, h, 20);
+    auto frame = std::make_shared<Frame>(calib, state->frameMaxCellSize_);
+    auto extractor = std::make_shared<FeatureExtractor>(state->extractorMaxQuality_);
+    auto manager = std::make_shared<MapManager>(state, frame, extractor);
+    Mapper mapper(state, manager, frame);
+    std::cout.clear();
+    auto pose = [](const double* p) { return Sophus::SE3d(Eigen::Quaterniond(p[6], p[3], p[4], p[5]), Eigen::Vector3d(p[0], p[1], p[2])); };
+    std::vector<std::shared_ptr<Frame>> kfs(n_kf);
+    for (int k = 0; k < n_kf; k++) {
+        kfs[k] = std::allocate_shared<Frame>(Eigen::aligned_allocator<Frame>(), calib, state->frameMaxCellSize_);
+        kfs[k]->keyframeId_ = kf_id[k];
+        kfs[k]->setTwc(pose(kf_Twc + 7 * k));
+        manager->mapKeyframes_.emplace(kf_id[k], kfs[k]);
+    }
+    for (int m = 0; m < n_mp; m++) {
+        auto mp = std::allocate_shared<MapPoint>(Eigen::aligned_allocator<MapPoint>());
+        mp->mapPointId_ = mp_id[m];
+        mp->isObserved_ = false;
+        mp->is3d_ = mp_is3d[m] != 0;
+        mp->point3d_ = Eigen::Vector3d(mp_wpt[3 * m], mp_wpt[3 * m + 1], mp_wpt[3 * m + 2]);
+        mp->keyframeId_ = obs_start[m + 1] > obs_start[m] ? kf_id[obs_kf[obs_start[m]]] : 0;
+        mp->invDepth_ = -1.;
+        for (int o = obs_start[m]; o < obs_start[m + 1]; o++) {
+            mp->observedKeyframeIds_.insert(kf_id[obs_kf[o]]);
+            kfs[obs_kf[o]]->addKeypoint(cv::Point2f(obs_px[2 * o], obs_px[2 * o + 1]), mp_id[m]);
+        }
+        for (int d = desc_start[m]; d < desc_start[m + 1]; d++) {
+            cv::Mat dm(1, 32, CV_8U);
+            memcpy(dm.ptr(), desc + (size_t)32 * d, 32);
+            mp->mapKeyframeDescriptors_.emplace(kf_id[desc_kf[d]], dm);
+            mp->desc_ = dm;
+        }
+        manager->mapMapPoints_.emplace(mp_id[m], mp);
+    }
+    frame->keyframeId_ = n_kf ? kf_id[n_kf - 1] + 1 : 0;
+    frame->setTwc(pose(Twc_cur));
+    for (int i = 0; i < n_kp; i++) frame->addKeypoint(cv::Point2f(kp_px[2 * i], kp_px[2 * i + 1]), kp_id[i]);
+    frame->numKeypoints3d_ = nkp3d;
+    std::unordered_set<int> local;
+    for (int i = 0; i < n_local; i++) local.insert(local_ids[i]);
+    int k = 0;
+    for (int id : local) order_out[k++] = id;
+    std::map<int, int> res = mapper.matchToMap(*frame, max_proj_err, dist_ratio, local);
+    int n = 0;
+    for (auto& kv : res) { match_kp[n] = kv.first; match_mp[n] = kv.second; n++; }
+    return n;
+}
+
 }  // extern "C"

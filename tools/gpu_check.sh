@@ -5,7 +5,7 @@ set +e
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-FILES=${FILES:-"test_gpu_frontend test_gpu_orb_match test_gpu_ba test_gpu_pipeline test_gpu_klt test_gpu_pose test_gpu_detect test_gpu_system"}
+FILES=${FILES:-"test_gpu_frontend test_gpu_orb_match test_gpu_ba test_gpu_pipeline test_gpu_klt test_gpu_pose test_gpu_detect test_gpu_match test_gpu_system"}
 rm -f gpurun_out/test_gpu_*.log
 for f in $FILES; do
   timeout 420 python -m pytest tests/$f.py -m gpu -x -q --durations=4 -p no:cacheprovider > gpurun_out/$f.log 2>&1
