@@ -60,10 +60,14 @@ struct alva_pipeline {
     int32_t *ba_anch_kf = nullptr, *ba_obs_kf = nullptr, *ba_obs_lm = nullptr;
     bool have_map = false, have_ba = false;
     // host-step staging
-    uint8_t* in_dev = nullptr;
+    // two staging slots: the upload of one submission overlaps the compute of the previous one (alva_pipeline_submit_host)
+    static constexpr int NSLOT = 2;
+    uint8_t* in_dev[NSLOT] = {nullptr, nullptr};
     static constexpr int NCHUNK = 4;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t chunk_ev[NCHUNK] = {}, start_ev = nullptr;
+    cudaEvent_t chunk_ev[NSLOT][NCHUNK] = {}, free_ev[NSLOT] = {}, done_ev[NSLOT] = {};
+    bool slot_used[NSLOT] = {false, false};
+    int next_slot = 0, outstanding = 0, oldest_slot = 0;
     static constexpr int NEV = 64;      // ring of event pairs around the fused front-end launch
     cudaEvent_t ev0[NEV] = {}, ev1[NEV] = {};
     // local BA runs beside the per-frame stages on its own (high-priority) stream, as the reference architecture's mapper
@@ -106,8 +110,11 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (p->copy_stream) {
         cudaStreamSynchronize(p->copy_stream);
         cudaStreamDestroy(p->copy_stream);
-        for (int i = 0; i < alva_pipeline::NCHUNK; i++) if (p->chunk_ev[i]) cudaEventDestroy(p->chunk_ev[i]);
-        if (p->start_ev) cudaEventDestroy(p->start_ev);
+        for (int s = 0; s < alva_pipeline::NSLOT; s++) {
+            for (int i = 0; i < alva_pipeline::NCHUNK; i++) if (p->chunk_ev[s][i]) cudaEventDestroy(p->chunk_ev[s][i]);
+            if (p->free_ev[s]) cudaEventDestroy(p->free_ev[s]);
+            if (p->done_ev[s]) cudaEventDestroy(p->done_ev[s]);
+        }
     }
     for (int i = 0; i < alva_pipeline::NEV; i++) {
         if (p->ev0[i]) cudaEventDestroy(p->ev0[i]);
@@ -375,40 +382,47 @@ extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev)
     return pipeline_ba_join(p);
 }
 
-// Host-buffer step (the e2e leg): the batch is uploaded in chunks on a dedicated copy stream while the compute stream
-// works on the chunks that have already landed (event-ordered), then the per-frame results come back.  One call, one
-// synchronisation at the end.
-extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
-                                       double* ba_poses_host, double* ba_summary_host) {
-    if (!p || !rgba_host) { alva_set_error("alva_pipeline_step_host: bad argument"); return ALVA_E_INVALID; }
+// Host-buffer step (the e2e leg).  alva_pipeline_submit_host enqueues one batch and returns at once: the batch is uploaded in
+// chunks on a dedicated copy stream into one of two staging slots while the compute stream works on the chunks that have
+// landed (event-ordered) -- and while the PREVIOUS submission is still computing -- then the per-frame results are copied
+// back.  alva_pipeline_wait blocks until the oldest outstanding submission (at most two) has delivered its results.
+// alva_pipeline_step_host = submit + wait.
+extern "C" int alva_pipeline_submit_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
+                                         double* ba_poses_host, double* ba_summary_host) {
+    if (!p || !rgba_host) { alva_set_error("alva_pipeline_submit_host: bad argument"); return ALVA_E_INVALID; }
     if (int e = pipeline_ready(p)) return e;
+    if (p->outstanding >= alva_pipeline::NSLOT) { alva_set_error("alva_pipeline_submit_host: two submissions outstanding, call alva_pipeline_wait"); return ALVA_E_STATE; }
     const alva_pipeline_config& c = p->cfg;
     const size_t frame_bytes = (size_t)c.w * c.h * 4;
-    if (!p->in_dev) { if (int e = palloc(p, (void**)&p->in_dev, frame_bytes * c.batch)) return e; }
+    const int slot = p->next_slot;
+    if (!p->in_dev[slot]) { if (int e = palloc(p, (void**)&p->in_dev[slot], frame_bytes * c.batch)) return e; }
     if (!p->copy_stream) {
         ALVA_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < alva_pipeline::NCHUNK; i++) ALVA_CUDA(cudaEventCreateWithFlags(&p->chunk_ev[i], cudaEventDisableTiming));
-        ALVA_CUDA(cudaEventCreateWithFlags(&p->start_ev, cudaEventDisableTiming));
+        for (int s = 0; s < alva_pipeline::NSLOT; s++) {
+            for (int i = 0; i < alva_pipeline::NCHUNK; i++) ALVA_CUDA(cudaEventCreateWithFlags(&p->chunk_ev[s][i], cudaEventDisableTiming));
+            ALVA_CUDA(cudaEventCreateWithFlags(&p->free_ev[s], cudaEventDisableTiming));
+            ALVA_CUDA(cudaEventCreateWithFlags(&p->done_ev[s], cudaEventDisableTiming));
+        }
     }
     cudaStream_t st = p->ctx->stream;
     const int nchunk = c.batch >= 4 * alva_pipeline::NCHUNK ? alva_pipeline::NCHUNK : 1;
     const int per = (c.batch + nchunk - 1) / nchunk;
-    // the upload may not overwrite frames an earlier step on the compute stream is still reading
-    ALVA_CUDA(cudaEventRecord(p->start_ev, st));
-    ALVA_CUDA(cudaStreamWaitEvent(p->copy_stream, p->start_ev, 0));
+    // the upload may not overwrite frames an earlier submission that used this slot is still reading
+    if (p->slot_used[slot]) ALVA_CUDA(cudaStreamWaitEvent(p->copy_stream, p->free_ev[slot], 0));
     for (int i = 0; i < nchunk; i++) {
         const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
         if (nf <= 0) break;
-        ALVA_CUDA(cudaMemcpyAsync(p->in_dev + frame_bytes * f0, rgba_host + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice, p->copy_stream));
-        ALVA_CUDA(cudaEventRecord(p->chunk_ev[i], p->copy_stream));
+        ALVA_CUDA(cudaMemcpyAsync(p->in_dev[slot] + frame_bytes * f0, rgba_host + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice, p->copy_stream));
+        ALVA_CUDA(cudaEventRecord(p->chunk_ev[slot][i], p->copy_stream));
     }
     for (int i = 0; i < nchunk; i++) {
         const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
         if (nf <= 0) break;
-        ALVA_CUDA(cudaStreamWaitEvent(st, p->chunk_ev[i], 0));
-        if (int e = pipeline_frames(p, p->in_dev, f0, nf, false, i == 0)) { pipeline_ba_join(p); return e; }
+        ALVA_CUDA(cudaStreamWaitEvent(st, p->chunk_ev[slot][i], 0));
+        if (int e = pipeline_frames(p, p->in_dev[slot], f0, nf, false, i == 0)) { pipeline_ba_join(p); return e; }
     }
     if (int e = pipeline_ba_join(p)) return e;
+    ALVA_CUDA(cudaEventRecord(p->free_ev[slot], st));   // the staged frames have been consumed
     if (nfeat_host) ALVA_CUDA(cudaMemcpyAsync(nfeat_host, p->selcounts, sizeof(int32_t) * c.batch, cudaMemcpyDeviceToHost, st));
     if (matches_host && c.map_size > 0)
         ALVA_CUDA(cudaMemcpyAsync(matches_host, p->matches, (size_t)c.batch * p->fcap * 16, cudaMemcpyDeviceToHost, st));
@@ -416,8 +430,29 @@ extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_hos
         if (ba_poses_host) ALVA_CUDA(cudaMemcpyAsync(ba_poses_host, p->ba_poses, (size_t)p->nprob * c.ba_nkf * 56, cudaMemcpyDeviceToHost, st));
         if (ba_summary_host) ALVA_CUDA(cudaMemcpyAsync(ba_summary_host, p->ba_summary, (size_t)p->nprob * 64, cudaMemcpyDeviceToHost, st));
     }
-    ALVA_CUDA(cudaStreamSynchronize(st));
+    ALVA_CUDA(cudaEventRecord(p->done_ev[slot], st));
+    p->slot_used[slot] = true;
+    if (p->outstanding == 0) p->oldest_slot = slot;
+    p->outstanding++;
+    p->next_slot = (slot + 1) % alva_pipeline::NSLOT;
     return 0;
+}
+
+extern "C" int alva_pipeline_wait(alva_pipeline* p) {
+    if (!p) { alva_set_error("alva_pipeline_wait: bad argument"); return ALVA_E_INVALID; }
+    if (p->outstanding == 0) return 0;
+    ALVA_CUDA(cudaEventSynchronize(p->done_ev[p->oldest_slot]));
+    p->outstanding--;
+    p->oldest_slot = (p->oldest_slot + 1) % alva_pipeline::NSLOT;
+    return 0;
+}
+
+extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
+                                       double* ba_poses_host, double* ba_summary_host) {
+    if (!p) { alva_set_error("alva_pipeline_step_host: bad argument"); return ALVA_E_INVALID; }
+    while (p->outstanding) if (int e = alva_pipeline_wait(p)) return e;
+    if (int e = alva_pipeline_submit_host(p, rgba_host, nfeat_host, matches_host, ba_poses_host, ba_summary_host)) return e;
+    return alva_pipeline_wait(p);
 }
 
 extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: fcap, kcap, nprob, map_size */) {

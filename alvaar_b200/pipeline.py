@@ -29,6 +29,8 @@ class Pipeline:
         L.alva_pipeline_set_ba.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
         L.alva_pipeline_step_dev.argtypes = [C.c_void_p, C.c_void_p]
         L.alva_pipeline_step_host.argtypes = [C.c_void_p] * 6
+        L.alva_pipeline_submit_host.argtypes = [C.c_void_p] * 6
+        L.alva_pipeline_wait.argtypes = [C.c_void_p]
         L.alva_pipeline_profile.argtypes = [C.c_void_p, C.c_int]
         L.alva_pipeline_frontend_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.alva_pipeline_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -70,6 +72,16 @@ class Pipeline:
     def step_host(self, rgba_host, nfeat=None, matches=None, ba_poses=None, ba_summary=None):
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         self._chk(self.L.alva_pipeline_step_host(self.h, p(rgba_host), p(nfeat), p(matches), p(ba_poses), p(ba_summary)))
+
+    def submit_host(self, rgba_host, nfeat=None, matches=None, ba_poses=None, ba_summary=None):
+        """asynchronous step_host: returns at once; at most two outstanding; pair every submit with a wait()"""
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        self._keep.append((rgba_host, nfeat, matches, ba_poses, ba_summary))
+        self._keep = self._keep[-4:]
+        self._chk(self.L.alva_pipeline_submit_host(self.h, p(rgba_host), p(nfeat), p(matches), p(ba_poses), p(ba_summary)))
+
+    def wait(self):
+        self._chk(self.L.alva_pipeline_wait(self.h))
 
     def profile(self, on):
         self._chk(self.L.alva_pipeline_profile(self.h, 1 if on else 0))

@@ -300,6 +300,14 @@ int  alva_pipeline_set_ba(alva_pipeline*, int slot, const double* calib, const d
 int  alva_pipeline_step_dev(alva_pipeline*, const uint8_t* rgba_dev);
 int  alva_pipeline_step_host(alva_pipeline*, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
                              double* ba_poses_host, double* ba_summary_host);
+/* Asynchronous form of step_host for throughput hosts: submit enqueues a batch (upload in chunks, compute, results back to the
+ * given host buffers) and returns at once; at most two submissions may be outstanding, so the upload of one overlaps the
+ * compute of the other.  wait blocks until the OLDEST outstanding submission has delivered its results.  The host buffers must
+ * stay valid (and the result buffers distinct per outstanding submission) until the matching wait returns.
+ * step_host == submit + wait. */
+int  alva_pipeline_submit_host(alva_pipeline*, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
+                               double* ba_poses_host, double* ba_summary_host);
+int  alva_pipeline_wait(alva_pipeline*);
 int  alva_pipeline_profile(alva_pipeline*, int enable);
 int  alva_pipeline_frontend_ms(alva_pipeline*, float* ms, int n);   /* CUDA-event durations of the fused front-end launch */
 int  alva_pipeline_info(const alva_pipeline*, int32_t* out4);

@@ -53,7 +53,7 @@ def test_match_vs_oracle_full_size(gpu_ctx, oracle, seed, nkp, nloc, w, h):
     for nk in (200, 7):
         want = oracle_match(oracle, p, order, nk)
         got, dist = gpu_match(gpu_ctx, p, order, nk)
-        assert got == want and len(want) > min(20, nkp // 4)
+        assert got == want and len(want) > min(20, nkp // 8)
         assert dist.max() <= 51.0
 
 

@@ -122,3 +122,27 @@ def test_pipeline_detect_and_compute_mode(gpu_ctx, oracle, w, h, batch, nfeat):
         oracle.orc_knn2(P(np.ascontiguousarray(wd[:n])), n, P(mapd), len(mapd), P(wm))
         assert (matches[f, :n] == wm).all() and (matches[f, n:] == -1).all()
     pipe.close()
+
+
+def test_submit_wait_equals_step_host(gpu_ctx):
+    """The asynchronous host step (two submissions in flight) delivers exactly what the synchronous one does."""
+    import alvaar_b200
+    from alvaar_b200.pipeline import Pipeline
+    w, h, B = 640, 480, 16
+    frames, _ = synth.make_frames(B, w, h, seed=5)
+    _, mapd = synth.make_descriptors(8, 2000, seed=7)
+    pipe = Pipeline(gpu_ctx, w, h, B, fast_thr=20, nfeatures=300, orb_flags=alvaar_b200.ORB_IC_ANGLE, map_size=2000)
+    pipe.set_map(mapd)
+    host = torch.from_numpy(frames).pin_memory()
+    mk = lambda: (torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros((B, pipe.fcap, 4), dtype=torch.int32).pin_memory())  # noqa: E731
+    a, b, c = mk(), mk(), mk()
+    pipe.step_host(host, *a)
+    pipe.submit_host(host, *b)
+    pipe.submit_host(host, *c)
+    with pytest.raises(alvaar_b200.AlvaError):
+        pipe.submit_host(host, *a)            # at most two outstanding
+    pipe.wait(); pipe.wait(); pipe.wait()     # the third wait is a no-op
+    assert a[0].sum() > 0
+    for x in (b, c):
+        assert torch.equal(x[0], a[0]) and torch.equal(x[1], a[1])
+    pipe.close()
