@@ -363,6 +363,7 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;   // the RGBA staging buffer is idle from here on
     uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + NWARPS * QCAP * 2);
     static_assert(NWARPS * QCAP * 2 + KPCAP * 4 <= BW * BH * 4, "queues + keypoint list must fit the staging buffer");
+    int qn = 0;   // candidates in this warp's queue (phase D fills it, phase E walks it again)
     if (P.keys) {
         const int thr = P.thr;
         const bool hi_thr = thr >= 128;
@@ -380,7 +381,6 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             const uint32_t colbytes = c1v >= c0v ? ((0x01010101u >> (8 * (3 - c1v))) & (0x01010101u << (8 * c0v))) : 0u;
             vm = colbytes * rowbits;                          // rowbits replicated into every valid byte
         }
-        int qn = 0;
         if (__any_sync(0xffffffffu, vm != 0)) {
             // gray rows needed: centre rows 8*warp+3 .. 8*warp+10, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
             const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
@@ -415,70 +415,36 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     __syncthreads();
 
     // ------------------------------------------------------------------ E. 3x3 NMS (strict >) + emit
+    // The warp's candidate queue is walked a second time: a candidate that became a corner (non-zero score, inside the tile
+    // interior) is compared with its 8 neighbours in the shared score tile.  Only corners pay for the neighbour loads
+    // (~4 % of the pixels); nothing scans the score tile.
     if (P.keys) {
-        const uint32_t* Sw = reinterpret_cast<const uint32_t*>(S.score);
-        // pass 1: every lane lists the rows (of its warp's 8) where its score word is non-zero; the (row, lane) items are
-        // compacted per warp so that pass 2 runs with full lanes on the ~25 % of words that hold a corner
-        uint32_t nz = 0;
-        if (lane >= 1 && lane <= 30) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int rr = 8 * warp + i;
-                if (rr >= 1 && rr <= TH && Sw[rr * SPW + lane] != 0) nz |= 1u << i;
-            }
-        }
-        const int mine = __popc(nz);
-        int incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
-        int pos = incl - mine;
-        const int nitems = __shfl_sync(0xffffffffu, incl, 31);
-        while (nz) {
-            const int i = __ffs(nz) - 1;
-            nz &= nz - 1;
-            Q[pos++] = (uint16_t)((8 * warp + i) * SPW + lane);
-        }
-        __syncwarp();
-        for (int q0 = 0; q0 < nitems; q0 += 32) {
-            uint32_t ok = 0, Sv = 0;
-            int rr = 0, gc = 0;
-            if (q0 + lane < nitems) {
-                const int widx = Q[q0 + lane];
-                rr = widx / SPW; gc = widx - rr * SPW;
-                const uint32_t* s0 = Sw + widx;
-                Sv = s0[0];
-                ok = ((Sv & ALVA_L) + ALVA_L) | Sv;   // bit7: byte != 0
-#pragma unroll
-                for (int dy = -1; dy <= 1; dy++) {
-                    const uint32_t L = s0[dy * SPW - 1], M = s0[dy * SPW], R = s0[dy * SPW + 1];
-                    const uint32_t nl = __byte_perm(L, M, 0x6543), nr = __byte_perm(M, R, 0x4321);
-                    ok &= ~swar_ge_raw(nl, Sv);   // Sv > nl  <=> !(nl >= Sv)
-                    ok &= ~swar_ge_raw(nr, Sv);
-                    if (dy != 0) ok &= ~swar_ge_raw(M, Sv);
+        for (int q0 = 0; q0 < qn; q0 += 32) {
+            bool iskp = false;
+            uint32_t key = 0;
+            if (q0 + lane < qn) {
+                const int pix = Q[q0 + lane];
+                const int pr = pix / GP, pcg = pix - pr * GP;
+                const int sr = pr - 3, scol = pcg - 4 * cbw;          // score-tile row / column (column 4 = image x0)
+                if (sr >= 1 && sr <= TH && scol >= 4 && scol < 4 + TW) {
+                    const uint8_t* sp = S.score + sr * SP + scol;
+                    const uint32_t v = sp[0];
+                    if (v) {
+                        const uint32_t m = max(max(max((uint32_t)sp[-SP - 1], (uint32_t)sp[-SP]), max((uint32_t)sp[-SP + 1], (uint32_t)sp[-1])),
+                                               max(max((uint32_t)sp[1], (uint32_t)sp[SP - 1]), max((uint32_t)sp[SP], (uint32_t)sp[SP + 1])));
+                        iskp = v > m;
+                        key = ((uint32_t)(y0 + sr - 1) << 20) | ((uint32_t)(x0 + scol - 4) << 8) | v;
+                    }
                 }
-                ok &= ALVA_H;
             }
-            // Two horizontally adjacent pixels cannot both be strict maxima, so a 4-pixel word holds at most 2 keypoints:
-            // two ballots rank them and ONE shared atomic per warp round reserves the slots (per-keypoint atomics on the
-            // CTA counter serialised the whole CTA here).
-            const int c = __popc(ok);
-            const uint32_t m1 = __ballot_sync(0xffffffffu, c >= 1), m2 = __ballot_sync(0xffffffffu, c >= 2);
-            const int n1 = __popc(m1), tot = n1 + __popc(m2);
-            if (tot) {
+            const uint32_t mk = __ballot_sync(0xffffffffu, iskp);
+            if (mk) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&S.kpcount, tot);
+                if (lane == 0) base = atomicAdd(&S.kpcount, __popc(mk));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const uint32_t lt = (1u << lane) - 1u;
-                const uint32_t yx = ((uint32_t)(y0 + rr - 1) << 20) | ((uint32_t)(x0 + 4 * (gc - 1)) << 8);
-                if (c >= 1) {
-                    const int j = (__ffs(ok) - 1) >> 3;
-                    const int kp = base + __popc(m1 & lt);
-                    if (kp < KPCAP) kplist[kp] = yx + ((uint32_t)j << 8) + ((Sv >> (8 * j)) & 0xff);
-                }
-                if (c >= 2) {
-                    const int j = (31 - __clz(ok)) >> 3;
-                    const int kp = base + n1 + __popc(m2 & lt);
-                    if (kp < KPCAP) kplist[kp] = yx + ((uint32_t)j << 8) + ((Sv >> (8 * j)) & 0xff);
+                if (iskp) {
+                    const int kp = base + __popc(mk & ((1u << lane) - 1u));
+                    if (kp < KPCAP) kplist[kp] = key;
                 }
             }
         }

@@ -81,20 +81,32 @@ __device__ __forceinline__ void lk_level(const uint8_t* __restrict__ I, const in
     __syncwarp();
     if (pix) {
         const int X = ipx + wx, Y = ipy + wy;
-        const int y0 = refl(Y, h), y1 = refl(Y + 1, h);
-        const bool yin0 = (Y >= 0 && Y < h), yin1 = (Y + 1 >= 0 && Y + 1 < h);
         int i0[4], i1[4], dx0[4], dx1[4], dy0[4], dy1[4];
         const uint32_t* D = reinterpret_cast<const uint32_t*>(dI);
+        if (ipx >= 0 && ipy >= 0 && ipx + WIN < w && ipy + WIN < h) {   // whole footprint inside the image (warp-uniform)
+            const size_t o = (size_t)Y * w + X;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int xr = refl(X + k, w);
-            const bool xin = (X + k >= 0 && X + k < w);
-            i0[k] = __ldg(I + (size_t)y0 * w + xr);
-            i1[k] = __ldg(I + (size_t)y1 * w + xr);
-            const uint32_t d0 = (xin && yin0) ? __ldg(D + (size_t)y0 * w + xr) : 0u;
-            const uint32_t d1 = (xin && yin1) ? __ldg(D + (size_t)y1 * w + xr) : 0u;
-            dx0[k] = (int)(short)(d0 & 0xffffu); dy0[k] = (int)d0 >> 16;
-            dx1[k] = (int)(short)(d1 & 0xffffu); dy1[k] = (int)d1 >> 16;
+            for (int k = 0; k < 4; k++) {
+                i0[k] = __ldg(I + o + k);
+                i1[k] = __ldg(I + o + w + k);
+                const uint32_t d0 = __ldg(D + o + k), d1 = __ldg(D + o + w + k);
+                dx0[k] = (int)(short)(d0 & 0xffffu); dy0[k] = (int)d0 >> 16;
+                dx1[k] = (int)(short)(d1 & 0xffffu); dy1[k] = (int)d1 >> 16;
+            }
+        } else {
+            const int y0 = refl(Y, h), y1 = refl(Y + 1, h);
+            const bool yin0 = (Y >= 0 && Y < h), yin1 = (Y + 1 >= 0 && Y + 1 < h);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int xr = refl(X + k, w);
+                const bool xin = (X + k >= 0 && X + k < w);
+                i0[k] = __ldg(I + (size_t)y0 * w + xr);
+                i1[k] = __ldg(I + (size_t)y1 * w + xr);
+                const uint32_t d0 = (xin && yin0) ? __ldg(D + (size_t)y0 * w + xr) : 0u;
+                const uint32_t d1 = (xin && yin1) ? __ldg(D + (size_t)y1 * w + xr) : 0u;
+                dx0[k] = (int)(short)(d0 & 0xffffu); dy0[k] = (int)d0 >> 16;
+                dx1[k] = (int)(short)(d1 & 0xffffu); dy1[k] = (int)d1 >> 16;
+            }
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -174,13 +186,19 @@ __device__ __forceinline__ void lk_level(const uint8_t* __restrict__ I, const in
         __syncwarp();
         if (pix) {
             const int X = inx + wx, Y = iny + wy;
-            const uint8_t* r0 = J + (size_t)refl(Y, h) * w;
-            const uint8_t* r1 = J + (size_t)refl(Y + 1, h) * w;
             int j0[4], j1[4];
+            if (inx >= 0 && iny >= 0 && inx + WIN < w && iny + WIN < h) {   // whole 10x10 footprint inside the image (warp-uniform)
+                const uint8_t* r0 = J + (size_t)Y * w + X;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int xr = refl(X + k, w);
-                j0[k] = __ldg(r0 + xr); j1[k] = __ldg(r1 + xr);
+                for (int k = 0; k < 4; k++) { j0[k] = __ldg(r0 + k); j1[k] = __ldg(r0 + w + k); }
+            } else {
+                const uint8_t* r0 = J + (size_t)refl(Y, h) * w;
+                const uint8_t* r1 = J + (size_t)refl(Y + 1, h) * w;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int xr = refl(X + k, w);
+                    j0[k] = __ldg(r0 + xr); j1[k] = __ldg(r1 + xr);
+                }
             }
 #pragma unroll
             for (int k = 0; k < 3; k++)
@@ -220,7 +238,7 @@ __device__ __forceinline__ void lk_level(const uint8_t* __restrict__ I, const in
 }
 
 template <bool FB>
-__global__ void __launch_bounds__(KLT_WARPS * 32) klt_kernel(const KltParams P) {
+__global__ void __launch_bounds__(KLT_WARPS * 32, 6) klt_kernel(const KltParams P) {
     __shared__ WarpWin win[KLT_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long g = (long long)blockIdx.x * KLT_WARPS + wid;
