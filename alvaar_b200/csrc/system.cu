@@ -68,12 +68,14 @@ public:
             }
         ok = ok && cudaMalloc(&pts_dev_, (size_t)cap_ * 8) == cudaSuccess && cudaMalloc(&pri_dev_, (size_t)cap_ * 8) == cudaSuccess &&
              cudaMalloc(&good_dev_, cap_) == cudaSuccess && cudaMalloc(&cnt_dev_, 16) == cudaSuccess &&
-             cudaMalloc(&quality_dev_, 8) == cudaSuccess;
+             cudaMalloc(&quality_dev_, 8) == cudaSuccess && cudaMalloc(&blur_dev_, (size_t)w_ * h_) == cudaSuccess &&
+             cudaMalloc(&desc_dev_, (size_t)cap_ * 32) == cudaSuccess && cudaMalloc(&kept_dev_, cap_) == cudaSuccess;
         if (!ok) { alva_set_error("System::configure: cudaMalloc failed"); return ALVA_E_CUDA; }
         const double q0 = 0.001;   // State::extractorMaxQuality_ (state.hpp:59); FeatureExtractor keeps adapting it across resets
         ALVA_CUDA(cudaMemcpy(quality_dev_, &q0, 8, cudaMemcpyHostToDevice));
         host_pts_.assign((size_t)cap_ * 2, 0.f);
         host_good_.assign(cap_, 0);
+        host_desc_.assign((size_t)cap_ * 32, 0);
         configured_ = true;
         reset();
         return 0;
@@ -130,12 +132,20 @@ public:
         return n;
     }
 
+    // the keypoints' ORB descriptors (same order as getTracks): FeatureExtractor::describeFeaturePoints at keyframe creation
+    // (feature_extractor.cpp:160-214; empty for points within 31 px of the border, orb.cpp:1130)
+    int getDescriptors(uint8_t* desc, uint8_t* has, int cap) {
+        const int n = (int)kps_.size();
+        for (int i = 0; i < n && i < cap; i++) { memcpy(desc + 32 * (size_t)i, kps_[i].desc, 32); has[i] = kps_[i].has_desc ? 1 : 0; }
+        return n;
+    }
+
     int numMatched() const { return (int)kps_.size(); }
     int initDue() const { return init_due_ ? 1 : 0; }
     int device_ = 0;
 
 private:
-    struct Kp { int id; float x, y, kfx, kfy; };
+    struct Kp { int id; float x, y, kfx, kfy; bool has_desc; uint8_t desc[32]; };
 
     // CameraCalibration::undistortImagePoint (camera_calibration.cpp:57-72): with the zero distortion the JS shim always passes
     // (system.js:84-141) cv::undistortPoints returns the input to float precision; non-zero coefficients are not supported yet
@@ -172,8 +182,18 @@ private:
         ALVA_CUDA(cudaMemcpyAsync(host_pts_.data(), pri_dev_, (size_t)cap_ * 8, cudaMemcpyDeviceToHost, st));
         ALVA_CUDA(cudaStreamSynchronize(st));
         if (n > cap_) n = cap_;
+        // describeFeaturePoints(imageRaw, newPoints) (map_manager.cpp:215-219): ORB::create(500, 1, 0)->compute at the new
+        // points = 7x7 blur (the shipped build's unfused arithmetic) + rBRIEF-256 steered by KeyPoint::convert's -1 degree
+        if (n > 0) {
+            if (int e = alva_k_orb_blur(ctx_, img_[cur_][0], blur_dev_, w_, h_, 1, 0)) return e;
+            if (int e = alva_k_orb_describe(ctx_, img_[cur_][0], blur_dev_, w_, h_, 1, pri_dev_, cnt_dev_, cap_, 0, desc_dev_, kept_dev_, nullptr)) return e;
+            ALVA_CUDA(cudaMemcpyAsync(host_desc_.data(), desc_dev_, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+            ALVA_CUDA(cudaMemcpyAsync(host_good_.data(), kept_dev_, n, cudaMemcpyDeviceToHost, st));
+            ALVA_CUDA(cudaStreamSynchronize(st));
+        }
         for (int i = 0; i < n; i++) {   // addKeypointsToFrame: id = running map point counter (map_manager.cpp:166-191)
-            Kp k{next_id_++, host_pts_[2 * i], host_pts_[2 * i + 1], 0.f, 0.f};
+            Kp k{next_id_++, host_pts_[2 * i], host_pts_[2 * i + 1], 0.f, 0.f, host_good_[i] != 0, {0}};
+            if (k.has_desc) memcpy(k.desc, host_desc_.data() + 32 * (size_t)i, 32);
             kps_.push_back(k);
         }
         for (auto& k : kps_) { k.kfx = k.x; k.kfy = k.y; }   // the keyframe is a copy of the frame (addKeyframe, :243-252)
@@ -250,6 +270,9 @@ private:
         if (good_dev_) { cudaFree(good_dev_); good_dev_ = nullptr; }
         if (cnt_dev_) { cudaFree(cnt_dev_); cnt_dev_ = nullptr; }
         if (quality_dev_) { cudaFree(quality_dev_); quality_dev_ = nullptr; }
+        if (blur_dev_) { cudaFree(blur_dev_); blur_dev_ = nullptr; }
+        if (desc_dev_) { cudaFree(desc_dev_); desc_dev_ = nullptr; }
+        if (kept_dev_) { cudaFree(kept_dev_); kept_dev_ = nullptr; }
         if (ctx_) { alva_ctx_destroy(ctx_); ctx_ = nullptr; }
         configured_ = false;
     }
@@ -262,6 +285,8 @@ private:
     uint8_t* good_dev_ = nullptr;
     int32_t* cnt_dev_ = nullptr;
     double* quality_dev_ = nullptr;
+    uint8_t *blur_dev_ = nullptr, *desc_dev_ = nullptr, *kept_dev_ = nullptr;
+    std::vector<uint8_t> host_desc_;
     std::vector<float> host_pts_;
     std::vector<uint8_t> host_good_;
     std::vector<Kp> kps_;
@@ -306,5 +331,9 @@ extern "C" int alva_system_num_matched(alva_system* s) { return s ? s->sys.numMa
 extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, int cap) {
     if (!s || !ids || !px || cap < 0) return ALVA_E_INVALID;
     return s->sys.getTracks(ids, px, cap);
+}
+extern "C" int alva_system_get_descriptors(alva_system* s, uint8_t* desc, uint8_t* has, int cap) {
+    if (!s || !desc || !has || cap < 0) return ALVA_E_INVALID;
+    return s->sys.getDescriptors(desc, has, cap);
 }
 extern "C" int alva_system_init_due(alva_system* s) { return s ? s->sys.initDue() : ALVA_E_INVALID; }

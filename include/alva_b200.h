@@ -332,6 +332,9 @@ int  alva_system_num_matched(alva_system*);   /* keypoints of the current frame 
 /* the frame's keypoints with their track ids (keypoint id == map point id, src/slam/src/map_manager.cpp:166-191) and
  * pixel positions px [cap][2]; returns the true count */
 int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, int cap);
+/* their 256-bit ORB descriptors (Keypoint::desc_, feature_extractor.cpp:160-214), same order: desc [cap][32], has [cap] (0 = the
+ * reference keeps an empty Mat: point within 31 px of the border) */
+int  alva_system_get_descriptors(alva_system*, uint8_t* desc, uint8_t* has, int cap);
 /* 1 once the reference's initialisation test has fired (median parallax > 40 px, visual_frontend.cpp:419-430); the
  * 5-point initialisation itself is not built yet, so the status stays 3 */
 int  alva_system_init_due(alva_system*);

@@ -74,6 +74,18 @@ int ref_system_get_frame_points(void* h, int32_t* xy, int32_t* ids, float* px, i
     return n;
 }
 
+// Keypoint::desc_ of the frame's 2-D keypoints, same order as ref_system_get_frame_points: desc [cap][32], has [cap]
+int ref_system_get_descriptors(void* h, uint8_t* desc, uint8_t* has, int cap) {
+    System* s = (System*)h;
+    auto kps = s->currFrame_->getKeypoints2d();
+    int n = (int)kps.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        has[i] = kps[i].desc_.empty() ? 0 : 1;
+        if (has[i]) memcpy(desc + 32 * (size_t)i, kps[i].desc_.ptr(), 32);
+    }
+    return n;
+}
+
 int ref_system_info(void* h, int32_t* out6) {
     System* s = (System*)h;
     out6[0] = s->currFrame_->id_; out6[1] = s->currFrame_->keyframeId_; out6[2] = (int)s->currFrame_->numKeypoints_;

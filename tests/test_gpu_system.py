@@ -23,6 +23,7 @@ def bind():
     L.alva_system_find_camera_pose_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.alva_system_get_frame_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.alva_system_get_tracks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.alva_system_get_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.alva_system_find_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     return L
 
@@ -53,6 +54,12 @@ def test_system_matches_reference_until_initialisation():
         assert (px[:n][o].view(np.uint32) == g[f"f{k}_px"].view(np.uint32)).all()   # pixel positions, float bits
         assert (xy[:n][o] == g[f"f{k}_xy"]).all()                                   # getFramePoints
         assert L.alva_system_init_due(s) == 0
+        if f"f{k}_desc" in g.files:                                                  # 256-bit ORB descriptors of the keypoints
+            desc = np.zeros((4096, 32), np.uint8); has = np.zeros(4096, np.uint8)
+            assert L.alva_system_get_descriptors(s, P(desc), P(has), 4096) == n
+            assert (has[:n][o] == g[f"f{k}_has_desc"]).all() and has[:n].sum() > 100
+            m = g[f"f{k}_has_desc"] == 1
+            assert (desc[:n][o][m] == g[f"f{k}_desc"][m]).all()
     # the frame on which the reference initialises: its parallax test fires here too; the 5-point initialisation is not built,
     # so the status honestly stays 3 (never a fabricated pose)
     st = L.alva_system_find_camera_pose(s, P(np.ascontiguousarray(frames[n_pre])), P(pose))

@@ -21,6 +21,7 @@ R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
 R.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
 R.ref_system_get_frame_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 R.ref_system_destroy.argtypes = [C.c_void_p]
+R.ref_system_get_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
 
 def main():
@@ -38,6 +39,10 @@ def main():
         n = R.ref_system_get_frame_points(s, P(xy), P(ids), P(px), 4096)
         o = np.argsort(ids[:n])
         d[f"f{k}_ids"], d[f"f{k}_px"], d[f"f{k}_xy"], d[f"f{k}_pose"] = ids[:n][o], px[:n][o], xy[:n][o], pose
+        if k in (0, 5):   # descriptors are computed at keyframe creation and carried by the tracked keypoints
+            desc = np.zeros((4096, 32), np.uint8); has = np.zeros(4096, np.uint8)
+            R.ref_system_get_descriptors(s, P(desc), P(has), 4096)
+            d[f"f{k}_desc"], d[f"f{k}_has_desc"] = desc[:n][o], has[:n][o]
         status.append(st)
         print(k, "status", st, "2-D keypoints", n)
     d["status"] = np.array(status, np.int32)
