@@ -331,7 +331,12 @@ def bench_b200(args, rank, world, local_rank):
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])   # both slots deliver the same results
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    tracking = tracking_stage_times(ctx, pipe, stream, local_rank) if rank == 0 else None
+    tracking = None
+    if rank == 0:
+        try:
+            tracking = tracking_stage_times(ctx, pipe, stream, local_rank)
+        except Exception as e:   # explanatory numbers only: never let them take the headline line down
+            tracking = {"error": repr(e)}
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
