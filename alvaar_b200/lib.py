@@ -65,6 +65,8 @@ _OPTIONAL = {
                             _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, C.c_float, C.c_float, _vp, _vp, _vp],
     "alva_k_p3p_lmeds": [_vp, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, C.c_float, C.c_float, C.c_uint32, _vp, _vp, _vp],
     "alva_k_pnp": [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _i32, _i32, _i32, _vp, _vp],
+    "alva_k_essential_5pt": [_vp, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, _i32, C.c_float, C.c_float, C.c_uint32, _vp, _vp, _vp],
+    "alva_k_triangulate": [_vp, _vp, _vp, _vp, _i32, _vp],
     "alva_k_klt_lk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.c_double, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "alva_k_klt_fb": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp, _i32, _vp],
     "alva_k_harris": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
@@ -216,6 +218,16 @@ class Context:
         """MultiViewGeometry::p3pRansac (Kneip P3P + LMedS), batched -- see alva_k_p3p_lmeds."""
         self._chk(self.L.alva_k_p3p_lmeds(self.h, nprob, cap, _ptr(bvs), _ptr(wpts), _ptr(counts), max_iter, err_px, fx, fy,
                                           seed, _ptr(Twc_out), _ptr(outlier), _ptr(info)))
+
+    def essential_5pt(self, nprob, cap, bv1, bv2, counts, Rt_out, outlier, info=None, max_iter=100, err_px=3.0, optimize=True,
+                      fx=1.0, fy=1.0, seed=12345):
+        """MultiViewGeometry::compute5ptEssentialMatrix (Nister 5-point RANSAC + refinement), batched -- see alva_k_essential_5pt."""
+        self._chk(self.L.alva_k_essential_5pt(self.h, nprob, cap, _ptr(bv1), _ptr(bv2), _ptr(counts), max_iter, err_px,
+                                              1 if optimize else 0, fx, fy, seed, _ptr(Rt_out), _ptr(outlier), _ptr(info)))
+
+    def triangulate(self, Tlr, bvl, bvr, n, out):
+        """MultiViewGeometry::triangulate (mid-point) for n bearing-vector pairs -- see alva_k_triangulate."""
+        self._chk(self.L.alva_k_triangulate(self.h, _ptr(Tlr), _ptr(bvl), _ptr(bvr), n, _ptr(out)))
 
     def pnp(self, nprob, cap, K, uv, X, counts, poses, outlier, summary, huber_delta, chi2_thr, max_iter=5, use_robust=True,
             apply_l2=True):

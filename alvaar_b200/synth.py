@@ -253,6 +253,32 @@ def make_pose_problem(n=300, seed=0, w=1280, h=720, noise_px=0.5, outlier_frac=0
                 bv=np.ascontiguousarray(bv), outlier_true=out)
 
 
+def make_twoview_problem(n=150, seed=0, w=640, h=480, noise_px=0.3, outlier_frac=0.1, baseline=0.4, rot_deg=3.0):
+    """n scene points seen by two cameras (camera 1 = the keyframe at the origin, camera 2 at [R12 | t12]): unit bearing
+    vectors of both views (Frame::computeKeypoint: normalised K^-1 [u v 1]) with pixel noise and gross outliers -- the
+    input of VisualFrontend::checkReadyForInit's 5-point initialisation."""
+    rng = np.random.default_rng(seed)
+    K = np.array(intrinsics(w, h))
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    ang = np.deg2rad(rot_deg) * rng.uniform(0.3, 1.0)
+    q = np.concatenate([np.sin(ang / 2) * ax, [np.cos(ang / 2)]])
+    R12 = quat_to_R(q)
+    t12 = rng.normal(size=3); t12[2] *= 0.3; t12 *= baseline / np.linalg.norm(t12)
+    uv1 = np.stack([rng.uniform(25, w - 25, n), rng.uniform(25, h - 25, n)], 1)
+    z = rng.uniform(2, 8, n)
+    X1 = np.stack([(uv1[:, 0] - K[2]) / K[0] * z, (uv1[:, 1] - K[3]) / K[1] * z, z], 1)
+    X2 = (X1 - t12) @ R12                      # R12^T (X1 - t12)
+    uv2 = np.stack([K[0] * X2[:, 0] / X2[:, 2] + K[2], K[1] * X2[:, 1] / X2[:, 2] + K[3]], 1)
+    uv1n = uv1 + rng.normal(0, noise_px, uv1.shape)
+    uv2n = uv2 + rng.normal(0, noise_px, uv2.shape)
+    out = rng.random(n) < outlier_frac
+    uv2n[out] += rng.normal(0, 25, (int(out.sum()), 2))
+
+    def bearing(uv):
+        b = np.stack([(uv[:, 0] - K[2]) / K[0], (uv[:, 1] - K[3]) / K[1], np.ones(len(uv))], 1)
+        return np.ascontiguousarray(b / np.linalg.norm(b, axis=1, keepdims=True))
+    return dict(K=K, R12=R12, t12=t12, bv1=bearing(uv1n), bv2=bearing(uv2n), uv1=uv1n, uv2=uv2n, outlier_true=out, X1=X1)
+
 def make_match_problem(seed=0, w=640, h=480, n_kf=6, n_frame_kp=150, n_local=400, dup_frac=0.4, cell=40):
     """A consistent little map for Mapper::matchToMap (mapper.cpp:354-587), in flat arrays:
     keyframes with poses; a current frame observing n_frame_kp map points (its keypoints); n_local further map points of the

@@ -202,6 +202,27 @@ int alva_k_pnp(alva_ctx*, int nprob, int cap, const double* K, const double* uv,
                double* poses, double huber_delta, double chi2_thr, int max_iter, int use_robust, int apply_l2,
                uint8_t* outlier, double* summary);
 
+/* Map initialisation: MultiViewGeometry::compute5ptEssentialMatrix(observations1, observations2, max_iter, err_px, optimize,
+ * doRandom, fx, fy, Rwc, twc, outliers) (src/slam/src/multi_view_geometry.cpp:225-318; caller
+ * VisualFrontend::checkReadyForInit, visual_frontend.cpp:517-528) = OpenGV's Ransac over CentralRelativePoseSacProblem (Nister's
+ * five-point solver on the first 5 of 8 drawn correspondences, the 8 disambiguate the <= 40 (R, t) candidates; inliers:
+ * mid-point triangulation error e1 + e2 < 2 (1 - cos(atan(err_px / focal))); adaptive iteration bound, probability 0.99;
+ * >= 10 inliers required) followed by relative_pose::optimize_nonlinear over the inliers when optimize != 0, batched over
+ * nprob independent problems.  DEVICE pointers, FP64: bv1 / bv2 [nprob][cap][3] = unit bearing vectors of the keyframe and of
+ * the current frame (only the first counts[p] are live; counts may be NULL; cap <= 8192).  seed as in alva_k_p3p_lmeds.
+ * Rt_out [nprob][12]: [Rwc | twc] 3x4 row-major, twc NOT normalised (the caller normalises it, visual_frontend.cpp:547);
+ * written only on success.  outlier [nprob][cap] (1 = outlier / dead slot).  info (optional) [nprob][4] = {success, #inliers,
+ * #RANSAC iterations, #draws}. */
+int alva_k_essential_5pt(alva_ctx*, int nprob, int cap, const double* bv1, const double* bv2, const int32_t* counts,
+                         int max_iter, float err_px, int optimize, float fx, float fy, uint32_t seed, double* Rt_out,
+                         uint8_t* outlier, double* info);
+
+/* MultiViewGeometry::triangulate (src/slam/src/multi_view_geometry.cpp:12-22 -> opengv::triangulation::triangulate2, the
+ * mid-point of the two rays; caller Mapper::triangulateTemporal, mapper.cpp:157-291) for n bearing-vector pairs.  DEVICE
+ * pointers, FP64: Tlr [7] = [t, q(x,y,z,w)] (pose of the right camera in the left one); bvl / bvr [n][3]; out [n][3] = points
+ * in the left camera frame. */
+int alva_k_triangulate(alva_ctx*, const double* Tlr, const double* bvl, const double* bvr, int n, double* out);
+
 /* Mapper::matchToMap (src/slam/src/mapper.cpp:354-587; caller matchingToLocalMap :293-352): every local-map point the
  * keyframe does not observe yet is projected into it (depth >= 0.1, view angle, in image), compared with the keypoints of
  * the 2x2 grid cells around the projection (pixel gate max_proj_err, doubled below 30 3-D keypoints; the two map points never

@@ -410,4 +410,33 @@ void ref_corner_subpix(const uint8_t* gray, int w, int h, float* pts, int n, int
     for (int i = 0; i < n; i++) { pts[2 * i] = p[i].x; pts[2 * i + 1] = p[i].y; }
 }
 
+// MultiViewGeometry::compute5ptEssentialMatrix (src/slam/src/multi_view_geometry.cpp:225-318), unmodified, called as
+// VisualFrontend::checkReadyForInit does (visual_frontend.cpp:517-528): OpenGV's Ransac over CentralRelativePoseSacProblem
+// (NISTER), doRandom = false (seed 12345).  bv1 = keyframe bearing vectors, bv2 = current frame's, [n][3].
+// Rt_out: 3x4 row-major [Rwc | twc] (twc NOT yet normalised); outlier [n].  Returns 1 on success.
+int ref_essential_5pt(const double* bv1, const double* bv2, int n, int max_iter, float err_px, int optimize, float fx, float fy,
+                      double* Rt_out, uint8_t* outlier) {
+    std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>> a(n), b(n);
+    for (int i = 0; i < n; i++) { a[i] = Eigen::Vector3d(bv1[3 * i], bv1[3 * i + 1], bv1[3 * i + 2]); b[i] = Eigen::Vector3d(bv2[3 * i], bv2[3 * i + 1], bv2[3 * i + 2]); }
+    Eigen::Matrix3d R = Eigen::Matrix3d::Identity();
+    Eigen::Vector3d t = Eigen::Vector3d::Zero();
+    std::vector<int> out;
+    bool ok = MultiViewGeometry::compute5ptEssentialMatrix(a, b, max_iter, err_px, optimize != 0, false, fx, fy, R, t, out);
+    memset(outlier, 0, n);
+    for (int i : out) outlier[i] = 1;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Rt_out[4 * i + j] = R(i, j); Rt_out[4 * i + 3] = t[i]; }
+    return ok ? 1 : 0;
+}
+
+// MultiViewGeometry::triangulate (src/slam/src/multi_view_geometry.cpp:12-22): OpenGV triangulate2 (mid-point) of n pairs.
+// Tlr = [t, q(x,y,z,w)] (left <- right); bvl / bvr [n][3]; out [n][3] in the left camera frame.
+void ref_triangulate(const double* Tlr, const double* bvl, const double* bvr, int n, double* out) {
+    Sophus::SE3d T(Eigen::Quaterniond(Tlr[6], Tlr[3], Tlr[4], Tlr[5]), Eigen::Vector3d(Tlr[0], Tlr[1], Tlr[2]));
+    for (int i = 0; i < n; i++) {
+        Eigen::Vector3d p = MultiViewGeometry::triangulate(T, Eigen::Vector3d(bvl[3 * i], bvl[3 * i + 1], bvl[3 * i + 2]),
+                                                           Eigen::Vector3d(bvr[3 * i], bvr[3 * i + 1], bvr[3 * i + 2]));
+        out[3 * i] = p[0]; out[3 * i + 1] = p[1]; out[3 * i + 2] = p[2];
+    }
+}
+
 }  // extern "C"

@@ -23,7 +23,7 @@ def P(a):
 def oracle():
     """The plain-C CPU oracle (oracle/alva_oracle.c), built on demand.  Test infrastructure only."""
     so = os.path.join(ROOT, "oracle", "_build", "libalva_oracle.so")
-    srcs = [os.path.join(ROOT, "oracle", f) for f in ("alva_oracle.c", "ba_oracle.c", "klt_oracle.c", "pose_oracle.c", "detect_oracle.c", "match_oracle.c")]
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("alva_oracle.c", "ba_oracle.c", "klt_oracle.c", "pose_oracle.c", "detect_oracle.c", "match_oracle.c", "init_oracle.c")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     L = C.CDLL(so)
