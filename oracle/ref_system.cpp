@@ -159,4 +159,31 @@ int ref_match_to_map(int w, int h, double fx, double fy, double cx, double cy, c
     return n;
 }
 
+// every keypoint of the current frame in the iteration order of Frame::mapKeypoints_ (the order the reference feeds its
+// solvers in): ids, px [n][2], is3d, world point of the 3-D ones; Twc7 = [t, q(x,y,z,w)] in double
+int ref_system_keypoints(void* h, int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap, double* Twc7) {
+    System* s = (System*)h;
+    int n = 0;
+    for (const auto& kv : s->currFrame_->mapKeypoints_) {
+        if (n < cap) {
+            ids[n] = kv.second.keypointId_; px[2 * n] = kv.second.px_.x; px[2 * n + 1] = kv.second.px_.y; is3d[n] = kv.second.is3d_;
+            auto mp = s->mapManager_->getMapPoint(kv.second.keypointId_);
+            for (int k = 0; k < 3; k++) wpt[3 * n + k] = (mp && mp->is3d_) ? mp->point3d_[k] : 0.0;
+        }
+        n++;
+    }
+    Sophus::SE3d T = s->currFrame_->getTwc();
+    Eigen::Quaterniond q = T.unit_quaternion();
+    Twc7[0] = T.translation()[0]; Twc7[1] = T.translation()[1]; Twc7[2] = T.translation()[2];
+    Twc7[3] = q.x(); Twc7[4] = q.y(); Twc7[5] = q.z(); Twc7[6] = q.w();
+    return n;
+}
+int ref_system_info8(void* h, int32_t* out8) {
+    System* s = (System*)h;
+    out8[0] = s->currFrame_->id_; out8[1] = s->currFrame_->keyframeId_; out8[2] = (int)s->currFrame_->numKeypoints_;
+    out8[3] = (int)s->currFrame_->numKeypoints3d_; out8[4] = s->state_->slamReadyForInit_ ? 1 : 0; out8[5] = (int)s->mapManager_->numKeyframes_;
+    out8[6] = (int)s->currFrame_->numOccupiedCells_; out8[7] = s->mapManager_->numMapPointIds_;
+    return 0;
+}
+
 }  // extern "C"
