@@ -1,6 +1,6 @@
-// system.cu -- host-side `System`: the reference's public class (src/slam/src/system.hpp:19-56) re-hosted on the
-// B200 hot path, plus its C ABI (alva_system_*).  Same method names, argument meaning and return conventions as the
-// reference so that embind.cpp / system.js stay source-compatible:
+// system.cu -- `System`: the reference's public class (src/slam/src/system.hpp:19-56) re-hosted on the B200 hot path, plus its
+// C ABI (alva_system_*).  Same method names, argument meaning and return conventions as the reference so that embind.cpp /
+// system.js stay source-compatible:
 //
 //   configure(w, h, fx, fy, cx, cy, k1, k2, p1, p2)      system.cpp:13-40
 //   reset()                                               system.cpp:42-55
@@ -9,292 +9,351 @@
 //   findPlane(out16, iterations) -> 0 / 1                 system.cpp:123-137
 //   getFramePoints(xy) -> count                           system.cpp:139-154
 //
-// What runs per call: the reference's own per-frame sequence up to map initialisation, every pixel stage on the GPU --
-//   System::findCameraPose        RGBA -> gray (system.cpp:112) + VisualFrontend::preprocessImage: pyramid + Scharr levels
-//                                 (visual_frontend.cpp:672-698)                         -> alva_k_frontend, Scharr levels
-//   first frame = keyframe        MapManager::createKeyframe -> extractKeypoints (map_manager.cpp:193-222):
-//                                 FeatureExtractor::detectFeaturePoints + ids           -> alva_k_detect_grid
-//   every other frame             VisualFrontend::kltTrackingFromMotionPrior (visual_frontend.cpp:103-243): all keypoints are
-//                                 2-D before initialisation, so one forward-backward KLT on 3 levels from the previous
-//                                 positions; failed tracks are dropped                   -> alva_k_klt_fb
-//                                 < 50 keypoints -> reset, status 2 (visual_frontend.cpp:54-58, system.cpp:163-167)
-//                                 median parallax to the keyframe (computeParallax, :596-670) decides when the reference
-//                                 attempts its 5-point initialisation (checkReadyForInit, :419-552)
-// Status, track ids and keypoint positions of this phase are bit-identical to the reference System (tests/test_gpu_system.py
-// against tests/golden/system.npz, dumped from the reference's own System).  Map initialisation (5-point essential matrix,
-// triangulation) and the mapper's bookkeeping are NOT built yet: once the parallax test fires the
-// reference initialises and starts reporting poses, while this class keeps tracking and keeps reporting status 3 ("not
-// initialised", pose = identity) -- it never fabricates a pose.  The per-frame pose kernels it will call then exist and are
-// parity-tested on their own (alva_k_p3p_lmeds, alva_k_pnp, alva_k_ba_local).
+// The state machine (keypoints, map points, keyframes, motion model, the reference's gates and status codes) is
+// system_core.h; this file is its CUDA Backend -- every pixel and solver stage of a call runs on the device:
+//   pyramid      RGBA -> gray + pyramid + Scharr levels           alva_k_frontend, Scharr levels   (system.cpp:112, visual_frontend.cpp:672-698)
+//   klt          forward-backward pyramidal LK                    alva_k_klt_fb                     (feature_tracker.cpp:5-111)
+//   detect       grid Shi-Tomasi + cornerSubPix                   alva_k_detect_grid                (feature_extractor.cpp:11-158)
+//   describe     7x7 blur + rBRIEF-256 at -1 degree               alva_k_orb_blur / _describe       (feature_extractor.cpp:160-214)
+//   essential    5-point RANSAC + refinement (initialisation)     alva_k_essential_5pt              (multi_view_geometry.cpp:225-318)
+//   p3p / pnp    per-frame pose                                   alva_k_p3p_lmeds, alva_k_pnp      (multi_view_geometry.cpp:24-223)
+//   triangulate  new map points at keyframes                      alva_k_triangulate                (multi_view_geometry.cpp:12-22)
+// There is no CPU fallback: configure() fails without an sm_100 device.  Lens distortion: the JS shim always passes zeros
+// (system.js:84-141); non-zero coefficients are rejected rather than silently ignored.
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
-#include <math.h>
-#include <string.h>
-#include <algorithm>
-#include <set>
-#include <vector>
+#include "system_core.h"
+#include <chrono>
 
 int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src, int16_t* const* dst, const int* w, const int* h,
                               int nframes);
 
-class System {
-public:
-    System() {}
-    ~System() { release(); }
+namespace {
 
-    int configure(int imageWidth, int imageHeight, double fx, double fy, double cx, double cy, double k1, double k2, double p1,
-                  double p2) {
+#define SYS_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            alva_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return ALVA_E_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+struct CudaBackend {
+    alva_ctx* ctx = nullptr;
+    int device = 0, w = 0, h = 0, nlev = 0, cur = 0, cap = 0;
+    int lw[4] = {0, 0, 0, 0}, lh[4] = {0, 0, 0, 0};
+    uint8_t* rgba_dev = nullptr;
+    uint8_t* img[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int16_t* der[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    float *pts_dev = nullptr, *pri_dev = nullptr;
+    uint8_t *flag_dev = nullptr, *blur_dev = nullptr, *desc_dev = nullptr;
+    int32_t* cnt_dev = nullptr;
+    double *quality_dev = nullptr, *dbl_dev = nullptr;   // dbl_dev: [A: 3 cap][B: 3 cap][C: 3 cap][small: 64]
+    bool blur_valid = false;
+
+    int init(int dev, int W, int H) {
         release();
-        w_ = imageWidth; h_ = imageHeight;
-        K_[0] = fx; K_[1] = fy; K_[2] = cx; K_[3] = cy; dist_[0] = k1; dist_[1] = k2; dist_[2] = p1; dist_[3] = p2;
-        ctx_ = alva_ctx_create(device_, nullptr);
-        if (!ctx_) return ALVA_E_CUDA;
-        // State(w, h, 40): frameMaxNumKeypoints = ceil(w/40) * ceil(h/40) (src/slam/src/state.cpp:3-12)
-        cell_ = 40;
-        max_kps_ = ((w_ + cell_ - 1) / cell_) * ((h_ + cell_ - 1) / cell_);
-        cap_ = std::max(64, 2 * (w_ / cell_) * (h_ / cell_));   // a cell yields at most a primary and a secondary corner
-        int ww = w_, hh = h_;
-        nlev_ = 0;
+        device = dev; w = W; h = H;
+        ctx = alva_ctx_create(device, nullptr);
+        if (!ctx) return ALVA_E_CUDA;
+        int ww = W, hh = H;
+        nlev = 0;
         for (int k = 0; k < 4; k++) {   // buildOpticalFlowPyramid(win 9, maxLevel 3) stops when a level is not larger than the window
-            lw_[k] = ww; lh_[k] = hh; nlev_ = k + 1;
+            lw[k] = ww; lh[k] = hh; nlev = k + 1;
             ww = (ww + 1) / 2; hh = (hh + 1) / 2;
             if (ww <= 9 || hh <= 9) break;
         }
-        bool ok = cudaMalloc(&rgba_dev_, (size_t)w_ * h_ * 4) == cudaSuccess;
-        for (int s = 0; s < 2 && ok; s++)
-            for (int k = 0; k < 4 && ok; k++) {
-                const size_t px = (size_t)lw_[k < nlev_ ? k : nlev_ - 1] * lh_[k < nlev_ ? k : nlev_ - 1];
-                ok = cudaMalloc(&img_[s][k], px) == cudaSuccess && cudaMalloc(&der_[s][k], px * 4) == cudaSuccess;
+        // a frame holds at most ~2 keypoints per 40-px cell; 4x leaves room for the transient overshoot before prepareFrame
+        cap = 4 * ((W + 39) / 40) * ((H + 39) / 40) + 64;
+        SYS_CUDA(cudaMalloc(&rgba_dev, (size_t)W * H * 4));
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 4; k++) {
+                const int kk = k < nlev ? k : nlev - 1;
+                const size_t px = (size_t)lw[kk] * lh[kk];
+                SYS_CUDA(cudaMalloc(&img[s][k], px));
+                SYS_CUDA(cudaMalloc(&der[s][k], px * 4));
             }
-        ok = ok && cudaMalloc(&pts_dev_, (size_t)cap_ * 8) == cudaSuccess && cudaMalloc(&pri_dev_, (size_t)cap_ * 8) == cudaSuccess &&
-             cudaMalloc(&good_dev_, cap_) == cudaSuccess && cudaMalloc(&cnt_dev_, 16) == cudaSuccess &&
-             cudaMalloc(&quality_dev_, 8) == cudaSuccess && cudaMalloc(&blur_dev_, (size_t)w_ * h_) == cudaSuccess &&
-             cudaMalloc(&desc_dev_, (size_t)cap_ * 32) == cudaSuccess && cudaMalloc(&kept_dev_, cap_) == cudaSuccess;
-        if (!ok) { alva_set_error("System::configure: cudaMalloc failed"); return ALVA_E_CUDA; }
+        SYS_CUDA(cudaMalloc(&pts_dev, (size_t)cap * 8));
+        SYS_CUDA(cudaMalloc(&pri_dev, (size_t)cap * 8));
+        SYS_CUDA(cudaMalloc(&flag_dev, cap));
+        SYS_CUDA(cudaMalloc(&cnt_dev, 16));
+        SYS_CUDA(cudaMalloc(&quality_dev, 8));
+        SYS_CUDA(cudaMalloc(&blur_dev, (size_t)W * H));
+        SYS_CUDA(cudaMalloc(&desc_dev, (size_t)cap * 32));
+        SYS_CUDA(cudaMalloc(&dbl_dev, ((size_t)cap * 9 + 64) * sizeof(double)));
         const double q0 = 0.001;   // State::extractorMaxQuality_ (state.hpp:59); FeatureExtractor keeps adapting it across resets
-        ALVA_CUDA(cudaMemcpy(quality_dev_, &q0, 8, cudaMemcpyHostToDevice));
-        host_pts_.assign((size_t)cap_ * 2, 0.f);
-        host_good_.assign(cap_, 0);
-        host_desc_.assign((size_t)cap_ * 32, 0);
-        configured_ = true;
-        reset();
+        SYS_CUDA(cudaMemcpy(quality_dev, &q0, 8, cudaMemcpyHostToDevice));
         return 0;
     }
 
-    void reset() {   // system.cpp:42-55: frame, front end, map and state flags
-        frame_id_ = -1;
-        kps_.clear();
-        next_id_ = 0;
-        cur_ = 0;
-        ready_for_init_ = false;
-        init_due_ = false;
+    void release() {
+        if (rgba_dev) { cudaFree(rgba_dev); rgba_dev = nullptr; }
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 4; k++) {
+                if (img[s][k]) { cudaFree(img[s][k]); img[s][k] = nullptr; }
+                if (der[s][k]) { cudaFree(der[s][k]); der[s][k] = nullptr; }
+            }
+        void** bufs[] = {(void**)&pts_dev, (void**)&pri_dev, (void**)&flag_dev, (void**)&cnt_dev, (void**)&quality_dev, (void**)&blur_dev,
+                         (void**)&desc_dev, (void**)&dbl_dev};
+        for (void** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
+        if (ctx) { alva_ctx_destroy(ctx); ctx = nullptr; }
     }
 
+    int pyramid(const uint8_t* rgba) {
+        cudaStream_t st = ctx->stream;
+        cur ^= 1;   // VisualFrontend::preprocessImage swaps prev / cur pyramids (visual_frontend.cpp:672-698)
+        blur_valid = false;
+        SYS_CUDA(cudaMemcpyAsync(rgba_dev, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, st));
+        uint8_t** L = img[cur];
+        if (int e = alva_k_frontend(ctx, rgba_dev, w, h, 1, L[0], nlev > 1 ? L[1] : nullptr, nlev > 2 ? L[2] : nullptr,
+                                    nlev > 3 ? L[3] : nullptr, 20, nullptr, nullptr, 0, 0))
+            return e;
+        const uint8_t* srcs[4] = {L[0], L[1], L[2], L[3]};
+        return alva_scharr_levels_launch(ctx, nlev, srcs, der[cur], lw, lh, 1);
+    }
+
+    int detect(const float* cpts, int ncur, std::vector<float>& fresh) {
+        cudaStream_t st = ctx->stream;
+        if (ncur > cap) { alva_set_error("System: %d keypoints exceed the frame capacity %d", ncur, cap); return ALVA_E_CAPACITY; }
+        int32_t nc = ncur;
+        if (ncur) SYS_CUDA(cudaMemcpyAsync(pts_dev, cpts, (size_t)ncur * 8, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(cnt_dev + 1, &nc, 4, cudaMemcpyHostToDevice, st));
+        const int32_t roi[4] = {20, 20, w - 40, h - 40};   // CameraCalibration(..., imgBorder 20): roi_rect_ (camera_calibration.cpp:21)
+        if (int e = alva_k_detect_grid(ctx, img[cur][0], w, h, 1, 40, pts_dev, cnt_dev + 1, cap, roi, quality_dev, pri_dev, nullptr, cnt_dev, cap))
+            return e;
+        int32_t n = 0;
+        SYS_CUDA(cudaMemcpyAsync(&n, cnt_dev, 4, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        if (n > cap) n = cap;
+        fresh.resize((size_t)2 * n);
+        if (n) {
+            SYS_CUDA(cudaMemcpyAsync(fresh.data(), pri_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            SYS_CUDA(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
+
+    // ORB::create(500, 1, 0)->compute at the given points = 7x7 blur (the shipped build's unfused arithmetic) + rBRIEF-256 steered
+    // by KeyPoint::convert's -1 degree; kept = 0 for points within 31 px of the border (empty descriptor in the reference)
+    int describe(const float* pts, int n, uint8_t* desc, uint8_t* kept) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d keypoints exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        if (!blur_valid) { if (int e = alva_k_orb_blur(ctx, img[cur][0], blur_dev, w, h, 1, 0)) return e; blur_valid = true; }
+        int32_t nn = n;
+        SYS_CUDA(cudaMemcpyAsync(pri_dev, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(cnt_dev + 2, &nn, 4, cudaMemcpyHostToDevice, st));
+        if (int e = alva_k_orb_describe(ctx, img[cur][0], blur_dev, w, h, 1, pri_dev, cnt_dev + 2, cap, 0, desc_dev, flag_dev, nullptr)) return e;
+        SYS_CUDA(cudaMemcpyAsync(desc, desc_dev, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(kept, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+
+    // FeatureTracker::fbKltTracking(prev pyramid, cur pyramid, 9, levels, 30, 0.5, pts, priors, status)
+    int klt(const float* pts, float* priors, int n, int levels, uint8_t* good) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d keypoints exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        SYS_CUDA(cudaMemcpyAsync(pts_dev, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(pri_dev, priors, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        const int prev = cur ^ 1;
+        if (int e = alva_k_klt_fb(ctx, img[prev], der[prev], img[cur], der[cur], w, h, 1, nlev - 1, levels, 9, 30.0f, 0.5f, pts_dev, pri_dev,
+                                  nullptr, n, flag_dev))
+            return e;
+        SYS_CUDA(cudaMemcpyAsync(priors, pri_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(good, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+
+    int essential(const double* b1, const double* b2, int n, float fx, float fy, double* Rt, uint8_t* outl) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d correspondences exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        double *A = dbl_dev, *Bv = dbl_dev + 3 * (size_t)cap, *S = dbl_dev + 9 * (size_t)cap;
+        SYS_CUDA(cudaMemcpyAsync(A, b1, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(Bv, b2, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        // sampler seed: the reference draws from the clock (state.hpp:67, multiViewRandomEnabled_ = true); any seed is a valid
+        // behaviour, the pinned one (12345, what doRandom = false selects) makes runs repeatable
+        if (int e = alva_k_essential_5pt(ctx, 1, n, A, Bv, nullptr, 100, 3.0f, 1, fx, fy, 12345u, S, flag_dev, S + 16)) return e;
+        double host[20];
+        SYS_CUDA(cudaMemcpyAsync(host, S, sizeof host, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(outl, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        memcpy(Rt, host, 12 * sizeof(double));
+        return host[16] != 0.0 ? 1 : 0;
+    }
+
+    int p3p(const double* bv, const double* X, int n, float fx, float fy, double* T12, uint8_t* outl) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d points exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        double *A = dbl_dev, *Bv = dbl_dev + 3 * (size_t)cap, *S = dbl_dev + 9 * (size_t)cap;
+        SYS_CUDA(cudaMemcpyAsync(A, bv, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(Bv, X, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        if (int e = alva_k_p3p_lmeds(ctx, 1, n, A, Bv, nullptr, 100, 3.0f, fx, fy, 12345u, S, flag_dev, S + 16)) return e;
+        double host[20];
+        SYS_CUDA(cudaMemcpyAsync(host, S, sizeof host, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(outl, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        memcpy(T12, host, 12 * sizeof(double));
+        return host[16] != 0.0 ? 1 : 0;
+    }
+
+    // ceresPnP(unpx, wpts, Twc, 5 iterations, chi2 5.9915, robust, L2 refinement, fx, fy, cx, cy) (visual_frontend.cpp:359-375)
+    int pnp(const double* uv, const double* X, int n, const double* K4, double* pose7, uint8_t* outl) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d points exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        double *U = dbl_dev, *Xd = dbl_dev + 3 * (size_t)cap, *S = dbl_dev + 9 * (size_t)cap;   // S: K[4] pose[7] .. summary at +16
+        SYS_CUDA(cudaMemcpyAsync(U, uv, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(Xd, X, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        double head[11];
+        memcpy(head, K4, 32); memcpy(head + 4, pose7, 56);
+        SYS_CUDA(cudaMemcpyAsync(S, head, sizeof head, cudaMemcpyHostToDevice, st));
+        const float chi2 = 5.9915f;   // State::robustCostThreshold_; ceresPnP takes it as float and uses sqrt(chi2) as the Huber width
+        if (int e = alva_k_pnp(ctx, 1, n, S, U, Xd, nullptr, S + 4, sqrt((double)chi2), (double)chi2, 5, 1, 1, flag_dev, S + 16)) return e;
+        double host[28];
+        SYS_CUDA(cudaMemcpyAsync(host, S, sizeof host, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(outl, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        memcpy(pose7, host + 4, 56);
+        return host[16 + 10] != 0.0 ? 1 : 0;
+    }
+
+    int triangulate(const double* T7, const double* bl, const double* br, int n, double* out) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d points exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        double *A = dbl_dev, *Bv = dbl_dev + 3 * (size_t)cap, *O = dbl_dev + 6 * (size_t)cap, *S = dbl_dev + 9 * (size_t)cap;
+        SYS_CUDA(cudaMemcpyAsync(S, T7, 56, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(A, bl, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        SYS_CUDA(cudaMemcpyAsync(Bv, br, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+        if (int e = alva_k_triangulate(ctx, S, A, Bv, n, O)) return e;
+        SYS_CUDA(cudaMemcpyAsync(out, O, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+};
+
+}  // namespace
+
+class System {
+public:
+    System() : core_(be_) {}
+    ~System() { be_.release(); }
+
+    int configure(int imageWidth, int imageHeight, double fx, double fy, double cx, double cy, double k1, double k2, double p1,
+                  double p2) {
+        configured_ = false;
+        if (k1 != 0. || k2 != 0. || p1 != 0. || p2 != 0.) {
+            alva_set_error("System::configure: non-zero lens distortion is not supported (the reference's shim always passes zeros)");
+            return ALVA_E_INVALID;
+        }
+        if (int e = be_.init(device_, imageWidth, imageHeight)) return e;
+        core_.configure(imageWidth, imageHeight, fx, fy, cx, cy);
+        configured_ = true;
+        return 0;
+    }
+
+    void reset() { if (configured_) core_.reset(); }
+
     // returns the reference's status codes; pose16 layout as Utils::toPoseArray (src/slam/src/utils.cpp:3-27)
-    int findCameraPose(const uint8_t* rgba, float* pose16) {
+    int findCameraPose(const uint8_t* rgba, double t_ms, float* pose16) {
         if (!configured_) { alva_set_error("System: not configured"); return ALVA_E_STATE; }
-        const int st = processCameraPose(rgba);
-        writeIdentity(pose16);   // Twc of a frame that is not initialised (or was just reset) is the identity
+        const int st = core_.process(rgba, t_ms);
+        if (st < 0) return st;
+        writePose(core_.cur.Twc, pose16);   // the current frame's Twc in every case (identity after a reset / before initialisation)
         return st;
     }
+    int findCameraPose(const uint8_t* rgba, float* pose16) { return findCameraPose(rgba, nowMs(), pose16); }
 
     int findCameraPoseWithIMU(const uint8_t* rgba, const double* imu, float* pose16) {
         if (!configured_) { alva_set_error("System: not configured"); return ALVA_E_STATE; }
-        const int st = processCameraPose(rgba);
+        const int st = core_.process(rgba, nowMs());
         if (st < 0) return st;
-        // system.cpp:66-69: quaternion (w, -x, y, z) -> R, inverted; translation only follows SLAM when status == 1
+        // system.cpp:66-104: rotation from the device orientation quaternion (w, -x, y, z), inverted; the translation follows the
+        // visual track while its status is 1 (increments of Twc.translation accumulated into currTranslation_)
         const double qw = imu[0], qx = -imu[1], qy = imu[2], qz = imu[3];
         const double n = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
         const double w = qw / n, x = qx / n, y = qy / n, z = qz / n;
         const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
                              2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
                              2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        if (st == 1) {
+            for (int i = 0; i < 3; i++) { imu_t_[i] += core_.cur.Twc.t[i] - imu_prev_[i]; imu_prev_[i] = core_.cur.Twc.t[i]; }
+        } else {
+            imu_prev_[0] = imu_prev_[1] = imu_prev_[2] = 0.;
+        }
         for (int i = 0; i < 16; i++) pose16[i] = 0.f;
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++) pose16[4 * r + c] = (float)R[3 * c + r];
+        pose16[12] = (float)imu_t_[0]; pose16[13] = (float)imu_t_[1]; pose16[14] = (float)imu_t_[2];
         pose16[15] = 1.f;
         return 1;
     }
 
-    int findPlane(float* /*out16*/, int /*numIterations*/) { return 0; }   // needs map points: none before initialisation
+    int findPlane(float* /*out16*/, int /*numIterations*/) { return 0; }   // the plane RANSAC of system.cpp:177-342 is out of scope
 
-    // (x, y) = truncated undistorted position of the frame's 2-D keypoints; writes min(n, cap) pairs, returns the true count
-    // (the reference overruns its 4096-int buffer here)
+    // (x, y) = truncated undistorted position of the frame's 2-D keypoints (Frame::getKeypoints2d order); writes min(n, cap)
+    // pairs, returns the true count (the reference overruns its 4096-int buffer here)
     int getFramePoints(int32_t* xy, int cap_pairs) {
-        const int n = (int)kps_.size();
-        for (int i = 0; i < n && i < cap_pairs; i++) { xy[2 * i] = (int)undist_x(kps_[i]); xy[2 * i + 1] = (int)undist_y(kps_[i]); }
+        int n = 0;
+        for (auto& kv : core_.cur.kps) {
+            if (kv.second.is3d) continue;
+            if (n < cap_pairs) { xy[2 * n] = (int)kv.second.ux; xy[2 * n + 1] = (int)kv.second.uy; }
+            n++;
+        }
         return n;
     }
-    // the same keypoints with their track ids (== keypoint ids == map point ids, map_manager.cpp:166-191) and pixel positions
-    int getTracks(int32_t* ids, float* px, int cap) {
-        const int n = (int)kps_.size();
-        for (int i = 0; i < n && i < cap; i++) { ids[i] = kps_[i].id; px[2 * i] = kps_[i].x; px[2 * i + 1] = kps_[i].y; }
+    // every keypoint of the frame, in the frame's own order: track id (== keypoint id == map point id, map_manager.cpp:166-191),
+    // pixel position, 3-D flag and (for 3-D keypoints) the map point's world position
+    int getTracks(int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap) {
+        int n = 0;
+        for (auto& kv : core_.cur.kps) {
+            const alva_sys::Keypoint& k = kv.second;
+            if (n < cap) {
+                ids[n] = k.id; px[2 * n] = k.px; px[2 * n + 1] = k.py;
+                if (is3d) is3d[n] = k.is3d ? 1 : 0;
+                if (wpt) {
+                    auto mp = core_.mappoints.find(k.id);
+                    for (int i = 0; i < 3; i++) wpt[3 * n + i] = (mp != core_.mappoints.end() && mp->second.is3d) ? mp->second.p[i] : 0.0;
+                }
+            }
+            n++;
+        }
         return n;
     }
-
     // the keypoints' ORB descriptors (same order as getTracks): FeatureExtractor::describeFeaturePoints at keyframe creation
     // (feature_extractor.cpp:160-214; empty for points within 31 px of the border, orb.cpp:1130)
     int getDescriptors(uint8_t* desc, uint8_t* has, int cap) {
-        const int n = (int)kps_.size();
-        for (int i = 0; i < n && i < cap; i++) { memcpy(desc + 32 * (size_t)i, kps_[i].desc, 32); has[i] = kps_[i].has_desc ? 1 : 0; }
+        int n = 0;
+        for (auto& kv : core_.cur.kps) {
+            if (n < cap) { memcpy(desc + 32 * (size_t)n, kv.second.desc, 32); has[n] = kv.second.has_desc ? 1 : 0; }
+            n++;
+        }
         return n;
     }
-
-    int numMatched() const { return (int)kps_.size(); }
-    int initDue() const { return init_due_ ? 1 : 0; }
+    int getPose(double* Twc7) { core_.cur.Twc.to7(Twc7); return 0; }
+    // {frame id, keyframe id, #keypoints, #3-D keypoints, initialised, #keyframes, #occupied cells, #map point ids}
+    int getInfo(int32_t* out8) {
+        out8[0] = core_.cur.id; out8[1] = core_.cur.kfid; out8[2] = core_.cur.n; out8[3] = core_.cur.n3d;
+        out8[4] = core_.ready_for_init ? 1 : 0; out8[5] = core_.n_kf; out8[6] = core_.cur.nocc; out8[7] = core_.n_mp_ids;
+        return 0;
+    }
+    int numMatched() const { return core_.cur.n; }
     int device_ = 0;
 
 private:
-    struct Kp { int id; float x, y, kfx, kfy; bool has_desc; uint8_t desc[32]; };
-
-    // CameraCalibration::undistortImagePoint (camera_calibration.cpp:57-72): with the zero distortion the JS shim always passes
-    // (system.js:84-141) cv::undistortPoints returns the input to float precision; non-zero coefficients are not supported yet
-    float undist_x(const Kp& k) const { return k.x; }
-    float undist_y(const Kp& k) const { return k.y; }
-
-    int buildPyramid(const uint8_t* rgba) {
-        cudaStream_t st = ctx_->stream;
-        cur_ ^= 1;   // VisualFrontend::preprocessImage swaps prev / cur pyramids (visual_frontend.cpp:672-698)
-        ALVA_CUDA(cudaMemcpyAsync(rgba_dev_, rgba, (size_t)w_ * h_ * 4, cudaMemcpyHostToDevice, st));
-        uint8_t** L = img_[cur_];
-        if (int e = alva_k_frontend(ctx_, rgba_dev_, w_, h_, 1, L[0], nlev_ > 1 ? L[1] : nullptr, nlev_ > 2 ? L[2] : nullptr,
-                                    nlev_ > 3 ? L[3] : nullptr, 20, nullptr, nullptr, 0, 0))
-            return e;
-        const uint8_t* srcs[4] = {L[0], L[1], L[2], L[3]};
-        return alva_scharr_levels_launch(ctx_, nlev_, srcs, der_[cur_], lw_, lh_, 1);
+    static double nowMs() {   // system.cpp:114: milliseconds since the epoch
+        return (double)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
     }
-
-    // MapManager::createKeyframe on the current frame (map_manager.cpp:12-22): extractKeypoints -> new keypoints with fresh ids
-    int createKeyframe() {
-        cudaStream_t st = ctx_->stream;
-        const int n0 = (int)kps_.size();
-        for (int i = 0; i < n0; i++) { host_pts_[2 * i] = kps_[i].x; host_pts_[2 * i + 1] = kps_[i].y; }
-        int32_t ncur = n0;
-        if (n0) ALVA_CUDA(cudaMemcpyAsync(pts_dev_, host_pts_.data(), (size_t)n0 * 8, cudaMemcpyHostToDevice, st));
-        ALVA_CUDA(cudaMemcpyAsync(cnt_dev_ + 1, &ncur, 4, cudaMemcpyHostToDevice, st));
-        const int32_t roi[4] = {20, 20, w_ - 40, h_ - 40};   // CameraCalibration(..., imgBorder 20): roi_rect_ (camera_calibration.cpp:21)
-        // numToDetect = frameMaxNumKeypoints - occupied cells > 0 always holds before initialisation (map_manager.cpp:206-208)
-        if (int e = alva_k_detect_grid(ctx_, img_[cur_][0], w_, h_, 1, cell_, pts_dev_, cnt_dev_ + 1, cap_, roi, quality_dev_, pri_dev_,
-                                       nullptr, cnt_dev_, cap_))
-            return e;
-        int32_t n = 0;
-        ALVA_CUDA(cudaMemcpyAsync(&n, cnt_dev_, 4, cudaMemcpyDeviceToHost, st));
-        ALVA_CUDA(cudaMemcpyAsync(host_pts_.data(), pri_dev_, (size_t)cap_ * 8, cudaMemcpyDeviceToHost, st));
-        ALVA_CUDA(cudaStreamSynchronize(st));
-        if (n > cap_) n = cap_;
-        // describeFeaturePoints(imageRaw, newPoints) (map_manager.cpp:215-219): ORB::create(500, 1, 0)->compute at the new
-        // points = 7x7 blur (the shipped build's unfused arithmetic) + rBRIEF-256 steered by KeyPoint::convert's -1 degree
-        if (n > 0) {
-            if (int e = alva_k_orb_blur(ctx_, img_[cur_][0], blur_dev_, w_, h_, 1, 0)) return e;
-            if (int e = alva_k_orb_describe(ctx_, img_[cur_][0], blur_dev_, w_, h_, 1, pri_dev_, cnt_dev_, cap_, 0, desc_dev_, kept_dev_, nullptr)) return e;
-            ALVA_CUDA(cudaMemcpyAsync(host_desc_.data(), desc_dev_, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
-            ALVA_CUDA(cudaMemcpyAsync(host_good_.data(), kept_dev_, n, cudaMemcpyDeviceToHost, st));
-            ALVA_CUDA(cudaStreamSynchronize(st));
-        }
-        for (int i = 0; i < n; i++) {   // addKeypointsToFrame: id = running map point counter (map_manager.cpp:166-191)
-            Kp k{next_id_++, host_pts_[2 * i], host_pts_[2 * i + 1], 0.f, 0.f, host_good_[i] != 0, {0}};
-            if (k.has_desc) memcpy(k.desc, host_desc_.data() + 32 * (size_t)i, 32);
-            kps_.push_back(k);
-        }
-        for (auto& k : kps_) { k.kfx = k.x; k.kfy = k.y; }   // the keyframe is a copy of the frame (addKeyframe, :243-252)
-        return 0;
+    static void writePose(const alva_sys::Se3& T, float* p) {
+        double R[9];
+        T.R(R);
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) p[4 * r + c] = (float)R[3 * r + c]; p[4 * r + 3] = 0.f; }
+        p[12] = (float)T.t[0]; p[13] = (float)T.t[1]; p[14] = (float)T.t[2]; p[15] = 1.f;
     }
-
-    // VisualFrontend::kltTrackingFromMotionPrior with 2-D keypoints only: fbKltTracking(levels 3, error 30, fb distance 0.5)
-    int kltTrack() {
-        cudaStream_t st = ctx_->stream;
-        const int n = (int)kps_.size();
-        if (!n) return 0;
-        for (int i = 0; i < n; i++) { host_pts_[2 * i] = kps_[i].x; host_pts_[2 * i + 1] = kps_[i].y; }
-        ALVA_CUDA(cudaMemcpyAsync(pts_dev_, host_pts_.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        ALVA_CUDA(cudaMemcpyAsync(pri_dev_, pts_dev_, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-        const int prev = cur_ ^ 1;
-        if (int e = alva_k_klt_fb(ctx_, img_[prev], der_[prev], img_[cur_], der_[cur_], w_, h_, 1, nlev_ - 1, 3, 9, 30.0f, 0.5f, pts_dev_,
-                                  pri_dev_, nullptr, n, good_dev_))
-            return e;
-        ALVA_CUDA(cudaMemcpyAsync(host_pts_.data(), pri_dev_, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        ALVA_CUDA(cudaMemcpyAsync(host_good_.data(), good_dev_, n, cudaMemcpyDeviceToHost, st));
-        ALVA_CUDA(cudaStreamSynchronize(st));
-        std::vector<Kp> kept;
-        kept.reserve(n);
-        for (int i = 0; i < n; i++)
-            if (host_good_[i]) { Kp k = kps_[i]; k.x = host_pts_[2 * i]; k.y = host_pts_[2 * i + 1]; kept.push_back(k); }   // updateKeypoint
-        kps_.swap(kept);                                                                          // removeObsFromCurrFrameById
-        return 0;
-    }
-
-    // VisualFrontend::computeParallax(keyframe, doUnRotate = false, doMedian = true) (visual_frontend.cpp:596-670): the "median"
-    // is the element size/2 of a std::set<float>, i.e. of the DISTINCT parallax values
-    float medianParallax() const {
-        std::set<float> s;
-        for (const auto& k : kps_) {
-            const float dx = undist_x(k) - k.kfx, dy = undist_y(k) - k.kfy;
-            s.insert((float)sqrt((double)dx * dx + (double)dy * dy));   // cv::norm(Point2f) is computed in double
-        }
-        if (s.empty()) return 0.f;
-        auto it = s.begin();
-        std::advance(it, s.size() / 2);
-        return *it;
-    }
-
-    int processCameraPose(const uint8_t* rgba) {   // system.cpp:156-175 + VisualFrontend::track / process
-        frame_id_++;
-        if (int e = buildPyramid(rgba)) return e;
-        if (frame_id_ == 0) {   // first frame -> keyframe (visual_frontend.cpp:42-45, 27)
-            if (int e = createKeyframe()) return e;
-            return 3;
-        }
-        if (int e = kltTrack()) return e;
-        if (!ready_for_init_) {
-            if ((int)kps_.size() < 50) { reset(); return 2; }        // visual_frontend.cpp:54-58 -> system.cpp:163-167
-            // checkReadyForInit (visual_frontend.cpp:419-552): the 5-point initialisation is due once the median parallax
-            // exceeds State::minAvgRotationParallax_ = 40 px; it is not built yet, so the frame stays "not initialised"
-            init_due_ = medianParallax() > 40.0f;
-        }
-        return 3;
-    }
-
-    static void writeIdentity(float* p) {
-        for (int i = 0; i < 16; i++) p[i] = (i % 5 == 0) ? 1.f : 0.f;
-    }
-
-    void release() {
-        if (rgba_dev_) { cudaFree(rgba_dev_); rgba_dev_ = nullptr; }
-        for (int s = 0; s < 2; s++)
-            for (int k = 0; k < 4; k++) {
-                if (img_[s][k]) { cudaFree(img_[s][k]); img_[s][k] = nullptr; }
-                if (der_[s][k]) { cudaFree(der_[s][k]); der_[s][k] = nullptr; }
-            }
-        if (pts_dev_) { cudaFree(pts_dev_); pts_dev_ = nullptr; }
-        if (pri_dev_) { cudaFree(pri_dev_); pri_dev_ = nullptr; }
-        if (good_dev_) { cudaFree(good_dev_); good_dev_ = nullptr; }
-        if (cnt_dev_) { cudaFree(cnt_dev_); cnt_dev_ = nullptr; }
-        if (quality_dev_) { cudaFree(quality_dev_); quality_dev_ = nullptr; }
-        if (blur_dev_) { cudaFree(blur_dev_); blur_dev_ = nullptr; }
-        if (desc_dev_) { cudaFree(desc_dev_); desc_dev_ = nullptr; }
-        if (kept_dev_) { cudaFree(kept_dev_); kept_dev_ = nullptr; }
-        if (ctx_) { alva_ctx_destroy(ctx_); ctx_ = nullptr; }
-        configured_ = false;
-    }
-
-    alva_ctx* ctx_ = nullptr;
-    uint8_t* rgba_dev_ = nullptr;
-    uint8_t* img_[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    int16_t* der_[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    float *pts_dev_ = nullptr, *pri_dev_ = nullptr;
-    uint8_t* good_dev_ = nullptr;
-    int32_t* cnt_dev_ = nullptr;
-    double* quality_dev_ = nullptr;
-    uint8_t *blur_dev_ = nullptr, *desc_dev_ = nullptr, *kept_dev_ = nullptr;
-    std::vector<uint8_t> host_desc_;
-    std::vector<float> host_pts_;
-    std::vector<uint8_t> host_good_;
-    std::vector<Kp> kps_;
-    int w_ = 0, h_ = 0, cell_ = 40, max_kps_ = 0, cap_ = 0, nlev_ = 0, cur_ = 0, next_id_ = 0;
-    int lw_[4] = {0, 0, 0, 0}, lh_[4] = {0, 0, 0, 0};
-    long long frame_id_ = -1;
-    double K_[4] = {0, 0, 0, 0}, dist_[4] = {0, 0, 0, 0};
-    bool configured_ = false, ready_for_init_ = false, init_due_ = false;
+    CudaBackend be_;
+    alva_sys::SystemCore<CudaBackend> core_;
+    bool configured_ = false;
+    double imu_t_[3] = {0, 0, 0}, imu_prev_[3] = {0, 0, 0};
 };
 
 struct alva_system { System sys; };
@@ -315,6 +374,10 @@ extern "C" int alva_system_find_camera_pose(alva_system* s, const uint8_t* rgba,
     if (!s || !rgba || !pose16) { alva_set_error("alva_system_find_camera_pose: bad argument"); return ALVA_E_INVALID; }
     return s->sys.findCameraPose(rgba, pose16);
 }
+extern "C" int alva_system_find_camera_pose_ts(alva_system* s, const uint8_t* rgba, double t_ms, float* pose16) {
+    if (!s || !rgba || !pose16) { alva_set_error("alva_system_find_camera_pose_ts: bad argument"); return ALVA_E_INVALID; }
+    return s->sys.findCameraPose(rgba, t_ms, pose16);
+}
 extern "C" int alva_system_find_camera_pose_imu(alva_system* s, const uint8_t* rgba, const double* imu, float* pose16) {
     if (!s || !rgba || !imu || !pose16) { alva_set_error("alva_system_find_camera_pose_imu: bad argument"); return ALVA_E_INVALID; }
     return s->sys.findCameraPoseWithIMU(rgba, imu, pose16);
@@ -328,12 +391,13 @@ extern "C" int alva_system_get_frame_points(alva_system* s, int32_t* xy, int cap
     return s->sys.getFramePoints(xy, cap_pairs);
 }
 extern "C" int alva_system_num_matched(alva_system* s) { return s ? s->sys.numMatched() : ALVA_E_INVALID; }
-extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, int cap) {
+extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap) {
     if (!s || !ids || !px || cap < 0) return ALVA_E_INVALID;
-    return s->sys.getTracks(ids, px, cap);
+    return s->sys.getTracks(ids, px, is3d, wpt, cap);
 }
 extern "C" int alva_system_get_descriptors(alva_system* s, uint8_t* desc, uint8_t* has, int cap) {
     if (!s || !desc || !has || cap < 0) return ALVA_E_INVALID;
     return s->sys.getDescriptors(desc, has, cap);
 }
-extern "C" int alva_system_init_due(alva_system* s) { return s ? s->sys.initDue() : ALVA_E_INVALID; }
+extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
+extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }

@@ -22,9 +22,9 @@
 // order, detector masks), so the iteration ORDER is part of its behaviour; the same container type with the same sequence of
 // insertions / erasures / copies is used here (libstdc++ is deterministic for equal histories).
 //
-// Not wired yet (the kernels exist and are parity-tested on their own): Mapper::matchingToLocalMap -> alva_k_match_to_map +
-// mergeMapPoints, Optimizer::localBA -> alva_k_ba_local, map filtering (mapper.cpp:66-155).  Poses therefore follow the
-// reference until its first local BA (keyframe id 2) and stay a plain keyframe-based visual odometry afterwards.
+//   mapper.cpp:66-155, 293-352               Mapper::optimize (local BA from keyframe 2, keyframe filtering from 20), matchingToLocalMap
+//   optimizer.cpp:4-531                      Optimizer::localBA: assembly, write-back, culling (the solves: Backend::ba_local)
+//   map_manager.cpp:407-575                  mergeMapPoints, removeKeyframe, removeMapPoint
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -163,6 +163,13 @@ struct Camera {
         bv[2] = (0.0 * (double)ux + 0.0 * (double)uy) + k22 * 1.0;
         const double n = sqrt((bv[0] * bv[0] + bv[1] * bv[1]) + bv[2] * bv[2]);
         bv[0] /= n; bv[1] /= n; bv[2] /= n;
+    }
+    void inverseK(float ux, float uy, double* b) const {   // inverseK_ * [unpx, 1] (not normalised)
+        const double id = 1. / (fx * fy);
+        const double k00 = fy * id, k02 = (-(cx * fy)) * id, k11 = fx * id, k12 = (-(fx * cy)) * id, k22 = (fx * fy) * id;
+        b[0] = (k00 * (double)ux + 0.0 * (double)uy) + k02 * 1.0;
+        b[1] = (0.0 * (double)ux + k11 * (double)uy) + k12 * 1.0;
+        b[2] = (0.0 * (double)ux + 0.0 * (double)uy) + k22 * 1.0;
     }
     void projCamToImage(const double* p, float& u, float& v) const {   // camera_calibration.cpp:26-32
         const double iz = 1. / p[2];
@@ -313,6 +320,11 @@ struct MapPoint {
     bool has_desc = false;
     Desc desc;                                       // desc_
 
+    bool isBad() {   // map_point.cpp:183-202 (it demotes the point as a side effect)
+        if (obs.size() < 2 && !observed && is3d) { is3d = false; return true; }
+        if (obs.size() == 0 && !observed) { is3d = false; return true; }
+        return false;
+    }
     // MapPoint::addDesc (map_point.cpp:129-180): keeps every keyframe's descriptor and the running distance sums; desc_ ends up
     // equal to the most recently added one
     void addDesc(int kf, const uint8_t* d) {
@@ -383,6 +395,35 @@ struct MotionModel {   // visual_frontend.hpp:17-56
     void reset() { prevTime = -1.; for (int i = 0; i < 6; i++) logRel[i] = 0; }
 };
 
+// ------------------------------------------------------------------------------------------------ flat problems handed to a Backend
+struct BaProblem {   // the layout of alva_k_ba_local
+    int nkf = 0, nlm = 0, nobs = 0;
+    double calib[4] = {0, 0, 0, 0};
+    std::vector<double> poses;          // [nkf][7] in/out
+    std::vector<uint8_t> pose_const;    // [nkf]
+    std::vector<double> invd;           // [nlm] in/out
+    std::vector<int32_t> anch_kf;       // [nlm] keyframe index
+    std::vector<double> anch_uv;        // [nlm][2]
+    std::vector<int32_t> obs_kf, obs_lm;
+    std::vector<double> obs_uv;         // [nobs][2]
+};
+struct MatchProblem {   // Mapper::matchToMap on flat arrays (alva_k_match_to_map / orc_match_to_map)
+    double Twc_cur[7];
+    int nkp3d = 0;
+    std::vector<int32_t> kp_id, kp_mp;  // keypoints cell by cell; kp_mp = index of the keypoint's own map point in the table
+    std::vector<float> kp_px;
+    std::vector<int32_t> kf_id;         // keyframes referenced by the observations
+    std::vector<double> kf_Twc;
+    std::vector<int32_t> mp_id;         // map point table
+    std::vector<double> mp_wpt;
+    std::vector<uint8_t> mp_is3d;
+    std::vector<int32_t> obs_start, obs_kfid;   // CSR; obs_kfid = keyframe ID, ascending per point
+    std::vector<float> obs_px;
+    std::vector<int32_t> desc_start, desc_kfid;
+    std::vector<uint8_t> desc;
+    std::vector<int32_t> local_mp;      // table indices of the local map, in the set's iteration order
+};
+
 // ------------------------------------------------------------------------------------------------ the state machine
 // Backend concept (host pointers in, host pointers out; < 0 = ALVA_E_* error):
 //   int pyramid(const uint8_t* rgba)                       gray + pyramid + Scharr levels of the new frame; previous <- current
@@ -393,6 +434,8 @@ struct MotionModel {   // visual_frontend.hpp:17-56
 //   int p3p(const double* bv, const double* X, int n, float fx, float fy, double* T12, uint8_t* outlier)            -> 1 / 0
 //   int pnp(const double* uv, const double* X, int n, const double* K4, double* pose7, uint8_t* outlier)            -> 1 / 0
 //   int triangulate(const double* Tlr7, const double* bvl, const double* bvr, int n, double* out)
+//   bool has_ba_local(); int ba_local(BaProblem& io, int32_t* flags)         Optimizer::localBA's numerical body (two solves + flags)
+//   bool has_match_to_map(); int match_to_map(const MatchProblem&, std::vector<int>& kp_match)   Mapper::matchToMap
 template <class Backend>
 class SystemCore {
 public:
@@ -588,7 +631,277 @@ private:
         }
         updateFrameCovisibility(*kf);
         cur.covis = kf->covis;
-        // matchingToLocalMap (kfid > 0) and optimize (local BA from keyframe 2, map filtering from keyframe 20): not wired yet
+        if (kfid > 0) matchingToLocalMap(*kf);
+        if (err) return;
+        // Mapper::optimize (mapper.cpp:66-155)
+        if (kf->kfid >= 2 && kf->n3d != 0) localBA(*kf);
+        if (err) return;
+        if (kf->kfid >= 20) filterKeyframes(*kf);   // State::mapKeyframeFilteringRatio_ = 0.95 < 1
+    }
+
+    // Mapper::matchingToLocalMap (mapper.cpp:293-352) + MapManager::mergeMapPoints (map_manager.cpp:407-495)
+    void matchingToLocalMap(Frame& frame) {
+        const size_t max_local = (size_t)max_kps * 10;
+        const std::map<int, int> cov = frame.covis;
+        if (!cov.empty() && frame.localmap.size() < max_local) {
+            int kfid = cov.begin()->first;
+            auto kf = keyframes.find(kfid);
+            while (kf == keyframes.end() && kfid > 0) { kfid--; kf = keyframes.find(kfid); }
+            if (kf != keyframes.end()) {
+                const std::unordered_set<int> add = kf->second->localmap;
+                frame.localmap.insert(add.begin(), add.end());
+                // "another round" looks the same keyframe up again (mapper.cpp:318-331): its set is already merged
+            }
+        }
+        if (frame.localmap.empty() || !B.has_match_to_map()) return;
+        MatchProblem mp;
+        buildMatchProblem(frame, mp);
+        std::vector<int> kp_match(mp.kp_id.size(), -1);
+        if ((err = B.match_to_map(mp, kp_match)) < 0) return;
+        err = 0;
+        std::map<int, int> prev_new;   // keypoint (= its own map point) id -> matched local map point id, ascending
+        for (size_t i = 0; i < kp_match.size(); i++)
+            if (kp_match[i] >= 0) prev_new.emplace(mp.kp_id[i], mp.mp_id[kp_match[i]]);
+        for (auto& kv : prev_new) mergeMapPoints(kv.first, kv.second);
+    }
+
+    void mergeMapPoints(int prev, int next) {
+        auto pit = mappoints.find(prev), nit = mappoints.find(next);
+        if (pit == mappoints.end() || nit == mappoints.end() || !nit->second.is3d) return;
+        const std::set<int> next_kfs = nit->second.obs, prev_kfs = pit->second.obs;
+        const std::unordered_map<int, Desc> prev_desc = pit->second.kfdesc;
+        for (int pk : prev_kfs) {
+            auto kf = keyframes.find(pk);
+            if (kf == keyframes.end()) continue;
+            if (kf->second->updateId(prev, next, nit->second.is3d)) {
+                nit->second.obs.insert(pk);
+                for (int nk : next_kfs) {
+                    auto co = keyframes.find(nk);
+                    if (co != keyframes.end()) { kf->second->covisAdd(nk); co->second->covisAdd(pk); }
+                }
+            }
+        }
+        for (auto& kv : prev_desc) nit->second.addDesc(kv.first, kv.second.b);
+        if (cur.kps.count(prev) && cur.updateId(prev, next, nit->second.is3d)) nit->second.observed = true;
+        mappoints.erase(prev);
+    }
+
+    void buildMatchProblem(const Frame& frame, MatchProblem& m) {
+        frame.Twc.to7(m.Twc_cur);
+        m.nkp3d = frame.n3d;
+        // the frame's keypoints cell by cell, each cell in its insertion order (what Frame::getSurroundingKeypoints walks)
+        std::unordered_map<int, int> mp_index;
+        auto add_mp = [&](int id) -> int {
+            auto it = mp_index.find(id);
+            if (it != mp_index.end()) return it->second;
+            auto mp = mappoints.find(id);
+            if (mp == mappoints.end()) return -1;
+            const int idx = (int)m.mp_id.size();
+            mp_index.emplace(id, idx);
+            m.mp_id.push_back(id);
+            m.mp_is3d.push_back(mp->second.is3d ? 1 : 0);
+            for (int i = 0; i < 3; i++) m.mp_wpt.push_back(mp->second.p[i]);
+            for (int k : mp->second.obs) {   // ascending keyframe id
+                auto kf = keyframes.find(k);
+                if (kf == keyframes.end()) continue;
+                const Keypoint* kk = kf->second->find(id);
+                if (!kk) continue;
+                int ki = -1;
+                for (size_t j = 0; j < m.kf_id.size(); j++) if (m.kf_id[j] == k) ki = (int)j;
+                if (ki < 0) { ki = (int)m.kf_id.size(); m.kf_id.push_back(k); double T[7]; kf->second->Twc.to7(T); m.kf_Twc.insert(m.kf_Twc.end(), T, T + 7); }
+                m.obs_kfid.push_back(k); m.obs_px.push_back(kk->px); m.obs_px.push_back(kk->py);
+            }
+            m.obs_start.push_back((int)m.obs_kfid.size());
+            for (auto& kv : mp->second.kfdesc) { m.desc_kfid.push_back(kv.first); m.desc.insert(m.desc.end(), kv.second.b, kv.second.b + 32); }
+            m.desc_start.push_back((int)m.desc_kfid.size());
+            return idx;
+        };
+        m.obs_start.push_back(0); m.desc_start.push_back(0);
+        for (const auto& cellv : frame.grid)
+            for (int id : cellv) {
+                const Keypoint* k = frame.find(id);
+                if (!k) continue;
+                m.kp_id.push_back(id); m.kp_px.push_back(k->px); m.kp_px.push_back(k->py);
+                m.kp_mp.push_back(add_mp(id));
+            }
+        for (int id : frame.localmap) { const int idx = add_mp(id); if (idx >= 0) m.local_mp.push_back(idx); }   // the set's iteration order
+    }
+
+    void removeMapPoint(int id) {   // map_manager.cpp:532-575
+        auto it = mappoints.find(id);
+        if (it == mappoints.end()) return;
+        const std::set<int> obs = it->second.obs;
+        for (int k : obs) {
+            auto kf = keyframes.find(k);
+            if (kf == keyframes.end()) continue;
+            kf->second->remove(id);
+            for (int co : obs)
+                if (co != k) kf->second->covisDecrease(co);
+        }
+        if (it->second.observed) cur.remove(id);
+        mappoints.erase(it);
+    }
+
+    void filterKeyframes(Frame& keyframe) {   // mapper.cpp:73-155
+        const std::map<int, int> cov = keyframe.covis;
+        for (auto it = cov.rbegin(); it != cov.rend(); ++it) {
+            const int kfid = it->first;
+            if (kfid == 0) break;
+            if (kfid >= keyframe.kfid) continue;
+            auto kfit = keyframes.find(kfid);
+            if (kfit == keyframes.end()) continue;   // (the reference dereferences a null pointer here)
+            std::shared_ptr<Frame> kf = kfit->second;
+            if (kf->n3d < 25 / 2) { removeKeyframe(kfid); continue; }
+            size_t good = 0, total = 0;
+            for (const Keypoint& k : kf->all3d()) {
+                auto mp = mappoints.find(k.id);
+                if (mp == mappoints.end()) { removeMapPointObs(k.id, kfid); continue; }
+                if (mp->second.isBad()) continue;
+                if (mp->second.obs.size() > 4) good++;
+                total++;
+            }
+            if ((float)good / (float)total > 0.95f) removeKeyframe(kfid);
+        }
+    }
+
+    // Optimizer::localBA (optimizer.cpp:4-531): assembly in the reference's order, the numerical body on the device
+    // (Backend::ba_local = alva_k_ba_local: two solves + both outlier passes), write-back and culling
+    void localBA(Frame& nf) {
+        const int min_cov = 25;   // State::baMinNumCommonKeypointsObservations_
+        if (nf.n3d < min_cov || !B.has_ba_local()) return;
+        std::map<int, int> cov = nf.covis;
+        cov.emplace(nf.kfid, nf.n3d);
+        std::unordered_map<int, std::shared_ptr<Frame>> local_kfs;   // map_local_pkfs (its iteration order fixes the gauge)
+        std::unordered_set<int> bad_lms, lms2opt, cst_kfs;
+        std::vector<int> kf_ids;                      // pose blocks in creation order
+        std::unordered_map<int, int> kf_index;
+        std::vector<double> poses;
+        auto add_pose = [&](int kfid, const std::shared_ptr<Frame>& kf) {
+            kf_index.emplace(kfid, (int)kf_ids.size());
+            kf_ids.push_back(kfid);
+            double T[7];
+            kf->Twc.to7(T);
+            poses.insert(poses.end(), T, T + 7);
+        };
+        bool all_cst = false;
+        const int nmaxkfid = cov.rbegin()->first;
+        for (auto it = cov.rbegin(); it != cov.rend(); ++it) {
+            const int kfid = it->first;
+            int score = it->second;
+            if (kfid > nf.kfid) score = nf.n;
+            auto kfit = keyframes.find(kfid);
+            if (kfit == keyframes.end()) { if (kfid != nf.kfid) nf.covis.erase(kfid); continue; }
+            add_pose(kfid, kfit->second);
+            if (score >= min_cov && !all_cst && kfid > 0) {
+                for (const Keypoint& k : kfit->second->all3d()) lms2opt.insert(k.id);
+            } else { cst_kfs.insert(kfid); all_cst = true; }
+            local_kfs.emplace(kfid, kfit->second);
+        }
+        struct Lm { int id, anch_kf; double au, av, invd; };
+        std::vector<Lm> lms;
+        std::unordered_map<int, int> lm_index;
+        std::unordered_map<int, bool> local_lms;      // map_local_plms (keys; iterated in this container's order below)
+        std::vector<int> obs_kf, obs_lm;
+        std::vector<double> obs_uv;
+        for (int lmid : lms2opt) {
+            auto mpit = mappoints.find(lmid);
+            if (mpit == mappoints.end()) continue;
+            MapPoint& mp = mpit->second;
+            if (mp.isBad()) { bad_lms.insert(lmid); continue; }
+            local_lms.emplace(lmid, true);
+            int anch = -1;
+            for (int kfid : std::set<int>(mp.obs)) {
+                if (kfid > nmaxkfid) continue;
+                auto lk = local_kfs.find(kfid);
+                std::shared_ptr<Frame> kf;
+                if (lk == local_kfs.end()) {
+                    auto kfit = keyframes.find(kfid);
+                    if (kfit == keyframes.end()) { removeMapPointObs(kfid, mp.id); continue; }   // (argument order as in the reference)
+                    kf = kfit->second;
+                    local_kfs.emplace(kfid, kf);
+                    add_pose(kfid, kf);
+                    cst_kfs.insert(kfid);
+                } else kf = lk->second;
+                const Keypoint* kp = kf->find(lmid);
+                if (!kp) { removeMapPointObs(lmid, kfid); continue; }
+                if (anch < 0) {
+                    anch = kfid;
+                    double c[3];
+                    kf->Tcw.apply(mp.p, c);
+                    lm_index.emplace(lmid, (int)lms.size());
+                    lms.push_back({lmid, kf_index.at(kfid), (double)kp->ux, (double)kp->uy, 1. / c[2]});
+                    continue;
+                }
+                obs_kf.push_back(kf_index.at(kfid)); obs_lm.push_back(lm_index.at(lmid));
+                obs_uv.push_back(kp->ux); obs_uv.push_back(kp->uy);
+            }
+        }
+        size_t ncst = cst_kfs.size();
+        if (ncst < 2)
+            for (auto it = local_kfs.begin(); ncst < 2 && it != local_kfs.end(); ++it) { cst_kfs.insert(it->first); ncst++; }   // optimizer.cpp:240-248 (counts even a repeat)
+        // ---- numerical body.  Landmarks without a residual are not part of Ceres' reduced program: leave them out
+        const int nkf = (int)kf_ids.size(), nobs = (int)obs_lm.size();
+        std::vector<int> used(lms.size(), -1), lm_of;
+        for (int o = 0; o < nobs; o++) if (used[obs_lm[o]] < 0) { used[obs_lm[o]] = (int)lm_of.size(); lm_of.push_back(obs_lm[o]); }
+        std::vector<int32_t> flags(nobs + 1, 0);
+        if (nobs > 0) {
+            BaProblem bp;
+            bp.nkf = nkf; bp.nlm = (int)lm_of.size(); bp.nobs = nobs;
+            bp.calib[0] = cam.fx; bp.calib[1] = cam.fy; bp.calib[2] = cam.cx; bp.calib[3] = cam.cy;
+            bp.poses = poses;
+            bp.pose_const.resize(nkf);
+            for (int i = 0; i < nkf; i++) bp.pose_const[i] = cst_kfs.count(kf_ids[i]) ? 1 : 0;
+            for (int l : lm_of) { bp.invd.push_back(lms[l].invd); bp.anch_kf.push_back(lms[l].anch_kf); bp.anch_uv.push_back(lms[l].au); bp.anch_uv.push_back(lms[l].av); }
+            bp.obs_kf.assign(obs_kf.begin(), obs_kf.end());
+            for (int o = 0; o < nobs; o++) bp.obs_lm.push_back(used[obs_lm[o]]);
+            bp.obs_uv = obs_uv;
+            if ((err = B.ba_local(bp, flags.data())) < 0) return;
+            err = 0;
+            poses = bp.poses;
+            for (size_t i = 0; i < lm_of.size(); i++) lms[lm_of[i]].invd = bp.invd[i];
+        }
+        // ---- 5. update state (optimizer.cpp:361-531): pass-1 outliers first, then pass-2, as badKeyframeLandmarkIds is filled
+        std::vector<std::pair<int, int>> bad;
+        for (int pass = 1; pass <= 2; pass++)
+            for (int o = 0; o < nobs; o++)
+                if (flags[o] == pass) { bad.emplace_back(kf_ids[obs_kf[o]], lms[obs_lm[o]].id); bad_lms.insert(lms[obs_lm[o]].id); }
+        for (auto& pr : bad) {
+            if (local_kfs.count(pr.first)) removeMapPointObs(pr.second, pr.first);
+            if (pr.first == cur.kfid) removeObsFromCurr(pr.second);
+            bad_lms.insert(pr.second);
+        }
+        for (auto& kv : local_kfs) {
+            if (cst_kfs.count(kv.first)) continue;
+            kv.second->setTwc(Se3::from7(&poses[7 * (size_t)kf_index.at(kv.first)]));
+        }
+        for (auto& kv : local_lms) {
+            const int lmid = kv.first;
+            auto mpit = mappoints.find(lmid);
+            if (mpit == mappoints.end()) { bad_lms.erase(lmid); continue; }
+            MapPoint& mp = mpit->second;
+            if (mp.isBad()) { removeMapPoint(lmid); bad_lms.erase(lmid); continue; }
+            if (mp.obs.size() < 3 && mp.kfid < nf.kfid - 3 && !mp.observed) { removeMapPoint(lmid); bad_lms.erase(lmid); continue; }
+            auto li = lm_index.find(lmid);
+            if (li == lm_index.end()) { bad_lms.insert(lmid); continue; }
+            const double invd = lms[li->second].invd, zanch = 1. / invd;
+            if (zanch <= 0.) { removeMapPoint(lmid); bad_lms.erase(lmid); continue; }
+            auto ak = local_kfs.find(mp.kfid);
+            if (ak == local_kfs.end()) { bad_lms.insert(lmid); continue; }
+            const Keypoint* kp = ak->second->find(lmid);
+            float ux = 0.f, uy = 0.f;   // a missing keypoint yields the reference's default Keypoint (unpx = 0, 0)
+            if (kp) { ux = kp->ux; uy = kp->uy; }
+            double b[3], c[3], wpt[3];
+            cam.inverseK(ux, uy, b);
+            for (int i = 0; i < 3; i++) c[i] = zanch * b[i];
+            ak->second->Twc.apply(c, wpt);
+            updateMapPoint(lmid, wpt, invd);
+        }
+        for (int lmid : std::unordered_set<int>(bad_lms)) {
+            auto mpit = mappoints.find(lmid);
+            if (mpit == mappoints.end()) continue;
+            if (mpit->second.isBad()) removeMapPoint(lmid);
+            else if (mpit->second.obs.size() < 3 && mpit->second.kfid < nf.kfid - 3 && !mpit->second.observed) removeMapPoint(lmid);
+        }
     }
 
     void removeKeyframe(int kfid) {   // map_manager.cpp:497-530

@@ -346,19 +346,25 @@ int  alva_system_configure(alva_system*, int w, int h, double fx, double fy, dou
                            double k1, double k2, double p1, double p2);
 int  alva_system_reset(alva_system*);
 int  alva_system_find_camera_pose(alva_system*, const uint8_t* rgba, float* pose16);
+/* the same with the frame's time stamp (milliseconds) supplied by the caller instead of read from the system clock
+ * (system.cpp:114): deterministic replays, and hosts that deliver frames faster than real time (two frames inside one
+ * millisecond give the reference's motion model dt = 0) */
+int  alva_system_find_camera_pose_ts(alva_system*, const uint8_t* rgba, double t_ms, float* pose16);
 int  alva_system_find_camera_pose_imu(alva_system*, const uint8_t* rgba, const double* imu, float* pose16);
 int  alva_system_find_plane(alva_system*, float* out16, int iterations);
 int  alva_system_get_frame_points(alva_system*, int32_t* xy, int cap_pairs);   /* returns the true count */
-int  alva_system_num_matched(alva_system*);   /* keypoints of the current frame that are tracked from the last keyframe */
-/* the frame's keypoints with their track ids (keypoint id == map point id, src/slam/src/map_manager.cpp:166-191) and
- * pixel positions px [cap][2]; returns the true count */
-int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, int cap);
+int  alva_system_num_matched(alva_system*);   /* keypoints of the current frame (Frame::numKeypoints_) */
+/* every keypoint of the current frame in the frame's own order: track ids (keypoint id == map point id,
+ * src/slam/src/map_manager.cpp:166-191), pixel positions px [cap][2], and optionally is3d [cap] and the map points' world
+ * positions wpt [cap][3] (zeros for 2-D keypoints); returns the true count */
+int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap);
 /* their 256-bit ORB descriptors (Keypoint::desc_, feature_extractor.cpp:160-214), same order: desc [cap][32], has [cap] (0 = the
  * reference keeps an empty Mat: point within 31 px of the border) */
 int  alva_system_get_descriptors(alva_system*, uint8_t* desc, uint8_t* has, int cap);
-/* 1 once the reference's initialisation test has fired (median parallax > 40 px, visual_frontend.cpp:419-430); the
- * 5-point initialisation itself is not built yet, so the status stays 3 */
-int  alva_system_init_due(alva_system*);
+/* the current frame's camera-to-world pose in double: [t, q(x,y,z,w)] */
+int  alva_system_get_pose(alva_system*, double* Twc7);
+/* {frame id, keyframe id, #keypoints, #3-D keypoints, initialised, #keyframes, #occupied grid cells, #map point ids} */
+int  alva_system_get_info(alva_system*, int32_t* out8);
 
 /* ---- host-buffer variants (copies inside; used for e2e timing and by non-CUDA hosts) ---------- */
 int alva_h_frontend(alva_ctx*, const uint8_t* rgba_host, int w, int h, int nframes, int thr,

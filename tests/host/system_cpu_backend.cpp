@@ -27,6 +27,14 @@ int orc_p3p_lmeds(const double* bvs, const double* wpts, int n, int max_iter, fl
 int orc_pnp(const double* K, const double* uv, const double* X, int n, double* pose, double huber_delta, double chi2_thr,
             int max_iter, int use_robust, int apply_l2, uint8_t* outlier, double* summary);
 void orc_triangulate(const double* Tlr, const double* bvl, const double* bvr, int n, double* out);
+int orc_ba_local(const double* calib, double* poses, const uint8_t* pose_const, int nkf, double* invd, const int32_t* anch_kf,
+                 const double* anch_uv, int nlm, const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, int nobs,
+                 double huber_delta, double chi2_thr, int max_iter, int32_t* flags, double* summary);
+int orc_match_to_map(int w, int h, double fx, double fy, double cx, double cy, const double* Twc_cur, int n_kp, const int32_t* kp_id,
+                     const float* kp_px, int nkp3d, int n_kf, const int32_t* kf_id, const double* kf_Twc, int n_mp, const int32_t* mp_id,
+                     const double* mp_wpt, const uint8_t* mp_is3d, const int32_t* obs_start, const int32_t* obs_kf, const float* obs_px,
+                     const int32_t* desc_start, const int32_t* desc_kf, const uint8_t* desc, int n_local, const int32_t* local_ids,
+                     float max_proj_err, float dist_ratio, int32_t* match_kp, int32_t* match_mp);
 }
 
 struct CpuBackend {
@@ -93,6 +101,34 @@ struct CpuBackend {
         return orc_pnp(K4, uv, X, n, pose7, std::sqrt((double)chi2), (double)chi2, 5, 1, 1, outl, summary);
     }
     int triangulate(const double* T7, const double* bl, const double* br, int n, double* out) { orc_triangulate(T7, bl, br, n, out); return 0; }
+    bool enable_ba = true, enable_match = true;
+    double fx = 0, fy = 0, cx = 0, cy = 0;
+    bool has_ba_local() const { return enable_ba; }
+    bool has_match_to_map() const { return enable_match; }
+    int ba_local(alva_sys::BaProblem& bp, int32_t* flags) {
+        double summary[10];
+        const float chi2 = 5.9915f;   // State::robustCostThreshold_ (float); Huber width std::sqrt(float)
+        orc_ba_local(bp.calib, bp.poses.data(), bp.pose_const.data(), bp.nkf, bp.invd.data(), bp.anch_kf.data(), bp.anch_uv.data(), bp.nlm,
+                     bp.obs_kf.data(), bp.obs_lm.data(), bp.obs_uv.data(), bp.nobs, (double)std::sqrt(chi2), (double)chi2, 5, flags, summary);
+        return 0;
+    }
+    int match_to_map(const alva_sys::MatchProblem& m, std::vector<int>& kp_match) {
+        const int n_kp = (int)m.kp_id.size(), n_mp = (int)m.mp_id.size();
+        std::vector<int32_t> obs_kf(m.obs_kfid.size()), local_ids(m.local_mp.size()), mk(n_kp + 1), mm(n_kp + 1);
+        for (size_t o = 0; o < obs_kf.size(); o++) { int ki = 0; while (m.kf_id[ki] != m.obs_kfid[o]) ki++; obs_kf[o] = ki; }
+        for (size_t i = 0; i < local_ids.size(); i++) local_ids[i] = m.mp_id[m.local_mp[i]];
+        const int n = orc_match_to_map(w, h, fx, fy, cx, cy, m.Twc_cur, n_kp, m.kp_id.data(), m.kp_px.data(), m.nkp3d, (int)m.kf_id.size(),
+                                       m.kf_id.data(), m.kf_Twc.data(), n_mp, m.mp_id.data(), m.mp_wpt.data(), m.mp_is3d.data(), m.obs_start.data(),
+                                       obs_kf.data(), m.obs_px.data(), m.desc_start.data(), m.desc_kfid.data(), m.desc.data(), (int)local_ids.size(),
+                                       local_ids.data(), 2.0f, 0.2f, mk.data(), mm.data());
+        for (int i = 0; i < n; i++) {
+            int ki = 0, mi = 0;
+            while (m.kp_id[ki] != mk[i]) ki++;
+            while (m.mp_id[mi] != mm[i]) mi++;
+            kp_match[ki] = mi;
+        }
+        return 0;
+    }
 };
 
 struct CpuSystem {
@@ -105,12 +141,14 @@ extern "C" {
 void* cpu_system_create(int w, int h, double fx, double fy, double cx, double cy) {
     CpuSystem* s = new CpuSystem();
     s->be.init(w, h);
+    s->be.fx = fx; s->be.fy = fy; s->be.cx = cx; s->be.cy = cy;
     s->core.configure(w, h, fx, fy, cx, cy);
     return s;
 }
 void cpu_system_set_essential_hook(void* p, void* fn) {
     ((CpuSystem*)p)->be.essential_hook = (int (*)(const double*, const double*, int, int, float, int, float, float, double*, uint8_t*))fn;
 }
+void cpu_system_enable(void* p, int ba, int match) { ((CpuSystem*)p)->be.enable_ba = ba != 0; ((CpuSystem*)p)->be.enable_match = match != 0; }
 void cpu_system_destroy(void* p) { delete (CpuSystem*)p; }
 int cpu_system_process(void* p, const uint8_t* rgba, double t_ms, double* Twc7) {
     CpuSystem* s = (CpuSystem*)p;

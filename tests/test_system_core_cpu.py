@@ -1,0 +1,96 @@
+"""CPU tests of the host-side System state machine (alvaar_b200/csrc/system_core.h) -- the code that, in the product, drives
+the CUDA kernels -- instantiated over the CPU oracle backend (test infrastructure) and compared with a 40-frame trace of the
+reference's own System (tests/golden/system.npz, dumped by tools/make_golden_system.py).
+
+What is exact: status codes, track ids IN THE REFERENCE'S ITERATION ORDER (it decides RANSAC sample indices and Ceres residual
+order), 3-D flags, keyframe events, frame counters -- over all 40 frames, i.e. also after the reference's first local BA --
+and, before the initialisation, every pixel position bit for bit.
+What is toleranced: after the initialisation poses / world points carry the reference's own noise-limited 5-point refinement
+(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2, |dq| < 1e-3 up to its first local
+BA.  With the reference's OWN initialisation stage plugged in (live reference only) everything downstream is in lockstep: poses
+1e-9, pixel positions bit-identical, until the first local BA (not wired yet)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import P
+from system_util import CAP, cpu_system_lib, frame_slice, frames_and_golden, quat_dist
+
+
+def run(S, frames, K, hook=None):
+    w, h = frames.shape[2], frames.shape[1]
+    s = S.cpu_system_create(w, h, K[0], K[1], K[2], K[3])
+    if hook is not None:
+        S.cpu_system_set_essential_hook(s, hook)
+    out = []
+    for k in range(len(frames)):
+        T = np.zeros(7)
+        st = S.cpu_system_process(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(T))
+        ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3)); info = np.zeros(8, np.int32)
+        n = S.cpu_system_keypoints(s, P(ids), P(px), P(d3), P(wp), CAP)
+        S.cpu_system_info(s, P(info))
+        out.append((st, T, info, ids[:n].copy(), px[:n].copy(), d3[:n].copy(), wp[:n].copy()))
+    S.cpu_system_destroy(s)
+    return out
+
+
+def test_state_machine_follows_the_reference(oracle):
+    g, frames = frames_and_golden()
+    tr = run(cpu_system_lib(), frames, g["K"])
+    fb = int(g["first_ba_frame"])
+    init = int(np.argmax(g["ref_status"] == 1))
+    assert 10 <= init < fb < len(frames)
+    for k, (st, T, info, ids, px, d3, wp) in enumerate(tr):
+        rids, rpx, rd3, rwp = frame_slice(g, "ref_", k)
+        assert st == g["ref_status"][k], k
+        assert (info == g["ref_info"][k]).all(), (k, info, g["ref_info"][k])
+        assert (ids == rids).all() and (d3 == rd3).all(), k                 # ids in the reference's iteration order, 3-D flags
+        if k < init:
+            assert (px.view(np.uint32) == rpx.view(np.uint32)).all()        # bit-identical tracks before the initialisation
+            assert (T == g["ref_Twc"][k]).all()
+        elif k < fb:
+            assert np.abs(px - rpx).max() < 0.02
+            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
+        else:
+            assert np.abs(px - rpx).max() < 0.05                            # the reference has run its local BA; this has not yet
+            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 5e-2
+        # the committed cpu_* trace (what the GPU build is compared with) is this very run
+        cids, cpx, cd3, cwp = frame_slice(g, "cpu_", k)
+        assert (ids == cids).all() and (px.view(np.uint32) == cpx.view(np.uint32)).all() and np.abs(T - g["cpu_Twc"][k]).max() < 1e-12
+
+
+def test_lockstep_given_the_reference_initialisation(oracle, ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    g, frames = frames_and_golden()
+    tr = run(cpu_system_lib(), frames, g["K"], C.cast(ref.ref_essential_5pt, C.c_void_p))
+    fb = int(g["first_ba_frame"])
+    for k in range(fb):
+        st, T, info, ids, px, d3, wp = tr[k]
+        rids, rpx, rd3, rwp = frame_slice(g, "ref_", k)
+        assert st == g["ref_status"][k] and (ids == rids).all() and (d3 == rd3).all()
+        assert (px.view(np.uint32) == rpx.view(np.uint32)).all()
+        assert np.abs(T - g["ref_Twc"][k]).max() < 1e-9
+        assert np.abs(wp - rwp).max() < 1e-9 * max(1.0, np.abs(rwp).max())
+
+
+def test_reset_when_tracks_are_lost(oracle):
+    """visual_frontend.cpp:54-58: fewer than 50 tracked keypoints before initialisation -> reset, status 2, a fresh first frame"""
+    from alvaar_b200 import synth
+    w, h = 640, 480
+    frames, _ = synth.make_frames(1, w, h, seed=3, rgba=True)
+    other = synth.random_rgba(w, h, 1, seed=5)[0]
+    K = synth.intrinsics(w, h)
+    S = cpu_system_lib()
+    s = S.cpu_system_create(w, h, K[0], K[1], K[2], K[3])
+    T = np.zeros(7)
+    assert S.cpu_system_process(s, P(np.ascontiguousarray(frames[0])), 0.0, P(T)) == 3
+    assert S.cpu_system_process(s, P(np.ascontiguousarray(other)), 33.3, P(T)) == 2
+    info = np.zeros(8, np.int32)
+    S.cpu_system_info(s, P(info))
+    assert info[0] == -1 and info[2] == 0 and info[5] == 0
+    assert S.cpu_system_process(s, P(np.ascontiguousarray(frames[0])), 66.6, P(T)) == 3
+    S.cpu_system_info(s, P(info))
+    assert info[0] == 0 and info[2] > 100 and info[5] == 1
+    S.cpu_system_destroy(s)

@@ -1,12 +1,22 @@
 #!/usr/bin/env python3
-"""Dump System-level golden vectors from the REFERENCE ITSELF: AlvaAR's own `System` (every src/slam/src/*.cpp except the
-Emscripten binding, compiled unmodified into oracle/_ref/libalva_ref.so; pins: sampler seed 12345, injected time stamps
-k * 33.333 ms, 1 thread -- oracle/ref_system.cpp).  Per frame: status, pose, and the 2-D keypoints (track ids, pixel
-positions, truncated getFramePoints coordinates).  The input frames are alvaar_b200.synth.make_frames(seed) -- their SHA-256
-is stored so that a change of the generator is noticed.  tests/golden/system.npz is committed."""
+"""Dump System-level golden vectors (tests/golden/system.npz, committed).
+
+`ref_*`: the REFERENCE ITSELF -- AlvaAR's own `System` (every src/slam/src/*.cpp except the Emscripten binding, compiled
+unmodified into oracle/_ref/libalva_ref.so; pins: sampler seed 12345, injected time stamps k * 33.333 ms, 1 thread --
+oracle/ref_system.cpp).  Per frame: status, pose (float[16] as the API returns it, and [t, q] in double), frame / keyframe
+counters, and every keypoint in the iteration order of Frame::mapKeypoints_ (track id, pixel position, 3-D flag, world point).
+The first `n_desc` frames' keyframe descriptors are stored for frame 0.
+
+`cpu_*`: alva's own host-side System state machine (alvaar_b200/csrc/system_core.h) run over the CPU oracle backend
+(tests/host/system_cpu_backend.cpp) on the same frames -- the trajectory the GPU build must reproduce tightly (same arithmetic,
+same initialisation); its distance to `ref_*` after the initialisation is bounded by the reference's own noise-limited 5-point
+refinement (tests/test_oracle_init.py).
+
+The input frames are alvaar_b200.synth.make_frames(seed); their SHA-256 is stored so that a change of the generator is noticed."""
 import ctypes as C
 import hashlib
 import os
+import subprocess
 import sys
 import numpy as np
 
@@ -14,39 +24,112 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from alvaar_b200 import synth  # noqa: E402
 
-R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libalva_ref.so"))
 P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-R.ref_system_create.restype = C.c_void_p
-R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
-R.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
-R.ref_system_get_frame_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-R.ref_system_destroy.argtypes = [C.c_void_p]
-R.ref_system_get_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+CAP = 4096
+
+
+def build_cpu_system():
+    so = os.path.join(ROOT, "tests", "_build", "libsystem_cpu.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so,
+                           os.path.join(ROOT, "tests", "host", "system_cpu_backend.cpp"), os.path.join(ROOT, "oracle", "_build", "libalva_oracle.so"),
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")])
+    S = C.CDLL(so)
+    S.cpu_system_create.restype = C.c_void_p
+    S.cpu_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 4
+    S.cpu_system_process.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    S.cpu_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    S.cpu_system_info.argtypes = [C.c_void_p, C.c_void_p]
+    S.cpu_system_set_essential_hook.argtypes = [C.c_void_p, C.c_void_p]
+    S.cpu_system_destroy.argtypes = [C.c_void_p]
+    return S
+
+
+class Trace:
+    def __init__(self):
+        self.status, self.T, self.info, self.start, self.ids, self.px, self.is3d, self.wpt = [], [], [], [0], [], [], [], []
+
+    def add(self, st, T, info, ids, px, is3d, wpt):
+        self.status.append(st); self.T.append(T.copy()); self.info.append(info.copy())
+        self.ids.append(ids.copy()); self.px.append(px.copy()); self.is3d.append(is3d.copy()); self.wpt.append(wpt.copy())
+        self.start.append(self.start[-1] + len(ids))
+
+    def dump(self, pre):
+        return {pre + "status": np.array(self.status, np.int32), pre + "Twc": np.array(self.T), pre + "info": np.array(self.info, np.int32),
+                pre + "start": np.array(self.start, np.int32), pre + "ids": np.concatenate(self.ids), pre + "px": np.concatenate(self.px),
+                pre + "is3d": np.concatenate(self.is3d), pre + "wpt": np.concatenate(self.wpt)}
+
+
+def run_cpu(S, frames, K, hook=None):
+    w, h = frames.shape[2], frames.shape[1]
+    s = S.cpu_system_create(w, h, K[0], K[1], K[2], K[3])
+    if hook is not None:
+        S.cpu_system_set_essential_hook(s, hook)
+    tr = Trace()
+    for k in range(len(frames)):
+        T = np.zeros(7)
+        st = S.cpu_system_process(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(T))
+        ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3)); info = np.zeros(8, np.int32)
+        n = S.cpu_system_keypoints(s, P(ids), P(px), P(d3), P(wp), CAP)
+        S.cpu_system_info(s, P(info))
+        tr.add(st, T, info, ids[:n], px[:n], d3[:n], wp[:n])
+    S.cpu_system_destroy(s)
+    return tr
 
 
 def main():
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libalva_ref.so"))
+    R.ref_system_create.restype = C.c_void_p
+    R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
+    R.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    R.ref_system_get_frame_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_system_destroy.argtypes = [C.c_void_p]
+    R.ref_system_get_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    R.ref_system_info8.argtypes = [C.c_void_p, C.c_void_p]
     R.ref_config(0, 1)
-    w, h, nf, seed = 640, 480, 20, 7
+    w, h, nf, seed = 640, 480, 40, 7
     K = synth.intrinsics(w, h)
     frames, _ = synth.make_frames(nf, w, h, seed=seed, rgba=True)
     d = {"w": w, "h": h, "nframes": nf, "seed": seed, "K": np.array(K), "sha256": hashlib.sha256(frames.tobytes()).hexdigest()}
     s = R.ref_system_create(w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0)
-    status = []
+    tr = Trace()
+    pose16, xys = [], []
     for k in range(nf):
         pose = np.zeros(16, np.float32)
         st = R.ref_system_find_camera_pose(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(pose))
-        xy = np.zeros((4096, 2), np.int32); ids = np.zeros(4096, np.int32); px = np.zeros((4096, 2), np.float32)
-        n = R.ref_system_get_frame_points(s, P(xy), P(ids), P(px), 4096)
-        o = np.argsort(ids[:n])
-        d[f"f{k}_ids"], d[f"f{k}_px"], d[f"f{k}_xy"], d[f"f{k}_pose"] = ids[:n][o], px[:n][o], xy[:n][o], pose
-        if k in (0, 5):   # descriptors are computed at keyframe creation and carried by the tracked keypoints
-            desc = np.zeros((4096, 32), np.uint8); has = np.zeros(4096, np.uint8)
-            R.ref_system_get_descriptors(s, P(desc), P(has), 4096)
-            d[f"f{k}_desc"], d[f"f{k}_has_desc"] = desc[:n][o], has[:n][o]
-        status.append(st)
-        print(k, "status", st, "2-D keypoints", n)
-    d["status"] = np.array(status, np.int32)
+        ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3)); T = np.zeros(7); info = np.zeros(8, np.int32)
+        n = R.ref_system_keypoints(s, P(ids), P(px), P(d3), P(wp), CAP, P(T))
+        R.ref_system_info8(s, P(info))
+        tr.add(st, T, info, ids[:n], px[:n], d3[:n], wp[:n])
+        pose16.append(pose)
+        xy = np.zeros((CAP, 2), np.int32); i2 = np.zeros(CAP, np.int32); p2 = np.zeros((CAP, 2), np.float32)
+        m = R.ref_system_get_frame_points(s, P(xy), P(i2), P(p2), CAP)   # System::getFramePoints: the 2-D keypoints, truncated unpx
+        xys.append(xy[:m].copy())
+        if k == 0:   # descriptors are computed at keyframe creation and carried by the tracked keypoints
+            desc = np.zeros((CAP, 32), np.uint8); has = np.zeros(CAP, np.uint8)
+            R.ref_system_get_descriptors(s, P(desc), P(has), CAP)
+            d["f0_desc"], d["f0_has_desc"] = desc[:m], has[:m]
+        print(k, "status", st, "keypoints", n, "3-D", int(d3[:n].sum()), "keyframe", info[1])
     R.ref_system_destroy(s)
+    d.update(tr.dump("ref_"))
+    d["ref_pose16"] = np.array(pose16)
+    d["ref_xy_start"] = np.cumsum([0] + [len(x) for x in xys]).astype(np.int32)
+    d["ref_xy"] = np.concatenate(xys)
+    kfid = d["ref_info"][:, 1]
+    d["first_ba_frame"] = int(np.argmax(kfid >= 2)) if (kfid >= 2).any() else nf   # Optimizer::localBA runs from keyframe id 2 on
+    S = build_cpu_system()
+    own = run_cpu(S, frames, K)
+    d.update(own.dump("cpu_"))
+    # sanity of what is committed: lockstep with the reference given the reference's own initialisation stage
+    hooked = run_cpu(S, frames, K, C.cast(R.ref_essential_5pt, C.c_void_p))
+    fb = d["first_ba_frame"]
+    for k in range(fb):
+        assert hooked.status[k] == tr.status[k] and (hooked.ids[k] == tr.ids[k]).all() and (hooked.px[k].view(np.uint32) == tr.px[k].view(np.uint32)).all()
+        assert np.abs(hooked.T[k] - tr.T[k]).max() < 1e-9
+    print("lockstep with the reference (its own initialisation plugged in) up to frame", fb, "; own initialisation: max |dt|",
+          float(np.abs(np.array(own.T)[:fb, :3] - np.array(tr.T)[:fb, :3]).max()))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "system.npz"), **d)
 
 
