@@ -18,6 +18,8 @@
 //   essential    5-point RANSAC + refinement (initialisation)     alva_k_essential_5pt              (multi_view_geometry.cpp:225-318)
 //   p3p / pnp    per-frame pose                                   alva_k_p3p_lmeds, alva_k_pnp      (multi_view_geometry.cpp:24-223)
 //   triangulate  new map points at keyframes                      alva_k_triangulate                (multi_view_geometry.cpp:12-22)
+//   match_to_map local map -> keyframe matching                   alva_k_match_to_map               (mapper.cpp:354-587)
+//   ba_local     local bundle adjustment, both solves + flags     alva_k_ba_local                   (optimizer.cpp:251-359)
 // There is no CPU fallback: configure() fails without an sm_100 device.  Lens distortion: the JS shim always passes zeros
 // (system.js:84-141); non-zero coefficients are rejected rather than silently ignored.
 #include "alva_common.cuh"
@@ -97,6 +99,7 @@ struct CudaBackend {
         void** bufs[] = {(void**)&pts_dev, (void**)&pri_dev, (void**)&flag_dev, (void**)&cnt_dev, (void**)&quality_dev, (void**)&blur_dev,
                          (void**)&desc_dev, (void**)&dbl_dev};
         for (void** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
+        if (arena) { cudaFree(arena); arena = nullptr; arena_cap = 0; }
         if (ctx) { alva_ctx_destroy(ctx); ctx = nullptr; }
     }
 
@@ -218,6 +221,96 @@ struct CudaBackend {
         return host[16 + 10] != 0.0 ? 1 : 0;
     }
 
+    // ---- variable-size problems (local BA, local-map matching): one growable device arena, bump-allocated per call
+    uint8_t* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    int arena_begin(size_t bytes) {
+        bytes += 4096;
+        if (bytes > arena_cap) {
+            if (arena) { cudaFree(arena); arena = nullptr; arena_cap = 0; }
+            const size_t want = bytes + bytes / 2;
+            SYS_CUDA(cudaMalloc(&arena, want));
+            arena_cap = want;
+        }
+        arena_off = 0;
+        return 0;
+    }
+    static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+    template <class T> T* arena_take(size_t n) { T* p = (T*)(arena + arena_off); arena_off += al256(n * sizeof(T) + 16); return p; }
+    template <class T> T* arena_put(const T* host, size_t n) {
+        T* p = arena_take<T>(n);
+        if (n) cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+        return p;
+    }
+
+    bool has_ba_local() const { return true; }
+    bool has_match_to_map() const { return true; }
+
+    // the numerical body of Optimizer::localBA (optimizer.cpp:251-359): two solves and both outlier passes in one launch sequence
+    int ba_local(alva_sys::BaProblem& bp, int32_t* flags) {
+        cudaStream_t st = ctx->stream;
+        const size_t nkf = bp.nkf, nlm = bp.nlm, nobs = bp.nobs;
+        if (int e = arena_begin(al256(32) + al256(nkf * 56) + al256(nkf) + 3 * al256(nlm * 16) + 4 * al256(nobs * 16) + 16 * 256)) return e;
+        double* calib = arena_put(bp.calib, 4);
+        double* poses = arena_put(bp.poses.data(), nkf * 7);
+        uint8_t* pc = arena_put(bp.pose_const.data(), nkf);
+        double* invd = arena_put(bp.invd.data(), nlm);
+        int32_t* akf = arena_put(bp.anch_kf.data(), nlm);
+        double* auv = arena_put(bp.anch_uv.data(), nlm * 2);
+        int32_t* okf = arena_put(bp.obs_kf.data(), nobs);
+        int32_t* olm = arena_put(bp.obs_lm.data(), nobs);
+        double* ouv = arena_put(bp.obs_uv.data(), nobs * 2);
+        int32_t* fl = arena_take<int32_t>(nobs);
+        SYS_CUDA(cudaMemsetAsync(fl, 0, nobs * 4, st));
+        const float chi2 = 5.9915f;   // State::robustCostThreshold_ (float); the Huber width is std::sqrt(float) (optimizer.cpp:22)
+        if (int e = alva_k_ba_local(ctx, 1, (int)nkf, (int)nlm, (int)nobs, calib, poses, pc, invd, akf, auv, okf, olm, ouv, (double)sqrtf(chi2),
+                                    (double)chi2, 5, fl, nullptr))
+            return e;
+        SYS_CUDA(cudaMemcpyAsync(bp.poses.data(), poses, nkf * 56, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(bp.invd.data(), invd, nlm * 8, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(flags, fl, nobs * 4, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+
+    // Mapper::matchToMap(frame, 2 px, 0.2, local map) (mapper.cpp:332)
+    int match_to_map(const alva_sys::MatchProblem& m, std::vector<int>& kp_match) {
+        cudaStream_t st = ctx->stream;
+        const size_t n_kp = m.kp_id.size(), n_mp = m.mp_id.size(), n_kf = m.kf_id.size(), n_obs = m.obs_kfid.size(), n_local = m.local_mp.size();
+        if (!n_kp || !n_mp || !n_local) return 0;
+        std::vector<int32_t> obs_kf(n_obs);   // keyframe id -> index into kf_Twc
+        for (size_t o = 0; o < n_obs; o++) { int ki = 0; while (m.kf_id[ki] != m.obs_kfid[o]) ki++; obs_kf[o] = ki; }
+        std::vector<uint8_t> desc = m.desc;
+        if (desc.empty()) desc.assign(32, 0);
+        const double kf0[7] = {0, 0, 0, 0, 0, 0, 1};
+        if (int e = arena_begin(al256(56) + 2 * al256(n_kp * 8) + al256(n_kf * 56 + 56) + al256(n_mp * 24) + al256(n_mp) + 2 * al256((n_mp + 1) * 4) +
+                                al256(n_obs * 4) + al256(n_obs * 8) + al256(desc.size()) + al256(n_local * 4) + al256(n_kp * 4) + 20 * 256))
+            return e;
+        double* Tc = arena_put(m.Twc_cur, 7);
+        int32_t* kpmp = arena_put(m.kp_mp.data(), n_kp);
+        float* kppx = arena_put(m.kp_px.data(), n_kp * 2);
+        double* kfT = n_kf ? arena_put(m.kf_Twc.data(), n_kf * 7) : arena_put(kf0, 7);
+        double* wpt = arena_put(m.mp_wpt.data(), n_mp * 3);
+        uint8_t* is3 = arena_put(m.mp_is3d.data(), n_mp);
+        int32_t* os = arena_put(m.obs_start.data(), n_mp + 1);
+        int32_t* ok = arena_put(obs_kf.data(), n_obs);
+        float* op = arena_put(m.obs_px.data(), n_obs * 2);
+        int32_t* ds = arena_put(m.desc_start.data(), n_mp + 1);
+        uint8_t* dd = arena_put(desc.data(), desc.size());
+        int32_t* lm = arena_put(m.local_mp.data(), n_local);
+        int32_t* out = arena_take<int32_t>(n_kp);
+        int32_t* nm = arena_take<int32_t>(4);
+        if (int e = alva_k_match_to_map(ctx, w, h, 40, fx, fy, cx, cy, Tc, (int)n_kp, kpmp, kppx, m.nkp3d, (int)(n_kf ? n_kf : 1), kfT, (int)n_mp, wpt, is3,
+                                        os, ok, op, ds, dd, (int)n_local, lm, 2.0f, 0.2f, out, nullptr, nm))
+            return e;
+        std::vector<int32_t> host(n_kp);
+        SYS_CUDA(cudaMemcpyAsync(host.data(), out, n_kp * 4, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n_kp; i++) kp_match[i] = host[i];
+        return 0;
+    }
+    double fx = 0, fy = 0, cx = 0, cy = 0;
+
     int triangulate(const double* T7, const double* bl, const double* br, int n, double* out) {
         cudaStream_t st = ctx->stream;
         if (n > cap) { alva_set_error("System: %d points exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
@@ -247,6 +340,7 @@ public:
             return ALVA_E_INVALID;
         }
         if (int e = be_.init(device_, imageWidth, imageHeight)) return e;
+        be_.fx = fx; be_.fy = fy; be_.cx = cx; be_.cy = cy;
         core_.configure(imageWidth, imageHeight, fx, fy, cx, cy);
         configured_ = true;
         return 0;

@@ -407,7 +407,7 @@ struct BaProblem {   // the layout of alva_k_ba_local
     std::vector<int32_t> obs_kf, obs_lm;
     std::vector<double> obs_uv;         // [nobs][2]
 };
-struct MatchProblem {   // Mapper::matchToMap on flat arrays (alva_k_match_to_map / orc_match_to_map)
+struct MatchProblem {   // Mapper::matchToMap on flat arrays (the contract of alva_k_match_to_map)
     double Twc_cur[7];
     int nkp3d = 0;
     std::vector<int32_t> kp_id, kp_mp;  // keypoints cell by cell; kp_mp = index of the keypoint's own map point in the table

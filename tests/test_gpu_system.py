@@ -5,7 +5,9 @@ machine run over the CPU oracle (`cpu_*`, tools/make_golden_system.py).
 Exact: status codes, track ids in the reference's iteration order, 3-D flags, keyframe events and frame counters over all 40
 frames; every pixel position bit for bit before the initialisation; getFramePoints.  Tight (same arithmetic, same
 initialisation): poses and world points vs `cpu_*` to 1e-6, pixel positions to 1e-3 px.  Bounded by the reference's own
-noise-limited initialisation (tests/test_oracle_init.py): poses vs `ref_*` |dt| < 1e-2, |dq| < 1e-3 up to its first local BA."""
+noise-limited initialisation (tests/test_oracle_init.py): poses vs `ref_*` |dt| < 1e-2, |dq| < 1e-3 -- over the whole trace,
+which contains two keyframes after the initialisation and a local BA (tests/test_system_core_cpu.py shows that, given the
+reference's own initialisation result, the same state machine is in lockstep with the reference to 1e-9)."""
 import ctypes as C
 
 import numpy as np
@@ -58,6 +60,7 @@ def test_system_follows_the_reference():
     assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
     fb = int(g["first_ba_frame"])
     init = int(np.argmax(g["ref_status"] == 1))
+    assert init < fb < nf
     for k in range(nf):
         st = L.alva_system_find_camera_pose_ts(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(pose))
         assert st == g["ref_status"][k], (k, st)
@@ -83,10 +86,9 @@ def test_system_follows_the_reference():
         else:
             assert np.abs(px - cpx).max() < 1e-3 and np.abs(T - g["cpu_Twc"][k]).max() < 1e-6
             assert np.abs(wp - cwp).max() < 1e-6 * max(1.0, np.abs(cwp).max())
-            if k < fb:
-                assert np.abs(px - rpx).max() < 0.02
-                assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
-                assert np.abs(xy[:m] - g["ref_xy"][a:b]).max() <= 1
+            assert np.abs(px - rpx).max() < 0.02                                        # also after the local BA at frame fb
+            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
+            assert np.abs(xy[:m] - g["ref_xy"][a:b]).max() <= 1
         if k == 0:                                                                      # 256-bit ORB descriptors of the keypoints
             desc = np.zeros((CAP, 32), np.uint8); has = np.zeros(CAP, np.uint8)
             assert L.alva_system_get_descriptors(s, P(desc), P(has), CAP) == n

@@ -1,14 +1,17 @@
 """CPU tests of the host-side System state machine (alvaar_b200/csrc/system_core.h) -- the code that, in the product, drives
 the CUDA kernels -- instantiated over the CPU oracle backend (test infrastructure) and compared with a 40-frame trace of the
-reference's own System (tests/golden/system.npz, dumped by tools/make_golden_system.py).
+reference's own System (tests/golden/system.npz, dumped by tools/make_golden_system.py: initialisation at frame 13, keyframes at
+13 and 27, the first local BA at 27).
 
-What is exact: status codes, track ids IN THE REFERENCE'S ITERATION ORDER (it decides RANSAC sample indices and Ceres residual
-order), 3-D flags, keyframe events, frame counters -- over all 40 frames, i.e. also after the reference's first local BA --
-and, before the initialisation, every pixel position bit for bit.
-What is toleranced: after the initialisation poses / world points carry the reference's own noise-limited 5-point refinement
-(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2, |dq| < 1e-3 up to its first local
-BA.  With the reference's OWN initialisation stage plugged in (live reference only) everything downstream is in lockstep: poses
-1e-9, pixel positions bit-identical, until the first local BA (not wired yet)."""
+What is exact over all 40 frames: status codes, track ids IN THE REFERENCE'S ITERATION ORDER (it decides RANSAC sample indices
+and Ceres residual order), 3-D flags, keyframe events, frame / map counters -- and, before the initialisation, every pixel
+position bit for bit.
+What is toleranced: after the initialisation, poses / world points carry the reference's own noise-limited 5-point refinement
+(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2, |dq| < 1e-3.
+With the reference's OWN initialisation stage plugged in (live reference only) everything downstream -- KLT with projected
+priors, P3P-LMedS, PnP, keyframe decisions, triangulation, local-map matching, local BA, culling -- is in lockstep: poses and
+world points 1e-9, pixel positions bit-identical, over the whole trace (tools/compare_system_cpu.py shows the same over 140
+frames / 11 keyframes / 9 local BAs)."""
 import ctypes as C
 
 import numpy as np
@@ -49,12 +52,9 @@ def test_state_machine_follows_the_reference(oracle):
         if k < init:
             assert (px.view(np.uint32) == rpx.view(np.uint32)).all()        # bit-identical tracks before the initialisation
             assert (T == g["ref_Twc"][k]).all()
-        elif k < fb:
+        else:
             assert np.abs(px - rpx).max() < 0.02
             assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
-        else:
-            assert np.abs(px - rpx).max() < 0.05                            # the reference has run its local BA; this has not yet
-            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 5e-2
         # the committed cpu_* trace (what the GPU build is compared with) is this very run
         cids, cpx, cd3, cwp = frame_slice(g, "cpu_", k)
         assert (ids == cids).all() and (px.view(np.uint32) == cpx.view(np.uint32)).all() and np.abs(T - g["cpu_Twc"][k]).max() < 1e-12
@@ -65,8 +65,8 @@ def test_lockstep_given_the_reference_initialisation(oracle, ref):
         pytest.skip("oracle/_ref not built here")
     g, frames = frames_and_golden()
     tr = run(cpu_system_lib(), frames, g["K"], C.cast(ref.ref_essential_5pt, C.c_void_p))
-    fb = int(g["first_ba_frame"])
-    for k in range(fb):
+    assert int(g["first_ba_frame"]) < len(frames) - 5                        # the trace does contain a local BA
+    for k in range(len(frames)):
         st, T, info, ids, px, d3, wp = tr[k]
         rids, rpx, rd3, rwp = frame_slice(g, "ref_", k)
         assert st == g["ref_status"][k] and (ids == rids).all() and (d3 == rd3).all()
