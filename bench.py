@@ -337,6 +337,10 @@ def bench_b200(args, rank, world, local_rank):
             tracking = tracking_stage_times(ctx, pipe, stream, local_rank)
         except Exception as e:   # explanatory numbers only: never let them take the headline line down
             tracking = {"error": repr(e)}
+        try:
+            tracking["system_api"] = system_api_times(not args.no_cpu_baseline)
+        except Exception as e:
+            tracking["system_api"] = {"error": repr(e)}
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
@@ -456,6 +460,62 @@ def tracking_stage_times(ctx, pipe, stream, local_rank):
             ctx.detect_grid(kimg, W, H, len(kf), 40, kcur, kn, kcur.shape[1], [20, 20, W - 40, H - 40], q, dout, None, dcnt, 2048)
         out[f"detect_grid_{len(kf)}kf"] = timed(det)
         out["detect_corners_per_kf"] = float(dcnt.float().mean().item())
+    return out
+
+
+def system_api_times(with_reference):
+    """The reference's public API itself -- System::findCameraPose, one 640x480 frame per call, host RGBA in, pose out
+    (alva_system_*: upload + pyramid + KLT + P3P/PnP every frame; detector, ORB, triangulation, local-map matching and local BA
+    on keyframes) -- over a 40-frame synthetic sequence, wall clock per call, AFTER the headline measurement.  With the
+    reference built in the tree (oracle/_ref), its own System is timed on the same frames (one host thread, as shipped)."""
+    import ctypes as C
+    import alvaar_b200
+    from alvaar_b200 import synth
+    w, h, nf = 640, 480, 40
+    K = synth.intrinsics(w, h)
+    frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    L = alvaar_b200.lib()
+    L.alva_system_create.restype = C.c_void_p
+    L.alva_system_configure.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 8
+    L.alva_system_find_camera_pose_ts.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.alva_system_get_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.alva_system_destroy.argtypes = [C.c_void_p]
+    out = {}
+    for rep in range(2):   # the second pass is the warm one
+        s = C.c_void_p(L.alva_system_create(0))
+        assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+        pose = np.zeros(16, np.float32)
+        ms, status, kf = [], [], []
+        info = np.zeros(8, np.int32)
+        last_kf = 0
+        for k in range(nf):
+            f = np.ascontiguousarray(frames[k])
+            t0 = time.perf_counter()
+            st = L.alva_system_find_camera_pose_ts(s, P(f), k * 33.333, P(pose))
+            ms.append((time.perf_counter() - t0) * 1e3)
+            L.alva_system_get_info(s, P(info))
+            status.append(int(st)); kf.append(int(info[5]) != last_kf); last_kf = int(info[5])
+        L.alva_system_destroy(s)
+    ms, kf, status = np.array(ms), np.array(kf), np.array(status)
+    out.update({"frames": nf, "frame": f"{w}x{h}", "ms_per_tracked_frame_median": float(np.median(ms[~kf & (status == 1)])),
+                "ms_per_keyframe_median": float(np.median(ms[kf])), "frames_per_sec_whole_sequence": float(nf / (ms.sum() * 1e-3)),
+                "status_counts": {str(v): int((status == v).sum()) for v in (1, 2, 3)}, "keyframes": int(kf.sum())})
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libalva_ref.so")
+    if with_reference and os.path.exists(ref_so):
+        R = C.CDLL(ref_so)
+        R.ref_config(1, 1)
+        R.ref_system_create.restype = C.c_void_p
+        R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
+        R.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        R.ref_system_destroy.argtypes = [C.c_void_p]
+        r = R.ref_system_create(w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0)
+        pose = np.zeros(16, np.float32)
+        t0 = time.perf_counter()
+        for k in range(nf):
+            R.ref_system_find_camera_pose(r, P(np.ascontiguousarray(frames[k])), k * 33.333, P(pose))
+        out["reference_system_frames_per_sec"] = float(nf / (time.perf_counter() - t0))
+        R.ref_system_destroy(r)
     return out
 
 
