@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem
         s.last_success = 1; s.n_success = 0; s.n_iter = 0; s.term = 1; s.done = 0; s.relin = 1; s.step_ok = 0;
         s.se_acc_ref = 0; s.se_acc_cand = 0; s.gmax = 1.0; s.model_change = 0; s.cand_cost = 0;
         s.chol_ok = 1; s.use_gather = 0; s.nb = c / 6; s.has_last = 0; s.skipped = 0;
+        if (c > 6 * NBMAX) {
+            // more free poses than the reduced-system buffers hold (NBMAX): refuse the problem -- every later kernel returns at
+            // once for a finished problem and the parameters stay untouched -- instead of writing past S / rhs.  term 2 = failure.
+            for (int k = 0; k < D.nkf; k++) P.pose_col[k] = -1;
+            s.ncols = 0; s.nb = 0; s.done = 1; s.term = 2;
+        }
     }
     // exclusive scan of counts -> lm_start
     {

@@ -839,6 +839,15 @@ private:
         size_t ncst = cst_kfs.size();
         if (ncst < 2)
             for (auto it = local_kfs.begin(); ncst < 2 && it != local_kfs.end(); ++it) { cst_kfs.insert(it->first); ncst++; }   // optimizer.cpp:240-248 (counts even a repeat)
+        // the device solver factors a reduced camera system of at most 21 free poses (126 columns, one CTA's shared memory):
+        // beyond that the OLDEST free keyframes are held fixed for this solve -- a deviation from the reference that its
+        // 30-keyframe window can only reach when more than 21 covisible keyframes each share >= 25 points with the new one
+        {
+            std::vector<int> free_ids;
+            for (int id : kf_ids) if (!cst_kfs.count(id)) free_ids.push_back(id);
+            std::sort(free_ids.begin(), free_ids.end());
+            for (size_t i = 0; i + 21 < free_ids.size(); i++) cst_kfs.insert(free_ids[i]);
+        }
         // ---- numerical body.  Landmarks without a residual are not part of Ceres' reduced program: leave them out
         const int nkf = (int)kf_ids.size(), nobs = (int)obs_lm.size();
         std::vector<int> used(lms.size(), -1), lm_of;

@@ -269,7 +269,9 @@ int alva_k_ba_solve(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
  *   4. flag (flags = 2, not removed) the observations that are outliers after that solve   optimizer.cpp:330-356
  * obs_lm is not modified; flags [nprob][nobs] int32 (0 = inlier / unused slot); summary (optional) [nprob][10]:
  * {initial cost, final cost, #successful, #iterations, termination} of solve 1, then of solve 2 (zeros if skipped).
- * The reference's 1 ms wall-clock cap on step 3 (and 5 ms on step 1) is lifted, as everywhere in this library. */
+ * The reference's 1 ms wall-clock cap on step 3 (and 5 ms on step 1) is lifted, as everywhere in this library.
+ * Size limit (alva_k_ba_solve too): at most 21 free (non-constant, referenced) poses per problem -- the reduced camera system
+ * is factored in one CTA's shared memory; a problem with more is refused (termination 2, parameters untouched). */
 int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
                     const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
                     const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta, double chi2_thr,
