@@ -26,6 +26,7 @@
 #include "../../include/alva_b200.h"
 #include "system_core.h"
 #include <chrono>
+#include <exception>
 
 int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src, int16_t* const* dst, const int* w, const int* h,
                               int nframes);
@@ -351,7 +352,7 @@ public:
     // returns the reference's status codes; pose16 layout as Utils::toPoseArray (src/slam/src/utils.cpp:3-27)
     int findCameraPose(const uint8_t* rgba, double t_ms, float* pose16) {
         if (!configured_) { alva_set_error("System: not configured"); return ALVA_E_STATE; }
-        const int st = core_.process(rgba, t_ms);
+        const int st = processGuarded(rgba, t_ms);
         if (st < 0) return st;
         writePose(core_.cur.Twc, pose16);   // the current frame's Twc in every case (identity after a reset / before initialisation)
         return st;
@@ -360,7 +361,7 @@ public:
 
     int findCameraPoseWithIMU(const uint8_t* rgba, const double* imu, float* pose16) {
         if (!configured_) { alva_set_error("System: not configured"); return ALVA_E_STATE; }
-        const int st = core_.process(rgba, nowMs());
+        const int st = processGuarded(rgba, nowMs());
         if (st < 0) return st;
         // system.cpp:66-104: rotation from the device orientation quaternion (w, -x, y, z), inverted; the translation follows the
         // visual track while its status is 1 (increments of Twc.translation accumulated into currTranslation_)
@@ -435,6 +436,16 @@ public:
     int device_ = 0;
 
 private:
+    // no exception crosses the C boundary (the reference aborts on its .at() throws; a library must not)
+    int processGuarded(const uint8_t* rgba, double t_ms) {
+        try {
+            return core_.process(rgba, t_ms);
+        } catch (const std::exception& e) {
+            alva_set_error("System: inconsistent map state (%s); tracker reset", e.what());
+            core_.reset();
+            return ALVA_E_STATE;
+        }
+    }
     static double nowMs() {   // system.cpp:114: milliseconds since the epoch
         return (double)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
     }
