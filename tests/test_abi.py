@@ -43,3 +43,17 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "libalva_oracle" not in txt and "libalva_ref" not in txt and "orc_" not in txt, (dp, f)
+
+
+def test_reference_class_shim_compiles_and_links():
+    """include/alva_system.hpp -- the reference's `class System` (system.hpp:28-38) over the C ABI, what embind.cpp binds --
+    compiles with the reference's exact member signatures, links against the library and fails cleanly when unconfigured."""
+    import subprocess
+    import alvaar_b200
+    out = os.path.join(ROOT, "tests", "_build", "system_shim_check")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    lib = alvaar_b200.lib_path()
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", out, os.path.join(ROOT, "tests", "host", "system_shim_check.cpp"), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    r = subprocess.run([out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
