@@ -170,9 +170,18 @@ struct CudaBackend {
         return 0;
     }
 
+    // test hook (alva_system_debug_set_initialisation): the result the next 5-point initialisation returns instead of running
+    std::vector<double> init_Rt;
+    std::vector<uint8_t> init_outlier;
     int essential(const double* b1, const double* b2, int n, float fx, float fy, double* Rt, uint8_t* outl) {
         cudaStream_t st = ctx->stream;
         if (n > cap) { alva_set_error("System: %d correspondences exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        if (init_Rt.size() == 12 && (int)init_outlier.size() == n) {
+            memcpy(Rt, init_Rt.data(), 12 * sizeof(double));
+            memcpy(outl, init_outlier.data(), n);
+            init_Rt.clear(); init_outlier.clear();
+            return 1;
+        }
         double *A = dbl_dev, *Bv = dbl_dev + 3 * (size_t)cap, *S = dbl_dev + 9 * (size_t)cap;
         SYS_CUDA(cudaMemcpyAsync(A, b1, (size_t)n * 24, cudaMemcpyHostToDevice, st));
         SYS_CUDA(cudaMemcpyAsync(Bv, b2, (size_t)n * 24, cudaMemcpyHostToDevice, st));
@@ -426,6 +435,10 @@ public:
         return n;
     }
     int getPose(double* Twc7) { core_.cur.Twc.to7(Twc7); return 0; }
+    void debugSetInitialisation(const double* Rt12, const uint8_t* outlier, int n) {
+        be_.init_Rt.assign(Rt12, Rt12 + 12);
+        be_.init_outlier.assign(outlier, outlier + n);
+    }
     // {frame id, keyframe id, #keypoints, #3-D keypoints, initialised, #keyframes, #occupied cells, #map point ids}
     int getInfo(int32_t* out8) {
         out8[0] = core_.cur.id; out8[1] = core_.cur.kfid; out8[2] = core_.cur.n; out8[3] = core_.cur.n3d;
@@ -503,6 +516,11 @@ extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, u
 extern "C" int alva_system_get_descriptors(alva_system* s, uint8_t* desc, uint8_t* has, int cap) {
     if (!s || !desc || !has || cap < 0) return ALVA_E_INVALID;
     return s->sys.getDescriptors(desc, has, cap);
+}
+extern "C" int alva_system_debug_set_initialisation(alva_system* s, const double* Rt12, const uint8_t* outlier, int n) {
+    if (!s || !Rt12 || !outlier || n < 8) return ALVA_E_INVALID;
+    s->sys.debugSetInitialisation(Rt12, outlier, n);
+    return 0;
 }
 extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
 extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }

@@ -363,6 +363,11 @@ int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, uint8_t* is3d
 /* their 256-bit ORB descriptors (Keypoint::desc_, feature_extractor.cpp:160-214), same order: desc [cap][32], has [cap] (0 = the
  * reference keeps an empty Mat: point within 31 px of the border) */
 int  alva_system_get_descriptors(alva_system*, uint8_t* desc, uint8_t* has, int cap);
+/* TEST HOOK: the result ([Rwc | twc] 3x4 row-major, outlier flags of the n correspondences) the NEXT 5-point initialisation
+ * returns instead of running alva_k_essential_5pt -- used by the parity tests to plug in the reference's own initialisation
+ * result (whose refinement is noise-limited) and check everything downstream of it at 1e-7; ignored when n does not
+ * match the number of correspondences of that initialisation. */
+int  alva_system_debug_set_initialisation(alva_system*, const double* Rt12, const uint8_t* outlier, int n);
 /* the current frame's camera-to-world pose in double: [t, q(x,y,z,w)] */
 int  alva_system_get_pose(alva_system*, double* Twc7);
 /* {frame id, keyframe id, #keypoints, #3-D keypoints, initialised, #keyframes, #occupied grid cells, #map point ids} */

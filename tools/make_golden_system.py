@@ -122,8 +122,21 @@ def main():
     S = build_cpu_system()
     own = run_cpu(S, frames, K)
     d.update(own.dump("cpu_"))
-    # sanity of what is committed: lockstep with the reference given the reference's own initialisation stage
-    hooked = run_cpu(S, frames, K, C.cast(R.ref_essential_5pt, C.c_void_p))
+    # sanity of what is committed: lockstep with the reference given the reference's own initialisation stage; its result
+    # (what MultiViewGeometry::compute5ptEssentialMatrix returned inside the reference run) is recorded for the GPU test
+    rec = {}
+    HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p)
+    R.ref_essential_5pt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+
+    def hook(b1, b2, n, it, err, opt, fx, fy, Rt, outl):
+        ok = R.ref_essential_5pt(b1, b2, n, it, err, opt, fx, fy, Rt, outl)
+        if ok and "Rt" not in rec:
+            rec["Rt"] = np.ctypeslib.as_array(C.cast(Rt, C.POINTER(C.c_double)), (12,)).copy()
+            rec["outlier"] = np.ctypeslib.as_array(C.cast(outl, C.POINTER(C.c_uint8)), (n,)).copy()
+        return ok
+    cb = HOOK(hook)
+    hooked = run_cpu(S, frames, K, C.cast(cb, C.c_void_p))
+    d["ref_init_Rt"], d["ref_init_outlier"] = rec["Rt"], rec["outlier"]
     for k in range(nf):
         assert hooked.status[k] == tr.status[k] and (hooked.ids[k] == tr.ids[k]).all() and (hooked.px[k].view(np.uint32) == tr.px[k].view(np.uint32)).all()
         assert np.abs(hooked.T[k] - tr.T[k]).max() < 1e-9
