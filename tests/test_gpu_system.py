@@ -1,12 +1,12 @@
 """GPU tests (B200): the System facade (alva_system_*) -- the reference's public API (system.hpp:28-38) on the CUDA kernels --
-against the 40-frame trace of the reference's own System (tests/golden/system.npz `ref_*`) and against the same host-side state
+against the 100-frame trace of the reference's own System (tests/golden/system.npz `ref_*`) and against the same host-side state
 machine run over the CPU oracle (`cpu_*`, tools/make_golden_system.py).
 
-Exact: status codes, track ids in the reference's iteration order, 3-D flags, keyframe events and frame counters over all 40
+Exact: status codes, track ids in the reference's iteration order, 3-D flags, keyframe events and frame counters over all 100
 frames; every pixel position bit for bit before the initialisation; getFramePoints.  Tight (same arithmetic, same
 initialisation up to the summation order of its refinement): poses vs `cpu_*` to 1e-4, world points 1e-3, pixels 2e-3 px.  Bounded by the reference's own
 noise-limited initialisation (tests/test_oracle_init.py; `test_system_lockstep_given_the_reference_initialisation` plugs the
-reference's own initialisation result in and gets 1e-7 over the whole trace): poses vs `ref_*` |dt| < 1e-2, |dq| < 1e-3 -- over the whole trace,
+reference's own initialisation result in and gets 1e-7 over the whole trace): poses vs `ref_*` |dt| < 1e-2 max(1, |t|), |dq| < 1e-3 -- over the whole trace,
 which contains two keyframes after the initialisation and a local BA (tests/test_system_core_cpu.py shows that, given the
 reference's own initialisation result, the same state machine is in lockstep with the reference to 1e-9)."""
 import ctypes as C
@@ -88,10 +88,11 @@ def test_system_follows_the_reference():
             # same arithmetic, but the initialisation's refinement sums its normal equations in another order on the device and
             # ends 5e-6 away in its flat valley; everything downstream inherits that
             # (pixels: KLT stops at 0.01 px updates, so priors that differ in the last digits may end a few 1e-3 px apart)
-            assert np.abs(px - cpx).max() < 0.02 and np.abs(T - g["cpu_Twc"][k]).max() < 1e-4
+            sc = max(1.0, float(np.linalg.norm(g["ref_Twc"][k][:3])))                     # the trajectory is measured in units of the initial baseline
+            assert np.abs(px - cpx).max() < 0.02 and np.abs(T - g["cpu_Twc"][k]).max() < 1e-4 * sc
             assert np.abs(wp - cwp).max() < 1e-3 * max(1.0, np.abs(cwp).max())
             assert np.abs(px - rpx).max() < 0.02                                        # also after the local BA at frame fb
-            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
+            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 * max(1.0, float(np.linalg.norm(g["ref_Twc"][k][:3]))) and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
             assert np.abs(xy[:m] - g["ref_xy"][a:b]).max() <= 1
         if k == 0:                                                                      # 256-bit ORB descriptors of the keypoints
             desc = np.zeros((CAP, 32), np.uint8); has = np.zeros(CAP, np.uint8)
@@ -138,7 +139,7 @@ def test_system_lockstep_given_the_reference_initialisation():
         assert st == g["ref_status"][k] and (info == g["ref_info"][k]).all(), (k, st, info)
         assert n == len(rids) and (ids[:n] == rids).all() and (d3[:n] == rd3).all(), k
         worst_px = max(worst_px, float(np.abs(px[:n] - rpx).max()))
-        worst_T = max(worst_T, float(np.abs(T[:3] - g["ref_Twc"][k][:3]).max()), quat_dist(T[3:], g["ref_Twc"][k][3:]))
+        worst_T = max(worst_T, float(np.abs(T[:3] - g["ref_Twc"][k][:3]).max()) / max(1.0, float(np.linalg.norm(g["ref_Twc"][k][:3]))), quat_dist(T[3:], g["ref_Twc"][k][3:]))
         assert np.abs(wp[:n] - rwp).max() < 1e-6 * max(1.0, np.abs(rwp).max()), k
         assert np.abs(pose - g["ref_pose16"][k]).max() < 1e-6, k                    # the API's float[16]
     assert worst_T < 1e-7 and worst_px < 1e-3, (worst_T, worst_px)

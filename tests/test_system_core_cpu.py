@@ -1,13 +1,13 @@
 """CPU tests of the host-side System state machine (alvaar_b200/csrc/system_core.h) -- the code that, in the product, drives
-the CUDA kernels -- instantiated over the CPU oracle backend (test infrastructure) and compared with a 40-frame trace of the
-reference's own System (tests/golden/system.npz, dumped by tools/make_golden_system.py: initialisation at frame 13, keyframes at
-13 and 27, the first local BA at 27).
+the CUDA kernels -- instantiated over the CPU oracle backend (test infrastructure) and compared with a 100-frame trace of the
+reference's own System (tests/golden/system.npz, dumped by tools/make_golden_system.py: initialisation at frame 13, eight keyframes,
+the first local BA at frame 27).
 
-What is exact over all 40 frames: status codes, track ids IN THE REFERENCE'S ITERATION ORDER (it decides RANSAC sample indices
+What is exact over all 100 frames: status codes, track ids IN THE REFERENCE'S ITERATION ORDER (it decides RANSAC sample indices
 and Ceres residual order), 3-D flags, keyframe events, frame / map counters -- and, before the initialisation, every pixel
 position bit for bit.
 What is toleranced: after the initialisation, poses / world points carry the reference's own noise-limited 5-point refinement
-(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2, |dq| < 1e-3.
+(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2 max(1, |t|), |dq| < 1e-3.
 With the reference's OWN initialisation stage plugged in (live reference only) everything downstream -- KLT with projected
 priors, P3P-LMedS, PnP, keyframe decisions, triangulation, local-map matching, local BA, culling -- is in lockstep: poses and
 world points 1e-9, pixel positions bit-identical, over the whole trace (tools/compare_system_cpu.py shows the same over 140
@@ -54,7 +54,7 @@ def test_state_machine_follows_the_reference(oracle):
             assert (T == g["ref_Twc"][k]).all()
         else:
             assert np.abs(px - rpx).max() < 0.02
-            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
+            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 * max(1.0, float(np.linalg.norm(g["ref_Twc"][k][:3]))) and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
         # the committed cpu_* trace (what the GPU build is compared with) is this very run
         cids, cpx, cd3, cwp = frame_slice(g, "cpu_", k)
         assert (ids == cids).all() and (px.view(np.uint32) == cpx.view(np.uint32)).all() and np.abs(T - g["cpu_Twc"][k]).max() < 1e-12

@@ -89,7 +89,7 @@ def main():
     R.ref_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     R.ref_system_info8.argtypes = [C.c_void_p, C.c_void_p]
     R.ref_config(0, 1)
-    w, h, nf, seed = 640, 480, 40, 7
+    w, h, nf, seed = 640, 480, 100, 7
     K = synth.intrinsics(w, h)
     frames, _ = synth.make_frames(nf, w, h, seed=seed, rgba=True)
     d = {"w": w, "h": h, "nframes": nf, "seed": seed, "K": np.array(K), "sha256": hashlib.sha256(frames.tobytes()).hexdigest()}
