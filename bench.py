@@ -464,14 +464,23 @@ def tracking_stage_times(ctx, pipe, stream, local_rank):
 
 
 def system_api_times(with_reference):
-    """The reference's public API itself -- System::findCameraPose, one 640x480 frame per call, host RGBA in, pose out
+    """findCameraPose timings at 640x480 (40 frames) and at the headline frame size 1280x720 (30 frames)."""
+    out = system_api_times_at(640, 480, 40, with_reference)
+    try:
+        out["at_1280x720"] = system_api_times_at(1280, 720, 30, with_reference)
+    except Exception as e:
+        out["at_1280x720"] = {"error": repr(e)}
+    return out
+
+
+def system_api_times_at(w, h, nf, with_reference):
+    """The reference's public API itself -- System::findCameraPose, one frame per call, host RGBA in, pose out
     (alva_system_*: upload + pyramid + KLT + P3P/PnP every frame; detector, ORB, triangulation, local-map matching and local BA
-    on keyframes) -- over a 40-frame synthetic sequence, wall clock per call, AFTER the headline measurement.  With the
+    on keyframes) -- over a synthetic sequence, wall clock per call, AFTER the headline measurement.  With the
     reference built in the tree (oracle/_ref), its own System is timed on the same frames (one host thread, as shipped)."""
     import ctypes as C
     import alvaar_b200
     from alvaar_b200 import synth
-    w, h, nf = 640, 480, 40
     K = synth.intrinsics(w, h)
     frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
     P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
