@@ -470,7 +470,55 @@ def system_api_times(with_reference):
         out["at_1280x720"] = system_api_times_at(1280, 720, 30, with_reference)
     except Exception as e:
         out["at_1280x720"] = {"error": repr(e)}
+    try:
+        out["concurrent_streams"] = system_concurrent_streams(8, 640, 480, 40)
+    except Exception as e:
+        out["concurrent_streams"] = {"error": repr(e)}
     return out
+
+
+def system_concurrent_streams(nstreams, w, h, nf):
+    """nstreams independent System handles (one camera stream each, own CUDA stream) driven from nstreams host threads on ONE
+    GPU, every call a host-RGBA findCameraPose: aggregate frames/s, and a determinism check -- all streams see the same frames,
+    so they must report bit-identical poses."""
+    import ctypes as C
+    import alvaar_b200
+    from alvaar_b200 import synth
+    K = synth.intrinsics(w, h)
+    frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
+    frames = [np.ascontiguousarray(f) for f in frames]
+    L = alvaar_b200.lib()
+    L.alva_system_create.restype = C.c_void_p
+    L.alva_system_configure.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 8
+    L.alva_system_find_camera_pose_ts.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.alva_system_destroy.argtypes = [C.c_void_p]
+    handles = []
+    for _ in range(nstreams):
+        s = C.c_void_p(L.alva_system_create(0))
+        assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+        handles.append(s)
+    poses = [np.zeros((nf, 16), np.float32) for _ in range(nstreams)]
+    status = [np.zeros(nf, np.int32) for _ in range(nstreams)]
+    start = threading.Barrier(nstreams + 1)
+
+    def run(i):
+        start.wait()
+        for k in range(nf):
+            status[i][k] = L.alva_system_find_camera_pose_ts(handles[i], frames[k].ctypes.data_as(C.c_void_p), k * 33.333,
+                                                             poses[i][k].ctypes.data_as(C.c_void_p))
+    th = [threading.Thread(target=run, args=(i,)) for i in range(nstreams)]
+    for t in th:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    for s in handles:
+        L.alva_system_destroy(s)
+    same = all(np.array_equal(poses[0], p) and np.array_equal(status[0], st) for p, st in zip(poses, status))
+    return {"streams": nstreams, "frame": f"{w}x{h}", "frames_per_stream": nf, "aggregate_frames_per_sec": float(nstreams * nf / dt),
+            "all_streams_bit_identical": bool(same), "final_status": int(status[0][-1])}
 
 
 def system_api_times_at(w, h, nf, with_reference):
