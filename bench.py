@@ -237,6 +237,7 @@ def bench_b200(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner ("NCCL version ...") must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     frames, _ = synth.make_frames(BATCH, W, H, seed=99 + rank)
