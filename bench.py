@@ -40,8 +40,8 @@ FAST_THR = 20
 # algorithmic bytes of the fused front-end kernel per frame: RGBA read once + gray + L1 written once
 ALGO_BYTES_FRONTEND = 4 * W * H + W * H + ((W + 1) // 2) * ((H + 1) // 2)
 # dram__bytes_read.sum + dram__bytes_write.sum of one 64-frame front-end launch, from the committed `ncu --set full`
-# capture (profiles/r01c_frontend_full.txt: 236.01 MB + 58.59 MB).  Static by nature: a profiler cannot run inside bench.
-FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_600_960
+# capture (profiles/r01f_frontend_full.txt: 236.11 MB + 58.62 MB).  Static by nature: a profiler cannot run inside bench.
+FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
 
 
 def read_peaks():
@@ -384,7 +384,7 @@ def bench_b200(args, rank, world, local_rank):
             "roofline": {"kernel": "frontend_tile_kernel<RGBA> (gray + pyramid L1 + FAST-9/NMS, fused)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": FRONTEND_DRAM_TRAFFIC_BYTES_B64 if BATCH == 64 else None,
-                         "traffic_source": "ncu --set full, profiles/r01c_frontend_full.txt (bytes per launch)",
+                         "traffic_source": "ncu --set full, profiles/r01f_frontend_full.txt (bytes per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_FRONTEND * BATCH,
                          "launch_ms": fe_avg_ms},
             "cpu_baseline": cpu,
