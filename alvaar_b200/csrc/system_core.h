@@ -454,8 +454,8 @@ public:
         keyframes.clear(); mappoints.clear();
         n_mp_ids = n_kf_ids = n_kf = 0;
         ready_for_init = reset_requested = false;
-        p3p_req = false; pose_failed = 0;
-        // VisualFrontend::reset leaves the motion model alone (visual_frontend.cpp:718-728); so does this
+        pose_failed = 0;
+        // VisualFrontend::reset leaves the motion model and p3pReq_ alone (visual_frontend.cpp:718-728); so does this
     }
 
     // System::processCameraPose: returns 1 tracking / 2 reset / 3 not initialised, or a negative backend error
