@@ -179,3 +179,39 @@ def test_system_resets_when_tracks_are_lost():
     assert L.alva_system_find_camera_pose_ts(s, P(np.ascontiguousarray(other)), 33.3, P(pose)) == 2
     assert L.alva_system_num_matched(s) == 0
     L.alva_system_destroy(s)
+
+
+def test_system_720p_against_the_cpu_oracle_backend():
+    """BASELINE's frame size (1280x720, 784 keypoints): the CUDA System against the same state machine run over the CPU oracle on
+    the spot (test infrastructure; tools/compare_system_cpu.py shows that one in lockstep with the reference at this size):
+    initialisation at frame 12, then tracking.  Discrete state equal; poses 1e-4 (the initialisation's refinement order)."""
+    from system_util import cpu_system_lib
+    w, h, nf = 1280, 720, 18
+    K = synth.intrinsics(w, h)
+    frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
+    S = cpu_system_lib()
+    c = S.cpu_system_create(w, h, K[0], K[1], K[2], K[3])
+    L = bind()
+    s = C.c_void_p(L.alva_system_create(0))
+    assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+    pose = np.zeros(16, np.float32)
+    seen = []
+    for k in range(nf):
+        f = np.ascontiguousarray(frames[k])
+        Tc = np.zeros(7); T = np.zeros(7)
+        st_c = S.cpu_system_process(c, P(f), k * 33.333, P(Tc))
+        st = L.alva_system_find_camera_pose_ts(s, P(f), k * 33.333, P(pose))
+        ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3))
+        cids = np.zeros(CAP, np.int32); cpx = np.zeros((CAP, 2), np.float32); cd3 = np.zeros(CAP, np.uint8); cwp = np.zeros((CAP, 3))
+        n = L.alva_system_get_tracks(s, P(ids), P(px), P(d3), P(wp), CAP)
+        m = S.cpu_system_keypoints(c, P(cids), P(cpx), P(cd3), P(cwp), CAP)
+        L.alva_system_get_pose(s, P(T))
+        assert st == st_c and n == m and (ids[:n] == cids[:n]).all() and (d3[:n] == cd3[:n]).all(), (k, st, st_c, n, m)
+        if st == 3:
+            assert (px[:n].view(np.uint32) == cpx[:n].view(np.uint32)).all(), k
+        else:
+            assert np.abs(px[:n] - cpx[:n]).max() < 0.02 and np.abs(T - Tc).max() < 1e-4 * max(1.0, float(np.linalg.norm(Tc[:3]))), k
+        seen.append(st)
+    assert seen[0] == 3 and seen[-1] == 1 and n > 500
+    S.cpu_system_destroy(c)
+    L.alva_system_destroy(s)
