@@ -465,12 +465,16 @@ def tracking_stage_times(ctx, pipe, stream, local_rank):
 
 
 def system_api_times(with_reference):
-    """findCameraPose timings at 640x480 (40 frames) and at the headline frame size 1280x720 (30 frames)."""
+    """findCameraPose timings at 640x480 (40 frames), at the headline frame size 1280x720 (30 frames) and at 1920x1080 (24 frames)."""
     out = system_api_times_at(640, 480, 40, with_reference)
     try:
         out["at_1280x720"] = system_api_times_at(1280, 720, 30, with_reference)
     except Exception as e:
         out["at_1280x720"] = {"error": repr(e)}
+    try:
+        out["at_1920x1080"] = system_api_times_at(1920, 1080, 24, with_reference)
+    except Exception as e:
+        out["at_1920x1080"] = {"error": repr(e)}
     try:
         out["concurrent_streams"] = system_concurrent_streams(8, 640, 480, 40)
     except Exception as e:

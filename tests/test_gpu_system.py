@@ -181,12 +181,12 @@ def test_system_resets_when_tracks_are_lost():
     L.alva_system_destroy(s)
 
 
-def test_system_720p_against_the_cpu_oracle_backend():
-    """BASELINE's frame size (1280x720, 784 keypoints): the CUDA System against the same state machine run over the CPU oracle on
-    the spot (test infrastructure; tools/compare_system_cpu.py shows that one in lockstep with the reference at this size):
-    initialisation at frame 12, then tracking.  Discrete state equal; poses 1e-4 (the initialisation's refinement order)."""
+@pytest.mark.parametrize("w,h,nf,nmin", [(1280, 720, 18, 500), (1920, 1080, 16, 1200)])
+def test_system_full_size_against_the_cpu_oracle_backend(w, h, nf, nmin):
+    """BASELINE's frame sizes (1280x720: 784 keypoints; 1920x1080: 1621): the CUDA System against the same state machine run over
+    the CPU oracle on the spot (test infrastructure; tools/compare_system_cpu.py shows that one in lockstep with the reference at
+    720p): initialisation at frame 12, then tracking.  Discrete state equal; poses 1e-4 (the initialisation's refinement order)."""
     from system_util import cpu_system_lib
-    w, h, nf = 1280, 720, 18
     K = synth.intrinsics(w, h)
     frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
     S = cpu_system_lib()
@@ -212,6 +212,6 @@ def test_system_720p_against_the_cpu_oracle_backend():
         else:
             assert np.abs(px[:n] - cpx[:n]).max() < 0.02 and np.abs(T - Tc).max() < 1e-4 * max(1.0, float(np.linalg.norm(Tc[:3]))), k
         seen.append(st)
-    assert seen[0] == 3 and seen[-1] == 1 and n > 500
+    assert seen[0] == 3 and seen[-1] == 1 and n > nmin
     S.cpu_system_destroy(c)
     L.alva_system_destroy(s)
