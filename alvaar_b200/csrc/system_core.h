@@ -534,13 +534,11 @@ private:
                 if (ids.size() > 2) {
                     int victim = -1;
                     size_t min_obs = (size_t)-1;
-                    bool broke = false;
-                    for (int lm : ids) {
+                    for (int lm : ids) {   // the cell's keypoint seen by the fewest keyframes goes (a keypoint without map point first)
                         auto it = mappoints.find(lm);
                         if (it != mappoints.end()) { if (it->second.obs.size() < min_obs) { victim = lm; min_obs = it->second.obs.size(); } }
-                        else { removeObsFromCurr(lm); broke = true; break; }
+                        else { removeObsFromCurr(lm); break; }
                     }
-                    (void)broke;
                     if (victim >= 0) removeObsFromCurr(victim);
                 }
             }

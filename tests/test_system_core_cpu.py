@@ -139,3 +139,44 @@ def test_failure_paths_in_lockstep_with_the_live_reference(oracle, ref):
     assert seen == {1, 2, 3}                                              # the sequence did exercise resets and re-initialisation
     ref.ref_system_destroy(r)
     S.cpu_system_destroy(s)
+
+
+def test_lockstep_at_720p_with_the_live_reference(oracle, ref):
+    """BASELINE's frame size (1280x720, 784 keypoints / frame): 36 frames through initialisation (frame 12), two more keyframes
+    and the first local BA against the live reference System, its own initialisation stage plugged in: lockstep as at 640x480."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    from alvaar_b200 import synth
+    w, h, nf = 1280, 720, 36
+    K = synth.intrinsics(w, h)
+    frames, _ = synth.make_frames(nf, w, h, seed=7, rgba=True)
+    ref.ref_system_create.restype = C.c_void_p
+    ref.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
+    ref.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    ref.ref_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    ref.ref_system_info8.argtypes = [C.c_void_p, C.c_void_p]
+    ref.ref_system_destroy.argtypes = [C.c_void_p]
+    S = cpu_system_lib()
+    r = ref.ref_system_create(w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0)
+    s = S.cpu_system_create(w, h, K[0], K[1], K[2], K[3])
+    S.cpu_system_set_essential_hook(s, C.cast(ref.ref_essential_5pt, C.c_void_p))
+    last = None
+    for k in range(nf):
+        f = np.ascontiguousarray(frames[k])
+        pose = np.zeros(16, np.float32); T_s = np.zeros(7); T_r = np.zeros(7)
+        st_r = ref.ref_system_find_camera_pose(r, P(f), k * 33.333, P(pose))
+        st_s = S.cpu_system_process(s, P(f), k * 33.333, P(T_s))
+        ids_r = np.zeros(CAP, np.int32); px_r = np.zeros((CAP, 2), np.float32); d3_r = np.zeros(CAP, np.uint8); w_r = np.zeros((CAP, 3))
+        ids_s = np.zeros(CAP, np.int32); px_s = np.zeros((CAP, 2), np.float32); d3_s = np.zeros(CAP, np.uint8); w_s = np.zeros((CAP, 3))
+        n_r = ref.ref_system_keypoints(r, P(ids_r), P(px_r), P(d3_r), P(w_r), CAP, P(T_r))
+        n_s = S.cpu_system_keypoints(s, P(ids_s), P(px_s), P(d3_s), P(w_s), CAP)
+        i_r = np.zeros(8, np.int32); i_s = np.zeros(8, np.int32)
+        ref.ref_system_info8(r, P(i_r)); S.cpu_system_info(s, P(i_s))
+        assert st_r == st_s and n_r == n_s and (i_r == i_s).all(), (k, st_r, st_s, i_r, i_s)
+        assert (ids_r[:n_r] == ids_s[:n_s]).all() and (d3_r[:n_r] == d3_s[:n_s]).all(), k
+        assert (px_r[:n_r].view(np.uint32) == px_s[:n_s].view(np.uint32)).all(), k
+        assert np.abs(T_r - T_s).max() < 1e-9 and np.abs(w_r[:n_r] - w_s[:n_s]).max() < 1e-9 * max(1.0, np.abs(w_r[:n_r]).max()), k
+        last = i_r
+    assert last[4] == 1 and last[1] >= 2 and last[2] > 500          # initialised, at least keyframe 2 (a local BA ran), 720p-sized
+    ref.ref_system_destroy(r)
+    S.cpu_system_destroy(s)
