@@ -182,7 +182,7 @@ def test_system_resets_when_tracks_are_lost():
 
 
 @pytest.mark.parametrize("w,h,nf,nmin", [(1280, 720, 18, 500), (1920, 1080, 16, 1200)])
-def test_system_full_size_against_the_cpu_oracle_backend(w, h, nf, nmin):
+def test_system_full_size_against_the_cpu_oracle_backend(oracle, w, h, nf, nmin):
     """BASELINE's frame sizes (1280x720: 784 keypoints; 1920x1080: 1621): the CUDA System against the same state machine run over
     the CPU oracle on the spot (test infrastructure; tools/compare_system_cpu.py shows that one in lockstep with the reference at
     720p): initialisation at frame 12, then tracking.  Discrete state equal; poses 1e-4 (the initialisation's refinement order)."""
