@@ -393,7 +393,8 @@ public:
         return 1;
     }
 
-    int findPlane(float* /*out16*/, int /*numIterations*/) { return 0; }   // the plane RANSAC of system.cpp:177-342 is out of scope
+    // system.cpp:123-137, 177-342 as intended (system_core.h::findPlane lists what the reference's own code actually does)
+    int findPlane(float* out16, int numIterations) { return configured_ ? core_.findPlane(out16, numIterations) : 0; }
 
     // (x, y) = truncated undistorted position of the frame's 2-D keypoints (Frame::getKeypoints2d order); writes min(n, cap)
     // pairs, returns the true count (the reference overruns its 4096-int buffer here)

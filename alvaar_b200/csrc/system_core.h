@@ -36,6 +36,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
+#include <random>
 
 namespace alva_sys {
 
@@ -475,6 +476,108 @@ public:
         if (!ready_for_init) return 3;
         return 1;
     }
+
+    // System::findPlane -> processPlane (system.cpp:123-137, 177-342) AS INTENDED.  The reference's own code cannot be matched
+    // and does not do what it says: it seeds from std::random_device; `A.row(i).colRange(0, 3) = points[i].t()` re-allocates
+    // the temporary row header (its points are CV_64F after cv::eigen2cv, A is CV_32F) so neither the 3-point sample planes
+    // nor the final fit ever see the coordinates; `distances = dists` is taken after std::nth_element has permuted dists, so
+    // inlier flags no longer belong to their points; and a normal parallel to (1, 0, 0) yields NaNs.  What it returns in
+    // practice is the centroid of a haphazard subset of the observed map points with an axis-aligned rotation.  Here: the
+    // same steps with those defects removed -- RANSAC over 3-point planes of the current frame's observed 3-D map points
+    // (planes within 5 degrees of facing the world z axis only, score = the max(0.2 N, 20)-th smallest point-plane residual),
+    // inliers below 1.4 x the best score, homogeneous least-squares refit, normal turned away from the camera, pose =
+    // [Rodrigues(up x n, angle(up, n)) * Rodrigues((1, 0, 0)) | inlier centroid], written as Utils::toPoseArray(Mat) does
+    // (column-major 4x4).  Sampling uses std::mt19937 seeded per call from a counter: repeatable.  Returns 1 / 0.
+    int findPlane(float* out16, int iterations) {
+        std::vector<double> pts;
+        for (auto& kv : mappoints)
+            if (kv.second.observed && kv.second.is3d) { pts.push_back(kv.second.p[0]); pts.push_back(kv.second.p[1]); pts.push_back(kv.second.p[2]); }
+        const int n = (int)pts.size() / 3;
+        if (n < 32) return 0;
+        std::vector<int> indices(n), pick(3);
+        for (int i = 0; i < n; i++) indices[i] = i;
+        std::vector<float> dists(n), best_d(n, 0.f), tmp(n);
+        float best = 1e10f;
+        std::mt19937 rng(0x9e3779b9u + plane_calls++);
+        const int kth = std::max((int)(0.2 * n), 20);
+        for (int it = 0; it < iterations; it++) {
+            std::sample(indices.begin(), indices.end(), pick.begin(), 3, rng);
+            const double* p0 = &pts[3 * pick[0]];
+            const double* p1 = &pts[3 * pick[1]];
+            const double* p2 = &pts[3 * pick[2]];
+            const double u[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, v[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+            double pl[4] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0], 0};
+            pl[3] = -(pl[0] * p0[0] + pl[1] * p0[1] + pl[2] * p0[2]);
+            const double nn = sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2] + pl[3] * pl[3]);   // the SVD's null vector has unit 4-norm
+            if (!(nn > 0)) continue;
+            const float a = (float)(pl[0] / nn), b = (float)(pl[1] / nn), c = (float)(pl[2] / nn), d = (float)(pl[3] / nn);
+            if (sqrt((double)a * a + (double)b * b) > sin(5.0f * 3.14159265358979323846 / 180.0f)) continue;   // |normal x z| > sin(5 deg)
+            const float f = 1.0f / sqrtf(a * a + b * b + c * c + d * d);
+            for (int i = 0; i < n; i++) dists[i] = fabsf((float)pts[3 * i] * a + (float)pts[3 * i + 1] * b + (float)pts[3 * i + 2] * c + d) * f;
+            tmp = dists;
+            std::nth_element(tmp.begin(), tmp.begin() + kth, tmp.end());
+            if (tmp[kth] < best) { best = tmp[kth]; best_d = dists; }
+        }
+        const float thr = 1.4f * best;
+        std::vector<int> inl;
+        for (int i = 0; i < n; i++) if (best_d[i] < thr) inl.push_back(i);
+        if ((int)inl.size() < 32 || !(best < 1e10f)) return 0;
+        // homogeneous refit: the eigenvector of sum [p 1]^T [p 1] with the smallest eigenvalue (cyclic Jacobi, 4x4)
+        double M[16] = {0}, origin[3] = {0, 0, 0};
+        for (int i : inl) {
+            const double q[4] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], 1.0};
+            for (int r = 0; r < 4; r++) for (int cc = 0; cc < 4; cc++) M[4 * r + cc] += q[r] * q[cc];
+            for (int r = 0; r < 3; r++) origin[r] += q[r];
+        }
+        for (int r = 0; r < 3; r++) origin[r] /= (double)inl.size();
+        double V[16];
+        for (int i = 0; i < 16; i++) V[i] = (i % 5 == 0);
+        for (int sweep = 0; sweep < 60; sweep++) {
+            double off = 0;
+            for (int r = 0; r < 4; r++) for (int cc = r + 1; cc < 4; cc++) off += M[4 * r + cc] * M[4 * r + cc];
+            if (off < 1e-300) break;
+            for (int pI = 0; pI < 3; pI++)
+                for (int qI = pI + 1; qI < 4; qI++) {
+                    const double apq = M[4 * pI + qI];
+                    if (apq == 0.0) continue;
+                    const double theta = (M[5 * qI] - M[5 * pI]) / (2 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                    const double cs = 1 / sqrt(t * t + 1), sn = t * cs;
+                    for (int k = 0; k < 4; k++) { const double x = M[4 * k + pI], y = M[4 * k + qI]; M[4 * k + pI] = cs * x - sn * y; M[4 * k + qI] = sn * x + cs * y; }
+                    for (int k = 0; k < 4; k++) { const double x = M[4 * pI + k], y = M[4 * qI + k]; M[4 * pI + k] = cs * x - sn * y; M[4 * qI + k] = sn * x + cs * y; }
+                    for (int k = 0; k < 4; k++) { const double x = V[4 * k + pI], y = V[4 * k + qI]; V[4 * k + pI] = cs * x - sn * y; V[4 * k + qI] = sn * x + cs * y; }
+                }
+        }
+        int m = 0;
+        for (int i = 1; i < 4; i++) if (M[5 * i] < M[5 * m]) m = i;
+        double a = V[m], b = V[4 + m], c = V[8 + m];
+        const double fn = 1.0 / sqrt(a * a + b * b + c * c);
+        // camera centre as the reference computes it from its transposed pose matrix (utils.cpp:51-75): Oc = -R t
+        double Rm[9], Oc[3];
+        cur.Twc.R(Rm);
+        for (int r = 0; r < 3; r++) Oc[r] = -(Rm[3 * r] * cur.Twc.t[0] + Rm[3 * r + 1] * cur.Twc.t[1] + Rm[3 * r + 2] * cur.Twc.t[2]);
+        if ((Oc[0] - origin[0]) * a + (Oc[1] - origin[1]) * b + (Oc[2] - origin[2]) * c > 0) { a = -a; b = -b; c = -c; }
+        const double nx = a * fn, ny = b * fn, nz = c * fn;
+        // R1 = Rodrigues((up x n) * angle / |up x n|), up = (1, 0, 0); R2 = Rodrigues(up) = 1 rad about x (as written in the reference)
+        const double vx = 0, vy = -nz, vz = ny, sa = sqrt(vy * vy + vz * vz), ca = nx, ang = atan2(sa, ca);
+        double R1[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (sa > 1e-12) {
+            const double kx = vx / sa, ky = vy / sa, kz = vz / sa, cA = cos(ang), sA = sin(ang), C1 = 1 - cA;
+            const double Rr[9] = {cA + kx * kx * C1, kx * ky * C1 - kz * sA, kx * kz * C1 + ky * sA,
+                                  ky * kx * C1 + kz * sA, cA + ky * ky * C1, ky * kz * C1 - kx * sA,
+                                  kz * kx * C1 - ky * sA, kz * ky * C1 + kx * sA, cA + kz * kz * C1};
+            for (int i = 0; i < 9; i++) R1[i] = Rr[i];
+        } else if (ca < 0) { R1[0] = -1; R1[4] = -1; }   // normal = -up: half a turn about z (the reference produces NaNs here)
+        const double c1 = cos(1.0), s1 = sin(1.0);
+        const double R2[9] = {1, 0, 0, 0, c1, -s1, 0, s1, c1};
+        double Rp[9];
+        for (int r = 0; r < 3; r++)
+            for (int cc = 0; cc < 3; cc++) Rp[3 * r + cc] = R1[3 * r] * R2[cc] + R1[3 * r + 1] * R2[3 + cc] + R1[3 * r + 2] * R2[6 + cc];
+        for (int cc = 0; cc < 3; cc++) { for (int r = 0; r < 3; r++) out16[4 * cc + r] = (float)Rp[3 * r + cc]; out16[4 * cc + 3] = 0.f; }
+        out16[12] = (float)origin[0]; out16[13] = (float)origin[1]; out16[14] = (float)origin[2]; out16[15] = 1.f;
+        return 1;
+    }
+    unsigned plane_calls = 0;
 
     // ---- state the facade reads
     Camera cam;

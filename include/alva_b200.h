@@ -353,6 +353,9 @@ int  alva_system_find_camera_pose(alva_system*, const uint8_t* rgba, float* pose
  * millisecond give the reference's motion model dt = 0) */
 int  alva_system_find_camera_pose_ts(alva_system*, const uint8_t* rgba, double t_ms, float* pose16);
 int  alva_system_find_camera_pose_imu(alva_system*, const uint8_t* rgba, const double* imu, float* pose16);
+/* System::findPlane (system.cpp:123-137, 177-342): RANSAC plane through the current frame's observed 3-D map points; out16 =
+ * plane pose, column-major 4x4 as Utils::toPoseArray(cv::Mat) writes it; returns 1 / 0 (fewer than 32 points or inliers).  The
+ * procedure is the reference's as intended -- its own code never fits a plane to the coordinates. */
 int  alva_system_find_plane(alva_system*, float* out16, int iterations);
 int  alva_system_get_frame_points(alva_system*, int32_t* xy, int cap_pairs);   /* returns the true count */
 int  alva_system_num_matched(alva_system*);   /* keypoints of the current frame (Frame::numKeypoints_) */

@@ -186,4 +186,14 @@ int ref_system_info8(void* h, int32_t* out8) {
     return 0;
 }
 
+// System::findPlane (system.cpp:123-137) -> processPlane (:177-342), unmodified: RANSAC over the current frame's observed 3-D
+// map points (seeded from std::random_device: not repeatable).  Returns the reference's 0 / 1; out16 as Utils::toPoseArray(Mat).
+int ref_system_find_plane(void* h, float* out16, int iterations) {
+    System* s = (System*)h;
+    cv::Mat mat = s->processPlane(s->mapManager_->getCurrentFrameMapPoints(), s->currFrame_->getTwc(), iterations);
+    if (mat.empty()) return 0;
+    Utils::toPoseArray(mat, out16);
+    return 1;
+}
+
 }  // extern "C"

@@ -170,6 +170,7 @@ int cpu_system_keypoints(void* p, int32_t* ids, float* px, uint8_t* is3d, double
     }
     return n;
 }
+int cpu_system_find_plane(void* p, float* out16, int iterations) { return ((CpuSystem*)p)->core.findPlane(out16, iterations); }
 int cpu_system_info(void* p, int32_t* out8) {
     CpuSystem* s = (CpuSystem*)p;
     out8[0] = s->core.cur.id; out8[1] = s->core.cur.kfid; out8[2] = s->core.cur.n; out8[3] = s->core.cur.n3d;

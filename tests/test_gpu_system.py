@@ -101,7 +101,10 @@ def test_system_follows_the_reference():
             mk = g["f0_has_desc"] == 1
             assert (desc[:n][mk] == g["f0_desc"][mk]).all()
     out = np.zeros(16, np.float32)
-    assert L.alva_system_find_plane(s, P(out), 50) == 0
+    assert L.alva_system_find_plane(s, P(out), 250) == 1                             # the scene is a plane facing the first camera
+    M = out.reshape(4, 4).T
+    assert np.abs(M[:3, :3].T @ M[:3, :3] - np.eye(3)).max() < 1e-5 and abs(M[2, 0]) > 0.99   # R1 maps (1,0,0) onto the normal ~ +-z
+    assert np.abs(M[:3, 3] - wp[d3 == 1].mean(0)).max() < 0.5                        # origin = centroid of the inliers
     assert L.alva_system_reset(s) == 0
     # after a reset the next frame is a first frame again: same keypoints as frame 0 except for the adapted detector quality
     assert L.alva_system_find_camera_pose_ts(s, P(np.ascontiguousarray(frames[0])), 5000.0, P(pose)) == 3

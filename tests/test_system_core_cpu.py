@@ -180,3 +180,34 @@ def test_lockstep_at_720p_with_the_live_reference(oracle, ref):
     assert last[4] == 1 and last[1] >= 2 and last[2] > 500          # initialised, at least keyframe 2 (a local BA ran), 720p-sized
     ref.ref_system_destroy(r)
     S.cpu_system_destroy(s)
+
+
+def test_find_plane_on_the_planar_scene(oracle):
+    """System::findPlane as intended (system_core.h lists the defects of the reference's own processPlane, which make it
+    unpinnable): 0 before the initialisation; afterwards the synthetic scene -- a textured plane facing the first camera -- is
+    found: unit rotation whose first column (the image of `up` = (1, 0, 0) under R1) is the plane normal ~ +-z, origin at the
+    inliers' centroid, normal pointing away from the camera; repeatable call to call."""
+    g, frames = frames_and_golden()
+    S = cpu_system_lib()
+    S.cpu_system_find_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    K = g["K"]
+    s = S.cpu_system_create(frames.shape[2], frames.shape[1], K[0], K[1], K[2], K[3])
+    out = np.zeros(16, np.float32)
+    T = np.zeros(7)
+    for k in range(40):
+        S.cpu_system_process(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(T))
+        if k == 5:
+            assert S.cpu_system_find_plane(s, P(out), 250) == 0          # fewer than 32 map points: no plane
+    assert S.cpu_system_find_plane(s, P(out), 250) == 1
+    M = out.reshape(4, 4).T                                              # Utils::toPoseArray(Mat) writes column-major
+    R, t = M[:3, :3].astype(np.float64), M[:3, 3]
+    assert np.abs(R.T @ R - np.eye(3)).max() < 1e-5 and abs(np.linalg.det(R) - 1) < 1e-5 and M[3, 3] == 1
+    n = R[:, 0]
+    assert abs(n[2]) > 0.999                                             # the plane z = const of the first camera
+    ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3))
+    m = S.cpu_system_keypoints(s, P(ids), P(px), P(d3), P(wp), CAP)
+    pts = wp[:m][d3[:m] == 1]
+    assert np.abs(t - pts.mean(0)).max() < 0.5 and np.abs((pts - t) @ n).mean() < 0.2   # on the plane of the map points
+    cam = T[:3]
+    assert (cam - t) @ n < 0                                             # turned away from the camera
+    S.cpu_system_destroy(s)
