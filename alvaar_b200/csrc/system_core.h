@@ -148,8 +148,13 @@ struct Camera {
     int w = 0, h = 0;
     // CameraCalibration::undistortImagePoint with the zero distortion the shim always passes: cv::undistortPoints(..., K, D, K)
     // evaluates fx * ((u - cx) * (1 / fx)) + cx in double and rounds to float (calib3d/src/undistort.dispatch.cpp)
+    double ifx = 1, ify = 1, k00 = 1, k02 = 0, k11 = 1, k12 = 0, k22 = 1;   // loop invariants of the two functions below
+    void prepare() {
+        ifx = 1. / fx; ify = 1. / fy;
+        const double id = 1. / (fx * fy);
+        k00 = fy * id; k02 = (-(cx * fy)) * id; k11 = fx * id; k12 = (-(fx * cy)) * id; k22 = (fx * fy) * id;
+    }
     void undistort(float u, float v, float& ux, float& uy) const {
-        const double ifx = 1. / fx, ify = 1. / fy;
         const double x = ((double)u - cx) * ifx, y = ((double)v - cy) * ify;
         ux = (float)(fx * x + cx); uy = (float)(fy * y + cy);
     }
@@ -157,8 +162,6 @@ struct Camera {
     // (cofactor * (1 / det), det = fx * fy), and the initialisation's refinement amplifies a 1-ulp change of a bearing vector to
     // 1e-4 in the pose, so the same expression tree is used here
     void bearing(float ux, float uy, double* bv) const {
-        const double id = 1. / (fx * fy);
-        const double k00 = fy * id, k02 = (-(cx * fy)) * id, k11 = fx * id, k12 = (-(fx * cy)) * id, k22 = (fx * fy) * id;
         bv[0] = (k00 * (double)ux + 0.0 * (double)uy) + k02 * 1.0;
         bv[1] = (0.0 * (double)ux + k11 * (double)uy) + k12 * 1.0;
         bv[2] = (0.0 * (double)ux + 0.0 * (double)uy) + k22 * 1.0;
@@ -166,8 +169,6 @@ struct Camera {
         bv[0] /= n; bv[1] /= n; bv[2] /= n;
     }
     void inverseK(float ux, float uy, double* b) const {   // inverseK_ * [unpx, 1] (not normalised)
-        const double id = 1. / (fx * fy);
-        const double k00 = fy * id, k02 = (-(cx * fy)) * id, k11 = fx * id, k12 = (-(fx * cy)) * id, k22 = (fx * fy) * id;
         b[0] = (k00 * (double)ux + 0.0 * (double)uy) + k02 * 1.0;
         b[1] = (0.0 * (double)ux + k11 * (double)uy) + k12 * 1.0;
         b[2] = (0.0 * (double)ux + 0.0 * (double)uy) + k22 * 1.0;
@@ -260,10 +261,9 @@ struct Frame {
     void update(int id, float x, float y) {
         auto it = kps.find(id);
         if (it == kps.end()) return;
-        Keypoint k = it->second;
-        compute(x, y, k);
-        if (cellIdx(it->second.px, it->second.py) != cellIdx(k.px, k.py)) { gridRemove(it->second); gridAdd(k); }
-        it->second = k;
+        Keypoint& k = it->second;   // same effect as the reference's copy / recompute / updateKeypointInGrid / assign
+        if (cellIdx(k.px, k.py) != cellIdx(x, y)) { gridRemove(k); compute(x, y, k); gridAdd(k); }
+        else compute(x, y, k);
     }
     void remove(int id) {
         auto it = kps.find(id);
@@ -444,6 +444,7 @@ public:
 
     void configure(int w, int h, double fx, double fy, double cx, double cy) {
         cam.w = w; cam.h = h; cam.fx = fx; cam.fy = fy; cam.cx = cx; cam.cy = cy;
+        cam.prepare();
         cell = 40;                                                        // State(w, h, 40) (system.cpp:15)
         max_kps = (int)(ceil((double)w / cell) * ceil((double)h / cell));   // state.cpp:3-12
         cur.init(&cam, cell);                                             // Frame(calibration, State::frameMaxCellSize_ = 40)
@@ -578,6 +579,7 @@ public:
         return 1;
     }
     unsigned plane_calls = 0;
+    std::vector<float> parallax_scratch;
 
     // ---- state the facade reads
     Camera cam;
@@ -1118,11 +1120,17 @@ private:
     void kltTracking() {   // kltTrackingFromMotionPrior (kltUsePrior_ = true)
         std::vector<int> ids3, ids;
         std::vector<float> kps3, pri3, kps, pri;
+        ids3.reserve(cur.n3d); kps3.reserve(2 * (size_t)cur.n3d); pri3.reserve(2 * (size_t)cur.n3d);
+        ids.reserve(cur.n); kps.reserve(2 * (size_t)cur.n); pri.reserve(2 * (size_t)cur.n);
+        double Rcw[9];
+        cur.Tcw.R(Rcw);
+        const double* tcw = cur.Tcw.t;
         for (auto& kv : cur.kps) {
             const Keypoint& k = kv.second;
             if (k.is3d) {
                 double c[3];
-                cur.Tcw.apply(mappoints.at(k.id).p, c);
+                const double* X = mappoints.at(k.id).p;
+                for (int i = 0; i < 3; i++) c[i] = (Rcw[3 * i] * X[0] + Rcw[3 * i + 1] * X[1] + Rcw[3 * i + 2] * X[2]) + tcw[i];
                 float u, v;
                 cam.projCamToImageDist(c, u, v);
                 if (cam.inImage(u, v)) {
@@ -1170,6 +1178,7 @@ private:
         if (cur.n3d < 4) return false;
         std::vector<double> bvs, wpts, uv;
         std::vector<int> ids;
+        bvs.reserve(3 * (size_t)cur.n3d); wpts.reserve(3 * (size_t)cur.n3d); uv.reserve(2 * (size_t)cur.n3d); ids.reserve(cur.n3d);
         const bool do_p3p = p3p_req || true;   // State::p3pEnabled_ = true (system.cpp:19)
         for (auto& kv : cur.kps) {
             const Keypoint& k = kv.second;
@@ -1239,7 +1248,8 @@ private:
         }
         float avg = 0.f;
         int np = 0;
-        std::set<float> s;
+        std::vector<float>& s = parallax_scratch;   // the reference collects into a std::set<float>: DISTINCT values, ascending
+        s.clear();
         for (auto& kv : cur.kps) {
             const Keypoint& k = kv.second;
             const Keypoint* kk = kf.find(k.id);
@@ -1253,11 +1263,15 @@ private:
             const float parallax = norm2f(ux, uy, kk->ux, kk->uy);
             avg += parallax;
             np++;
-            if (median) s.insert(parallax);
+            if (median) s.push_back(parallax);
         }
         if (np == 0) return 0.f;
         avg /= (float)np;
-        if (median) { auto it = s.begin(); std::advance(it, s.size() / 2); avg = *it; }
+        if (median) {   // element size/2 of the set == of the sorted distinct values (no per-value node allocation here)
+            std::sort(s.begin(), s.end());
+            s.erase(std::unique(s.begin(), s.end()), s.end());
+            avg = s[s.size() / 2];
+        }
         return avg;
     }
 
