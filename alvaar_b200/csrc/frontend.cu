@@ -19,6 +19,7 @@
 //   * keypoints leave as packed keys (y<<20 | x<<8 | score); a row-bucket pass restores cv::FAST's
 //     row-major order when the caller asks for it.
 #include "alva_common.cuh"
+#include "fast_swar.h"
 #include "../../include/alva_b200.h"
 #include <stdlib.h>
 #include <algorithm>
@@ -187,7 +188,7 @@ __device__ __forceinline__ uint32_t fast_candidates8(const uint32_t* g0, uint32_
     return cand;
 }
 
-template <bool RGBA>
+template <bool RGBA, bool ANTI = false>
 __global__ void __launch_bounds__(NTHREADS, 4)
 frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -384,7 +385,23 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
         if (__any_sync(0xffffffffu, vm != 0)) {
             // gray rows needed: centre rows 8*warp+3 .. 8*warp+10, i.e. rows 8*warp .. 8*warp + 13 (< BH = 70)
             const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
-            uint32_t cand = hi_thr ? fast_candidates8<true>(g0, K, P.mul) : fast_candidates8<false>(g0, K, P.mul);
+            uint32_t cand;
+            if (ANTI) {
+                // experimental (alva_set_option("frontend_antipodal", 1)): 8 of the 16 ring flag words are assembled from their
+                // antipodal partners instead of recomputed -- fast_swar.h; its host emulation is checked in the CPU suite
+                uint32_t acc[16];
+                if (hi_thr) fast_swar::phase1<true, GPW>(g0, K, P.mul, acc); else fast_swar::phase1<false, GPW>(g0, K, P.mul, acc);
+#define ALVA_ASM_LEFT(M)  { const uint32_t o_ = acc[fast_swar::source_of(M)]; acc[M] = fast_swar::assemble<M>(o_, __shfl_up_sync(0xffffffffu, o_, 1), 0u, acc[M]); }
+#define ALVA_ASM_RIGHT(M) { const uint32_t o_ = acc[fast_swar::source_of(M)]; acc[M] = fast_swar::assemble<M>(o_, 0u, __shfl_down_sync(0xffffffffu, o_, 1), acc[M]); }
+                ALVA_ASM_RIGHT(5) ALVA_ASM_RIGHT(6) ALVA_ASM_RIGHT(7)       // sources 13, 14, 15: dx < 0 -> pixels to the right
+                acc[8] = fast_swar::assemble<8>(acc[0], 0u, 0u, acc[8]);    // source 0: dx = 0
+                ALVA_ASM_LEFT(9) ALVA_ASM_LEFT(10) ALVA_ASM_LEFT(11) ALVA_ASM_LEFT(12)   // sources 1..4: dx > 0 -> pixels to the left
+#undef ALVA_ASM_LEFT
+#undef ALVA_ASM_RIGHT
+                cand = fast_swar::contiguous9(acc);
+            } else {
+                cand = hi_thr ? fast_candidates8<true>(g0, K, P.mul) : fast_candidates8<false>(g0, K, P.mul);
+            }
             cand &= vm;
             // ordered compaction of the candidate pixels into the warp queue (one prefix sum per 8 rows)
             const int mine = __popc(cand);
@@ -708,6 +725,8 @@ __global__ void __launch_bounds__(256) scharr_kernel(const ScharrLevels L) {
 }  // namespace
 
 // =================================================================================== host launchers
+int alva_g_frontend_antipodal = 0;   // alva_set_option("frontend_antipodal", 1): experimental pre-test variant (RGBA path only)
+
 static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
                            uint8_t* l1, int thr, uint32_t* keys, int32_t* counts, int cap) {
     FrontendParams P{};
@@ -736,7 +755,10 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     P.use_tma = (tma_ok && !no_tma) ? 1 : 0;
     const int grid = P.tiles_x * P.tiles_y * nframes;
     const size_t smem = sizeof(SmemLayout) + 128;
-    if (rgba_mode) {
+    if (rgba_mode && alva_g_frontend_antipodal) {
+        ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_tile_kernel<true, true><<<grid, NTHREADS, smem, ctx->stream>>>(tmap, P);
+    } else if (rgba_mode) {
         ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         frontend_tile_kernel<true><<<grid, NTHREADS, smem, ctx->stream>>>(tmap, P);
     } else {
