@@ -279,6 +279,8 @@ int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
 
 /* Library-wide switches.  "ba_dense_schur" = 1: compute the -(E'F)'(E'E)^-1(E'F) part of the Schur complement as a dense
  * FP64 tensor-core SYRK (S -= Wt'Wt, DMMA) instead of per-landmark atomics (default 0).
+ * "frontend_antipodal" = 1: EXPERIMENTAL variant of the fused front end's FAST-9 pre-test (antipodal flag sharing, csrc/fast_swar.h;
+ * same results by construction, checked by host emulation, not yet validated on a GPU) -- default 0.
  * "pipeline_ba_overlap" = 0: alva_pipeline runs the local BA after the per-frame stages instead of beside them on its own
  * stream (default 1; results are identical, only the schedule changes).
  * "knn_qpw" = 4 | 8: queries a warp of the Hamming matcher keeps in registers (8: 128 registers / 16 warps per SM;
