@@ -272,6 +272,21 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
             if (it < ROUNDS - 1 || warp + NWARPS * it < BH) px[it] = sp[it * NWARPS * 32];
         uint8_t* d = l0 ? l0 + (size_t)(y0 + warp - 4) * w + x : nullptr;
         const size_t dstep = (size_t)NWARPS * w;
+        if (ANTI && w4) {
+            // experimental instantiation: the same conversion and stores with the row / width tests hoisted out of the rounds
+            // (the default loop below re-tests w % 4 and carries the byte-store fallback in every round: more predicate and
+            // branch scaffolding than arithmetic, profiles/r01f_frontend_full.txt)
+            const int by_end = min(4 + TH, h - y0 + 4);   // box rows [4, by_end) are image rows of this tile
+#pragma unroll
+            for (int it = 0; it < ROUNDS; it++) {
+                const int by = warp + NWARPS * it;
+                if (it < ROUNDS - 1 || by < BH) {
+                    const uint32_t v = gray4(px[it]);
+                    gp[it * NWARPS * GPW] = v;
+                    if (colstore && (it > 0 || by >= 4) && by < by_end) *reinterpret_cast<uint32_t*>(d + it * dstep) = v;
+                }
+            }
+        } else
 #pragma unroll
         for (int it = 0; it < ROUNDS; it++) {
             const int by = warp + NWARPS * it;
