@@ -340,7 +340,10 @@ struct CudaBackend {
 class System {
 public:
     System() : core_(be_) {}
-    ~System() { be_.release(); }
+    ~System() {
+        for (void* p : pinned_) { cudaHostUnregister(p); cudaGetLastError(); }
+        be_.release();
+    }
 
     int configure(int imageWidth, int imageHeight, double fx, double fy, double cx, double cy, double k1, double k2, double p1,
                   double p2) {
@@ -436,6 +439,21 @@ public:
         return n;
     }
     int getPose(double* Twc7) { core_.cur.Twc.to7(Twc7); return 0; }
+    // page-lock a caller-owned frame buffer that is reused from call to call (the reference's shim allocates its image buffer once,
+    // system.js:63-67): uploads from it then run at the host link's rate instead of through the driver's pageable staging
+    int pinBuffer(void* ptr, size_t bytes) {
+        if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+            alva_set_error("alva_system_pin_buffer: cudaHostRegister -> %s", cudaGetErrorString(cudaGetLastError()));
+            return ALVA_E_CUDA;
+        }
+        pinned_.push_back(ptr);
+        return 0;
+    }
+    int unpinBuffer(void* ptr) {
+        for (size_t i = 0; i < pinned_.size(); i++)
+            if (pinned_[i] == ptr) { cudaHostUnregister(ptr); cudaGetLastError(); pinned_.erase(pinned_.begin() + i); return 0; }
+        return ALVA_E_INVALID;
+    }
     void debugSetInitialisation(const double* Rt12, const uint8_t* outlier, int n) {
         be_.init_Rt.assign(Rt12, Rt12 + 12);
         be_.init_outlier.assign(outlier, outlier + n);
@@ -469,6 +487,7 @@ private:
         for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) p[4 * r + c] = (float)R[3 * r + c]; p[4 * r + 3] = 0.f; }
         p[12] = (float)T.t[0]; p[13] = (float)T.t[1]; p[14] = (float)T.t[2]; p[15] = 1.f;
     }
+    std::vector<void*> pinned_;
     CudaBackend be_;
     alva_sys::SystemCore<CudaBackend> core_;
     bool configured_ = false;
@@ -523,5 +542,10 @@ extern "C" int alva_system_debug_set_initialisation(alva_system* s, const double
     s->sys.debugSetInitialisation(Rt12, outlier, n);
     return 0;
 }
+extern "C" int alva_system_pin_buffer(alva_system* s, void* host_ptr, size_t bytes) {
+    if (!s || !host_ptr || !bytes) return ALVA_E_INVALID;
+    return s->sys.pinBuffer(host_ptr, bytes);
+}
+extern "C" int alva_system_unpin_buffer(alva_system* s, void* host_ptr) { return (s && host_ptr) ? s->sys.unpinBuffer(host_ptr) : ALVA_E_INVALID; }
 extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
 extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }

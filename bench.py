@@ -543,10 +543,13 @@ def system_api_times_at(w, h, nf, with_reference):
     L.alva_system_find_camera_pose_ts.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.alva_system_get_info.argtypes = [C.c_void_p, C.c_void_p]
     L.alva_system_destroy.argtypes = [C.c_void_p]
+    L.alva_system_pin_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     out = {}
     for rep in range(2):   # the second pass is the warm one
         s = C.c_void_p(L.alva_system_create(0))
         assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+        # the caller-owned frame memory is page-locked once, as a host that reuses its image buffer would do (e2e: pinned host RGBA in)
+        out["input_pinned"] = L.alva_system_pin_buffer(s, P(frames), frames.nbytes) == 0
         pose = np.zeros(16, np.float32)
         ms, status, kf = [], [], []
         info = np.zeros(8, np.int32)

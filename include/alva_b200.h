@@ -368,6 +368,11 @@ int  alva_system_get_tracks(alva_system*, int32_t* ids, float* px, uint8_t* is3d
 /* their 256-bit ORB descriptors (Keypoint::desc_, feature_extractor.cpp:160-214), same order: desc [cap][32], has [cap] (0 = the
  * reference keeps an empty Mat: point within 31 px of the border) */
 int  alva_system_get_descriptors(alva_system*, uint8_t* desc, uint8_t* has, int cap);
+/* Page-lock (cudaHostRegister) a caller-owned frame buffer that is reused from call to call -- the reference's shim allocates its
+ * image buffer once (system.js:63-67) -- so that alva_system_find_camera_pose uploads it at the host link's rate; unpin before
+ * freeing it (alva_system_destroy unpins what is left).  Optional: un-pinned buffers work, through the driver's pageable staging. */
+int  alva_system_pin_buffer(alva_system*, void* host_ptr, size_t bytes);
+int  alva_system_unpin_buffer(alva_system*, void* host_ptr);
 /* TEST HOOK: the result ([Rwc | twc] 3x4 row-major, outlier flags of the n correspondences) the NEXT 5-point initialisation
  * returns instead of running alva_k_essential_5pt -- used by the parity tests to plug in the reference's own initialisation
  * result (whose refinement is noise-limited) and check everything downstream of it at 1e-7; ignored when n does not
