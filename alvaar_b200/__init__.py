@@ -6,6 +6,7 @@ works anywhere (so the symbol table can be checked), but creating a context with
 """
 from .lib import (AlvaError, Context, lib, lib_path, key_x, key_y, key_score, unpack_keys,
                   ORB_FMA, ORB_IC_ANGLE, ORB_HARRIS)
+from .system import System
 
 __all__ = ["AlvaError", "Context", "lib", "lib_path", "key_x", "key_y", "key_score", "unpack_keys",
-           "ORB_FMA", "ORB_IC_ANGLE", "ORB_HARRIS"]
+           "ORB_FMA", "ORB_IC_ANGLE", "ORB_HARRIS", "System"]

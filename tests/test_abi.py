@@ -57,3 +57,14 @@ def test_reference_class_shim_compiles_and_links():
                            "-Wl,-rpath," + os.path.dirname(lib)])
     r = subprocess.run([out], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_python_system_binding_fails_loudly_without_a_gpu():
+    """alvaar_b200.System (the ctypes mirror of the reference's class): without an sm_100 device configure() must raise -- never a
+    silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import alvaar_b200
+    with pytest.raises(alvaar_b200.AlvaError):
+        alvaar_b200.System(640, 480, 500.0, 500.0, 320.0, 240.0)

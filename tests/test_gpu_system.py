@@ -218,3 +218,24 @@ def test_system_full_size_against_the_cpu_oracle_backend(oracle, w, h, nf, nmin)
     assert seen[0] == 3 and seen[-1] == 1 and n > nmin
     S.cpu_system_destroy(c)
     L.alva_system_destroy(s)
+
+
+def test_python_system_class():
+    """alvaar_b200.System: the ctypes mirror of the reference's class, end to end on the golden's first frames"""
+    import alvaar_b200
+    g, frames = frames_and_golden()
+    K = g["K"]
+    s = alvaar_b200.System(frames.shape[2], frames.shape[1], K[0], K[1], K[2], K[3])
+    with pytest.raises(ValueError):
+        s.find_camera_pose(frames[0][:, :, :3])
+    seen = []
+    for k in range(20):
+        st, pose = s.find_camera_pose(np.ascontiguousarray(frames[k]), k * 33.333)
+        assert st == g["ref_status"][k]
+        seen.append(st)
+    ids, px, d3, wp = s.tracks()
+    rids, rpx, rd3, rwp = frame_slice(g, "ref_", 19)
+    assert (ids == rids).all() and (d3 == rd3).all() and s.info()["initialised"] == 1 and s.find_plane() is not None
+    s.reset()
+    assert s.info()["keypoints"] == 0
+    s.close()
