@@ -26,6 +26,23 @@ struct alva_ctx {
     size_t ba_ws_bytes = 0;
     void* det_ws = nullptr;         // alva_k_orb_detect's intermediate lists (own allocation, same reason)
     size_t det_ws_bytes = 0;
+    void* knn_ws = nullptr;         // tensor-core matcher: expanded int8 operand tiles, row map (hamming_mma.cu)
+    size_t knn_ws_bytes = 0;
+};
+
+// Every public entry point runs on the context's device whatever the caller's current device is (two Systems on two GPUs
+// driven from one thread; a System driven from a thread that did not create it) and restores the caller's device on exit.
+struct AlvaDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit AlvaDeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    explicit AlvaDeviceGuard(const alva_ctx* c) : AlvaDeviceGuard(c ? c->device : -1) {}
+    ~AlvaDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    AlvaDeviceGuard(const AlvaDeviceGuard&) = delete;
+    AlvaDeviceGuard& operator=(const AlvaDeviceGuard&) = delete;
 };
 
 void alva_set_error(const char* fmt, ...);

@@ -79,7 +79,9 @@ extern "C" alva_ctx* alva_ctx_create(int device, void* stream) {
         return nullptr;
     }
     if (device < 0 || device >= n) { alva_set_error("alva_ctx_create: device %d out of range (%d)", device, n); return nullptr; }
-    if ((e = cudaSetDevice(device)) != cudaSuccess) { alva_set_error("cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+    AlvaDeviceGuard guard__(device);   // the caller's current device is left as it was
+    int curdev = -1;
+    if ((e = cudaGetDevice(&curdev)) != cudaSuccess || curdev != device) { alva_set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return nullptr; }
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { alva_set_error("props: %s", cudaGetErrorString(e)); return nullptr; }
     if (prop.major != 10) {
@@ -103,17 +105,18 @@ extern "C" alva_ctx* alva_ctx_create(int device, void* stream) {
 
 extern "C" void alva_ctx_destroy(alva_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    AlvaDeviceGuard guard__(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->dev_stage) cudaFree(ctx->dev_stage);
     if (ctx->ba_ws) cudaFree(ctx->ba_ws);
     if (ctx->det_ws) cudaFree(ctx->det_ws);
+    if (ctx->knn_ws) cudaFree(ctx->knn_ws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
-extern "C" int alva_ctx_sync(alva_ctx* ctx) {
+extern "C" int alva_ctx_sync(alva_ctx* ctx) { AlvaDeviceGuard guard__(ctx);
     if (!ctx) { alva_set_error("null ctx"); return ALVA_E_INVALID; }
     ALVA_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -1394,7 +1394,7 @@ static bool ba_args_ok(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, con
 extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
                                const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
                                const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
-                               int max_iter, double* summary) {
+                               int max_iter, double* summary) { AlvaDeviceGuard guard__(ctx);
     if (!ba_args_ok(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, max_iter)) {
         alva_set_error("alva_k_ba_solve: bad argument (need 1 <= nkf <= 256)");
         return ALVA_E_INVALID;
@@ -1419,7 +1419,7 @@ extern "C" int alva_k_ba_solve(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
 extern "C" int alva_k_ba_local(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, const double* calib, double* poses,
                                const uint8_t* pose_const, double* invd, const int32_t* anch_kf, const double* anch_uv,
                                const int32_t* obs_kf, const int32_t* obs_lm, const double* obs_uv, double huber_delta,
-                               double chi2_thr, int max_iter, int32_t* flags, double* summary) {
+                               double chi2_thr, int max_iter, int32_t* flags, double* summary) { AlvaDeviceGuard guard__(ctx);
     if (!ba_args_ok(ctx, nprob, nkf, nlm, nobs, calib, poses, pose_const, invd, anch_kf, anch_uv, obs_kf, obs_lm, obs_uv, max_iter) ||
         !flags) {
         alva_set_error("alva_k_ba_local: bad argument (need 1 <= nkf <= 256, flags != NULL)");
@@ -1449,7 +1449,7 @@ extern "C" int alva_k_ba_local(alva_ctx* ctx, int nprob, int nkf, int nlm, int n
 extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, const double* calib, const double* poses,
                                    const double* invd, const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf,
                                    const int32_t* obs_lm, const double* obs_uv, double huber_delta, double* res, double* Ja,
-                                   double* Jp, double* Jd, double* cost_per_obs) {
+                                   double* Jp, double* Jd, double* cost_per_obs) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || nobs < 1 || !calib || !poses || !invd || !res || !Ja || !Jp || !Jd || !cost_per_obs) {
         alva_set_error("alva_k_ba_linearize: bad argument");
         return ALVA_E_INVALID;
@@ -1466,12 +1466,16 @@ extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, co
 extern int alva_g_knn_qpw;   // hamming.cu
 int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside the frame stages
 
-extern int alva_g_frontend_antipodal;   // frontend.cu
+extern int alva_g_frontend_antipodal, alva_g_frontend_variant;   // frontend.cu
+extern int alva_g_knn_mma, alva_g_knn_mma_mode;   // hamming_mma.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
+    if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
     if (name && !strcmp(name, "pipeline_ba_overlap")) { alva_g_ba_overlap = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "knn_qpw") && (value == 4 || value == 8)) { alva_g_knn_qpw = value; return 0; }
+    if (name && !strcmp(name, "knn_mma") && value >= 0 && value <= 2) { alva_g_knn_mma = value; return 0; }
+    if (name && !strcmp(name, "knn_mma_mode") && value >= 0 && value <= 2) { alva_g_knn_mma_mode = value; return 0; }
     alva_set_error("alva_set_option: unknown option");
     return ALVA_E_INVALID;
 }

@@ -467,7 +467,7 @@ void subpix_mask(float* m) {   // cornersubpix.cpp:72-81 with win = 3
 }  // namespace
 
 extern "C" int alva_k_corner_subpix(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, float* pts,
-                                    const int32_t* counts, int cap) {
+                                    const int32_t* counts, int cap) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !pts || !counts || nframes < 1 || cap < 1 || w < 11 || h < 11) { alva_set_error("alva_k_corner_subpix: bad argument"); return ALVA_E_INVALID; }
     DetectParams P{};
     P.img = gray; P.w = w; P.h = h; P.nframes = nframes;
@@ -479,7 +479,7 @@ extern "C" int alva_k_corner_subpix(alva_ctx* ctx, const uint8_t* gray, int w, i
 
 extern "C" int alva_k_detect_grid(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, int cell, const float* cur,
                                   const int32_t* ncur, int cur_cap, const int32_t* roi, double* quality, float* out,
-                                  int32_t* out_int, int32_t* counts, int out_cap) {
+                                  int32_t* out_int, int32_t* counts, int out_cap) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !roi || !quality || !out || !counts || nframes < 1 || out_cap < 1 || (ncur && (!cur || cur_cap < 1))) {
         alva_set_error("alva_k_detect_grid: bad argument");
         return ALVA_E_INVALID;

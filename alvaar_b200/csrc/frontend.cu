@@ -491,6 +491,285 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
     }
 }
 
+// ======================================================================================== variant 2
+// Same tile geometry, same results; what changed against frontend_tile_kernel (profiles/r01f_frontend_full.txt named the costs):
+//   * gray: row / width tests hoisted out of the rounds (the conversion was 18 % IDP and 80 % scaffolding);
+//   * pyramid L1: a thread owns 4 adjacent outputs x 2 rows (7 gray rows x {LDS.32, LDS.64, LDS.32}) instead of 2 x 4;
+//   * FAST pre-test with antipodal flag sharing (fast_swar.h);
+//   * candidate compaction on the TRANSPOSED bit matrix: a lane's 4 x 8 pixel block is either empty or crowded (corner
+//     clusters), so the per-lane emit loop ran at 14.6 active lanes; after a 32 x 32 bit transpose across the warp (2 PRMT + 3
+//     mask stages on SHFL.BFLY) lane b owns bit position b = (pixel j, row i) of all 32 lanes -- pixels 4 apart in one row,
+//     which no cluster fills -- and the loop is balanced.  The queue order that results (same row, distinct words) also makes
+//     the 16 ring loads of the scoring phase almost bank-conflict free;
+//   * the scoring loop compacts the true corners of the tile interior in place (queue prefix), so the NMS / emit phase walks
+//     ~4 % of the pixels with full lanes instead of re-walking every candidate; the score tile has a 33-word pitch.
+constexpr int SP2 = 132;
+constexpr int SPW2 = SP2 / 4;
+struct __align__(128) SmemLayout2 {
+    uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode); later the per-warp queues + the tile's keypoint list
+    uint8_t gray[GP * BH];         // TMA destination (gray mode)
+    uint8_t score[SP2 * SR];
+    uint64_t bar;
+    int kpcount;
+    int kpbase;
+};
+
+template <bool RGBA>
+__global__ void __launch_bounds__(NTHREADS, 4)
+frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    SmemLayout2& S = *reinterpret_cast<SmemLayout2*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int t = blockIdx.x;
+    const int tiles_per_frame = P.tiles_x * P.tiles_y;
+    const int f = t / tiles_per_frame;
+    t -= f * tiles_per_frame;
+    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int w = P.w, h = P.h;
+    const int sh = RGBA ? 0 : ((x0 - 8) & 15);
+    const int cbw = 1 + (sh >> 2);   // word index (within a gray smem row) of image column x0-4
+
+    // ------------------------------------------------------------------ A. load the tile (TMA only: the launcher falls back
+    // to the baseline kernel for geometries the tensor map cannot express)
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (RGBA) {
+            mbar_arrive_expect_tx(&S.bar, BW * BH * 4);
+            tma_load_3d(S.rgba, &tmap, &S.bar, x0 - 4, y0 - 4, f);
+        } else {
+            mbar_arrive_expect_tx(&S.bar, GP * BH);
+            tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8 - sh, y0 - 4, f);
+        }
+    }
+    {
+        uint32_t* sc = reinterpret_cast<uint32_t*>(S.score);
+        for (int i = tid; i < SP2 * SR / 4; i += NTHREADS) sc[i] = 0;
+        if (tid == 0) S.kpcount = 0;
+    }
+    mbar_wait(&S.bar, 0);
+
+    // ------------------------------------------------------------------ B. gray (w % 4 == 0 guaranteed by the TMA path)
+    if (RGBA) {
+        const uint4* src4 = reinterpret_cast<const uint4*>(S.rgba);
+        uint32_t* gw = reinterpret_cast<uint32_t*>(S.gray);
+        uint8_t* l0 = P.l0 ? P.l0 + (size_t)f * w * h : nullptr;
+        const int g = lane;
+        const int x = x0 + 4 * (g - 1);
+        const bool colstore = l0 && g >= 1 && g <= 30 && x < w;
+        constexpr int ROUNDS = (BH + NWARPS - 1) / NWARPS;
+        const uint4* sp = src4 + warp * 32 + g;
+        uint32_t* gp = gw + warp * GPW + 1 + g;
+        uint4 px[ROUNDS];
+#pragma unroll
+        for (int it = 0; it < ROUNDS; it++)
+            if (it < ROUNDS - 1 || warp + NWARPS * it < BH) px[it] = sp[it * NWARPS * 32];
+        uint8_t* d = l0 ? l0 + (ptrdiff_t)(y0 + warp - 4) * w + x : nullptr;
+        const size_t dstep = (size_t)NWARPS * w;
+        const int by_end = min(4 + TH, h - y0 + 4);   // box rows [4, by_end) are image rows of this tile
+#pragma unroll
+        for (int it = 0; it < ROUNDS; it++) {
+            const int by = warp + NWARPS * it;
+            if (it < ROUNDS - 1 || by < BH) {
+                const uint32_t v = gray4(px[it]);
+                gp[it * NWARPS * GPW] = v;
+                if (colstore && (it > 0 || by >= 4) && by < by_end) *reinterpret_cast<uint32_t*>(d + it * dstep) = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    const bool edge_l = (x0 == 0), edge_r = (x0 + TW >= w), edge_t = (y0 == 0), edge_b = (y0 + TH >= h);
+    if (P.l1 && (edge_l || edge_r || edge_t || edge_b)) {
+        if (edge_l || edge_r) {
+            for (int r = tid; r < BH; r += NTHREADS) {
+                uint8_t* row = S.gray + r * GP;
+                if (edge_l) { row[7 + sh] = row[9 + sh]; row[6 + sh] = row[10 + sh]; }
+                if (edge_r) {
+                    const int cw = w - x0 + 8 + sh;
+                    row[cw] = row[cw - 2];
+                    row[cw + 1] = row[cw - 3];
+                }
+            }
+            __syncthreads();
+        }
+        if (edge_t || edge_b) {
+            for (int c = tid; c < GP; c += NTHREADS) {
+                if (edge_t) { S.gray[3 * GP + c] = S.gray[5 * GP + c]; S.gray[2 * GP + c] = S.gray[6 * GP + c]; }
+                if (edge_b) {
+                    const int rh = h - y0 + 4;
+                    S.gray[rh * GP + c] = S.gray[(rh - 2) * GP + c];
+                    S.gray[(rh + 1) * GP + c] = S.gray[(rh - 3) * GP + c];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    const uint32_t* G = reinterpret_cast<const uint32_t*>(S.gray);
+
+    // ------------------------------------------------------------------ C. pyramid level 1: 4 outputs x 2 rows per thread
+    if (P.l1) {
+        const int w1 = (w + 1) >> 1, h1 = (h + 1) >> 1;
+        uint8_t* l1 = P.l1 + (size_t)f * w1 * h1;
+        const int pc = tid % 15, sg = tid / 15;   // 15 quad-columns x 16 row pairs (threads 240..255 idle)
+        const int lx = (x0 >> 1) + 4 * pc;
+        const int ly0 = (y0 >> 1) + 2 * sg;
+        if (sg < 16 && lx < w1 && ly0 < h1) {
+            const uint32_t* base = G + (4 * sg + 2) * GPW + cbw + 2 * pc;   // gray row 2j+2 for output row j = 2*sg
+            uint32_t hs[7][4];
+#pragma unroll
+            for (int r = 0; r < 7; r++) {
+                const uint32_t W0 = base[r * GPW], W1 = base[r * GPW + 1], W2 = base[r * GPW + 2], W3 = base[r * GPW + 3];
+                hs[r][0] = __dp4a(__byte_perm(W0, W1, 0x5432), 0x04060401u, __dp4a(W1, 0x00010000u, 0u));
+                hs[r][1] = __dp4a(W1, 0x04060401u, __dp4a(W2, 0x00000001u, 0u));
+                hs[r][2] = __dp4a(__byte_perm(W1, W2, 0x5432), 0x04060401u, __dp4a(W2, 0x00010000u, 0u));
+                hs[r][3] = __dp4a(W2, 0x04060401u, __dp4a(W3, 0x00000001u, 0u));
+            }
+            const bool quad_ok = (lx + 3 < w1) && ((w1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.l1) & 3) == 0);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int ly = ly0 + j;
+                if (ly < h1 && 2 * sg + j < TH / 2) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        v[i] = hs[2 * j][i] + hs[2 * j + 4][i] + (hs[2 * j + 1][i] + hs[2 * j + 3][i]) * 4u + hs[2 * j + 2][i] * 6u + 128u;
+                    // byte 1 of each sum
+                    const uint32_t o = __byte_perm(__byte_perm(v[0], v[1], 0x0051), __byte_perm(v[2], v[3], 0x0051), 0x5410);
+                    uint8_t* d = l1 + (size_t)ly * w1 + lx;
+                    if (quad_ok) *reinterpret_cast<uint32_t*>(d) = o;
+                    else
+                        for (int i = 0; i < 4 && lx + i < w1; i++) d[i] = (uint8_t)(o >> (8 * i));
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ D. FAST candidates + exact score
+    uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;
+    uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + NWARPS * QCAP * 2);
+    int cn = 0;   // corners of this warp inside the tile interior: prefix of Q after this phase
+    if (P.keys) {
+        const int thr = P.thr;
+        const bool hi_thr = thr >= 128;
+        const uint32_t K = (uint32_t)(hi_thr ? 255 - thr : 127 - thr) * 0x01010101u;
+        uint32_t vm;
+        {
+            const int xlo = max(3, x0 - 1), xhi = min(w - 4, x0 + TW);
+            const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
+            const int yb = y0 - 1 + 8 * warp;
+            const int r0v = max(ylo - yb, 0), r1v = min(yhi - yb, 7);
+            const uint32_t rowbits = r1v >= r0v ? ((0xffu >> (7 - r1v)) & (0xffu << r0v)) & 0xffu : 0u;
+            const int xb = x0 - 4 + 4 * lane;
+            const int c0v = max(xlo - xb, 0), c1v = min(xhi - xb, 3);
+            const uint32_t colbytes = c1v >= c0v ? ((0x01010101u >> (8 * (3 - c1v))) & (0x01010101u << (8 * c0v))) : 0u;
+            vm = colbytes * rowbits;
+        }
+        if (__any_sync(0xffffffffu, vm != 0)) {
+            const uint32_t* g0 = G + (8 * warp) * GPW + cbw + lane;
+            uint32_t acc[16];
+            if (hi_thr) fast_swar::phase1<true, GPW>(g0, K, P.mul, acc); else fast_swar::phase1<false, GPW>(g0, K, P.mul, acc);
+#define ALVA_ASM_LEFT(M)  { const uint32_t o_ = acc[fast_swar::source_of(M)]; acc[M] = fast_swar::assemble<M>(o_, __shfl_up_sync(0xffffffffu, o_, 1), 0u, acc[M]); }
+#define ALVA_ASM_RIGHT(M) { const uint32_t o_ = acc[fast_swar::source_of(M)]; acc[M] = fast_swar::assemble<M>(o_, 0u, __shfl_down_sync(0xffffffffu, o_, 1), acc[M]); }
+            ALVA_ASM_RIGHT(5) ALVA_ASM_RIGHT(6) ALVA_ASM_RIGHT(7)
+            acc[8] = fast_swar::assemble<8>(acc[0], 0u, 0u, acc[8]);
+            ALVA_ASM_LEFT(9) ALVA_ASM_LEFT(10) ALVA_ASM_LEFT(11) ALVA_ASM_LEFT(12)
+#undef ALVA_ASM_LEFT
+#undef ALVA_ASM_RIGHT
+            uint32_t u = fast_swar::contiguous9(acc) & vm;
+            // 32 x 32 bit transpose across the warp: afterwards lane b holds, in bit l, lane l's flag for bit position b
+            {
+                uint32_t x = __shfl_xor_sync(0xffffffffu, u, 16);
+                u = __byte_perm(u, x, (lane & 16) ? 0x3276u : 0x5410u);
+                x = __shfl_xor_sync(0xffffffffu, u, 8);
+                u = __byte_perm(u, x, (lane & 8) ? 0x3715u : 0x6240u);
+                x = __shfl_xor_sync(0xffffffffu, u, 4);
+                u = (lane & 4) ? ((u & 0xf0f0f0f0u) | ((x >> 4) & 0x0f0f0f0fu)) : ((u & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4));
+                x = __shfl_xor_sync(0xffffffffu, u, 2);
+                u = (lane & 2) ? ((u & 0xccccccccu) | ((x >> 2) & 0x33333333u)) : ((u & 0x33333333u) | ((x & 0x33333333u) << 2));
+                x = __shfl_xor_sync(0xffffffffu, u, 1);
+                u = (lane & 1) ? ((u & 0xaaaaaaaau) | ((x >> 1) & 0x55555555u)) : ((u & 0x55555555u) | ((x & 0x55555555u) << 1));
+            }
+            const int mine = __popc(u);
+            int incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+            int pos = incl - mine;
+            const int qn = __shfl_sync(0xffffffffu, incl, 31);
+            // queue entry = (gray row << 8) | gray byte column; this lane's bit position is pixel j = lane >> 3, row i = lane & 7
+            const uint32_t e0 = ((uint32_t)(8 * warp + 3 + (lane & 7)) << 8) | (uint32_t)(4 * cbw + (lane >> 3));
+            while (u) {
+                const int l = __ffs(u) - 1;
+                u &= u - 1;
+                Q[pos++] = (uint16_t)(e0 + 4 * l);
+            }
+            __syncwarp();
+            const uint32_t lt = (1u << lane) - 1u;
+            for (int q0 = 0; q0 < qn; q0 += 32) {
+                bool corner_in = false;
+                uint32_t centry = 0;
+                if (q0 + lane < qn) {
+                    const uint32_t e = Q[q0 + lane];
+                    const int pr = e >> 8, pcg = e & 255;
+                    const int sc = fast_strength2(S.gray + pr * GP + pcg);
+                    if (sc > thr) {
+                        const int sr = pr - 3, scol = pcg - 4 * cbw;   // score-tile row / column (column 4 = image x0)
+                        S.score[sr * SP2 + scol] = (uint8_t)(sc - 1);
+                        corner_in = sr >= 1 && sr <= TH && scol >= 4 && scol < 4 + TW;
+                        centry = ((uint32_t)sr << 7) | (uint32_t)scol;
+                    }
+                }
+                const uint32_t mk = __ballot_sync(0xffffffffu, corner_in);
+                if (corner_in) Q[cn + __popc(mk & lt)] = (uint16_t)centry;   // cn + rank <= q0 + lane: never ahead of the reads
+                cn += __popc(mk);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ E. 3x3 NMS (strict >) over the corners + emit
+    if (P.keys) {
+        for (int c0 = 0; c0 < cn; c0 += 32) {
+            bool iskp = false;
+            uint32_t key = 0;
+            if (c0 + lane < cn) {
+                const uint32_t e = Q[c0 + lane];
+                const int sr = e >> 7, scol = e & 127;
+                const uint8_t* sp = S.score + sr * SP2 + scol;
+                const uint32_t v = sp[0];
+                const uint32_t m = max(max(max((uint32_t)sp[-SP2 - 1], (uint32_t)sp[-SP2]), max((uint32_t)sp[-SP2 + 1], (uint32_t)sp[-1])),
+                                       max(max((uint32_t)sp[1], (uint32_t)sp[SP2 - 1]), max((uint32_t)sp[SP2], (uint32_t)sp[SP2 + 1])));
+                iskp = v > m;
+                key = ((uint32_t)(y0 + sr - 1) << 20) | ((uint32_t)(x0 + scol - 4) << 8) | v;
+            }
+            const uint32_t mk = __ballot_sync(0xffffffffu, iskp);
+            if (mk) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.kpcount, __popc(mk));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (iskp) {
+                    const int kp = base + __popc(mk & ((1u << lane) - 1u));
+                    if (kp < KPCAP) kplist[kp] = key;
+                }
+            }
+        }
+        __syncthreads();
+        const int n = min(S.kpcount, KPCAP);
+        if (tid == 0) S.kpbase = n ? atomicAdd(P.counts + f, n) : 0;
+        __syncthreads();
+        const int base = S.kpbase;
+        uint32_t* out = P.keys + (size_t)f * P.cap;
+        for (int i = tid; i < n; i += NTHREADS)
+            if (base + i < P.cap) out[base + i] = kplist[i];
+    }
+}
+
 // ---- standalone RGBA -> gray (alva_k_gray) ---------------------------------------------------------
 __global__ void gray_kernel(const uint8_t* __restrict__ rgba, uint8_t* __restrict__ gray, size_t npix) {
     const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -741,6 +1020,7 @@ __global__ void __launch_bounds__(256) scharr_kernel(const ScharrLevels L) {
 
 // =================================================================================== host launchers
 int alva_g_frontend_antipodal = 0;   // alva_set_option("frontend_antipodal", 1): experimental pre-test variant (RGBA path only)
+int alva_g_frontend_variant = 2;     // alva_set_option("frontend_variant", 0 | 2): 0 = the round-1 kernel, 2 = frontend_tile_kernel_v2
 
 static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
                            uint8_t* l1, int thr, uint32_t* keys, int32_t* counts, int cap) {
@@ -770,7 +1050,16 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     P.use_tma = (tma_ok && !no_tma) ? 1 : 0;
     const int grid = P.tiles_x * P.tiles_y * nframes;
     const size_t smem = sizeof(SmemLayout) + 128;
-    if (rgba_mode && alva_g_frontend_antipodal) {
+    if (P.use_tma && alva_g_frontend_variant == 2 && !alva_g_frontend_antipodal) {
+        const size_t smem2 = sizeof(SmemLayout2) + 128;
+        if (rgba_mode) {
+            ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            frontend_tile_kernel_v2<true><<<grid, NTHREADS, smem2, ctx->stream>>>(tmap, P);
+        } else {
+            ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            frontend_tile_kernel_v2<false><<<grid, NTHREADS, smem2, ctx->stream>>>(tmap, P);
+        }
+    } else if (rgba_mode && alva_g_frontend_antipodal) {
         ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         frontend_tile_kernel<true, true><<<grid, NTHREADS, smem, ctx->stream>>>(tmap, P);
     } else if (rgba_mode) {
@@ -814,7 +1103,7 @@ static int check_dims(int w, int h, int nframes) {
     return 0;
 }
 
-extern "C" int alva_k_gray(alva_ctx* ctx, const uint8_t* rgba, uint8_t* gray, int w, int h, int nframes) {
+extern "C" int alva_k_gray(alva_ctx* ctx, const uint8_t* rgba, uint8_t* gray, int w, int h, int nframes) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !rgba || !gray || w < 1 || h < 1 || nframes < 1) { alva_set_error("alva_k_gray: bad argument"); return ALVA_E_INVALID; }
     const size_t npix = (size_t)w * h * nframes;
     const size_t nthr = (npix + 3) / 4;
@@ -840,7 +1129,7 @@ int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src
     return 0;
 }
 
-extern "C" int alva_k_scharr(alva_ctx* ctx, const uint8_t* gray, int16_t* deriv, int w, int h, int nframes) {
+extern "C" int alva_k_scharr(alva_ctx* ctx, const uint8_t* gray, int16_t* deriv, int w, int h, int nframes) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !deriv || w < 1 || h < 1 || nframes < 1 || ((uintptr_t)deriv & 3)) {
         alva_set_error("alva_k_scharr: bad argument");
         return ALVA_E_INVALID;
@@ -848,7 +1137,7 @@ extern "C" int alva_k_scharr(alva_ctx* ctx, const uint8_t* gray, int16_t* deriv,
     return alva_scharr_levels_launch(ctx, 1, &gray, &deriv, &w, &h, nframes);
 }
 
-extern "C" int alva_k_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) {
+extern "C" int alva_k_pyrdown(alva_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !src || !dst || w < 1 || h < 1 || nframes < 1) { alva_set_error("alva_k_pyrdown: bad argument"); return ALVA_E_INVALID; }
     return launch_pyrdown(ctx, src, dst, w, h, nframes);
 }
@@ -879,19 +1168,19 @@ static int fast_common(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w,
 }
 
 extern "C" int alva_k_fast9(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, int thr, uint32_t* keys,
-                            int32_t* counts, int cap, int sorted) {
+                            int32_t* counts, int cap, int sorted) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !keys) { alva_set_error("alva_k_fast9: bad argument"); return ALVA_E_INVALID; }
     return fast_common(ctx, false, gray, w, h, nframes, nullptr, nullptr, nullptr, nullptr, thr, keys, counts, cap, sorted);
 }
 
 extern "C" int alva_k_frontend(alva_ctx* ctx, const uint8_t* rgba, int w, int h, int nframes, uint8_t* l0, uint8_t* l1,
-                               uint8_t* l2, uint8_t* l3, int thr, uint32_t* keys, int32_t* counts, int cap, int sorted) {
+                               uint8_t* l2, uint8_t* l3, int thr, uint32_t* keys, int32_t* counts, int cap, int sorted) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !rgba) { alva_set_error("alva_k_frontend: bad argument"); return ALVA_E_INVALID; }
     return fast_common(ctx, true, rgba, w, h, nframes, l0, l1, l2, l3, thr, keys, counts, cap, sorted);
 }
 
 extern "C" int alva_k_retain_best(alva_ctx* ctx, const uint32_t* keys, const int32_t* counts, int cap, int nframes, int w,
-                                  int h, int n, int edge, uint32_t* out_keys, int32_t* out_counts, int out_cap) {
+                                  int h, int n, int edge, uint32_t* out_keys, int32_t* out_counts, int out_cap) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !keys || !counts || !out_keys || !out_counts || nframes < 1 || cap < 1 || out_cap < 1) {
         alva_set_error("alva_k_retain_best: bad argument");
         return ALVA_E_INVALID;
@@ -906,7 +1195,7 @@ extern "C" int alva_k_retain_best(alva_ctx* ctx, const uint32_t* keys, const int
 // Host-buffer front end: pinned/pageable host RGBA in, packed keys + counts out.  The copies are part of the call
 // (bench.py's e2e leg; also what a host without device pointers binds).
 extern "C" int alva_h_frontend(alva_ctx* ctx, const uint8_t* rgba_host, int w, int h, int nframes, int thr,
-                               uint32_t* keys_host, int32_t* counts_host, int cap) {
+                               uint32_t* keys_host, int32_t* counts_host, int cap) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !rgba_host || !keys_host || !counts_host) { alva_set_error("alva_h_frontend: bad argument"); return ALVA_E_INVALID; }
     if (int e = check_dims(w, h, nframes)) return e;
     const size_t in_bytes = (size_t)w * h * 4 * nframes;

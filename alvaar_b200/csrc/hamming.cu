@@ -177,7 +177,18 @@ static void knn_chunks(const alva_ctx* ctx, int nq, int nt, int QPW, int* nchunk
 
 int alva_g_knn_qpw = 4;   // alva_set_option("knn_qpw", 4 | 8)
 
+// hamming_mma.cu: the tensor-core formulation (large query sets)
+bool alva_knn2_mma_wanted(int nq, int nt);
+int alva_knn2_mma_launch(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out, const int32_t* counts,
+                         int nbatch, int qcap, int32_t* dbg_out);
+int alva_knn2_merge_launch(alva_ctx* ctx, const uint2* partial, int nq, int nchunks, int32_t* out, const int32_t* counts, int qcap) {
+    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 static int knn_launch(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out, const int32_t* counts, int qcap) {
+    if (alva_knn2_mma_wanted(nq, nt)) return alva_knn2_mma_launch(ctx, q, nq, t, nt, out, counts, counts ? nq / qcap : 0, qcap, nullptr);
     int nchunks, chunk_len;
     const int QPW = alva_g_knn_qpw == 4 ? 4 : 8;
     knn_chunks(ctx, nq, nt, QPW, &nchunks, &chunk_len);
@@ -191,12 +202,10 @@ static int knn_launch(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t,
         knn2_partial_kernel<4><<<grid, WPC * 32, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, partial, nchunks, chunk_len,
                                                                    counts, qcap, 1u << 22, 1u << 23, 1u << 24);
     ALVA_LAUNCH_CHECK(ctx);
-    knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(partial, nq, nchunks, out, counts, qcap);
-    ALVA_LAUNCH_CHECK(ctx);
-    return 0;
+    return alva_knn2_merge_launch(ctx, partial, nq, nchunks, out, counts, qcap);
 }
 
-extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) {
+extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !q || !t || !out || nq < 1 || nt < 1 || nt >= (1 << 22) || ((uintptr_t)q & 15) || ((uintptr_t)t & 15) ||
         ((uintptr_t)out & 15)) {
         alva_set_error("alva_k_hamming_knn2: bad argument (need 16-byte aligned buffers, 1 <= nt < 2^22)");
@@ -206,7 +215,7 @@ extern "C" int alva_k_hamming_knn2(alva_ctx* ctx, const uint8_t* q, int nq, cons
 }
 
 extern "C" int alva_k_hamming_knn2_batch(alva_ctx* ctx, const uint8_t* q, const int32_t* counts, int nbatch, int qcap,
-                                         const uint8_t* t, int nt, int32_t* out) {
+                                         const uint8_t* t, int nt, int32_t* out) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !q || !counts || !t || !out || nbatch < 1 || qcap < 1 || (qcap % QPW_MAX) != 0 || nt < 1 || nt >= (1 << 22) ||
         ((uintptr_t)q & 15) || ((uintptr_t)t & 15) || ((uintptr_t)out & 15)) {
         alva_set_error("alva_k_hamming_knn2_batch: bad argument (qcap must be a multiple of %d)", QPW_MAX);

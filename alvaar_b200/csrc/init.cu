@@ -218,7 +218,7 @@ static void make_rnd_table_init(uint32_t seed, int n, std::vector<int32_t>& out)
 
 extern "C" int alva_k_essential_5pt(alva_ctx* ctx, int nprob, int cap, const double* bv1, const double* bv2, const int32_t* counts,
                                     int max_iter, float err_px, int optimize, float fx, float fy, uint32_t seed, double* Rt_out,
-                                    uint8_t* outlier, double* info) {
+                                    uint8_t* outlier, double* info) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !bv1 || !bv2 || !Rt_out || !outlier || nprob < 1 || cap < 1 || max_iter < 1 || max_iter > 1024) {
         alva_set_error("alva_k_essential_5pt: bad argument");
         return ALVA_E_INVALID;
@@ -243,7 +243,7 @@ extern "C" int alva_k_essential_5pt(alva_ctx* ctx, int nprob, int cap, const dou
     return 0;
 }
 
-extern "C" int alva_k_triangulate(alva_ctx* ctx, const double* Tlr, const double* bvl, const double* bvr, int n, double* out) {
+extern "C" int alva_k_triangulate(alva_ctx* ctx, const double* Tlr, const double* bvl, const double* bvr, int n, double* out) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !Tlr || !bvl || !bvr || !out || n < 0) { alva_set_error("alva_k_triangulate: bad argument"); return ALVA_E_INVALID; }
     if (n == 0) return 0;
     triangulate_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(Tlr, bvl, bvr, n, out);

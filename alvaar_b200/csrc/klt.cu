@@ -320,7 +320,7 @@ int fill_params(KltParams& P, const uint8_t* const* prev_img, const int16_t* con
 extern "C" int alva_k_klt_lk(alva_ctx* ctx, const uint8_t* const* prev_img, const int16_t* const* prev_der,
                              const uint8_t* const* cur_img, int w, int h, int nframes, int pyr_levels, int levels, int win,
                              int max_count, double epsilon, int use_initial, const float* pts, float* next,
-                             const int32_t* npts_per_frame, int npts, uint8_t* status, float* err) {
+                             const int32_t* npts_per_frame, int npts, uint8_t* status, float* err) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !prev_img || !prev_der || !cur_img || !pts || !next || !status || npts < 1) { alva_set_error("alva_k_klt_lk: bad argument"); return ALVA_E_INVALID; }
     KltParams P{};
     if (int e = fill_params(P, prev_img, prev_der, cur_img, nullptr, w, h, nframes, pyr_levels, levels, win, max_count, epsilon, "alva_k_klt_lk")) return e;
@@ -335,7 +335,7 @@ extern "C" int alva_k_klt_lk(alva_ctx* ctx, const uint8_t* const* prev_img, cons
 extern "C" int alva_k_klt_fb(alva_ctx* ctx, const uint8_t* const* prev_img, const int16_t* const* prev_der,
                              const uint8_t* const* cur_img, const int16_t* const* cur_der, int w, int h, int nframes,
                              int pyr_levels, int levels, int win, float error_value, float max_fb_dist, const float* pts,
-                             float* priors, const int32_t* npts_per_frame, int npts, uint8_t* good) {
+                             float* priors, const int32_t* npts_per_frame, int npts, uint8_t* good) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !prev_img || !prev_der || !cur_img || !cur_der || !pts || !priors || !good || npts < 1) { alva_set_error("alva_k_klt_fb: bad argument"); return ALVA_E_INVALID; }
     KltParams P{};
     // FeatureTracker(30, 0.01): kltConvCriteria_ (src/slam/src/system.cpp:31 -> feature_tracker.hpp:14)

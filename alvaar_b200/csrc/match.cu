@@ -230,7 +230,7 @@ extern "C" int alva_k_match_to_map(alva_ctx* ctx, int w, int h, int cell, double
                                    const double* kf_Twc, int n_mp, const double* mp_wpt, const uint8_t* mp_is3d,
                                    const int32_t* obs_start, const int32_t* obs_kf, const float* obs_px, const int32_t* desc_start,
                                    const uint8_t* desc, int n_local, const int32_t* local_mp, float max_proj_err, float dist_ratio,
-                                   int32_t* kp_match, float* kp_dist, int32_t* n_match) {
+                                   int32_t* kp_match, float* kp_dist, int32_t* n_match) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !Twc_cur || !kp_mp || !kp_px || !kf_Twc || !mp_wpt || !mp_is3d || !obs_start || !obs_kf || !obs_px || !desc_start ||
         !desc || !local_mp || !kp_match || !n_match || n_kp < 1 || n_mp < 1 || n_local < 1 || cell < 1) {
         alva_set_error("alva_k_match_to_map: bad argument");

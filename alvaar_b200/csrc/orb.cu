@@ -401,7 +401,7 @@ __global__ void keys_to_pts_kernel(const uint32_t* __restrict__ keys, const int3
 
 }  // namespace
 
-extern "C" int alva_k_orb_blur(alva_ctx* ctx, const uint8_t* gray, uint8_t* blurred, int w, int h, int nframes, int flags) {
+extern "C" int alva_k_orb_blur(alva_ctx* ctx, const uint8_t* gray, uint8_t* blurred, int w, int h, int nframes, int flags) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !blurred || w < 8 || h < 8 || nframes < 1 || gray == blurred) {
         alva_set_error("alva_k_orb_blur: bad argument (in-place not supported)");
         return ALVA_E_INVALID;
@@ -424,7 +424,7 @@ extern "C" int alva_k_orb_blur(alva_ctx* ctx, const uint8_t* gray, uint8_t* blur
 
 extern "C" int alva_k_orb_describe(alva_ctx* ctx, const uint8_t* gray, const uint8_t* blurred, int w, int h, int nframes,
                                    const float* pts, const int32_t* npts_per_frame, int npts, int flags, uint8_t* desc,
-                                   uint8_t* kept, float* angles_out) {
+                                   uint8_t* kept, float* angles_out) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !blurred || !pts || !desc || !kept || w < 1 || h < 1 || nframes < 1 || npts < 1 ||
         ((flags & ALVA_ORB_IC_ANGLE) && !gray)) {
         alva_set_error("alva_k_orb_describe: bad argument");
@@ -457,7 +457,7 @@ int alva_harris_launch(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nfr
 }
 
 extern "C" int alva_k_harris(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, const float* pts,
-                             const int32_t* npts_per_frame, int npts, float* resp) {
+                             const int32_t* npts_per_frame, int npts, float* resp) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !pts || !resp || w < 9 || h < 9 || nframes < 1 || npts < 1) {
         alva_set_error("alva_k_harris: bad argument");
         return ALVA_E_INVALID;
@@ -469,7 +469,7 @@ extern "C" int alva_k_harris(alva_ctx* ctx, const uint8_t* gray, int w, int h, i
 // retainBest(2n) by FAST score -> Harris -> retainBest(n) by Harris -> IC angle -> blur -> steered rBRIEF.
 // Composition of this library's own stage kernels; intermediate lists live in a context-owned workspace.
 extern "C" int alva_k_orb_detect(alva_ctx* ctx, const uint8_t* gray, int w, int h, int nframes, int nfeatures, int fast_thr,
-                                 int flags, float* kp_out, uint8_t* desc, int32_t* counts, int out_cap) {
+                                 int flags, float* kp_out, uint8_t* desc, int32_t* counts, int out_cap) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !gray || !kp_out || !desc || !counts || w < 64 || h < 64 || nframes < 1 || nfeatures < 1 || out_cap < 1) {
         alva_set_error("alva_k_orb_detect: bad argument (need w, h >= 64)");
         return ALVA_E_INVALID;

@@ -96,6 +96,7 @@ static int palloc(alva_pipeline* p, void** ptr, size_t bytes) {
 
 extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (!p) return;
+    AlvaDeviceGuard guard__(p->ctx);
     cudaStreamSynchronize(p->ctx->stream);
     for (void* a : p->allocs) cudaFree(a);
     if (p->sel_ctx) { alva_ctx_destroy(p->sel_ctx); p->sel_ctx = nullptr; }
@@ -123,7 +124,7 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     delete p;
 }
 
-extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipeline_config* cfg) {
+extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipeline_config* cfg) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !cfg || cfg->batch < 1 || cfg->w < 64 || cfg->h < 64 || cfg->w > ALVA_MAX_DIM || cfg->h > ALVA_MAX_DIM ||
         cfg->nfeatures < 1 || cfg->map_size < 0 || cfg->kf_interval < 0) {
         alva_set_error("alva_pipeline_create: bad configuration");
@@ -190,7 +191,7 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
     return p;
 }
 
-extern "C" int alva_pipeline_set_map(alva_pipeline* p, const uint8_t* desc_host, int n) {
+extern "C" int alva_pipeline_set_map(alva_pipeline* p, const uint8_t* desc_host, int n) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !desc_host || n != p->cfg.map_size) { alva_set_error("alva_pipeline_set_map: need exactly map_size descriptors"); return ALVA_E_INVALID; }
     ALVA_CUDA(cudaMemcpyAsync(p->map, desc_host, (size_t)n * 32, cudaMemcpyHostToDevice, p->ctx->stream));
     ALVA_CUDA(cudaStreamSynchronize(p->ctx->stream));
@@ -201,7 +202,7 @@ extern "C" int alva_pipeline_set_map(alva_pipeline* p, const uint8_t* desc_host,
 // One BA problem (host arrays, layout of alva_k_ba_solve) replicated into slot `slot` of the per-step BA batch.
 extern "C" int alva_pipeline_set_ba(alva_pipeline* p, int slot, const double* calib, const double* poses, const uint8_t* pose_const,
                                     const double* invd, const int32_t* anch_kf, const double* anch_uv, const int32_t* obs_kf,
-                                    const int32_t* obs_lm, const double* obs_uv) {
+                                    const int32_t* obs_lm, const double* obs_uv) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || slot < 0 || slot >= p->nprob) { alva_set_error("alva_pipeline_set_ba: bad slot"); return ALVA_E_INVALID; }
     const size_t nkf = p->cfg.ba_nkf, nlm = p->cfg.ba_nlm, nobs = p->cfg.ba_nobs, s = slot;
     cudaStream_t st = p->ctx->stream;
@@ -219,7 +220,7 @@ extern "C" int alva_pipeline_set_ba(alva_pipeline* p, int slot, const double* ca
     return 0;
 }
 
-extern "C" int alva_pipeline_profile(alva_pipeline* p, int enable) {
+extern "C" int alva_pipeline_profile(alva_pipeline* p, int enable) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p) return ALVA_E_INVALID;
     p->profile = enable != 0;
     p->step_index = 0;
@@ -228,7 +229,7 @@ extern "C" int alva_pipeline_profile(alva_pipeline* p, int enable) {
 
 // Durations (ms) of the fused front-end launch (gray + pyramid L1 + FAST) of the last min(n, steps, 64) steps since
 // profiling was enabled, measured with CUDA events on the launch stream.  Returns how many were written.
-extern "C" int alva_pipeline_frontend_ms(alva_pipeline* p, float* ms, int n) {
+extern "C" int alva_pipeline_frontend_ms(alva_pipeline* p, float* ms, int n) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !ms || !p->profile) { alva_set_error("profiling not enabled"); return ALVA_E_STATE; }
     ALVA_CUDA(cudaStreamSynchronize(p->ctx->stream));
     const long long have = p->step_index < alva_pipeline::NEV ? p->step_index : alva_pipeline::NEV;
@@ -375,7 +376,7 @@ static int pipeline_ready(alva_pipeline* p) {
     return 0;
 }
 
-extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) {
+extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
     if (int e = pipeline_ready(p)) return e;
     if (int e = pipeline_frames(p, rgba_dev, 0, p->cfg.batch, true, true)) { pipeline_ba_join(p); return e; }
@@ -388,7 +389,7 @@ extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev)
 // back.  alva_pipeline_wait blocks until the oldest outstanding submission (at most two) has delivered its results.
 // alva_pipeline_step_host = submit + wait.
 extern "C" int alva_pipeline_submit_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
-                                         double* ba_poses_host, double* ba_summary_host) {
+                                         double* ba_poses_host, double* ba_summary_host) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !rgba_host) { alva_set_error("alva_pipeline_submit_host: bad argument"); return ALVA_E_INVALID; }
     if (int e = pipeline_ready(p)) return e;
     if (p->outstanding >= alva_pipeline::NSLOT) { alva_set_error("alva_pipeline_submit_host: two submissions outstanding, call alva_pipeline_wait"); return ALVA_E_STATE; }
@@ -438,7 +439,7 @@ extern "C" int alva_pipeline_submit_host(alva_pipeline* p, const uint8_t* rgba_h
     return 0;
 }
 
-extern "C" int alva_pipeline_wait(alva_pipeline* p) {
+extern "C" int alva_pipeline_wait(alva_pipeline* p) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p) { alva_set_error("alva_pipeline_wait: bad argument"); return ALVA_E_INVALID; }
     if (p->outstanding == 0) return 0;
     ALVA_CUDA(cudaEventSynchronize(p->done_ev[p->oldest_slot]));
@@ -448,14 +449,14 @@ extern "C" int alva_pipeline_wait(alva_pipeline* p) {
 }
 
 extern "C" int alva_pipeline_step_host(alva_pipeline* p, const uint8_t* rgba_host, int32_t* nfeat_host, int32_t* matches_host,
-                                       double* ba_poses_host, double* ba_summary_host) {
+                                       double* ba_poses_host, double* ba_summary_host) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p) { alva_set_error("alva_pipeline_step_host: bad argument"); return ALVA_E_INVALID; }
     while (p->outstanding) if (int e = alva_pipeline_wait(p)) return e;
     if (int e = alva_pipeline_submit_host(p, rgba_host, nfeat_host, matches_host, ba_poses_host, ba_summary_host)) return e;
     return alva_pipeline_wait(p);
 }
 
-extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: fcap, kcap, nprob, map_size */) {
+extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: fcap, kcap, nprob, map_size */) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !out) return ALVA_E_INVALID;
     out[0] = p->fcap; out[1] = p->kcap; out[2] = p->nprob; out[3] = p->cfg.map_size;
     return 0;
@@ -463,7 +464,7 @@ extern "C" int alva_pipeline_info(const alva_pipeline* p, int32_t* out /* [4]: f
 
 // device pointer of an intermediate (tests): 0 l0, 1 l1, 2 l2, 3 l3, 4 blur, 5 keys, 6 counts, 7 sel, 8 selcounts, 9 pts,
 // 10 angles, 11 desc, 12 kept, 13 matches, 14 ba_poses, 15 ba_invd, 16 ba_summary
-extern "C" void* alva_pipeline_buffer(alva_pipeline* p, int which) {
+extern "C" void* alva_pipeline_buffer(alva_pipeline* p, int which) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p) return nullptr;
     void* t[] = {p->l0, p->l1, p->l2, p->l3, p->blur, p->keys, p->counts, p->sel, p->selcounts, p->pts, p->angles, p->desc,
                  p->kept, p->matches, p->ba_poses, p->ba_invd, p->ba_summary, p->d0, p->d1, p->d2, p->d3};

@@ -752,7 +752,7 @@ static void make_rnd_table(uint32_t seed, int n, std::vector<int32_t>& out) {
 
 extern "C" int alva_k_p3p_lmeds(alva_ctx* ctx, int nprob, int cap, const double* bvs, const double* wpts, const int32_t* counts,
                                 int max_iter, float err_px, float fx, float fy, uint32_t seed, double* Twc_out,
-                                uint8_t* outlier, double* info) {
+                                uint8_t* outlier, double* info) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !bvs || !wpts || !Twc_out || !outlier || nprob < 1 || cap < 1 || max_iter < 1 || max_iter > 1024) {
         alva_set_error("alva_k_p3p_lmeds: bad argument");
         return ALVA_E_INVALID;
@@ -790,7 +790,7 @@ extern "C" int alva_k_p3p_lmeds(alva_ctx* ctx, int nprob, int cap, const double*
 
 extern "C" int alva_k_pnp(alva_ctx* ctx, int nprob, int cap, const double* K, const double* uv, const double* X,
                           const int32_t* counts, double* poses, double huber_delta, double chi2_thr, int max_iter,
-                          int use_robust, int apply_l2, uint8_t* outlier, double* summary) {
+                          int use_robust, int apply_l2, uint8_t* outlier, double* summary) { AlvaDeviceGuard guard__(ctx);
     if (!ctx || !K || !uv || !X || !poses || !outlier || !summary || nprob < 1 || cap < 1 || max_iter < 0) {
         alva_set_error("alva_k_pnp: bad argument");
         return ALVA_E_INVALID;

@@ -222,7 +222,7 @@ struct CudaBackend {
         memcpy(head, K4, 32); memcpy(head + 4, pose7, 56);
         SYS_CUDA(cudaMemcpyAsync(S, head, sizeof head, cudaMemcpyHostToDevice, st));
         const float chi2 = 5.9915f;   // State::robustCostThreshold_; ceresPnP takes it as float and uses sqrt(chi2) as the Huber width
-        if (int e = alva_k_pnp(ctx, 1, n, S, U, Xd, nullptr, S + 4, sqrt((double)chi2), (double)chi2, 5, 1, 1, flag_dev, S + 16)) return e;
+        if (int e = alva_k_pnp(ctx, 1, n, S, U, Xd, nullptr, S + 4, (double)sqrtf(chi2), (double)chi2, 5, 1, 1, flag_dev, S + 16)) return e;
         double host[28];
         SYS_CUDA(cudaMemcpyAsync(host, S, sizeof host, cudaMemcpyDeviceToHost, st));
         SYS_CUDA(cudaMemcpyAsync(outl, flag_dev, n, cudaMemcpyDeviceToHost, st));
@@ -501,51 +501,55 @@ extern "C" alva_system* alva_system_create(int device) {
     s->sys.device_ = device;
     return s;
 }
-extern "C" void alva_system_destroy(alva_system* s) { delete s; }
+extern "C" void alva_system_destroy(alva_system* s) {
+    if (!s) return;
+    AlvaDeviceGuard guard__(s->sys.device_);
+    delete s;
+}
 extern "C" int alva_system_configure(alva_system* s, int w, int h, double fx, double fy, double cx, double cy, double k1,
-                                     double k2, double p1, double p2) {
+                                     double k2, double p1, double p2) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || w < 64 || h < 64) { alva_set_error("alva_system_configure: bad argument"); return ALVA_E_INVALID; }
     return s->sys.configure(w, h, fx, fy, cx, cy, k1, k2, p1, p2);
 }
-extern "C" int alva_system_reset(alva_system* s) { if (!s) return ALVA_E_INVALID; s->sys.reset(); return 0; }
-extern "C" int alva_system_find_camera_pose(alva_system* s, const uint8_t* rgba, float* pose16) {
+extern "C" int alva_system_reset(alva_system* s) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); if (!s) return ALVA_E_INVALID; s->sys.reset(); return 0; }
+extern "C" int alva_system_find_camera_pose(alva_system* s, const uint8_t* rgba, float* pose16) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !rgba || !pose16) { alva_set_error("alva_system_find_camera_pose: bad argument"); return ALVA_E_INVALID; }
     return s->sys.findCameraPose(rgba, pose16);
 }
-extern "C" int alva_system_find_camera_pose_ts(alva_system* s, const uint8_t* rgba, double t_ms, float* pose16) {
+extern "C" int alva_system_find_camera_pose_ts(alva_system* s, const uint8_t* rgba, double t_ms, float* pose16) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !rgba || !pose16) { alva_set_error("alva_system_find_camera_pose_ts: bad argument"); return ALVA_E_INVALID; }
     return s->sys.findCameraPose(rgba, t_ms, pose16);
 }
-extern "C" int alva_system_find_camera_pose_imu(alva_system* s, const uint8_t* rgba, const double* imu, float* pose16) {
+extern "C" int alva_system_find_camera_pose_imu(alva_system* s, const uint8_t* rgba, const double* imu, float* pose16) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !rgba || !imu || !pose16) { alva_set_error("alva_system_find_camera_pose_imu: bad argument"); return ALVA_E_INVALID; }
     return s->sys.findCameraPoseWithIMU(rgba, imu, pose16);
 }
-extern "C" int alva_system_find_plane(alva_system* s, float* out16, int iterations) {
+extern "C" int alva_system_find_plane(alva_system* s, float* out16, int iterations) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !out16) return ALVA_E_INVALID;
     return s->sys.findPlane(out16, iterations);
 }
-extern "C" int alva_system_get_frame_points(alva_system* s, int32_t* xy, int cap_pairs) {
+extern "C" int alva_system_get_frame_points(alva_system* s, int32_t* xy, int cap_pairs) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !xy || cap_pairs < 0) return ALVA_E_INVALID;
     return s->sys.getFramePoints(xy, cap_pairs);
 }
-extern "C" int alva_system_num_matched(alva_system* s) { return s ? s->sys.numMatched() : ALVA_E_INVALID; }
-extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap) {
+extern "C" int alva_system_num_matched(alva_system* s) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return s ? s->sys.numMatched() : ALVA_E_INVALID; }
+extern "C" int alva_system_get_tracks(alva_system* s, int32_t* ids, float* px, uint8_t* is3d, double* wpt, int cap) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !ids || !px || cap < 0) return ALVA_E_INVALID;
     return s->sys.getTracks(ids, px, is3d, wpt, cap);
 }
-extern "C" int alva_system_get_descriptors(alva_system* s, uint8_t* desc, uint8_t* has, int cap) {
+extern "C" int alva_system_get_descriptors(alva_system* s, uint8_t* desc, uint8_t* has, int cap) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !desc || !has || cap < 0) return ALVA_E_INVALID;
     return s->sys.getDescriptors(desc, has, cap);
 }
-extern "C" int alva_system_debug_set_initialisation(alva_system* s, const double* Rt12, const uint8_t* outlier, int n) {
+extern "C" int alva_system_debug_set_initialisation(alva_system* s, const double* Rt12, const uint8_t* outlier, int n) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !Rt12 || !outlier || n < 8) return ALVA_E_INVALID;
     s->sys.debugSetInitialisation(Rt12, outlier, n);
     return 0;
 }
-extern "C" int alva_system_pin_buffer(alva_system* s, void* host_ptr, size_t bytes) {
+extern "C" int alva_system_pin_buffer(alva_system* s, void* host_ptr, size_t bytes) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1);
     if (!s || !host_ptr || !bytes) return ALVA_E_INVALID;
     return s->sys.pinBuffer(host_ptr, bytes);
 }
-extern "C" int alva_system_unpin_buffer(alva_system* s, void* host_ptr) { return (s && host_ptr) ? s->sys.unpinBuffer(host_ptr) : ALVA_E_INVALID; }
-extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
-extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }
+extern "C" int alva_system_unpin_buffer(alva_system* s, void* host_ptr) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && host_ptr) ? s->sys.unpinBuffer(host_ptr) : ALVA_E_INVALID; }
+extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
+extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }

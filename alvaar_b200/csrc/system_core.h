@@ -389,8 +389,13 @@ struct MotionModel {   // visual_frontend.hpp:17-56
         if (prevTime < 0.) { prevTime = time; prevTwc = Twc; return; }
         const double dt = time - prevTime;
         prevTime = time;
-        (prevTwc.inverse() * Twc).log(logRel);
-        for (int i = 0; i < 6; i++) logRel[i] /= dt;
+        // dt == 0 (two frames inside one millisecond of the wall clock: a tracked frame takes well under 1 ms here) would turn the
+        // reference's division (visual_frontend.hpp:42-53) into inf / NaN velocities that survive until the next P3P success:
+        // keep the previous velocity instead.  dt > 0 is the reference's arithmetic unchanged.
+        if (dt > 0.) {
+            (prevTwc.inverse() * Twc).log(logRel);
+            for (int i = 0; i < 6; i++) logRel[i] /= dt;
+        }
         prevTwc = Twc;
     }
     void reset() { prevTime = -1.; for (int i = 0; i < 6; i++) logRel[i] = 0; }

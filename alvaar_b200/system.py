@@ -102,8 +102,20 @@ class System:
         return dict(zip(("frame", "keyframe", "keypoints", "keypoints_3d", "initialised", "keyframes", "occupied_cells", "map_point_ids"), o.tolist()))
 
     def pin(self, array):
-        """page-lock a frame buffer that is reused from call to call (alva_system_pin_buffer)"""
-        return self.L.alva_system_pin_buffer(self.h, array.ctypes.data_as(_vp), array.nbytes) == 0
+        """page-lock a frame buffer that is reused from call to call (alva_system_pin_buffer).  The array is kept alive
+        until unpin() / close(): a garbage-collected buffer would stay registered with the driver."""
+        ok = self.L.alva_system_pin_buffer(self.h, array.ctypes.data_as(_vp), array.nbytes) == 0
+        if ok:
+            if not hasattr(self, "_pinned"):
+                self._pinned = {}
+            self._pinned[array.ctypes.data] = array
+        return ok
+
+    def unpin(self, array):
+        """undo pin() (alva_system_unpin_buffer)"""
+        ok = self.L.alva_system_unpin_buffer(self.h, array.ctypes.data_as(_vp)) == 0
+        getattr(self, "_pinned", {}).pop(array.ctypes.data, None)
+        return ok
 
     def reset(self):
         self.L.alva_system_reset(self.h)

@@ -284,8 +284,15 @@ int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
  * "pipeline_ba_overlap" = 0: alva_pipeline runs the local BA after the per-frame stages instead of beside them on its own
  * stream (default 1; results are identical, only the schedule changes).
  * "knn_qpw" = 4 | 8: queries a warp of the Hamming matcher keeps in registers (8: 128 registers / 16 warps per SM;
- * 4: 80 registers / 24 warps per SM).  Results are identical. */
+ * 4: 80 registers / 24 warps per SM).  Results are identical.
+ * "knn_mma" = 0 | 1 | 2: the tensor-core formulation of the Hamming matcher (hamming_mma.cu: descriptors expanded to +-1
+ * int8, tcgen05.mma.kind::i8, dot = 256 - 2 * distance): 0 never, 1 for large query sets (default), 2 always.  Results
+ * are identical.  "knn_mma_mode" = 0 | 1 | 2: shared-memory operand layout of that kernel (0 no swizzle, 1 128-byte
+ * swizzle, 2 debugging variant). */
 int alva_set_option(const char* name, int value);
+/* Debugging aid: the tensor-core matcher unconditionally on q [nq][32] x t [nt][32] (device pointers, 16-byte aligned);
+ * dbg_dev (optional, 16384 int32 of device memory) receives the raw dot products of the first 128 x 128 tile. */
+int alva_debug_knn2_mma(alva_ctx*, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* out, int32_t* dbg_dev);
 
 /* Residual / Jacobian build alone (DirectSE3::ReprojectionErrorKSE3AnchInvDepth::Evaluate,
  * src/slam/src/ceres_parametrization.cpp:157-269, + Huber corrector): res [nobs][2], Ja/Jp [nobs][2][6] (local

@@ -50,7 +50,8 @@ def golden(name):
 @pytest.fixture(scope="session")
 def gpu_ctx():
     import torch
-    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    if not torch.cuda.is_available():   # a plain `pytest tests` on a machine without a GPU: skip, do not error
+        pytest.skip("gpu tests need a CUDA device")
     import alvaar_b200
     ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)
     yield ctx

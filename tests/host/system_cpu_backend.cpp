@@ -98,7 +98,7 @@ struct CpuBackend {
     int pnp(const double* uv, const double* X, int n, const double* K4, double* pose7, uint8_t* outl) {
         double summary[10];
         const float chi2 = 5.9915f;
-        return orc_pnp(K4, uv, X, n, pose7, std::sqrt((double)chi2), (double)chi2, 5, 1, 1, outl, summary);
+        return orc_pnp(K4, uv, X, n, pose7, (double)std::sqrt(chi2), (double)chi2, 5, 1, 1, outl, summary);
     }
     int triangulate(const double* T7, const double* bl, const double* br, int n, double* out) { orc_triangulate(T7, bl, br, n, out); return 0; }
     bool enable_ba = true, enable_match = true;

@@ -148,6 +148,73 @@ def test_knn2_self_match_property(gpu_ctx):
     assert (o[:, 0] == np.arange(20000)).all() and (o[:, 1] == 0).all() and (o[:, 3] > 0).all()
 
 
+@pytest.fixture
+def knn_mma(gpu_ctx):
+    """force the tensor-core formulation (hamming_mma.cu) for every size; restored to automatic afterwards"""
+    assert gpu_ctx.L.alva_set_option(b"knn_mma", 2) == 0
+    yield gpu_ctx
+    gpu_ctx.L.alva_set_option(b"knn_mma", 1)
+    gpu_ctx.L.alva_set_option(b"knn_mma_mode", 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("nq,nt", [(1000, 10000), (1000, 1000), (7, 1), (1, 2), (33, 1025), (1000, 20000), (257, 129), (4100, 300)])
+def test_knn2_mma_vs_oracle(knn_mma, oracle, nq, nt, mode):
+    """tcgen05 int8 formulation (dot = 256 - 2 * distance): bit-identical 2-NN lists incl. the tie rule, both operand layouts"""
+    assert knn_mma.L.alva_set_option(b"knn_mma_mode", mode) == 0
+    q, t = synth.make_descriptors(nq, nt, seed=nq + nt, planted=0.3 if nt >= nq else 0.0)
+    if nt > 100:
+        t[nt // 2:nt // 2 + 20] = t[:20]
+    want = np.zeros((nq, 4), np.int32)
+    oracle.orc_knn2(P(q), nq, P(t), nt, P(want))
+    out = torch.full((nq, 4), -7, dtype=torch.int32, device=DEV)
+    knn_mma.hamming_knn2(dev(q), nq, dev(t), nt, out)
+    assert (out.cpu().numpy() == want).all()
+
+
+def test_knn2_mma_golden(knn_mma):
+    g = golden("knn")
+    out = torch.zeros((len(g["q"]), 4), dtype=torch.int32, device=DEV)
+    knn_mma.hamming_knn2(dev(g["q"]), len(g["q"]), dev(g["t"]), len(g["t"]), out)
+    assert (out.cpu().numpy() == g["out"]).all()
+
+
+def test_knn2_mma_ragged_batch(knn_mma, oracle):
+    """[nbatch][qcap] query slots with per-batch live counts (incl. an empty and a full batch): live slots equal the oracle's
+    lists, dead slots come back as -1 -- the compaction of the live rows must not leak between batches."""
+    nb, qcap, nt = 9, 256, 3000
+    counts = np.array([256, 0, 1, 255, 17, 128, 129, 200, 64], np.int32)
+    q, t = synth.make_descriptors(nb * qcap, nt, seed=11, planted=0.3)
+    out = torch.full((nb * qcap, 4), -7, dtype=torch.int32, device=DEV)
+    knn_mma.hamming_knn2_batch(dev(q), torch.from_numpy(counts).to(DEV), nb, qcap, dev(t), nt, out)
+    got = out.cpu().numpy().reshape(nb, qcap, 4)
+    for b in range(nb):
+        c = int(counts[b])
+        if c:
+            want = np.zeros((c, 4), np.int32)
+            qb = np.ascontiguousarray(q[b * qcap:b * qcap + c])
+            oracle.orc_knn2(P(qb), c, P(t), nt, P(want))
+            assert (got[b, :c] == want).all(), b
+        assert (got[b, c:] == -1).all(), b
+
+
+def test_knn2_mma_equals_lop3_on_bench_shape(gpu_ctx):
+    """the bench's matcher problem (64 x 1536 slots, ~1100 live, 10 000-descriptor map): automatic dispatch (tensor cores)
+    against the LOP3 / POPC kernel"""
+    nb, qcap, nt = 64, 1536, 10000
+    rng = np.random.default_rng(3)
+    q, t = synth.make_descriptors(nb * qcap, nt, seed=21, planted=0.3)
+    counts = torch.from_numpy(rng.integers(900, 1300, nb).astype(np.int32)).to(DEV)
+    outs = []
+    for opt in (0, 1):
+        assert gpu_ctx.L.alva_set_option(b"knn_mma", opt) == 0
+        out = torch.full((nb * qcap, 4), -7, dtype=torch.int32, device=DEV)
+        gpu_ctx.hamming_knn2_batch(dev(q), counts, nb, qcap, dev(t), nt, out)
+        outs.append(out.cpu().numpy())
+    gpu_ctx.L.alva_set_option(b"knn_mma", 1)
+    assert (outs[0] == outs[1]).all()
+
+
 @pytest.mark.parametrize("w,h,n", [(640, 480, 700), (130, 100, 40)])
 def test_harris_vs_oracle(gpu_ctx, oracle, w, h, n):
     """HarrisResponses: integer block sums + float formula in the reference's order -> bit-identical floats."""
