@@ -503,19 +503,28 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
 //     the 16 ring loads of the scoring phase almost bank-conflict free;
 //   * the scoring loop compacts the true corners of the tile interior in place (queue prefix), so the NMS / emit phase walks
 //     ~4 % of the pixels with full lanes instead of re-walking every candidate; the score tile has a 33-word pitch.
-constexpr int SP2 = 132;
-constexpr int SPW2 = SP2 / 4;
+//   * 120 x 60 tiles (720 and 1080 are multiples of 60: no ragged bottom row) and the score tile folded into the idle RGBA
+//     staging buffer: 44.8 KB of shared memory per CTA instead of 54.4 -> 5 CTAs per SM (40 warps) instead of 4.
+constexpr int TH2 = 60, BH2 = TH2 + 8;    // tile interior rows / loaded box rows
+constexpr int SR2 = TH2 + 2;              // score rows: image y0-1 .. y0+TH2
+constexpr int SP2 = 132;                  // score pitch: 33 words -> rows rotate through the banks
+constexpr int KPCAP2 = TW * TH2 / 4;      // NMS leaves at most one keypoint per 2x2
 struct __align__(128) SmemLayout2 {
-    uint8_t rgba[BW * BH * 4];     // TMA destination (RGBA mode); later the per-warp queues + the tile's keypoint list
-    uint8_t gray[GP * BH];         // TMA destination (gray mode)
-    uint8_t score[SP2 * SR];
+    // TMA destination (RGBA mode).  After the gray pass: per-warp queues (NWARPS * QCAP u16), the tile's keypoint list
+    // (KPCAP2 words) and the score tile (SP2 * SR2 bytes)
+    uint8_t rgba[BW * BH2 * 4];
+    uint8_t gray[GP * BH2];        // TMA destination (gray mode)
     uint64_t bar;
     int kpcount;
     int kpbase;
 };
+constexpr int V2_KPLIST_OFF = NWARPS * QCAP * 2;
+constexpr int V2_SCORE_OFF = V2_KPLIST_OFF + KPCAP2 * 4;
+static_assert(V2_SCORE_OFF % 4 == 0 && V2_SCORE_OFF + SP2 * SR2 <= BW * BH2 * 4, "queues + keypoint list + score tile must fit the staging buffer");
+static_assert(NWARPS * 8 >= SR2, "8 score rows per warp");
 
 template <bool RGBA>
-__global__ void __launch_bounds__(NTHREADS, 4)
+__global__ void __launch_bounds__(NTHREADS, 5)
 frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const FrontendParams P) {
     extern __shared__ uint8_t smem_raw[];
     SmemLayout2& S = *reinterpret_cast<SmemLayout2*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
@@ -526,7 +535,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     const int f = t / tiles_per_frame;
     t -= f * tiles_per_frame;
     const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
-    const int x0 = tx * TW, y0 = ty * TH;
+    const int x0 = tx * TW, y0 = ty * TH2;
     const int w = P.w, h = P.h;
     const int sh = RGBA ? 0 : ((x0 - 8) & 15);
     const int cbw = 1 + (sh >> 2);   // word index (within a gray smem row) of image column x0-4
@@ -540,18 +549,14 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     __syncthreads();
     if (tid == 0) {
         if (RGBA) {
-            mbar_arrive_expect_tx(&S.bar, BW * BH * 4);
+            mbar_arrive_expect_tx(&S.bar, BW * BH2 * 4);
             tma_load_3d(S.rgba, &tmap, &S.bar, x0 - 4, y0 - 4, f);
         } else {
-            mbar_arrive_expect_tx(&S.bar, GP * BH);
+            mbar_arrive_expect_tx(&S.bar, GP * BH2);
             tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8 - sh, y0 - 4, f);
         }
     }
-    {
-        uint32_t* sc = reinterpret_cast<uint32_t*>(S.score);
-        for (int i = tid; i < SP2 * SR / 4; i += NTHREADS) sc[i] = 0;
-        if (tid == 0) S.kpcount = 0;
-    }
+    if (tid == 0) S.kpcount = 0;
     mbar_wait(&S.bar, 0);
 
     // ------------------------------------------------------------------ B. gray (w % 4 == 0 guaranteed by the TMA path)
@@ -562,20 +567,20 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
         const int g = lane;
         const int x = x0 + 4 * (g - 1);
         const bool colstore = l0 && g >= 1 && g <= 30 && x < w;
-        constexpr int ROUNDS = (BH + NWARPS - 1) / NWARPS;
+        constexpr int ROUNDS = (BH2 + NWARPS - 1) / NWARPS;
         const uint4* sp = src4 + warp * 32 + g;
         uint32_t* gp = gw + warp * GPW + 1 + g;
         uint4 px[ROUNDS];
 #pragma unroll
         for (int it = 0; it < ROUNDS; it++)
-            if (it < ROUNDS - 1 || warp + NWARPS * it < BH) px[it] = sp[it * NWARPS * 32];
+            if (it < ROUNDS - 1 || warp + NWARPS * it < BH2) px[it] = sp[it * NWARPS * 32];
         uint8_t* d = l0 ? l0 + (ptrdiff_t)(y0 + warp - 4) * w + x : nullptr;
         const size_t dstep = (size_t)NWARPS * w;
-        const int by_end = min(4 + TH, h - y0 + 4);   // box rows [4, by_end) are image rows of this tile
+        const int by_end = min(4 + TH2, h - y0 + 4);   // box rows [4, by_end) are image rows of this tile
 #pragma unroll
         for (int it = 0; it < ROUNDS; it++) {
             const int by = warp + NWARPS * it;
-            if (it < ROUNDS - 1 || by < BH) {
+            if (it < ROUNDS - 1 || by < BH2) {
                 const uint32_t v = gray4(px[it]);
                 gp[it * NWARPS * GPW] = v;
                 if (colstore && (it > 0 || by >= 4) && by < by_end) *reinterpret_cast<uint32_t*>(d + it * dstep) = v;
@@ -584,10 +589,18 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     }
     __syncthreads();
 
-    const bool edge_l = (x0 == 0), edge_r = (x0 + TW >= w), edge_t = (y0 == 0), edge_b = (y0 + TH >= h);
+    // the staging buffer is idle from here on: every warp clears the 8 score rows it will write in phase D
+    uint8_t* const score = S.rgba + V2_SCORE_OFF;
+    {
+        uint32_t* sc = reinterpret_cast<uint32_t*>(score) + warp * 8 * (SP2 / 4);
+        const int nwords = (min(SR2, 8 * warp + 8) - 8 * warp) * (SP2 / 4);
+        for (int i = lane; i < nwords; i += 32) sc[i] = 0;
+    }
+
+    const bool edge_l = (x0 == 0), edge_r = (x0 + TW >= w), edge_t = (y0 == 0), edge_b = (y0 + TH2 >= h);
     if (P.l1 && (edge_l || edge_r || edge_t || edge_b)) {
         if (edge_l || edge_r) {
-            for (int r = tid; r < BH; r += NTHREADS) {
+            for (int r = tid; r < BH2; r += NTHREADS) {
                 uint8_t* row = S.gray + r * GP;
                 if (edge_l) { row[7 + sh] = row[9 + sh]; row[6 + sh] = row[10 + sh]; }
                 if (edge_r) {
@@ -635,7 +648,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int ly = ly0 + j;
-                if (ly < h1 && 2 * sg + j < TH / 2) {
+                if (ly < h1 && 2 * sg + j < TH2 / 2) {
                     uint32_t v[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++)
@@ -653,7 +666,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
 
     // ------------------------------------------------------------------ D. FAST candidates + exact score
     uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;
-    uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + NWARPS * QCAP * 2);
+    uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + V2_KPLIST_OFF);
     int cn = 0;   // corners of this warp inside the tile interior: prefix of Q after this phase
     if (P.keys) {
         const int thr = P.thr;
@@ -662,7 +675,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
         uint32_t vm;
         {
             const int xlo = max(3, x0 - 1), xhi = min(w - 4, x0 + TW);
-            const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH);
+            const int ylo = max(3, y0 - 1), yhi = min(h - 4, y0 + TH2);
             const int yb = y0 - 1 + 8 * warp;
             const int r0v = max(ylo - yb, 0), r1v = min(yhi - yb, 7);
             const uint32_t rowbits = r1v >= r0v ? ((0xffu >> (7 - r1v)) & (0xffu << r0v)) & 0xffu : 0u;
@@ -720,8 +733,8 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
                     const int sc = fast_strength2(S.gray + pr * GP + pcg);
                     if (sc > thr) {
                         const int sr = pr - 3, scol = pcg - 4 * cbw;   // score-tile row / column (column 4 = image x0)
-                        S.score[sr * SP2 + scol] = (uint8_t)(sc - 1);
-                        corner_in = sr >= 1 && sr <= TH && scol >= 4 && scol < 4 + TW;
+                        score[sr * SP2 + scol] = (uint8_t)(sc - 1);
+                        corner_in = sr >= 1 && sr <= TH2 && scol >= 4 && scol < 4 + TW;
                         centry = ((uint32_t)sr << 7) | (uint32_t)scol;
                     }
                 }
@@ -741,7 +754,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
             if (c0 + lane < cn) {
                 const uint32_t e = Q[c0 + lane];
                 const int sr = e >> 7, scol = e & 127;
-                const uint8_t* sp = S.score + sr * SP2 + scol;
+                const uint8_t* sp = score + sr * SP2 + scol;
                 const uint32_t v = sp[0];
                 const uint32_t m = max(max(max((uint32_t)sp[-SP2 - 1], (uint32_t)sp[-SP2]), max((uint32_t)sp[-SP2 + 1], (uint32_t)sp[-1])),
                                        max(max((uint32_t)sp[1], (uint32_t)sp[SP2 - 1]), max((uint32_t)sp[SP2], (uint32_t)sp[SP2 + 1])));
@@ -755,12 +768,12 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (iskp) {
                     const int kp = base + __popc(mk & ((1u << lane) - 1u));
-                    if (kp < KPCAP) kplist[kp] = key;
+                    if (kp < KPCAP2) kplist[kp] = key;
                 }
             }
         }
         __syncthreads();
-        const int n = min(S.kpcount, KPCAP);
+        const int n = min(S.kpcount, KPCAP2);
         if (tid == 0) S.kpbase = n ? atomicAdd(P.counts + f, n) : 0;
         __syncthreads();
         const int base = S.kpbase;
@@ -1027,7 +1040,12 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     FrontendParams P{};
     P.src = src; P.l0 = l0; P.l1 = l1; P.keys = keys; P.counts = counts;
     P.w = w; P.h = h; P.nframes = nframes;
-    P.tiles_x = (w + TW - 1) / TW; P.tiles_y = (h + TH - 1) / TH;
+    static const bool no_tma = getenv("ALVA_DISABLE_TMA") != nullptr;   // debugging aid: force the plain-load path
+    const bool tma_geom = rgba_mode ? (w % 4 == 0) && ((uintptr_t)src % 16 == 0)
+                                    : (w % 16 == 0) && (((size_t)w * h) % 16 == 0) && ((uintptr_t)src % 16 == 0);
+    const bool v2 = tma_geom && !no_tma && alva_g_frontend_variant == 2 && !alva_g_frontend_antipodal;
+    const int th = v2 ? TH2 : TH, bh = v2 ? BH2 : BH;
+    P.tiles_x = (w + TW - 1) / TW; P.tiles_y = (h + th - 1) / th;
     P.thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr); P.cap = cap;
     for (int i = 0; i < 7; i++) P.mul[i] = 1u << (25 + i);
     CUtensorMap tmap;
@@ -1036,21 +1054,19 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     if (rgba_mode) {
         uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)nframes};
         uint64_t strides[2] = {(uint64_t)w * 4, (uint64_t)w * h * 4};
-        uint32_t box[3] = {BW, BH, 1};
-        tma_ok = (w % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
-                 alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src, dims, strides, box);
+        uint32_t box[3] = {BW, (uint32_t)bh, 1};
+        tma_ok = tma_geom && alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src, dims, strides, box);
     } else {
         uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)nframes};
         uint64_t strides[2] = {(uint64_t)w, (uint64_t)w * h};
-        uint32_t box[3] = {GP, BH, 1};
-        tma_ok = (w % 16 == 0) && (((size_t)w * h) % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
-                 alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, src, dims, strides, box);
+        uint32_t box[3] = {GP, (uint32_t)bh, 1};
+        tma_ok = tma_geom && alva_make_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, src, dims, strides, box);
     }
-    static const bool no_tma = getenv("ALVA_DISABLE_TMA") != nullptr;   // debugging aid: force the plain-load path
+    if (v2 && !tma_ok) { alva_set_error("front end: cuTensorMapEncodeTiled failed"); return ALVA_E_CUDA; }
     P.use_tma = (tma_ok && !no_tma) ? 1 : 0;
     const int grid = P.tiles_x * P.tiles_y * nframes;
     const size_t smem = sizeof(SmemLayout) + 128;
-    if (P.use_tma && alva_g_frontend_variant == 2 && !alva_g_frontend_antipodal) {
+    if (v2) {
         const size_t smem2 = sizeof(SmemLayout2) + 128;
         if (rgba_mode) {
             ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

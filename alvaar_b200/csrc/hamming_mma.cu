@@ -4,15 +4,19 @@
 //   opencv features2d/src/matchers.cpp:757 -> core/src/batch_distance.cpp:103-123 (batchDistHamming),
 //   k-NN insertion :235-248 (strict '<': ties keep the lowest train index).
 //
-// Why tensor cores: brute-force Hamming IS a contraction.  With every descriptor bit b expanded to the int8 value
-// 2b - 1 (+1 / -1), the dot product of two 256-element rows is  256 - 2 * hamming,  an exact int32.  So the N_q x N_t
-// distance matrix is one int8 GEMM with K = 256, and the integer pipes (which bound the LOP3/POPC kernel of hamming.cu
-// at ~7.5e11 distances/s) are left with nothing but the top-2 selection.
+// Why tensor cores: brute-force Hamming IS a contraction.  With every descriptor bit b expanded to the 8-bit value
+// 2b - 1 (+1 / -1), the dot product of two 256-element rows is  256 - 2 * hamming,  exactly (an int32, or a float whose
+// partial sums are all integers of magnitude <= 256).  So the N_q x N_t distance matrix is one 8-bit GEMM with K = 256, and the
+// integer pipes (which bound the LOP3/POPC kernel of hamming.cu at ~7.5e11 distances/s) are left with nothing but the top-2
+// selection.  Two operand kinds are built: kind::i8 (+-1 as int8, int32 accumulators) and kind::f8f6f4 (+-1.0 as E4M3, fp32
+// accumulators).  Measured on B200 (profiles/r02_knn_mma_i8_full.txt): the int8 path keeps the IMMA sub-pipe busy 95 % of the
+// kernel and still only delivers ~1 900 MAC/clk/SM -- a quarter of the FP8 rate -- so FP8 is the default; the results are
+// bit-identical (every value involved is an exactly representable integer).
 //
 // Shape of the kernel (one CTA per 256 query rows, 1 CTA / SM, 12 warps):
 //   warp 0   producer : bulk async copies (cp.async.bulk, SASS UBLKCP -- the TMA engine's 1-D mode) of pre-tiled 32 KB
 //                       operand blobs into a 4-stage shared-memory ring, completion on mbarriers
-//   warp 1   issuer   : one elected thread issues tcgen05.mma.kind::i8 (SASS UTCIMMA), M = 128, N = 128, K = 32 per
+//   warp 1   issuer   : one elected thread issues tcgen05.mma.kind::f8f6f4 / kind::i8 (SASS UTCQMMA / UTCIMMA), M = 128, N = 128, K = 32 per
 //                       instruction, 8 per K = 256, for TWO 128-row query tiles per train tile (every train byte that
 //                       leaves L2 feeds 256 query rows); accumulators live in TMEM, double-buffered (4 x 128 columns
 //                       = all 512), tcgen05.commit signals "smem stage free" and "accumulator ready"
@@ -82,6 +86,15 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t d
         "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -121,14 +134,14 @@ __global__ void __launch_bounds__(256) knn2_offsets_kernel(const int32_t* __rest
     if (tid == 255) offsets[nbatch] = part[255];
 }
 
-// 16 descriptor bits -> 16 int8 (+1 for a set bit, -1 for a clear one), LSB first
-__device__ __forceinline__ uint4 expand16(uint32_t v) {
+// 16 descriptor bits -> 16 bytes (+1 for a set bit, -1 for a clear one), LSB first.  int8: 0x01 / 0xFF; E4M3: 0x38 / 0xB8
+__device__ __forceinline__ uint4 expand16(uint32_t v, int kind) {
     uint32_t w[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         const uint32_t nib = (v >> (4 * g)) & 15u;
         const uint32_t b01 = (nib * 0x00204081u) & 0x01010101u;   // bit i of the nibble -> byte i
-        w[g] = ~(b01 * 0xFEu);                                    // 1 -> 0x01, 0 -> 0xFF
+        w[g] = kind ? (0xB8B8B8B8u ^ (b01 * 0x80u)) : ~(b01 * 0xFEu);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -139,7 +152,7 @@ __device__ __forceinline__ uint4 expand16(uint32_t v) {
 __global__ void __launch_bounds__(256) knn2_expand_kernel(const uint8_t* __restrict__ q, const int32_t* __restrict__ offsets,
                                                           int nbatch, int qcap, int nq_slots, uint8_t* __restrict__ Aexp,
                                                           int32_t* __restrict__ rowmap, int a_blocks, const uint8_t* __restrict__ t,
-                                                          int nt, uint8_t* __restrict__ Bexp, int mode) {
+                                                          int nt, uint8_t* __restrict__ Bexp, int mode, int kind) {
     const bool is_a = (int)blockIdx.x < a_blocks;
     const int idx = (is_a ? blockIdx.x : blockIdx.x - a_blocks) * 256 + threadIdx.x;
     const int tile = idx >> 11, wi = idx & 2047, c = wi >> 7, r = wi & 127;
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(256) knn2_expand_kernel(const uint8_t* __restr
         if (R < nt) src = t + (size_t)R * 32;
     }
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (src) o = expand16(*reinterpret_cast<const uint16_t*>(src + 2 * c));
+    if (src) o = expand16(*reinterpret_cast<const uint16_t*>(src + 2 * c), kind);
     uint8_t* dst = (is_a ? Aexp : Bexp) + (size_t)tile * BLOB + tile_offset(mode, r, c);
     *reinterpret_cast<uint4*>(dst) = o;
 }
@@ -178,6 +191,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, const MmaLayout& L
     return (uint64_t)lo | ((uint64_t)L.desc_hi << 32);
 }
 
+// accumulator value type per operand kind, and the bit pattern <-> value conversions of the epilogue
+template <int KIND> struct Acc;
+template <> struct Acc<0> { using T = int;   static __device__ __forceinline__ int from_bits(int b) { return b; }
+                            static __device__ __forceinline__ int neg() { return NEG; }  static __device__ __forceinline__ int to_int(int v) { return v; } };
+template <> struct Acc<1> { using T = float; static __device__ __forceinline__ float from_bits(int b) { return __int_as_float(b); }
+                            static __device__ __forceinline__ float neg() { return (float)NEG; }  static __device__ __forceinline__ int to_int(float v) { return (int)v; } };
+
+template <int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Bexp, const int32_t* __restrict__ rowmap,
                 const int32_t* __restrict__ total_ptr, int nrows, int nt, int ntiles, int tiles_per_chunk, int nchunks,
@@ -238,8 +259,10 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
                 for (int t = 0; t < 2; t++) {
                     const uint32_t d = tmem + (uint32_t)((as * 2 + t) * TN);
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        umma_i8(d, make_desc(a0 + t * BLOB + L.koff[j], L), make_desc(b0 + L.koff[j], L), idesc, j > 0 ? 1u : 0u);
+                    for (int j = 0; j < 8; j++) {
+                        const uint64_t da = make_desc(a0 + t * BLOB + L.koff[j], L), db = make_desc(b0 + L.koff[j], L);
+                        if (KIND) umma_f8(d, da, db, idesc, j > 0 ? 1u : 0u); else umma_i8(d, da, db, idesc, j > 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&B.empty[s]);          // fires when the MMAs above have finished reading shared memory
                 umma_commit(&B.tfull[as]);         // ... and their results are in TMEM
@@ -250,7 +273,9 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
         // ---------------------------------------------------------------- epilogue: top-2 per query row
         const int t = (warp - EPI_WARP0) >> 2, lq = warp & 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) ..
         const int row = pair * 2 * TM + t * TM + lq * 32 + lane;
-        int a1 = NEG, a2 = NEG, i1 = -1, i2 = -1;
+        using A = Acc<KIND>;
+        typename A::T a1 = A::neg(), a2 = A::neg();
+        int i1 = -1, i2 = -1;
         for (int it = 0; it < nit; it++) {
             const int as = it & 1, aph = (it >> 1) & 1;
             mbar_wait(&B.tfull[as], aph);
@@ -259,16 +284,19 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
             const int nbase = (tile0 + it) * TN;
 #pragma unroll 1
             for (int cb = 0; cb < TN / 32; cb++) {
-                int v[32];
-                tmem_ld32(taddr + cb * 32, v);
+                int vb[32];
+                tmem_ld32(taddr + cb * 32, vb);
                 const int n0 = nbase + cb * 32;
-                if (n0 + 32 > nt) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = NEG;
-                }
                 if (dbg && pair == 0 && chunk == 0 && it == 0 && t == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) dbg[(lq * 32 + lane) * TN + cb * 32 + j] = v[j];
+                    for (int j = 0; j < 32; j++) dbg[(lq * 32 + lane) * TN + cb * 32 + j] = A::to_int(A::from_bits(vb[j]));
+                }
+                typename A::T v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = A::from_bits(vb[j]);
+                if (n0 + 32 > nt) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();
                 }
                 bool hit = false;
 #pragma unroll
@@ -276,7 +304,7 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
                 if (hit) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int a = v[j];
+                        const typename A::T a = v[j];
                         if (a > a2) {
                             if (a > a1) { a2 = a1; i2 = i1; a1 = a; i1 = n0 + j; }
                             else { a2 = a; i2 = n0 + j; }
@@ -292,8 +320,8 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
             const int slot = rowmap ? rowmap[row] : row;
             if (slot >= 0) {
                 // dot = 256 - 2 * hamming  ->  (256 - dot) << 21 == hamming << 22
-                const uint32_t k1 = i1 >= 0 ? (((uint32_t)(256 - a1)) << 21) | (uint32_t)i1 : NONE;
-                const uint32_t k2 = i2 >= 0 ? (((uint32_t)(256 - a2)) << 21) | (uint32_t)i2 : NONE;
+                const uint32_t k1 = i1 >= 0 ? (((uint32_t)(256 - A::to_int(a1))) << 21) | (uint32_t)i1 : NONE;
+                const uint32_t k2 = i2 >= 0 ? (((uint32_t)(256 - A::to_int(a2))) << 21) | (uint32_t)i2 : NONE;
                 partial[(size_t)slot * nchunks + chunk] = make_uint2(k1, k2);
             }
         }
@@ -307,6 +335,7 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
 
 // ---------------------------------------------------------------------------------------------- host side
 int alva_g_knn_mma = 1;        // alva_set_option("knn_mma", 0 never | 1 automatic (large query sets) | 2 always)
+int alva_g_knn_mma_kind = 1;   // alva_set_option("knn_mma_kind", 0 int8 operands / int32 accumulators | 1 E4M3 operands / fp32 accumulators)
 int alva_g_knn_mma_mode = 0;   // alva_set_option("knn_mma_mode", 0 no swizzle | 1 128-byte swizzle | 2 debugging variant of 0)
 
 int alva_knn2_merge_launch(alva_ctx* ctx, const uint2* partial, int nq, int nchunks, int32_t* out, const int32_t* counts, int qcap);
@@ -374,16 +403,25 @@ int alva_knn2_mma_launch(alva_ctx* ctx, const uint8_t* q, int nq, const uint8_t*
         ALVA_LAUNCH_CHECK(ctx);
     }
     const int a_blocks = a_tiles * 8, b_blocks = b_tiles * 8;
-    knn2_expand_kernel<<<a_blocks + b_blocks, 256, 0, ctx->stream>>>(q, offsets, nbatch, qcap, nq, Aexp, rowmap, a_blocks, t, nt, Bexp, L.mode);
+    const int kind = alva_g_knn_mma_kind ? 1 : 0;
+    knn2_expand_kernel<<<a_blocks + b_blocks, 256, 0, ctx->stream>>>(q, offsets, nbatch, qcap, nq, Aexp, rowmap, a_blocks, t, nt, Bexp, L.mode, kind);
     ALVA_LAUNCH_CHECK(ctx);
 
-    // instruction descriptor: D = S32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9, 10-12 = 1), both K-major,
-    // N >> 3 at bit 17, M >> 4 at bit 24
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    // instruction descriptor (both operands K-major): N >> 3 at bit 17, M >> 4 at bit 24;
+    //   kind::i8     : D = S32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9, 10-12 = 1)
+    //   kind::f8f6f4 : D = F32 (bits 4-5 = 1), A = B = E4M3 (bits 7-9, 10-12 = 0)
+    const uint32_t shape = ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t idesc = kind ? ((1u << 4) | shape) : ((2u << 4) | (1u << 7) | (1u << 10) | shape);
     const size_t smem = (size_t)(2 + NSTAGE) * BLOB + sizeof(SmemBars) + 1024;
-    ALVA_CUDA(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn2_mma_kernel<<<dim3(npairs, nchunks), NTHREADS, smem, ctx->stream>>>(Aexp, Bexp, rowmap, counts ? offsets + nbatch : nullptr, nq, nt,
-                                                                           b_tiles, tiles_per_chunk, nchunks, partial, L, idesc, dbg_out);
+    const dim3 grid(npairs, nchunks);
+    const int32_t* total_ptr = counts ? offsets + nbatch : nullptr;
+    if (kind) {
+        ALVA_CUDA(cudaFuncSetAttribute(knn2_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn2_mma_kernel<1><<<grid, NTHREADS, smem, ctx->stream>>>(Aexp, Bexp, rowmap, total_ptr, nq, nt, b_tiles, tiles_per_chunk, nchunks, partial, L, idesc, dbg_out);
+    } else {
+        ALVA_CUDA(cudaFuncSetAttribute(knn2_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn2_mma_kernel<0><<<grid, NTHREADS, smem, ctx->stream>>>(Aexp, Bexp, rowmap, total_ptr, nq, nt, b_tiles, tiles_per_chunk, nchunks, partial, L, idesc, dbg_out);
+    }
     ALVA_LAUNCH_CHECK(ctx);
     return alva_knn2_merge_launch(ctx, partial, nq, nchunks, out, counts, qcap);
 }

@@ -155,13 +155,16 @@ def knn_mma(gpu_ctx):
     yield gpu_ctx
     gpu_ctx.L.alva_set_option(b"knn_mma", 1)
     gpu_ctx.L.alva_set_option(b"knn_mma_mode", 0)
+    gpu_ctx.L.alva_set_option(b"knn_mma_kind", 1)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("kind,mode", [(1, 0), (1, 1), (0, 0), (0, 1)])
 @pytest.mark.parametrize("nq,nt", [(1000, 10000), (1000, 1000), (7, 1), (1, 2), (33, 1025), (1000, 20000), (257, 129), (4100, 300)])
-def test_knn2_mma_vs_oracle(knn_mma, oracle, nq, nt, mode):
-    """tcgen05 int8 formulation (dot = 256 - 2 * distance): bit-identical 2-NN lists incl. the tie rule, both operand layouts"""
+def test_knn2_mma_vs_oracle(knn_mma, oracle, nq, nt, kind, mode):
+    """tcgen05 formulation (dot = 256 - 2 * distance; E4M3 / fp32 and int8 / int32 operand kinds, both shared-memory operand
+    layouts): bit-identical 2-NN lists incl. the tie rule"""
     assert knn_mma.L.alva_set_option(b"knn_mma_mode", mode) == 0
+    assert knn_mma.L.alva_set_option(b"knn_mma_kind", kind) == 0
     q, t = synth.make_descriptors(nq, nt, seed=nq + nt, planted=0.3 if nt >= nq else 0.0)
     if nt > 100:
         t[nt // 2:nt // 2 + 20] = t[:20]
@@ -179,12 +182,14 @@ def test_knn2_mma_golden(knn_mma):
     assert (out.cpu().numpy() == g["out"]).all()
 
 
-def test_knn2_mma_ragged_batch(knn_mma, oracle):
+@pytest.mark.parametrize("kind", [1, 0])
+def test_knn2_mma_ragged_batch(knn_mma, oracle, kind):
     """[nbatch][qcap] query slots with per-batch live counts (incl. an empty and a full batch): live slots equal the oracle's
     lists, dead slots come back as -1 -- the compaction of the live rows must not leak between batches."""
     nb, qcap, nt = 9, 256, 3000
     counts = np.array([256, 0, 1, 255, 17, 128, 129, 200, 64], np.int32)
     q, t = synth.make_descriptors(nb * qcap, nt, seed=11, planted=0.3)
+    assert knn_mma.L.alva_set_option(b"knn_mma_kind", kind) == 0
     out = torch.full((nb * qcap, 4), -7, dtype=torch.int32, device=DEV)
     knn_mma.hamming_knn2_batch(dev(q), torch.from_numpy(counts).to(DEV), nb, qcap, dev(t), nt, out)
     got = out.cpu().numpy().reshape(nb, qcap, 4)
@@ -203,7 +208,7 @@ def test_knn2_mma_equals_lop3_on_bench_shape(gpu_ctx):
     against the LOP3 / POPC kernel"""
     nb, qcap, nt = 64, 1536, 10000
     rng = np.random.default_rng(3)
-    q, t = synth.make_descriptors(nb * qcap, nt, seed=21, planted=0.3)
+    q, t = synth.make_descriptors(nb * qcap, nt, seed=21, planted=0.05)
     counts = torch.from_numpy(rng.integers(900, 1300, nb).astype(np.int32)).to(DEV)
     outs = []
     for opt in (0, 1):

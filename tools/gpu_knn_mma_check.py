@@ -12,12 +12,14 @@ import alvaar_b200
 
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 do_time = len(sys.argv) > 2 and sys.argv[2] == "time"
+kind = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = "cuda:0"
 ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)
 L = ctx.L
 vp, i32 = C.c_void_p, C.c_int
 L.alva_debug_knn2_mma.argtypes = [vp, vp, i32, vp, i32, vp, vp]
 assert L.alva_set_option(b"knn_mma_mode", mode) == 0
+assert L.alva_set_option(b"knn_mma_kind", kind) == 0
 P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
 POP = np.array([bin(i).count("1") for i in range(256)], np.int32)
@@ -62,7 +64,7 @@ for (nq, nt) in [(128, 128), (300, 1000), (1000, 2500), (257, 129)]:
     got = out.cpu().numpy()
     ref = ref_knn2(q, t)
     res_ok = np.array_equal(got, ref)
-    print(f"mode {mode} nq {nq} nt {nt}: first tile {'OK' if tile_ok else 'MISMATCH'}  2-NN {'OK' if res_ok else 'MISMATCH'}")
+    print(f"kind {kind} mode {mode} nq {nq} nt {nt}: first tile {'OK' if tile_ok else 'MISMATCH'}  2-NN {'OK' if res_ok else 'MISMATCH'}")
     if not tile_ok:
         bad = np.argwhere(g[:m, :n] != want)
         print("  mismatching cells:", len(bad), "of", m * n, " first:", bad[:5].tolist())
@@ -105,5 +107,5 @@ if ok_all and do_time:
     print("tensor-core result == LOP3 result on the bench shape:", same)
     ok_all &= same
     L.alva_set_option(b"knn_mma", 1)
-print("RESULT mode", mode, "PASS" if ok_all else "FAIL")
+print("RESULT kind", kind, "mode", mode, "PASS" if ok_all else "FAIL")
 sys.exit(0 if ok_all else 1)

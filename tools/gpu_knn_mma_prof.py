@@ -10,9 +10,11 @@ import alvaar_b200
 
 opt = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 rep = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+kind = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = "cuda:0"
 ctx = alvaar_b200.Context(0, torch.cuda.current_stream().cuda_stream)
 assert ctx.L.alva_set_option(b"knn_mma", opt) == 0
+assert ctx.L.alva_set_option(b"knn_mma_kind", kind) == 0
 rng = np.random.default_rng(5)
 nb, qcap, live, nt = 64, 1536, 1137, 10000
 q = rng.integers(0, 256, (nb * qcap, 32), dtype=np.uint8)
