@@ -513,7 +513,8 @@ struct __align__(128) SmemLayout2 {
     // TMA destination (RGBA mode).  After the gray pass: per-warp queues (NWARPS * QCAP u16), the tile's keypoint list
     // (KPCAP2 words) and the score tile (SP2 * SR2 bytes)
     uint8_t rgba[BW * BH2 * 4];
-    uint8_t gray[GP * BH2];        // TMA destination (gray mode)
+    uint8_t gray[GP * (BH2 + 2)];  // TMA destination (gray mode); + 2 rows: the last warp's pre-test window (8 * 7 + 14 rows) reads
+                                   // two rows past the box -- they only feed pixels its validity mask drops
     uint64_t bar;
     int kpcount;
     int kpbase;

@@ -21,11 +21,15 @@
 //                       leaves L2 feeds 256 query rows); accumulators live in TMEM, double-buffered (4 x 128 columns
 //                       = all 512), tcgen05.commit signals "smem stage free" and "accumulator ready"
 //   warp 2   TMEM allocator
-//   warps 4-11 epilogue: tcgen05.ld (SASS LDTM) 32 columns at a time; a row (= query) lives in one thread, which scans its
-//                       128 dot products with ONE compare each (is it above my current second best?) and only on a hit
-//                       runs the exact (distance, index) top-2 insertion -- indices arrive in increasing order, so
-//                       "strictly greater dot product" is exactly OpenCV's strict '<' on the distance with ties to the
-//                       lowest train index.
+//   warps 4-19 epilogue: 2 query tiles x 4 TMEM lane quarters x 2 column halves.  tcgen05.ld (SASS LDTM) 2 x 32 columns in
+//                       flight; a row (= query) lives in one thread per column half, which reduces its 32 dot products to
+//                       four group maxima (3-input max) and compares the largest with its current second best; only on a
+//                       hit, and only in the groups that hit, runs the exact (distance, index) top-2 insertion, branch-free
+//                       -- indices arrive in increasing order, so "strictly greater dot product" is exactly OpenCV's strict
+//                       '<' on the distance with ties to the lowest train index.  The two halves of a row are merged through
+//                       shared memory at the end (value first, lower index on ties).
+//                       The epilogue is what bounds this kernel (profiles/r02b_knn_mma_f8_full.txt: with 8 epilogue warps and
+//                       a branchy insertion the MMAs waited on it 3/4 of the time; int8 and FP8 operands ran equally fast).
 // The operands are expanded from the packed 256-bit descriptors by knn2_expand_kernel straight into the shared-memory
 // image of a tile (UMMA canonical K-major layout), so the producer needs no tensor map and no swizzle pattern has to be
 // matched by hand anywhere else.  Live queries of a batch are compacted on the way ([nbatch][qcap] slots, counts[b] live).
@@ -39,8 +43,9 @@ constexpr int TN = 128;                 // train rows per N tile (UMMA N)
 constexpr int KBYTES = 256;             // int8 elements per expanded descriptor
 constexpr int BLOB = TM * KBYTES;       // one operand tile in shared memory: 32 KB
 constexpr int NSTAGE = 4;               // train-tile ring
-constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 16;            // 2 query tiles x 4 TMEM lane quarters x 2 column halves
+constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr uint32_t NONE = 0xffffffffu;
 constexpr int NEG = -(1 << 20);         // "no candidate yet" dot product
 
@@ -98,7 +103,7 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t da, uint64_t d
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -108,8 +113,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------- operand expansion
 // offsets[b] = number of live queries in batches < b  (counts clamped to [0, qcap]); one small CTA
@@ -184,6 +190,8 @@ __global__ void __launch_bounds__(256) knn2_expand_kernel(const uint8_t* __restr
 struct SmemBars {
     uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], afull;
     uint32_t tmem_base;
+    uint32_t pad[3];
+    int4 xchg[2 * TM];      // top-2 of the upper column half of every row: (best bits, best index, second bits, second index)
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, const MmaLayout& L) {
@@ -218,7 +226,7 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&B.full[s], 1); mbar_init(&B.empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&B.tfull[s], 1); mbar_init(&B.tempty[s], 8); }
+        for (int s = 0; s < 2; s++) { mbar_init(&B.tfull[s], 1); mbar_init(&B.tempty[s], EPI_WARPS); }
         mbar_init(&B.afull, 1);
         fence_barrier_init();
     }
@@ -270,59 +278,91 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
             __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
-        // ---------------------------------------------------------------- epilogue: top-2 per query row
-        const int t = (warp - EPI_WARP0) >> 2, lq = warp & 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) ..
-        const int row = pair * 2 * TM + t * TM + lq * 32 + lane;
+        // ---------------------------------------------------------------- epilogue: top-2 per query row and column half
+        const int e = warp - EPI_WARP0;
+        const int lq = e & 3, t = (e >> 2) & 1, half = e >> 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) ..; EPI_WARP0 % 4 == 0
+        const int trow = lq * 32 + lane;                         // row inside the 128-row tile
+        const int row = pair * 2 * TM + t * TM + trow;
         using A = Acc<KIND>;
-        typename A::T a1 = A::neg(), a2 = A::neg();
+        using T = typename A::T;
+        T a1 = A::neg(), a2 = A::neg();
         int i1 = -1, i2 = -1;
+        // exact insertion of one candidate, branch-free.  Candidates reach a thread in increasing index order, so a strictly
+        // larger dot product is OpenCV's strict '<' on the distance with ties kept by the lower index.
+        auto insert = [&](T a, int idx) {
+            const bool gt1 = a > a1, gt2 = a > a2;
+            a2 = gt1 ? a1 : (gt2 ? a : a2);
+            i2 = gt1 ? i1 : (gt2 ? idx : i2);
+            a1 = gt1 ? a : a1;
+            i1 = gt1 ? idx : i1;
+        };
+        auto max3 = [](T x, T y, T z) { return max(max(x, y), z); };
+        auto scan32 = [&](int (&vb)[32], int n0) {
+            T v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = A::from_bits(vb[j]);
+            if (n0 + 32 > nt) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();
+            }
+            T g[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                g[k] = max3(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), max(v[8 * k + 6], v[8 * k + 7]));
+            if (max(max(g[0], g[1]), max(g[2], g[3])) > a2) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (g[k] > a2) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) insert(v[8 * k + j], n0 + 8 * k + j);
+                    }
+                }
+            }
+        };
         for (int it = 0; it < nit; it++) {
             const int as = it & 1, aph = (it >> 1) & 1;
             mbar_wait(&B.tfull[as], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)((as * 2 + t) * TN);
-            const int nbase = (tile0 + it) * TN;
-#pragma unroll 1
-            for (int cb = 0; cb < TN / 32; cb++) {
-                int vb[32];
-                tmem_ld32(taddr + cb * 32, vb);
-                const int n0 = nbase + cb * 32;
-                if (dbg && pair == 0 && chunk == 0 && it == 0 && t == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) dbg[(lq * 32 + lane) * TN + cb * 32 + j] = A::to_int(A::from_bits(vb[j]));
-                }
-                typename A::T v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = A::from_bits(vb[j]);
-                if (n0 + 32 > nt) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();
-                }
-                bool hit = false;
-#pragma unroll
-                for (int j = 0; j < 32; j++) hit |= v[j] > a2;
-                if (hit) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const typename A::T a = v[j];
-                        if (a > a2) {
-                            if (a > a1) { a2 = a1; i2 = i1; a1 = a; i1 = n0 + j; }
-                            else { a2 = a; i2 = n0 + j; }
-                        }
-                    }
-                }
-            }
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)((as * 2 + t) * TN + half * (TN / 2));
+            const int n0 = (tile0 + it) * TN + half * (TN / 2);
+            int vb0[32], vb1[32];
+            tmem_ld32_issue(taddr, vb0);
+            tmem_ld32_issue(taddr + 32, vb1);
+            tmem_ld_wait();
+            // the accumulators are in registers: hand the stage back to the MMA issuer before the selection work
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.tempty[as]);
+            if (dbg && pair == 0 && chunk == 0 && it == 0 && t == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    dbg[trow * TN + half * (TN / 2) + j] = A::to_int(A::from_bits(vb0[j]));
+                    dbg[trow * TN + half * (TN / 2) + 32 + j] = A::to_int(A::from_bits(vb1[j]));
+                }
+            }
+            scan32(vb0, n0);
+            scan32(vb1, n0 + 32);
         }
-        if (row < total) {
+        // merge the two column halves of a row: the upper half hands its pair over through shared memory
+        if (half == 1) B.xchg[t * TM + trow] = make_int4(A::to_int(a1), i1, A::to_int(a2), i2);
+        bar_sync_named(1, EPI_WARPS * 32);
+        if (half == 0 && row < total) {
             const int slot = rowmap ? rowmap[row] : row;
             if (slot >= 0) {
-                // dot = 256 - 2 * hamming  ->  (256 - dot) << 21 == hamming << 22
-                const uint32_t k1 = i1 >= 0 ? (((uint32_t)(256 - A::to_int(a1))) << 21) | (uint32_t)i1 : NONE;
-                const uint32_t k2 = i2 >= 0 ? (((uint32_t)(256 - A::to_int(a2))) << 21) | (uint32_t)i2 : NONE;
-                partial[(size_t)slot * nchunks + chunk] = make_uint2(k1, k2);
+                const int4 o = B.xchg[t * TM + trow];
+                // keys: (256 - dot) << 21 == hamming << 22, index in the low bits -> the lexicographic (distance, index) order
+                // of OpenCV's insertion is an unsigned min
+                auto key = [](int a, int idx) { return idx >= 0 ? (((uint32_t)(256 - a)) << 21) | (uint32_t)idx : NONE; };
+                uint32_t k[4] = {key(A::to_int(a1), i1), key(A::to_int(a2), i2), key(o.x, o.y), key(o.z, o.w)};
+                uint32_t b0 = NONE, b1 = NONE;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (k[c] < b1) {
+                        if (k[c] < b0) { b1 = b0; b0 = k[c]; }
+                        else b1 = k[c];
+                    }
+                }
+                partial[(size_t)slot * nchunks + chunk] = make_uint2(b0, b1);
             }
         }
     }

@@ -7,7 +7,9 @@ What is exact over all 100 frames: status codes, track ids IN THE REFERENCE'S IT
 and Ceres residual order), 3-D flags, keyframe events, frame / map counters -- and, before the initialisation, every pixel
 position bit for bit.
 What is toleranced: after the initialisation, poses / world points carry the reference's own noise-limited 5-point refinement
-(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by up to 1e-3): |dt| < 1e-2 max(1, |t|), |dq| < 1e-3.
+(tests/test_oracle_init.py: a 1-ulp input change moves ITS result by 1e-6 .. 1e-3).  The bar is data-driven (system_util.
+pose_deviation): 1e-4 relative (north_star), or 4 x the reference's OWN spread on this trace under a 1-ulp change of one intrinsic
+(stored in the golden) where that spread is larger; the worst observed deviation is printed.
 With the reference's OWN initialisation stage plugged in (live reference only) everything downstream -- KLT with projected
 priors, P3P-LMedS, PnP, keyframe decisions, triangulation, local-map matching, local BA, culling -- is in lockstep: poses and
 world points 1e-9, pixel positions bit-identical, over the whole trace (tools/compare_system_cpu.py shows the same over 140
@@ -18,7 +20,7 @@ import numpy as np
 import pytest
 
 from conftest import P
-from system_util import CAP, cpu_system_lib, frame_slice, frames_and_golden, quat_dist
+from system_util import CAP, PoseReport, cpu_system_lib, frame_slice, frames_and_golden, quat_dist
 
 
 def run(S, frames, K, hook=None):
@@ -44,6 +46,7 @@ def test_state_machine_follows_the_reference(oracle):
     fb = int(g["first_ba_frame"])
     init = int(np.argmax(g["ref_status"] == 1))
     assert 10 <= init < fb < len(frames)
+    rep = PoseReport("state machine over the CPU oracle vs the reference System, free-running")
     for k, (st, T, info, ids, px, d3, wp) in enumerate(tr):
         rids, rpx, rd3, rwp = frame_slice(g, "ref_", k)
         assert st == g["ref_status"][k], k
@@ -54,10 +57,11 @@ def test_state_machine_follows_the_reference(oracle):
             assert (T == g["ref_Twc"][k]).all()
         else:
             assert np.abs(px - rpx).max() < 0.02
-            assert np.abs(T[:3] - g["ref_Twc"][k][:3]).max() < 1e-2 * max(1.0, float(np.linalg.norm(g["ref_Twc"][k][:3]))) and quat_dist(T[3:], g["ref_Twc"][k][3:]) < 1e-3
+            rep.check(g, k, T)                                               # 1e-4, or SPREAD_K x the reference's own 1-ulp spread where that is larger
         # the committed cpu_* trace (what the GPU build is compared with) is this very run
         cids, cpx, cd3, cwp = frame_slice(g, "cpu_", k)
         assert (ids == cids).all() and (px.view(np.uint32) == cpx.view(np.uint32)).all() and np.abs(T - g["cpu_Twc"][k]).max() < 1e-12
+    rep.summary(g)
 
 
 def test_lockstep_given_the_reference_initialisation(oracle, ref):

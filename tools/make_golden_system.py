@@ -89,6 +89,7 @@ def main():
     R.ref_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     R.ref_system_info8.argtypes = [C.c_void_p, C.c_void_p]
     R.ref_config(0, 1)
+    R.ref_config_time_caps(1)   # the three wall-clock caps of the Ceres solves lifted (oracle/build_ref.sh): the golden must not depend on host load
     w, h, nf, seed = 640, 480, 100, 7
     K = synth.intrinsics(w, h)
     frames, _ = synth.make_frames(nf, w, h, seed=seed, rgba=True)
@@ -114,6 +115,35 @@ def main():
         print(k, "status", st, "keypoints", n, "3-D", int(d3[:n].sum()), "keyframe", info[1])
     R.ref_system_destroy(s)
     d.update(tr.dump("ref_"))
+    # The reference's OWN sensitivity on this trace: the same run with one intrinsic moved by one ulp (every bearing vector
+    # then changes in its last bit).  Its 5-point refinement is noise-limited (tests/test_oracle_init.py), so the trajectory
+    # the reference itself produces moves by `ref_spread_*` -- no independent implementation can be asked to sit closer to
+    # `ref_Twc` than the reference sits to itself.  Stored per frame: max over the perturbed runs of |dt|_inf and of the
+    # quaternion distance; runs whose discrete state (status, keypoint ids) leaves the base run's are dropped from that frame on.
+    base_T = np.array(tr.T)
+    spread_t, spread_q, nruns = np.zeros(nf), np.zeros(nf), np.zeros(nf, np.int32)
+    for which in range(4):
+        for sgn in (+1, -1):
+            Kp = list(K)
+            Kp[which] = float(np.nextafter(K[which], K[which] + sgn))
+            s2 = R.ref_system_create(w, h, Kp[0], Kp[1], Kp[2], Kp[3], 0, 0, 0, 0)
+            alive = True
+            for k in range(nf):
+                pose = np.zeros(16, np.float32)
+                st = R.ref_system_find_camera_pose(s2, P(np.ascontiguousarray(frames[k])), k * 33.333, P(pose))
+                ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3)); T = np.zeros(7)
+                n = R.ref_system_keypoints(s2, P(ids), P(px), P(d3), P(wp), CAP, P(T))
+                alive = alive and st == tr.status[k] and n == len(tr.ids[k]) and (ids[:n] == tr.ids[k]).all()
+                if not alive:
+                    break
+                spread_t[k] = max(spread_t[k], float(np.abs(T[:3] - base_T[k, :3]).max()))
+                qd = 1.0 - abs(float(np.dot(T[3:], base_T[k, 3:])))
+                spread_q[k] = max(spread_q[k], float(np.sqrt(max(2.0 * qd, 0.0))))
+                nruns[k] += 1
+            R.ref_system_destroy(s2)
+    d["ref_spread_t"], d["ref_spread_q"], d["ref_spread_runs"] = spread_t, spread_q, nruns
+    print("reference vs itself under a 1-ulp change of one intrinsic: max |dt|", float(spread_t.max()), "max |dq|", float(spread_q.max()),
+          "runs alive at the last frame:", int(nruns[-1]), "of 8")
     d["ref_pose16"] = np.array(pose16)
     d["ref_xy_start"] = np.cumsum([0] + [len(x) for x in xys]).astype(np.int32)
     d["ref_xy"] = np.concatenate(xys)
