@@ -22,12 +22,11 @@
 //                       = all 512), tcgen05.commit signals "smem stage free" and "accumulator ready"
 //   warp 2   TMEM allocator
 //   warps 4-19 epilogue: 2 query tiles x 4 TMEM lane quarters x 2 column halves.  tcgen05.ld (SASS LDTM) 2 x 32 columns in
-//                       flight; a row (= query) lives in one thread per column half, which reduces its 32 dot products to
-//                       four group maxima (3-input max) and compares the largest with its current second best; only on a
-//                       hit, and only in the groups that hit, runs the exact (distance, index) top-2 insertion, branch-free
-//                       -- indices arrive in increasing order, so "strictly greater dot product" is exactly OpenCV's strict
-//                       '<' on the distance with ties to the lowest train index.  The two halves of a row are merged through
-//                       shared memory at the end (value first, lower index on ties).
+//                       flight; a row (= query) lives in one thread per column half, which reduces every 8 dot products to
+//                       their maximum (3-input max) and compares it with the dot product of its current second best; only
+//                       the groups that hit run the top-2 insertion, on packed keys hamming << 22 | index (one multiply-add
+//                       builds a key, three min / max insert it: OpenCV's strict '<' with ties to the lowest train index is
+//                       the unsigned order of those keys).  The two halves of a row are merged through shared memory.
 //                       The epilogue is what bounds this kernel (profiles/r02b_knn_mma_f8_full.txt: with 8 epilogue warps and
 //                       a branchy insertion the MMAs waited on it 3/4 of the time; int8 and FP8 operands ran equally fast).
 // The operands are expanded from the packed 256-bit descriptors by knn2_expand_kernel straight into the shared-memory
@@ -191,7 +190,7 @@ struct SmemBars {
     uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], afull;
     uint32_t tmem_base;
     uint32_t pad[3];
-    int4 xchg[2 * TM];      // top-2 of the upper column half of every row: (best bits, best index, second bits, second index)
+    uint2 xchg[2 * TM];     // the two best keys of the upper column half of every row
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, const MmaLayout& L) {
@@ -201,10 +200,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, const MmaLayout& L
 
 // accumulator value type per operand kind, and the bit pattern <-> value conversions of the epilogue
 template <int KIND> struct Acc;
-template <> struct Acc<0> { using T = int;   static __device__ __forceinline__ int from_bits(int b) { return b; }
-                            static __device__ __forceinline__ int neg() { return NEG; }  static __device__ __forceinline__ int to_int(int v) { return v; } };
-template <> struct Acc<1> { using T = float; static __device__ __forceinline__ float from_bits(int b) { return __int_as_float(b); }
-                            static __device__ __forceinline__ float neg() { return (float)NEG; }  static __device__ __forceinline__ int to_int(float v) { return (int)v; } };
+template <> struct Acc<0> {
+    using T = int;
+    static __device__ __forceinline__ int from_bits(int b) { return b; }
+    static __device__ __forceinline__ int neg() { return NEG; }
+    static __device__ __forceinline__ int to_int(int v) { return v; }
+    // (256 - dot) << 21 | idx as one multiply-add: dot * -(2^21) + ((256 << 21) + idx)  (idx < 2^22, (256 - dot) even)
+    static __device__ __forceinline__ uint32_t key(int v, int idx) { return (uint32_t)v * 0xFFE00000u + ((256u << 21) + (uint32_t)idx); }
+    static __device__ __forceinline__ int dot_of_key(uint32_t k) { return 256 - (int)(k >> 21); }   // NONE -> -1791: below every dot product
+};
+template <> struct Acc<1> {
+    using T = float;
+    static __device__ __forceinline__ float from_bits(int b) { return __int_as_float(b); }
+    static __device__ __forceinline__ float neg() { return (float)NEG; }
+    // the accumulators are integer-valued floats of magnitude <= 256: adding 1.5 * 2^23 leaves the integer in the low mantissa bits
+    static __device__ __forceinline__ int to_int(float v) { return __float_as_int(v + 12582912.0f) - 0x4B400000; }
+    static __device__ __forceinline__ uint32_t key(float v, int idx) { return (uint32_t)to_int(v) * 0xFFE00000u + ((256u << 21) + (uint32_t)idx); }
+    static __device__ __forceinline__ float dot_of_key(uint32_t k) { return (float)(256 - (int)(k >> 21)); }
+};
 
 template <int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -285,17 +298,12 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
         const int row = pair * 2 * TM + t * TM + trow;
         using A = Acc<KIND>;
         using T = typename A::T;
-        T a1 = A::neg(), a2 = A::neg();
-        int i1 = -1, i2 = -1;
-        // exact insertion of one candidate, branch-free.  Candidates reach a thread in increasing index order, so a strictly
-        // larger dot product is OpenCV's strict '<' on the distance with ties kept by the lower index.
-        auto insert = [&](T a, int idx) {
-            const bool gt1 = a > a1, gt2 = a > a2;
-            a2 = gt1 ? a1 : (gt2 ? a : a2);
-            i2 = gt1 ? i1 : (gt2 ? idx : i2);
-            a1 = gt1 ? a : a1;
-            i1 = gt1 ? idx : i1;
-        };
+        // Per thread: the two smallest keys seen, key = hamming << 22 | index = (256 - dot) << 21 | index -- the lexicographic
+        // (distance, index) order of OpenCV's insertion as ONE unsigned compare, so the insertion itself is three min / max and
+        // needs no order of arrival.  thr = the dot product of the current second best: a candidate can only matter if its dot
+        // product is strictly above it (its index is larger than everything this thread has seen).
+        uint32_t k0 = NONE, k1 = NONE;
+        T thr = A::neg();
         auto max3 = [](T x, T y, T z) { return max(max(x, y), z); };
         auto scan32 = [&](int (&vb)[32], int n0) {
             T v[32];
@@ -305,17 +313,18 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
 #pragma unroll
                 for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();
             }
-            T g[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                g[k] = max3(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), max(v[8 * k + 6], v[8 * k + 7]));
-            if (max(max(g[0], g[1]), max(g[2], g[3])) > a2) {
+            for (int k = 0; k < 4; k++) {
+                const T g = max3(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), max(v[8 * k + 6], v[8 * k + 7]));
+                if (g > thr) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (g[k] > a2) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) insert(v[8 * k + j], n0 + 8 * k + j);
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t key = A::key(v[8 * k + j], n0 + 8 * k + j);
+                        const uint32_t hi = max(k0, key);
+                        k0 = min(k0, key);
+                        k1 = min(k1, hi);
                     }
+                    thr = A::dot_of_key(k1);
                 }
             }
         };
@@ -344,24 +353,15 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
             scan32(vb1, n0 + 32);
         }
         // merge the two column halves of a row: the upper half hands its pair over through shared memory
-        if (half == 1) B.xchg[t * TM + trow] = make_int4(A::to_int(a1), i1, A::to_int(a2), i2);
+        if (half == 1) B.xchg[t * TM + trow] = make_uint2(k0, k1);
         bar_sync_named(1, EPI_WARPS * 32);
         if (half == 0 && row < total) {
             const int slot = rowmap ? rowmap[row] : row;
             if (slot >= 0) {
-                const int4 o = B.xchg[t * TM + trow];
-                // keys: (256 - dot) << 21 == hamming << 22, index in the low bits -> the lexicographic (distance, index) order
-                // of OpenCV's insertion is an unsigned min
-                auto key = [](int a, int idx) { return idx >= 0 ? (((uint32_t)(256 - a)) << 21) | (uint32_t)idx : NONE; };
-                uint32_t k[4] = {key(A::to_int(a1), i1), key(A::to_int(a2), i2), key(o.x, o.y), key(o.z, o.w)};
-                uint32_t b0 = NONE, b1 = NONE;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (k[c] < b1) {
-                        if (k[c] < b0) { b1 = b0; b0 = k[c]; }
-                        else b1 = k[c];
-                    }
-                }
+                const uint2 o = B.xchg[t * TM + trow];
+                const uint32_t hi = max(k0, o.x);
+                const uint32_t b0 = min(k0, o.x);
+                const uint32_t b1 = min(min(k1, o.y), hi);
                 partial[(size_t)slot * nchunks + chunk] = make_uint2(b0, b1);
             }
         }
@@ -375,7 +375,7 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
 
 // ---------------------------------------------------------------------------------------------- host side
 int alva_g_knn_mma = 1;        // alva_set_option("knn_mma", 0 never | 1 automatic (large query sets) | 2 always)
-int alva_g_knn_mma_kind = 1;   // alva_set_option("knn_mma_kind", 0 int8 operands / int32 accumulators | 1 E4M3 operands / fp32 accumulators)
+int alva_g_knn_mma_kind = 0;   // alva_set_option("knn_mma_kind", 0 int8 operands / int32 accumulators | 1 E4M3 operands / fp32 accumulators)
 int alva_g_knn_mma_mode = 0;   // alva_set_option("knn_mma_mode", 0 no swizzle | 1 128-byte swizzle | 2 debugging variant of 0)
 
 int alva_knn2_merge_launch(alva_ctx* ctx, const uint2* partial, int nq, int nchunks, int32_t* out, const int32_t* counts, int qcap);

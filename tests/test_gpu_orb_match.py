@@ -155,7 +155,7 @@ def knn_mma(gpu_ctx):
     yield gpu_ctx
     gpu_ctx.L.alva_set_option(b"knn_mma", 1)
     gpu_ctx.L.alva_set_option(b"knn_mma_mode", 0)
-    gpu_ctx.L.alva_set_option(b"knn_mma_kind", 1)
+    gpu_ctx.L.alva_set_option(b"knn_mma_kind", 0)
 
 
 @pytest.mark.parametrize("kind,mode", [(1, 0), (1, 1), (0, 0), (0, 1)])
