@@ -309,9 +309,10 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
             T v[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = A::from_bits(vb[j]);
-            if (n0 + 32 > nt) {
+            const bool tail = n0 + 32 > nt;   // only the last train tile: columns past nt hold the dot products of zero rows
+            if (tail) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();
+                for (int j = 0; j < 32; j++) if (n0 + j >= nt) v[j] = A::neg();   // below every threshold: never opens a group
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -319,7 +320,8 @@ knn2_mma_kernel(const uint8_t* __restrict__ Aexp, const uint8_t* __restrict__ Be
                 if (g > thr) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const uint32_t key = A::key(v[8 * k + j], n0 + 8 * k + j);
+                        uint32_t key = A::key(v[8 * k + j], n0 + 8 * k + j);
+                        if (tail && n0 + 8 * k + j >= nt) key = NONE;
                         const uint32_t hi = max(k0, key);
                         k0 = min(k0, key);
                         k1 = min(k1, hi);

@@ -17,6 +17,7 @@
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
 #include "init_core.h"
+#include "lmdif_core.h"
 #include <limits>
 #include <random>
 #include <vector>
@@ -33,6 +34,7 @@ struct EssentialParams {
     int max_iter; int optimize; double threshold;
     const int32_t* rnd; int table_len;
     double* Rt; uint8_t* outlier; double* info;
+    double* work; int32_t* inl;   // optimize == 2: [nprob][8 * cap] doubles + [nprob][cap] inlier indices for the MINPACK-style refinement
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -126,7 +128,29 @@ __global__ void __launch_bounds__(INIT_THREADS) essential_kernel(const Essential
     const int m = (int)(block_sum((double)mine, red) + 0.5);
     if (tid == 0 && info) { info[0] = m >= 10 ? 1 : 0; info[1] = m; info[2] = rs.iterations; info[3] = rs.draws; }
     if (m < 10) return;   // multi_view_geometry.cpp:283-286: fewer than 10 inliers -> false
-    if (P.optimize) {
+    if (P.optimize == 2) {
+        // the reference's own minimiser restated (lmdif_core.h): MINPACK Levenberg-Marquardt on a forward-difference Jacobian,
+        // ftol = xtol = 10 eps, maxfev 1000 (relative_pose/methods.cpp:1152-1177).  One thread: the stage runs once per session.
+        __syncthreads();
+        if (tid == 0) {
+            int32_t* inl = P.inl + (size_t)prob * P.cap;
+            int mm = 0;
+            for (int i = 0; i < n; i++) if (!outlier[i]) inl[mm++] = i;
+            double x[6];
+            for (int i = 0; i < 3; i++) x[i] = bestm[9 + i];
+            rot2cayley(bestm, x + 3);
+            double* w = P.work + (size_t)prob * P.cap * 8;
+            auto fun = [&](const double* xx, double* f) {
+                double R[9];
+                cayley2rot(xx + 3, R);
+                for (int i = 0; i < mm; i++) f[i] = relpose_dist(R, xx, bv1 + 3 * inl[i], bv2 + 3 * inl[i]);
+            };
+            alva_lm::lmdif(fun, mm, x, w, w + mm, w + 7 * (size_t)mm, 10 * DBL_EPSILON, 10 * DBL_EPSILON, 1000);
+            for (int i = 0; i < 3; i++) bestm[9 + i] = x[i];
+            cayley2rot(x + 3, bestm);
+        }
+        __syncthreads();
+    } else if (P.optimize) {
         if (tid == 0) { for (int i = 0; i < 3; i++) xs[i] = bestm[9 + i]; rot2cayley(bestm, xs + 3); }
         __syncthreads();
         double local = 0;
@@ -231,8 +255,12 @@ extern "C" int alva_k_essential_5pt(alva_ctx* ctx, int nprob, int cap, const dou
     P.bv1 = bv1; P.bv2 = bv2; P.counts = counts; P.cap = cap; P.max_iter = max_iter; P.optimize = optimize;
     P.table_len = 8 * (11 * max_iter + 3 * CHUNK);
     const size_t tab_b = ((size_t)P.table_len * 4 + 255) & ~(size_t)255;
-    int32_t* tab = (int32_t*)alva_scratch(ctx, tab_b);
-    if (!tab) return ALVA_E_CUDA;
+    const size_t work_b = optimize == 2 ? (size_t)nprob * cap * 8 * sizeof(double) : 0;
+    const size_t inl_b = optimize == 2 ? (((size_t)nprob * cap * 4 + 255) & ~(size_t)255) : 0;
+    uint8_t* scr = (uint8_t*)alva_scratch(ctx, tab_b + work_b + inl_b);
+    if (!scr) return ALVA_E_CUDA;
+    int32_t* tab = (int32_t*)scr;
+    P.work = (double*)(scr + tab_b); P.inl = (int32_t*)(scr + tab_b + work_b);
     P.rnd = tab; P.Rt = Rt_out; P.outlier = outlier; P.info = info;
     static thread_local std::vector<int32_t> host_tab;
     static thread_local uint32_t host_seed = 0;

@@ -223,7 +223,7 @@ class Context:
                       fx=1.0, fy=1.0, seed=12345):
         """MultiViewGeometry::compute5ptEssentialMatrix (Nister 5-point RANSAC + refinement), batched -- see alva_k_essential_5pt."""
         self._chk(self.L.alva_k_essential_5pt(self.h, nprob, cap, _ptr(bv1), _ptr(bv2), _ptr(counts), max_iter, err_px,
-                                              1 if optimize else 0, fx, fy, seed, _ptr(Rt_out), _ptr(outlier), _ptr(info)))
+                                              int(optimize), fx, fy, seed, _ptr(Rt_out), _ptr(outlier), _ptr(info)))
 
     def triangulate(self, Tlr, bvl, bvr, n, out):
         """MultiViewGeometry::triangulate (mid-point) for n bearing-vector pairs -- see alva_k_triangulate."""

@@ -212,7 +212,12 @@ int alva_k_pnp(alva_ctx*, int nprob, int cap, const double* K, const double* uv,
  * the current frame (only the first counts[p] are live; counts may be NULL; cap <= 8192).  seed as in alva_k_p3p_lmeds.
  * Rt_out [nprob][12]: [Rwc | twc] 3x4 row-major, twc NOT normalised (the caller normalises it, visual_frontend.cpp:547);
  * written only on success.  outlier [nprob][cap] (1 = outlier / dead slot).  info (optional) [nprob][4] = {success, #inliers,
- * #RANSAC iterations, #draws}. */
+ * #RANSAC iterations, #draws}.
+ * optimize: 0 = RANSAC model only; 1 = refinement by Levenberg-Marquardt on central differences (block-parallel; the default
+ * of `System`: it converges to the cost's minimum and is insensitive to rounding noise); 2 = the reference's own minimiser
+ * restated -- MINPACK LM on a forward-difference Jacobian, ftol = xtol = 10 eps (csrc/lmdif_core.h; one thread).  The
+ * reference's end point is noise-limited (its Jacobian carries ~10 % rounding noise): modes 1 and 2 both end as far from it as
+ * the reference ends from itself when it is rebuilt with other compiler flags. */
 int alva_k_essential_5pt(alva_ctx*, int nprob, int cap, const double* bv1, const double* bv2, const int32_t* counts,
                          int max_iter, float err_px, int optimize, float fx, float fy, uint32_t seed, double* Rt_out,
                          uint8_t* outlier, double* info);

@@ -14,6 +14,14 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 REF=${ALVA_REFERENCE:-/root/reference}
 P=${ALVA_REF_PREFIX:-/tmp/probe}
 OUT="$HERE/_ref"
+# ALVA_REF_VARIANT=fma builds a SECOND copy of the reference, libalva_ref_fma.so, with FMA contraction enabled for AlvaAR's own
+# sources and OpenGV (-O2 -mfma -ffp-contract=fast: what gcc does by default on aarch64, and what -march=native does on x86;
+# -U__AVX__ -U__FMA__ keeps Eigen on the SSE2 packet types the prebuilt Ceres / OpenCV objects use -- only the contraction changes).
+# Same sources, another legitimate build: tools/make_golden_system.py stores how far the two builds' trajectories are apart
+# (ref_alt_*), the yardstick for the free-running pose tolerance.  Never shipped, never timed.
+VARIANT=${ALVA_REF_VARIANT:-}
+XFLAGS=""; LIBNAME=libalva_ref.so; GVDIR=opengv
+if [ "$VARIANT" = fma ]; then XFLAGS="-mfma -ffp-contract=fast -U__AVX__ -U__FMA__"; LIBNAME=libalva_ref_fma.so; GVDIR=opengv_fma; fi
 [ -d "$REF/src/slam/src" ] || { echo "reference tree not found at $REF" >&2; exit 3; }
 mkdir -p "$OUT" "$P"
 J=${JOBS:-$(nproc)}
@@ -52,14 +60,14 @@ EOS
 fi
 # OpenGV 1.0 (P3P-Kneip / LMedS for the per-frame pose): its own CMake flags (-march=native -O3) produce a library that
 # crashes under gcc 13, so the sources are compiled directly, in place, with plain -O2.
-if [ ! -f "$P/opengv/libopengv.a" ]; then
-  mkdir -p "$P/opengv/obj"
+if [ ! -f "$P/$GVDIR/libopengv.a" ]; then
+  mkdir -p "$P/$GVDIR/obj"
   GV="$REF/src/libs/opengv"
   find "$GV/src" -name '*.cpp' | grep -v -i -e python -e matlab | while read -r f; do
-    o="$P/opengv/obj/$(echo "${f#$GV/src/}" | tr '/' '_' | sed 's/\.cpp$/.o/')"
-    echo "g++ -std=c++17 -O2 -w -fPIC -fno-strict-aliasing -I$GV/include -I$REF/src/libs/eigen -I$REF/src/libs/eigen/unsupported -c $f -o $o"
+    o="$P/$GVDIR/obj/$(echo "${f#$GV/src/}" | tr '/' '_' | sed 's/\.cpp$/.o/')"
+    echo "g++ -std=c++17 -O2 $XFLAGS -w -fPIC -fno-strict-aliasing -I$GV/include -I$REF/src/libs/eigen -I$REF/src/libs/eigen/unsupported -c $f -o $o"
   done | xargs -P "$J" -I{} sh -c '{}'
-  ar rcs "$P/opengv/libopengv.a" "$P"/opengv/obj/*.o
+  ar rcs "$P/$GVDIR/libopengv.a" "$P"/$GVDIR/obj/*.o
 fi
 INC="-I$REF/src/slam/src -I$REF/src/libs/opencv/modules/highgui/include -I$REF/src/libs/opencv/modules/imgcodecs/include -I$REF/src/libs/opencv/modules/videoio/include -I$REF/src/libs/opengv/include -I$P/ocv_install/include/opencv4 -I$REF/src/libs/eigen -I$REF/src/libs/Sophus \
  -I$P/ceres_install/include -I$P/ceres_install/include/ceres/internal/miniglog"
@@ -88,19 +96,19 @@ for f in camera_calibration ceres_parametrization feature_extractor feature_trac
          multi_view_geometry optimizer state system utils visual_frontend; do
   src="$REF/src/slam/src/$f.cpp"
   [ -f "$OUT/patched/$f.cpp" ] && src="$OUT/patched/$f.cpp"
-  echo "g++ -std=c++20 -O2 -w -fPIC -c $src -o $OUT/$f.o $INC"
+  echo "g++ -std=c++20 -O2 $XFLAGS -w -fPIC -c $src -o $OUT/$f.o $INC"
   OBJS="$OBJS $f.o"
 done | xargs -P "$J" -I{} sh -c '{}'
 for f in camera_calibration ceres_parametrization feature_extractor feature_tracker frame map_manager map_point mapper \
          multi_view_geometry optimizer state system utils visual_frontend; do OBJS="$OBJS $f.o"; done
 g++ -std=c++17 -O2 -w -fPIC -c "$HERE/ref_harness.cpp" -o ref_harness.o $INC
 g++ -std=c++20 -O2 -w -fPIC -c "$HERE/ref_system.cpp" -o ref_system.o $INC
-g++ -shared -o libalva_ref.so ref_harness.o ref_system.o $OBJS \
+g++ -shared -o $LIBNAME ref_harness.o ref_system.o $OBJS \
   -Wl,--start-group "$P"/ocv_install/lib/libopencv_video.a "$P"/ocv_install/lib/libopencv_calib3d.a \
   "$P"/ocv_install/lib/libopencv_features2d.a "$P"/ocv_install/lib/libopencv_flann.a \
   "$P"/ocv_install/lib/libopencv_imgproc.a "$P"/ocv_install/lib/libopencv_core.a \
-  "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a "$P"/opengv/libopengv.a -Wl,--end-group \
+  "$P"/ocv_install/lib/opencv4/3rdparty/libzlib.a "$P"/ceres_install/lib/libceres.a "$P"/$GVDIR/libopengv.a -Wl,--end-group \
   -lpthread -ldl -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL
 rm -f ref_harness.o ref_system.o $OBJS
 rm -rf "$OUT/patched"
-echo "built $OUT/libalva_ref.so"
+echo "built $OUT/$LIBNAME"

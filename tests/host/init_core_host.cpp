@@ -4,6 +4,7 @@
 // reference.  The serial driver below mirrors essential_kernel's control flow (chunk-free: one hypothesis at a time, which is
 // what the kernel's replay of RansacState amounts to).  Never linked into libalva_b200.so.
 #include "../../alvaar_b200/csrc/init_core.h"
+#include "../../alvaar_b200/csrc/lmdif_core.h"
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -47,7 +48,25 @@ int host_essential_5pt(const double* bv1, const double* bv2, int n, int max_iter
     for (int i = 0; i < n; i++) { const bool in = relpose_dist(bestm, bestm + 9, bv1 + 3 * i, bv2 + 3 * i) < threshold; outlier[i] = !in; m += in; }
     info[0] = m >= 10; info[1] = m;
     if (m < 10) return 0;
-    if (optimize) {
+    if (optimize == 2) {   // the reference's minimiser restated (lmdif_core.h): MINPACK LM on forward differences, ftol = xtol = 10 eps
+        double x[6];
+        for (int i = 0; i < 3; i++) x[i] = bestm[9 + i];
+        rot2cayley(bestm, x + 3);
+        std::vector<int> inl;
+        for (int i = 0; i < n; i++) if (!outlier[i]) inl.push_back(i);
+        const int mm = (int)inl.size();
+        std::vector<double> work((size_t)mm * 8);
+        auto fun = [&](const double* xx, double* f) {
+            double R[9];
+            cayley2rot(xx + 3, R);
+            for (int i = 0; i < mm; i++) f[i] = relpose_dist(R, xx, bv1 + 3 * inl[i], bv2 + 3 * inl[i]);
+        };
+        int nfev = 0;
+        const int st = alva_lm::lmdif(fun, mm, x, work.data(), work.data() + mm, work.data() + 7 * (size_t)mm, 10 * DBL_EPSILON, 10 * DBL_EPSILON, 1000, &nfev);
+        (void)st; (void)nfev;
+        for (int i = 0; i < 3; i++) bestm[9 + i] = x[i];
+        cayley2rot(x + 3, bestm);
+    } else if (optimize) {
         double x[6], xn[6];
         for (int i = 0; i < 3; i++) x[i] = bestm[9 + i];
         rot2cayley(bestm, x + 3);

@@ -36,7 +36,8 @@ def ref_essential(ref, bv1, bv2, K, opt, max_iter=100, err=3.0):
 def host_core():
     """alvaar_b200/csrc/init_core.h (the arithmetic the CUDA kernels run) compiled for the host -- test infrastructure."""
     so = os.path.join(ROOT, "tests", "_build", "libinit_core_host.so")
-    srcs = [os.path.join(ROOT, "tests", "host", "init_core_host.cpp"), os.path.join(ROOT, "alvaar_b200", "csrc", "init_core.h")]
+    srcs = [os.path.join(ROOT, "tests", "host", "init_core_host.cpp"), os.path.join(ROOT, "alvaar_b200", "csrc", "init_core.h"),
+            os.path.join(ROOT, "alvaar_b200", "csrc", "lmdif_core.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, srcs[0]])

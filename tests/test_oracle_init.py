@@ -48,9 +48,11 @@ def test_refined_model_golden(oracle, tag):
 
 
 @pytest.mark.parametrize("tag", TAGS)
-@pytest.mark.parametrize("opt", [0, 1])
+@pytest.mark.parametrize("opt", [0, 1, 2])
 def test_device_arithmetic_on_host_golden(oracle, tag, opt):
-    """init_core.h compiled for the host == the oracle == the reference (same bars)."""
+    """init_core.h compiled for the host == the oracle == the reference (same bars).  opt = 2: the refinement by the reference's
+    own minimiser restated (lmdif_core.h: MINPACK LM on forward differences) -- same bar on the pose; its cost may sit a little
+    above the reference's (both stall in the rounding noise of the forward differences, at different points)."""
     g = golden("init")
     H = host_core()
     bv1, bv2, K = np.ascontiguousarray(g[f"{tag}_bv1"]), np.ascontiguousarray(g[f"{tag}_bv2"]), g[f"{tag}_K"]
@@ -60,7 +62,7 @@ def test_device_arithmetic_on_host_golden(oracle, tag, opt):
     Rt, o, info = np.zeros(12), np.zeros(n, np.uint8), np.zeros(4)
     ok = H.host_essential_5pt(P(bv1), P(bv2), n, 100, ransac_threshold(K), opt, P(tab), len(tab), P(Rt), P(o), P(info))
     assert ok == 1 and info[0] == 1 and (o == g[f"{tag}_outlier"]).all()
-    _, _, _, oinfo = orc_essential(oracle, bv1, bv2, K, opt)
+    _, _, _, oinfo = orc_essential(oracle, bv1, bv2, K, min(opt, 1))
     assert info[1] == oinfo[0] and info[2] == oinfo[1] and info[3] == oinfo[2]          # inliers, iterations, draws
     if opt == 0:
         assert np.abs(Rt - g[f"{tag}_ransac_Rt"]).max() < 1e-9
@@ -68,7 +70,7 @@ def test_device_arithmetic_on_host_golden(oracle, tag, opt):
         tolR, tolt = spread(g, tag)
         dR, dt = pose_error(Rt, g[f"{tag}_refined_Rt"])
         assert dR < tolR and dt < tolt
-        assert refine_cost(Rt, bv1, bv2, o == 0) <= refine_cost(g[f"{tag}_refined_Rt"], bv1, bv2, o == 0) * (1 + 1e-4)
+        assert refine_cost(Rt, bv1, bv2, o == 0) <= refine_cost(g[f"{tag}_refined_Rt"], bv1, bv2, o == 0) * (1 + (1e-4 if opt == 1 else 0.5))
 
 
 def test_fivept_recovers_the_true_essential_matrix(oracle):

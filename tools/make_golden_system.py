@@ -78,7 +78,34 @@ def run_cpu(S, frames, K, hook=None):
     return tr
 
 
+def trace_only(libpath, out):
+    """the reference System trace of another build of the reference (status, Twc, keypoint ids per frame) -> out (npz)"""
+    R = C.CDLL(libpath)
+    R.ref_system_create.restype = C.c_void_p
+    R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
+    R.ref_system_find_camera_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    R.ref_system_keypoints.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    R.ref_system_destroy.argtypes = [C.c_void_p]
+    R.ref_config(0, 1)
+    R.ref_config_time_caps(1)
+    w, h, nf, seed = 640, 480, 100, 7
+    K = synth.intrinsics(w, h)
+    frames, _ = synth.make_frames(nf, w, h, seed=seed, rgba=True)
+    s = R.ref_system_create(w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0)
+    status, Ts, ids_all, start = [], [], [], [0]
+    for k in range(nf):
+        pose = np.zeros(16, np.float32)
+        st = R.ref_system_find_camera_pose(s, P(np.ascontiguousarray(frames[k])), k * 33.333, P(pose))
+        ids = np.zeros(CAP, np.int32); px = np.zeros((CAP, 2), np.float32); d3 = np.zeros(CAP, np.uint8); wp = np.zeros((CAP, 3)); T = np.zeros(7)
+        n = R.ref_system_keypoints(s, P(ids), P(px), P(d3), P(wp), CAP, P(T))
+        status.append(st); Ts.append(T.copy()); ids_all.append(ids[:n].copy()); start.append(start[-1] + n)
+    R.ref_system_destroy(s)
+    np.savez(out, status=np.array(status, np.int32), Twc=np.array(Ts), ids=np.concatenate(ids_all), start=np.array(start, np.int32))
+
+
 def main():
+    if len(sys.argv) == 4 and sys.argv[1] == "--trace":
+        return trace_only(sys.argv[2], sys.argv[3])
     R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libalva_ref.so"))
     R.ref_system_create.restype = C.c_void_p
     R.ref_system_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 8
@@ -115,7 +142,7 @@ def main():
         print(k, "status", st, "keypoints", n, "3-D", int(d3[:n].sum()), "keyframe", info[1])
     R.ref_system_destroy(s)
     d.update(tr.dump("ref_"))
-    # The reference's OWN sensitivity on this trace: the same run with one intrinsic moved by one ulp (every bearing vector
+    # The reference's OWN sensitivity on this trace: the same run with one intrinsic moved by one or two ulps (16 runs; every bearing vector
     # then changes in its last bit).  Its 5-point refinement is noise-limited (tests/test_oracle_init.py), so the trajectory
     # the reference itself produces moves by `ref_spread_*` -- no independent implementation can be asked to sit closer to
     # `ref_Twc` than the reference sits to itself.  Stored per frame: max over the perturbed runs of |dt|_inf and of the
@@ -123,9 +150,10 @@ def main():
     base_T = np.array(tr.T)
     spread_t, spread_q, nruns = np.zeros(nf), np.zeros(nf), np.zeros(nf, np.int32)
     for which in range(4):
-        for sgn in (+1, -1):
+        for sgn in (+1, -1, +2, -2):
             Kp = list(K)
-            Kp[which] = float(np.nextafter(K[which], K[which] + sgn))
+            for _ in range(abs(sgn)):
+                Kp[which] = float(np.nextafter(Kp[which], Kp[which] + sgn))
             s2 = R.ref_system_create(w, h, Kp[0], Kp[1], Kp[2], Kp[3], 0, 0, 0, 0)
             alive = True
             for k in range(nf):
@@ -141,9 +169,35 @@ def main():
                 spread_q[k] = max(spread_q[k], float(np.sqrt(max(2.0 * qd, 0.0))))
                 nruns[k] += 1
             R.ref_system_destroy(s2)
+    # ... and under a rebuild: the SAME reference sources compiled with FMA contraction (oracle/build_ref.sh, ALVA_REF_VARIANT=fma:
+    # -O2 -mfma -ffp-contract=fast for AlvaAR's sources and OpenGV -- gcc's default on aarch64, -march=native on x86).  Two
+    # legitimate builds of the reference; how far apart they end up is the floor for any third implementation.
+    alt = os.path.join(ROOT, "oracle", "_ref", "libalva_ref_fma.so")
+    build_t, build_q, build_alive = np.zeros(nf), np.zeros(nf), np.zeros(nf, np.uint8)
+    if os.path.exists(alt):
+        # in its own process: two builds of the same C++ symbols cannot share one
+        tmp = os.path.join(ROOT, "tests", "_build", "alt_trace.npz")
+        os.makedirs(os.path.dirname(tmp), exist_ok=True)
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--trace", alt, tmp])
+        t2 = np.load(tmp)
+        alive = True
+        for k in range(nf):
+            a0, a1 = int(t2["start"][k]), int(t2["start"][k + 1])
+            alive = alive and int(t2["status"][k]) == tr.status[k] and (a1 - a0) == len(tr.ids[k]) and (t2["ids"][a0:a1] == tr.ids[k]).all()
+            if not alive:
+                break
+            T = t2["Twc"][k]
+            build_t[k] = float(np.abs(T[:3] - base_T[k, :3]).max())
+            build_q[k] = float(np.sqrt(max(2.0 * (1.0 - abs(float(np.dot(T[3:], base_T[k, 3:])))), 0.0)))
+            build_alive[k] = 1
+        print("reference (-O2) vs reference (-O2 -mfma -ffp-contract=fast): max |dt|", float(build_t.max()), "max |dq|", float(build_q.max()),
+              "same discrete state for", int(build_alive.sum()), "of", nf, "frames")
+    else:
+        print("oracle/_ref/libalva_ref_fma.so not built (ALVA_REF_VARIANT=fma bash oracle/build_ref.sh): ref_build_* left at zero")
+    d["ref_build_t"], d["ref_build_q"], d["ref_build_alive"] = build_t, build_q, build_alive
     d["ref_spread_t"], d["ref_spread_q"], d["ref_spread_runs"] = spread_t, spread_q, nruns
     print("reference vs itself under a 1-ulp change of one intrinsic: max |dt|", float(spread_t.max()), "max |dq|", float(spread_q.max()),
-          "runs alive at the last frame:", int(nruns[-1]), "of 8")
+          "runs alive at the last frame:", int(nruns[-1]), "of 16")
     d["ref_pose16"] = np.array(pose16)
     d["ref_xy_start"] = np.cumsum([0] + [len(x) for x in xys]).astype(np.int32)
     d["ref_xy"] = np.concatenate(xys)
