@@ -26,6 +26,9 @@ struct alva_ctx {
     size_t ba_ws_bytes = 0;
     void* det_ws = nullptr;         // alva_k_orb_detect's intermediate lists (own allocation, same reason)
     size_t det_ws_bytes = 0;
+    void* p3p_tab = nullptr;        // P3P-LMedS sampler table (depends on seed and length only): resident across calls
+    int p3p_tab_len = 0;
+    uint32_t p3p_tab_seed = 0;
     void* knn_ws = nullptr;         // tensor-core matcher: expanded int8 operand tiles, row map (hamming_mma.cu)
     size_t knn_ws_bytes = 0;
 };

@@ -112,6 +112,7 @@ extern "C" void alva_ctx_destroy(alva_ctx* ctx) {
     if (ctx->ba_ws) cudaFree(ctx->ba_ws);
     if (ctx->det_ws) cudaFree(ctx->det_ws);
     if (ctx->knn_ws) cudaFree(ctx->knn_ws);
+    if (ctx->p3p_tab) cudaFree(ctx->p3p_tab);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

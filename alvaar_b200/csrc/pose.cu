@@ -739,6 +739,71 @@ __global__ void __launch_bounds__(PNP_THREADS) pnp_kernel(const PnpParams P) {
     if (tid == 0) { summ[10] = usable; summ[11] = bad; }
 }
 
+
+// ---- P3P -> PnP hand-over on the device (System's per-frame pose without a host round trip in between) ----------------------
+// What VisualFrontend::computePose does on the host between the two solvers (visual_frontend.cpp:300-357): the P3P pose becomes
+// the PnP start (rotation matrix -> Eigen quaternion), the P3P outliers leave the correspondence list (order kept).
+__global__ void __launch_bounds__(256) pnp_from_p3p_kernel(int cap, const int32_t* __restrict__ counts, int n_fixed,
+                                                           const double* __restrict__ T12, const uint8_t* __restrict__ outl,
+                                                           const double* __restrict__ uv, const double* __restrict__ X,
+                                                           double* __restrict__ uv2, double* __restrict__ X2, int32_t* __restrict__ n2,
+                                                           double* __restrict__ pose7) {
+    __shared__ int woff[8];
+    __shared__ int base_s;
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = counts ? min(counts[prob], cap) : n_fixed;
+    const uint8_t* o = outl + (size_t)prob * cap;
+    const double *u = uv + (size_t)prob * cap * 2, *x = X + (size_t)prob * cap * 3;
+    double *u2 = uv2 + (size_t)prob * cap * 2, *x2 = X2 + (size_t)prob * cap * 3;
+    if (tid == 0) {
+        base_s = 0;
+        // Se3::setR (system_core.h) = Eigen's matrix -> quaternion, then normalised; no contraction (the host compiles it with
+        // -ffp-contract=off)
+        const double* T = T12 + 12 * prob;
+        const double M[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+        double q[4];
+        double tr = __dadd_rn(__dadd_rn(M[0], M[4]), M[8]);
+        if (tr > 0) {
+            tr = sqrt(__dadd_rn(tr, 1.0));
+            q[3] = __dmul_rn(0.5, tr); tr = 0.5 / tr;
+            q[0] = __dmul_rn(__dsub_rn(M[7], M[5]), tr); q[1] = __dmul_rn(__dsub_rn(M[2], M[6]), tr); q[2] = __dmul_rn(__dsub_rn(M[3], M[1]), tr);
+        } else {
+            int i = 0;
+            if (M[4] > M[0]) i = 1;
+            if (M[8] > M[4 * i]) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            tr = sqrt(__dadd_rn(__dsub_rn(__dsub_rn(M[4 * i], M[4 * j]), M[4 * k]), 1.0));
+            q[i] = __dmul_rn(0.5, tr); tr = 0.5 / tr;
+            q[3] = __dmul_rn(__dsub_rn(M[3 * k + j], M[3 * j + k]), tr);
+            q[j] = __dmul_rn(__dadd_rn(M[3 * j + i], M[3 * i + j]), tr);
+            q[k] = __dmul_rn(__dadd_rn(M[3 * k + i], M[3 * i + k]), tr);
+        }
+        const double nn = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], q[0]), __dmul_rn(q[1], q[1])), __dmul_rn(q[2], q[2])), __dmul_rn(q[3], q[3])));
+        double* p = pose7 + 7 * prob;
+        p[0] = T[3]; p[1] = T[7]; p[2] = T[11];
+        for (int c = 0; c < 4; c++) p[3 + c] = q[c] / nn;
+    }
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        const bool keep = i < n && o[i] == 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) woff[warp] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; w++) off += woff[w];
+        if (keep) {
+            const int d = off + __popc(m & ((1u << lane) - 1u));
+            u2[2 * d] = u[2 * i]; u2[2 * d + 1] = u[2 * i + 1];
+            x2[3 * d] = x[3 * i]; x2[3 * d + 1] = x[3 * i + 1]; x2[3 * d + 2] = x[3 * i + 2];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += woff[w]; base_s += t; }
+        __syncthreads();
+    }
+    if (tid == 0) n2[prob] = base_s;
+}
+
 }  // namespace
 
 // SampleConsensusProblem::rnd() for a given seed: std::uniform_int_distribution<int>(0, INT_MAX) over std::mt19937 -- the very
@@ -773,10 +838,17 @@ extern "C" int alva_k_p3p_lmeds(alva_ctx* ctx, int nprob, int cap, const double*
     int32_t* tab = (int32_t*)(ws + hyp_b + pen_b);
     P.rnd = tab; P.nhyp = (int32_t*)(ws + hyp_b + pen_b + tab_b);
     P.Twc = Twc_out; P.outlier = outlier; P.info = info;
-    static thread_local std::vector<int32_t> host_tab;
-    static thread_local uint32_t host_seed = 0;
-    if ((int)host_tab.size() != P.table_len || host_seed != seed) { make_rnd_table(seed, P.table_len, host_tab); host_seed = seed; }
-    ALVA_CUDA(cudaMemcpyAsync(tab, host_tab.data(), (size_t)P.table_len * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // the sampler table depends only on (seed, length): kept on the device across calls (System draws it every frame)
+    if (!ctx->p3p_tab || ctx->p3p_tab_len != P.table_len || ctx->p3p_tab_seed != seed) {
+        std::vector<int32_t> host_tab;
+        make_rnd_table(seed, P.table_len, host_tab);
+        if (ctx->p3p_tab) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->p3p_tab)); ctx->p3p_tab = nullptr; }
+        ALVA_CUDA(cudaMalloc(&ctx->p3p_tab, (size_t)P.table_len * 4));
+        ALVA_CUDA(cudaMemcpy(ctx->p3p_tab, host_tab.data(), (size_t)P.table_len * 4, cudaMemcpyHostToDevice));
+        ctx->p3p_tab_len = P.table_len; ctx->p3p_tab_seed = seed;
+    }
+    (void)tab;
+    P.rnd = (const int32_t*)ctx->p3p_tab;
     p3p_hypotheses_kernel<<<nprob, HYP_THREADS, (size_t)cap * sizeof(int), ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
     int m = 1;
@@ -799,4 +871,17 @@ extern "C" int alva_k_pnp(alva_ctx* ctx, int nprob, int cap, const double* K, co
     pnp_kernel<<<nprob, PNP_THREADS, 0, ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// internal (system.cu): P3P-LMedS -> hand-over -> PnP for ONE problem, everything on the stream, no host synchronisation.
+// bvs / X / uv: the n correspondences (device); K4: calibration (device, 4 doubles); T12 + info: P3P's result ([12] + [4]);
+// o1 [cap]: P3P outliers; uv2 / X2 [cap]: scratch for the surviving correspondences; n2: their count; pose7: PnP start -> result;
+// o2 [cap]: PnP outliers over the survivors; summ [12]: PnP summary.
+int alva_pose_chain_launch(alva_ctx* ctx, int n, int cap, const double* bvs, const double* X, const double* uv, const double* K4,
+                           float fx, float fy, uint32_t seed, double* T12, double* info, uint8_t* o1, double* uv2, double* X2,
+                           int32_t* n2, double* pose7, uint8_t* o2, double* summ, double huber, double chi2) {
+    if (int e = alva_k_p3p_lmeds(ctx, 1, n, bvs, X, nullptr, 100, 3.0f, fx, fy, seed, T12, o1, info)) return e;
+    pnp_from_p3p_kernel<<<1, 256, 0, ctx->stream>>>(cap, nullptr, n, T12, o1, uv, X, uv2, X2, n2, pose7);
+    ALVA_LAUNCH_CHECK(ctx);
+    return alva_k_pnp(ctx, 1, cap, K4, uv2, X2, n2, pose7, huber, chi2, 5, 1, 1, o2, summ);
 }

@@ -27,9 +27,14 @@
 #include "system_core.h"
 #include <chrono>
 #include <exception>
+#include <thread>
+#include <vector>
 
 int alva_scharr_levels_launch(alva_ctx* ctx, int nlev, const uint8_t* const* src, int16_t* const* dst, const int* w, const int* h,
                               int nframes);
+int alva_pose_chain_launch(alva_ctx* ctx, int n, int cap, const double* bvs, const double* X, const double* uv, const double* K4,
+                           float fx, float fy, uint32_t seed, double* T12, double* info, uint8_t* o1, double* uv2, double* X2,
+                           int32_t* n2, double* pose7, uint8_t* o2, double* summ, double huber, double chi2);
 
 namespace {
 
@@ -42,8 +47,44 @@ namespace {
         }                                                                                         \
     } while (0)
 
+// One page-locked host buffer and its device mirror: a stage packs its small inputs into the host side, uploads them with ONE
+// copy, runs its kernels on the mirror and reads the results back with ONE copy.  (The state machine's own containers are
+// pageable std::vectors: copying from them directly costs a driver-side staging pass and an implicit synchronisation per call.)
+struct Staging {
+    uint8_t *h = nullptr, *d = nullptr;
+    size_t cap = 0, off = 0;
+    int init(size_t bytes) {
+        release();
+        if (cudaHostAlloc((void**)&h, bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&d, bytes) != cudaSuccess) {
+            alva_set_error("System: staging allocation of %zu bytes failed (%s)", bytes, cudaGetErrorString(cudaGetLastError()));
+            release();
+            return ALVA_E_CUDA;
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (h) { cudaFreeHost(h); h = nullptr; }
+        if (d) { cudaFree(d); d = nullptr; }
+        cap = off = 0;
+    }
+    void reset() { off = 0; }
+    // n elements of T at the next 256-byte boundary: returns the device pointer, *host receives the host-side twin
+    template <class T> T* take(size_t n, T** host) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = (T*)(d + off);
+        if (host) *host = (T*)(h + off);
+        off += n * sizeof(T);
+        return p;
+    }
+    bool fits(size_t bytes) const { return bytes + 4096 <= cap; }
+};
+
 struct CudaBackend {
     alva_ctx* ctx = nullptr;
+    Staging stg;
+    cudaGraphExec_t pyr_graph[2] = {nullptr, nullptr};   // the pyramid chain of a frame (front end + pyrDown levels + Scharr), per ping-pong side
+    bool graphs_ok = true;
     int device = 0, w = 0, h = 0, nlev = 0, cur = 0, cap = 0;
     int lw[4] = {0, 0, 0, 0}, lh[4] = {0, 0, 0, 0};
     uint8_t* rgba_dev = nullptr;
@@ -87,6 +128,7 @@ struct CudaBackend {
         SYS_CUDA(cudaMalloc(&dbl_dev, ((size_t)cap * 9 + 64) * sizeof(double)));
         const double q0 = 0.001;   // State::extractorMaxQuality_ (state.hpp:59); FeatureExtractor keeps adapting it across resets
         SYS_CUDA(cudaMemcpy(quality_dev, &q0, 8, cudaMemcpyHostToDevice));
+        if (int e = stg.init((size_t)cap * 160 + 65536)) return e;
         return 0;
     }
 
@@ -101,20 +143,47 @@ struct CudaBackend {
                          (void**)&desc_dev, (void**)&dbl_dev};
         for (void** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
         if (arena) { cudaFree(arena); arena = nullptr; arena_cap = 0; }
+        for (int k = 0; k < 2; k++) if (pyr_graph[k]) { cudaGraphExecDestroy(pyr_graph[k]); pyr_graph[k] = nullptr; }
+        graphs_ok = true;
+        stg.release();
         if (ctx) { alva_ctx_destroy(ctx); ctx = nullptr; }
     }
 
-    int pyramid(const uint8_t* rgba) {
-        cudaStream_t st = ctx->stream;
-        cur ^= 1;   // VisualFrontend::preprocessImage swaps prev / cur pyramids (visual_frontend.cpp:672-698)
-        blur_valid = false;
-        SYS_CUDA(cudaMemcpyAsync(rgba_dev, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, st));
+    int pyramid_launches() {
         uint8_t** L = img[cur];
         if (int e = alva_k_frontend(ctx, rgba_dev, w, h, 1, L[0], nlev > 1 ? L[1] : nullptr, nlev > 2 ? L[2] : nullptr,
                                     nlev > 3 ? L[3] : nullptr, 20, nullptr, nullptr, 0, 0))
             return e;
         const uint8_t* srcs[4] = {L[0], L[1], L[2], L[3]};
         return alva_scharr_levels_launch(ctx, nlev, srcs, der[cur], lw, lh, 1);
+    }
+    // The chain is the same 4 launches on the same buffers every other frame: captured once per ping-pong side into a CUDA
+    // graph and replayed with one call (no per-launch driver work, no tensor-map encode, dependent launches back to back).
+    int pyramid(const uint8_t* rgba) {
+        cudaStream_t st = ctx->stream;
+        cur ^= 1;   // VisualFrontend::preprocessImage swaps prev / cur pyramids (visual_frontend.cpp:672-698)
+        blur_valid = false;
+        SYS_CUDA(cudaMemcpyAsync(rgba_dev, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, st));
+        if (graphs_ok && !pyr_graph[cur]) {
+            cudaGraph_t g = nullptr;
+            const long long l0 = ctx->launches;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            int e = 0;
+            if (ok) {
+                e = pyramid_launches();
+                ok = cudaStreamEndCapture(st, &g) == cudaSuccess && e == 0 && g != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&pyr_graph[cur], g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            ctx->launches = l0;
+            if (!ok) { cudaGetLastError(); graphs_ok = false; pyr_graph[cur] = nullptr; }
+        }
+        if (pyr_graph[cur]) {
+            SYS_CUDA(cudaGraphLaunch(pyr_graph[cur], st));
+            ctx->launches += 2 + (nlev > 2 ? nlev - 2 : 0);
+            return 0;
+        }
+        return pyramid_launches();
     }
 
     int detect(const float* cpts, int ncur, std::vector<float>& fresh) {
@@ -158,15 +227,23 @@ struct CudaBackend {
     int klt(const float* pts, float* priors, int n, int levels, uint8_t* good) {
         cudaStream_t st = ctx->stream;
         if (n > cap) { alva_set_error("System: %d keypoints exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
-        SYS_CUDA(cudaMemcpyAsync(pts_dev, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        SYS_CUDA(cudaMemcpyAsync(pri_dev, priors, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        stg.reset();
+        float *hp, *hq;
+        uint8_t* hg;
+        float* dp = stg.take<float>((size_t)2 * n, &hp);
+        float* dq = stg.take<float>((size_t)2 * n, &hq);
+        const size_t q_off = (uint8_t*)dq - stg.d, up_end = stg.off;
+        uint8_t* dg = stg.take<uint8_t>(n, &hg);
+        memcpy(hp, pts, (size_t)n * 8);
+        memcpy(hq, priors, (size_t)n * 8);
+        SYS_CUDA(cudaMemcpyAsync(stg.d, stg.h, up_end, cudaMemcpyHostToDevice, st));
         const int prev = cur ^ 1;
-        if (int e = alva_k_klt_fb(ctx, img[prev], der[prev], img[cur], der[cur], w, h, 1, nlev - 1, levels, 9, 30.0f, 0.5f, pts_dev, pri_dev,
-                                  nullptr, n, flag_dev))
+        if (int e = alva_k_klt_fb(ctx, img[prev], der[prev], img[cur], der[cur], w, h, 1, nlev - 1, levels, 9, 30.0f, 0.5f, dp, dq, nullptr, n, dg))
             return e;
-        SYS_CUDA(cudaMemcpyAsync(priors, pri_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        SYS_CUDA(cudaMemcpyAsync(good, flag_dev, n, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaMemcpyAsync(stg.h + q_off, stg.d + q_off, stg.off - q_off, cudaMemcpyDeviceToHost, st));
         SYS_CUDA(cudaStreamSynchronize(st));
+        memcpy(priors, hq, (size_t)n * 8);
+        memcpy(good, hg, n);
         return 0;
     }
 
@@ -229,6 +306,47 @@ struct CudaBackend {
         SYS_CUDA(cudaStreamSynchronize(st));
         memcpy(pose7, host + 4, 56);
         return host[16 + 10] != 0.0 ? 1 : 0;
+    }
+
+    // P3P-LMedS + hand-over + PnP of one frame with one upload, one download and ONE synchronisation (system_core.h replays the
+    // host-side decisions of VisualFrontend::computePose on the results).  T12 [12] / ok1: P3P; o1 [n]: its outliers; pose7 / ok2:
+    // PnP started from the P3P pose on the survivors; o2 [n - #o1]: its outliers, in the survivors' order.
+    bool has_pose_chain() const { return true; }
+    int pose_chain(const double* bv, const double* X, const double* uv, int n, const double* K4, float fxf, float fyf, double* T12,
+                   uint8_t* o1, int& ok1, double* pose7, uint8_t* o2, int& ok2) {
+        cudaStream_t st = ctx->stream;
+        if (n > cap) { alva_set_error("System: %d points exceed the frame capacity %d", n, cap); return ALVA_E_CAPACITY; }
+        stg.reset();
+        double *hb, *hx, *hu, *hk, *hs;
+        uint8_t *ho1, *ho2;
+        double* db = stg.take<double>((size_t)3 * n, &hb);
+        double* dx = stg.take<double>((size_t)3 * n, &hx);
+        double* du = stg.take<double>((size_t)2 * n, &hu);
+        double* dk = stg.take<double>(4, &hk);
+        const size_t up_end = stg.off;
+        double* ds = stg.take<double>(48, &hs);            // [0,12) T12  [12,16) P3P info  [16,23) pose7  [24,36) PnP summary  [40] n2
+        const size_t down_off = (uint8_t*)ds - stg.d;
+        uint8_t* d1 = stg.take<uint8_t>(n, &ho1);
+        uint8_t* d2 = stg.take<uint8_t>(n, &ho2);
+        const size_t down_end = stg.off;
+        double* du2 = stg.take<double>((size_t)2 * n, (double**)nullptr);
+        double* dx2 = stg.take<double>((size_t)3 * n, (double**)nullptr);
+        if (!stg.fits(stg.off)) { alva_set_error("System: staging buffer too small for %d points", n); return ALVA_E_CAPACITY; }
+        memcpy(hb, bv, (size_t)n * 24); memcpy(hx, X, (size_t)n * 24); memcpy(hu, uv, (size_t)n * 16); memcpy(hk, K4, 32);
+        SYS_CUDA(cudaMemcpyAsync(stg.d, stg.h, up_end, cudaMemcpyHostToDevice, st));
+        const float chi2 = 5.9915f;   // State::robustCostThreshold_; ceresPnP: Huber width std::sqrt(float)
+        if (int e = alva_pose_chain_launch(ctx, n, n, db, dx, du, dk, fxf, fyf, 12345u, ds, ds + 12, d1, du2, dx2, (int32_t*)(ds + 40), ds + 16, d2,
+                                           ds + 24, (double)sqrtf(chi2), (double)chi2))
+            return e;
+        SYS_CUDA(cudaMemcpyAsync(stg.h + down_off, stg.d + down_off, down_end - down_off, cudaMemcpyDeviceToHost, st));
+        SYS_CUDA(cudaStreamSynchronize(st));
+        memcpy(T12, hs, 96);
+        ok1 = hs[12] != 0.0 ? 1 : 0;
+        memcpy(pose7, hs + 16, 56);
+        ok2 = hs[24 + 10] != 0.0 ? 1 : 0;
+        memcpy(o1, ho1, n);
+        memcpy(o2, ho2, n);
+        return 0;
     }
 
     // ---- variable-size problems (local BA, local-map matching): one growable device arena, bump-allocated per call
@@ -553,3 +671,25 @@ extern "C" int alva_system_pin_buffer(alva_system* s, void* host_ptr, size_t byt
 extern "C" int alva_system_unpin_buffer(alva_system* s, void* host_ptr) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && host_ptr) ? s->sys.unpinBuffer(host_ptr) : ALVA_E_INVALID; }
 extern "C" int alva_system_get_pose(alva_system* s, double* Twc7) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && Twc7) ? s->sys.getPose(Twc7) : ALVA_E_INVALID; }
 extern "C" int alva_system_get_info(alva_system* s, int32_t* out8) { AlvaDeviceGuard guard__(s ? s->sys.device_ : -1); return (s && out8) ? s->sys.getInfo(out8) : ALVA_E_INVALID; }
+
+// N independent camera streams in one call: handles[i] processes rgba[i] (time stamp t_ms[i]; t_ms may be NULL = the system
+// clock); poses16 [n][16], status [n] = the per-stream return value of alva_system_find_camera_pose_ts.  Every System owns its
+// CUDA stream and its state, so the streams run concurrently on the device: the call drives them from n host threads (the last
+// one is the caller's) and returns when all are done.  Returns 0, or the first negative status.
+extern "C" int alva_system_find_camera_pose_batch(alva_system* const* handles, const uint8_t* const* rgba, const double* t_ms, int n,
+                                                  float* poses16, int* status) {
+    if (!handles || !rgba || !poses16 || !status || n < 1) { alva_set_error("alva_system_find_camera_pose_batch: bad argument"); return ALVA_E_INVALID; }
+    for (int i = 0; i < n; i++)
+        if (!handles[i] || !rgba[i]) { alva_set_error("alva_system_find_camera_pose_batch: null handle / frame %d", i); return ALVA_E_INVALID; }
+    auto one = [&](int i) {
+        AlvaDeviceGuard guard__(handles[i]->sys.device_);
+        status[i] = t_ms ? handles[i]->sys.findCameraPose(rgba[i], t_ms[i], poses16 + 16 * (size_t)i) : handles[i]->sys.findCameraPose(rgba[i], poses16 + 16 * (size_t)i);
+    };
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (int i = 0; i + 1 < n; i++) th.emplace_back(one, i);
+    one(n - 1);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++) if (status[i] < 0) return status[i];
+    return 0;
+}

@@ -30,6 +30,8 @@
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
+#include <type_traits>
+#include <utility>
 #include <map>
 #include <memory>
 #include <set>
@@ -400,6 +402,11 @@ struct MotionModel {   // visual_frontend.hpp:17-56
     }
     void reset() { prevTime = -1.; for (int i = 0; i < 6; i++) logRel[i] = 0; }
 };
+
+// a Backend may offer the fused per-frame pose sequence (pose_chain); backends without it (the CPU oracle backend of the test
+// suite) go through p3p() and pnp() one after the other -- both paths take the same decisions on the same numbers
+template <class B, class = void> struct BackendHasPoseChain : std::false_type {};
+template <class B> struct BackendHasPoseChain<B, std::void_t<decltype(std::declval<B&>().has_pose_chain())>> : std::true_type {};
 
 // ------------------------------------------------------------------------------------------------ flat problems handed to a Backend
 struct BaProblem {   // the layout of alva_k_ba_local
@@ -1197,6 +1204,40 @@ private:
         }
         Se3 Twc = cur.Twc;
         std::vector<uint8_t> outl(ids.size() + 1);
+        if constexpr (BackendHasPoseChain<Backend>::value) if (do_p3p && B.has_pose_chain()) {
+            // Same decisions as below, replayed on the results of ONE device sequence (P3P-LMedS -> outliers dropped, P3P pose as the
+            // PnP start -> PnP): the backend needs no host round trip between the two solvers.
+            const int n = (int)ids.size();
+            const double K4[4] = {(double)(float)cam.fx, (double)(float)cam.fy, (double)(float)cam.cx, (double)(float)cam.cy};
+            double T12[12], pose7[7];
+            std::vector<uint8_t> o2(n + 1);
+            int ok1 = 0, ok2 = 0;
+            const int rc = B.pose_chain(bvs.data(), wpts.data(), uv.data(), n, K4, (float)cam.fx, (float)cam.fy, T12, outl.data(), ok1, pose7, o2.data(), ok2);
+            if (rc < 0) { err = rc; return false; }
+            int nout = 0;
+            for (int i = 0; i < n; i++) nout += outl[i] != 0;
+            const double tt[3] = {T12[3], T12[7], T12[11]};
+            if (!ok1 || n - nout < 5 || !finite3(tt)) { resetFrame(); return false; }
+            const double Rm[9] = {T12[0], T12[1], T12[2], T12[4], T12[5], T12[6], T12[8], T12[9], T12[10]};
+            Twc.setR(Rm);
+            Twc.t[0] = tt[0]; Twc.t[1] = tt[1]; Twc.t[2] = tt[2];
+            cur.setTwc(Twc);
+            std::vector<int> ids2;
+            ids2.reserve(n);
+            for (int i = 0; i < n; i++) {
+                if (outl[i]) { removeObsFromCurr(ids[i]); continue; }
+                ids2.push_back(ids[i]);
+            }
+            const int n2 = (int)ids2.size();
+            int nout2 = 0;
+            for (int i = 0; i < n2; i++) nout2 += o2[i] != 0;
+            if (!ok2 || n2 - nout2 < 5 || nout2 > 0.5 * n2 || !finite3(pose7)) { resetFrame(); return false; }
+            cur.setTwc(Se3::from7(pose7));
+            p3p_req = false;
+            for (int i = 0; i < n2; i++)
+                if (o2[i]) removeObsFromCurr(ids2[i]);
+            return true;
+        }
         if (do_p3p) {
             double T12[12];
             const int n = (int)ids.size();

@@ -483,9 +483,9 @@ def system_api_times(with_reference):
 
 
 def system_concurrent_streams(nstreams, w, h, nf):
-    """nstreams independent System handles (one camera stream each, own CUDA stream) driven from nstreams host threads on ONE
-    GPU, every call a host-RGBA findCameraPose: aggregate frames/s, and a determinism check -- all streams see the same frames,
-    so they must report bit-identical poses."""
+    """nstreams independent System handles (one camera stream each, own CUDA stream) on ONE GPU, driven through the batched entry
+    point (alva_system_find_camera_pose_batch: one call per frame step, host RGBA in): aggregate frames/s, and a determinism
+    check -- all streams see the same frames, so they must report bit-identical poses."""
     import ctypes as C
     import alvaar_b200
     from alvaar_b200 import synth
@@ -502,28 +502,32 @@ def system_concurrent_streams(nstreams, w, h, nf):
         s = C.c_void_p(L.alva_system_create(0))
         assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
         handles.append(s)
+    L.alva_system_pin_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    fr_all = np.ascontiguousarray(np.stack(frames))      # one page-locked block for the sequence (registration is process-wide)
+    frames = [fr_all[k] for k in range(nf)]
+    pinned = L.alva_system_pin_buffer(handles[0], fr_all.ctypes.data_as(C.c_void_p), fr_all.nbytes) == 0
     poses = [np.zeros((nf, 16), np.float32) for _ in range(nstreams)]
     status = [np.zeros(nf, np.int32) for _ in range(nstreams)]
-    start = threading.Barrier(nstreams + 1)
-
-    def run(i):
-        start.wait()
-        for k in range(nf):
-            status[i][k] = L.alva_system_find_camera_pose_ts(handles[i], frames[k].ctypes.data_as(C.c_void_p), k * 33.333,
-                                                             poses[i][k].ctypes.data_as(C.c_void_p))
-    th = [threading.Thread(target=run, args=(i,)) for i in range(nstreams)]
-    for t in th:
-        t.start()
-    start.wait()
+    # all streams through ONE call per frame step (alva_system_find_camera_pose_batch: one host thread per stream inside the library)
+    L.alva_system_find_camera_pose_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    harr = (C.c_void_p * nstreams)(*[s.value for s in handles])
+    bp = np.zeros((nstreams, 16), np.float32)
+    bs = np.zeros(nstreams, np.int32)
     t0 = time.perf_counter()
-    for t in th:
-        t.join()
+    for k in range(nf):
+        parr = (C.c_void_p * nstreams)(*[frames[k].ctypes.data] * nstreams)
+        ts = np.full(nstreams, k * 33.333)
+        L.alva_system_find_camera_pose_batch(harr, parr, ts.ctypes.data_as(C.c_void_p), nstreams, bp.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p))
+        for i in range(nstreams):
+            poses[i][k] = bp[i]
+            status[i][k] = bs[i]
     dt = time.perf_counter() - t0
     for s in handles:
         L.alva_system_destroy(s)
     same = all(np.array_equal(poses[0], p) and np.array_equal(status[0], st) for p, st in zip(poses, status))
     return {"streams": nstreams, "frame": f"{w}x{h}", "frames_per_stream": nf, "aggregate_frames_per_sec": float(nstreams * nf / dt),
-            "all_streams_bit_identical": bool(same), "final_status": int(status[0][-1])}
+            "all_streams_bit_identical": bool(same), "final_status": int(status[0][-1]), "input_pinned": bool(pinned),
+            "api": "alva_system_find_camera_pose_batch"}
 
 
 def system_api_times_at(w, h, nf, with_reference):

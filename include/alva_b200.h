@@ -392,6 +392,12 @@ int  alva_system_unpin_buffer(alva_system*, void* host_ptr);
  * returns instead of running alva_k_essential_5pt -- used by the parity tests to plug in the reference's own initialisation
  * result (whose refinement is noise-limited) and check everything downstream of it at 1e-7; ignored when n does not
  * match the number of correspondences of that initialisation. */
+/* N independent camera streams in one call (streams are independent, System holds all state): handles[i]
+ * processes the frame rgba[i] with time stamp t_ms[i] (t_ms NULL = the system clock).  poses16 [n][16], status [n] (the value
+ * alva_system_find_camera_pose_ts would return for that stream).  The streams run concurrently on the device (every System
+ * owns a CUDA stream).  Returns 0, or the first negative status. */
+int  alva_system_find_camera_pose_batch(alva_system* const* handles, const uint8_t* const* rgba, const double* t_ms, int n,
+                                        float* poses16, int* status);
 int  alva_system_debug_set_initialisation(alva_system*, const double* Rt12, const uint8_t* outlier, int n);
 /* the current frame's camera-to-world pose in double: [t, q(x,y,z,w)] */
 int  alva_system_get_pose(alva_system*, double* Twc7);

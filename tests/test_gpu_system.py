@@ -241,3 +241,42 @@ def test_python_system_class():
     s.reset()
     assert s.info()["keypoints"] == 0
     s.close()
+
+
+def test_system_batch_entry_point_equals_single_calls():
+    """alva_system_find_camera_pose_batch: four independent streams (two sequences, each twice) through one call per frame step
+    give, per stream, exactly what alva_system_find_camera_pose_ts gives a single System -- status and float[16] pose bits."""
+    w, h, nf = 640, 480, 30
+    K = synth.intrinsics(w, h)
+    seqs = [synth.make_frames(nf, w, h, seed=sd, rgba=True)[0] for sd in (7, 11)]
+    L = bind()
+    L.alva_system_find_camera_pose_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    single = []
+    for fr in seqs:
+        s = C.c_void_p(L.alva_system_create(0))
+        assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+        out = []
+        for k in range(nf):
+            pose = np.zeros(16, np.float32)
+            st = L.alva_system_find_camera_pose_ts(s, P(np.ascontiguousarray(fr[k])), k * 33.333, P(pose))
+            out.append((st, pose.copy()))
+        L.alva_system_destroy(s)
+        single.append(out)
+    n = 4
+    hs = [C.c_void_p(L.alva_system_create(0)) for _ in range(n)]
+    for s in hs:
+        assert L.alva_system_configure(s, w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0) == 0
+    harr = (C.c_void_p * n)(*[s.value for s in hs])
+    for k in range(nf):
+        fr = [np.ascontiguousarray(seqs[i % 2][k]) for i in range(n)]
+        parr = (C.c_void_p * n)(*[f.ctypes.data for f in fr])
+        ts = np.full(n, k * 33.333)
+        poses = np.zeros((n, 16), np.float32)
+        status = np.zeros(n, np.int32)
+        assert L.alva_system_find_camera_pose_batch(harr, parr, P(ts), n, P(poses), P(status)) == 0
+        for i in range(n):
+            st, pose = single[i % 2][k]
+            assert status[i] == st and (poses[i].view(np.uint32) == pose.view(np.uint32)).all(), (k, i)
+    assert single[0][-1][0] == 1                        # the sequences do initialise and track
+    for s in hs:
+        L.alva_system_destroy(s)
