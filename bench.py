@@ -30,18 +30,65 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# workloads (BASELINE.json configs): c2 = the headline (1280x720, 1000 features; `metric` is quoted on it), c3 = 1920x1080 with
+# 2000 features through the same pipeline.  --config selects; the module constants below are the selected workload's.
+CONFIGS = {"c2": dict(w=1280, h=720, nfeat=1000, batch=64, name="c2_720p_stream+c4_local_ba"),
+           "c3": dict(w=1920, h=1080, nfeat=2000, batch=32, name="c3_1080p_stream+c4_local_ba")}
 W, H = 1280, 720
 BATCH = 64            # frames per step: 64 x 3.69 MB RGBA = 236 MB per step, larger than the 126 MB L2
 NFEAT = 1000
+WORKLOAD = "c2_720p_stream+c4_local_ba"
 MAP_SIZE = 10000
 KF_INTERVAL = 5
 BA_NKF, BA_NLM, BA_OBS_PER_LM, BA_ITERS = 20, 3000, 4, 5
 FAST_THR = 20
 # algorithmic bytes of the fused front-end kernel per frame: RGBA read once + gray + L1 written once
 ALGO_BYTES_FRONTEND = 4 * W * H + W * H + ((W + 1) // 2) * ((H + 1) // 2)
+
+
+METRIC = {"c2": "frames_per_sec_720p_1000orb_20kf_ba", "c3": "frames_per_sec_1080p_2000orb_20kf_ba"}
+
+
+def select_config(name):
+    global W, H, BATCH, NFEAT, WORKLOAD, ALGO_BYTES_FRONTEND
+    c = CONFIGS[name]
+    W, H, BATCH, NFEAT, WORKLOAD = c["w"], c["h"], c["batch"], c["nfeat"], c["name"]
+    ALGO_BYTES_FRONTEND = 4 * W * H + W * H + ((W + 1) // 2) * ((H + 1) // 2)
 # dram__bytes_read.sum + dram__bytes_write.sum of one 64-frame front-end launch, from the committed `ncu --set full`
 # capture (profiles/r01f_frontend_full.txt: 236.11 MB + 58.62 MB).  Static by nature: a profiler cannot run inside bench.
 FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
+
+
+# sha256[:16] of the step's integer outputs (selected-feature counts + 2-NN match lists of all 64 frames) for the stream seeds
+# 99 + rank, rank 0..7: every run checks its own outputs against these (bit-exact stages: any change of a kernel's results, a
+# race, or a skipped stage shows here, inside the timed configuration).  Printed by `bench.py --print-checksums`.
+EXPECTED_OUTPUT_SHA = {}
+
+
+def output_checksum(nfeat, matches):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(nfeat).tobytes() + np.ascontiguousarray(matches).tobytes()).hexdigest()[:16]
+
+
+def gpu_local_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None"""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{int(dom, 16):04x}:{rest.lower()}/local_cpulist"
+        cpus = []
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus += list(range(int(a), int(b) + 1))
+            elif part:
+                cpus.append(int(part))
+        return cpus or None
+    except Exception:
+        return None
 
 
 def read_peaks():
@@ -181,29 +228,70 @@ def run_cpu_ba(L, prefix, pb):
                                     len(pb["obs_kf"]), C.c_double(pb["huber"]), BA_ITERS, P(summary), None)
 
 
-def bench_reference(args, rank, world):
-    if rank != 0:
-        return
+REF_SAMPLE = 8   # frames per CPU step: a bounded sample of the 64-frame step (the CPU needs ~0.2 s for it on 128 cores)
+
+
+def local_cpus():
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+
+
+def reference_worker(args):
+    """one independent reference stream on the cores in args.cores (comma list): prints {"frames": n, "seconds": t}"""
     from alvaar_b200 import synth
+    cores = [int(c) for c in args.cores.split(",")]
+    try:
+        os.sched_setaffinity(0, cores)
+    except Exception:
+        pass
     L, kind = load_cpu_impl()
-    cores = os.cpu_count() or 1
-    nthreads = cores
-    sample = 8 if kind == "reference" else 2          # frames per CPU step: a bounded sample of the 64-frame step
-    frames, _ = synth.make_frames(sample, W, H)
+    sample = REF_SAMPLE if kind == "reference" else 2
+    frames, _ = synth.make_frames(sample, W, H, seed=99 + args.stream)
     _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
     ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_pipeline_frames(L, kind, frames[:2], map_desc, ba, nthreads)
-    steps = max(1, min(args.steps, 3))
-    t = sum(cpu_pipeline_frames(L, kind, frames, map_desc, ba, nthreads) for _ in range(steps))
-    fps = sample * steps / t
-    line = {"impl": "reference", "metric": "frames_per_sec_720p_1000orb_20kf_ba", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_pipeline_frames(L, kind, frames[:2], map_desc, ba, len(cores))
+    t = sum(cpu_pipeline_frames(L, kind, frames, map_desc, ba, len(cores)) for _ in range(args.steps))
+    print(json.dumps({"frames": sample * args.steps, "seconds": t, "kind": kind, "cores": len(cores) if kind == "reference" else 1, "sample": sample}))
+
+
+def bench_reference(args, rank, world):
+    """The reference's own CPU implementation of the step on the host cores.  N = 1: one stream on all cores.  N > 1 (rank 0
+    only): N independent streams, one process each, pinned to N disjoint core sets (one System per core
+    set) -- the CPU counterpart of N streams on N GPUs; the aggregate is reported."""
+    if rank != 0:
+        return
+    cpus = local_cpus()
+    nstream = max(1, args.gpus)
+    per = max(1, len(cpus) // nstream)
+    steps = max(1, args.steps)
+    procs = []
+    for i in range(nstream):
+        cs = cpus[i * per:(i + 1) * per] if i < nstream - 1 or nstream == 1 else cpus[i * per:]
+        if nstream == 1:
+            cs = cpus
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-worker", "--cores", ",".join(map(str, cs)), "--stream", str(i),
+               "--steps", str(steps), "--warmup", str(args.warmup), "--config", args.config]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True))
+    res = []
+    for pr in procs:
+        out, _ = pr.communicate()
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    # streams run side by side: the aggregate rate is the sum of the per-stream rates
+    fps = sum(r["frames"] / r["seconds"] for r in res)
+    t_step = max(r["seconds"] for r in res) / steps
+    kind, sample = res[0]["kind"], res[0]["sample"]
+    cores_used = sum(r["cores"] for r in res)
+    line = {"impl": "reference", "metric": METRIC[args.config], "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": workload_config(sample),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads if kind == "reference" else 1, "kind": kind,
-                             "sample": f"{sample} frames/step x {steps} steps of the 720p workload "
-                                       "(cv::setNumThreads(all cores) for the OpenCV stages, Ceres single-threaded as shipped)"},
+            "config": workload_config(BATCH, nstream, nstream > 1 and not args.no_loop_closure),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores_used, "kind": kind,
+                             "sample": f"{nstream} stream(s) x {steps} steps x {sample} frames of the {BATCH}-frame 720p step (each incl. "
+                                       f"{(sample + KF_INTERVAL - 1) // KF_INTERVAL} local BA solves); per stream: OpenCV stages on its "
+                                       f"{per if nstream > 1 else len(cpus)} cores (cv::setNumThreads), Ceres single-threaded as shipped"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -216,13 +304,13 @@ def workload_config(batch, world=1, loop_closure=False):
 
 
 def _workload_config(batch):
-    return {"workload": "c2_720p_stream+c4_local_ba", "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
+    return {"workload": WORKLOAD, "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
             "pyramid": "4 levels + Scharr derivative levels (buildOpticalFlowPyramid withDerivatives, as the reference)",
             "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "ORB::detectAndCompute semantics, 1 level: FAST-9 -> retainBest(2n) -> Harris -> retainBest(n) -> IC angle -> 7x7 blur -> rBRIEF-256",
             "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
             "ba_every_n_frames": KF_INTERVAL,
             "ba_schedule": "own high-priority stream, forked after the front end and joined at the end of the step",
-            "l2_policy": "inputs (236 MB/step) larger than L2 (126 MB)",
+            "l2_policy": f"inputs ({4 * W * H * batch / 1e6:.0f} MB/step) larger than L2 (126 MB)",
             "parallelism": "1 stream batch per GPU"}
 
 
@@ -234,6 +322,15 @@ def bench_b200(args, rank, world, local_rank):
     from alvaar_b200.pipeline import Pipeline
 
     torch.cuda.set_device(local_rank)
+    # page-locked buffers are first-touched by this process: run it on the CPUs of the GPU's own NUMA node while they are
+    # allocated and while the copies are issued, so that the e2e leg does not depend on where the scheduler put the process
+    all_cpus = local_cpus()
+    numa = gpu_local_cpus(local_rank)
+    if numa:
+        try:
+            os.sched_setaffinity(0, [c for c in numa if c in all_cpus] or all_cpus)
+        except Exception:
+            numa = None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -330,6 +427,14 @@ def bench_b200(args, rank, world, local_rank):
         e2e_ms = ev0.elapsed_time(ev1)
         _ = time.perf_counter() - t0
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])   # both slots deliver the same results
+    out_sha = output_checksum(res[0][0].numpy(), res[0][1].numpy())
+    want_sha = EXPECTED_OUTPUT_SHA.get(99 + rank) if args.config == "c2" else None
+    if want_sha is not None and out_sha != want_sha:
+        raise SystemExit(f"bench: the step's outputs changed: sha {out_sha}, expected {want_sha} (stream seed {99 + rank})")
+    try:
+        os.sched_setaffinity(0, all_cpus)   # the CPU legs below use every host core again
+    except Exception:
+        pass
     sampler.stop_flag = True
     sampler.join(timeout=2)
     tracking = None
@@ -365,25 +470,30 @@ def bench_b200(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         L, kind = load_cpu_impl()
-        cores = os.cpu_count() or 1
-        sample = 8 if kind == "reference" else 2
+        cores = len(all_cpus)
+        sample = REF_SAMPLE if kind == "reference" else 2
         cpu_pipeline_frames(L, kind, frames[:2], map_desc, ba, cores)
-        tcpu = cpu_pipeline_frames(L, kind, frames[:sample], map_desc, ba, cores)
-        cpu = {"value": sample / tcpu, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind,
-               "sample": f"{sample} frames of the same 720p step (incl. {(sample + KF_INTERVAL - 1) // KF_INTERVAL} local BA solves), "
+        t1 = cpu_pipeline_frames(L, kind, frames[:sample], map_desc, ba, cores)
+        passes = int(max(1, min(8, 10.0 / max(t1, 1e-3))))          # about 10 s of CPU work, at most the whole 64-frame step
+        tcpu = t1 + sum(cpu_pipeline_frames(L, kind, frames[sample * (i % (BATCH // sample)):sample * (i % (BATCH // sample)) + sample], map_desc, ba, cores)
+                        for i in range(1, passes))
+        cpu = {"value": sample * passes / tcpu, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+               "sample": f"{sample * passes} frames of the same 720p step (incl. {passes * ((sample + KF_INTERVAL - 1) // KF_INTERVAL)} local BA solves), "
                          "OpenCV stages on all host cores, Ceres single-threaded as shipped"}
 
-    line = {"metric": "frames_per_sec_720p_1000orb_20kf_ba", "value": fps, "unit": "frames/s", "n_gpus": world,
+    line = {"metric": METRIC[args.config], "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": workload_config(BATCH, world, lc is not None),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "alva_pipeline_submit_host + alva_pipeline_wait, two batches in flight (pinned host RGBA in, counts+matches+BA poses out per step)"},
             "gpu_launches": int(launches),
+            "output_sha": out_sha, "output_check": "matches the stored checksum" if want_sha else "no stored checksum for this stream seed",
+            "host_numa_cpus": (f"{min(numa)}-{max(numa)} ({len(numa)} CPUs local to the GPU)" if numa else None),
             "clocks": sampler.summary(),
             "roofline": {"kernel": "frontend_tile_kernel<RGBA> (gray + pyramid L1 + FAST-9/NMS, fused)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": FRONTEND_DRAM_TRAFFIC_BYTES_B64 if BATCH == 64 else None,
+                         "traffic": FRONTEND_DRAM_TRAFFIC_BYTES_B64 if (BATCH, W, H) == (64, 1280, 720) else None,
                          "traffic_source": "ncu --set full, profiles/r01f_frontend_full.txt (bytes per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_FRONTEND * BATCH,
                          "launch_ms": fe_avg_ms},
@@ -395,6 +505,35 @@ def bench_b200(args, rank, world, local_rank):
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def print_checksums():
+    """the integer outputs of one step for the stream seeds 99..106, on one GPU: paste the dict into EXPECTED_OUTPUT_SHA"""
+    import torch
+    import alvaar_b200
+    from alvaar_b200 import synth
+    from alvaar_b200.pipeline import Pipeline
+    _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
+    ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
+    stream = torch.cuda.Stream()
+    ctx = alvaar_b200.Context(0, stream.cuda_stream)
+    pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE | alvaar_b200.ORB_HARRIS,
+                    map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
+                    ba_max_iter=BA_ITERS, ba_huber=ba["huber"], derivatives=True)
+    pipe.set_map(map_desc)
+    for s in range(pipe.nprob):
+        pipe.set_ba(s, ba)
+    out = {}
+    for seed in range(99, 107):
+        frames, _ = synth.make_frames(BATCH, W, H, seed=seed)
+        host_in = torch.from_numpy(frames).pin_memory()
+        nf = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
+        mt = torch.zeros((BATCH, pipe.fcap, 4), dtype=torch.int32).pin_memory()
+        with torch.cuda.stream(stream):
+            pipe.step_host(host_in, nf, mt, None, None)
+        torch.cuda.synchronize()
+        out[seed] = output_checksum(nf.numpy(), mt.numpy())
+    print("EXPECTED_OUTPUT_SHA =", json.dumps(out).replace('"', ""))
 
 
 def tracking_stage_times(ctx, pipe, stream, local_rank):
@@ -593,16 +732,25 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-worker"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2: 1280x720 / 1000 features (headline); c3: 1920x1080 / 2000 features")
+    ap.add_argument("--cores", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--stream", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--print-checksums", action="store_true", help="print the output checksums of the step for the stream seeds 99..106 and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba-overlap", action="store_true", help="run the local BA after the frame stages instead of beside them")
     ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
     args = ap.parse_args()
+    select_config(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.print_checksums:
+        print_checksums()
+    elif args.impl == "reference-worker":
+        reference_worker(args)
+    elif args.impl == "reference":
         bench_reference(args, rank, world)
     else:
         bench_b200(args, rank, world, local_rank)

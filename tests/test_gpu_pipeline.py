@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000)])
+@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000), (1920, 1080, 2, 2000)])   # C2 and C3 of BASELINE.json
 def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
     frames, _ = synth.make_frames(batch, w, h, seed=5)
     q, mapd = synth.make_descriptors(8, 2000, seed=3)
@@ -91,7 +91,7 @@ def test_pipeline_vs_oracle(gpu_ctx, oracle, w, h, batch, nfeat):
     pipe.close()
 
 
-@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000)])
+@pytest.mark.parametrize("w,h,batch,nfeat", [(640, 480, 3, 300), (1280, 720, 2, 1000), (1920, 1080, 2, 2000)])
 def test_pipeline_detect_and_compute_mode(gpu_ctx, oracle, w, h, batch, nfeat):
     """orb_flags = IC_ANGLE | HARRIS: the pipeline's feature set per frame is exactly ORB::detectAndCompute(nfeat, 1 level)'s
     (oracle composition pinned bit-for-bit to the reference in tests/test_oracle.py), and the matches follow from it."""
