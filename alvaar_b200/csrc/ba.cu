@@ -1467,11 +1467,13 @@ extern int alva_g_knn_qpw;   // hamming.cu
 int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside the frame stages
 
 extern int alva_g_frontend_antipodal, alva_g_frontend_variant;   // frontend.cu
-extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;   // hamming_mma.cu
+extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
+extern int alva_g_pipeline_graphs;   // pipeline.cu   // hamming_mma.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
+    if (name && !strcmp(name, "pipeline_graphs")) { alva_g_pipeline_graphs = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_ba_overlap")) { alva_g_ba_overlap = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "knn_qpw") && (value == 4 || value == 8)) { alva_g_knn_qpw = value; return 0; }
     if (name && !strcmp(name, "knn_mma") && value >= 0 && value <= 2) { alva_g_knn_mma = value; return 0; }

@@ -7,6 +7,8 @@
 // feature front end; `System` (system.cu) drives it one frame at a time, bench.py drives it in batches.
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
+#include <map>
+#include <tuple>
 #include <vector>
 
 // stage entry points implemented in the other translation units
@@ -84,6 +86,17 @@ struct alva_pipeline {
     bool profile = false;
     long long step_index = 0;
     std::vector<void*> allocs;
+    // CUDA graphs: the per-frame stages of a frame range (keyed by input pointer and range: the kernel arguments are baked in) and
+    // the step's local-BA chain are each captured once, after a first direct run has sized every scratch buffer, and replayed
+    // with one launch (~60 + ~50 dependent launches per step otherwise).  Not used while profiling: a graph cannot carry the
+    // per-launch event pairs alva_pipeline_frontend_ms reads.
+    struct Graph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::map<std::tuple<const uint8_t*, int, int>, Graph> frame_graphs;
+    std::map<std::tuple<const uint8_t*, int, int>, int> frame_runs;   // direct runs seen per key (capture after the first)
+    Graph ba_graph;
+    int ba_runs = 0;
+    bool graphs_failed = false;
+    long long graph_replays = 0;
 };
 
 static int palloc(alva_pipeline* p, void** ptr, size_t bytes) {
@@ -98,6 +111,8 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     if (!p) return;
     AlvaDeviceGuard guard__(p->ctx);
     cudaStreamSynchronize(p->ctx->stream);
+    for (auto& kv : p->frame_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (p->ba_graph.exec) cudaGraphExecDestroy(p->ba_graph.exec);
     for (void* a : p->allocs) cudaFree(a);
     if (p->sel_ctx) { alva_ctx_destroy(p->sel_ctx); p->sel_ctx = nullptr; }
     if (p->sel_stream) { cudaStreamSynchronize(p->sel_stream); cudaStreamDestroy(p->sel_stream); }
@@ -338,12 +353,33 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
 // otherwise leave most SMs idle overlap the wide per-frame kernels.
 extern int alva_g_ba_overlap;   // alva_set_option("pipeline_ba_overlap", 0): run BA after the frame stages instead (A/B measurement)
 
-static int pipeline_ba_launch(alva_pipeline* p) {
+int alva_g_pipeline_graphs = 1;   // alva_set_option("pipeline_graphs", 0): always launch kernel by kernel
+
+static bool graphs_on(const alva_pipeline* p) { return alva_g_pipeline_graphs && !p->profile && !p->graphs_failed; }
+
+// capture what `body` enqueues on `st` (and on streams it forks to and joins back from) into an executable graph
+template <class F>
+static bool capture_graph(alva_pipeline* p, cudaStream_t st, alva_pipeline::Graph& out, F&& body) {
+    cudaGraph_t g = nullptr;
+    const long long l0 = p->ctx->launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    const int e = body();
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    const long long n = p->ctx->launches - l0;
+    p->ctx->launches = l0;
+    bool ok = ce == cudaSuccess && e == 0 && g != nullptr;
+    if (ok) ok = cudaGraphInstantiate(&out.exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) { cudaGetLastError(); out.exec = nullptr; return false; }
+    out.launches = n;
+    return true;
+}
+
+// the BA chain itself, on the BA stream (pristine copies -> working copies, then the solve)
+static int pipeline_ba_body(alva_pipeline* p) {
     const alva_pipeline_config& c = p->cfg;
     cudaStream_t st = p->ba_stream;
     const size_t np = p->nprob;
-    ALVA_CUDA(cudaEventRecord(p->ba_fork, p->ctx->stream));
-    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_fork, 0));
     ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
     ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
     const long long before = p->ba_ctx->launches;
@@ -351,8 +387,25 @@ static int pipeline_ba_launch(alva_pipeline* p) {
                                   p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber, c.ba_max_iter,
                                   p->ba_summary);
     p->ctx->launches += p->ba_ctx->launches - before;   // one launch counter per pipeline (alva_ctx_launches)
-    p->ba_forked = true;
     return e;
+}
+
+static int pipeline_ba_launch(alva_pipeline* p) {
+    cudaStream_t st = p->ba_stream;
+    ALVA_CUDA(cudaEventRecord(p->ba_fork, p->ctx->stream));
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_fork, 0));
+    p->ba_forked = true;
+    if (graphs_on(p)) {
+        if (!p->ba_graph.exec && p->ba_runs >= 1 && !capture_graph(p, st, p->ba_graph, [&] { return pipeline_ba_body(p); })) p->graphs_failed = true;
+        if (p->ba_graph.exec) {
+            ALVA_CUDA(cudaGraphLaunch(p->ba_graph.exec, st));
+            p->ctx->launches += p->ba_graph.launches;
+            p->graph_replays++;
+            return 0;
+        }
+    }
+    p->ba_runs++;
+    return pipeline_ba_body(p);
 }
 
 static int pipeline_ba_fork(alva_pipeline* p) {
@@ -376,11 +429,40 @@ static int pipeline_ready(alva_pipeline* p) {
     return 0;
 }
 
+// the per-frame stages of frames [f0, f0 + nf): a graph replay when one exists for this (input, range), else direct launches
+// (the first direct run of a key sizes the scratch buffers; the second call captures)
+static int pipeline_frames_auto(alva_pipeline* p, const uint8_t* rgba_dev, int f0, int nf, bool timed, bool fork_ba) {
+    if (!graphs_on(p)) return pipeline_frames(p, rgba_dev, f0, nf, timed, fork_ba);
+    if (fork_ba) if (int e = pipeline_ba_fork(p)) return e;   // the BA chain is its own graph on its own stream
+    const auto key = std::make_tuple(rgba_dev, f0, nf);
+    alva_pipeline::Graph& g = p->frame_graphs[key];
+    if (!g.exec && p->frame_runs[key] >= 1 &&
+        !capture_graph(p, p->ctx->stream, g, [&] { return pipeline_frames(p, rgba_dev, f0, nf, false, false); }))
+        p->graphs_failed = true;
+    if (g.exec) {
+        ALVA_CUDA(cudaGraphLaunch(g.exec, p->ctx->stream));
+        p->ctx->launches += g.launches;
+        p->graph_replays++;
+        return 0;
+    }
+    p->frame_runs[key]++;
+    return pipeline_frames(p, rgba_dev, f0, nf, timed, false);
+}
+
 extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
     if (!p || !rgba_dev) { alva_set_error("alva_pipeline_step_dev: bad argument"); return ALVA_E_INVALID; }
     if (int e = pipeline_ready(p)) return e;
-    if (int e = pipeline_frames(p, rgba_dev, 0, p->cfg.batch, true, true)) { pipeline_ba_join(p); return e; }
+    if (int e = pipeline_frames_auto(p, rgba_dev, 0, p->cfg.batch, true, true)) { pipeline_ba_join(p); return e; }
     return pipeline_ba_join(p);
+}
+
+// {graphs captured, graph launches so far, 1 if a capture failed and the pipeline fell back to direct launches}
+extern "C" int alva_pipeline_graph_stats(alva_pipeline* p, int32_t* out3) {
+    if (!p || !out3) return ALVA_E_INVALID;
+    int n = p->ba_graph.exec ? 1 : 0;
+    for (auto& kv : p->frame_graphs) n += kv.second.exec ? 1 : 0;
+    out3[0] = n; out3[1] = (int32_t)p->graph_replays; out3[2] = p->graphs_failed ? 1 : 0;
+    return 0;
 }
 
 // Host-buffer step (the e2e leg).  alva_pipeline_submit_host enqueues one batch and returns at once: the batch is uploaded in
@@ -420,7 +502,7 @@ extern "C" int alva_pipeline_submit_host(alva_pipeline* p, const uint8_t* rgba_h
         const int f0 = i * per, nf = (f0 + per <= c.batch) ? per : c.batch - f0;
         if (nf <= 0) break;
         ALVA_CUDA(cudaStreamWaitEvent(st, p->chunk_ev[slot][i], 0));
-        if (int e = pipeline_frames(p, p->in_dev[slot], f0, nf, false, i == 0)) { pipeline_ba_join(p); return e; }
+        if (int e = pipeline_frames_auto(p, p->in_dev[slot], f0, nf, false, i == 0)) { pipeline_ba_join(p); return e; }
     }
     if (int e = pipeline_ba_join(p)) return e;
     ALVA_CUDA(cudaEventRecord(p->free_ev[slot], st));   // the staged frames have been consumed

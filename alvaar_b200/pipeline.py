@@ -86,6 +86,13 @@ class Pipeline:
     def profile(self, on):
         self._chk(self.L.alva_pipeline_profile(self.h, 1 if on else 0))
 
+    def graph_stats(self):
+        """(CUDA graphs captured, graph launches so far, capture failed -> direct launches)"""
+        out = (C.c_int32 * 3)()
+        self.L.alva_pipeline_graph_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(self.L.alva_pipeline_graph_stats(self.h, out))
+        return int(out[0]), int(out[1]), bool(out[2])
+
     def frontend_ms(self, n):
         n = min(n, 64)
         out = (C.c_float * n)()

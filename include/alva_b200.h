@@ -288,6 +288,7 @@ int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
  * same results by construction, checked by host emulation, not yet validated on a GPU) -- default 0.
  * "pipeline_ba_overlap" = 0: alva_pipeline runs the local BA after the per-frame stages instead of beside them on its own
  * stream (default 1; results are identical, only the schedule changes).
+ * "pipeline_graphs" = 0: alva_pipeline launches kernel by kernel instead of replaying CUDA graphs (default 1; results identical).
  * "knn_qpw" = 4 | 8: queries a warp of the Hamming matcher keeps in registers (8: 128 registers / 16 warps per SM;
  * 4: 80 registers / 24 warps per SM).  Results are identical.
  * "knn_mma" = 0 | 1 | 2: the tensor-core formulation of the Hamming matcher (hamming_mma.cu: descriptors expanded to +-1
@@ -351,6 +352,8 @@ int  alva_pipeline_wait(alva_pipeline*);
 int  alva_pipeline_profile(alva_pipeline*, int enable);
 int  alva_pipeline_frontend_ms(alva_pipeline*, float* ms, int n);   /* CUDA-event durations of the fused front-end launch */
 int  alva_pipeline_info(const alva_pipeline*, int32_t* out4);
+/* {CUDA graphs captured so far, graph launches so far, 1 if a capture failed and the pipeline fell back to direct launches} */
+int  alva_pipeline_graph_stats(alva_pipeline*, int32_t* out3);
 void* alva_pipeline_buffer(alva_pipeline*, int which);
 
 /* ---- System: the reference's public class, one handle per camera stream ------------------------
