@@ -159,6 +159,49 @@ __global__ void knn2_merge_kernel(const uint2* __restrict__ partial, int nq, int
     reinterpret_cast<int4*>(out)[qi] = r;
 }
 
+
+// ---- block-pair matching for the cross-stream loop-closure search (loopclosure.cu) --------------------------------------------
+// gathered: [world][K] keyframe blocks of `block_bytes` each (wire format: include/alva_b200.h, "keyframe block"); this rank's
+// keyframe e is matched against keyframe e of every other rank r: 2-NN of each live local descriptor among the live remote
+// ones.  grid (query tiles, world, K); out [K][world][n_max] int4 = (idx0, dist0, idx1, dist1), -1 where there is none.
+__global__ void __launch_bounds__(WPC * 32, 3) knn2_blockpair_kernel(const uint8_t* __restrict__ gathered, size_t block_bytes, int n_max, int K,
+                                                                      int rank, int hdr_bytes, int4* __restrict__ out, uint32_t mul22,
+                                                                      uint32_t mul23, uint32_t mul24) {
+    constexpr int QPW = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.y, e = blockIdx.z;
+    if (r == rank) return;
+    const uint8_t* lb = gathered + ((size_t)rank * K + e) * block_bytes;
+    const uint8_t* rb = gathered + ((size_t)r * K + e) * block_bytes;
+    const int nq = min(reinterpret_cast<const int32_t*>(lb)[4], n_max), nt = min(reinterpret_cast<const int32_t*>(rb)[4], n_max);
+    const int q0 = (blockIdx.x * WPC + warp) * QPW;
+    if (q0 >= nq) return;
+    const uint4* q = reinterpret_cast<const uint4*>(lb + hdr_bytes + (size_t)n_max * 8);
+    const uint4* t = reinterpret_cast<const uint4*>(rb + hdr_bytes + (size_t)n_max * 8);
+    int4* o = out + ((size_t)e * gridDim.y + r) * n_max;
+    uint4 qa[QPW], qb[QPW];
+#pragma unroll
+    for (int i = 0; i < QPW; i++) {
+        const int qi = min(q0 + i, nq - 1);
+        qa[i] = __ldg(q + 2 * qi);
+        qb[i] = __ldg(q + 2 * qi + 1);
+    }
+    uint32_t k0[QPW], k1[QPW], tk[QPW];
+#pragma unroll
+    for (int i = 0; i < QPW; i++) k0[i] = k1[i] = tk[i] = NONE;
+    const int full_steps = nt >> 5;
+    for (int sidx = 0; sidx < full_steps; sidx++) knn_step<QPW, false>(qa, qb, k0, k1, tk, t, 32 * sidx + lane, nt, mul22, mul23, mul24);
+    if (32 * full_steps < nt) knn_step<QPW, true>(qa, qb, k0, k1, tk, t, 32 * full_steps + lane, nt, mul22, mul23, mul24);
+#pragma unroll
+    for (int i = 0; i < QPW; i++) {
+        uint32_t m0, m1;
+        warp_top2(k0[i], k1[i], m0, m1);
+        if (lane == 0 && q0 + i < nq)
+            o[q0 + i] = make_int4(m0 == NONE ? -1 : (int)(m0 & 0x3fffff), m0 == NONE ? -1 : (int)(m0 >> 22), m1 == NONE ? -1 : (int)(m1 & 0x3fffff),
+                                  m1 == NONE ? -1 : (int)(m1 >> 22));
+    }
+}
+
 }  // namespace
 
 // Chunking of the train set.  Long chunks make the selection filter effective (its rare path runs ~2 ln(chunk) times per
@@ -223,4 +266,14 @@ extern "C" int alva_k_hamming_knn2_batch(alva_ctx* ctx, const uint8_t* q, const 
     }
     const int nq = nbatch * qcap;
     return knn_launch(ctx, q, nbatch * qcap, t, nt, out, counts, qcap);
+}
+
+// internal (loopclosure.cu)
+int alva_knn2_blockpair_launch(alva_ctx* ctx, const uint8_t* gathered, size_t block_bytes, int n_max, int K, int world, int rank,
+                               int hdr_bytes, int32_t* out) {
+    dim3 grid((n_max + 4 * WPC - 1) / (4 * WPC), world, K);
+    knn2_blockpair_kernel<<<grid, WPC * 32, 0, ctx->stream>>>(gathered, block_bytes, n_max, K, rank, hdr_bytes, reinterpret_cast<int4*>(out),
+                                                               1u << 22, 1u << 23, 1u << 24);
+    ALVA_LAUNCH_CHECK(ctx);
+    return 0;
 }

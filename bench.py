@@ -299,7 +299,7 @@ def bench_reference(args, rank, world):
 def workload_config(batch, world=1, loop_closure=False):
     cfg = _workload_config(batch)
     cfg["parallelism"] = f"{world} independent camera-stream batch(es), one per GPU" + (
-        "; NCCL all-gather of keyframe descriptor blocks + cross-stream Hamming match per step" if loop_closure else "")
+        "; NCCL all-gather of the step's keyframe blocks + cross-stream loop-closure detection on a side stream" if loop_closure else "")
     return cfg
 
 
@@ -368,20 +368,36 @@ def bench_b200(args, rank, world, local_rank):
     # local keyframe is matched (brute-force Hamming 2-NN) against every gathered block.  No reference behaviour to
     # match (the reference is single-stream); validated as "gather == concatenation of the per-rank inputs".
     lc = None
+    lc_events, det = [], None
     if dist is not None and not args.no_loop_closure:
-        from alvaar_b200 import dist as adist
-        kf_idx = torch.arange(0, BATCH, KF_INTERVAL, device=f"cuda:{local_rank}")[:pipe.nprob]
+        from alvaar_b200.loopclosure import LoopClosure, block_bytes
+        dev_s = f"cuda:{local_rank}"
+        side = torch.cuda.Stream()
+        lc_ctx = alvaar_b200.Context(local_rank, side.cuda_stream)
+        det = LoopClosure(lc_ctx, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H))
+        kf_idx = torch.arange(0, BATCH, KF_INTERVAL, dtype=torch.int32, device=dev_s)[:pipe.nprob].contiguous()
         desc_all = pipe.buffer("desc", (BATCH, pipe.fcap, 32), torch.uint8)
+        pts_all = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
         cnt_all = pipe.buffer("selcounts", (BATCH,), torch.int32)
-        lc_out = torch.zeros((pipe.fcap, 4), dtype=torch.int32, device=f"cuda:{local_rank}")
+        bb = block_bytes(pipe.fcap)
+        send = torch.zeros(pipe.nprob * bb, dtype=torch.uint8, device=dev_s)
+        gathered_buf = torch.zeros(world * pipe.nprob * bb, dtype=torch.uint8, device=dev_s)
+        ev_ready, ev_packed = torch.cuda.Event(), torch.cuda.Event()
 
         def lc():
-            kd = desc_all.index_select(0, kf_idx).contiguous()
-            kc = cnt_all.index_select(0, kf_idx).contiguous()
-            gd, gc = adist.gather_keyframe_descriptors(kd, kc)
-            q = kd[-1]
-            ctx.hamming_knn2(q, pipe.fcap, gd.reshape(-1, 32), gd.numel() // 32, lc_out)
-            return gd, gc
+            # Off the per-frame path: the step's keyframe blocks are packed on a side stream as soon as the descriptors exist, the
+            # NCCL all-gather and the cross-stream detection (Hamming 2-NN of the live descriptors, ratio test, five-point RANSAC)
+            # run there beside the next step; the main stream only waits for the (microseconds-long) pack before it reuses the
+            # descriptor buffers.  Results are polled without blocking.
+            ev_ready.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_ready)
+                det.pack(desc_all, pts_all, cnt_all, kf_idx, send)
+                ev_packed.record(side)
+                det.exchange_and_detect(send, gathered_buf)
+            stream.wait_event(ev_packed)
+            lc_events.extend(det.poll())
+            return gathered_buf
 
     sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
@@ -455,6 +471,15 @@ def bench_b200(args, rank, world, local_rank):
         except Exception as e:
             tracking["system_api"] = {"error": repr(e)}
 
+    lc_report = None
+    if det is not None:
+        torch.cuda.synchronize()
+        lc_events.extend(det.poll(wait=True))
+        sc = det.last_scores()
+        lc_report = {"keyframe_blocks_per_step": int(world * pipe.nprob), "block_bytes": int(block_bytes(pipe.fcap)),
+                     "events": len(lc_events), "last_step_pairs_checked": int((sc[:, :, 0] >= 30).sum()),
+                     "last_step_pairs_verified": int((sc[:, :, 1] == 1).sum()),
+                     "schedule": "side stream: pack -> ncclAllGather -> Hamming 2-NN (live descriptors) -> ratio test -> 5-point RANSAC; polled"}
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -495,6 +520,7 @@ def bench_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "alva_pipeline_submit_host + alva_pipeline_wait, two batches in flight (pinned host RGBA in, counts+matches+BA poses out per step)"},
             "gpu_launches": int(launches),
+            "loop_closure": lc_report,
             "cuda_graphs": {"captured": graphs[0], "graph_launches": graphs[1], "capture_failed": graphs[2],
                             "note": "gpu_launches counts the kernels inside the replayed graphs"},
             "output_sha": out_sha, "output_check": "matches the stored checksum" if want_sha else "no stored checksum for this stream seed",

@@ -395,6 +395,50 @@ int  alva_system_unpin_buffer(alva_system*, void* host_ptr);
  * returns instead of running alva_k_essential_5pt -- used by the parity tests to plug in the reference's own initialisation
  * result (whose refinement is noise-limited) and check everything downstream of it at 1e-7; ignored when n does not
  * match the number of correspondences of that initialisation. */
+/* ---- cross-stream loop closure (the reference has none: parity unpinned, validated by determinism and
+ * planted revisits).  KEYFRAME BLOCK wire format (what one rank contributes per new keyframe to the NCCL all-gather;
+ * little-endian, fixed size so that the exchange has static shapes):
+ *     offset 0    int32 magic = ALVA_LC_MAGIC ('ALKF'), int32 version = ALVA_LC_VERSION, int32 stream id (rank), int32 keyframe
+ *                 sequence number, int32 count (live entries, <= n_max), int32 n_max, float32 fx, fy, cx, cy, 6 x int32 reserved (0)
+ *     offset 64   float32 px[n_max][2]      pixel position of keypoint i (entries >= count are 0)
+ *     then        uint8   desc[n_max][32]   its 256-bit ORB descriptor
+ * alva_lc_block_bytes(n_max) = 64 + 40 * n_max.  A step's exchange is [world][kf_per_step] such blocks.
+ * alva_lc_pack      : this rank's kf_per_step new keyframes (frames kf_frames[e] of a frame-major batch: desc [nframes][cap][32],
+ *                     pts [nframes][cap][2] float, counts [nframes]; all DEVICE pointers) -> send (device, kf_per_step blocks).
+ *                     K4 (host): fx, fy, cx, cy.  kf_seq0: sequence number of the first of them.
+ * alva_lc_detect    : on the gathered blocks (device, [world][kf_per_step] blocks): Hamming 2-NN of keyframe e of this rank against
+ *                     keyframe e of every other rank, ratio test, five-point RANSAC on the putative matches; enqueues only.
+ * alva_lc_poll      : finished steps are consumed in order; a loop with remote stream r is reported when the last min_consecutive
+ *                     keyframe events against r all passed RANSAC with >= min_inliers inliers.  Returns the number of events. */
+#define ALVA_LC_MAGIC        0x464B4C41   /* "ALKF" */
+#define ALVA_LC_VERSION      1
+#define ALVA_LC_HEADER_BYTES 64
+typedef struct alva_lc alva_lc;
+typedef struct {
+    int32_t n_max, kf_per_step, world, rank;
+    int32_t min_matches;       /* putative matches needed before the geometric check runs (default 30) */
+    int32_t max_dist;          /* absolute Hamming gate on the best match (default 64) */
+    int32_t ratio_num, ratio_den;   /* ratio test: best * ratio_den < second * ratio_num (default 4 / 5) */
+    int32_t min_consecutive;   /* keyframe events in a row that must pass (default 3) */
+    int32_t min_inliers;       /* RANSAC inliers needed (default 20) */
+    float err_px, fx_hint, fy_hint;   /* RANSAC threshold in pixels (default 3) at this focal length (default 500) */
+} alva_lc_config;
+typedef struct {
+    int32_t local_kf, remote_rank, remote_kf, n_matches, n_inliers, consecutive;
+    double Rt[12];             /* relative pose [R | t] (3 x 4 row-major, t up to scale) of the remote keyframe in the local one */
+} alva_lc_event;
+size_t   alva_lc_block_bytes(int n_max);
+alva_lc* alva_lc_create(alva_ctx*, const alva_lc_config*);
+void     alva_lc_destroy(alva_lc*);
+int      alva_lc_pack(alva_lc*, const uint8_t* desc, const float* pts, const int32_t* counts, int cap, const int32_t* kf_frames,
+                      int kf_seq0, const float* K4, uint8_t* send);
+int      alva_lc_detect(alva_lc*, const uint8_t* gathered);
+int      alva_lc_poll(alva_lc*, alva_lc_event* out, int cap, int wait);
+/* steps enqueued by alva_lc_detect whose results alva_lc_poll has not consumed yet (at most 4 may be in flight) */
+int      alva_lc_inflight(const alva_lc*);
+/* diagnostics: per keyframe pair of the last step, out [kf_per_step][world][4] = {matches, RANSAC success, inliers, remote keyframe} */
+int      alva_lc_last_scores(alva_lc*, double* out);
+
 /* N independent camera streams in one call (streams are independent, System holds all state): handles[i]
  * processes the frame rgba[i] with time stamp t_ms[i] (t_ms NULL = the system clock).  poses16 [n][16], status [n] (the value
  * alva_system_find_camera_pose_ts would return for that stream).  The streams run concurrently on the device (every System

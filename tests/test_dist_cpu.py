@@ -31,3 +31,20 @@ def test_world2_gloo(tmp_path):
     for r_ in res:
         assert (r_["gd"][0] == res[0]["desc"]).all() and (r_["gd"][1] == res[1]["desc"]).all()   # gather == concat
         assert (r_["gc"] == np.array([[16, 3], [15, 4]])).all()
+
+
+def test_keyframe_block_wire_format_constants():
+    """the Python side of the loop-closure exchange and the C header agree on the keyframe block (no GPU: symbol + constants)"""
+    import ctypes as C
+    import re
+    from alvaar_b200 import lib
+    from alvaar_b200.loopclosure import HEADER_BYTES, MAGIC, VERSION, LcConfig, LcEvent, block_bytes
+    L = lib()
+    L.alva_lc_block_bytes.restype = C.c_size_t
+    for n in (8, 1024, 1536):
+        assert int(L.alva_lc_block_bytes(n)) == block_bytes(n) == 64 + 40 * n
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "alva_b200.h")).read()
+    assert int(re.search(r"#define ALVA_LC_MAGIC\s+(0x[0-9A-Fa-f]+)", hdr).group(1), 16) == MAGIC == int.from_bytes(b"ALKF", "little")
+    assert int(re.search(r"#define ALVA_LC_VERSION\s+(\d+)", hdr).group(1)) == VERSION
+    assert int(re.search(r"#define ALVA_LC_HEADER_BYTES\s+(\d+)", hdr).group(1)) == HEADER_BYTES
+    assert C.sizeof(LcConfig) == 13 * 4 and C.sizeof(LcEvent) == 6 * 4 + 12 * 8
