@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
 // matrix-vector product over the already finished columns (8 threads per row, shuffle-reduced) and ONE barrier -- no
 // square roots, no trailing updates, no serial panel.  S = L D L' with L[i][k] = V[i][k] / d_k.  Then the two triangular
 // solves (warp 0, lane-strided dot products).  yf = S^-1 rhs.
-constexpr int CH_THREADS = 512, CH_PARTS = 4;   // 128 rows x 4 threads per row
+constexpr int CH_THREADS = 1024, CH_PARTS = 8;   // 128 rows x 8 threads per row (the per-column dot product is the serial part)
 __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     extern __shared__ double sm[];
     const BaProblem P = probs[blockIdx.x];
@@ -988,8 +988,9 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
             if (k < j) s0 += V[row * ld + k] * (V[j * ld + k] * invd[k]);
         }
         double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans eight rows)
+        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans four rows)
         s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (act && part == 0) {
             const double v = V[row * ld + j] - s;
             V[row * ld + j] = v;

@@ -62,7 +62,8 @@ FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
 # sha256[:16] of the step's integer outputs (selected-feature counts + 2-NN match lists of all 64 frames) for the stream seeds
 # 99 + rank, rank 0..7: every run checks its own outputs against these (bit-exact stages: any change of a kernel's results, a
 # race, or a skipped stage shows here, inside the timed configuration).  Printed by `bench.py --print-checksums`.
-EXPECTED_OUTPUT_SHA = {}
+EXPECTED_OUTPUT_SHA = {99: "204d42bd422277ed", 100: "e04ea0ed49e3f800", 101: "e24449c668b5ec3d", 102: "9a985c1e891a9927",
+                       103: "755d6b883377afbf", 104: "1a0e044321185545", 105: "e4c0192f6cdbd669", 106: "33e552d94e9a17d7"}
 
 
 def output_checksum(nfeat, matches):
