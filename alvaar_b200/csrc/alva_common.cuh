@@ -31,6 +31,10 @@ struct alva_ctx {
     uint32_t p3p_tab_seed = 0;
     void* knn_ws = nullptr;         // tensor-core matcher: expanded int8 operand tiles, row map (hamming_mma.cu)
     size_t knn_ws_bytes = 0;
+    // fork / join inside one entry point (BA: the structure kernels run beside the first linearisation).  Created with the
+    // context so that nothing is allocated while a caller captures `stream` into a CUDA graph.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
 };
 
 // Every public entry point runs on the context's device whatever the caller's current device is (two Systems on two GPUs

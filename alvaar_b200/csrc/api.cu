@@ -100,6 +100,15 @@ extern "C" alva_ctx* alva_ctx_create(int device, void* stream) {
         }
         ctx->own_stream = true;
     }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess) {
+        alva_set_error("alva_ctx_create: auxiliary stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+        alva_ctx_destroy(ctx);
+        return nullptr;
+    }
     return ctx;
 }
 
@@ -113,6 +122,9 @@ extern "C" void alva_ctx_destroy(alva_ctx* ctx) {
     if (ctx->det_ws) cudaFree(ctx->det_ws);
     if (ctx->knn_ws) cudaFree(ctx->knn_ws);
     if (ctx->p3p_tab) cudaFree(ctx->p3p_tab);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

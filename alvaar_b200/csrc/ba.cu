@@ -495,11 +495,20 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
         const uint32_t en = live ? P.plist[idx] : 0u;
         const int l = en >> 8, su = en & 0xff;
         const int ob = live ? P.lm_start[l] : 0, ns = live ? P.lm_start[l + 1] - ob : -1;
+        // the reduced-system columns of the first four slots, fetched together (independent loads) before the serial rounds
+        int cv0 = -1, cv1 = -1, cv2 = -1, cv3 = -1;
+        if (live) {
+            cv0 = P.anch_col[l];
+            const int o1 = ns >= 1 ? P.lm_obs[ob] : -1, o2 = ns >= 2 ? P.lm_obs[ob + 1] : -1, o3 = ns >= 3 ? P.lm_obs[ob + 2] : -1;
+            if (o1 >= 0) cv1 = P.obs_col[o1];
+            if (o2 >= 0) cv2 = P.obs_col[o2];
+            if (o3 >= 0) cv3 = P.obs_col[o3];
+        }
         for (int sv = 0; sv <= 255; sv++) {                 // slot-major rounds (ns is small: 3 in the reference's problems)
             if (!__any_sync(0xffffffffu, live && sv <= ns)) break;
             int bjv = -1;
             if (live && sv <= ns) {
-                const int cv = sv ? P.obs_col[P.lm_obs[ob + sv - 1]] : P.anch_col[l];
+                const int cv = sv == 0 ? cv0 : sv == 1 ? cv1 : sv == 2 ? cv2 : sv == 3 ? cv3 : P.obs_col[P.lm_obs[ob + sv - 1]];
                 if (cv >= 0) { const int bj = cv / 6; if (bj > bi || (bj == bi && sv >= su)) bjv = bj; }
                 // a landmark seen twice from one keyframe (two slots on the same pose) needs the transposed contribution
                 // as well; localBA never builds that, so such problems simply take the atomic Schur path instead
@@ -531,10 +540,11 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
 
 // ------------------------------------------------------------------------------------------ control: before the step
 // TrustRegionMinimizer::{IterationZero, FinalizeIterationAndCheckIfMinimizerCanContinue} + LM ComputeStep's diagonal.
-__global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+constexpr int CT_THREADS = 1024;   // control kernels: one CTA per problem; their loops over landmarks are chains of L2 round trips, so be wide
+__global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.x];
     BaState& st = *P.st;
-    __shared__ double red[256];
+    __shared__ double red[CT_THREADS];
     __shared__ int go;
     const int tid = threadIdx.x;
     const int n = st.ncols;
@@ -542,19 +552,19 @@ __global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict
     if (st.relin) {
         // cost at the (new) current point, in a fixed summation order
         double c = 0;
-        for (int i = tid; i < D.nblk; i += 256) c += P.cost_part[i];
-        const double x_cost = block_sum<256>(c, red);
+        for (int i = tid; i < D.nblk; i += CT_THREADS) c += P.cost_part[i];
+        const double x_cost = block_sum<CT_THREADS>(c, red);
         // |x|
         double xn = 0;
-        for (int k = tid; k < D.nkf; k += 256)
+        for (int k = tid; k < D.nkf; k += CT_THREADS)
             if (P.pose_col[k] >= 0) for (int i = 0; i < 7; i++) xn += P.poses[7 * k + i] * P.poses[7 * k + i];
-        for (int l = tid; l < D.nlm; l += 256)
+        for (int l = tid; l < D.nlm; l += CT_THREADS)
             if (P.lm_start[l + 1] > P.lm_start[l]) xn += P.invd[l] * P.invd[l];
         __syncthreads();
-        xn = block_sum<256>(xn, red);
+        xn = block_sum<CT_THREADS>(xn, red);
         // gradient max-norm |x - Plus(x, -g)|_inf
         double gm = 0;
-        for (int k = tid; k < D.nkf; k += 256) {
+        for (int k = tid; k < D.nkf; k += CT_THREADS) {
             const int c0 = P.pose_col[k];
             if (c0 < 0) continue;
             double dlt[6], out[7];
@@ -562,16 +572,16 @@ __global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict
             se3_plus(P.poses + 7 * k, dlt, out);
             for (int i = 0; i < 7; i++) gm = fmax(gm, fabs(P.poses[7 * k + i] - out[i]));
         }
-        for (int l = tid; l < D.nlm; l += 256)
+        for (int l = tid; l < D.nlm; l += CT_THREADS)
             if (P.lm_start[l + 1] > P.lm_start[l]) gm = fmax(gm, fabs(P.ge[l]));
         __syncthreads();
         red[tid] = gm;
         __syncthreads();
-        for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); __syncthreads(); }
+        for (int s = CT_THREADS / 2; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); __syncthreads(); }
         gm = red[0];
         if (st.iteration == 0) {   // Jacobi scaling is fixed at iteration 0 (trust_region_minimizer.cc:266-275)
-            for (int i = tid; i < n; i += 256) P.scf[i] = 1.0 / (1.0 + sqrt(P.nf[i]));
-            for (int l = tid; l < D.nlm; l += 256) P.sce[l] = 1.0 / (1.0 + sqrt(P.ne[l]));
+            for (int i = tid; i < n; i += CT_THREADS) P.scf[i] = 1.0 / (1.0 + sqrt(P.nf[i]));
+            for (int l = tid; l < D.nlm; l += CT_THREADS) P.sce[l] = 1.0 / (1.0 + sqrt(P.ne[l]));
         }
         __syncthreads();
         if (tid == 0) {
@@ -602,18 +612,18 @@ __global__ void __launch_bounds__(256) ba_pre_kernel(const BaProblem* __restrict
     const bool reuse = st.reuse_diagonal;
     const double radius = st.radius;
     __syncthreads();   // everyone has read the state before thread 0 updates it below
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += CT_THREADS) {
         if (!reuse) P.diagf[i] = fmin(fmax(P.nf[i] * P.scf[i] * P.scf[i], 1e-6), 1e32);
         P.Df[i] = sqrt(P.diagf[i] / radius);
     }
-    for (int l = tid; l < D.nlm; l += 256) {
+    for (int l = tid; l < D.nlm; l += CT_THREADS) {
         if (!reuse) P.diage[l] = fmin(fmax(P.ne[l] * P.sce[l] * P.sce[l], 1e-6), 1e32);
         P.De[l] = sqrt(P.diage[l] / radius);
     }
-    for (int i = tid; i < NMAX * NMAX; i += 256) P.S[i] = 0;
-    for (int i = tid; i < NMAX; i += 256) P.rhs[i] = 0;
+    for (int i = tid; i < NMAX * NMAX; i += CT_THREADS) P.S[i] = 0;
+    for (int i = tid; i < NMAX; i += CT_THREADS) P.rhs[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += 256) P.S[i * NMAX + i] = P.Df[i] * P.Df[i];
+    for (int i = tid; i < n; i += CT_THREADS) P.S[i * NMAX + i] = P.Df[i] * P.Df[i];
     if (tid == 0) st.reuse_diagonal = 1;
 }
 
@@ -889,10 +899,10 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, co
 #undef ACC
 }
 
-// One CTA (2 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
+// One CTA (8 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
 // private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction; the block and its mirror are
 // stored -- no atomics, bit-reproducible.
-constexpr int GA_THREADS = 64;
+constexpr int GA_THREADS = 256;   // the diagonal blocks hold ~600 entries, each a chain of dependent loads: width hides it
 __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
@@ -954,11 +964,15 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
 }
 
 // ------------------------------------------------------------------------------------------ reduced solve (1 CTA / problem)
-// Left-looking LDL' of the <= 126 x 126 reduced camera system in shared memory: column j of V = L D is one parallel
-// matrix-vector product over the already finished columns (8 threads per row, shuffle-reduced) and ONE barrier -- no
-// square roots, no trailing updates, no serial panel.  S = L D L' with L[i][k] = V[i][k] / d_k.  Then the two triangular
-// solves (warp 0, lane-strided dot products).  yf = S^-1 rhs.
-constexpr int CH_THREADS = 1024, CH_PARTS = 8;   // 128 rows x 8 threads per row (the per-column dot product is the serial part)
+// Right-looking LDL' of the <= 126 x 126 reduced camera system, REGISTER-TILED: the lower triangle of the (augmented) 128 x 128
+// matrix is cut into 4 x 4 tiles, one per thread (528 tiles, column-block-major, so whole warps retire as the elimination moves
+// right); V = L D is built in place.  Per column j: the threads holding it publish the column through shared memory (double
+// buffered: ONE barrier per column), then every live tile takes its rank-1 update  a[i][c] -= V[i][j] (V[c][j] / d_j)  from 8
+// shared-memory words -- 16 FP64 FMAs against 8 loads, where the left-looking form spent three loads per multiply-add and was
+// shared-memory-bandwidth bound (113 us; profiles/r02_kernels_full.txt).  Row n of the matrix is the right-hand side, so the
+// forward substitution z = L^-1 b falls out of the same updates.  Then x = L^-T D^-1 z by warp 0 (lane-strided, registers).
+// No square roots; fixed operation order (bit-reproducible).  yf = S^-1 rhs.
+constexpr int CH_TILES = 32 * 33 / 2, CH_THREADS = (CH_TILES + 31) / 32 * 32;   // 528 tiles -> 544 threads
 __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     extern __shared__ double sm[];
     const BaProblem P = probs[blockIdx.x];
@@ -966,41 +980,79 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
     if (st.done) return;
     const int n = st.ncols, tid = threadIdx.x, lane = tid & 31;
     const int ld = NMAX + 1;
-    double* V = sm;                 // (n + 1) x ld: row n is the right-hand side (augmented system)
+    double* V = sm;                 // (n + 1) x ld, filled after the factorisation for the backward solve
     double* invd = sm + NMAX * ld;  // NMAX
+    __shared__ double colbuf[2][NMAX];
+    __shared__ double pivinv[2];
     __shared__ int ok_s;
-    for (int i = tid; i < n * n; i += CH_THREADS) { const int r = i / n, c = i - r * n; V[r * ld + c] = P.S[r * NMAX + c]; }
-    for (int i = tid; i < n; i += CH_THREADS) V[n * ld + i] = P.rhs[i];
+    // tile of this thread: column block tj, row block ti >= tj
+    int tj = 0, rem = tid;
+    while (tj < 32 && rem >= 32 - tj) { rem -= 32 - tj; tj++; }
+    const int ti = tj + rem;
+    const bool tile = tid < CH_TILES;
+    const int r0 = 4 * ti, c0 = 4 * tj;
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int gr = r0 + r, gc = c0 + c;
+            double v = 0.0;
+            if (tile && gc < n) {
+                if (gr < n) v = P.S[gr * NMAX + gc];
+                else if (gr == n) v = P.rhs[gc];
+            }
+            a[r][c] = v;
+        }
     if (tid == 0) ok_s = 1;
-    __syncthreads();
-    // column j of V = L D:  V[i][j] = A[i][j] - sum_{k<j} V[i][k] V[j][k] / d_k  for all rows i >= j -- including the
-    // augmented row n, whose entries are the forward-substituted right-hand side z = L^-1 b.
-    const int row = tid / CH_PARTS, part = tid % CH_PARTS;
-    for (int j = 0; j < n; j++) {
-        const bool act = row >= j && row <= n;
-        double s0 = 0, s1 = 0;
-        if (act) {
-            int k = part;
-            for (; k + CH_PARTS < j; k += 2 * CH_PARTS) {
-                s0 += V[row * ld + k] * (V[j * ld + k] * invd[k]);
-                s1 += V[row * ld + k + CH_PARTS] * (V[j * ld + k + CH_PARTS] * invd[k + CH_PARTS]);
+    const int last_jb = (n - 1) >> 2;
+    // a tile is live while columns of its own column block are still to be eliminated
+    for (int jb = 0; jb <= last_jb; jb++) {
+        const bool live = tile && tj >= jb;   // column-block-major tile order: a warp's lanes drop out almost together, and a
+                                              // retired warp only keeps arriving at the barriers
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j = 4 * jb + jj;
+            if (j >= n) break;   // uniform
+            double* cb = colbuf[j & 1];
+            if (live && tj == jb) {   // publish column j (rows >= j of it are final)
+#pragma unroll
+                for (int r = 0; r < 4; r++) cb[r0 + r] = a[r][jj];
+                if (ti == tj) {
+                    const double d = a[jj][jj];
+                    if (!(d > 0)) ok_s = 0;
+                    const double inv = 1.0 / (d > 0 ? d : 1.0);
+                    pivinv[j & 1] = inv;
+                    invd[j] = inv;
+                }
             }
-            if (k < j) s0 += V[row * ld + k] * (V[j * ld + k] * invd[k]);
-        }
-        double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);   // all lanes take part (a warp spans four rows)
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (act && part == 0) {
-            const double v = V[row * ld + j] - s;
-            V[row * ld + j] = v;
-            if (row == j) {
-                if (!(v > 0)) ok_s = 0;
-                invd[j] = 1.0 / (v > 0 ? v : 1.0);
+            __syncthreads();
+            if (live) {
+                const double inv = pivinv[j & 1];
+                double lr[4], lc[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) lr[r] = cb[r0 + r];
+#pragma unroll
+                for (int c = 0; c < 4; c++) lc[c] = cb[c0 + c] * inv;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (tj > jb || c > jj) a[r][c] -= lr[r] * lc[c];   // columns right of j only (tj == jb: compile-time c > jj)
             }
         }
-        __syncthreads();
     }
+    // V for the backward solve (lower triangle + the augmented row)
+    if (tile) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gr = r0 + r, gc = c0 + c;
+                if (gr <= n && gc < n) V[gr * ld + gc] = a[r][c];
+            }
+    }
+    __syncthreads();
     // backward: x = L^-T D^-1 z, column-oriented inside one warp: lane owns entries lane, lane+32, lane+64, lane+96 in
     // registers; after x_i is final it is broadcast and eliminated from the entries above it.
     if (tid < 32) {
@@ -1075,17 +1127,17 @@ __global__ void __launch_bounds__(BS_THREADS) ba_backsub_kernel(const BaProblem*
 }
 
 // ------------------------------------------------------------------------------------------ control: after the step
-__global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+__global__ void __launch_bounds__(CT_THREADS) ba_post_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.x];
     BaState& st = *P.st;
-    __shared__ double red[256];
+    __shared__ double red[CT_THREADS];
     __shared__ int accept_s;
     const int tid = threadIdx.x;
     if (st.done) return;
     // model cost change -(J s)'(r + J s / 2) from the back-substitution partials (fixed order)
     double mcs = 0;
-    for (int i = tid; i < D.nbs; i += 256) mcs += P.mc_part[i];
-    const double model_change = -block_sum<256>(mcs, red);
+    for (int i = tid; i < D.nbs; i += CT_THREADS) mcs += P.mc_part[i];
+    const double model_change = -block_sum<CT_THREADS>(mcs, red);
     const bool valid = st.chol_ok && (model_change > 0.0);
     __syncthreads();
     if (!valid) {   // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
@@ -1102,21 +1154,21 @@ __global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restric
     if (P.last_poses) {
         // the candidate has been evaluated (cost-only pass): from here until the next valid step it is the point the
         // reference's functors were evaluated at last, whether or not the step is accepted or a tolerance ends the solve
-        for (int i = tid; i < 7 * D.nkf; i += 256) P.last_poses[i] = P.cand_poses[i];
-        for (int l = tid; l < D.nlm; l += 256) P.last_invd[l] = P.cand_invd[l];
+        for (int i = tid; i < 7 * D.nkf; i += CT_THREADS) P.last_poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += CT_THREADS) P.last_invd[l] = P.cand_invd[l];
         if (tid == 0) st.has_last = 1;
     }
     double c = 0;
-    for (int i = tid; i < D.nblk; i += 256) c += P.cost_part[i];
-    const double cand_cost = block_sum<256>(c, red);
+    for (int i = tid; i < D.nblk; i += CT_THREADS) c += P.cost_part[i];
+    const double cand_cost = block_sum<CT_THREADS>(c, red);
     double sn = 0;
-    for (int k = tid; k < D.nkf; k += 256)
+    for (int k = tid; k < D.nkf; k += CT_THREADS)
         if (P.pose_col[k] >= 0)
             for (int i = 0; i < 7; i++) { const double d = P.poses[7 * k + i] - P.cand_poses[7 * k + i]; sn += d * d; }
-    for (int l = tid; l < D.nlm; l += 256)
+    for (int l = tid; l < D.nlm; l += CT_THREADS)
         if (P.lm_start[l + 1] > P.lm_start[l]) { const double d = P.invd[l] - P.cand_invd[l]; sn += d * d; }
     __syncthreads();
-    sn = block_sum<256>(sn, red);
+    sn = block_sum<CT_THREADS>(sn, red);
     if (tid == 0) {
         int accept = 0;
         st.invalid_steps = 0;
@@ -1153,10 +1205,10 @@ __global__ void __launch_bounds__(256) ba_post_kernel(const BaProblem* __restric
     }
     __syncthreads();
     if (accept_s) {
-        for (int i = tid; i < 7 * D.nkf; i += 256) P.poses[i] = P.cand_poses[i];
-        for (int l = tid; l < D.nlm; l += 256) P.invd[l] = P.cand_invd[l];
-        for (int i = tid; i < NMAX; i += 256) { P.nf[i] = 0; P.gf[i] = 0; }
-        for (int l = tid; l < D.nlm; l += 256) { P.ne[l] = 0; P.ge[l] = 0; }
+        for (int i = tid; i < 7 * D.nkf; i += CT_THREADS) P.poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += CT_THREADS) P.invd[l] = P.cand_invd[l];
+        for (int i = tid; i < NMAX; i += CT_THREADS) { P.nf[i] = 0; P.gf[i] = 0; }
+        for (int l = tid; l < D.nlm; l += CT_THREADS) { P.ne[l] = 0; P.ge[l] = 0; }
     }
 }
 
@@ -1345,27 +1397,37 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(D.nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
-    if (!dense) {   // structure of the gather-form Schur complement, once per solve
+    bool forked = false;
+    if (!dense) {   // structure of the gather-form Schur complement, once per solve -- beside the first linearisation, which
+                    // does not need it (fork / join on the context's auxiliary stream; also valid inside a stream capture)
         const dim3 pr_grid(NBMAX, nprob);
-        ba_pairs_kernel<0><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
+        cudaStream_t ps = ctx->stream;
+        if (ctx->aux_stream && cudaEventRecord(ctx->aux_fork, ctx->stream) == cudaSuccess &&
+            cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0) == cudaSuccess) { ps = ctx->aux_stream; forked = true; }
+        ba_pairs_kernel<0><<<pr_grid, 32, 0, ps>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_pairs_kernel<1><<<pr_grid, 32, 0, ctx->stream>>>(dp, D);
+        ba_pairs_kernel<1><<<pr_grid, 32, 0, ps>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
+        if (forked) ALVA_CUDA(cudaEventRecord(ctx->aux_join, ps));
     }
     for (int it = 0; it <= D.max_iter; it++) {
         ba_linearize_kernel<true><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         ba_stats_kernel<<<stats_grid, BS_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_pre_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+        ba_pre_kernel<<<nprob, CT_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        if (it == D.max_iter) break;   // the last pass only finalises (iteration count reached)
+        if (it == D.max_iter) {   // the last pass only finalises (iteration count reached)
+            if (forked) { ALVA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0)); forked = false; }   // max_iter == 0
+            break;
+        }
         if (dense) {
             ba_schur_kernel<true><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
             ba_syrk_dmma_kernel<<<syrk_grid, 128, 0, ctx->stream>>>(dp, D);
             ALVA_LAUNCH_CHECK(ctx);
         } else {
+            if (forked) { ALVA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0)); forked = false; }   // use_gather is final
             ba_lm_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);           // gather path (no-op if structure too large)
             ALVA_LAUNCH_CHECK(ctx);
             ba_gather_kernel<<<key_grid, GA_THREADS, 0, ctx->stream>>>(dp, D);
@@ -1379,7 +1441,7 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
         ALVA_LAUNCH_CHECK(ctx);
         ba_linearize_kernel<false><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_post_kernel<<<nprob, 256, 0, ctx->stream>>>(dp, D);
+        ba_post_kernel<<<nprob, CT_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
     return 0;

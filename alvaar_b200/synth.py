@@ -97,8 +97,9 @@ def gray_to_rgba(g):
     return out
 
 
-def make_frames(nframes, w, h, seed=99, rgba=True):
-    tex = make_texture()
+def make_frames(nframes, w, h, seed=99, rgba=True, texture_seed=1234):
+    """`seed` picks the camera path, `texture_seed` the scene (two calls with the same texture_seed look at the same plane)."""
+    tex = make_texture(seed=texture_seed)
     poses = trajectory(nframes, w, h, seed)
     frames = [render_gray(tex, p, w, h) for p in poses]
     g = np.stack(frames)

@@ -53,7 +53,7 @@ def run_steps(ctx, local, remote, kf, nsteps, world=2, **kw):
 
 def test_wire_format_and_planted_revisit(gpu_ctx):
     frames, _ = synth.make_frames(14, W, H, seed=7, rgba=True)
-    other, _ = synth.make_frames(14, W, H, seed=23, rgba=True)
+    other, _ = synth.make_frames(14, W, H, seed=23, rgba=True, texture_seed=777)
     a = features(gpu_ctx, frames[:12])                # local stream: frames 0..11
     b = features(gpu_ctx, frames[2:14])               # remote stream 1: the same scene two frames later (the planted revisit)
     c = features(gpu_ctx, other[:12])                 # remote stream 2: an unrelated scene
@@ -86,7 +86,7 @@ def test_wire_format_and_planted_revisit(gpu_ctx):
 
 def test_detection_is_deterministic_and_interrupted_runs_do_not_report(gpu_ctx):
     frames, _ = synth.make_frames(12, W, H, seed=7, rgba=True)
-    other, _ = synth.make_frames(12, W, H, seed=31, rgba=True)
+    other, _ = synth.make_frames(12, W, H, seed=31, rgba=True, texture_seed=778)
     a = features(gpu_ctx, frames[:10])
     b = features(gpu_ctx, frames[1:11])
     kf = [[0, 1, 2], [3, 4, 5]]
