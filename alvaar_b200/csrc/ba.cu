@@ -66,6 +66,8 @@ struct BaProblem {
     int32_t *lm_start, *lm_obs;             // CSR landmark -> observations: [nlm+1], [nobs]
     double* Wt;                             // dense Schur path: [nlm_pad][NMAX]
     double* mc_part;                        // model-cost partials, one per back-substitution CTA
+    double* ga_part;                        // gather Schur: [NBMAX][GA_SPLIT][42] partial sums of the diagonal blocks
+    int32_t* ga_ticket;                     // gather Schur: [NBMAX] arrival counters of a diagonal block's parts (wrap to 0)
     int32_t *obs_col, *anch_col;            // reduced-system column of each observation's / landmark anchor's pose (-1: fixed)
     int32_t *pstart;                        // gather Schur: [NBMAX + 1] ranges of plist per free pose
     uint32_t *plist;                        // gather Schur: (landmark << 8) | slot, every (landmark, slot) seeing that pose, by landmark
@@ -208,6 +210,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 constexpr int SETUP_THREADS = 1024;
 __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.x];
+    if (threadIdx.x < NBMAX) P.ga_ticket[threadIdx.x] = 0;   // arrival counters of the gather kernel's diagonal parts
     __shared__ int ref[256];
     __shared__ int scan_s[SETUP_THREADS + 1];
     __shared__ int wcount[32][NBMAX + 1];
@@ -899,21 +902,29 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, co
 #undef ACC
 }
 
-// One CTA (8 warps) per upper-triangular 6x6 block (bi <= bj): threads stride over the block's entry list, each keeps a
-// private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction; the block and its mirror are
-// stored -- no atomics, bit-reproducible.
-constexpr int GA_THREADS = 256;   // the diagonal blocks hold ~600 entries, each a chain of dependent loads: width hides it
+// One CTA (2 warps) per upper-triangular 6x6 block (bi < bj) and GA_SPLIT CTAs per DIAGONAL block, whose lists are the long
+// ones (every landmark the pose sees, ~600 entries against ~100): a part strides over the block's entry list, each thread
+// keeps a private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction.  Diagonal parts leave their
+// partial sums in a scratch slot; the part that arrives last (ticket) adds the GA_SPLIT slots in slot order.  The block and its
+// mirror are stored -- no floating-point atomics, bit-reproducible.
+constexpr int GA_THREADS = 64, GA_SPLIT = 8;
+constexpr int GA_GRID = NBMAX * GA_SPLIT + (MAXKEYS - NBMAX);   // diagonal parts first, then the strictly upper blocks
 __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
     if (st.done || !st.use_gather) return;
-    int bi = 0, rem = blockIdx.x;                        // grid.x enumerates the upper triangle over NBMAX
-    while (bi < NBMAX && rem >= NBMAX - bi) { rem -= NBMAX - bi; bi++; }
-    const int bj = bi + rem;
+    int bi, bj, part = 0, nparts = 1;
+    if ((int)blockIdx.x < NBMAX * GA_SPLIT) { bi = bj = blockIdx.x / GA_SPLIT; part = blockIdx.x % GA_SPLIT; nparts = GA_SPLIT; }
+    else {
+        int rem = blockIdx.x - NBMAX * GA_SPLIT;     // enumerates (bi, bj > bi) over NBMAX
+        bi = 0;
+        while (bi < NBMAX - 1 && rem >= NBMAX - 1 - bi) { rem -= NBMAX - 1 - bi; bi++; }
+        bj = bi + 1 + rem;
+    }
     if (bi >= st.nb || bj >= st.nb) return;
     const int blk = bi * NBMAX + bj;
     __shared__ double red[GA_THREADS / 32][42];
-    __shared__ int eb_s;
+    __shared__ int eb_s, last_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci = 6 * bi, cj = 6 * bj;
     if (warp == 0) {   // start of this block's entries = sum of the counts of all preceding blocks
@@ -933,7 +944,7 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
     double sci[6], scj[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
-    for (int idx = eb + tid; idx < ee; idx += GA_THREADS) {
+    for (int idx = eb + part * GA_THREADS + tid; idx < ee; idx += nparts * GA_THREADS) {
         const uint32_t en = P.pairs[idx];
         gather_entry<false>(P, en, sci, scj, acc, rh);   // (duplicate-pose pairs never reach this kernel: see ba_pairs_kernel)
     }
@@ -951,10 +962,28 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
         if (lane == 0) red[warp][36 + i] = rh[i];
     }
     __syncthreads();
+    double v = 0;
     if (tid < 42) {
-        double v = 0;
 #pragma unroll
         for (int wv = 0; wv < GA_THREADS / 32; wv++) v += red[wv][tid];
+    }
+    if (nparts > 1) {
+        double* slot = P.ga_part + ((size_t)bi * GA_SPLIT + part) * 42;
+        if (tid < 42) slot[tid] = v;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_s = atomicInc(reinterpret_cast<unsigned int*>(P.ga_ticket + bi), GA_SPLIT - 1) == GA_SPLIT - 1;   // wraps to 0
+        __syncthreads();
+        if (!last_s) return;
+        __threadfence();
+        if (tid < 42) {
+            v = 0;
+            const volatile double* all = P.ga_part + (size_t)bi * GA_SPLIT * 42;
+#pragma unroll
+            for (int q = 0; q < GA_SPLIT; q++) v += all[q * 42 + tid];
+        }
+    }
+    if (tid < 42) {
         if (tid < 36) {
             const int a = tid / 6, c = tid % 6;
             if (bi == bj) P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
@@ -1021,7 +1050,13 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
                 if (ti == tj) {
                     const double d = a[jj][jj];
                     if (!(d > 0)) ok_s = 0;
-                    const double inv = 1.0 / (d > 0 ? d : 1.0);
+                    // 1 / d sits on the serial chain of the elimination (pivot j + 1 needs it): MUFU.RCP64H seed (>= 20 bits) + two
+                    // Newton steps = 5 dependent operations instead of the IEEE division's subroutine; error <= 1 ulp, fixed sequence
+                    const double dd = d > 0 ? d : 1.0;
+                    double inv;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(dd));
+                    inv = fma(inv, fma(-dd, inv, 1.0), inv);
+                    inv = fma(inv, fma(-dd, inv, 1.0), inv);
                     pivinv[j & 1] = inv;
                     invd[j] = inv;
                 }
@@ -1304,11 +1339,13 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     d += (size_t)nkf * 7 + nlm;                      // cand
     d += (size_t)nblk;                               // cost partials
     d += (size_t)((nlm + BS_THREADS - 1) / BS_THREADS);   // model-cost partials
+    d += (size_t)NBMAX * 8 * 42;                          // gather partials (GA_SPLIT = 8)
     size_t bytes = d * sizeof(double);
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
     bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
     bytes += align_up((size_t)(NBMAX + 1) * 4, 8) + align_up(((size_t)nobs + (size_t)nlm) * 4, 8);   // pstart, plist
     bytes += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);   // blk_start, pairs
+    bytes += align_up((size_t)NBMAX * 4, 8);                                                        // ga_ticket
     bytes += align_up(sizeof(BaState), 8);
     return align_up(bytes, 256);
 }
@@ -1357,6 +1394,7 @@ static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, cons
             P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
             P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
             P.mc_part = take((size_t)((nlm + BS_THREADS - 1) / BS_THREADS));
+            P.ga_part = take((size_t)NBMAX * GA_SPLIT * 42);
             P.last_poses = local ? take(7 * (size_t)nkf) : nullptr;
             P.last_invd = local ? take(nlm) : nullptr;
             uint8_t* b = reinterpret_cast<uint8_t*>(d);
@@ -1369,6 +1407,7 @@ static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, cons
             P.plist = reinterpret_cast<uint32_t*>(b); b += align_up(((size_t)nobs + (size_t)nlm) * 4, 8);
             P.blk_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8);
             P.pairs = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+            P.ga_ticket = reinterpret_cast<int32_t*>(b); b += align_up((size_t)NBMAX * 4, 8);
             P.obs_lm_in = nullptr; P.obs_lm_w = nullptr; P.flags = nullptr;
             if (local) {
                 P.obs_lm_in = P.obs_lm;
@@ -1396,7 +1435,7 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
     ba_setup_kernel<<<nprob, SETUP_THREADS, 0, ctx->stream>>>(dp, D);
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(D.nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
-    const dim3 key_grid(MAXKEYS, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
+    const dim3 key_grid(GA_GRID, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
     bool forked = false;
     if (!dense) {   // structure of the gather-form Schur complement, once per solve -- beside the first linearisation, which
                     // does not need it (fork / join on the context's auxiliary stream; also valid inside a stream capture)
@@ -1529,13 +1568,14 @@ extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, co
 extern int alva_g_knn_qpw;   // hamming.cu
 int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside the frame stages
 
-extern int alva_g_frontend_antipodal, alva_g_frontend_variant;   // frontend.cu
+extern int alva_g_frontend_antipodal, alva_g_frontend_variant, alva_g_frontend_prefetch;   // frontend.cu
 extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
 extern int alva_g_pipeline_graphs;   // pipeline.cu   // hamming_mma.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
+    if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_graphs")) { alva_g_pipeline_graphs = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_ba_overlap")) { alva_g_ba_overlap = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "knn_qpw") && (value == 4 || value == 8)) { alva_g_knn_qpw = value; return 0; }

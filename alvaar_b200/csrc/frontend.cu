@@ -46,6 +46,7 @@ struct FrontendParams {
     int32_t* counts;
     int w, h, nframes, tiles_x, tiles_y;
     int thr, cap, use_tma;
+    int prefetch;         // variant 2: frames ahead whose tile (same position) is pulled into L2 while this one is processed; 0 = off
     uint32_t mul[7];      // 2^(25+i): kept as run-time data so the row-packing multiply-high stays an FMA-pipe IMAD.HI
 };
 
@@ -505,23 +506,25 @@ frontend_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FrontendPar
 //     ~4 % of the pixels with full lanes instead of re-walking every candidate; the score tile has a 33-word pitch.
 //   * 120 x 60 tiles (720 and 1080 are multiples of 60: no ragged bottom row) and the score tile folded into the idle RGBA
 //     staging buffer: 44.8 KB of shared memory per CTA instead of 54.4 -> 5 CTAs per SM (40 warps) instead of 4.
+//   * (profiles/r02a_frontend_v2_4cta_full.txt, per-line counts) a (tiles_x, tiles_y, frames) grid instead of two run-time
+//     divisions per warp (4.7 % of the instructions); each warp sends its keypoints straight to the frame's list (one global
+//     atomic per warp) instead of a tile list + two barriers + a copy loop; the pyramid's edge words come from the neighbour
+//     lanes (the 2-way conflicted 32-bit loads were 23 % of the excess shared-memory wavefronts); 128-bit score clears;
+//     optionally the tile `prefetch` frames ahead is pulled into L2 by TMA.
 constexpr int TH2 = 60, BH2 = TH2 + 8;    // tile interior rows / loaded box rows
 constexpr int SR2 = TH2 + 2;              // score rows: image y0-1 .. y0+TH2
 constexpr int SP2 = 132;                  // score pitch: 33 words -> rows rotate through the banks
-constexpr int KPCAP2 = TW * TH2 / 4;      // NMS leaves at most one keypoint per 2x2
 struct __align__(128) SmemLayout2 {
-    // TMA destination (RGBA mode).  After the gray pass: per-warp queues (NWARPS * QCAP u16), the tile's keypoint list
-    // (KPCAP2 words) and the score tile (SP2 * SR2 bytes)
+    // TMA destination (RGBA mode).  After the gray pass: per-warp queues (NWARPS * QCAP u16) and the score tile (SP2 bytes x
+    // 8 rows per warp)
     uint8_t rgba[BW * BH2 * 4];
     uint8_t gray[GP * (BH2 + 2)];  // TMA destination (gray mode); + 2 rows: the last warp's pre-test window (8 * 7 + 14 rows) reads
                                    // two rows past the box -- they only feed pixels its validity mask drops
     uint64_t bar;
-    int kpcount;
-    int kpbase;
 };
-constexpr int V2_KPLIST_OFF = NWARPS * QCAP * 2;
-constexpr int V2_SCORE_OFF = V2_KPLIST_OFF + KPCAP2 * 4;
-static_assert(V2_SCORE_OFF % 4 == 0 && V2_SCORE_OFF + SP2 * SR2 <= BW * BH2 * 4, "queues + keypoint list + score tile must fit the staging buffer");
+constexpr int V2_SCORE_OFF = NWARPS * QCAP * 2;
+static_assert(V2_SCORE_OFF % 16 == 0 && (8 * SP2) % 16 == 0 && V2_SCORE_OFF + SP2 * 8 * NWARPS <= BW * BH2 * 4,
+              "queues + score tile must fit the staging buffer; 128-bit clears");
 static_assert(NWARPS * 8 >= SR2, "8 score rows per warp");
 
 template <bool RGBA>
@@ -531,11 +534,7 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     SmemLayout2& S = *reinterpret_cast<SmemLayout2*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int t = blockIdx.x;
-    const int tiles_per_frame = P.tiles_x * P.tiles_y;
-    const int f = t / tiles_per_frame;
-    t -= f * tiles_per_frame;
-    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
     const int x0 = tx * TW, y0 = ty * TH2;
     const int w = P.w, h = P.h;
     const int sh = RGBA ? 0 : ((x0 - 8) & 15);
@@ -556,8 +555,11 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
             mbar_arrive_expect_tx(&S.bar, GP * BH2);
             tma_load_3d(S.gray, &tmap, &S.bar, x0 - 8 - sh, y0 - 4, f);
         }
+        if (P.prefetch && f + P.prefetch < P.nframes) {
+            if (RGBA) tma_prefetch_l2_3d(&tmap, x0 - 4, y0 - 4, f + P.prefetch);
+            else tma_prefetch_l2_3d(&tmap, x0 - 8 - sh, y0 - 4, f + P.prefetch);
+        }
     }
-    if (tid == 0) S.kpcount = 0;
     mbar_wait(&S.bar, 0);
 
     // ------------------------------------------------------------------ B. gray (w % 4 == 0 guaranteed by the TMA path)
@@ -593,9 +595,10 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     // the staging buffer is idle from here on: every warp clears the 8 score rows it will write in phase D
     uint8_t* const score = S.rgba + V2_SCORE_OFF;
     {
-        uint32_t* sc = reinterpret_cast<uint32_t*>(score) + warp * 8 * (SP2 / 4);
-        const int nwords = (min(SR2, 8 * warp + 8) - 8 * warp) * (SP2 / 4);
-        for (int i = lane; i < nwords; i += 32) sc[i] = 0;
+        uint4* sc = reinterpret_cast<uint4*>(score + warp * 8 * SP2);
+#pragma unroll
+        for (int i = 0; i < (8 * SP2 / 16 + 31) / 32; i++)
+            if (lane + 32 * i < 8 * SP2 / 16) sc[lane + 32 * i] = make_uint4(0u, 0u, 0u, 0u);
     }
 
     const bool edge_l = (x0 == 0), edge_r = (x0 + TW >= w), edge_t = (y0 == 0), edge_b = (y0 + TH2 >= h);
@@ -634,17 +637,24 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
         const int pc = tid % 15, sg = tid / 15;   // 15 quad-columns x 16 row pairs (threads 240..255 idle)
         const int lx = (x0 >> 1) + 4 * pc;
         const int ly0 = (y0 >> 1) + 2 * sg;
-        if (sg < 16 && lx < w1 && ly0 < h1) {
-            const uint32_t* base = G + (4 * sg + 2) * GPW + cbw + 2 * pc;   // gray row 2j+2 for output row j = 2*sg
-            uint32_t hs[7][4];
+        // Every lane loads its two middle words of the 7 rows; the edge words W0 (2 bytes used) / W3 (1 byte) are the
+        // neighbour lanes' W2 / W1 -- only the first / last quad of a row group and the warp's end lanes load them.  All 32
+        // lanes run this part (shuffles), whether or not their outputs exist (idle lanes read row group 15 again).
+        const uint32_t* base = G + (4 * min(sg, 15) + 2) * GPW + cbw + 2 * pc;   // gray row 2j+2 for output row j = 2*sg
+        const bool ld0 = pc == 0 || lane == 0, ld3 = pc == 14 || lane == 31;
+        uint32_t hs[7][4];
 #pragma unroll
-            for (int r = 0; r < 7; r++) {
-                const uint32_t W0 = base[r * GPW], W1 = base[r * GPW + 1], W2 = base[r * GPW + 2], W3 = base[r * GPW + 3];
-                hs[r][0] = __dp4a(__byte_perm(W0, W1, 0x5432), 0x04060401u, __dp4a(W1, 0x00010000u, 0u));
-                hs[r][1] = __dp4a(W1, 0x04060401u, __dp4a(W2, 0x00000001u, 0u));
-                hs[r][2] = __dp4a(__byte_perm(W1, W2, 0x5432), 0x04060401u, __dp4a(W2, 0x00010000u, 0u));
-                hs[r][3] = __dp4a(W2, 0x04060401u, __dp4a(W3, 0x00000001u, 0u));
-            }
+        for (int r = 0; r < 7; r++) {
+            const uint32_t W1 = base[r * GPW + 1], W2 = base[r * GPW + 2];
+            uint32_t W0 = __shfl_up_sync(0xffffffffu, W2, 1), W3 = __shfl_down_sync(0xffffffffu, W1, 1);
+            if (ld0) W0 = base[r * GPW];
+            if (ld3) W3 = base[r * GPW + 3];
+            hs[r][0] = __dp4a(__byte_perm(W0, W1, 0x5432), 0x04060401u, __dp4a(W1, 0x00010000u, 0u));
+            hs[r][1] = __dp4a(W1, 0x04060401u, __dp4a(W2, 0x00000001u, 0u));
+            hs[r][2] = __dp4a(__byte_perm(W1, W2, 0x5432), 0x04060401u, __dp4a(W2, 0x00010000u, 0u));
+            hs[r][3] = __dp4a(W2, 0x04060401u, __dp4a(W3, 0x00000001u, 0u));
+        }
+        if (sg < 16 && lx < w1 && ly0 < h1) {
             const bool quad_ok = (lx + 3 < w1) && ((w1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.l1) & 3) == 0);
 #pragma unroll
             for (int j = 0; j < 2; j++) {
@@ -667,7 +677,6 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
 
     // ------------------------------------------------------------------ D. FAST candidates + exact score
     uint16_t* Q = reinterpret_cast<uint16_t*>(S.rgba) + warp * QCAP;
-    uint32_t* kplist = reinterpret_cast<uint32_t*>(S.rgba + V2_KPLIST_OFF);
     int cn = 0;   // corners of this warp inside the tile interior: prefix of Q after this phase
     if (P.keys) {
         const int thr = P.thr;
@@ -748,7 +757,10 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     __syncthreads();
 
     // ------------------------------------------------------------------ E. 3x3 NMS (strict >) over the corners + emit
+    // The warp compacts its keypoints in place (queue prefix again), takes its range of the frame's list with ONE global
+    // atomic and stores it -- no tile-level list, no further barrier (order_keys_kernel sorts the frame's list anyway).
     if (P.keys) {
+        int kn = 0;
         for (int c0 = 0; c0 < cn; c0 += 32) {
             bool iskp = false;
             uint32_t key = 0;
@@ -763,24 +775,49 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
                 key = ((uint32_t)(y0 + sr - 1) << 20) | ((uint32_t)(x0 + scol - 4) << 8) | v;
             }
             const uint32_t mk = __ballot_sync(0xffffffffu, iskp);
-            if (mk) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&S.kpcount, __popc(mk));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (iskp) {
-                    const int kp = base + __popc(mk & ((1u << lane) - 1u));
-                    if (kp < KPCAP2) kplist[kp] = key;
+            if (c0 == 0 && cn <= 32) {   // the usual case: one round, keys stay in registers
+                if (mk) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(P.counts + f, __popc(mk));
+                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(mk & ((1u << lane) - 1u));
+                    if (iskp && base < P.cap) P.keys[(size_t)f * P.cap + base] = key;
+                }
+            } else {
+                // keys are 32 bits, queue slots 16: a key takes the two slots 2 kn', 2 kn' + 1 <= 2 (c0 + lane) + 1.  Slots
+                // < 2 * (c0 + 32) have all been read (or belong to this round, read above), but slots of LATER rounds must not
+                // be overwritten: 2 kn' + 1 < c0 + 32 is required, otherwise the round is flushed first.
+                if (2 * (kn + __popc(mk)) > c0 + 32) {   // warp-uniform: flush what is buffered
+                    if (kn) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(P.counts + f, kn);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const uint32_t* kb = reinterpret_cast<const uint32_t*>(Q);
+                        for (int i = lane; i < kn; i += 32)
+                            if (base + i < P.cap) P.keys[(size_t)f * P.cap + base + i] = kb[i];
+                        kn = 0;
+                        __syncwarp();
+                    }
+                    if (mk) {   // this round goes out directly
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(P.counts + f, __popc(mk));
+                        base = __shfl_sync(0xffffffffu, base, 0) + __popc(mk & ((1u << lane) - 1u));
+                        if (iskp && base < P.cap) P.keys[(size_t)f * P.cap + base] = key;
+                    }
+                } else {
+                    if (iskp) reinterpret_cast<uint32_t*>(Q)[kn + __popc(mk & ((1u << lane) - 1u))] = key;
+                    kn += __popc(mk);
+                    __syncwarp();
                 }
             }
         }
-        __syncthreads();
-        const int n = min(S.kpcount, KPCAP2);
-        if (tid == 0) S.kpbase = n ? atomicAdd(P.counts + f, n) : 0;
-        __syncthreads();
-        const int base = S.kpbase;
-        uint32_t* out = P.keys + (size_t)f * P.cap;
-        for (int i = tid; i < n; i += NTHREADS)
-            if (base + i < P.cap) out[base + i] = kplist[i];
+        if (kn) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(P.counts + f, kn);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t* kb = reinterpret_cast<const uint32_t*>(Q);
+            for (int i = lane; i < kn; i += 32)
+                if (base + i < P.cap) P.keys[(size_t)f * P.cap + base + i] = kb[i];
+        }
     }
 }
 
@@ -1034,6 +1071,7 @@ __global__ void __launch_bounds__(256) scharr_kernel(const ScharrLevels L) {
 
 // =================================================================================== host launchers
 int alva_g_frontend_antipodal = 0;   // alva_set_option("frontend_antipodal", 1): experimental pre-test variant (RGBA path only)
+int alva_g_frontend_prefetch = 0;    // alva_set_option("frontend_prefetch", 1): variant 2 pulls a later frame's tile into L2 (TMA prefetch)
 int alva_g_frontend_variant = 2;     // alva_set_option("frontend_variant", 0 | 2): 0 = the round-1 kernel, 2 = frontend_tile_kernel_v2
 
 static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
@@ -1069,12 +1107,17 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     const size_t smem = sizeof(SmemLayout) + 128;
     if (v2) {
         const size_t smem2 = sizeof(SmemLayout2) + 128;
+        if (P.tiles_y > 65535 || nframes > 65535) { alva_set_error("front end: more than 65535 frames / tile rows in one launch"); return ALVA_E_INVALID; }
+        const dim3 grid3(P.tiles_x, P.tiles_y, nframes);
+        // L2 prefetch distance: the tile at the same position this many frames ahead starts about one residency later
+        // (5 CTAs per SM in flight, tiles dispatched frame-major)
+        P.prefetch = alva_g_frontend_prefetch ? (5 * ctx->num_sms + P.tiles_x * P.tiles_y - 1) / (P.tiles_x * P.tiles_y) + 1 : 0;
         if (rgba_mode) {
             ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            frontend_tile_kernel_v2<true><<<grid, NTHREADS, smem2, ctx->stream>>>(tmap, P);
+            frontend_tile_kernel_v2<true><<<grid3, NTHREADS, smem2, ctx->stream>>>(tmap, P);
         } else {
             ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            frontend_tile_kernel_v2<false><<<grid, NTHREADS, smem2, ctx->stream>>>(tmap, P);
+            frontend_tile_kernel_v2<false><<<grid3, NTHREADS, smem2, ctx->stream>>>(tmap, P);
         }
     } else if (rgba_mode && alva_g_frontend_antipodal) {
         ALVA_CUDA(cudaFuncSetAttribute(frontend_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

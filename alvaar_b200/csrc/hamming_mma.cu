@@ -8,12 +8,14 @@
 // 2b - 1 (+1 / -1), the dot product of two 256-element rows is  256 - 2 * hamming,  exactly (an int32, or a float whose
 // partial sums are all integers of magnitude <= 256).  So the N_q x N_t distance matrix is one 8-bit GEMM with K = 256, and the
 // integer pipes (which bound the LOP3/POPC kernel of hamming.cu at ~7.5e11 distances/s) are left with nothing but the top-2
-// selection.  Two operand kinds are built: kind::i8 (+-1 as int8, int32 accumulators) and kind::f8f6f4 (+-1.0 as E4M3, fp32
-// accumulators).  Measured on B200 (profiles/r02_knn_mma_i8_full.txt): the int8 path keeps the IMMA sub-pipe busy 95 % of the
-// kernel and still only delivers ~1 900 MAC/clk/SM -- a quarter of the FP8 rate -- so FP8 is the default; the results are
-// bit-identical (every value involved is an exactly representable integer).
+// selection.  Two operand kinds are built: kind::i8 (+-1 as int8, int32 accumulators; the default) and kind::f8f6f4 (+-1.0 as
+// E4M3, fp32 accumulators); the results are bit-identical (every value involved is an exactly representable integer).
+// Measured on B200 (profiles/r02a_knn_mma_i8_full.txt, tools/gpu_knn_mma_prof.py): once the epilogue was out of the way both
+// kinds run at the same rate, ~4 030 MAC/clk/SM (M = N = 128, cta_group::1: ~130 clk per instruction, tensor pipe ~49 % busy) --
+// the limit at this tile shape is the rate the MMA unit streams its two 32 KB operands from shared memory, not the arithmetic
+// kind.  N = 256 tiles (half the A re-reads per MAC), A kept in TMEM, or cta_group::2 are the next steps.
 //
-// Shape of the kernel (one CTA per 256 query rows, 1 CTA / SM, 12 warps):
+// Shape of the kernel (one CTA per 256 query rows, 1 CTA / SM, 20 warps):
 //   warp 0   producer : bulk async copies (cp.async.bulk, SASS UBLKCP -- the TMA engine's 1-D mode) of pre-tiled 32 KB
 //                       operand blobs into a 4-stage shared-memory ring, completion on mbarriers
 //   warp 1   issuer   : one elected thread issues tcgen05.mma.kind::f8f6f4 / kind::i8 (SASS UTCQMMA / UTCIMMA), M = 128, N = 128, K = 32 per
@@ -27,8 +29,8 @@
 //                       the groups that hit run the top-2 insertion, on packed keys hamming << 22 | index (one multiply-add
 //                       builds a key, three min / max insert it: OpenCV's strict '<' with ties to the lowest train index is
 //                       the unsigned order of those keys).  The two halves of a row are merged through shared memory.
-//                       The epilogue is what bounds this kernel (profiles/r02b_knn_mma_f8_full.txt: with 8 epilogue warps and
-//                       a branchy insertion the MMAs waited on it 3/4 of the time; int8 and FP8 operands ran equally fast).
+//                       (With 8 epilogue warps and a branchy insertion the MMAs waited on the epilogue 3/4 of the time and
+//                       int8 and FP8 operands ran equally slowly; 16 warps + the gated insertion moved the bound to the MMAs.)
 // The operands are expanded from the packed 256-bit descriptors by knn2_expand_kernel straight into the shared-memory
 // image of a tile (UMMA canonical K-major layout), so the producer needs no tensor map and no swizzle pattern has to be
 // matched by hand anywhere else.  Live queries of a batch are compacted on the way ([nbatch][qcap] slots, counts[b] live).

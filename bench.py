@@ -462,7 +462,7 @@ def bench_b200(args, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     tracking = None
-    if rank == 0:
+    if rank == 0 and not args.no_stage_stats:
         try:
             tracking = tracking_stage_times(ctx, pipe, stream, local_rank)
         except Exception as e:   # explanatory numbers only: never let them take the headline line down
@@ -776,6 +776,9 @@ def main():
     ap.add_argument("--stream", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--print-checksums", action="store_true", help="print the output checksums of the step for the stream seeds 99..106 and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-stats", action="store_true",
+                    help="skip the explanatory per-stage / System-API timings after the timed region (profiling aid: ncu's "
+                         "serialisation of the 8 concurrent System threads corrupted its own heap at visit 9)")
     ap.add_argument("--no-ba-overlap", action="store_true", help="run the local BA after the frame stages instead of beside them")
     ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs (profiling aid)")

@@ -293,11 +293,13 @@ int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
  * 4: 80 registers / 24 warps per SM).  Results are identical.
  * "knn_mma" = 0 | 1 | 2: the tensor-core formulation of the Hamming matcher (hamming_mma.cu: descriptors expanded to +-1
  * int8, tcgen05.mma.kind::i8, dot = 256 - 2 * distance): 0 never, 1 for large query sets (default), 2 always.  Results
- * are identical.  "knn_mma_kind" = 1 | 0: operand kind of that kernel (1: +-1.0 as E4M3, kind::f8f6f4, fp32 accumulators --
- * default, 4x the int8 rate on B200; 0: +-1 as int8, kind::i8, int32 accumulators).  "knn_mma_mode" = 0 | 1 | 2: its
+ * are identical.  "knn_mma_kind" = 0 | 1: operand kind of that kernel (0: +-1 as int8, kind::i8, int32 accumulators -- default;
+ * 1: +-1.0 as E4M3, kind::f8f6f4, fp32 accumulators; both run at the same measured rate at this tile shape).  "knn_mma_mode" = 0 | 1 | 2: its
  * shared-memory operand layout (0 no swizzle, 1 128-byte swizzle, 2 debugging variant).
  * "frontend_variant" = 2 | 0: the fused front-end kernel (2: frontend_tile_kernel_v2, default; 0: the round-1 kernel, which
- * also serves geometries a TMA tensor map cannot express).  Results are identical. */
+ * also serves geometries a TMA tensor map cannot express).  Results are identical.
+ * "frontend_prefetch" = 0 | 1: variant 2 also pulls the tile at the same position a few frames ahead into L2 (TMA prefetch)
+ * while it works on its own (default 0).  Results are identical. */
 int alva_set_option(const char* name, int value);
 /* Debugging aid: the tensor-core matcher unconditionally on q [nq][32] x t [nt][32] (device pointers, 16-byte aligned);
  * dbg_dev (optional, 16384 int32 of device memory) receives the raw dot products of the first 128 x 128 tile. */

@@ -78,7 +78,7 @@ def test_wire_format_and_planted_revisit(gpu_ctx):
     assert ev[0]["local_kf"] == 2 and ev[0]["consecutive"] == 3 and ev[0]["n_inliers"] >= 20
     for s in sc:
         assert (s[:, 1, 0] >= 30).all() and (s[:, 1, 1] == 1).all()      # stream 1: many putative matches, RANSAC succeeds
-        assert (s[:, 2, 0] < 30).all() and (s[:, 2, 1] == 0).all()       # stream 2: too few matches, no geometric check
+        assert (4 * s[:, 2, 0] < s[:, 1, 0]).all() and (s[:, 2, 1] == 0).all()   # stream 2: a few chance matches (~6 % of the keypoints), no geometry
         assert (s[:, 0] == 0).all()                                      # a stream is not matched against itself
     R = ev[0]["Rt"][:, :3]
     assert np.abs(R @ R.T - np.eye(3)).max() < 1e-9 and np.abs(R - np.eye(3)).max() < 0.05    # two frames apart: nearly the same view

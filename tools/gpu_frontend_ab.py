@@ -1,5 +1,5 @@
 """A/B timing of the fused front-end launch (64 x 1280x720 RGBA, one launch) over its kernel variants:
-round-1 kernel, its antipodal instantiation, and frontend_tile_kernel_v2.  CUDA events, median of 8 after 2 warm-ups."""
+round-1 kernel, frontend_tile_kernel_v2, and v2 with the TMA L2 prefetch of a later frame's tile.  CUDA events, median of 8 after 2 warm-ups."""
 import os
 import sys
 
@@ -18,9 +18,10 @@ l1 = torch.zeros((n, h // 2, w // 2), dtype=torch.uint8, device="cuda")
 keys = torch.zeros((n, 32768), dtype=torch.int32, device="cuda")
 cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
 ALG = 4838400 * n
-for name, var, anti in (("round-1", 0, 0), ("round-1 + antipodal", 0, 1), ("v2", 2, 0)) * 2:
+for name, var, anti, pf in (("round-1", 0, 0, 0), ("v2", 2, 0, 0), ("v2 + L2 prefetch", 2, 0, 1)) * 3:
     ctx.L.alva_set_option(b"frontend_variant", var)
     ctx.L.alva_set_option(b"frontend_antipodal", anti)
+    ctx.L.alva_set_option(b"frontend_prefetch", pf)
     ts = []
     for _ in range(10):
         cnt.zero_()
@@ -34,3 +35,4 @@ for name, var, anti in (("round-1", 0, 0), ("round-1 + antipodal", 0, 1), ("v2",
     print(f"{name:22s} median {us:7.1f} us  -> {ALG / us / 1e3:7.1f} GB/s algorithmic  corners {int(cnt.sum())}")
 ctx.L.alva_set_option(b"frontend_variant", 2)
 ctx.L.alva_set_option(b"frontend_antipodal", 0)
+ctx.L.alva_set_option(b"frontend_prefetch", 0)
