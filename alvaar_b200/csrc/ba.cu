@@ -1570,13 +1570,14 @@ int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside t
 
 extern int alva_g_frontend_antipodal, alva_g_frontend_variant, alva_g_frontend_prefetch;   // frontend.cu
 extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
-extern int alva_g_pipeline_graphs;   // pipeline.cu   // hamming_mma.cu
+extern int alva_g_pipeline_graphs, alva_g_ba_lag;   // pipeline.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
     if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_graphs")) { alva_g_pipeline_graphs = value ? 1 : 0; return 0; }
+    if (name && !strcmp(name, "pipeline_ba_lag")) { alva_g_ba_lag = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_ba_overlap")) { alva_g_ba_overlap = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "knn_qpw") && (value == 4 || value == 8)) { alva_g_knn_qpw = value; return 0; }
     if (name && !strcmp(name, "knn_mma") && value >= 0 && value <= 2) { alva_g_knn_mma = value; return 0; }

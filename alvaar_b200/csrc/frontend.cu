@@ -757,66 +757,53 @@ frontend_tile_kernel_v2(const __grid_constant__ CUtensorMap tmap, const Frontend
     __syncthreads();
 
     // ------------------------------------------------------------------ E. 3x3 NMS (strict >) over the corners + emit
-    // The warp compacts its keypoints in place (queue prefix again), takes its range of the frame's list with ONE global
-    // atomic and stores it -- no tile-level list, no further barrier (order_keys_kernel sorts the frame's list anyway).
+    // A warp's first four rounds (128 corners; ~40 is typical) keep their keys in registers: ONE global atomic takes the warp's
+    // range of the frame's list, then the rounds store.  No tile-level list, no further barrier (order_keys_kernel sorts the
+    // frame's list anyway).  Corners beyond 128 take one atomic per round.
     if (P.keys) {
-        int kn = 0;
-        for (int c0 = 0; c0 < cn; c0 += 32) {
-            bool iskp = false;
-            uint32_t key = 0;
-            if (c0 + lane < cn) {
-                const uint32_t e = Q[c0 + lane];
-                const int sr = e >> 7, scol = e & 127;
-                const uint8_t* sp = score + sr * SP2 + scol;
-                const uint32_t v = sp[0];
-                const uint32_t m = max(max(max((uint32_t)sp[-SP2 - 1], (uint32_t)sp[-SP2]), max((uint32_t)sp[-SP2 + 1], (uint32_t)sp[-1])),
-                                       max(max((uint32_t)sp[1], (uint32_t)sp[SP2 - 1]), max((uint32_t)sp[SP2], (uint32_t)sp[SP2 + 1])));
-                iskp = v > m;
-                key = ((uint32_t)(y0 + sr - 1) << 20) | ((uint32_t)(x0 + scol - 4) << 8) | v;
+        const uint32_t lt = (1u << lane) - 1u;
+        auto nms_key = [&](int c, uint32_t& key) -> bool {
+            if (c >= cn) return false;
+            const uint32_t e = Q[c];
+            const int sr = e >> 7, scol = e & 127;
+            const uint8_t* sp = score + sr * SP2 + scol;
+            const uint32_t v = sp[0];
+            const uint32_t m = max(max(max((uint32_t)sp[-SP2 - 1], (uint32_t)sp[-SP2]), max((uint32_t)sp[-SP2 + 1], (uint32_t)sp[-1])),
+                                   max(max((uint32_t)sp[1], (uint32_t)sp[SP2 - 1]), max((uint32_t)sp[SP2], (uint32_t)sp[SP2 + 1])));
+            key = ((uint32_t)(y0 + sr - 1) << 20) | ((uint32_t)(x0 + scol - 4) << 8) | v;
+            return v > m;
+        };
+        uint32_t* const out = P.keys + (size_t)f * P.cap;
+        uint32_t keyr[4] = {0u, 0u, 0u, 0u}, mkr[4] = {0u, 0u, 0u, 0u};
+        bool isr[4] = {false, false, false, false};
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (32 * r < cn) {   // warp-uniform
+                isr[r] = nms_key(32 * r + lane, keyr[r]);
+                mkr[r] = __ballot_sync(0xffffffffu, isr[r]);
             }
-            const uint32_t mk = __ballot_sync(0xffffffffu, iskp);
-            if (c0 == 0 && cn <= 32) {   // the usual case: one round, keys stay in registers
-                if (mk) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(P.counts + f, __popc(mk));
-                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(mk & ((1u << lane) - 1u));
-                    if (iskp && base < P.cap) P.keys[(size_t)f * P.cap + base] = key;
-                }
-            } else {
-                // keys are 32 bits, queue slots 16: a key takes the two slots 2 kn', 2 kn' + 1 <= 2 (c0 + lane) + 1.  Slots
-                // < 2 * (c0 + 32) have all been read (or belong to this round, read above), but slots of LATER rounds must not
-                // be overwritten: 2 kn' + 1 < c0 + 32 is required, otherwise the round is flushed first.
-                if (2 * (kn + __popc(mk)) > c0 + 32) {   // warp-uniform: flush what is buffered
-                    if (kn) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(P.counts + f, kn);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        const uint32_t* kb = reinterpret_cast<const uint32_t*>(Q);
-                        for (int i = lane; i < kn; i += 32)
-                            if (base + i < P.cap) P.keys[(size_t)f * P.cap + base + i] = kb[i];
-                        kn = 0;
-                        __syncwarp();
-                    }
-                    if (mk) {   // this round goes out directly
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(P.counts + f, __popc(mk));
-                        base = __shfl_sync(0xffffffffu, base, 0) + __popc(mk & ((1u << lane) - 1u));
-                        if (iskp && base < P.cap) P.keys[(size_t)f * P.cap + base] = key;
-                    }
-                } else {
-                    if (iskp) reinterpret_cast<uint32_t*>(Q)[kn + __popc(mk & ((1u << lane) - 1u))] = key;
-                    kn += __popc(mk);
-                    __syncwarp();
-                }
+        const int total = __popc(mkr[0]) + __popc(mkr[1]) + __popc(mkr[2]) + __popc(mkr[3]);
+        if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(P.counts + f, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int pos = base + __popc(mkr[r] & lt);
+                if (isr[r] && pos < P.cap) out[pos] = keyr[r];
+                base += __popc(mkr[r]);
             }
         }
-        if (kn) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(P.counts + f, kn);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t* kb = reinterpret_cast<const uint32_t*>(Q);
-            for (int i = lane; i < kn; i += 32)
-                if (base + i < P.cap) P.keys[(size_t)f * P.cap + base + i] = kb[i];
+        for (int c0 = 128; c0 < cn; c0 += 32) {
+            uint32_t key = 0;
+            const bool iskp = nms_key(c0 + lane, key);
+            const uint32_t mk = __ballot_sync(0xffffffffu, iskp);
+            if (mk) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(P.counts + f, __popc(mk));
+                base = __shfl_sync(0xffffffffu, base, 0) + __popc(mk & lt);
+                if (iskp && base < P.cap) out[base] = key;
+            }
         }
     }
 }

@@ -79,10 +79,20 @@ struct alva_pipeline {
     alva_ctx* sel_ctx = nullptr;
     cudaStream_t sel_stream = nullptr;
     cudaEvent_t sel_fork = nullptr, sel_join = nullptr, pyr_join = nullptr;
-    alva_ctx* ba_ctx = nullptr;
-    cudaStream_t ba_stream = nullptr;
-    cudaEvent_t ba_fork = nullptr, ba_join = nullptr;
-    bool ba_forked = false;
+    // BA slots.  Slot 0: the step's BA is joined at the end of the SAME step and works in place on the public buffers
+    // (ba_poses / ba_invd / ba_summary).  Slots 1, 2 ("pipeline_ba_lag" = 1): the chain of step s is joined at the end of step
+    // s + 1, two chains in flight on two streams -- a chain is ~60 dependent, latency-bound launches that use a few percent of
+    // the GPU but take longer than the frame stages of a step, so in-step joining makes it the critical path; the mapper of the
+    // reference delivers its results asynchronously in the same way.  These slots solve in private buffers and the joined
+    // result is copied to the public ones (alva_pipeline_drain joins what is still in flight).
+    static constexpr int NBA = 3;
+    alva_ctx* ba_ctx[NBA] = {nullptr, nullptr, nullptr};
+    cudaStream_t ba_stream[NBA] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ba_fork[NBA] = {nullptr, nullptr, nullptr}, ba_join[NBA] = {nullptr, nullptr, nullptr};
+    bool ba_forked[NBA] = {false, false, false};
+    double *ba_wposes[NBA] = {nullptr, nullptr, nullptr}, *ba_winvd[NBA] = {nullptr, nullptr, nullptr}, *ba_wsummary[NBA] = {nullptr, nullptr, nullptr};
+    int ba_last = -1;          // slot forked most recently (-1: none in flight or joined)
+    long long ba_forks = 0;    // lagged forks so far (parity picks the slot)
     bool profile = false;
     long long step_index = 0;
     std::vector<void*> allocs;
@@ -93,8 +103,8 @@ struct alva_pipeline {
     struct Graph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     std::map<std::tuple<const uint8_t*, int, int>, Graph> frame_graphs;
     std::map<std::tuple<const uint8_t*, int, int>, int> frame_runs;   // direct runs seen per key (capture after the first)
-    Graph ba_graph;
-    int ba_runs = 0;
+    Graph ba_graph[NBA];
+    int ba_runs[NBA] = {0, 0, 0};
     bool graphs_failed = false;
     long long graph_replays = 0;
 };
@@ -112,17 +122,22 @@ extern "C" void alva_pipeline_destroy(alva_pipeline* p) {
     AlvaDeviceGuard guard__(p->ctx);
     cudaStreamSynchronize(p->ctx->stream);
     for (auto& kv : p->frame_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    if (p->ba_graph.exec) cudaGraphExecDestroy(p->ba_graph.exec);
+    for (int k = 0; k < alva_pipeline::NBA; k++) {
+        if (p->ba_stream[k]) cudaStreamSynchronize(p->ba_stream[k]);
+        if (p->ba_graph[k].exec) cudaGraphExecDestroy(p->ba_graph[k].exec);
+    }
     for (void* a : p->allocs) cudaFree(a);
     if (p->sel_ctx) { alva_ctx_destroy(p->sel_ctx); p->sel_ctx = nullptr; }
     if (p->sel_stream) { cudaStreamSynchronize(p->sel_stream); cudaStreamDestroy(p->sel_stream); }
     if (p->sel_fork) cudaEventDestroy(p->sel_fork);
     if (p->sel_join) cudaEventDestroy(p->sel_join);
     if (p->pyr_join) cudaEventDestroy(p->pyr_join);
-    if (p->ba_ctx) { alva_ctx_destroy(p->ba_ctx); p->ba_ctx = nullptr; }
-    if (p->ba_stream) { cudaStreamSynchronize(p->ba_stream); cudaStreamDestroy(p->ba_stream); }
-    if (p->ba_fork) cudaEventDestroy(p->ba_fork);
-    if (p->ba_join) cudaEventDestroy(p->ba_join);
+    for (int k = 0; k < alva_pipeline::NBA; k++) {
+        if (p->ba_ctx[k]) { alva_ctx_destroy(p->ba_ctx[k]); p->ba_ctx[k] = nullptr; }
+        if (p->ba_stream[k]) { cudaStreamSynchronize(p->ba_stream[k]); cudaStreamDestroy(p->ba_stream[k]); }
+        if (p->ba_fork[k]) cudaEventDestroy(p->ba_fork[k]);
+        if (p->ba_join[k]) cudaEventDestroy(p->ba_join[k]);
+    }
     if (p->copy_stream) {
         cudaStreamSynchronize(p->copy_stream);
         cudaStreamDestroy(p->copy_stream);
@@ -179,13 +194,17 @@ extern "C" alva_pipeline* alva_pipeline_create(alva_ctx* ctx, const alva_pipelin
         PALLOC(ba_anch_kf, np * nlm * 4); PALLOC(ba_obs_kf, np * nobs * 4); PALLOC(ba_obs_lm, np * nobs * 4);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&p->ba_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
-            cudaEventCreateWithFlags(&p->ba_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&p->ba_join, cudaEventDisableTiming) != cudaSuccess ||
-            !(p->ba_ctx = alva_ctx_create(ctx->device, (void*)p->ba_stream))) {
-            alva_set_error("alva_pipeline_create: BA stream setup failed");
-            alva_pipeline_destroy(p);
-            return nullptr;
+        for (int k = 0; k < alva_pipeline::NBA; k++) {
+            if (cudaStreamCreateWithPriority(&p->ba_stream[k], cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ba_fork[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ba_join[k], cudaEventDisableTiming) != cudaSuccess ||
+                !(p->ba_ctx[k] = alva_ctx_create(ctx->device, (void*)p->ba_stream[k]))) {
+                alva_set_error("alva_pipeline_create: BA stream setup failed");
+                alva_pipeline_destroy(p);
+                return nullptr;
+            }
+            if (k == 0) { p->ba_wposes[0] = p->ba_poses; p->ba_winvd[0] = p->ba_invd; p->ba_wsummary[0] = p->ba_summary; }
+            else { PALLOC(ba_wposes[k], np * nkf * 7 * 8); PALLOC(ba_winvd[k], np * nlm * 8); PALLOC(ba_wsummary[k], np * 8 * 8); }
         }
     }
     if (cudaStreamCreateWithFlags(&p->sel_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -352,6 +371,7 @@ static int pipeline_frames(alva_pipeline* p, const uint8_t* rgba_dev, int f0, in
 // this step's frames), joined at the end: small dependent launches (1 CTA per problem in the factorisation) that would
 // otherwise leave most SMs idle overlap the wide per-frame kernels.
 extern int alva_g_ba_overlap;   // alva_set_option("pipeline_ba_overlap", 0): run BA after the frame stages instead (A/B measurement)
+int alva_g_ba_lag = 0;          // alva_set_option("pipeline_ba_lag", 1): join a step's BA at the end of the NEXT step (two chains in flight)
 
 int alva_g_pipeline_graphs = 1;   // alva_set_option("pipeline_graphs", 0): always launch kernel by kernel
 
@@ -375,51 +395,94 @@ static bool capture_graph(alva_pipeline* p, cudaStream_t st, alva_pipeline::Grap
     return true;
 }
 
-// the BA chain itself, on the BA stream (pristine copies -> working copies, then the solve)
-static int pipeline_ba_body(alva_pipeline* p) {
+// the BA chain itself, on slot k's stream (pristine copies -> working copies, then the solve)
+static int pipeline_ba_body(alva_pipeline* p, int k) {
     const alva_pipeline_config& c = p->cfg;
-    cudaStream_t st = p->ba_stream;
+    cudaStream_t st = p->ba_stream[k];
     const size_t np = p->nprob;
-    ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
-    ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
-    const long long before = p->ba_ctx->launches;
-    const int e = alva_k_ba_solve(p->ba_ctx, p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_poses, p->ba_const, p->ba_invd,
-                                  p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber, c.ba_max_iter,
-                                  p->ba_summary);
-    p->ctx->launches += p->ba_ctx->launches - before;   // one launch counter per pipeline (alva_ctx_launches)
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_wposes[k], p->ba_poses0, np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
+    ALVA_CUDA(cudaMemcpyAsync(p->ba_winvd[k], p->ba_invd0, np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
+    const long long before = p->ba_ctx[k]->launches;
+    const int e = alva_k_ba_solve(p->ba_ctx[k], p->nprob, c.ba_nkf, c.ba_nlm, c.ba_nobs, p->ba_calib, p->ba_wposes[k], p->ba_const,
+                                  p->ba_winvd[k], p->ba_anch_kf, p->ba_anch_uv, p->ba_obs_kf, p->ba_obs_lm, p->ba_obs_uv, c.ba_huber,
+                                  c.ba_max_iter, p->ba_wsummary[k]);
+    p->ctx->launches += p->ba_ctx[k]->launches - before;   // one launch counter per pipeline (alva_ctx_launches)
     return e;
 }
 
-static int pipeline_ba_launch(alva_pipeline* p) {
-    cudaStream_t st = p->ba_stream;
-    ALVA_CUDA(cudaEventRecord(p->ba_fork, p->ctx->stream));
-    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_fork, 0));
-    p->ba_forked = true;
+static int pipeline_ba_launch(alva_pipeline* p, int k) {
+    cudaStream_t st = p->ba_stream[k];
+    ALVA_CUDA(cudaEventRecord(p->ba_fork[k], p->ctx->stream));
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_fork[k], 0));
+    p->ba_forked[k] = true;
+    p->ba_last = k;
     if (graphs_on(p)) {
-        if (!p->ba_graph.exec && p->ba_runs >= 1 && !capture_graph(p, st, p->ba_graph, [&] { return pipeline_ba_body(p); })) p->graphs_failed = true;
-        if (p->ba_graph.exec) {
-            ALVA_CUDA(cudaGraphLaunch(p->ba_graph.exec, st));
-            p->ctx->launches += p->ba_graph.launches;
+        if (!p->ba_graph[k].exec && p->ba_runs[k] >= 1 && !capture_graph(p, st, p->ba_graph[k], [&] { return pipeline_ba_body(p, k); }))
+            p->graphs_failed = true;
+        if (p->ba_graph[k].exec) {
+            ALVA_CUDA(cudaGraphLaunch(p->ba_graph[k].exec, st));
+            p->ctx->launches += p->ba_graph[k].launches;
             p->graph_replays++;
             return 0;
         }
     }
-    p->ba_runs++;
-    return pipeline_ba_body(p);
+    p->ba_runs[k]++;
+    return pipeline_ba_body(p, k);
 }
+
+// main stream waits for slot k's chain; a lagged slot's results go to the public buffers
+static int pipeline_ba_join_slot(alva_pipeline* p, int k) {
+    if (!p->ba_forked[k]) return 0;
+    p->ba_forked[k] = false;
+    if (p->ba_last == k) p->ba_last = -1;
+    cudaStream_t st = p->ctx->stream;
+    ALVA_CUDA(cudaEventRecord(p->ba_join[k], p->ba_stream[k]));
+    ALVA_CUDA(cudaStreamWaitEvent(st, p->ba_join[k], 0));
+    if (k != 0) {
+        const alva_pipeline_config& c = p->cfg;
+        const size_t np = p->nprob;
+        ALVA_CUDA(cudaMemcpyAsync(p->ba_poses, p->ba_wposes[k], np * c.ba_nkf * 56, cudaMemcpyDeviceToDevice, st));
+        ALVA_CUDA(cudaMemcpyAsync(p->ba_invd, p->ba_winvd[k], np * c.ba_nlm * 8, cudaMemcpyDeviceToDevice, st));
+        ALVA_CUDA(cudaMemcpyAsync(p->ba_summary, p->ba_wsummary[k], np * 64, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+static bool ba_lagged() { return alva_g_ba_overlap && alva_g_ba_lag; }
 
 static int pipeline_ba_fork(alva_pipeline* p) {
     if (p->nprob <= 0 || !alva_g_ba_overlap) return 0;
-    return pipeline_ba_launch(p);
+    if (!ba_lagged()) {
+        for (int k = 1; k < alva_pipeline::NBA; k++) if (int e = pipeline_ba_join_slot(p, k)) return e;   // mode switched
+        return pipeline_ba_launch(p, 0);
+    }
+    if (int e = pipeline_ba_join_slot(p, 0)) return e;
+    const int k = 1 + (int)(p->ba_forks++ & 1);
+    if (int e = pipeline_ba_join_slot(p, k)) return e;   // (joined a step ago in the steady state)
+    return pipeline_ba_launch(p, k);
 }
 
+// end of a step: same-step mode joins the step's own chain; lagged mode joins the PREVIOUS step's
 static int pipeline_ba_join(alva_pipeline* p) {
-    if (p->nprob > 0 && !alva_g_ba_overlap && !p->ba_forked)
-        if (int e = pipeline_ba_launch(p)) return e;
-    if (!p->ba_forked) return 0;
-    p->ba_forked = false;
-    ALVA_CUDA(cudaEventRecord(p->ba_join, p->ba_stream));
-    ALVA_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ba_join, 0));
+    if (p->nprob > 0 && !alva_g_ba_overlap && !p->ba_forked[0])
+        if (int e = pipeline_ba_launch(p, 0)) return e;
+    if (!ba_lagged()) {
+        for (int k = 0; k < alva_pipeline::NBA; k++) if (int e = pipeline_ba_join_slot(p, k)) return e;
+        return 0;
+    }
+    const int cur = p->ba_last;
+    for (int k = 0; k < alva_pipeline::NBA; k++)
+        if (k != cur) if (int e = pipeline_ba_join_slot(p, k)) return e;
+    p->ba_last = cur;
+    return 0;
+}
+
+// joins every chain still in flight (lagged mode leaves the last step's); the public BA buffers then hold the newest result
+extern "C" int alva_pipeline_drain(alva_pipeline* p) { AlvaDeviceGuard guard__(p ? p->ctx : nullptr);
+    if (!p) { alva_set_error("alva_pipeline_drain: bad argument"); return ALVA_E_INVALID; }
+    const int cur = p->ba_last;
+    for (int k = 0; k < alva_pipeline::NBA; k++) if (k != cur) if (int e = pipeline_ba_join_slot(p, k)) return e;
+    if (cur >= 0) if (int e = pipeline_ba_join_slot(p, cur)) return e;   // the newest last: its copy wins
     return 0;
 }
 
@@ -459,7 +522,8 @@ extern "C" int alva_pipeline_step_dev(alva_pipeline* p, const uint8_t* rgba_dev)
 // {graphs captured, graph launches so far, 1 if a capture failed and the pipeline fell back to direct launches}
 extern "C" int alva_pipeline_graph_stats(alva_pipeline* p, int32_t* out3) {
     if (!p || !out3) return ALVA_E_INVALID;
-    int n = p->ba_graph.exec ? 1 : 0;
+    int n = 0;
+    for (int k = 0; k < alva_pipeline::NBA; k++) n += p->ba_graph[k].exec ? 1 : 0;
     for (auto& kv : p->frame_graphs) n += kv.second.exec ? 1 : 0;
     out3[0] = n; out3[1] = (int32_t)p->graph_replays; out3[2] = p->graphs_failed ? 1 : 0;
     return 0;

@@ -94,6 +94,7 @@ class LoopClosure:
                      consecutive=e.consecutive, Rt=np.array(list(e.Rt)).reshape(3, 4)) for e in ev[:n]]
 
     def last_scores(self):
+        """[K, world, 4]: putative matches, geometric check passed (0/1), inliers, remote keyframe sequence number"""
         out = np.zeros((self.K, self.world, 4))
         self._chk(self.L.alva_lc_last_scores(self.h, out.ctypes.data_as(C.c_void_p)))
         return out

@@ -86,6 +86,10 @@ class Pipeline:
     def profile(self, on):
         self._chk(self.L.alva_pipeline_profile(self.h, 1 if on else 0))
 
+    def drain(self):
+        """join every BA chain still in flight ("pipeline_ba_lag" = 1 leaves the last step's) into the context stream"""
+        self._chk(self.L.alva_pipeline_drain(self.h))
+
     def graph_stats(self):
         """(CUDA graphs captured, graph launches so far, capture failed -> direct launches)"""
         out = (C.c_int32 * 3)()

@@ -304,13 +304,18 @@ def workload_config(batch, world=1, loop_closure=False):
     return cfg
 
 
+BA_SCHEDULE = ["own high-priority streams, forked at the start of the step; the chain of step s is joined at the end of step s+1 (two chains in "
+               "flight, results delivered one step later as the reference's mapper thread does); the timed region starts drained and "
+               "ends with alva_pipeline_drain, so it holds exactly K frame batches and K x 13 BA solves"]
+
+
 def _workload_config(batch):
     return {"workload": WORKLOAD, "frame": f"{W}x{H} RGBA", "batch_frames_per_step": batch,
             "pyramid": "4 levels + Scharr derivative levels (buildOpticalFlowPyramid withDerivatives, as the reference)",
             "features_per_frame": NFEAT, "fast_threshold": FAST_THR, "orb": "ORB::detectAndCompute semantics, 1 level: FAST-9 -> retainBest(2n) -> Harris -> retainBest(n) -> IC angle -> 7x7 blur -> rBRIEF-256",
             "map_descriptors": MAP_SIZE, "ba": f"{BA_NKF} KF x {BA_NLM} landmarks x {BA_NLM * BA_OBS_PER_LM} obs, LM<={BA_ITERS}",
             "ba_every_n_frames": KF_INTERVAL,
-            "ba_schedule": "own high-priority stream, forked after the front end and joined at the end of the step",
+            "ba_schedule": BA_SCHEDULE[0],
             "l2_policy": f"inputs ({4 * W * H * batch / 1e6:.0f} MB/step) larger than L2 (126 MB)",
             "parallelism": "1 stream batch per GPU"}
 
@@ -344,6 +349,10 @@ def bench_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     ctx = alvaar_b200.Context(local_rank, stream.cuda_stream)
     ctx.L.alva_set_option(b"pipeline_ba_overlap", 0 if args.no_ba_overlap else 1)
+    ctx.L.alva_set_option(b"pipeline_ba_lag", 0 if (args.no_ba_lag or args.no_ba_overlap) else 1)
+    if args.no_ba_lag or args.no_ba_overlap:
+        BA_SCHEDULE[0] = ("own high-priority stream, forked at the start of the step and joined at its end" if not args.no_ba_overlap
+                          else "after the frame stages, same stream (A/B measurement)")
     ctx.L.alva_set_option(b"pipeline_graphs", 0 if args.no_graphs else 1)
     pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE | alvaar_b200.ORB_HARRIS,
                     map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
@@ -406,6 +415,7 @@ def bench_b200(args, rank, world, local_rank):
             pipe.step_dev(d_in)
             if lc:
                 lc()
+        pipe.drain()
         barrier()
         l0 = ctx.launches
         sampler.start()
@@ -415,6 +425,7 @@ def bench_b200(args, rank, world, local_rank):
             pipe.step_dev(d_in)
             if lc:
                 gathered = lc()
+        pipe.drain()   # the last step's BA chain belongs to the timed region
         ev1.record(stream)
         barrier()
         launches = ctx.launches - l0
@@ -426,6 +437,7 @@ def bench_b200(args, rank, world, local_rank):
         pipe.profile(True)
         for _ in range(args.steps):
             pipe.step_dev(d_in)
+        pipe.drain()
         barrier()
         fe = pipe.frontend_ms(args.steps)
         pipe.profile(False)
@@ -437,6 +449,7 @@ def bench_b200(args, rank, world, local_rank):
                 torch.zeros_like(poses_host).pin_memory(), torch.zeros_like(summ_host).pin_memory())]
         for _ in range(min(args.warmup, 2)):
             pipe.step_host(host_in, *res[0])
+        pipe.drain()
         barrier()
         e2e_steps = max(2, min(args.steps, 10))
         t0 = time.perf_counter()
@@ -446,6 +459,7 @@ def bench_b200(args, rank, world, local_rank):
             if i >= 1:
                 pipe.wait()
         pipe.wait()
+        pipe.drain()
         ev1.record(stream)
         barrier()
         e2e_ms = ev0.elapsed_time(ev1)
@@ -781,6 +795,7 @@ def main():
                          "serialisation of the 8 concurrent System threads corrupted its own heap at visit 9)")
     ap.add_argument("--no-ba-overlap", action="store_true", help="run the local BA after the frame stages instead of beside them")
     ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
+    ap.add_argument("--no-ba-lag", action="store_true", help="join a step's BA chain at the end of the same step (pipeline_ba_lag = 0)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs (profiling aid)")
     args = ap.parse_args()
     select_config(args.config)

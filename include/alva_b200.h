@@ -288,6 +288,8 @@ int alva_k_ba_local(alva_ctx*, int nprob, int nkf, int nlm, int nobs, const doub
  * same results by construction, checked by host emulation, not yet validated on a GPU) -- default 0.
  * "pipeline_ba_overlap" = 0: alva_pipeline runs the local BA after the per-frame stages instead of beside them on its own
  * stream (default 1; results are identical, only the schedule changes).
+ * "pipeline_ba_lag" = 1: the BA chain of step s is joined at the end of step s + 1 instead of step s (default 0; per-step results
+ * are the same numbers, delivered one step later; see alva_pipeline_drain).
  * "pipeline_graphs" = 0: alva_pipeline launches kernel by kernel instead of replaying CUDA graphs (default 1; results identical).
  * "knn_qpw" = 4 | 8: queries a warp of the Hamming matcher keeps in registers (8: 128 registers / 16 warps per SM;
  * 4: 80 registers / 24 warps per SM).  Results are identical.
@@ -356,6 +358,11 @@ int  alva_pipeline_frontend_ms(alva_pipeline*, float* ms, int n);   /* CUDA-even
 int  alva_pipeline_info(const alva_pipeline*, int32_t* out4);
 /* {CUDA graphs captured so far, graph launches so far, 1 if a capture failed and the pipeline fell back to direct launches} */
 int  alva_pipeline_graph_stats(alva_pipeline*, int32_t* out3);
+/* With alva_set_option("pipeline_ba_lag", 1) a step's local-BA chain is joined at the end of the NEXT step (two chains in
+ * flight on two streams; a step then delivers the BA poses / summary of the step before it, as the reference's mapper thread
+ * delivers its results asynchronously).  alva_pipeline_drain makes the context stream wait for every chain still in flight;
+ * afterwards the BA buffers hold the newest step's result.  A no-op in the default (same-step) mode. */
+int  alva_pipeline_drain(alva_pipeline*);
 void* alva_pipeline_buffer(alva_pipeline*, int which);
 
 /* ---- System: the reference's public class, one handle per camera stream ------------------------

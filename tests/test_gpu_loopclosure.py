@@ -79,7 +79,7 @@ def test_wire_format_and_planted_revisit(gpu_ctx):
     for s in sc:
         assert (s[:, 1, 0] >= 30).all() and (s[:, 1, 1] == 1).all()      # stream 1: many putative matches, RANSAC succeeds
         assert (4 * s[:, 2, 0] < s[:, 1, 0]).all() and (s[:, 2, 1] == 0).all()   # stream 2: a few chance matches (~6 % of the keypoints), no geometry
-        assert (s[:, 0] == 0).all()                                      # a stream is not matched against itself
+        assert (s[:, 0, :3] == 0).all()                                  # a stream is not matched against itself (field 3: the block's keyframe number)
     R = ev[0]["Rt"][:, :3]
     assert np.abs(R @ R.T - np.eye(3)).max() < 1e-9 and np.abs(R - np.eye(3)).max() < 0.05    # two frames apart: nearly the same view
 
