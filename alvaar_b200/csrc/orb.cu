@@ -19,7 +19,7 @@
 
 namespace {
 
-__constant__ int8_t c_pattern[1024] = {
+__constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 // getGaussianKernel(7, 2, CV_32F) (imgproc/src/smooth.dispatch.cpp:76-190): k[3], k[2]=k[4], k[1]=k[5], k[0]=k[6]
@@ -193,8 +193,11 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
                                                            const int32_t* __restrict__ npts_per_frame, int npts, int flags,
                                                            uint8_t* __restrict__ desc, uint8_t* __restrict__ kept,
                                                            float* __restrict__ angles_out) {
-    __shared__ int8_t pat_s[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) pat_s[i] = c_pattern[i];
+    // the 256 test pairs as words (x0, y0, x1, y1), TRANSPOSED: pair 8 * lane + t sits at [t][lane], so the 8 loads of a warp are
+    // conflict-free (pair-major order put the lanes 32 bytes apart: 4 byte loads per pair, each 8-way bank conflicted --
+    // 81 % of this kernel's shared-memory wavefronts, profiles/r02_kernels_full.txt)
+    __shared__ uint32_t pat_s[8][32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) pat_s[i & 7][i >> 3] = reinterpret_cast<const uint32_t*>(c_pattern)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.y;
@@ -249,8 +252,8 @@ __global__ void __launch_bounds__(256) orb_describe_kernel(const uint8_t* __rest
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        const int8_t* p = pat_s + 4 * (8 * lane + t);
-        const float p0x = (float)p[0], p0y = (float)p[1], p1x = (float)p[2], p1y = (float)p[3];
+        const uint32_t pw = pat_s[t][lane];
+        const float p0x = (float)(int8_t)pw, p0y = (float)(int8_t)(pw >> 8), p1x = (float)(int8_t)(pw >> 16), p1y = (float)(int8_t)(pw >> 24);
         const int x0 = __float2int_rn(__fsub_rn(__fmul_rn(p0x, a), __fmul_rn(p0y, b)));
         const int y0 = __float2int_rn(__fadd_rn(__fmul_rn(p0x, b), __fmul_rn(p0y, a)));
         const int x1 = __float2int_rn(__fsub_rn(__fmul_rn(p1x, a), __fmul_rn(p1y, b)));

@@ -304,9 +304,7 @@ def workload_config(batch, world=1, loop_closure=False):
     return cfg
 
 
-BA_SCHEDULE = ["own high-priority streams, forked at the start of the step; the chain of step s is joined at the end of step s+1 (two chains in "
-               "flight, results delivered one step later as the reference's mapper thread does); the timed region starts drained and "
-               "ends with alva_pipeline_drain, so it holds exactly K frame batches and K x 13 BA solves"]
+BA_SCHEDULE = ["own high-priority stream, forked after the front end and joined at the end of the step"]
 
 
 def _workload_config(batch):
@@ -349,10 +347,14 @@ def bench_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     ctx = alvaar_b200.Context(local_rank, stream.cuda_stream)
     ctx.L.alva_set_option(b"pipeline_ba_overlap", 0 if args.no_ba_overlap else 1)
-    ctx.L.alva_set_option(b"pipeline_ba_lag", 0 if (args.no_ba_lag or args.no_ba_overlap) else 1)
-    if args.no_ba_lag or args.no_ba_overlap:
-        BA_SCHEDULE[0] = ("own high-priority stream, forked at the start of the step and joined at its end" if not args.no_ba_overlap
-                          else "after the frame stages, same stream (A/B measurement)")
+    lag = args.ba_lag and not args.no_ba_overlap
+    ctx.L.alva_set_option(b"pipeline_ba_lag", 1 if lag else 0)
+    if args.no_ba_overlap:
+        BA_SCHEDULE[0] = "after the frame stages, same stream (A/B measurement)"
+    elif lag:
+        BA_SCHEDULE[0] = ("own high-priority streams; the chain of step s is joined at the end of step s+1 (two chains in flight, results "
+                          "delivered one step later as the reference's mapper thread does); the timed region starts drained and ends with "
+                          "alva_pipeline_drain, so it holds exactly K frame batches and K x 13 BA solves")
     ctx.L.alva_set_option(b"pipeline_graphs", 0 if args.no_graphs else 1)
     pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE | alvaar_b200.ORB_HARRIS,
                     map_size=MAP_SIZE, kf_interval=KF_INTERVAL, ba_nkf=BA_NKF, ba_nlm=BA_NLM, ba_nobs=len(ba["obs_kf"]),
@@ -795,7 +797,9 @@ def main():
                          "serialisation of the 8 concurrent System threads corrupted its own heap at visit 9)")
     ap.add_argument("--no-ba-overlap", action="store_true", help="run the local BA after the frame stages instead of beside them")
     ap.add_argument("--no-loop-closure", action="store_true", help="N > 1: skip the NCCL keyframe-descriptor all-gather")
-    ap.add_argument("--no-ba-lag", action="store_true", help="join a step's BA chain at the end of the same step (pipeline_ba_lag = 0)")
+    ap.add_argument("--ba-lag", action="store_true",
+                    help="join a step's BA chain at the end of the NEXT step (pipeline_ba_lag = 1; measured +6 %% frames/s, but the chain "
+                         "then shares the GPU with the next step's front end, whose launch the roofline figure times)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs (profiling aid)")
     args = ap.parse_args()
     select_config(args.config)
