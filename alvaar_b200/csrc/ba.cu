@@ -202,6 +202,31 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
     return sm[0];
 }
 
+// the same for any block size that is a multiple of 32 (<= 1024): butterfly inside each warp, then the warps in order.  Every
+// thread of the block must call; the result is returned to all.  sm: >= 33 doubles.
+__device__ __forceinline__ double block_sum_dyn(double v, double* sm) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();   // earlier readers of sm are done
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < nw; w++) t += sm[w]; sm[32] = t; }
+    __syncthreads();
+    return sm[32];
+}
+__device__ __forceinline__ double block_max_dyn(double v, double* sm) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = sm[0]; for (int w = 1; w < nw; w++) t = fmax(t, sm[w]); sm[32] = t; }
+    __syncthreads();
+    return sm[32];
+}
+
 // ------------------------------------------------------------------------------------------ setup (1 CTA / problem)
 // Structure of the problem, computed once per solve: free-pose columns, landmark -> observation CSR, and per free pose
 // the list of (landmark, slot) pairs that see it (slot 0 = anchor keyframe, 1 + k = the landmark's k-th observation).
@@ -353,6 +378,27 @@ __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem
 // ------------------------------------------------------------------------------------------ linearise (thread / obs)
 // FULL: residuals + Jacobians at the current point (column norms and gradient follow in ba_stats_kernel, without atomics);
 // otherwise cost only at the candidate point.  Per-block cost partials (deterministic order in the control kernels).
+// one observation: cost (FULL: + corrected residual and Jacobians stored) at `poses` / `invd_l`
+template <bool FULL>
+__device__ __forceinline__ double lin_obs(const BaProblem& P, const BaDims& D, int o, int l, const double* poses, double invd_l) {
+    const int ka = P.anch_kf[l], kp = P.obs_kf[o];
+    double r[2], Ja[12], Jp[12], Jd[2];
+    ba_evaluate(P.calib, poses + 7 * ka, poses + 7 * kp, invd_l, P.obs_uv[2 * o], P.obs_uv[2 * o + 1], P.anch_uv[2 * l],
+                P.anch_uv[2 * l + 1], r, FULL ? Ja : nullptr, Jp, Jd);
+    double rho0, rho1;
+    huber(r[0] * r[0] + r[1] * r[1], D.huber, rho0, rho1);
+    if (FULL) {
+        const double sc = sqrt(rho1);
+        r[0] *= sc; r[1] *= sc;
+        P.res[2 * o] = r[0]; P.res[2 * o + 1] = r[1];
+        Jd[0] *= sc; Jd[1] *= sc;
+        P.Jd[2 * o] = Jd[0]; P.Jd[2 * o + 1] = Jd[1];
+#pragma unroll
+        for (int i = 0; i < 12; i++) { Ja[i] *= sc; Jp[i] *= sc; P.Ja[12 * o + i] = Ja[i]; P.Jp[12 * o + i] = Jp[i]; }
+    }
+    return 0.5 * rho0;
+}
+
 template <bool FULL>
 __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
@@ -363,63 +409,32 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProbl
     const int o = blockIdx.x * LIN_THREADS + threadIdx.x;
     double cost = 0;
     const int l = o < D.nobs ? P.obs_lm[o] : -1;
-    if (l >= 0) {
-        const double* poses = FULL ? P.poses : P.cand_poses;
-        const double* invd = FULL ? P.invd : P.cand_invd;
-        const int ka = P.anch_kf[l], kp = P.obs_kf[o];
-        double r[2], Ja[12], Jp[12], Jd[2];
-        ba_evaluate(P.calib, poses + 7 * ka, poses + 7 * kp, invd[l], P.obs_uv[2 * o], P.obs_uv[2 * o + 1], P.anch_uv[2 * l],
-                    P.anch_uv[2 * l + 1], r, FULL ? Ja : nullptr, Jp, Jd);
-        double rho0, rho1;
-        huber(r[0] * r[0] + r[1] * r[1], D.huber, rho0, rho1);
-        cost = 0.5 * rho0;
-        if (FULL) {
-            const double sc = sqrt(rho1);
-            r[0] *= sc; r[1] *= sc;
-            P.res[2 * o] = r[0]; P.res[2 * o + 1] = r[1];
-            Jd[0] *= sc; Jd[1] *= sc;
-            P.Jd[2 * o] = Jd[0]; P.Jd[2 * o + 1] = Jd[1];
-#pragma unroll
-            for (int i = 0; i < 12; i++) { Ja[i] *= sc; Jp[i] *= sc; P.Ja[12 * o + i] = Ja[i]; P.Jp[12 * o + i] = Jp[i]; }
-        }
-    }
+    if (l >= 0) cost = lin_obs<FULL>(P, D, o, l, FULL ? P.poses : P.cand_poses, (FULL ? P.invd : P.cand_invd)[l]);
     const double tot = block_sum<LIN_THREADS>(cost, red);
     if (threadIdx.x == 0) P.cost_part[blockIdx.x] = tot;
 }
 
-// ------------------------------------------------------------------------------------------ column norms and gradient
-// Squared column norms of the (unscaled) Jacobian and the gradient J'r, in fixed summation order:
-//   blocks [0, nbs)          : thread per landmark -> inverse-depth column (ne, ge)
-//   blocks [nbs, nbs+NBMAX)  : 4 warps per free pose over its (landmark, slot) list -> 6 pose columns (nf, gf)
-__global__ void __launch_bounds__(BS_THREADS) ba_stats_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.y];
-    const BaState& st = *P.st;
-    if (st.done || !st.relin) return;
-    __shared__ double part[4][12];
-    if ((int)blockIdx.x < D.nbs) {
-        const int l = blockIdx.x * BS_THREADS + threadIdx.x;
-        if (l >= D.nlm) return;
-        double ne = 0, ge = 0;
-        for (int i = P.lm_start[l]; i < P.lm_start[l + 1]; i++) {
-            const int o = P.lm_obs[i];
-            const double d0 = P.Jd[2 * o], d1 = P.Jd[2 * o + 1];
-            ne += d0 * d0 + d1 * d1;
-            ge += d0 * P.res[2 * o] + d1 * P.res[2 * o + 1];
-        }
-        P.ne[l] = ne;
-        P.ge[l] = ge;
-        return;
+// squared column norm and gradient entry of one landmark's inverse-depth column
+__device__ __forceinline__ void stats_landmark(const BaProblem& P, int l) {
+    double ne = 0, ge = 0;
+    for (int i = P.lm_start[l]; i < P.lm_start[l + 1]; i++) {
+        const int o = P.lm_obs[i];
+        const double d0 = P.Jd[2 * o], d1 = P.Jd[2 * o + 1];
+        ne += d0 * d0 + d1 * d1;
+        ge += d0 * P.res[2 * o] + d1 * P.res[2 * o + 1];
     }
-    const int b = blockIdx.x - D.nbs;
-    if (b >= st.ncols / 6) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    P.ne[l] = ne;
+    P.ge[l] = ge;
+}
+// thread gt of the BS_THREADS that share free pose b: its share (stride BS_THREADS over the pose's (landmark, slot) list) of the
+// six squared column norms v[0..5] and gradient entries v[6..11]
+__device__ __forceinline__ void stats_pose_partial(const BaProblem& P, int b, int gt, double* v) {
     int eb = 0;
     for (int i = 0; i < b; i++) eb += P.pstart[i + 1];
     const int ee = eb + P.pstart[b + 1];
-    double v[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) v[i] = 0;
-    for (int idx = eb + threadIdx.x; idx < ee; idx += BS_THREADS) {
+    for (int idx = eb + gt; idx < ee; idx += BS_THREADS) {
         const uint32_t en = P.plist[idx];
         const int l = en >> 8, su = en & 0xff;
         const int ob = P.lm_start[l];
@@ -445,6 +460,28 @@ __global__ void __launch_bounds__(BS_THREADS) ba_stats_kernel(const BaProblem* _
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------ column norms and gradient
+// Squared column norms of the (unscaled) Jacobian and the gradient J'r, in fixed summation order:
+//   blocks [0, nbs)          : thread per landmark -> inverse-depth column (ne, ge)
+//   blocks [nbs, nbs+NBMAX)  : 4 warps per free pose over its (landmark, slot) list -> 6 pose columns (nf, gf)
+__global__ void __launch_bounds__(BS_THREADS) ba_stats_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    const BaState& st = *P.st;
+    if (st.done || !st.relin) return;
+    __shared__ double part[4][12];
+    if ((int)blockIdx.x < D.nbs) {
+        const int l = blockIdx.x * BS_THREADS + threadIdx.x;
+        if (l >= D.nlm) return;
+        stats_landmark(P, l);
+        return;
+    }
+    const int b = blockIdx.x - D.nbs;
+    if (b >= st.ncols / 6) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[12];
+    stats_pose_partial(P, b, threadIdx.x, v);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
 #pragma unroll
@@ -544,30 +581,29 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
 // ------------------------------------------------------------------------------------------ control: before the step
 // TrustRegionMinimizer::{IterationZero, FinalizeIterationAndCheckIfMinimizerCanContinue} + LM ComputeStep's diagonal.
 constexpr int CT_THREADS = 1024;   // control kernels: one CTA per problem; their loops over landmarks are chains of L2 round trips, so be wide
-__global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.x];
+// (one CTA of any size that is a multiple of 32; every thread calls)
+__device__ void ba_pre_body(const BaProblem& P, const BaDims& D) {
     BaState& st = *P.st;
-    __shared__ double red[CT_THREADS];
+    __shared__ double red[34];
     __shared__ int go;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x;
     const int n = st.ncols;
     if (st.done) return;
     if (st.relin) {
         // cost at the (new) current point, in a fixed summation order
         double c = 0;
-        for (int i = tid; i < D.nblk; i += CT_THREADS) c += P.cost_part[i];
-        const double x_cost = block_sum<CT_THREADS>(c, red);
+        for (int i = tid; i < D.nblk; i += NT) c += P.cost_part[i];
+        const double x_cost = block_sum_dyn(c, red);
         // |x|
         double xn = 0;
-        for (int k = tid; k < D.nkf; k += CT_THREADS)
+        for (int k = tid; k < D.nkf; k += NT)
             if (P.pose_col[k] >= 0) for (int i = 0; i < 7; i++) xn += P.poses[7 * k + i] * P.poses[7 * k + i];
-        for (int l = tid; l < D.nlm; l += CT_THREADS)
+        for (int l = tid; l < D.nlm; l += NT)
             if (P.lm_start[l + 1] > P.lm_start[l]) xn += P.invd[l] * P.invd[l];
-        __syncthreads();
-        xn = block_sum<CT_THREADS>(xn, red);
+        xn = block_sum_dyn(xn, red);
         // gradient max-norm |x - Plus(x, -g)|_inf
         double gm = 0;
-        for (int k = tid; k < D.nkf; k += CT_THREADS) {
+        for (int k = tid; k < D.nkf; k += NT) {
             const int c0 = P.pose_col[k];
             if (c0 < 0) continue;
             double dlt[6], out[7];
@@ -575,16 +611,12 @@ __global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __r
             se3_plus(P.poses + 7 * k, dlt, out);
             for (int i = 0; i < 7; i++) gm = fmax(gm, fabs(P.poses[7 * k + i] - out[i]));
         }
-        for (int l = tid; l < D.nlm; l += CT_THREADS)
+        for (int l = tid; l < D.nlm; l += NT)
             if (P.lm_start[l + 1] > P.lm_start[l]) gm = fmax(gm, fabs(P.ge[l]));
-        __syncthreads();
-        red[tid] = gm;
-        __syncthreads();
-        for (int s = CT_THREADS / 2; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); __syncthreads(); }
-        gm = red[0];
+        gm = block_max_dyn(gm, red);
         if (st.iteration == 0) {   // Jacobi scaling is fixed at iteration 0 (trust_region_minimizer.cc:266-275)
-            for (int i = tid; i < n; i += CT_THREADS) P.scf[i] = 1.0 / (1.0 + sqrt(P.nf[i]));
-            for (int l = tid; l < D.nlm; l += CT_THREADS) P.sce[l] = 1.0 / (1.0 + sqrt(P.ne[l]));
+            for (int i = tid; i < n; i += NT) P.scf[i] = 1.0 / (1.0 + sqrt(P.nf[i]));
+            for (int l = tid; l < D.nlm; l += NT) P.sce[l] = 1.0 / (1.0 + sqrt(P.ne[l]));
         }
         __syncthreads();
         if (tid == 0) {
@@ -615,19 +647,24 @@ __global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __r
     const bool reuse = st.reuse_diagonal;
     const double radius = st.radius;
     __syncthreads();   // everyone has read the state before thread 0 updates it below
-    for (int i = tid; i < n; i += CT_THREADS) {
+    for (int i = tid; i < n; i += NT) {
         if (!reuse) P.diagf[i] = fmin(fmax(P.nf[i] * P.scf[i] * P.scf[i], 1e-6), 1e32);
         P.Df[i] = sqrt(P.diagf[i] / radius);
     }
-    for (int l = tid; l < D.nlm; l += CT_THREADS) {
+    for (int l = tid; l < D.nlm; l += NT) {
         if (!reuse) P.diage[l] = fmin(fmax(P.ne[l] * P.sce[l] * P.sce[l], 1e-6), 1e32);
         P.De[l] = sqrt(P.diage[l] / radius);
     }
-    for (int i = tid; i < NMAX * NMAX; i += CT_THREADS) P.S[i] = 0;
-    for (int i = tid; i < NMAX; i += CT_THREADS) P.rhs[i] = 0;
+    for (int i = tid; i < NMAX * NMAX; i += NT) P.S[i] = 0;
+    for (int i = tid; i < NMAX; i += NT) P.rhs[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += CT_THREADS) P.S[i * NMAX + i] = P.Df[i] * P.Df[i];
+    for (int i = tid; i < n; i += NT) P.S[i * NMAX + i] = P.Df[i] * P.Df[i];
     if (tid == 0) st.reuse_diagonal = 1;
+}
+
+__global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    ba_pre_body(P, D);
 }
 
 // ------------------------------------------------------------------------------------------ Schur (thread / landmark)
@@ -636,12 +673,7 @@ __global__ void __launch_bounds__(CT_THREADS) ba_pre_kernel(const BaProblem* __r
 // Wt = diag(E'E + D^2)^-1/2 (E'F)  (nlm x 128, zero outside the landmark's pose blocks) is written for the FP64
 // tensor-core SYRK below (S -= Wt' Wt), which is where that term is a genuine dense contraction.
 template <bool DENSE>
-__global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.y];
-    if (P.st->done) return;
-    if (!DENSE && P.st->use_gather) return;   // the gather path already assembled S
-    const int l = blockIdx.x * 128 + threadIdx.x;
-    if (l >= D.nlm_pad) return;
+__device__ void schur_landmark(const BaProblem& P, const BaDims& D, int l) {
     if (DENSE) {   // rows are rewritten every iteration; padding rows and unused landmarks stay zero
         double* row = P.Wt + (size_t)l * NMAX;
         for (int i = 0; i < NMAX; i++) row[i] = 0.0;
@@ -742,6 +774,16 @@ __global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restri
     }
 }
 
+template <bool DENSE>
+__global__ void __launch_bounds__(128) ba_schur_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    if (P.st->done) return;
+    if (!DENSE && P.st->use_gather) return;   // the gather path already assembled S
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= D.nlm_pad) return;
+    schur_landmark<DENSE>(P, D, l);
+}
+
 // ------------------------------------------------------------------------------------------ dense Schur term on tensor cores
 // S -= Wt' * Wt  with Wt [K = nlm_pad][128] row-major, FP64 tensor-core MMA (mma.sync.m8n8k4.f64 -> SASS DMMA; tcgen05 has
 // no FP64 kind).  Grid: (16 output blocks of 32x32) x (K splits) x problems; 4 warps per CTA interleave the K steps, the
@@ -807,11 +849,7 @@ __global__ void __launch_bounds__(128) ba_syrk_dmma_kernel(const BaProblem* __re
 // order) by ba_plist_kernel; every LM iteration then runs ba_lm_kernel (per-landmark E'E, E'b, F'e) and ba_gather_kernel
 // (one warp per block, fixed summation order -> bit-reproducible results, zero atomics).
 // per-landmark Schur ingredients: E'E + D^2, E'b, F'e for the anchor slot (wa) and every observation slot (wp)
-__global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.y];
-    if (P.st->done || !P.st->use_gather) return;
-    const int l = blockIdx.x * 128 + threadIdx.x;
-    if (l >= D.nlm) return;
+__device__ __forceinline__ void lm_landmark(const BaProblem& P, int l) {
     const int b = P.lm_start[l], e = P.lm_start[l + 1];
     if (e == b) return;
     const int ca = P.pose_col[P.anch_kf[l]];
@@ -831,6 +869,12 @@ __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict_
     P.ete[l] = ete;
     P.etb[l] = etb;
     for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
+}
+__global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.y];
+    if (P.st->done || !P.st->use_gather) return;
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l < D.nlm) lm_landmark(P, l);
 }
 
 // Contribution of one (landmark, slot_u, slot_v) entry to block (bi, bj):  C = F_u'F_v - w_u w_v' / (E'E + D^2)  and, for
@@ -1002,11 +1046,9 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
 // forward substitution z = L^-1 b falls out of the same updates.  Then x = L^-T D^-1 z by warp 0 (lane-strided, registers).
 // No square roots; fixed operation order (bit-reproducible).  yf = S^-1 rhs.
 constexpr int CH_TILES = 32 * 33 / 2, CH_THREADS = (CH_TILES + 31) / 32 * 32;   // 528 tiles -> 544 threads
-__global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    extern __shared__ double sm[];
-    const BaProblem P = probs[blockIdx.x];
+// (a CTA of exactly CH_THREADS threads; sm: (NMAX * (NMAX + 1) + NMAX) doubles of shared memory)
+__device__ void ba_chol_body(const BaProblem& P, double* sm) {
     BaState& st = *P.st;
-    if (st.done) return;
     const int n = st.ncols, tid = threadIdx.x, lane = tid & 31;
     const int ld = NMAX + 1;
     double* V = sm;                 // (n + 1) x ld, filled after the factorisation for the backward solve
@@ -1109,70 +1151,79 @@ __global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __
         if (lane == 0) st.chol_ok = ok_s;
     }
 }
+__global__ void __launch_bounds__(CH_THREADS) ba_chol_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    extern __shared__ double sm[];
+    const BaProblem P = probs[blockIdx.x];
+    if (P.st->done) return;
+    ba_chol_body(P, sm);
+}
 
 // ------------------------------------------------------------------------------------------ back-substitution (thread / landmark)
 // ye = (E'b - E'F yf) / (E'E + D^2), candidate inverse depths, this landmark's share of the model cost change
 // -(J s)'(r + J s / 2); CTA (0, p) also builds the candidate poses Plus(x, delta).
+// candidate pose of keyframe k: Plus(x, -yf * scale) for a free pose, a copy otherwise
+__device__ __forceinline__ void backsub_cand_pose(const BaProblem& P, int k, double* out) {
+    const int c0 = P.pose_col[k];
+    if (c0 >= 0) {
+        double dlt[6];
+        for (int i = 0; i < 6; i++) dlt[i] = -P.yf[c0 + i] * P.scf[c0 + i];
+        se3_plus(P.poses + 7 * k, dlt, out);
+    } else
+        for (int i = 0; i < 7; i++) out[i] = P.poses[7 * k + i];
+}
+// one landmark: ye, candidate inverse depth, and its share of the model cost change (returned)
+__device__ __forceinline__ double backsub_landmark(const BaProblem& P, int l) {
+    const int b = P.lm_start[l], e = P.lm_start[l + 1];
+    double ye = 0, acc = 0;
+    if (e > b) {
+        double s = P.etb[l];
+        const int ca = P.pose_col[P.anch_kf[l]];
+        if (ca >= 0) for (int c = 0; c < 6; c++) s -= P.wa[6 * l + c] * P.yf[ca + c];
+        for (int i = b; i < e; i++) {
+            const int o = P.lm_obs[i];
+            const int cp = P.pose_col[P.obs_kf[o]];
+            if (cp >= 0) for (int c = 0; c < 6; c++) s -= P.wp[6 * o + c] * P.yf[cp + c];
+        }
+        ye = s / P.ete[l];
+        const double se = -ye * P.sce[l];
+        for (int i = b; i < e; i++) {
+            const int o = P.lm_obs[i];
+            const int cp = P.pose_col[P.obs_kf[o]];
+            double m0 = P.Jd[2 * o] * se, m1 = P.Jd[2 * o + 1] * se;
+            for (int c = 0; c < 6; c++) {
+                if (ca >= 0) { const double q = -P.yf[ca + c] * P.scf[ca + c]; m0 += P.Ja[12 * o + c] * q; m1 += P.Ja[12 * o + 6 + c] * q; }
+                if (cp >= 0) { const double q = -P.yf[cp + c] * P.scf[cp + c]; m0 += P.Jp[12 * o + c] * q; m1 += P.Jp[12 * o + 6 + c] * q; }
+            }
+            acc += m0 * (P.res[2 * o] + m0 / 2.0) + m1 * (P.res[2 * o + 1] + m1 / 2.0);
+        }
+        P.cand_invd[l] = P.invd[l] + se;
+    } else
+        P.cand_invd[l] = P.invd[l];
+    P.ye[l] = ye;
+    return acc;
+}
 __global__ void __launch_bounds__(BS_THREADS) ba_backsub_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     __shared__ double red[BS_THREADS];
     if (P.st->done) return;
     const int l = blockIdx.x * BS_THREADS + threadIdx.x;
-    double acc = 0;
-    if (blockIdx.x == 0 && (int)threadIdx.x < D.nkf) {
-        const int k = threadIdx.x, c0 = P.pose_col[k];
-        if (c0 >= 0) {
-            double dlt[6];
-            for (int i = 0; i < 6; i++) dlt[i] = -P.yf[c0 + i] * P.scf[c0 + i];
-            se3_plus(P.poses + 7 * k, dlt, P.cand_poses + 7 * k);
-        } else
-            for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = P.poses[7 * k + i];
-    }
-    if (l < D.nlm) {
-        const int b = P.lm_start[l], e = P.lm_start[l + 1];
-        double ye = 0;
-        if (e > b) {
-            double s = P.etb[l];
-            const int ca = P.pose_col[P.anch_kf[l]];
-            if (ca >= 0) for (int c = 0; c < 6; c++) s -= P.wa[6 * l + c] * P.yf[ca + c];
-            for (int i = b; i < e; i++) {
-                const int o = P.lm_obs[i];
-                const int cp = P.pose_col[P.obs_kf[o]];
-                if (cp >= 0) for (int c = 0; c < 6; c++) s -= P.wp[6 * o + c] * P.yf[cp + c];
-            }
-            ye = s / P.ete[l];
-            const double se = -ye * P.sce[l];
-            for (int i = b; i < e; i++) {
-                const int o = P.lm_obs[i];
-                const int cp = P.pose_col[P.obs_kf[o]];
-                double m0 = P.Jd[2 * o] * se, m1 = P.Jd[2 * o + 1] * se;
-                for (int c = 0; c < 6; c++) {
-                    if (ca >= 0) { const double q = -P.yf[ca + c] * P.scf[ca + c]; m0 += P.Ja[12 * o + c] * q; m1 += P.Ja[12 * o + 6 + c] * q; }
-                    if (cp >= 0) { const double q = -P.yf[cp + c] * P.scf[cp + c]; m0 += P.Jp[12 * o + c] * q; m1 += P.Jp[12 * o + 6 + c] * q; }
-                }
-                acc += m0 * (P.res[2 * o] + m0 / 2.0) + m1 * (P.res[2 * o + 1] + m1 / 2.0);
-            }
-            P.cand_invd[l] = P.invd[l] + se;
-        } else
-            P.cand_invd[l] = P.invd[l];
-        P.ye[l] = ye;
-    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < D.nkf) backsub_cand_pose(P, threadIdx.x, P.cand_poses + 7 * threadIdx.x);
+    const double acc = l < D.nlm ? backsub_landmark(P, l) : 0.0;
     const double tot = block_sum<BS_THREADS>(acc, red);
     if (threadIdx.x == 0) P.mc_part[blockIdx.x] = tot;
 }
 
 // ------------------------------------------------------------------------------------------ control: after the step
-__global__ void __launch_bounds__(CT_THREADS) ba_post_kernel(const BaProblem* __restrict__ probs, BaDims D) {
-    const BaProblem P = probs[blockIdx.x];
+__device__ void ba_post_body(const BaProblem& P, const BaDims& D) {
     BaState& st = *P.st;
-    __shared__ double red[CT_THREADS];
+    __shared__ double red[34];
     __shared__ int accept_s;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x;
     if (st.done) return;
     // model cost change -(J s)'(r + J s / 2) from the back-substitution partials (fixed order)
     double mcs = 0;
-    for (int i = tid; i < D.nbs; i += CT_THREADS) mcs += P.mc_part[i];
-    const double model_change = -block_sum<CT_THREADS>(mcs, red);
+    for (int i = tid; i < D.nbs; i += NT) mcs += P.mc_part[i];
+    const double model_change = -block_sum_dyn(mcs, red);
     const bool valid = st.chol_ok && (model_change > 0.0);
     __syncthreads();
     if (!valid) {   // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
@@ -1189,21 +1240,20 @@ __global__ void __launch_bounds__(CT_THREADS) ba_post_kernel(const BaProblem* __
     if (P.last_poses) {
         // the candidate has been evaluated (cost-only pass): from here until the next valid step it is the point the
         // reference's functors were evaluated at last, whether or not the step is accepted or a tolerance ends the solve
-        for (int i = tid; i < 7 * D.nkf; i += CT_THREADS) P.last_poses[i] = P.cand_poses[i];
-        for (int l = tid; l < D.nlm; l += CT_THREADS) P.last_invd[l] = P.cand_invd[l];
+        for (int i = tid; i < 7 * D.nkf; i += NT) P.last_poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += NT) P.last_invd[l] = P.cand_invd[l];
         if (tid == 0) st.has_last = 1;
     }
     double c = 0;
-    for (int i = tid; i < D.nblk; i += CT_THREADS) c += P.cost_part[i];
-    const double cand_cost = block_sum<CT_THREADS>(c, red);
+    for (int i = tid; i < D.nblk; i += NT) c += P.cost_part[i];
+    const double cand_cost = block_sum_dyn(c, red);
     double sn = 0;
-    for (int k = tid; k < D.nkf; k += CT_THREADS)
+    for (int k = tid; k < D.nkf; k += NT)
         if (P.pose_col[k] >= 0)
             for (int i = 0; i < 7; i++) { const double d = P.poses[7 * k + i] - P.cand_poses[7 * k + i]; sn += d * d; }
-    for (int l = tid; l < D.nlm; l += CT_THREADS)
+    for (int l = tid; l < D.nlm; l += NT)
         if (P.lm_start[l + 1] > P.lm_start[l]) { const double d = P.invd[l] - P.cand_invd[l]; sn += d * d; }
-    __syncthreads();
-    sn = block_sum<CT_THREADS>(sn, red);
+    sn = block_sum_dyn(sn, red);
     if (tid == 0) {
         int accept = 0;
         st.invalid_steps = 0;
@@ -1240,11 +1290,16 @@ __global__ void __launch_bounds__(CT_THREADS) ba_post_kernel(const BaProblem* __
     }
     __syncthreads();
     if (accept_s) {
-        for (int i = tid; i < 7 * D.nkf; i += CT_THREADS) P.poses[i] = P.cand_poses[i];
-        for (int l = tid; l < D.nlm; l += CT_THREADS) P.invd[l] = P.cand_invd[l];
-        for (int i = tid; i < NMAX; i += CT_THREADS) { P.nf[i] = 0; P.gf[i] = 0; }
-        for (int l = tid; l < D.nlm; l += CT_THREADS) { P.ne[l] = 0; P.ge[l] = 0; }
+        for (int i = tid; i < 7 * D.nkf; i += NT) P.poses[i] = P.cand_poses[i];
+        for (int l = tid; l < D.nlm; l += NT) P.invd[l] = P.cand_invd[l];
+        for (int i = tid; i < NMAX; i += NT) { P.nf[i] = 0; P.gf[i] = 0; }
+        for (int l = tid; l < D.nlm; l += NT) { P.ne[l] = 0; P.ge[l] = 0; }
     }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) ba_post_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+    const BaProblem P = probs[blockIdx.x];
+    ba_post_body(P, D);
 }
 
 // kernel-level dump of the linearisation (corrected residuals and local Jacobians) for parity tests
@@ -1321,12 +1376,270 @@ __global__ void ba_summary_kernel(const BaProblem* __restrict__ probs, double* _
     }
 }
 
+// ------------------------------------------------------------------------------------------ the LM loop as ONE kernel
+// A thread-block cluster of MG_CL CTAs per problem runs the whole trust-region loop -- the launch sequence of ba_run_solve
+// with hardware cluster barriers (barrier.cluster, release / acquire) where the kernel boundaries were.  The phases are the same
+// device functions the stand-alone kernels call, strided over the cluster's threads; what was a 1-CTA kernel (control, reduced
+// solve) runs in the cluster's first CTA while the others wait at the barrier.  Why: a solve was ~55 dependent launches of
+// 10-75 us kernels that were each dominated by launch / drain and first-touch latency (profiles/r02_kernels_full.txt: issue
+// slots 2-12 % busy), and the chain -- not the frame stages -- bounded the pipeline's step.
+//   mode 0: head -- linearise, column norms / gradient, control of iteration 0 (needs no block lists: runs beside ba_pairs_kernel)
+//   mode 1: the rest of iteration 0 and every later iteration
+constexpr int MG_CL = 8;                  // CTAs per cluster (portable maximum)
+constexpr int MG_THREADS = CH_THREADS;    // the reduced solve's tiling fixes the CTA size (17 warps)
+constexpr int MG_WARPS = MG_THREADS / 32;
+constexpr int MG_SPLIT = 16;              // parts per diagonal block of the gather (a warp per part)
+constexpr int MG_UNITS = NBMAX * MG_SPLIT + (MAXKEYS - NBMAX);
+static_assert(MG_WARPS >= 16, "four 4-warp groups for the pose statistics");
+
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// rows [3 * half, 3 * half + 3) of one (landmark, slot_u, slot_v) entry's contribution (see gather_entry): acc[3][6], rh[3]
+__device__ __forceinline__ void gather_entry_half(const BaProblem& P, uint32_t en, const double* sci, const double* scj, int half,
+                                                  double* acc, double* rh) {
+    const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
+    const int ob = P.lm_start[l];
+    const double inv = 1.0 / P.ete[l], etb = P.etb[l];
+    const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+    double wu[3], wv[6], scu[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int ag = a + 3 * half;
+        wu[a] = (su ? P.wp[6 * ou + ag] : P.wa[6 * l + ag]) * inv;
+        scu[a] = half ? sci[3 + a] : sci[a];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) wv[c] = sv ? P.wp[6 * ov + c] : P.wa[6 * l + c];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc[6 * a + c] -= wu[a] * wv[c];
+    if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
+        const int oe = P.lm_start[l + 1];
+        for (int i = ob; i < oe; i++) {
+            const int o = P.lm_obs[i];
+            double F0[6], F1[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) { F0[c] = P.Ja[12 * o + c] * sci[c]; F1[c] = P.Ja[12 * o + 6 + c] * sci[c]; }
+            const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const double f0 = half ? F0[3 + a] : F0[a], f1 = half ? F1[3 + a] : F1[a];
+                rh[a] += f0 * r0 + f1 * r1;
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[6 * a + c] += f0 * F0[c] + f1 * F1[c];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) rh[a] -= wu[a] * etb;
+    } else if (su == sv) {                           // observation x itself
+        double F0[6], F1[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { F0[c] = P.Jp[12 * ou + c] * sci[c]; F1[c] = P.Jp[12 * ou + 6 + c] * sci[c]; }
+        const double r0 = P.res[2 * ou], r1 = P.res[2 * ou + 1];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double f0 = half ? F0[3 + a] : F0[a], f1 = half ? F1[3 + a] : F1[a];
+            rh[a] += f0 * r0 + f1 * r1 - wu[a] * etb;
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[6 * a + c] += f0 * F0[c] + f1 * F1[c];
+        }
+    } else if (su == 0 || sv == 0) {                 // anchor x observation (either order): rows of that observation
+        const int o = su ? ou : ov;
+        double A0[3], A1[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int ag = a + 3 * half;
+            A0[a] = (su ? P.Jp[12 * o + ag] : P.Ja[12 * o + ag]) * scu[a];
+            A1[a] = (su ? P.Jp[12 * o + 6 + ag] : P.Ja[12 * o + 6 + ag]) * scu[a];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const double b0 = (sv ? P.Jp[12 * o + c] : P.Ja[12 * o + c]) * scj[c];
+            const double b1 = (sv ? P.Jp[12 * o + 6 + c] : P.Ja[12 * o + 6 + c]) * scj[c];
+#pragma unroll
+            for (int a = 0; a < 3; a++) acc[6 * a + c] += A0[a] * b0 + A1[a] * b1;
+        }
+    }
+}
+
+__global__ void __cluster_dims__(MG_CL, 1, 1) __launch_bounds__(MG_THREADS, 1)
+ba_mega_kernel(const BaProblem* __restrict__ probs, BaDims D, int mode) {
+    extern __shared__ double sm[];
+    __shared__ double red[34];
+    __shared__ double part[4][4][12];
+    __shared__ double cand_s[7 * 256];   // candidate poses (nkf <= 256), rebuilt by every CTA
+    const BaProblem P = probs[blockIdx.y];
+    BaState& st = *P.st;
+    const int rank = blockIdx.x;   // gridDim.x == MG_CL: the cluster is the problem's row of the grid
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int vt = rank * MG_THREADS + tid, VT = MG_CL * MG_THREADS;
+    D.nblk = MG_CL;   // cost partials: one per CTA of the cluster
+    D.nbs = MG_CL;    // model-cost partials likewise
+
+    for (int it = 0; it <= D.max_iter; it++) {
+        if (st.done) break;   // (cluster-uniform: written before the last barrier)
+        if (mode == 0 || it > 0) {
+            // ---- A. linearise at the current point
+            if (st.relin) {
+                double cost = 0;
+                for (int o = vt; o < D.nobs; o += VT) {
+                    const int l = P.obs_lm[o];
+                    if (l >= 0) cost += lin_obs<true>(P, D, o, l, P.poses, P.invd[l]);
+                }
+                const double tot = block_sum_dyn(cost, red);
+                if (tid == 0) P.cost_part[rank] = tot;
+            }
+            cluster_barrier();
+            // ---- B. column norms and gradient
+            if (st.relin) {
+                for (int l = vt; l < D.nlm; l += VT) stats_landmark(P, l);
+                const int grp = warp >> 2, gt = tid & 127;   // four 4-warp groups per CTA, one free pose each
+                const int b = rank * 4 + grp;
+                const bool act = warp < 16 && b < st.ncols / 6;
+                double v[12];
+                if (act) stats_pose_partial(P, b, gt, v);
+                else
+#pragma unroll
+                    for (int i = 0; i < 12; i++) v[i] = 0;
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+#pragma unroll
+                    for (int off = 16; off; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+                    if (lane == 0 && warp < 16) part[grp][warp & 3][i] = v[i];
+                }
+                __syncthreads();
+                if (act && gt < 12) {
+                    const double t = part[grp][0][gt] + part[grp][1][gt] + part[grp][2][gt] + part[grp][3][gt];
+                    if (gt < 6) P.nf[6 * b + gt] = t;
+                    else P.gf[6 * b + gt - 6] = t;
+                }
+            }
+            cluster_barrier();
+            // ---- C. control before the step
+            if (rank == 0) ba_pre_body(P, D);
+            cluster_barrier();
+            if (mode == 0) return;
+        }
+        if (st.done || it == D.max_iter) break;
+        // ---- D. per-landmark Schur ingredients
+        const bool use_gather = st.use_gather != 0;
+        if (use_gather)
+            for (int l = vt; l < D.nlm; l += VT) lm_landmark(P, l);
+        cluster_barrier();
+        // ---- E. reduced camera system
+        if (use_gather) {
+            const int gw = rank * MG_WARPS + warp, half = lane >> 4, hl = lane & 15;
+            for (int u = gw; u < MG_UNITS; u += MG_CL * MG_WARPS) {
+                int bi, bj, prt = 0, nparts = 1;
+                if (u < NBMAX * MG_SPLIT) { bi = bj = u / MG_SPLIT; prt = u % MG_SPLIT; nparts = MG_SPLIT; }
+                else {
+                    int rem = u - NBMAX * MG_SPLIT;
+                    bi = 0;
+                    while (bi < NBMAX - 1 && rem >= NBMAX - 1 - bi) { rem -= NBMAX - 1 - bi; bi++; }
+                    bj = bi + 1 + rem;
+                }
+                if (bi >= st.nb || bj >= st.nb) continue;   // warp-uniform
+                const int blk = bi * NBMAX + bj, ci = 6 * bi, cj = 6 * bj;
+                int eb = 0;
+                for (int i = lane; i < blk; i += 32) eb += P.blk_start[i + 1];
+#pragma unroll
+                for (int off = 16; off; off >>= 1) eb += __shfl_xor_sync(0xffffffffu, eb, off);
+                const int ee = eb + P.blk_start[blk + 1];
+                double acc[18], rh[3], sci[6], scj[6];
+#pragma unroll
+                for (int i = 0; i < 18; i++) acc[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) rh[i] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
+                for (int idx = eb + prt * 16 + hl; idx < ee; idx += nparts * 16)
+                    gather_entry_half(P, P.pairs[idx], sci, scj, half, acc, rh);
+                // fixed-order reduction over the 16 lanes of a half-warp
+#pragma unroll
+                for (int i = 0; i < 18; i++)
+#pragma unroll
+                    for (int off = 8; off; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int off = 8; off; off >>= 1) rh[i] += __shfl_xor_sync(0xffffffffu, rh[i], off);
+                if (hl == 0) {
+                    if (bi == bj) {
+                        double* slot = P.ga_part + ((size_t)bi * MG_SPLIT + prt) * 42;
+#pragma unroll
+                        for (int i = 0; i < 18; i++) slot[18 * half + i] = acc[i];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) slot[36 + 3 * half + i] = rh[i];
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int c = 0; c < 6; c++) {
+                                const int ag = a + 3 * half;
+                                P.S[(ci + ag) * NMAX + cj + c] = acc[6 * a + c];
+                                P.S[(cj + c) * NMAX + ci + ag] = acc[6 * a + c];
+                            }
+                    }
+                }
+            }
+            cluster_barrier();
+            // diagonal blocks: the MG_SPLIT partial sums in part order
+            for (int x = vt; x < st.nb * 42; x += VT) {
+                const int bi = x / 42, e = x - 42 * bi, ci = 6 * bi;
+                const double* all = P.ga_part + (size_t)bi * MG_SPLIT * 42;
+                double v = 0;
+#pragma unroll
+                for (int q = 0; q < MG_SPLIT; q++) v += all[q * 42 + e];
+                if (e < 36) {
+                    const int a = e / 6, c = e - 6 * a;
+                    P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
+                } else P.rhs[ci + e - 36] = v;
+            }
+        } else {
+            for (int l = vt; l < D.nlm; l += VT) schur_landmark<false>(P, D, l);   // FP64-atomic fallback (structure too large)
+            cluster_barrier();
+        }
+        cluster_barrier();
+        // ---- F. reduced solve
+        if (rank == 0) ba_chol_body(P, sm);
+        cluster_barrier();
+        // ---- G. back-substitution + cost at the candidate point
+        {
+            for (int k = tid; k < D.nkf; k += MG_THREADS) {
+                backsub_cand_pose(P, k, cand_s + 7 * k);
+                if (rank == 0) for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = cand_s[7 * k + i];
+            }
+            __syncthreads();
+            double acc = 0, cost = 0;
+            for (int l = vt; l < D.nlm; l += VT) {
+                acc += backsub_landmark(P, l);
+                const double ci = P.cand_invd[l];
+                for (int i = P.lm_start[l]; i < P.lm_start[l + 1]; i++) {
+                    const int o = P.lm_obs[i];
+                    cost += lin_obs<false>(P, D, o, l, cand_s, ci);
+                }
+            }
+            const double tm = block_sum_dyn(acc, red);
+            const double tc = block_sum_dyn(cost, red);
+            if (tid == 0) { P.mc_part[rank] = tm; P.cost_part[rank] = tc; }
+        }
+        cluster_barrier();
+        // ---- H. control after the step
+        if (rank == 0) ba_post_body(P, D);
+        cluster_barrier();
+    }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
 // Workspace carving: one contiguous block per problem.
 static int g_ba_dense_schur = 0;   // alva_set_option("ba_dense_schur", 1): tensor-core SYRK for the Schur term
+static int g_ba_mega = 1;          // alva_set_option("ba_mega", 0): one launch per phase (the round-1 sequence) instead of ba_mega_kernel
 
 static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     size_t d = 0;
@@ -1339,7 +1652,7 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     d += (size_t)nkf * 7 + nlm;                      // cand
     d += (size_t)nblk;                               // cost partials
     d += (size_t)((nlm + BS_THREADS - 1) / BS_THREADS);   // model-cost partials
-    d += (size_t)NBMAX * 8 * 42;                          // gather partials (GA_SPLIT = 8)
+    d += (size_t)NBMAX * 16 * 42;                         // gather partials (max(GA_SPLIT, MG_SPLIT) = 16)
     size_t bytes = d * sizeof(double);
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
     bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
@@ -1394,7 +1707,7 @@ static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, cons
             P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
             P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
             P.mc_part = take((size_t)((nlm + BS_THREADS - 1) / BS_THREADS));
-            P.ga_part = take((size_t)NBMAX * GA_SPLIT * 42);
+            P.ga_part = take((size_t)NBMAX * 16 * 42);
             P.last_poses = local ? take(7 * (size_t)nkf) : nullptr;
             P.last_invd = local ? take(nlm) : nullptr;
             uint8_t* b = reinterpret_cast<uint8_t*>(d);
@@ -1436,6 +1749,26 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(D.nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     const dim3 key_grid(GA_GRID, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
+    if (g_ba_mega && !dense) {
+        // setup -> { block lists on the auxiliary stream | head of iteration 0 } -> the loop: 5 launches per solve
+        ALVA_CUDA(cudaFuncSetAttribute(ba_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+        const dim3 pr_grid(NBMAX, nprob), mg_grid(MG_CL, nprob);
+        cudaStream_t ps = ctx->stream;
+        bool fk = false;
+        if (ctx->aux_stream && cudaEventRecord(ctx->aux_fork, ctx->stream) == cudaSuccess &&
+            cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0) == cudaSuccess) { ps = ctx->aux_stream; fk = true; }
+        ba_pairs_kernel<0><<<pr_grid, 32, 0, ps>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        ba_pairs_kernel<1><<<pr_grid, 32, 0, ps>>>(dp, D);
+        ALVA_LAUNCH_CHECK(ctx);
+        if (fk) ALVA_CUDA(cudaEventRecord(ctx->aux_join, ps));
+        ba_mega_kernel<<<mg_grid, MG_THREADS, chol_smem, ctx->stream>>>(dp, D, 0);
+        ALVA_LAUNCH_CHECK(ctx);
+        if (fk) ALVA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+        ba_mega_kernel<<<mg_grid, MG_THREADS, chol_smem, ctx->stream>>>(dp, D, 1);
+        ALVA_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     bool forked = false;
     if (!dense) {   // structure of the gather-form Schur complement, once per solve -- beside the first linearisation, which
                     // does not need it (fork / join on the context's auxiliary stream; also valid inside a stream capture)
@@ -1573,6 +1906,7 @@ extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
 extern int alva_g_pipeline_graphs, alva_g_ba_lag;   // pipeline.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
+    if (name && !strcmp(name, "ba_mega")) { g_ba_mega = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
     if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }
