@@ -29,6 +29,9 @@ struct alva_ctx {
     void* p3p_tab = nullptr;        // P3P-LMedS sampler table (depends on seed and length only): resident across calls
     int p3p_tab_len = 0;
     uint32_t p3p_tab_seed = 0;
+    void* init_tab = nullptr;       // five-point RANSAC sampler table, likewise (the loop-closure detector runs it every step)
+    int init_tab_len = 0;
+    uint32_t init_tab_seed = 0;
     void* knn_ws = nullptr;         // tensor-core matcher: expanded int8 operand tiles, row map (hamming_mma.cu)
     size_t knn_ws_bytes = 0;
     // fork / join inside one entry point (BA: the structure kernels run beside the first linearisation).  Created with the

@@ -122,6 +122,7 @@ extern "C" void alva_ctx_destroy(alva_ctx* ctx) {
     if (ctx->det_ws) cudaFree(ctx->det_ws);
     if (ctx->knn_ws) cudaFree(ctx->knn_ws);
     if (ctx->p3p_tab) cudaFree(ctx->p3p_tab);
+    if (ctx->init_tab) cudaFree(ctx->init_tab);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);

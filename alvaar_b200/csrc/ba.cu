@@ -1392,8 +1392,13 @@ constexpr int MG_SPLIT = 16;              // parts per diagonal block of the gat
 constexpr int MG_UNITS = NBMAX * MG_SPLIT + (MAXKEYS - NBMAX);
 static_assert(MG_WARPS >= 16, "four 4-warp groups for the pose statistics");
 
+// Global-memory results of one phase are read by OTHER CTAs (other SMs, other L1s) in the next: gpu-scope fences on both sides
+// of the cluster barrier (its own release / acquire is cluster-scoped; without the fences a CTA read stale L1 lines of the
+// arrays a neighbour had rewritten -- two good iterations, then rejected steps).
 __device__ __forceinline__ void cluster_barrier() {
+    __threadfence();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __threadfence();
 }
 
 // rows [3 * half, 3 * half + 3) of one (landmark, slot_u, slot_v) entry's contribution (see gather_entry): acc[3][6], rh[3]
@@ -1639,7 +1644,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Workspace carving: one contiguous block per problem.
 static int g_ba_dense_schur = 0;   // alva_set_option("ba_dense_schur", 1): tensor-core SYRK for the Schur term
-static int g_ba_mega = 1;          // alva_set_option("ba_mega", 0): one launch per phase (the round-1 sequence) instead of ba_mega_kernel
+static int g_ba_mega = 0;          // alva_set_option("ba_mega", 1): the LM loop as ONE kernel (ba_mega_kernel) instead of one launch per phase
 
 static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     size_t d = 0;

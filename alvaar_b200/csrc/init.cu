@@ -27,7 +27,9 @@ namespace {
 using namespace alva_init;
 
 constexpr int INIT_THREADS = 128;
-constexpr int CHUNK = 32;
+constexpr int CHUNK = INIT_THREADS;   // hypotheses solved per round, one per thread.  The bookkeeping replays them in draw order with the
+                                      // reference's adaptive bound, so the chunk size only decides how many are solved speculatively: 32
+                                      // (one warp working, three idle) made a 100-iteration RANSAC four serial rounds of ~0.7 ms each
 
 struct EssentialParams {
     const double* bv1; const double* bv2; const int32_t* counts; int cap;
@@ -254,18 +256,24 @@ extern "C" int alva_k_essential_5pt(alva_ctx* ctx, int nprob, int cap, const dou
     P.threshold = 2.0 * (1.0 - cosf(atanf(err_px / focal)));
     P.bv1 = bv1; P.bv2 = bv2; P.counts = counts; P.cap = cap; P.max_iter = max_iter; P.optimize = optimize;
     P.table_len = 8 * (11 * max_iter + 3 * CHUNK);
-    const size_t tab_b = ((size_t)P.table_len * 4 + 255) & ~(size_t)255;
+    const size_t tab_b = 0;   // (the sampler table lives on the context)
     const size_t work_b = optimize == 2 ? (size_t)nprob * cap * 8 * sizeof(double) : 0;
     const size_t inl_b = optimize == 2 ? (((size_t)nprob * cap * 4 + 255) & ~(size_t)255) : 0;
-    uint8_t* scr = (uint8_t*)alva_scratch(ctx, tab_b + work_b + inl_b);
+    uint8_t* scr = (uint8_t*)alva_scratch(ctx, tab_b + work_b + inl_b + 256);
     if (!scr) return ALVA_E_CUDA;
-    int32_t* tab = (int32_t*)scr;
     P.work = (double*)(scr + tab_b); P.inl = (int32_t*)(scr + tab_b + work_b);
-    P.rnd = tab; P.Rt = Rt_out; P.outlier = outlier; P.info = info;
-    static thread_local std::vector<int32_t> host_tab;
-    static thread_local uint32_t host_seed = 0;
-    if ((int)host_tab.size() != P.table_len || host_seed != seed) { make_rnd_table_init(seed, P.table_len, host_tab); host_seed = seed; }
-    ALVA_CUDA(cudaMemcpyAsync(tab, host_tab.data(), (size_t)P.table_len * 4, cudaMemcpyHostToDevice, ctx->stream));
+    P.Rt = Rt_out; P.outlier = outlier; P.info = info;
+    // the sampler table depends only on (seed, length): kept on the device across calls -- a per-call upload from pageable memory
+    // made every call wait for the stream to drain (the loop-closure detector calls this every step)
+    if (!ctx->init_tab || ctx->init_tab_len != P.table_len || ctx->init_tab_seed != seed) {
+        std::vector<int32_t> host_tab;
+        make_rnd_table_init(seed, P.table_len, host_tab);
+        if (ctx->init_tab) { ALVA_CUDA(cudaStreamSynchronize(ctx->stream)); ALVA_CUDA(cudaFree(ctx->init_tab)); ctx->init_tab = nullptr; }
+        ALVA_CUDA(cudaMalloc(&ctx->init_tab, (size_t)P.table_len * 4));
+        ALVA_CUDA(cudaMemcpy(ctx->init_tab, host_tab.data(), (size_t)P.table_len * 4, cudaMemcpyHostToDevice));
+        ctx->init_tab_len = P.table_len; ctx->init_tab_seed = seed;
+    }
+    P.rnd = (const int32_t*)ctx->init_tab;
     essential_kernel<<<nprob, INIT_THREADS, (size_t)cap * sizeof(int), ctx->stream>>>(P);
     ALVA_LAUNCH_CHECK(ctx);
     return 0;

@@ -212,15 +212,23 @@ extern "C" alva_lc* alva_lc_create(alva_ctx* ctx, const alva_lc_config* cfg) { A
     return lc;
 }
 
-extern "C" int alva_lc_pack(alva_lc* lc, const uint8_t* desc, const float* pts, const int32_t* counts, int cap, const int32_t* kf_frames,
-                            int kf_seq0, const float* K4, uint8_t* send) { AlvaDeviceGuard guard__(lc ? lc->ctx : nullptr);
+// `on`: the context whose stream runs the pack kernel -- the producer of desc / pts (the per-frame context), so that packing never
+// queues behind a detection on the detector's own stream; NULL = the detector's context.
+extern "C" int alva_lc_pack_on(alva_lc* lc, alva_ctx* on, const uint8_t* desc, const float* pts, const int32_t* counts, int cap,
+                               const int32_t* kf_frames, int kf_seq0, const float* K4, uint8_t* send) { AlvaDeviceGuard guard__(lc ? lc->ctx : nullptr);
     if (!lc || !desc || !pts || !counts || !kf_frames || !K4 || !send || cap < 1) { alva_set_error("alva_lc_pack: bad argument"); return ALVA_E_INVALID; }
+    alva_ctx* ctx = on ? on : lc->ctx;
+    if (ctx->device != lc->ctx->device) { alva_set_error("alva_lc_pack_on: context of another device"); return ALVA_E_INVALID; }
     const int K = lc->cfg.kf_per_step;
-    lc_pack_kernel<<<dim3(4, K), 256, 0, lc->ctx->stream>>>(desc, pts, counts, kf_frames, cap, lc->cfg.n_max, lc->cfg.rank, kf_seq0, K4[0], K4[1],
-                                                            K4[2], K4[3], send, lc->block_bytes);
-    ALVA_LAUNCH_CHECK(lc->ctx);
+    lc_pack_kernel<<<dim3(4, K), 256, 0, ctx->stream>>>(desc, pts, counts, kf_frames, cap, lc->cfg.n_max, lc->cfg.rank, kf_seq0, K4[0], K4[1],
+                                                        K4[2], K4[3], send, lc->block_bytes);
+    ALVA_LAUNCH_CHECK(ctx);
     lc->step_seq0 = kf_seq0;
     return 0;
+}
+extern "C" int alva_lc_pack(alva_lc* lc, const uint8_t* desc, const float* pts, const int32_t* counts, int cap, const int32_t* kf_frames,
+                            int kf_seq0, const float* K4, uint8_t* send) {
+    return alva_lc_pack_on(lc, nullptr, desc, pts, counts, cap, kf_frames, kf_seq0, K4, send);
 }
 
 extern "C" int alva_lc_detect(alva_lc* lc, const uint8_t* gathered) { AlvaDeviceGuard guard__(lc ? lc->ctx : nullptr);

@@ -66,12 +66,13 @@ class LoopClosure:
             raise AlvaError(f"rc={rc}: {self.L.alva_last_error().decode()}")
         return rc
 
-    def pack(self, desc, pts, counts, kf_frames, send):
+    def pack(self, desc, pts, counts, kf_frames, send, on=None):
         """desc [nframes, cap, 32] u8, pts [nframes, cap, 2] f32, counts [nframes] i32, kf_frames [K] i32 (device tensors) ->
-        send (device u8 tensor of K * block_bytes)"""
+        send (device u8 tensor of K * block_bytes).  on: the alvaar_b200.Context whose stream runs the pack (default: the detector's)"""
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        self._chk(self.L.alva_lc_pack(self.h, p(desc), p(pts), p(counts), int(desc.shape[1]), p(kf_frames), self.seq,
-                                      self.K4.ctypes.data_as(C.c_void_p), p(send)))
+        self.L.alva_lc_pack_on.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self._chk(self.L.alva_lc_pack_on(self.h, on.h if on is not None else None, p(desc), p(pts), p(counts), int(desc.shape[1]), p(kf_frames),
+                                         self.seq, self.K4.ctypes.data_as(C.c_void_p), p(send)))
         self.seq += self.K
 
     def detect(self, gathered):

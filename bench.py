@@ -392,24 +392,32 @@ def bench_b200(args, rank, world, local_rank):
         pts_all = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
         cnt_all = pipe.buffer("selcounts", (BATCH,), torch.int32)
         bb = block_bytes(pipe.fcap)
-        send = torch.zeros(pipe.nprob * bb, dtype=torch.uint8, device=dev_s)
-        gathered_buf = torch.zeros(world * pipe.nprob * bb, dtype=torch.uint8, device=dev_s)
-        ev_ready, ev_packed = torch.cuda.Event(), torch.cuda.Event()
+        LC_RING = 3
+        send = [torch.zeros(pipe.nprob * bb, dtype=torch.uint8, device=dev_s) for _ in range(LC_RING)]
+        gathered_buf = [torch.zeros(world * pipe.nprob * bb, dtype=torch.uint8, device=dev_s) for _ in range(LC_RING)]
+        ev_packed = [torch.cuda.Event() for _ in range(LC_RING)]
+        ev_gathered = [torch.cuda.Event() for _ in range(LC_RING)]
+        lc_state = {"step": 0}
 
         def lc():
-            # Off the per-frame path: the step's keyframe blocks are packed on a side stream as soon as the descriptors exist, the
-            # NCCL all-gather and the cross-stream detection (Hamming 2-NN of the live descriptors, ratio test, five-point RANSAC)
-            # run there beside the next step; the main stream only waits for the (microseconds-long) pack before it reuses the
-            # descriptor buffers.  Results are polled without blocking.
-            ev_ready.record(stream)
+            # Off the per-frame path.  The step's keyframe blocks are packed on the MAIN stream (microseconds, right behind the
+            # kernels that produced the descriptors) into a ring of send buffers; the NCCL all-gather and the cross-stream detection
+            # (Hamming 2-NN of the live descriptors, ratio test, five-point RANSAC) run on a side stream beside the next steps.  The
+            # main stream never waits for a detection: only, three steps later, for the all-gather that read the ring slot it is
+            # about to refill.  Results are polled without blocking (the detector keeps at most 4 steps in flight).
+            i = lc_state["step"] % LC_RING
+            if lc_state["step"] >= LC_RING:
+                stream.wait_event(ev_gathered[i])
+            det.pack(desc_all, pts_all, cnt_all, kf_idx, send[i], on=ctx)
+            ev_packed[i].record(stream)
             with torch.cuda.stream(side):
-                side.wait_event(ev_ready)
-                det.pack(desc_all, pts_all, cnt_all, kf_idx, send)
-                ev_packed.record(side)
-                det.exchange_and_detect(send, gathered_buf)
-            stream.wait_event(ev_packed)
+                side.wait_event(ev_packed[i])
+                dist.all_gather_into_tensor(gathered_buf[i], send[i])
+                ev_gathered[i].record(side)
+                det.detect(gathered_buf[i])
+            lc_state["step"] += 1
             lc_events.extend(det.poll())
-            return gathered_buf
+            return gathered_buf[i]
 
     sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
@@ -418,6 +426,8 @@ def bench_b200(args, rank, world, local_rank):
             if lc:
                 lc()
         pipe.drain()
+        if lc:
+            stream.wait_stream(side)
         barrier()
         l0 = ctx.launches
         sampler.start()
@@ -428,6 +438,8 @@ def bench_b200(args, rank, world, local_rank):
             if lc:
                 gathered = lc()
         pipe.drain()   # the last step's BA chain belongs to the timed region
+        if lc:
+            stream.wait_stream(side)   # ... and so does the last step's exchange + detection
         ev1.record(stream)
         barrier()
         launches = ctx.launches - l0

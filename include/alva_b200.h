@@ -441,6 +441,10 @@ alva_lc* alva_lc_create(alva_ctx*, const alva_lc_config*);
 void     alva_lc_destroy(alva_lc*);
 int      alva_lc_pack(alva_lc*, const uint8_t* desc, const float* pts, const int32_t* counts, int cap, const int32_t* kf_frames,
                       int kf_seq0, const float* K4, uint8_t* send);
+/* The same with the pack kernel enqueued on `on`'s stream (NULL: the detector's): pass the context that produced desc / pts so that
+ * packing never waits behind a detection still running on the detector's stream. */
+int alva_lc_pack_on(alva_lc*, alva_ctx* on, const uint8_t* desc, const float* pts, const int32_t* counts, int cap,
+                    const int32_t* kf_frames, int kf_seq0, const float* K4, uint8_t* send);
 int      alva_lc_detect(alva_lc*, const uint8_t* gathered);
 int      alva_lc_poll(alva_lc*, alva_lc_event* out, int cap, int wait);
 /* steps enqueued by alva_lc_detect whose results alva_lc_poll has not consumed yet (at most 4 may be in flight) */
