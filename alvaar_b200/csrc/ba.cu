@@ -1376,275 +1376,12 @@ __global__ void ba_summary_kernel(const BaProblem* __restrict__ probs, double* _
     }
 }
 
-// ------------------------------------------------------------------------------------------ the LM loop as ONE kernel
-// A thread-block cluster of MG_CL CTAs per problem runs the whole trust-region loop -- the launch sequence of ba_run_solve
-// with hardware cluster barriers (barrier.cluster, release / acquire) where the kernel boundaries were.  The phases are the same
-// device functions the stand-alone kernels call, strided over the cluster's threads; what was a 1-CTA kernel (control, reduced
-// solve) runs in the cluster's first CTA while the others wait at the barrier.  Why: a solve was ~55 dependent launches of
-// 10-75 us kernels that were each dominated by launch / drain and first-touch latency (profiles/r02_kernels_full.txt: issue
-// slots 2-12 % busy), and the chain -- not the frame stages -- bounded the pipeline's step.
-//   mode 0: head -- linearise, column norms / gradient, control of iteration 0 (needs no block lists: runs beside ba_pairs_kernel)
-//   mode 1: the rest of iteration 0 and every later iteration
-constexpr int MG_CL = 8;                  // CTAs per cluster (portable maximum)
-constexpr int MG_THREADS = CH_THREADS;    // the reduced solve's tiling fixes the CTA size (17 warps)
-constexpr int MG_WARPS = MG_THREADS / 32;
-constexpr int MG_SPLIT = 16;              // parts per diagonal block of the gather (a warp per part)
-constexpr int MG_UNITS = NBMAX * MG_SPLIT + (MAXKEYS - NBMAX);
-static_assert(MG_WARPS >= 16, "four 4-warp groups for the pose statistics");
-
-// Global-memory results of one phase are read by OTHER CTAs (other SMs, other L1s) in the next: gpu-scope fences on both sides
-// of the cluster barrier (its own release / acquire is cluster-scoped; without the fences a CTA read stale L1 lines of the
-// arrays a neighbour had rewritten -- two good iterations, then rejected steps).
-__device__ __forceinline__ void cluster_barrier() {
-    __threadfence();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    __threadfence();
-}
-
-// rows [3 * half, 3 * half + 3) of one (landmark, slot_u, slot_v) entry's contribution (see gather_entry): acc[3][6], rh[3]
-__device__ __forceinline__ void gather_entry_half(const BaProblem& P, uint32_t en, const double* sci, const double* scj, int half,
-                                                  double* acc, double* rh) {
-    const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
-    const int ob = P.lm_start[l];
-    const double inv = 1.0 / P.ete[l], etb = P.etb[l];
-    const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
-    double wu[3], wv[6], scu[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        const int ag = a + 3 * half;
-        wu[a] = (su ? P.wp[6 * ou + ag] : P.wa[6 * l + ag]) * inv;
-        scu[a] = half ? sci[3 + a] : sci[a];
-    }
-#pragma unroll
-    for (int c = 0; c < 6; c++) wv[c] = sv ? P.wp[6 * ov + c] : P.wa[6 * l + c];
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) acc[6 * a + c] -= wu[a] * wv[c];
-    if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
-        const int oe = P.lm_start[l + 1];
-        for (int i = ob; i < oe; i++) {
-            const int o = P.lm_obs[i];
-            double F0[6], F1[6];
-#pragma unroll
-            for (int c = 0; c < 6; c++) { F0[c] = P.Ja[12 * o + c] * sci[c]; F1[c] = P.Ja[12 * o + 6 + c] * sci[c]; }
-            const double r0 = P.res[2 * o], r1 = P.res[2 * o + 1];
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                const double f0 = half ? F0[3 + a] : F0[a], f1 = half ? F1[3 + a] : F1[a];
-                rh[a] += f0 * r0 + f1 * r1;
-#pragma unroll
-                for (int c = 0; c < 6; c++) acc[6 * a + c] += f0 * F0[c] + f1 * F1[c];
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; a++) rh[a] -= wu[a] * etb;
-    } else if (su == sv) {                           // observation x itself
-        double F0[6], F1[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) { F0[c] = P.Jp[12 * ou + c] * sci[c]; F1[c] = P.Jp[12 * ou + 6 + c] * sci[c]; }
-        const double r0 = P.res[2 * ou], r1 = P.res[2 * ou + 1];
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const double f0 = half ? F0[3 + a] : F0[a], f1 = half ? F1[3 + a] : F1[a];
-            rh[a] += f0 * r0 + f1 * r1 - wu[a] * etb;
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc[6 * a + c] += f0 * F0[c] + f1 * F1[c];
-        }
-    } else if (su == 0 || sv == 0) {                 // anchor x observation (either order): rows of that observation
-        const int o = su ? ou : ov;
-        double A0[3], A1[3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const int ag = a + 3 * half;
-            A0[a] = (su ? P.Jp[12 * o + ag] : P.Ja[12 * o + ag]) * scu[a];
-            A1[a] = (su ? P.Jp[12 * o + 6 + ag] : P.Ja[12 * o + 6 + ag]) * scu[a];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            const double b0 = (sv ? P.Jp[12 * o + c] : P.Ja[12 * o + c]) * scj[c];
-            const double b1 = (sv ? P.Jp[12 * o + 6 + c] : P.Ja[12 * o + 6 + c]) * scj[c];
-#pragma unroll
-            for (int a = 0; a < 3; a++) acc[6 * a + c] += A0[a] * b0 + A1[a] * b1;
-        }
-    }
-}
-
-__global__ void __cluster_dims__(MG_CL, 1, 1) __launch_bounds__(MG_THREADS, 1)
-ba_mega_kernel(const BaProblem* __restrict__ probs, BaDims D, int mode) {
-    extern __shared__ double sm[];
-    __shared__ double red[34];
-    __shared__ double part[4][4][12];
-    __shared__ double cand_s[7 * 256];   // candidate poses (nkf <= 256), rebuilt by every CTA
-    const BaProblem P = probs[blockIdx.y];
-    BaState& st = *P.st;
-    const int rank = blockIdx.x;   // gridDim.x == MG_CL: the cluster is the problem's row of the grid
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int vt = rank * MG_THREADS + tid, VT = MG_CL * MG_THREADS;
-    D.nblk = MG_CL;   // cost partials: one per CTA of the cluster
-    D.nbs = MG_CL;    // model-cost partials likewise
-
-    for (int it = 0; it <= D.max_iter; it++) {
-        if (st.done) break;   // (cluster-uniform: written before the last barrier)
-        if (mode == 0 || it > 0) {
-            // ---- A. linearise at the current point
-            if (st.relin) {
-                double cost = 0;
-                for (int o = vt; o < D.nobs; o += VT) {
-                    const int l = P.obs_lm[o];
-                    if (l >= 0) cost += lin_obs<true>(P, D, o, l, P.poses, P.invd[l]);
-                }
-                const double tot = block_sum_dyn(cost, red);
-                if (tid == 0) P.cost_part[rank] = tot;
-            }
-            cluster_barrier();
-            // ---- B. column norms and gradient
-            if (st.relin) {
-                for (int l = vt; l < D.nlm; l += VT) stats_landmark(P, l);
-                const int grp = warp >> 2, gt = tid & 127;   // four 4-warp groups per CTA, one free pose each
-                const int b = rank * 4 + grp;
-                const bool act = warp < 16 && b < st.ncols / 6;
-                double v[12];
-                if (act) stats_pose_partial(P, b, gt, v);
-                else
-#pragma unroll
-                    for (int i = 0; i < 12; i++) v[i] = 0;
-#pragma unroll
-                for (int i = 0; i < 12; i++) {
-#pragma unroll
-                    for (int off = 16; off; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
-                    if (lane == 0 && warp < 16) part[grp][warp & 3][i] = v[i];
-                }
-                __syncthreads();
-                if (act && gt < 12) {
-                    const double t = part[grp][0][gt] + part[grp][1][gt] + part[grp][2][gt] + part[grp][3][gt];
-                    if (gt < 6) P.nf[6 * b + gt] = t;
-                    else P.gf[6 * b + gt - 6] = t;
-                }
-            }
-            cluster_barrier();
-            // ---- C. control before the step
-            if (rank == 0) ba_pre_body(P, D);
-            cluster_barrier();
-            if (mode == 0) return;
-        }
-        if (st.done || it == D.max_iter) break;
-        // ---- D. per-landmark Schur ingredients
-        const bool use_gather = st.use_gather != 0;
-        if (use_gather)
-            for (int l = vt; l < D.nlm; l += VT) lm_landmark(P, l);
-        cluster_barrier();
-        // ---- E. reduced camera system
-        if (use_gather) {
-            const int gw = rank * MG_WARPS + warp, half = lane >> 4, hl = lane & 15;
-            for (int u = gw; u < MG_UNITS; u += MG_CL * MG_WARPS) {
-                int bi, bj, prt = 0, nparts = 1;
-                if (u < NBMAX * MG_SPLIT) { bi = bj = u / MG_SPLIT; prt = u % MG_SPLIT; nparts = MG_SPLIT; }
-                else {
-                    int rem = u - NBMAX * MG_SPLIT;
-                    bi = 0;
-                    while (bi < NBMAX - 1 && rem >= NBMAX - 1 - bi) { rem -= NBMAX - 1 - bi; bi++; }
-                    bj = bi + 1 + rem;
-                }
-                if (bi >= st.nb || bj >= st.nb) continue;   // warp-uniform
-                const int blk = bi * NBMAX + bj, ci = 6 * bi, cj = 6 * bj;
-                int eb = 0;
-                for (int i = lane; i < blk; i += 32) eb += P.blk_start[i + 1];
-#pragma unroll
-                for (int off = 16; off; off >>= 1) eb += __shfl_xor_sync(0xffffffffu, eb, off);
-                const int ee = eb + P.blk_start[blk + 1];
-                double acc[18], rh[3], sci[6], scj[6];
-#pragma unroll
-                for (int i = 0; i < 18; i++) acc[i] = 0.0;
-#pragma unroll
-                for (int i = 0; i < 3; i++) rh[i] = 0.0;
-#pragma unroll
-                for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
-                for (int idx = eb + prt * 16 + hl; idx < ee; idx += nparts * 16)
-                    gather_entry_half(P, P.pairs[idx], sci, scj, half, acc, rh);
-                // fixed-order reduction over the 16 lanes of a half-warp
-#pragma unroll
-                for (int i = 0; i < 18; i++)
-#pragma unroll
-                    for (int off = 8; off; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int off = 8; off; off >>= 1) rh[i] += __shfl_xor_sync(0xffffffffu, rh[i], off);
-                if (hl == 0) {
-                    if (bi == bj) {
-                        double* slot = P.ga_part + ((size_t)bi * MG_SPLIT + prt) * 42;
-#pragma unroll
-                        for (int i = 0; i < 18; i++) slot[18 * half + i] = acc[i];
-#pragma unroll
-                        for (int i = 0; i < 3; i++) slot[36 + 3 * half + i] = rh[i];
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < 3; a++)
-#pragma unroll
-                            for (int c = 0; c < 6; c++) {
-                                const int ag = a + 3 * half;
-                                P.S[(ci + ag) * NMAX + cj + c] = acc[6 * a + c];
-                                P.S[(cj + c) * NMAX + ci + ag] = acc[6 * a + c];
-                            }
-                    }
-                }
-            }
-            cluster_barrier();
-            // diagonal blocks: the MG_SPLIT partial sums in part order
-            for (int x = vt; x < st.nb * 42; x += VT) {
-                const int bi = x / 42, e = x - 42 * bi, ci = 6 * bi;
-                const double* all = P.ga_part + (size_t)bi * MG_SPLIT * 42;
-                double v = 0;
-#pragma unroll
-                for (int q = 0; q < MG_SPLIT; q++) v += all[q * 42 + e];
-                if (e < 36) {
-                    const int a = e / 6, c = e - 6 * a;
-                    P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
-                } else P.rhs[ci + e - 36] = v;
-            }
-        } else {
-            for (int l = vt; l < D.nlm; l += VT) schur_landmark<false>(P, D, l);   // FP64-atomic fallback (structure too large)
-            cluster_barrier();
-        }
-        cluster_barrier();
-        // ---- F. reduced solve
-        if (rank == 0) ba_chol_body(P, sm);
-        cluster_barrier();
-        // ---- G. back-substitution + cost at the candidate point
-        {
-            for (int k = tid; k < D.nkf; k += MG_THREADS) {
-                backsub_cand_pose(P, k, cand_s + 7 * k);
-                if (rank == 0) for (int i = 0; i < 7; i++) P.cand_poses[7 * k + i] = cand_s[7 * k + i];
-            }
-            __syncthreads();
-            double acc = 0, cost = 0;
-            for (int l = vt; l < D.nlm; l += VT) {
-                acc += backsub_landmark(P, l);
-                const double ci = P.cand_invd[l];
-                for (int i = P.lm_start[l]; i < P.lm_start[l + 1]; i++) {
-                    const int o = P.lm_obs[i];
-                    cost += lin_obs<false>(P, D, o, l, cand_s, ci);
-                }
-            }
-            const double tm = block_sum_dyn(acc, red);
-            const double tc = block_sum_dyn(cost, red);
-            if (tid == 0) { P.mc_part[rank] = tm; P.cost_part[rank] = tc; }
-        }
-        cluster_barrier();
-        // ---- H. control after the step
-        if (rank == 0) ba_post_body(P, D);
-        cluster_barrier();
-    }
-}
-
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
 // Workspace carving: one contiguous block per problem.
 static int g_ba_dense_schur = 0;   // alva_set_option("ba_dense_schur", 1): tensor-core SYRK for the Schur term
-static int g_ba_mega = 0;          // alva_set_option("ba_mega", 1): the LM loop as ONE kernel (ba_mega_kernel) instead of one launch per phase
 
 static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     size_t d = 0;
@@ -1657,7 +1394,7 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     d += (size_t)nkf * 7 + nlm;                      // cand
     d += (size_t)nblk;                               // cost partials
     d += (size_t)((nlm + BS_THREADS - 1) / BS_THREADS);   // model-cost partials
-    d += (size_t)NBMAX * 16 * 42;                         // gather partials (max(GA_SPLIT, MG_SPLIT) = 16)
+    d += (size_t)NBMAX * GA_SPLIT * 42;                   // gather partials
     size_t bytes = d * sizeof(double);
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
     bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
@@ -1712,7 +1449,7 @@ static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, cons
             P.cand_poses = take(7 * (size_t)nkf); P.cand_invd = take(nlm); P.cost_part = take(nblk);
             P.Wt = g_ba_dense_schur ? take((size_t)((nlm + 3) / 4 * 4) * NMAX) : nullptr;
             P.mc_part = take((size_t)((nlm + BS_THREADS - 1) / BS_THREADS));
-            P.ga_part = take((size_t)NBMAX * 16 * 42);
+            P.ga_part = take((size_t)NBMAX * GA_SPLIT * 42);
             P.last_poses = local ? take(7 * (size_t)nkf) : nullptr;
             P.last_invd = local ? take(nlm) : nullptr;
             uint8_t* b = reinterpret_cast<uint8_t*>(d);
@@ -1754,26 +1491,6 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
     ALVA_LAUNCH_CHECK(ctx);
     const dim3 lin_grid(D.nblk, nprob), schur_grid((D.nlm_pad + 127) / 128, nprob), syrk_grid(16, SYRK_KSPLIT, nprob);
     const dim3 key_grid(GA_GRID, nprob), bs_grid(D.nbs, nprob), stats_grid(D.nbs + NBMAX, nprob);
-    if (g_ba_mega && !dense) {
-        // setup -> { block lists on the auxiliary stream | head of iteration 0 } -> the loop: 5 launches per solve
-        ALVA_CUDA(cudaFuncSetAttribute(ba_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-        const dim3 pr_grid(NBMAX, nprob), mg_grid(MG_CL, nprob);
-        cudaStream_t ps = ctx->stream;
-        bool fk = false;
-        if (ctx->aux_stream && cudaEventRecord(ctx->aux_fork, ctx->stream) == cudaSuccess &&
-            cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0) == cudaSuccess) { ps = ctx->aux_stream; fk = true; }
-        ba_pairs_kernel<0><<<pr_grid, 32, 0, ps>>>(dp, D);
-        ALVA_LAUNCH_CHECK(ctx);
-        ba_pairs_kernel<1><<<pr_grid, 32, 0, ps>>>(dp, D);
-        ALVA_LAUNCH_CHECK(ctx);
-        if (fk) ALVA_CUDA(cudaEventRecord(ctx->aux_join, ps));
-        ba_mega_kernel<<<mg_grid, MG_THREADS, chol_smem, ctx->stream>>>(dp, D, 0);
-        ALVA_LAUNCH_CHECK(ctx);
-        if (fk) ALVA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
-        ba_mega_kernel<<<mg_grid, MG_THREADS, chol_smem, ctx->stream>>>(dp, D, 1);
-        ALVA_LAUNCH_CHECK(ctx);
-        return 0;
-    }
     bool forked = false;
     if (!dense) {   // structure of the gather-form Schur complement, once per solve -- beside the first linearisation, which
                     // does not need it (fork / join on the context's auxiliary stream; also valid inside a stream capture)
@@ -1911,7 +1628,6 @@ extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
 extern int alva_g_pipeline_graphs, alva_g_ba_lag;   // pipeline.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
-    if (name && !strcmp(name, "ba_mega")) { g_ba_mega = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
     if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }

@@ -27,9 +27,8 @@ namespace {
 using namespace alva_init;
 
 constexpr int INIT_THREADS = 128;
-constexpr int CHUNK = INIT_THREADS;   // hypotheses solved per round, one per thread.  The bookkeeping replays them in draw order with the
-                                      // reference's adaptive bound, so the chunk size only decides how many are solved speculatively: 32
-                                      // (one warp working, three idle) made a 100-iteration RANSAC four serial rounds of ~0.7 ms each
+constexpr int CHUNK = 32;   // hypotheses solved per round (one per thread of the first warp; the solver's local arrays make it
+                            // local-memory bound: 128 per round was measured slower, 3.8 vs 2.8 ms for a 100-iteration RANSAC)
 
 struct EssentialParams {
     const double* bv1; const double* bv2; const int32_t* counts; int cap;

@@ -62,8 +62,15 @@ FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
 # sha256[:16] of the step's integer outputs (selected-feature counts + 2-NN match lists of all 64 frames) for the stream seeds
 # 99 + rank, rank 0..7: every run checks its own outputs against these (bit-exact stages: any change of a kernel's results, a
 # race, or a skipped stage shows here, inside the timed configuration).  Printed by `bench.py --print-checksums`.
-EXPECTED_OUTPUT_SHA = {99: "204d42bd422277ed", 100: "e04ea0ed49e3f800", 101: "e24449c668b5ec3d", 102: "9a985c1e891a9927",
-                       103: "755d6b883377afbf", 104: "1a0e044321185545", 105: "e4c0192f6cdbd669", 106: "33e552d94e9a17d7"}
+EXPECTED_OUTPUT_SHA = {99: "204d42bd422277ed", 100: "e04ea0ed49e3f800"}   # streams 2..7: regenerate (scene per pair of ranks)
+
+
+def stream_frames(rank):
+    """Synthetic camera stream of a rank: its own path (seed 99 + rank) over a scene it shares with ONE other stream (ranks 2k and
+    2k + 1 watch the same plane, other pairs other planes) -- so that at any N every stream has exactly one remote stream to close
+    loops with, and the cross-stream detector's work per rank does not grow with N."""
+    from alvaar_b200 import synth
+    return synth.make_frames(BATCH, W, H, seed=99 + rank, texture_seed=1234 + rank // 2)[0]
 
 
 def output_checksum(nfeat, matches):
@@ -249,7 +256,7 @@ def reference_worker(args):
         pass
     L, kind = load_cpu_impl()
     sample = REF_SAMPLE if kind == "reference" else 2
-    frames, _ = synth.make_frames(sample, W, H, seed=99 + args.stream)
+    frames = synth.make_frames(sample, W, H, seed=99 + args.stream, texture_seed=1234 + args.stream // 2)[0]
     _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
     ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -341,7 +348,7 @@ def bench_b200(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner ("NCCL version ...") must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    frames, _ = synth.make_frames(BATCH, W, H, seed=99 + rank)
+    frames = stream_frames(rank)
     _, map_desc = synth.make_descriptors(8, MAP_SIZE, seed=7)
     ba = synth.make_ba_problem(BA_NKF, BA_NLM, BA_OBS_PER_LM, seed=42)
     stream = torch.cuda.Stream()
@@ -386,7 +393,7 @@ def bench_b200(args, rank, world, local_rank):
         dev_s = f"cuda:{local_rank}"
         side = torch.cuda.Stream()
         lc_ctx = alvaar_b200.Context(local_rank, side.cuda_stream)
-        det = LoopClosure(lc_ctx, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H))
+        det = LoopClosure(lc_ctx, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H), min_matches=max(30, NFEAT // 10))
         kf_idx = torch.arange(0, BATCH, KF_INTERVAL, dtype=torch.int32, device=dev_s)[:pipe.nprob].contiguous()
         desc_all = pipe.buffer("desc", (BATCH, pipe.fcap, 32), torch.uint8)
         pts_all = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
@@ -591,7 +598,7 @@ def print_checksums():
         pipe.set_ba(s, ba)
     out = {}
     for seed in range(99, 107):
-        frames, _ = synth.make_frames(BATCH, W, H, seed=seed)
+        frames = stream_frames(seed - 99)
         host_in = torch.from_numpy(frames).pin_memory()
         nf = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
         mt = torch.zeros((BATCH, pipe.fcap, 4), dtype=torch.int32).pin_memory()

@@ -221,25 +221,3 @@ def test_local_ba_batch_mixed_skip(gpu_ctx, oracle):
         if i == 1:
             assert nb == 0 and (gs[i][5:] == 0).all()
 
-
-@pytest.mark.parametrize("nkf,nlm,opl,seed,iters", [(20, 3000, 4, 42, 5), (8, 300, 3, 7, 5), (12, 900, 3, 3, 0), (20, 3000, 4, 9, 12)])
-def test_one_kernel_loop_equals_launch_sequence(gpu_ctx, nkf, nlm, opl, seed, iters):
-    """ba_mega_kernel (a thread-block cluster per problem runs the whole LM loop, cluster barriers between the phases) against
-    the one-launch-per-phase sequence: same device functions, different summation partitions -> agreement to rounding, identical
-    iteration counts / termination; and the result does not depend on how many problems share the launch."""
-    pbs = [synth.make_ba_problem(nkf, nlm, opl, seed=seed + i) for i in range(3)]
-    L = gpu_ctx.L
-    try:
-        assert L.alva_set_option(b"ba_mega", 0) == 0
-        p0, d0, s0 = gpu_solve(gpu_ctx, pbs, max_iter=iters)
-        assert L.alva_set_option(b"ba_mega", 1) == 0
-        p1, d1, s1 = gpu_solve(gpu_ctx, pbs, max_iter=iters)
-        p2, d2, s2 = gpu_solve(gpu_ctx, pbs, max_iter=iters)
-        q1, e1, t1 = gpu_solve(gpu_ctx, pbs[1:2], max_iter=iters)
-    finally:
-        L.alva_set_option(b"ba_mega", 1)
-    assert np.array_equal(s0[:, 2:5], s1[:, 2:5])                       # successful steps, iterations, termination
-    assert np.allclose(s0[:, :2], s1[:, :2], rtol=1e-9)                 # initial / final cost
-    assert np.abs(p0 - p1).max() < 1e-9 and np.abs(d0 - d1).max() < 1e-9
-    assert np.array_equal(p1, p2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)      # bit-reproducible run to run
-    assert np.array_equal(q1[0], p1[1]) and np.array_equal(e1[0], d1[1])                      # independent of the batch
