@@ -71,8 +71,10 @@ struct BaProblem {
     int32_t *obs_col, *anch_col;            // reduced-system column of each observation's / landmark anchor's pose (-1: fixed)
     int32_t *pstart;                        // gather Schur: [NBMAX + 1] ranges of plist per free pose
     uint32_t *plist;                        // gather Schur: (landmark << 8) | slot, every (landmark, slot) seeing that pose, by landmark
-    int32_t *blk_start;                     // gather Schur: [NBMAX*NBMAX + 1] entry ranges per 6x6 block (bi <= bj), row-major
-    uint32_t *pairs;                        // gather Schur: (landmark << 16) | (slot_u << 8) | slot_v per block, in plist order
+    int32_t *blk_start;                     // gather Schur: [NBMAX*NBMAX + 1] entry COUNTS per 6x6 block (bi <= bj), row-major, at [blk + 1]
+    int32_t *blk_off;                       // gather Schur: [NBMAX*NBMAX] first entry of each block
+    uint64_t *pairs;                        // gather Schur: per block, in plist order: landmark << 48 | slot_u << 40 | slot_v << 32 |
+                                            //   observation index of slot_u << 16 | of slot_v (0xffff for the anchor slot)
     // alva_k_ba_local only (null otherwise): obs_lm above then points at obs_lm_w, the working copy removals are made in
     const int32_t* obs_lm_in;               // caller's obs_lm
     int32_t* obs_lm_w;                      // [nobs]
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) ba_setup_kernel(const BaProblem
     if (tid == 0) {
         int mo = 0;
         for (int i = 0; i < NT / 32; i++) mo = max(mo, scan_s[i]);
-        P.st->use_gather = (mo < 255 && D.nlm < 65536) ? 1 : 0;
+        P.st->use_gather = (mo < 255 && D.nlm < 65536 && D.nobs < 65535) ? 1 : 0;
     }
 }
 
@@ -523,7 +525,10 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
     if (lane < NBMAX) cnt[lane] = 0;
     if (lane == 0) {
         int run = base_row;
-        for (int bj = 0; bj < NBMAX; bj++) { boff[bj] = run; if (MODE == 1) run += P.blk_start[bi * NBMAX + bj + 1]; }
+        for (int bj = 0; bj < NBMAX; bj++) {
+            boff[bj] = run;
+            if (MODE == 1) { P.blk_off[bi * NBMAX + bj] = run; run += P.blk_start[bi * NBMAX + bj + 1]; }
+        }
     }
     __syncwarp();
     int eb = 0;
@@ -536,19 +541,22 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
         const int l = en >> 8, su = en & 0xff;
         const int ob = live ? P.lm_start[l] : 0, ns = live ? P.lm_start[l + 1] - ob : -1;
         // the reduced-system columns of the first four slots, fetched together (independent loads) before the serial rounds
-        int cv0 = -1, cv1 = -1, cv2 = -1, cv3 = -1;
+        int cv0 = -1, cv1 = -1, cv2 = -1, cv3 = -1, o1 = -1, o2 = -1, o3 = -1, ou = 0xffff;
         if (live) {
             cv0 = P.anch_col[l];
-            const int o1 = ns >= 1 ? P.lm_obs[ob] : -1, o2 = ns >= 2 ? P.lm_obs[ob + 1] : -1, o3 = ns >= 3 ? P.lm_obs[ob + 2] : -1;
+            o1 = ns >= 1 ? P.lm_obs[ob] : -1; o2 = ns >= 2 ? P.lm_obs[ob + 1] : -1; o3 = ns >= 3 ? P.lm_obs[ob + 2] : -1;
             if (o1 >= 0) cv1 = P.obs_col[o1];
             if (o2 >= 0) cv2 = P.obs_col[o2];
             if (o3 >= 0) cv3 = P.obs_col[o3];
+            if (MODE == 1 && su) ou = su == 1 ? o1 : su == 2 ? o2 : su == 3 ? o3 : P.lm_obs[ob + su - 1];
         }
         for (int sv = 0; sv <= 255; sv++) {                 // slot-major rounds (ns is small: 3 in the reference's problems)
             if (!__any_sync(0xffffffffu, live && sv <= ns)) break;
-            int bjv = -1;
+            int bjv = -1, bjv_ov = 0xffff;
             if (live && sv <= ns) {
-                const int cv = sv == 0 ? cv0 : sv == 1 ? cv1 : sv == 2 ? cv2 : sv == 3 ? cv3 : P.obs_col[P.lm_obs[ob + sv - 1]];
+                const int ov = sv == 0 ? 0xffff : sv == 1 ? o1 : sv == 2 ? o2 : sv == 3 ? o3 : P.lm_obs[ob + sv - 1];
+                bjv_ov = ov;
+                const int cv = sv == 0 ? cv0 : sv == 1 ? cv1 : sv == 2 ? cv2 : sv == 3 ? cv3 : P.obs_col[ov];
                 if (cv >= 0) { const int bj = cv / 6; if (bj > bi || (bj == bi && sv >= su)) bjv = bj; }
                 // a landmark seen twice from one keyframe (two slots on the same pose) needs the transposed contribution
                 // as well; localBA never builds that, so such problems simply take the atomic Schur path instead
@@ -561,7 +569,9 @@ __global__ void __launch_bounds__(32) ba_pairs_kernel(const BaProblem* __restric
                 const int old = cnt[bjv];
                 if (MODE == 1) {
                     const int pos = boff[bjv] + old + rank;
-                    if (pos < D.ecap) P.pairs[pos] = ((uint32_t)l << 16) | ((uint32_t)su << 8) | (uint32_t)sv;
+                    if (pos < D.ecap)
+                        P.pairs[pos] = ((uint64_t)l << 48) | ((uint64_t)su << 40) | ((uint64_t)sv << 32) | ((uint64_t)(ou & 0xffff) << 16) |
+                                       (uint64_t)(bjv_ov & 0xffff);
                 }
                 __syncwarp(m);
                 if (rank == 0) cnt[bjv] = old + __popc(m);
@@ -880,12 +890,13 @@ __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict_
 // Contribution of one (landmark, slot_u, slot_v) entry to block (bi, bj):  C = F_u'F_v - w_u w_v' / (E'E + D^2)  and, for
 // u == v, the right-hand side F_u'b - w_u E'b / (E'E + D^2).  TRANSPOSE adds C' instead (second half of a duplicate-pose pair).
 template <bool TRANSPOSE>   // TRANSPOSE is kept for completeness; the kernel only instantiates <false>
-__device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, const double* sci, const double* scj, double* acc,
+__device__ __forceinline__ void gather_entry(const BaProblem& P, uint64_t en, const double* sci, const double* scj, double* acc,
                                              double* rh) {
-    const int l = en >> 16, su = (en >> 8) & 0xff, sv = en & 0xff;
-    const int ob = P.lm_start[l];
+    // the entry carries the observation indices of its two slots: the loads below depend on it alone (the first version looked them
+    // up through lm_start -> lm_obs: two more round trips in a kernel that is nothing but dependent round trips)
+    const int l = (int)(en >> 48), su = (int)(en >> 40) & 0xff, sv = (int)(en >> 32) & 0xff;
     const double inv = 1.0 / P.ete[l], etb = P.etb[l];
-    const int ou = su ? P.lm_obs[ob + su - 1] : -1, ov = sv ? P.lm_obs[ob + sv - 1] : -1;
+    const int ou = su ? (int)(en >> 16) & 0xffff : -1, ov = sv ? (int)en & 0xffff : -1;
     double wu[6], wv[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) {
@@ -899,7 +910,7 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, co
         for (int c = 0; c < 6; c++) ACC(a, c) -= wu[a] * wv[c];
     // F_u' F_v: non-zero only when both slots share a residual row pair
     if (su == 0 && sv == 0) {                        // anchor x anchor: every observation of the landmark
-        const int oe = P.lm_start[l + 1];
+        const int ob = P.lm_start[l], oe = P.lm_start[l + 1];
         for (int i = ob; i < oe; i++) {
             const int o = P.lm_obs[i];
             double F0[6], F1[6];
@@ -953,7 +964,7 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint32_t en, co
 // mirror are stored -- no floating-point atomics, bit-reproducible.
 constexpr int GA_THREADS = 64, GA_SPLIT = 8;
 constexpr int GA_GRID = NBMAX * GA_SPLIT + (MAXKEYS - NBMAX);   // diagonal parts first, then the strictly upper blocks
-__global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+__global__ void __launch_bounds__(GA_THREADS, 8) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
     if (st.done || !st.use_gather) return;
@@ -968,18 +979,10 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
     if (bi >= st.nb || bj >= st.nb) return;
     const int blk = bi * NBMAX + bj;
     __shared__ double red[GA_THREADS / 32][42];
-    __shared__ int eb_s, last_s;
+    __shared__ int last_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci = 6 * bi, cj = 6 * bj;
-    if (warp == 0) {   // start of this block's entries = sum of the counts of all preceding blocks
-        int sum = 0;
-        for (int i = lane; i < blk; i += 32) sum += P.blk_start[i + 1];
-#pragma unroll
-        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (lane == 0) eb_s = sum;
-    }
-    __syncthreads();
-    const int eb = eb_s, ee = eb + P.blk_start[blk + 1];
+    const int eb = P.blk_off[blk], ee = eb + P.blk_start[blk + 1];
     double acc[36], rh[6];
 #pragma unroll
     for (int i = 0; i < 36; i++) acc[i] = 0.0;
@@ -989,7 +992,7 @@ __global__ void __launch_bounds__(GA_THREADS) ba_gather_kernel(const BaProblem* 
 #pragma unroll
     for (int c = 0; c < 6; c++) { sci[c] = P.scf[ci + c]; scj[c] = P.scf[cj + c]; }
     for (int idx = eb + part * GA_THREADS + tid; idx < ee; idx += nparts * GA_THREADS) {
-        const uint32_t en = P.pairs[idx];
+        const uint64_t en = P.pairs[idx];
         gather_entry<false>(P, en, sci, scj, acc, rh);   // (duplicate-pose pairs never reach this kernel: see ba_pairs_kernel)
     }
     // fixed-order reduction: butterfly inside each warp, then the warps in order
@@ -1382,6 +1385,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Workspace carving: one contiguous block per problem.
 static int g_ba_dense_schur = 0;   // alva_set_option("ba_dense_schur", 1): tensor-core SYRK for the Schur term
+static int g_ba_ctl_threads = CT_THREADS;   // alva_set_option("ba_ctl_threads", 256 | 512 | 1024): CTA size of the control kernels
 
 static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     size_t d = 0;
@@ -1399,7 +1403,7 @@ static size_t ba_ws_bytes(int nkf, int nlm, int nobs, int nblk) {
     bytes += align_up((size_t)nkf * 4, 8) + align_up((size_t)(nlm + 1) * 4, 8) + align_up((size_t)nobs * 4, 8);
     bytes += align_up((size_t)nobs * 4, 8) + align_up((size_t)nlm * 4, 8);                          // obs_col, anch_col
     bytes += align_up((size_t)(NBMAX + 1) * 4, 8) + align_up(((size_t)nobs + (size_t)nlm) * 4, 8);   // pstart, plist
-    bytes += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);   // blk_start, pairs
+    bytes += 2 * align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8) + align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 8, 8);   // blk_start, blk_off, pairs
     bytes += align_up((size_t)NBMAX * 4, 8);                                                        // ga_ticket
     bytes += align_up(sizeof(BaState), 8);
     return align_up(bytes, 256);
@@ -1461,7 +1465,8 @@ static int ba_prepare(alva_ctx* ctx, int nprob, int nkf, int nlm, int nobs, cons
             P.pstart = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX + 1) * 4, 8);
             P.plist = reinterpret_cast<uint32_t*>(b); b += align_up(((size_t)nobs + (size_t)nlm) * 4, 8);
             P.blk_start = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8);
-            P.pairs = reinterpret_cast<uint32_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 4, 8);
+            P.blk_off = reinterpret_cast<int32_t*>(b); b += align_up((size_t)(NBMAX * NBMAX + 1) * 4, 8);
+            P.pairs = reinterpret_cast<uint64_t*>(b); b += align_up((size_t)(8 * (size_t)nobs + 2 * (size_t)nlm) * 8, 8);
             P.ga_ticket = reinterpret_cast<int32_t*>(b); b += align_up((size_t)NBMAX * 4, 8);
             P.obs_lm_in = nullptr; P.obs_lm_w = nullptr; P.flags = nullptr;
             if (local) {
@@ -1509,7 +1514,7 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
         ALVA_LAUNCH_CHECK(ctx);
         ba_stats_kernel<<<stats_grid, BS_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_pre_kernel<<<nprob, CT_THREADS, 0, ctx->stream>>>(dp, D);
+        ba_pre_kernel<<<nprob, g_ba_ctl_threads, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
         if (it == D.max_iter) {   // the last pass only finalises (iteration count reached)
             if (forked) { ALVA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0)); forked = false; }   // max_iter == 0
@@ -1535,7 +1540,7 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
         ALVA_LAUNCH_CHECK(ctx);
         ba_linearize_kernel<false><<<lin_grid, LIN_THREADS, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
-        ba_post_kernel<<<nprob, CT_THREADS, 0, ctx->stream>>>(dp, D);
+        ba_post_kernel<<<nprob, g_ba_ctl_threads, 0, ctx->stream>>>(dp, D);
         ALVA_LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -1628,6 +1633,7 @@ extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
 extern int alva_g_pipeline_graphs, alva_g_ba_lag;   // pipeline.cu
 extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_dense_schur")) { g_ba_dense_schur = value ? 1 : 0; return 0; }
+    if (name && !strcmp(name, "ba_ctl_threads") && (value == 256 || value == 512 || value == 1024)) { g_ba_ctl_threads = value; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
     if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }
