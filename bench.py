@@ -62,7 +62,8 @@ FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
 # sha256[:16] of the step's integer outputs (selected-feature counts + 2-NN match lists of all 64 frames) for the stream seeds
 # 99 + rank, rank 0..7: every run checks its own outputs against these (bit-exact stages: any change of a kernel's results, a
 # race, or a skipped stage shows here, inside the timed configuration).  Printed by `bench.py --print-checksums`.
-EXPECTED_OUTPUT_SHA = {99: "204d42bd422277ed", 100: "e04ea0ed49e3f800"}   # streams 2..7: regenerate (scene per pair of ranks)
+EXPECTED_OUTPUT_SHA = {99: "204d42bd422277ed", 100: "e04ea0ed49e3f800", 101: "acde5d4ba6701be4", 102: "f54044662430e0e4",
+                       103: "31071a9894265b65", 104: "75e995f22e29f387", 105: "d98331275913f47e", 106: "0e082756b2905b60"}
 
 
 def stream_frames(rank):
@@ -393,15 +394,18 @@ def bench_b200(args, rank, world, local_rank):
     if dist is not None and not args.no_loop_closure:
         from alvaar_b200.loopclosure import LoopClosure, block_bytes
         dev_s = f"cuda:{local_rank}"
-        side = torch.cuda.Stream()
-        lc_ctx = alvaar_b200.Context(local_rank, side.cuda_stream)
-        det = LoopClosure(lc_ctx, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H), min_matches=max(30, NFEAT // 10))
+        # LC_RING detectors, each with its own stream and buffers, take the steps in turn: one geometric check (five-point RANSAC of
+        # the step's keyframe pairs) takes ~2.8 ms -- two steps -- so three in flight keep up with the frame rate
+        LC_RING = 3
+        sides = [torch.cuda.Stream() for _ in range(LC_RING)]
+        lc_ctxs = [alvaar_b200.Context(local_rank, sd.cuda_stream) for sd in sides]
+        dets = [LoopClosure(c, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H), min_matches=max(30, NFEAT // 10)) for c in lc_ctxs]
+        det = dets[0]
         kf_idx = torch.arange(0, BATCH, KF_INTERVAL, dtype=torch.int32, device=dev_s)[:pipe.nprob].contiguous()
         desc_all = pipe.buffer("desc", (BATCH, pipe.fcap, 32), torch.uint8)
         pts_all = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
         cnt_all = pipe.buffer("selcounts", (BATCH,), torch.int32)
         bb = block_bytes(pipe.fcap)
-        LC_RING = 3
         send = [torch.zeros(pipe.nprob * bb, dtype=torch.uint8, device=dev_s) for _ in range(LC_RING)]
         gathered_buf = [torch.zeros(world * pipe.nprob * bb, dtype=torch.uint8, device=dev_s) for _ in range(LC_RING)]
         ev_packed = [torch.cuda.Event() for _ in range(LC_RING)]
@@ -415,17 +419,19 @@ def bench_b200(args, rank, world, local_rank):
             # main stream never waits for a detection: only, three steps later, for the all-gather that read the ring slot it is
             # about to refill.  Results are polled without blocking (the detector keeps at most 4 steps in flight).
             i = lc_state["step"] % LC_RING
+            d, side = dets[i], sides[i]
             if lc_state["step"] >= LC_RING:
                 stream.wait_event(ev_gathered[i])
-            det.pack(desc_all, pts_all, cnt_all, kf_idx, send[i], on=ctx)
+            d.seq = lc_state["step"] * pipe.nprob          # keyframe sequence numbers run on across the detectors
+            d.pack(desc_all, pts_all, cnt_all, kf_idx, send[i], on=ctx)
             ev_packed[i].record(stream)
             with torch.cuda.stream(side):
                 side.wait_event(ev_packed[i])
                 dist.all_gather_into_tensor(gathered_buf[i], send[i])
                 ev_gathered[i].record(side)
-                det.detect(gathered_buf[i])
+                d.detect(gathered_buf[i])
             lc_state["step"] += 1
-            lc_events.extend(det.poll())
+            lc_events.extend(d.poll())
             return gathered_buf[i]
 
     sampler = ClockSampler(local_rank)
@@ -436,7 +442,8 @@ def bench_b200(args, rank, world, local_rank):
                 lc()
         pipe.drain()
         if lc:
-            stream.wait_stream(side)
+            for sd in sides:
+                stream.wait_stream(sd)
         barrier()
         l0 = ctx.launches
         sampler.start()
@@ -448,7 +455,8 @@ def bench_b200(args, rank, world, local_rank):
                 gathered = lc()
         pipe.drain()   # the last step's BA chain belongs to the timed region
         if lc:
-            stream.wait_stream(side)   # ... and so does the last step's exchange + detection
+            for sd in sides:
+                stream.wait_stream(sd)   # ... and so do the exchanges + detections still in flight
         ev1.record(stream)
         barrier()
         launches = ctx.launches - l0
@@ -512,12 +520,15 @@ def bench_b200(args, rank, world, local_rank):
     lc_report = None
     if det is not None:
         torch.cuda.synchronize()
-        lc_events.extend(det.poll(wait=True))
+        for d in dets:
+            lc_events.extend(d.poll(wait=True))
         sc = det.last_scores()
         lc_report = {"keyframe_blocks_per_step": int(world * pipe.nprob), "block_bytes": int(block_bytes(pipe.fcap)),
-                     "events": len(lc_events), "last_step_pairs_checked": int((sc[:, :, 0] >= 30).sum()),
+                     "events": len(lc_events), "remote_ranks_with_events": sorted({int(e["remote_rank"]) for e in lc_events}),
+                     "last_step_pairs_checked": int((sc[:, :, 0] >= max(30, NFEAT // 10)).sum()),
                      "last_step_pairs_verified": int((sc[:, :, 1] == 1).sum()),
-                     "schedule": "side stream: pack -> ncclAllGather -> Hamming 2-NN (live descriptors) -> ratio test -> 5-point RANSAC; polled"}
+                     "schedule": "pack on the main stream -> ring of 3 side streams, one detector each: ncclAllGather -> Hamming 2-NN (live "
+                                 "descriptors) -> ratio test -> 5-point RANSAC; polled; streams 2k and 2k+1 watch the same scene"}
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
