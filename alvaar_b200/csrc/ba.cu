@@ -1628,7 +1628,7 @@ extern "C" int alva_k_ba_linearize(alva_ctx* ctx, int nkf, int nlm, int nobs, co
 extern int alva_g_knn_qpw;   // hamming.cu
 int alva_g_ba_overlap = 1;   // pipeline.cu: local BA on its own stream beside the frame stages
 
-extern int alva_g_frontend_antipodal, alva_g_frontend_variant, alva_g_frontend_prefetch;   // frontend.cu
+extern int alva_g_frontend_antipodal, alva_g_frontend_variant, alva_g_frontend_prefetch, alva_g_frontend_ctas;   // frontend.cu
 extern int alva_g_knn_mma, alva_g_knn_mma_mode, alva_g_knn_mma_kind;
 extern int alva_g_pipeline_graphs, alva_g_ba_lag;   // pipeline.cu
 extern "C" int alva_set_option(const char* name, int value) {
@@ -1636,6 +1636,7 @@ extern "C" int alva_set_option(const char* name, int value) {
     if (name && !strcmp(name, "ba_ctl_threads") && (value == 256 || value == 512 || value == 1024)) { g_ba_ctl_threads = value; return 0; }
     if (name && !strcmp(name, "frontend_antipodal")) { alva_g_frontend_antipodal = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "frontend_variant") && (value == 0 || value == 2)) { alva_g_frontend_variant = value; return 0; }
+    if (name && !strcmp(name, "frontend_ctas") && (value == 4 || value == 5)) { alva_g_frontend_ctas = value; return 0; }
     if (name && !strcmp(name, "frontend_prefetch")) { alva_g_frontend_prefetch = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_graphs")) { alva_g_pipeline_graphs = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "pipeline_ba_lag")) { alva_g_ba_lag = value ? 1 : 0; return 0; }

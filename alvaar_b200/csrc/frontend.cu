@@ -1059,6 +1059,7 @@ __global__ void __launch_bounds__(256) scharr_kernel(const ScharrLevels L) {
 // =================================================================================== host launchers
 int alva_g_frontend_antipodal = 0;   // alva_set_option("frontend_antipodal", 1): experimental pre-test variant (RGBA path only)
 int alva_g_frontend_prefetch = 0;    // alva_set_option("frontend_prefetch", 1): variant 2 pulls a later frame's tile into L2 (TMA prefetch)
+int alva_g_frontend_ctas = 5;        // alva_set_option("frontend_ctas", 4 | 5): resident CTAs per SM of variant 2
 int alva_g_frontend_variant = 2;     // alva_set_option("frontend_variant", 0 | 2): 0 = the round-1 kernel, 2 = frontend_tile_kernel_v2
 
 static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, int w, int h, int nframes, uint8_t* l0,
@@ -1093,7 +1094,9 @@ static int launch_frontend(alva_ctx* ctx, bool rgba_mode, const uint8_t* src, in
     const int grid = P.tiles_x * P.tiles_y * nframes;
     const size_t smem = sizeof(SmemLayout) + 128;
     if (v2) {
-        const size_t smem2 = sizeof(SmemLayout2) + 128;
+        // "frontend_ctas" = 4: pad the request so that only 4 CTAs fit an SM (5 by default) -- leaves registers and shared memory
+        // for the small kernels of a concurrent stream (the pipeline's BA chain)
+        const size_t smem2 = sizeof(SmemLayout2) + 128 + (alva_g_frontend_ctas == 4 ? 11 * 1024 : 0);
         if (P.tiles_y > 65535 || nframes > 65535) { alva_set_error("front end: more than 65535 frames / tile rows in one launch"); return ALVA_E_INVALID; }
         const dim3 grid3(P.tiles_x, P.tiles_y, nframes);
         // L2 prefetch distance: the tile at the same position this many frames ahead starts about one residency later

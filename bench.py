@@ -364,6 +364,8 @@ def bench_b200(args, rank, world, local_rank):
                           "delivered one step later as the reference's mapper thread does); the timed region starts drained and ends with "
                           "alva_pipeline_drain, so it holds exactly K frame batches and K x 13 BA solves")
     ctx.L.alva_set_option(b"pipeline_graphs", 0 if args.no_graphs else 1)
+    if args.frontend_ctas:
+        assert ctx.L.alva_set_option(b"frontend_ctas", args.frontend_ctas) == 0
     if args.ba_ctl_threads:
         assert ctx.L.alva_set_option(b"ba_ctl_threads", args.ba_ctl_threads) == 0
     pipe = Pipeline(ctx, W, H, BATCH, fast_thr=FAST_THR, nfeatures=NFEAT, orb_flags=alvaar_b200.ORB_IC_ANGLE | alvaar_b200.ORB_HARRIS,
@@ -832,6 +834,7 @@ def main():
     ap.add_argument("--ba-lag", action="store_true",
                     help="join a step's BA chain at the end of the NEXT step (pipeline_ba_lag = 1; measured +6 %% frames/s, but the chain "
                          "then shares the GPU with the next step's front end, whose launch the roofline figure times)")
+    ap.add_argument("--frontend-ctas", type=int, default=0, help="A/B: resident front-end CTAs per SM (4 | 5)")
     ap.add_argument("--ba-ctl-threads", type=int, default=0, help="A/B: CTA size of the BA control kernels (256 | 512 | 1024)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs (profiling aid)")
     args = ap.parse_args()
