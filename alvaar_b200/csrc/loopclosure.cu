@@ -12,11 +12,12 @@
 //      2-NN over the live descriptors only;
 //   2. lc_score_kernel: ratio test (best * ratio_den < second * ratio_num) + absolute distance gate -> putative matches, their
 //      count, and the matched pairs' bearing vectors (pixel -> unit bearing with the block's own intrinsics);
-//   3. alva_k_essential_5pt over all K x world candidate pairs in one batch (pairs with fewer than min_matches matches have
-//      count 0 and return at once): five-point RANSAC = the geometric check;
+//   3. alva_k_essential_5pt (32 hypotheses = one round of the five-point RANSAC) for the NEWEST keyframe of the step against every
+//      remote stream with >= min_matches matches: the geometric check (every other pair has count 0 and returns at once);
 //   4. one small device-to-host copy of {matches, success, inliers} per pair into page-locked memory + an event.
-// alva_lc_poll() (host) consumes finished steps in order and applies the temporal rule: a loop with remote stream r is reported
-// when the last `min_consecutive` keyframe events against r all passed the geometric check with >= min_inliers inliers.
+// alva_lc_poll() (host) consumes finished steps in order and applies the temporal rule: a loop with remote stream r is reported on
+// the newest keyframe of a step when the last `min_consecutive` keyframe events against r all had >= min_matches putative matches
+// and that keyframe passed the geometric check with >= min_inliers inliers.
 #include "alva_common.cuh"
 #include "../../include/alva_b200.h"
 #include <deque>
@@ -126,7 +127,10 @@ __global__ void __launch_bounds__(256) lc_score_kernel(const uint8_t* __restrict
     if (tid == 0) {
         const int n = base_s;
         nmatch[p] = n;
-        npair[p] = n >= min_matches ? min(n, PAIR_CAP) : 0;   // 0 -> the geometric check returns at once for this pair
+        // the geometric check is run for the NEWEST keyframe of the step only (0 -> it returns at once for this pair): one round of
+        // the five-point RANSAC is ~2.8 ms of serial FP64 (Sturm / Newton root isolation: dependent Horner chains), longer than a
+        // pipeline step, and the temporal rule already asks the earlier events of the streak for match counts only
+        npair[p] = (e == K - 1 && n >= min_matches) ? min(n, PAIR_CAP) : 0;
     }
 }
 
@@ -280,9 +284,13 @@ extern "C" int alva_lc_poll(alva_lc* lc, alva_lc_event* out, int cap, int wait) 
             for (int r = 0; r < c.world; r++) {
                 if (r == c.rank) continue;
                 const double* o = res + (size_t)(e * c.world + r) * 16;
-                const bool pass = o[1] != 0.0 && (int)o[2] >= c.min_inliers;
+                // streak of keyframe events with enough ratio-tested matches; on the newest keyframe of a step the geometric check
+                // ran as well and must have passed -- a loop is reported there, once the streak is long enough
+                const bool enough = (int)o[0] >= c.min_matches;
+                const bool checked = e == c.kf_per_step - 1;
+                const bool pass = enough && (!checked || (o[1] != 0.0 && (int)o[2] >= c.min_inliers));
                 lc->consecutive[r] = pass ? lc->consecutive[r] + 1 : 0;
-                if (pass && lc->consecutive[r] >= c.min_consecutive) {
+                if (pass && checked && lc->consecutive[r] >= c.min_consecutive) {
                     alva_lc_event ev{};
                     ev.local_kf = lc->local_seq0[slot] + e; ev.remote_rank = r; ev.remote_kf = (int)o[3];
                     ev.n_matches = (int)o[0]; ev.n_inliers = (int)o[2]; ev.consecutive = lc->consecutive[r];

@@ -418,19 +418,21 @@ int  alva_system_unpin_buffer(alva_system*, void* host_ptr);
  *                     pts [nframes][cap][2] float, counts [nframes]; all DEVICE pointers) -> send (device, kf_per_step blocks).
  *                     K4 (host): fx, fy, cx, cy.  kf_seq0: sequence number of the first of them.
  * alva_lc_detect    : on the gathered blocks (device, [world][kf_per_step] blocks): Hamming 2-NN of keyframe e of this rank against
- *                     keyframe e of every other rank, ratio test, five-point RANSAC on the putative matches; enqueues only.
- * alva_lc_poll      : finished steps are consumed in order; a loop with remote stream r is reported when the last min_consecutive
- *                     keyframe events against r all passed RANSAC with >= min_inliers inliers.  Returns the number of events. */
+ *                     keyframe e of every other rank, ratio test; five-point RANSAC (32 hypotheses) on the putative matches of the
+ *                     step's NEWEST keyframe against every remote stream with >= min_matches of them; enqueues only.
+ * alva_lc_poll      : finished steps are consumed in order; a loop with remote stream r is reported on the newest keyframe of a
+ *                     step when the last min_consecutive keyframe events against r all had >= min_matches putative matches and
+ *                     that keyframe passed RANSAC with >= min_inliers inliers.  Returns the number of events. */
 #define ALVA_LC_MAGIC        0x464B4C41   /* "ALKF" */
 #define ALVA_LC_VERSION      1
 #define ALVA_LC_HEADER_BYTES 64
 typedef struct alva_lc alva_lc;
 typedef struct {
     int32_t n_max, kf_per_step, world, rank;
-    int32_t min_matches;       /* putative matches needed before the geometric check runs (default 30) */
+    int32_t min_matches;       /* putative matches a keyframe event needs to count / before the geometric check runs (default 30) */
     int32_t max_dist;          /* absolute Hamming gate on the best match (default 64) */
     int32_t ratio_num, ratio_den;   /* ratio test: best * ratio_den < second * ratio_num (default 4 / 5) */
-    int32_t min_consecutive;   /* keyframe events in a row that must pass (default 3) */
+    int32_t min_consecutive;   /* keyframe events in a row that must have enough matches (default 3) */
     int32_t min_inliers;       /* RANSAC inliers needed (default 20) */
     float err_px, fx_hint, fy_hint;   /* RANSAC threshold in pixels (default 3) at this focal length (default 500) */
 } alva_lc_config;
