@@ -396,13 +396,18 @@ def bench_b200(args, rank, world, local_rank):
     if dist is not None and not args.no_loop_closure:
         from alvaar_b200.loopclosure import LoopClosure, block_bytes
         dev_s = f"cuda:{local_rank}"
-        # LC_RING detectors, each with its own stream and buffers, take the steps in turn: one geometric check (five-point RANSAC of
-        # the step's keyframe pairs) takes ~2.8 ms -- two steps -- so three in flight keep up with the frame rate
-        LC_RING = 3
-        sides = [torch.cuda.Stream() for _ in range(LC_RING)]
+        # One communication stream (the NCCL all-gather of every step, never behind a detection) and ND detectors, each with its own
+        # stream and buffers.  A geometric check (one round of the five-point RANSAC) takes 2.8 ms alone and ~6 ms beside the frame
+        # stages -- several steps -- so a step's gathered blocks go to a detector only if one is idle; otherwise the step is exchanged
+        # but not examined (counted in loop_closure.steps_not_examined).  Skipping is a local decision: the collective runs every step.
+        LC_RING, ND = 8, 3
+        comm = torch.cuda.Stream()
+        sides = [torch.cuda.Stream() for _ in range(ND)]
         lc_ctxs = [alvaar_b200.Context(local_rank, sd.cuda_stream) for sd in sides]
         dets = [LoopClosure(c, pipe.fcap, pipe.nprob, world, rank, synth.intrinsics(W, H), min_matches=max(30, NFEAT // 10)) for c in lc_ctxs]
         det = dets[0]
+        for d in dets:
+            d.L.alva_lc_inflight.argtypes = [C.c_void_p]
         kf_idx = torch.arange(0, BATCH, KF_INTERVAL, dtype=torch.int32, device=dev_s)[:pipe.nprob].contiguous()
         desc_all = pipe.buffer("desc", (BATCH, pipe.fcap, 32), torch.uint8)
         pts_all = pipe.buffer("pts", (BATCH, pipe.fcap, 2), torch.float32)
@@ -412,28 +417,45 @@ def bench_b200(args, rank, world, local_rank):
         gathered_buf = [torch.zeros(world * pipe.nprob * bb, dtype=torch.uint8, device=dev_s) for _ in range(LC_RING)]
         ev_packed = [torch.cuda.Event() for _ in range(LC_RING)]
         ev_gathered = [torch.cuda.Event() for _ in range(LC_RING)]
-        lc_state = {"step": 0}
+        ev_examined = [torch.cuda.Event() for _ in range(LC_RING)]
+        slot_examined = [False] * LC_RING
+        lc_state = {"step": 0, "examined": 0, "skipped": 0}
 
         def lc():
             # Off the per-frame path.  The step's keyframe blocks are packed on the MAIN stream (microseconds, right behind the
-            # kernels that produced the descriptors) into a ring of send buffers; the NCCL all-gather and the cross-stream detection
-            # (Hamming 2-NN of the live descriptors, ratio test, five-point RANSAC) run on a side stream beside the next steps.  The
-            # main stream never waits for a detection: only, three steps later, for the all-gather that read the ring slot it is
-            # about to refill.  Results are polled without blocking (the detector keeps at most 4 steps in flight).
-            i = lc_state["step"] % LC_RING
-            d, side = dets[i], sides[i]
-            if lc_state["step"] >= LC_RING:
+            # kernels that produced the descriptors) into a ring of send buffers; the all-gather runs on the communication stream;
+            # the detection (Hamming 2-NN of the live descriptors, ratio test, five-point RANSAC) on an idle detector's stream.  The
+            # main stream never waits for a detection: only, LC_RING steps later, for the all-gather that read the ring slot it is
+            # about to refill.  Results are polled without blocking.
+            st_ = lc_state["step"]
+            i = st_ % LC_RING
+            for d in dets:
+                lc_events.extend(d.poll())
+            idle = [j for j in range(ND) if dets[j].L.alva_lc_inflight(dets[j].h) == 0]
+            d = dets[idle[0]] if idle else dets[0]
+            if st_ >= LC_RING:
                 stream.wait_event(ev_gathered[i])
-            d.seq = lc_state["step"] * pipe.nprob          # keyframe sequence numbers run on across the detectors
+            d.seq = st_ * pipe.nprob          # keyframe sequence numbers run on across the detectors
             d.pack(desc_all, pts_all, cnt_all, kf_idx, send[i], on=ctx)
             ev_packed[i].record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(ev_packed[i])
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_packed[i])
+                if slot_examined[i]:
+                    comm.wait_event(ev_examined[i])   # the detection that read this slot LC_RING steps ago
+                    slot_examined[i] = False
                 dist.all_gather_into_tensor(gathered_buf[i], send[i])
-                ev_gathered[i].record(side)
-                d.detect(gathered_buf[i])
+                ev_gathered[i].record(comm)
+            if idle:
+                side = sides[idle[0]]
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_gathered[i])
+                    d.detect(gathered_buf[i])
+                    ev_examined[i].record(side)
+                slot_examined[i] = True
+                lc_state["examined"] += 1
+            else:
+                lc_state["skipped"] += 1
             lc_state["step"] += 1
-            lc_events.extend(d.poll())
             return gathered_buf[i]
 
     sampler = ClockSampler(local_rank)
@@ -444,8 +466,9 @@ def bench_b200(args, rank, world, local_rank):
                 lc()
         pipe.drain()
         if lc:
-            for sd in sides:
+            for sd in sides + [comm]:
                 stream.wait_stream(sd)
+            lc_state["examined"] = lc_state["skipped"] = 0
         barrier()
         l0 = ctx.launches
         sampler.start()
@@ -457,7 +480,7 @@ def bench_b200(args, rank, world, local_rank):
                 gathered = lc()
         pipe.drain()   # the last step's BA chain belongs to the timed region
         if lc:
-            for sd in sides:
+            for sd in sides + [comm]:
                 stream.wait_stream(sd)   # ... and so do the exchanges + detections still in flight
         ev1.record(stream)
         barrier()
@@ -526,11 +549,13 @@ def bench_b200(args, rank, world, local_rank):
             lc_events.extend(d.poll(wait=True))
         sc = det.last_scores()
         lc_report = {"keyframe_blocks_per_step": int(world * pipe.nprob), "block_bytes": int(block_bytes(pipe.fcap)),
+                     "steps_examined": lc_state["examined"], "steps_not_examined": lc_state["skipped"],
                      "events": len(lc_events), "remote_ranks_with_events": sorted({int(e["remote_rank"]) for e in lc_events}),
                      "last_step_pairs_checked": int((sc[:, :, 0] >= max(30, NFEAT // 10)).sum()),
                      "last_step_pairs_verified": int((sc[:, :, 1] == 1).sum()),
-                     "schedule": "pack on the main stream -> ring of 3 side streams, one detector each: ncclAllGather -> Hamming 2-NN (live "
-                                 "descriptors) -> ratio test -> 5-point RANSAC; polled; streams 2k and 2k+1 watch the same scene"}
+                     "schedule": "pack on the main stream -> ncclAllGather on a communication stream (every step) -> an idle detector (3, own "
+                                 "streams): Hamming 2-NN (live descriptors) -> ratio test -> 5-point RANSAC on the newest keyframe; polled; "
+                                 "streams 2k and 2k+1 watch the same scene"}
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -3,7 +3,7 @@
 set +e
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-python -m pytest tests/test_gpu_loopclosure.py -x -q 2>&1 | tail -3
+python -m pytest tests/test_gpu_loopclosure.py -x -q 2>&1 | grep -E "^E |assert|passed|failed" | head -20
 python tools/gpu_lc_bench.py 2>&1 | tail -2
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-stage-stats > gpurun_out/bench_r2_n1_samebox.json 2> gpurun_out/bench_r2_n1_samebox.err
 echo "== n1 rc=$?"
