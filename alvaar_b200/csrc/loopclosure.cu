@@ -130,19 +130,26 @@ __global__ void __launch_bounds__(256) lc_score_kernel(const uint8_t* __restrict
         // the geometric check is run for the NEWEST keyframe of the step only (0 -> it returns at once for this pair): one round of
         // the five-point RANSAC is ~2.8 ms of serial FP64 (Sturm / Newton root isolation: dependent Horner chains), longer than a
         // pipeline step, and the temporal rule already asks the earlier events of the streak for match counts only
-        npair[p] = (e == K - 1 && n >= min_matches) ? min(n, PAIR_CAP) : 0;
+        // "enough" is relative as well: unrelated scenes still leave ~6 % of the keypoints as chance matches after the ratio test
+        npair[p] = (e == K - 1 && n >= max(min_matches, nq / 8)) ? min(n, PAIR_CAP) : 0;
     }
 }
 
 // {matches, RANSAC success, inliers, remote keyframe sequence number} per pair, gathered for one small copy
-__global__ void lc_collect_kernel(const uint8_t* __restrict__ gathered, size_t block_bytes, int K, int world, const int32_t* __restrict__ nmatch,
-                                  const double* __restrict__ info, const double* __restrict__ Rt, double* __restrict__ out) {
+// verdict: 0 = too few matches (or the geometric check failed), 1 = geometric check passed, 2 = enough matches, not checked (not the
+// step's newest keyframe)
+__global__ void lc_collect_kernel(const uint8_t* __restrict__ gathered, size_t block_bytes, int K, int world, int rank, int n_max, int min_matches,
+                                  const int32_t* __restrict__ nmatch, const double* __restrict__ info, const double* __restrict__ Rt,
+                                  double* __restrict__ out) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= K * world) return;
     const int e = p / world, r = p - e * world;
     const int32_t* rh = reinterpret_cast<const int32_t*>(gathered + ((size_t)r * K + e) * block_bytes);
+    const int32_t* lh = reinterpret_cast<const int32_t*>(gathered + ((size_t)rank * K + e) * block_bytes);
+    const int nq = lh[0] == ALVA_LC_MAGIC ? min(lh[4], n_max) : 0;
+    const bool enough = r != rank && nmatch[p] >= max(min_matches, nq / 8);
     double* o = out + (size_t)p * 16;
-    o[0] = nmatch[p]; o[1] = info[4 * p]; o[2] = info[4 * p + 1]; o[3] = rh[3];
+    o[0] = nmatch[p]; o[1] = e == K - 1 ? info[4 * p] : (enough ? 2.0 : 0.0); o[2] = info[4 * p + 1]; o[3] = rh[3];
     for (int i = 0; i < 12; i++) o[4 + i] = Rt[12 * p + i];
 }
 
@@ -254,7 +261,8 @@ extern "C" int alva_lc_detect(alva_lc* lc, const uint8_t* gathered) { AlvaDevice
     if (int e = alva_k_essential_5pt(ctx, lc->npair, PAIR_CAP, lc->bvl, lc->bvr, lc->npairs, 32, c.err_px, 0, c.fx_hint > 0 ? c.fx_hint : 500.f,
                                      c.fy_hint > 0 ? c.fy_hint : 500.f, 12345u, lc->Rt, lc->outl, lc->info))
         return e;
-    lc_collect_kernel<<<(lc->npair + 127) / 128, 128, 0, ctx->stream>>>(gathered, lc->block_bytes, K, W, lc->nmatch, lc->info, lc->Rt, lc->res_dev);
+    lc_collect_kernel<<<(lc->npair + 127) / 128, 128, 0, ctx->stream>>>(gathered, lc->block_bytes, K, W, c.rank, c.n_max, c.min_matches, lc->nmatch,
+                                                                          lc->info, lc->Rt, lc->res_dev);
     ALVA_LAUNCH_CHECK(ctx);
     const int slot = lc->next_slot;
     ALVA_CUDA(cudaMemcpyAsync(lc->res_host[slot], lc->res_dev, (size_t)lc->npair * 128, cudaMemcpyDeviceToHost, ctx->stream));
@@ -286,9 +294,8 @@ extern "C" int alva_lc_poll(alva_lc* lc, alva_lc_event* out, int cap, int wait) 
                 const double* o = res + (size_t)(e * c.world + r) * 16;
                 // streak of keyframe events with enough ratio-tested matches; on the newest keyframe of a step the geometric check
                 // ran as well and must have passed -- a loop is reported there, once the streak is long enough
-                const bool enough = (int)o[0] >= c.min_matches;
                 const bool checked = e == c.kf_per_step - 1;
-                const bool pass = enough && (!checked || (o[1] != 0.0 && (int)o[2] >= c.min_inliers));
+                const bool pass = checked ? (o[1] == 1.0 && (int)o[2] >= c.min_inliers) : o[1] == 2.0;
                 lc->consecutive[r] = pass ? lc->consecutive[r] + 1 : 0;
                 if (pass && checked && lc->consecutive[r] >= c.min_consecutive) {
                     alva_lc_event ev{};

@@ -95,7 +95,8 @@ class LoopClosure:
                      consecutive=e.consecutive, Rt=np.array(list(e.Rt)).reshape(3, 4)) for e in ev[:n]]
 
     def last_scores(self):
-        """[K, world, 4]: putative matches, geometric check passed (0/1), inliers, remote keyframe sequence number"""
+        """[K, world, 4]: putative matches, verdict (0 too few matches / check failed, 1 geometric check passed, 2 enough matches but not
+        the step's newest keyframe: not checked), inliers, remote keyframe sequence number"""
         out = np.zeros((self.K, self.world, 4))
         self._chk(self.L.alva_lc_last_scores(self.h, out.ctypes.data_as(C.c_void_p)))
         return out

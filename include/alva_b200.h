@@ -429,7 +429,8 @@ int  alva_system_unpin_buffer(alva_system*, void* host_ptr);
 typedef struct alva_lc alva_lc;
 typedef struct {
     int32_t n_max, kf_per_step, world, rank;
-    int32_t min_matches;       /* putative matches a keyframe event needs to count / before the geometric check runs (default 30) */
+    int32_t min_matches;       /* putative matches a keyframe event needs to count / before the geometric check runs: at least this
+                                * (default 30) and at least 1/8 of the local keyframe's descriptors */
     int32_t max_dist;          /* absolute Hamming gate on the best match (default 64) */
     int32_t ratio_num, ratio_den;   /* ratio test: best * ratio_den < second * ratio_num (default 4 / 5) */
     int32_t min_consecutive;   /* keyframe events in a row that must have enough matches (default 3) */

@@ -77,7 +77,7 @@ def test_wire_format_and_planted_revisit(gpu_ctx):
     assert len(ev) >= 1 and all(e["remote_rank"] == 1 for e in ev)
     assert ev[0]["local_kf"] == 2 and ev[0]["consecutive"] == 3 and ev[0]["n_inliers"] >= 20
     for s in sc:
-        assert (s[:, 1, 0] >= 30).all() and s[-1, 1, 1] == 1 and (s[:-1, 1, 1] == 0).all()   # stream 1: many putative matches; RANSAC runs on the step's newest keyframe and succeeds
+        assert (s[:, 1, 0] >= 30).all() and s[-1, 1, 1] == 1 and (s[:-1, 1, 1] == 2).all()   # stream 1: many putative matches (verdict 2); RANSAC runs on the step's newest keyframe and succeeds (1)
         assert (4 * s[:, 2, 0] < s[:, 1, 0]).all() and (s[:, 2, 1] == 0).all()   # stream 2: a few chance matches (~6 % of the keypoints), no geometry
         assert (s[:, 0, :3] == 0).all()                                  # a stream is not matched against itself (field 3: the block's keyframe number)
     R = ev[0]["Rt"][:, :3]
