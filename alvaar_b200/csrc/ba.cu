@@ -402,7 +402,7 @@ __device__ __forceinline__ double lin_obs(const BaProblem& P, const BaDims& D, i
 }
 
 template <bool FULL>
-__global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+__global__ void __launch_bounds__(LIN_THREADS, 7) ba_linearize_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     __shared__ double red[LIN_THREADS];
     const BaState& st = *P.st;

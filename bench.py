@@ -55,8 +55,8 @@ def select_config(name):
     W, H, BATCH, NFEAT, WORKLOAD = c["w"], c["h"], c["batch"], c["nfeat"], c["name"]
     ALGO_BYTES_FRONTEND = 4 * W * H + W * H + ((W + 1) // 2) * ((H + 1) // 2)
 # dram__bytes_read.sum + dram__bytes_write.sum of one 64-frame front-end launch, from the committed `ncu --set full`
-# capture (profiles/r01f_frontend_full.txt: 236.11 MB + 58.62 MB).  Static by nature: a profiler cannot run inside bench.
-FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_733_312
+# capture (profiles/r02_frontend_v2_full.txt).  Static by nature: a profiler cannot run inside bench.
+FRONTEND_DRAM_TRAFFIC_BYTES_B64 = 294_047_488   # dram__bytes_read.sum 235.976 MB + dram__bytes_write.sum 58.072 MB
 
 
 # sha256[:16] of the step's integer outputs (selected-feature counts + 2-NN match lists of all 64 frames) for the stream seeds
@@ -602,10 +602,10 @@ def bench_b200(args, rank, world, local_rank):
             "output_sha": out_sha, "output_check": "matches the stored checksum" if want_sha else "no stored checksum for this stream seed",
             "host_numa_cpus": (f"{min(numa)}-{max(numa)} ({len(numa)} CPUs local to the GPU)" if numa else None),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "frontend_tile_kernel<RGBA> (gray + pyramid L1 + FAST-9/NMS, fused)", "bound": "hbm",
+            "roofline": {"kernel": "frontend_tile_kernel_v2<RGBA> (gray + pyramid L1 + FAST-9/NMS, fused)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": FRONTEND_DRAM_TRAFFIC_BYTES_B64 if (BATCH, W, H) == (64, 1280, 720) else None,
-                         "traffic_source": "ncu --set full, profiles/r01f_frontend_full.txt (bytes per launch)",
+                         "traffic_source": "ncu --set full of frontend_tile_kernel_v2, profiles/r02_frontend_v2_full.txt (bytes per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_FRONTEND * BATCH,
                          "launch_ms": fe_avg_ms,
                          "launch_ms_source": f"CUDA events around the launch in each of {len(fe)} steps of a second, kernel-by-kernel pass "
