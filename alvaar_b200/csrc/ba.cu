@@ -957,14 +957,15 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint64_t en, co
 #undef ACC
 }
 
-// One CTA (one warp) per upper-triangular 6x6 block (bi < bj) and GA_SPLIT CTAs per DIAGONAL block, whose lists are the long
+// One CTA (2 warps) per upper-triangular 6x6 block (bi < bj) and GA_SPLIT CTAs per DIAGONAL block, whose lists are the long
 // ones (every landmark the pose sees, ~600 entries against ~100): a part strides over the block's entry list, each thread
 // keeps a private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction.  Diagonal parts leave their
 // partial sums in a scratch slot; the part that arrives last (ticket) adds the GA_SPLIT slots in slot order.  The block and its
 // mirror are stored -- no floating-point atomics, bit-reproducible.
-constexpr int GA_THREADS = 32, GA_SPLIT = 16;   // one warp per part: 4 k registers per CTA, so 16 CTAs share an SM (and fit beside the frame kernels)
+constexpr int GA_THREADS = 64, GA_SPLIT = 8;   // (one warp per part was tried: the 42-entry combine below needs >= 42 threads)
 constexpr int GA_GRID = NBMAX * GA_SPLIT + (MAXKEYS - NBMAX);   // diagonal parts first, then the strictly upper blocks
-__global__ void __launch_bounds__(GA_THREADS, 16) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
+static_assert(GA_THREADS >= 42, "threads 0..41 combine the 36 + 6 entries of a block");
+__global__ void __launch_bounds__(GA_THREADS, 8) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
     if (st.done || !st.use_gather) return;
