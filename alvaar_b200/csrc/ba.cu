@@ -880,11 +880,14 @@ __device__ __forceinline__ void lm_landmark(const BaProblem& P, int l) {
     P.etb[l] = etb;
     for (int c = 0; c < 6; c++) P.wa[6 * l + c] = wa[c];
 }
+// ... or, for a problem whose structure the packed lists cannot express (use_gather == 0), the whole per-landmark Schur update with
+// FP64 atomics (one launch serves both paths: a problem takes exactly one of them)
 __global__ void __launch_bounds__(128) ba_lm_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
-    if (P.st->done || !P.st->use_gather) return;
+    if (P.st->done) return;
     const int l = blockIdx.x * 128 + threadIdx.x;
-    if (l < D.nlm) lm_landmark(P, l);
+    if (P.st->use_gather) { if (l < D.nlm) lm_landmark(P, l); }
+    else if (l < D.nlm) schur_landmark<false>(P, D, l);
 }
 
 // Contribution of one (landmark, slot_u, slot_v) entry to block (bi, bj):  C = F_u'F_v - w_u w_v' / (E'E + D^2)  and, for
@@ -1531,8 +1534,6 @@ static int ba_run_solve(alva_ctx* ctx, const BaProblem* dp, const BaDims& D, int
             ba_lm_kernel<<<schur_grid, 128, 0, ctx->stream>>>(dp, D);           // gather path (no-op if structure too large)
             ALVA_LAUNCH_CHECK(ctx);
             ba_gather_kernel<<<key_grid, GA_THREADS, 0, ctx->stream>>>(dp, D);
-            ALVA_LAUNCH_CHECK(ctx);
-            ba_schur_kernel<false><<<schur_grid, 128, 0, ctx->stream>>>(dp, D);  // atomic fallback (no-op when gather ran)
             ALVA_LAUNCH_CHECK(ctx);
         }
         ba_chol_kernel<<<nprob, CH_THREADS, chol_smem, ctx->stream>>>(dp, D);

@@ -1,10 +1,11 @@
 #!/usr/bin/env bash
-# round 2, last visit: gather with one warp per part -- BA / pipeline / system tests, then the bench lines again
+# round 2, last visit: the whole GPU suite on the final tree, smoke, the bench lines again
 set +e
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-SKIP_BENCH=1 SKIP_NCU=1 SKIP_AB=1 FILES="test_gpu_ba test_gpu_pipeline test_gpu_system" bash tools/gpu_check.sh 2>&1 | grep -E "passed|failed|rc=|Error|error|assert" | head -20
-python tools/gpu_ba_bench.py 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/test_gpu_all.log 2>&1
+echo "== pytest -m gpu rc=$?"; tail -4 gpurun_out/test_gpu_all.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
 timeout 500 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 echo "== bench rc=$?"; tail -3 gpurun_out/r02_bench.err
 timeout 300 python bench.py --config c3 --steps 10 --warmup 3 --no-stage-stats > gpurun_out/r02_bench_c3.json 2> gpurun_out/r02_bench_c3.err
