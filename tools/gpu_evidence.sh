@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, evidence visit: whole GPU suite, smoke, bench lines (c2 / c3 / reference arm), launch list, per-kernel ncu summaries
+# evidence visit (round 2): whole GPU suite, smoke, bench lines (c2 / c3 / reference arm), launch list, per-kernel ncu summaries
 set +e
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
