@@ -965,9 +965,8 @@ __device__ __forceinline__ void gather_entry(const BaProblem& P, uint64_t en, co
 // keeps a private 6x6 (+ rhs) accumulator, then a fixed-order shuffle + shared-memory reduction.  Diagonal parts leave their
 // partial sums in a scratch slot; the part that arrives last (ticket) adds the GA_SPLIT slots in slot order.  The block and its
 // mirror are stored -- no floating-point atomics, bit-reproducible.
-constexpr int GA_THREADS = 64, GA_SPLIT = 8;   // (one warp per part was tried: the 42-entry combine below needs >= 42 threads)
+constexpr int GA_THREADS = 64, GA_SPLIT = 8;   // (one warp per part x 16 parts measured the same: 0.91 vs 0.92 ms per batch)
 constexpr int GA_GRID = NBMAX * GA_SPLIT + (MAXKEYS - NBMAX);   // diagonal parts first, then the strictly upper blocks
-static_assert(GA_THREADS >= 42, "threads 0..41 combine the 36 + 6 entries of a block");
 __global__ void __launch_bounds__(GA_THREADS, 8) ba_gather_kernel(const BaProblem* __restrict__ probs, BaDims D) {
     const BaProblem P = probs[blockIdx.y];
     const BaState& st = *P.st;
@@ -1013,33 +1012,37 @@ __global__ void __launch_bounds__(GA_THREADS, 8) ba_gather_kernel(const BaProble
         if (lane == 0) red[warp][36 + i] = rh[i];
     }
     __syncthreads();
-    double v = 0;
-    if (tid < 42) {
-#pragma unroll
-        for (int wv = 0; wv < GA_THREADS / 32; wv++) v += red[wv][tid];
-    }
+    // the 36 + 6 entries of the block are finished by threads x = tid, tid + GA_THREADS, ... (any CTA size)
     if (nparts > 1) {
         double* slot = P.ga_part + ((size_t)bi * GA_SPLIT + part) * 42;
-        if (tid < 42) slot[tid] = v;
+        for (int x = tid; x < 42; x += GA_THREADS) {
+            double v = 0;
+#pragma unroll
+            for (int wv = 0; wv < GA_THREADS / 32; wv++) v += red[wv][x];
+            slot[x] = v;
+        }
         __threadfence();
         __syncthreads();
         if (tid == 0) last_s = atomicInc(reinterpret_cast<unsigned int*>(P.ga_ticket + bi), GA_SPLIT - 1) == GA_SPLIT - 1;   // wraps to 0
         __syncthreads();
         if (!last_s) return;
         __threadfence();
-        if (tid < 42) {
-            v = 0;
+    }
+    for (int x = tid; x < 42; x += GA_THREADS) {
+        double v = 0;
+        if (nparts > 1) {
             const volatile double* all = P.ga_part + (size_t)bi * GA_SPLIT * 42;
 #pragma unroll
-            for (int q = 0; q < GA_SPLIT; q++) v += all[q * 42 + tid];
+            for (int q = 0; q < GA_SPLIT; q++) v += all[q * 42 + x];
+        } else {
+#pragma unroll
+            for (int wv = 0; wv < GA_THREADS / 32; wv++) v += red[wv][x];
         }
-    }
-    if (tid < 42) {
-        if (tid < 36) {
-            const int a = tid / 6, c = tid % 6;
+        if (x < 36) {
+            const int a = x / 6, c = x % 6;
             if (bi == bj) P.S[(ci + a) * NMAX + ci + c] = v + (a == c ? P.Df[ci + a] * P.Df[ci + a] : 0.0);
             else { P.S[(ci + a) * NMAX + cj + c] = v; P.S[(cj + c) * NMAX + ci + a] = v; }
-        } else if (bi == bj) P.rhs[ci + tid - 36] = v;
+        } else if (bi == bj) P.rhs[ci + x - 36] = v;
     }
 }
 
