@@ -1,4 +1,4 @@
-"""CPU test: the committed bench lines (profiles/r01f_bench*.json, produced by `python bench.py` on a B200) carry every key the
+"""CPU test: the committed bench lines (profiles/r02_bench*.json, produced by `python bench.py` on B200s) carry every key the
 bench contract names, with consistent values -- a regression net for bench.py's output format."""
 import json
 import os
@@ -27,8 +27,10 @@ def check_common(d, cpu_baseline=True):
 
 
 def test_b200_line():
-    d = load("r01f_bench.json")
+    d = load("r02_bench.json")
     check_common(d)
+    assert d["output_check"] == "matches the stored checksum"                         # the step's integer outputs, hashed inside the run
+    assert d["config"]["workload"].startswith("c2_720p") and d["config"]["batch_frames_per_step"] == 64
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["data"] == "synthetic"
     assert abs(d["value"] - 64 * 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]          # 64 frames per step
     assert d["e2e"]["h2d_bytes_per_step"] == 64 * 1280 * 720 * 4 and d["e2e"]["d2h_bytes_per_step"] > 0
@@ -44,13 +46,26 @@ def test_b200_line():
 
 
 def test_reference_line():
-    d = load("r01f_bench_reference.json")
+    d = load("r02_bench_reference.json")
     check_common(d)
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    assert d["config"] == load("r02_bench.json")["config"]                            # same config dict as the repo arm
 
 
-def test_two_gpu_line():
-    d = load("r01f_bench_n2.json")
+def test_c3_line():
+    d = load("r02_bench_c3.json")
     check_common(d, cpu_baseline=False)
-    one = load("r01f_bench.json")
-    assert d["n_gpus"] == 2 and 1.6 * one["value"] < d["value"] < 2.05 * one["value"]   # whole-job aggregate, weak scaling
+    assert d["config"]["frame"] == "1920x1080 RGBA" and d["config"]["features_per_frame"] == 2000
+    assert abs(d["value"] - d["config"]["batch_frames_per_step"] * 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    assert d["roofline"]["frac"] > 0.2
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_multi_gpu_lines(n):
+    d = load(f"r02_bench_n{n}.json")
+    check_common(d, cpu_baseline=False)
+    one = load(f"r02_bench_n1_same_box_as_n{n}.json")
+    assert d["n_gpus"] == n and 0.9 * n * one["value"] < d["value"] < 1.02 * n * one["value"]   # whole-job aggregate, weak scaling
+    lc = d["loop_closure"]
+    assert lc["keyframe_blocks_per_step"] == 13 * n and lc["steps_examined"] >= 1 and lc["events"] >= 1
+    assert lc["remote_ranks_with_events"] == [1]                                     # streams 0 and 1 watch the same scene
