@@ -312,7 +312,7 @@ def workload_config(batch, world=1, loop_closure=False):
     return cfg
 
 
-BA_SCHEDULE = ["own high-priority stream, forked after the front end and joined at the end of the step"]
+BA_SCHEDULE = ["own high-priority stream, forked at the start of the step and joined at its end"]
 
 
 def _workload_config(batch):
